@@ -1,0 +1,296 @@
+// abi.cu -- the C ABI declared in include/exon_gpu.h: contexts, partition streams, the device arena that
+// holds fed bytes, and the glue that launches the kernels.  No compute happens on the host here: every
+// result comes from a CUDA kernel, and every entry point fails loudly without a usable sm_100 device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/exon_gpu.h"
+#include "internal.h"
+
+namespace exon {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? EXON_GPU_ERR_OOM : EXON_GPU_ERR_CUDA, "%s: %s", \
+                        #expr, cudaGetErrorString(_e));                                                  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------
+// Arena: device blocks that hold fed body bytes.  Blocks are recycled through the context so that a
+// steady-state query does no cudaMalloc.
+// ---------------------------------------------------------------------------------------------------
+int Ctx::get_block(size_t min_bytes, DevBlock *out) {
+    std::lock_guard<std::mutex> g(mu);
+    for (size_t i = 0; i < free_blocks.size(); ++i) {
+        if (free_blocks[i].cap >= min_bytes) {
+            *out = free_blocks[i];
+            free_blocks.erase(free_blocks.begin() + (long)i);
+            return EXON_GPU_OK;
+        }
+    }
+    size_t cap = std::max(min_bytes, kArenaBlock);
+    void *p = nullptr;
+    // +256: tail padding so that the 16-byte granule holding the last byte is always readable
+    CUDA_TRY(cudaMalloc(&p, cap + 256));
+    out->ptr = (uint8_t *)p;
+    out->cap = cap;
+    out->used = 0;
+    return EXON_GPU_OK;
+}
+
+void Ctx::put_block(DevBlock b) {
+    std::lock_guard<std::mutex> g(mu);
+    b.used = 0;
+    free_blocks.push_back(b);
+}
+
+static int ensure_device(Ctx *c) {
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(EXON_GPU_ERR_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
+    return EXON_GPU_OK;
+}
+
+}  // namespace exon
+
+using namespace exon;
+
+
+extern "C" {
+
+const char *exon_gpu_last_error(void) { return g_last_error.c_str(); }
+const char *exon_gpu_version(void) { return "exon_gpu 0.1.0 sm_100a"; }
+
+int exon_gpu_ctx_create(int device, void *cuda_stream, exon_gpu_ctx **out) {
+    if (!out) return fail(EXON_GPU_ERR_ARG, "exon_gpu_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(EXON_GPU_ERR_CUDA, "no CUDA device available (%s); exon_gpu has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(EXON_GPU_ERR_ARG, "device %d out of range [0, %d)", device, n);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(EXON_GPU_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    auto *c = new exon_gpu_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+        c->own_stream = false;
+    } else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            return fail(EXON_GPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_ctx_destroy(exon_gpu_ctx *c) {
+    if (!c) return EXON_GPU_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &b : c->free_blocks) cudaFree(b.ptr);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    nccl_teardown(c);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_ctx_launch_count(exon_gpu_ctx *c, int64_t *out) {
+    if (!c || !out) return fail(EXON_GPU_ERR_ARG, "launch_count: NULL argument");
+    *out = c->launches.load();
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_ctx_last_kernel_ms(exon_gpu_ctx *c, float *out) {
+    if (!c || !out) return fail(EXON_GPU_ERR_ARG, "last_kernel_ms: NULL argument");
+    if (int rc = ensure_device(c)) return rc;
+    if (!c->timed) return fail(EXON_GPU_ERR_STATE, "no fused-scan kernel has been launched on this context");
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    CUDA_TRY(cudaEventElapsedTime(out, c->ev0, c->ev1));
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_ctx_synchronize(exon_gpu_ctx *c) {
+    if (!c) return fail(EXON_GPU_ERR_ARG, "synchronize: ctx is NULL");
+    if (int rc = ensure_device(c)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_host_alloc(exon_gpu_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return fail(EXON_GPU_ERR_ARG, "host_alloc: NULL argument");
+    if (int rc = ensure_device(c)) return rc;
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return EXON_GPU_OK;
+}
+int exon_gpu_host_free(exon_gpu_ctx *c, void *p) {
+    if (!c) return fail(EXON_GPU_ERR_ARG, "host_free: ctx is NULL");
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return EXON_GPU_OK;
+}
+int exon_gpu_device_alloc(exon_gpu_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return fail(EXON_GPU_ERR_ARG, "device_alloc: NULL argument");
+    if (int rc = ensure_device(c)) return rc;
+    CUDA_TRY(cudaMalloc(out, (bytes ? bytes : 1) + 256));
+    return EXON_GPU_OK;
+}
+int exon_gpu_device_free(exon_gpu_ctx *c, void *p) {
+    if (!c) return fail(EXON_GPU_ERR_ARG, "device_free: ctx is NULL");
+    if (int rc = ensure_device(c)) return rc;
+    if (p) CUDA_TRY(cudaFree(p));
+    return EXON_GPU_OK;
+}
+int exon_gpu_memcpy_h2d(exon_gpu_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c || (!dst && bytes) || (!src && bytes)) return fail(EXON_GPU_ERR_ARG, "memcpy_h2d: NULL argument");
+    if (int rc = ensure_device(c)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return EXON_GPU_OK;
+}
+
+// ---- VCF partition stream ---------------------------------------------------------------------------
+
+int exon_gpu_vcf_open(exon_gpu_ctx *c, const exon_gpu_vcf_opts *o, exon_gpu_stream **out) {
+    if (!c || !out) return fail(EXON_GPU_ERR_ARG, "vcf_open: NULL argument");
+    *out = nullptr;
+    if (int rc = ensure_device(c)) return rc;
+    auto *s = new exon_gpu_stream();
+    s->ctx = c;
+    s->batch_rows = 8192;
+    if (o) {
+        if (o->batch_rows < 0 || o->n_projection < 0 || (o->n_projection > 0 && !o->projection)) {
+            delete s;
+            return fail(EXON_GPU_ERR_ARG, "vcf_open: bad batch_rows / projection");
+        }
+        if (o->batch_rows > 0) s->batch_rows = o->batch_rows;
+        for (int i = 0; i < o->n_projection; ++i) {
+            if (o->projection[i] < 0 || o->projection[i] > 8) {
+                delete s;
+                return fail(EXON_GPU_ERR_ARG, "vcf_open: projection index %d is not a VCF file-schema column",
+                            o->projection[i]);
+            }
+            if (o->projection[i] > 1) {
+                delete s;
+                return fail(EXON_GPU_ERR_UNSUPPORTED,
+                            "vcf_open: column %d is not built on the GPU yet (supported: 0 chrom, 1 pos)",
+                            o->projection[i]);
+            }
+            s->projection.push_back(o->projection[i]);
+        }
+        s->columns_on_device = o->columns_on_device != 0;
+        s->strict = o->strict != 0;
+        s->variant = o->kernel_variant;
+        if (o->pushdown) {
+            if (int rc = s->pushdown.assign(o->pushdown)) {
+                delete s;
+                return rc;
+            }
+            s->has_pushdown = true;
+        }
+    }
+    // device + pinned result slots: [0] count, [1] flags, [2] eager accumulator, [3] eager flags
+    cudaError_t e = cudaMalloc((void **)&s->d_res, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&s->h_res, 8 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_res, 0, 8 * sizeof(unsigned long long), c->stream);
+    if (e != cudaSuccess) {
+        if (s->d_res) cudaFree(s->d_res);
+        delete s;
+        return fail(EXON_GPU_ERR_CUDA, "vcf_open: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_vcf_close(exon_gpu_stream *s) {
+    if (!s) return EXON_GPU_OK;
+    Ctx *c = s->ctx;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    s->release_all();
+    if (s->d_res) cudaFree(s->d_res);
+    if (s->h_res) cudaFreeHost(s->h_res);
+    if (s->d_segs) cudaFree(s->d_segs);
+    delete s;
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_vcf_reset(exon_gpu_stream *s) {
+    if (!s) return fail(EXON_GPU_ERR_ARG, "vcf_reset: stream is NULL");
+    if (int rc = ensure_device(s->ctx)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    s->release_all();
+    CUDA_TRY(cudaMemsetAsync(s->d_res, 0, 8 * sizeof(unsigned long long), s->ctx->stream));
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_vcf_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last) {
+    if (!s || (!text && len)) return fail(EXON_GPU_ERR_ARG, "vcf_feed: NULL argument");
+    if (int rc = ensure_device(s->ctx)) return rc;
+    if (s->drained) return fail(EXON_GPU_ERR_STATE, "vcf_feed: the stream has already produced batches");
+    return is_device_ptr ? s->feed_device(text, len, is_last != 0) : s->feed_host(text, len, is_last != 0);
+}
+
+int exon_gpu_vcf_filter_count_async(exon_gpu_stream *s, const exon_gpu_region *region, int64_t *device_out) {
+    if (!s || !device_out) return fail(EXON_GPU_ERR_ARG, "vcf_filter_count_async: NULL argument");
+    if (int rc = ensure_device(s->ctx)) return rc;
+    return s->filter_count(region, device_out, nullptr);
+}
+
+int exon_gpu_vcf_filter_count(exon_gpu_stream *s, const exon_gpu_region *region, int64_t *out_count) {
+    if (!s || !out_count) return fail(EXON_GPU_ERR_ARG, "vcf_filter_count: NULL argument");
+    if (int rc = ensure_device(s->ctx)) return rc;
+    return s->filter_count(region, nullptr, out_count);
+}
+
+int exon_gpu_vcf_rows(exon_gpu_stream *s, int64_t *out_rows) {
+    if (!s || !out_rows) return fail(EXON_GPU_ERR_ARG, "vcf_rows: NULL argument");
+    if (int rc = ensure_device(s->ctx)) return rc;
+    return s->filter_count(nullptr, nullptr, out_rows);
+}
+
+int exon_gpu_vcf_body_bytes(exon_gpu_stream *s, int64_t *out_bytes) {
+    if (!s || !out_bytes) return fail(EXON_GPU_ERR_ARG, "vcf_body_bytes: NULL argument");
+    *out_bytes = s->body_bytes;
+    return EXON_GPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,255 @@
+// filter_agg.cu -- K3: columnar filter + partial aggregate over one Arrow record batch.
+//
+// Replaces DataFusion's FilterExec (arrow-ord `eq` Utf8-vs-scalar, `gt_eq` / `lt_eq` Int64, arrow-arith
+// `and_kleene`, arrow-select `filter_record_batch`) followed by AggregateExec(Partial) `count(*)`, `count(x)`,
+// `sum(x)`, `avg(x)` (datafusion-physical-plan / datafusion-functions-aggregate 44.0.0, third party; predicate
+// shape as in exon/exon-core/src/physical_plan/pos_interval_physical_expr.rs:79-98 and
+// region_physical_expr.rs:220-240).  Nothing is compacted: the selection mask lives in registers and feeds the
+// accumulators directly, so each column byte is read once and 24 bytes come back.
+//
+// Null semantics: a NULL operand makes a comparison NULL, `and_kleene` keeps NULL unless the other side is
+// false, and FilterExec drops rows whose predicate is NULL or false -- i.e. a row is selected iff every
+// operand is valid and every comparison true.  count(x) / sum(x) / avg(x) skip NULL x.
+#include <cstring>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace exon {
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? EXON_GPU_ERR_OOM : EXON_GPU_ERR_CUDA, "%s: %s", \
+                        #expr, cudaGetErrorString(_e));                                                  \
+    } while (0)
+
+namespace {
+
+enum ValueType { kValNone = 0, kValI64 = 1, kValF64 = 2, kValF32 = 3, kValI32 = 4 };
+
+struct FilterAggArgs {
+    int64_t n_rows;
+    // chrom: utf8
+    const uint8_t *chrom_valid;  // may be NULL
+    const int32_t *chrom_offsets;
+    const uint8_t *chrom_values;
+    int64_t chrom_off;  // logical offset of row 0
+    int32_t has_chrom;
+    int32_t lit_len;
+    uint8_t lit[kMaxChrom + 1];
+    // pos: int64
+    const uint8_t *pos_valid;
+    const int64_t *pos;
+    int64_t pos_off;
+    int32_t has_pos;
+    int64_t lo, hi;
+    // aggregated value
+    const uint8_t *val_valid;
+    const void *val;
+    int64_t val_off;
+    int32_t val_type;
+    int32_t agg_kind;
+    // out: [0] count (u64) [1] sum_i64 (as u64, two's complement) [2] sum_f64
+    unsigned long long *out;
+};
+
+__device__ __forceinline__ bool bit_set(const uint8_t *bits, int64_t i) {
+    return bits == nullptr || ((bits[i >> 3] >> (i & 7)) & 1);
+}
+
+constexpr int kFaThreads = 256;
+
+__global__ void __launch_bounds__(kFaThreads) filter_agg_kernel(const __grid_constant__ FilterAggArgs a) {
+    unsigned long long cnt = 0;
+    long long si = 0;
+    double sf = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * kFaThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kFaThreads + threadIdx.x; i < a.n_rows; i += stride) {
+        bool sel = true;
+        if (a.has_chrom) {
+            const int64_t r = i + a.chrom_off;
+            sel = bit_set(a.chrom_valid, r);
+            if (sel) {
+                const int32_t s = a.chrom_offsets[r], e = a.chrom_offsets[r + 1];
+                sel = (e - s) == a.lit_len;
+                for (int32_t j = 0; sel && j < a.lit_len; ++j) sel = a.chrom_values[s + j] == a.lit[j];
+            }
+        }
+        if (sel && a.has_pos) {
+            const int64_t r = i + a.pos_off;
+            sel = bit_set(a.pos_valid, r);
+            if (sel) {
+                const int64_t v = a.pos[r];
+                sel = (v >= a.lo) & (v <= a.hi);
+            }
+        }
+        if (!sel) continue;
+        if (a.agg_kind == EXON_GPU_AGG_COUNT_STAR) {
+            ++cnt;
+        } else {
+            const int64_t r = i + a.val_off;
+            if (!bit_set(a.val_valid, r)) continue;
+            ++cnt;
+            if (a.agg_kind != EXON_GPU_AGG_COUNT) {
+                if (a.val_type == kValI64) si += static_cast<const int64_t *>(a.val)[r];
+                else if (a.val_type == kValI32) si += static_cast<const int32_t *>(a.val)[r];
+                else if (a.val_type == kValF64) sf += static_cast<const double *>(a.val)[r];
+                else if (a.val_type == kValF32) sf += (double)static_cast<const float *>(a.val)[r];
+            }
+        }
+    }
+    // warp shuffle reduction, then one atomic per warp
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+        si += __shfl_xor_sync(0xFFFFFFFFu, si, d);
+        sf += __shfl_xor_sync(0xFFFFFFFFu, sf, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cnt) atomicAdd(a.out, cnt);
+        if (si) atomicAdd(a.out + 1, (unsigned long long)si);
+        if (sf != 0.0) atomicAdd(reinterpret_cast<double *>(a.out + 2), sf);
+    }
+}
+
+struct Staged {
+    const void *ptr = nullptr;
+};
+
+}  // namespace
+
+}  // namespace exon
+
+using namespace exon;
+
+extern "C" int exon_gpu_filter_agg(exon_gpu_ctx *c, const struct ArrowArray *batch, const struct ArrowSchema *schema,
+                                   int buffers_on_device, const exon_gpu_pred *pred, const exon_gpu_agg *agg,
+                                   exon_gpu_partial *out) {
+    if (!c || !batch || !schema || !agg || !out) return fail(EXON_GPU_ERR_ARG, "filter_agg: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!schema->format || strcmp(schema->format, "+s") != 0 || schema->n_children != batch->n_children)
+        return fail(EXON_GPU_ERR_ARG, "filter_agg: batch must be a struct array (\"+s\") matching its schema");
+    const int64_t n = batch->length;
+    const int nc = (int)batch->n_children;
+    auto child_ok = [&](int idx) { return idx >= 0 && idx < nc && batch->children[idx] && schema->children[idx]; };
+
+    FilterAggArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_rows = n;
+    a.agg_kind = agg->kind;
+    if (agg->kind < EXON_GPU_AGG_COUNT_STAR || agg->kind > EXON_GPU_AGG_AVG)
+        return fail(EXON_GPU_ERR_ARG, "filter_agg: unknown aggregate kind %d", agg->kind);
+
+    // plan the staging area: every buffer the kernel reads, 256-byte aligned
+    struct Piece { const void *src; size_t bytes; const void **dst; };
+    std::vector<Piece> pieces;
+    const void *p_chrom_valid = nullptr, *p_chrom_off = nullptr, *p_chrom_val = nullptr, *p_pos_valid = nullptr,
+               *p_pos = nullptr, *p_val_valid = nullptr, *p_val = nullptr;
+
+    if (pred && pred->chrom_col >= 0 && pred->region.has_chrom) {
+        if (!child_ok(pred->chrom_col)) return fail(EXON_GPU_ERR_ARG, "filter_agg: chrom_col out of range");
+        const ArrowArray *ch = batch->children[pred->chrom_col];
+        if (strcmp(schema->children[pred->chrom_col]->format, "u") != 0)
+            return fail(EXON_GPU_ERR_UNSUPPORTED, "filter_agg: chrom column must be utf8 (\"u\")");
+        if (ch->n_buffers != 3 || (n > 0 && (!ch->buffers[1] || (!ch->buffers[2] && false))))
+            return fail(EXON_GPU_ERR_ARG, "filter_agg: malformed utf8 array");
+        if (pred->region.chrom_len < 0 || pred->region.chrom_len > kMaxChrom || (!pred->region.chrom && pred->region.chrom_len))
+            return fail(EXON_GPU_ERR_ARG, "filter_agg: bad chrom literal");
+        a.has_chrom = 1;
+        a.lit_len = pred->region.chrom_len;
+        memcpy(a.lit, pred->region.chrom, (size_t)a.lit_len);
+        a.chrom_off = batch->offset + ch->offset;
+        const int64_t rows_end = a.chrom_off + n;
+        if (ch->buffers[0]) pieces.push_back({ch->buffers[0], (size_t)((rows_end + 7) / 8), &p_chrom_valid});
+        pieces.push_back({ch->buffers[1], sizeof(int32_t) * (size_t)(rows_end + 1), &p_chrom_off});
+        size_t vbytes = 0;
+        if (n > 0) {
+            if (buffers_on_device) {
+                int32_t last = 0;
+                CUDA_TRY(cudaMemcpyAsync(&last, (const int32_t *)ch->buffers[1] + rows_end, sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                vbytes = (size_t)last;
+            } else {
+                vbytes = (size_t)((const int32_t *)ch->buffers[1])[rows_end];
+            }
+        }
+        pieces.push_back({ch->buffers[2], vbytes, &p_chrom_val});
+    }
+    if (pred && pred->pos_col >= 0 && pred->region.has_interval) {
+        if (!child_ok(pred->pos_col)) return fail(EXON_GPU_ERR_ARG, "filter_agg: pos_col out of range");
+        const ArrowArray *ps = batch->children[pred->pos_col];
+        if (strcmp(schema->children[pred->pos_col]->format, "l") != 0)
+            return fail(EXON_GPU_ERR_UNSUPPORTED, "filter_agg: pos column must be int64 (\"l\")");
+        if (ps->n_buffers != 2) return fail(EXON_GPU_ERR_ARG, "filter_agg: malformed int64 array");
+        a.has_pos = 1;
+        a.lo = pred->region.lo;
+        a.hi = pred->region.hi;
+        a.pos_off = batch->offset + ps->offset;
+        const int64_t rows_end = a.pos_off + n;
+        if (ps->buffers[0]) pieces.push_back({ps->buffers[0], (size_t)((rows_end + 7) / 8), &p_pos_valid});
+        pieces.push_back({ps->buffers[1], sizeof(int64_t) * (size_t)rows_end, &p_pos});
+    }
+    if (agg->kind != EXON_GPU_AGG_COUNT_STAR) {
+        if (!child_ok(agg->value_col)) return fail(EXON_GPU_ERR_ARG, "filter_agg: value_col out of range");
+        const ArrowArray *v = batch->children[agg->value_col];
+        const char *f = schema->children[agg->value_col]->format;
+        size_t width = 0;
+        if (!strcmp(f, "l")) { a.val_type = kValI64; width = 8; }
+        else if (!strcmp(f, "g")) { a.val_type = kValF64; width = 8; }
+        else if (!strcmp(f, "f")) { a.val_type = kValF32; width = 4; }
+        else if (!strcmp(f, "i")) { a.val_type = kValI32; width = 4; }
+        else if (agg->kind == EXON_GPU_AGG_COUNT) { a.val_type = kValNone; }
+        else return fail(EXON_GPU_ERR_UNSUPPORTED, "filter_agg: cannot aggregate a column of format \"%s\"", f);
+        a.val_off = batch->offset + v->offset;
+        const int64_t rows_end = a.val_off + n;
+        if (v->n_buffers >= 1 && v->buffers[0]) pieces.push_back({v->buffers[0], (size_t)((rows_end + 7) / 8), &p_val_valid});
+        if (width) {
+            if (v->n_buffers != 2) return fail(EXON_GPU_ERR_ARG, "filter_agg: malformed primitive array");
+            pieces.push_back({v->buffers[1], width * (size_t)rows_end, &p_val});
+        }
+    }
+
+    size_t total = 64;  // result slots live at the front of the scratch area
+    std::vector<size_t> offs(pieces.size());
+    for (size_t i = 0; i < pieces.size(); ++i) {
+        offs[i] = total;
+        total += (pieces[i].bytes + 255) & ~(size_t)255;
+    }
+    if (int rc = c->ensure_scratch(buffers_on_device ? 64 : total, 64)) return rc;
+    uint8_t *scratch = (uint8_t *)c->scratch;
+    for (size_t i = 0; i < pieces.size(); ++i) {
+        if (buffers_on_device) {
+            *pieces[i].dst = pieces[i].src;
+        } else {
+            if (pieces[i].bytes)
+                CUDA_TRY(cudaMemcpyAsync(scratch + offs[i], pieces[i].src, pieces[i].bytes, cudaMemcpyHostToDevice, c->stream));
+            *pieces[i].dst = scratch + offs[i];
+        }
+    }
+    a.chrom_valid = (const uint8_t *)p_chrom_valid;
+    a.chrom_offsets = (const int32_t *)p_chrom_off;
+    a.chrom_values = (const uint8_t *)p_chrom_val;
+    a.pos_valid = (const uint8_t *)p_pos_valid;
+    a.pos = (const int64_t *)p_pos;
+    a.val_valid = (const uint8_t *)p_val_valid;
+    a.val = p_val;
+    a.out = (unsigned long long *)scratch;
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, 64, c->stream));
+    if (n > 0) {
+        int grid = (int)std::min<int64_t>((n + kFaThreads - 1) / kFaThreads, (int64_t)c->sm_count * 8);
+        filter_agg_kernel<<<grid, kFaThreads, 0, c->stream>>>(a);
+        c->launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_scratch, scratch, 24, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const unsigned long long *r = (const unsigned long long *)c->h_scratch;
+    out->count = (int64_t)r[0];
+    out->sum_i64 = (int64_t)r[1];
+    memcpy(&out->sum_f64, &r[2], sizeof(double));
+    if (a.val_type == kValI64 || a.val_type == kValI32) out->sum_f64 = (double)out->sum_i64;
+    return EXON_GPU_OK;
+}

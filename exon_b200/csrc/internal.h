@@ -1,0 +1,123 @@
+// internal.h -- library-internal state behind the opaque handles of include/exon_gpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/exon_gpu.h"
+#include "vcf_scan.cuh"
+
+namespace exon {
+
+int fail(int code, const char *fmt, ...);
+
+constexpr size_t kArenaBlock = (size_t)256 << 20;  // arena granularity (HBM is 180 GB; blocks are recycled)
+
+struct DevBlock {
+    uint8_t *ptr = nullptr;
+    size_t cap = 0, used = 0;
+};
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::atomic<int64_t> launches{0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the most recent fused-scan launch
+    bool timed = false;
+    std::mutex mu;
+    std::vector<DevBlock> free_blocks;
+    // scratch for filter_agg / allreduce
+    void *scratch = nullptr;
+    size_t scratch_cap = 0;
+    void *h_scratch = nullptr;
+    size_t h_scratch_cap = 0;
+    // NCCL (dlopen'ed lazily; see nccl.cu)
+    void *nccl_comm = nullptr;
+    int nccl_ranks = 0;
+
+    int get_block(size_t min_bytes, DevBlock *out);
+    void put_block(DevBlock b);
+    int ensure_scratch(size_t dev_bytes, size_t host_bytes);
+};
+
+void nccl_teardown(Ctx *c);
+
+// A region whose chrom bytes are owned (the caller's exon_gpu_region may go away).
+struct OwnedRegion {
+    std::string chrom;
+    bool has_chrom = false, has_interval = false;
+    int64_t lo = 1, hi = INT64_MAX;
+    int assign(const exon_gpu_region *r);
+};
+
+// One resident run of body bytes.
+struct Run {
+    const uint8_t *base;  // first valid byte (any alignment)
+    int64_t len;
+    bool ends_with_newline;
+};
+
+struct VcfStream {
+    Ctx *ctx = nullptr;
+    int batch_rows = 8192;
+    std::vector<int> projection;
+    bool columns_on_device = false, strict = false, has_pushdown = false, drained = false;
+    int variant = 0;
+    OwnedRegion pushdown;
+
+    // ---- file framing state (what read_header + the line reader keep between feeds) ----
+    enum HdrState { kAtLineStart, kInHeaderLine, kBody };
+    HdrState hdr = kAtLineStart;
+    bool file_open = false;       // a file has received bytes and no is_last yet
+    bool last_byte_newline = true;  // last body byte appended so far was '\n' (or nothing appended yet)
+
+    // ---- arena ----
+    std::vector<DevBlock> blocks;   // owned blocks, in fill order
+    std::vector<Run> runs;          // resident body bytes in scan order (arena runs and zero-copy device ranges)
+    bool cur_run_open = false;      // runs.back() lives at the tail of blocks.back() and may still grow
+    int64_t tail_len = 0;           // bytes after the last '\n' of the open arena run (a partial line)
+    int64_t body_bytes = 0;
+
+    // ---- eager (pushdown) scan bookkeeping ----
+    int64_t eager_scanned = 0;      // bytes of the open run already covered by eager launches
+    size_t eager_runs_done = 0;     // runs [0, eager_runs_done) fully covered
+
+    // ---- device-side tables / results ----
+    ScanSeg *d_segs = nullptr;
+    size_t d_segs_cap = 0;
+    std::vector<ScanSeg> h_segs;
+    bool segs_dirty = true;
+    int seg_variant = -1;
+    int64_t n_tiles = 0;
+    unsigned long long *d_res = nullptr;  // [0] count [1] flags [2] eager count [3] eager flags
+    unsigned long long *h_res = nullptr;  // pinned mirror
+
+    // ---- column build (K2) state lives in vcf_columns.cu ----
+    struct Columns *cols = nullptr;
+
+    int feed_host(const uint8_t *text, size_t len, bool is_last);
+    int feed_device(const uint8_t *text, size_t len, bool is_last);
+    int append_host(const uint8_t *p, size_t n);
+    int end_file();
+    int filter_count(const exon_gpu_region *region, int64_t *device_out, int64_t *host_out);
+    int launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_segs, int64_t tiles, unsigned long long *d_count,
+                    unsigned long long *d_flags, bool timed);
+    int build_seg_table();
+    int eager_scan(bool final_flush);
+    void release_all();
+};
+
+// defined in vcf_columns.cu
+void columns_free(VcfStream *s);
+int columns_next_batch(VcfStream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
+
+}  // namespace exon
+
+struct exon_gpu_ctx : public exon::Ctx {};
+struct exon_gpu_stream : public exon::VcfStream {};

@@ -1,0 +1,254 @@
+"""Thin object layer over the C ABI: contexts, pinned buffers, partition streams, Arrow batch import.
+
+These classes add no logic of their own -- each method is one exon_gpu_* call (plus buffer bookkeeping), so
+the tests that go through them are tests of the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import ExonGpuError, check  # noqa: F401
+
+
+class PinnedBuffer:
+    """Page-locked host memory from exon_gpu_host_alloc, exposed as a numpy uint8 array."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self._ctx = ctx
+        self._ptr = C.c_void_p()
+        check(ctx.lib.exon_gpu_host_alloc(ctx.handle, max(int(nbytes), 1), C.byref(self._ptr)))
+        self.nbytes = int(nbytes)
+        self.array = np.ctypeslib.as_array(C.cast(self._ptr, C.POINTER(C.c_uint8)), (max(self.nbytes, 1),))[: self.nbytes]
+
+    @property
+    def ptr(self) -> int:
+        return self._ptr.value
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            check(self._ctx.lib.exon_gpu_host_free(self._ctx.handle, self._ptr))
+            self._ptr = C.c_void_p()
+
+
+class DeviceBuffer:
+    def __init__(self, ctx: "Context", nbytes: int):
+        self._ctx = ctx
+        self._ptr = C.c_void_p()
+        check(ctx.lib.exon_gpu_device_alloc(ctx.handle, max(int(nbytes), 1), C.byref(self._ptr)))
+        self.nbytes = int(nbytes)
+
+    @property
+    def ptr(self) -> int:
+        return self._ptr.value
+
+    def upload(self, host: np.ndarray, offset: int = 0):
+        assert host.dtype == np.uint8 and host.flags.c_contiguous and offset + host.size <= self.nbytes
+        check(self._ctx.lib.exon_gpu_memcpy_h2d(self._ctx.handle, self.ptr + offset, host.ctypes.data, host.size))
+
+    def free(self):
+        if self._ptr:
+            check(self._ctx.lib.exon_gpu_device_free(self._ctx.handle, self._ptr))
+            self._ptr = C.c_void_p()
+
+
+class Context:
+    """exon_gpu_ctx: one per (process, device)."""
+
+    def __init__(self, device: int = 0, cuda_stream: int | None = None):
+        self.lib = _abi.load()
+        self.handle = C.c_void_p()
+        check(self.lib.exon_gpu_ctx_create(int(device), C.c_void_p(cuda_stream) if cuda_stream else None,
+                                           C.byref(self.handle)))
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.lib.exon_gpu_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        check(self.lib.exon_gpu_ctx_launch_count(self.handle, C.byref(v)))
+        return v.value
+
+    def last_kernel_ms(self) -> float:
+        v = C.c_float()
+        check(self.lib.exon_gpu_ctx_last_kernel_ms(self.handle, C.byref(v)))
+        return v.value
+
+    def synchronize(self):
+        check(self.lib.exon_gpu_ctx_synchronize(self.handle))
+
+    def pinned(self, nbytes: int) -> PinnedBuffer:
+        return PinnedBuffer(self, nbytes)
+
+    def device_buffer(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def open_vcf(self, **kw) -> "VcfStream":
+        return VcfStream(self, **kw)
+
+    # ---- multi-GPU final aggregate ----
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(_abi.NCCL_ID_BYTES)
+        check(self.lib.exon_gpu_nccl_unique_id(buf))
+        return buf.raw
+
+    def nccl_init(self, unique_id: bytes, n_ranks: int, rank: int):
+        check(self.lib.exon_gpu_nccl_init(self.handle, unique_id, n_ranks, rank))
+
+    def allreduce_partial(self, count: int = 0, sum_i64: int = 0, sum_f64: float = 0.0):
+        p = _abi.Partial(count, sum_i64, sum_f64)
+        check(self.lib.exon_gpu_allreduce_partial(self.handle, C.byref(p)))
+        return p.count, p.sum_i64, p.sum_f64
+
+    # ---- K3 ----
+    def filter_agg(self, arrow_array: "_abi.ArrowArray", arrow_schema: "_abi.ArrowSchema", *, on_device: bool,
+                   chrom_col: int = -1, pos_col: int = -1, region: "_abi.Region | None" = None,
+                   kind: int = _abi.AGG_COUNT_STAR, value_col: int = -1):
+        pred = _abi.Pred(chrom_col, pos_col, region if region is not None else _abi.Region())
+        agg = _abi.Agg(kind, value_col)
+        out = _abi.Partial()
+        check(self.lib.exon_gpu_filter_agg(self.handle, C.byref(arrow_array), C.byref(arrow_schema), int(on_device),
+                                           C.byref(pred), C.byref(agg), C.byref(out)))
+        return out.count, out.sum_i64, out.sum_f64
+
+
+class VcfBatch:
+    """One record batch from exon_gpu_vcf_next_batch, imported into numpy (host columns only)."""
+
+    def __init__(self, arr: _abi.ArrowArray, schema: _abi.ArrowSchema, on_device: bool):
+        self._arr, self._schema = arr, schema
+        self.on_device = on_device
+        self.num_rows = int(arr.length)
+        self.names = [schema.children[i].contents.name.decode() for i in range(schema.n_children)]
+        self.formats = [schema.children[i].contents.format.decode() for i in range(schema.n_children)]
+
+    def buffer_ptrs(self, name: str):
+        ch = self._arr.children[self.names.index(name)].contents
+        return [ch.buffers[i] for i in range(ch.n_buffers)]
+
+    def column(self, name: str):
+        """chrom -> (offsets int32[rows+1], values uint8[...]); pos -> int64[rows]  (copies)."""
+        assert not self.on_device, "device-resident batch: read it with a CUDA consumer"
+        i = self.names.index(name)
+        ch = self._arr.children[i].contents
+        n = self.num_rows
+        if self.formats[i] == "u":
+            off = np.ctypeslib.as_array(C.cast(ch.buffers[1], C.POINTER(C.c_int32)), (n + 1,)).copy()
+            nv = int(off[-1])
+            val = (np.ctypeslib.as_array(C.cast(ch.buffers[2], C.POINTER(C.c_uint8)), (max(nv, 1),))[:nv].copy()
+                   if nv else np.zeros(0, np.uint8))
+            return off, val
+        if self.formats[i] == "l":
+            return np.ctypeslib.as_array(C.cast(ch.buffers[1], C.POINTER(C.c_int64)), (max(n, 1),))[:n].copy()
+        raise NotImplementedError(self.formats[i])
+
+    def chrom_strings(self):
+        off, val = self.column("chrom")
+        b = val.tobytes()
+        return [b[off[i]:off[i + 1]].decode() for i in range(self.num_rows)]
+
+    def release(self):
+        if self._arr is not None and self._arr.release:
+            self._arr.release(C.byref(self._arr))
+        if self._schema is not None and self._schema.release:
+            self._schema.release(C.byref(self._schema))
+        self._arr = self._schema = None
+
+    @property
+    def c_array(self):
+        return self._arr
+
+    @property
+    def c_schema(self):
+        return self._schema
+
+
+class VcfStream:
+    """exon_gpu_stream: one DataFusion partition stream over a group of VCF files."""
+
+    def __init__(self, ctx: Context, *, batch_rows: int = 8192, projection=(0, 1), columns_on_device: bool = False,
+                 pushdown: "_abi.Region | None" = None, strict: bool = False, kernel_variant: int = 0):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self._proj = (C.c_int32 * len(projection))(*projection)
+        self._pushdown = pushdown
+        opts = _abi.VcfOpts(batch_rows, len(projection), self._proj, int(columns_on_device),
+                            C.pointer(pushdown) if pushdown is not None else None, int(strict), kernel_variant)
+        self.handle = C.c_void_p()
+        check(self.lib.exon_gpu_vcf_open(ctx.handle, C.byref(opts), C.byref(self.handle)))
+        self.columns_on_device = columns_on_device
+
+    def close(self):
+        if self.handle:
+            self.lib.exon_gpu_vcf_close(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self):
+        check(self.lib.exon_gpu_vcf_reset(self.handle))
+
+    def feed(self, data, *, is_last: bool = True, device_ptr: int | None = None, nbytes: int | None = None):
+        """Feed host bytes (bytes / numpy uint8 / PinnedBuffer) or a raw device range (device_ptr, nbytes)."""
+        if device_ptr is not None:
+            check(self.lib.exon_gpu_vcf_feed(self.handle, C.c_void_p(device_ptr), int(nbytes), 1, int(is_last)))
+            return
+        if isinstance(data, PinnedBuffer):
+            data = data.array
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        self._last_host = data  # keep alive until the next synchronising call
+        check(self.lib.exon_gpu_vcf_feed(self.handle, C.c_void_p(data.ctypes.data), data.size, 0, int(is_last)))
+
+    def filter_count(self, region: "_abi.Region | None" = None) -> int:
+        out = C.c_int64()
+        check(self.lib.exon_gpu_vcf_filter_count(self.handle, C.byref(region) if region is not None else None,
+                                                 C.byref(out)))
+        return out.value
+
+    def filter_count_async(self, region, device_out_ptr: int):
+        check(self.lib.exon_gpu_vcf_filter_count_async(self.handle, C.byref(region) if region is not None else None,
+                                                       C.c_void_p(device_out_ptr)))
+
+    def rows(self) -> int:
+        out = C.c_int64()
+        check(self.lib.exon_gpu_vcf_rows(self.handle, C.byref(out)))
+        return out.value
+
+    def body_bytes(self) -> int:
+        out = C.c_int64()
+        check(self.lib.exon_gpu_vcf_body_bytes(self.handle, C.byref(out)))
+        return out.value
+
+    def next_batch(self) -> VcfBatch | None:
+        arr, sch = _abi.ArrowArray(), _abi.ArrowSchema()
+        check(self.lib.exon_gpu_vcf_next_batch(self.handle, C.byref(arr), C.byref(sch)))
+        if not arr.release:
+            if sch.release:
+                sch.release(C.byref(sch))
+            return None
+        return VcfBatch(arr, sch, self.columns_on_device)
+
+    def batches(self):
+        while True:
+            b = self.next_batch()
+            if b is None:
+                return
+            yield b

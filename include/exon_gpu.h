@@ -1,0 +1,215 @@
+/*
+ * exon_gpu.h -- C ABI of the B200-native scan -> filter -> aggregate path for Exon.
+ *
+ * This is the drop-in boundary.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference repo root, wheretrue/exon v0.32.4).  The Rust side binds these
+ * with bindgen (INTEGRATION.md shows the stub); in this repository the same symbols are bound with ctypes by
+ * exon_b200/_abi.py, and the host-side mirror of the reference operators lives in exon_b200/host/.
+ *
+ * Conventions
+ *   - every function returns an int status (EXON_GPU_OK == 0); on failure a thread-local message is readable
+ *     through exon_gpu_last_error() -- the same contract as ArrowArrayStream.get_last_error, which is the
+ *     reference's own FFI convention (exon/exon-core/src/ffi/mod.rs:58-73);
+ *   - handles are opaque; ONE exon_gpu_stream per DataFusion partition stream, one CUDA stream per handle;
+ *     calls are thread-safe across handles and not re-entrant on one handle (the threading contract of
+ *     ExecutionPlan::execute, exon/exon-core/src/datasources/vcf/scanner.rs:142-162);
+ *   - columns cross the boundary as Arrow C Data Interface structs whose buffers stay owned by the library
+ *     until the consumer calls release();
+ *   - there is NO CPU fallback: every compute entry point fails with EXON_GPU_ERR_CUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef EXON_GPU_H
+#define EXON_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ---------------- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+    const char *format;
+    const char *name;
+    const char *metadata;
+    int64_t flags;
+    int64_t n_children;
+    struct ArrowSchema **children;
+    struct ArrowSchema *dictionary;
+    void (*release)(struct ArrowSchema *);
+    void *private_data;
+};
+struct ArrowArray {
+    int64_t length;
+    int64_t null_count;
+    int64_t offset;
+    int64_t n_buffers;
+    int64_t n_children;
+    const void **buffers;
+    struct ArrowArray **children;
+    struct ArrowArray *dictionary;
+    void (*release)(struct ArrowArray *);
+    void *private_data;
+};
+#endif
+
+/* ---- status codes ---------------------------------------------------------------------------------- */
+enum {
+    EXON_GPU_OK = 0,
+    EXON_GPU_ERR_ARG = 1,         /* bad argument / NULL pointer */
+    EXON_GPU_ERR_CUDA = 2,        /* CUDA runtime failure, or no sm_100 device */
+    EXON_GPU_ERR_PARSE = 3,       /* malformed record (the reference surfaces these as ArrowError::ExternalError) */
+    EXON_GPU_ERR_STATE = 4,       /* call sequence violated (e.g. feed after the stream was drained) */
+    EXON_GPU_ERR_OOM = 5,
+    EXON_GPU_ERR_UNSUPPORTED = 6, /* valid request outside what this build implements */
+    EXON_GPU_ERR_NCCL = 7
+};
+
+typedef struct exon_gpu_ctx exon_gpu_ctx;
+typedef struct exon_gpu_stream exon_gpu_stream;
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *exon_gpu_last_error(void);
+/* "exon_gpu <semver> sm_100a" */
+const char *exon_gpu_version(void);
+
+/* ---- context --------------------------------------------------------------------------------------- */
+/* One context per (process, device).  `cuda_stream` may carry a caller-owned cudaStream_t / CUstream on which
+ * every kernel and copy of streams opened from this context is enqueued (so the caller can bracket work with
+ * its own events); NULL lets the library create a private non-blocking stream. */
+int exon_gpu_ctx_create(int device, void *cuda_stream, exon_gpu_ctx **out);
+int exon_gpu_ctx_destroy(exon_gpu_ctx *ctx);
+/* Kernels launched by this library through `ctx` since creation (bench.py's `gpu_launches`). */
+int exon_gpu_ctx_launch_count(exon_gpu_ctx *ctx, int64_t *out);
+/* Device time of the most recent fused-scan kernel launch, measured with CUDA events on the launching stream. */
+int exon_gpu_ctx_last_kernel_ms(exon_gpu_ctx *ctx, float *out);
+int exon_gpu_ctx_synchronize(exon_gpu_ctx *ctx);
+
+/* Pinned host / device buffers for callers that want zero-staging feeds. */
+int exon_gpu_host_alloc(exon_gpu_ctx *ctx, size_t bytes, void **out);
+int exon_gpu_host_free(exon_gpu_ctx *ctx, void *p);
+int exon_gpu_device_alloc(exon_gpu_ctx *ctx, size_t bytes, void **out);
+int exon_gpu_device_free(exon_gpu_ctx *ctx, void *p);
+int exon_gpu_memcpy_h2d(exon_gpu_ctx *ctx, void *dst_device, const void *src_host, size_t bytes);
+
+/* ---- region predicate (a10/a11) --------------------------------------------------------------------- */
+/* `chrom = <name> AND pos BETWEEN lo AND hi` -- 1-based, both ends inclusive
+ * (exon/exon-core/src/physical_plan/pos_interval_physical_expr.rs:79-98, region_physical_expr.rs:220-240,
+ * exon/exon-core/src/udfs/vcf/mod.rs:65-131).  has_chrom == 0 drops the name test (interval_match, :232-274);
+ * has_interval == 0 drops the position test (chrom_match, :167-196). */
+typedef struct {
+    const char *chrom;
+    int32_t chrom_len;
+    int32_t has_chrom;
+    int32_t has_interval;
+    int64_t lo; /* >= 1 */
+    int64_t hi; /* INT64_MAX = open end */
+} exon_gpu_region;
+
+/* Parses "name", "name:start", "name:start-end" the way noodles-core Region::from_str does at its reference
+ * call sites (exon/exon-core/src/physical_plan/infer_region.rs:25-42, udfs/vcf/mod.rs:85-95).
+ * `name_buf` (>= 256 bytes) receives the contig name and out->chrom points into it. */
+int exon_gpu_region_parse(const char *s, char *name_buf, size_t name_buf_len, exon_gpu_region *out);
+/* Interval literal of interval_match ("a-b", "a", "a-", "-b"; udfs/vcf/mod.rs:246-252): has_chrom = 0. */
+int exon_gpu_interval_parse(const char *s, exon_gpu_region *out);
+
+/* ---- file -> partition assignment (a3) ---------------------------------------------------------------- */
+/* ExonFileScanConfig::regroup_files_by_size (exon/exon-core/src/datasources/exon_file_scan_config.rs:79-110):
+ * stable sort by size ascending, partitions = min(target, n_files), file i of the sorted order -> i % partitions.
+ * out_partition[i] is the partition of INPUT file i; *out_n_partitions the number of non-empty partitions. */
+int exon_gpu_regroup_files_by_size(const int64_t *sizes, int32_t n_files, int32_t target_partitions,
+                                   int32_t *out_partition, int32_t *out_n_partitions);
+
+/* ---- VCF partition stream (a4-a9) --------------------------------------------------------------------- */
+typedef struct {
+    int32_t batch_rows;        /* session batch size; reference default 8192 (exon/exon-common/src/lib.rs:27) */
+    int32_t n_projection;      /* file-schema column indices to materialise, in output order ... */
+    const int32_t *projection; /* ... VCFConfig.projection (exon/exon-vcf/src/config.rs:23-64); cols 0 (chrom), 1 (pos) */
+    int32_t columns_on_device; /* 0: next_batch buffers are pinned host memory; 1: device memory */
+    /* Optional predicate declared up front so that every feed() can be scanned while the next one is still
+     * copying (fused a5-a9).  NULL = none declared; filter_count() then scans what is resident. */
+    const exon_gpu_region *pushdown;
+    int32_t strict;            /* 1: validate POS of every row like the reference does; 0: only rows the predicate reads */
+    int32_t kernel_variant;    /* 0 = default (TMA-staged); other values select experimental kernels */
+} exon_gpu_vcf_opts;
+
+/* VCFScan::execute + VCFOpener::open (exon/exon-core/src/datasources/vcf/scanner.rs:142-162,
+ * vcf/file_opener/unindex_file_opener.rs:48-92): opens one partition stream. */
+int exon_gpu_vcf_open(exon_gpu_ctx *ctx, const exon_gpu_vcf_opts *opts, exon_gpu_stream **out);
+int exon_gpu_vcf_close(exon_gpu_stream *s);
+/* Forget everything fed so far but keep the device arena for the next query on this partition. */
+int exon_gpu_vcf_reset(exon_gpu_stream *s);
+
+/* Bytes in.  Consecutive calls deliver consecutive byte ranges of ONE file (uncompressed VCF text, header
+ * included -- the library skips it like `read_header`, unindex_file_opener.rs:74-88); is_last != 0 ends the
+ * file, and the next feed() starts the next file of the partition's file group (what FileStream does).
+ * is_device_ptr != 0: `text` is device memory, 16-byte aligned, used in place (zero copy) and must stay
+ * valid until the stream is closed; a non-final device range must end on a line boundary. */
+int exon_gpu_vcf_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last);
+
+/* Columns out: AsyncBatchStream::read_batch + LazyVCFArrayBuilder::{append,finish} +
+ * ExonArrayBuilder::try_into_record_batch (exon/exon-vcf/src/async_batch_stream.rs:80-109,
+ * exon/exon-vcf/src/array_builder/lazy_array_builder.rs:153-484, exon/exon-common/src/array_builder.rs:25-36).
+ * Fills a struct array (format "+s") of <= batch_rows rows whose children are the projected columns in
+ * projection order: chrom = utf8 ("u": validity NULL, int32 offsets starting at 0, bytes), pos = int64 ("l").
+ * End of stream: returns EXON_GPU_OK with out->release == NULL (ArrowArrayStream.get_next convention). */
+int exon_gpu_vcf_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
+
+/* Fused a5-a9: the count FilterExec + AggregateExec(Partial) would produce for this partition.
+ * region == NULL counts every record (COUNT(*) with an empty projection).
+ * Synchronises the stream and returns the count on the host. */
+int exon_gpu_vcf_filter_count(exon_gpu_stream *s, const exon_gpu_region *region, int64_t *out_count);
+/* Same, but leaves the int64 partial in caller-provided DEVICE memory and does not synchronise (used when the
+ * partial feeds an all-reduce on the same CUDA stream). */
+int exon_gpu_vcf_filter_count_async(exon_gpu_stream *s, const exon_gpu_region *region, int64_t *device_out);
+/* Records (lines after the header) fed so far. */
+int exon_gpu_vcf_rows(exon_gpu_stream *s, int64_t *out_rows);
+/* Body bytes (text minus headers) resident for this stream: the algorithmic bytes of the fused scan. */
+int exon_gpu_vcf_body_bytes(exon_gpu_stream *s, int64_t *out_bytes);
+
+/* ---- columnar filter + aggregate over Arrow buffers (a8-a9) ---------------------------------------------- */
+enum { EXON_GPU_AGG_COUNT_STAR = 0, EXON_GPU_AGG_COUNT = 1, EXON_GPU_AGG_SUM = 2, EXON_GPU_AGG_AVG = 3 };
+
+typedef struct {
+    int32_t chrom_col;  /* child index of the utf8 column compared with region.chrom, -1 = none */
+    int32_t pos_col;    /* child index of the int64 column compared with [lo, hi], -1 = none */
+    exon_gpu_region region;
+} exon_gpu_pred;
+
+typedef struct {
+    int32_t kind;       /* EXON_GPU_AGG_* */
+    int32_t value_col;  /* child index of the aggregated column (int64 "l", float32 "f" or float64 "g"); -1 for COUNT(*) */
+} exon_gpu_agg;
+
+/* AggregateExec(Partial) state: COUNT -> count; SUM -> sum_*; AVG -> (sum, count) (datafusion-functions-aggregate 44). */
+typedef struct {
+    int64_t count;
+    int64_t sum_i64;
+    double sum_f64;
+} exon_gpu_partial;
+
+/* FilterExec (arrow eq / gt_eq / lt_eq / and_kleene: a NULL operand makes the row unselected) followed by the
+ * partial aggregate, over ONE record batch given as an Arrow struct array.  Buffers may be host or device
+ * memory (`buffers_on_device`); host buffers are staged through the context's pinned ring. */
+int exon_gpu_filter_agg(exon_gpu_ctx *ctx, const struct ArrowArray *batch, const struct ArrowSchema *schema,
+                        int buffers_on_device, const exon_gpu_pred *pred, const exon_gpu_agg *agg,
+                        exon_gpu_partial *out);
+
+/* ---- multi-GPU final aggregate ---------------------------------------------------------------- */
+/* CoalescePartitionsExec + AggregateExec(Final) across GPUs: one ncclAllReduce(sum) of the partial over
+ * NVLink.  The communicator is created from an id produced on rank 0 and distributed by the host. */
+#define EXON_GPU_NCCL_ID_BYTES 128
+int exon_gpu_nccl_unique_id(uint8_t id[EXON_GPU_NCCL_ID_BYTES]);
+int exon_gpu_nccl_init(exon_gpu_ctx *ctx, const uint8_t id[EXON_GPU_NCCL_ID_BYTES], int n_ranks, int rank);
+int exon_gpu_allreduce_partial(exon_gpu_ctx *ctx, exon_gpu_partial *inout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXON_GPU_H */

@@ -1,0 +1,188 @@
+"""ctypes wrapper over oracle/liboracle.so -- the CPU restatement of the reference path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` leg.  The product package (exon_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+INT64_MAX = (1 << 63) - 1
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith(".c")]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+class Region(C.Structure):
+    _fields_ = [("name", C.c_char * 256), ("name_len", C.c_int32), ("has_interval", C.c_int32),
+                ("lo", C.c_int64), ("hi", C.c_int64)]
+
+
+class VcfBatch(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("chrom_offsets", C.POINTER(C.c_int32)), ("chrom_values", C.POINTER(C.c_uint8)),
+                ("chrom_values_len", C.c_int64), ("pos", C.POINTER(C.c_int64))]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        L = _lib
+        L.exo_vcf_header_len.restype = C.c_int64
+        L.exo_vcf_header_len.argtypes = [C.c_void_p, C.c_int64]
+        L.exo_region_parse.restype = C.c_int
+        L.exo_region_parse.argtypes = [C.c_char_p, C.POINTER(Region)]
+        L.exo_interval_parse.restype = C.c_int
+        L.exo_interval_parse.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.exo_vcf_reader_open.restype = C.c_void_p
+        L.exo_vcf_reader_open.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int32), C.c_int32]
+        L.exo_vcf_reader_next.restype = C.c_int
+        L.exo_vcf_reader_next.argtypes = [C.c_void_p, C.POINTER(VcfBatch)]
+        L.exo_vcf_reader_close.argtypes = [C.c_void_p]
+        L.exo_vcf_reader_err_row.restype = C.c_int64
+        L.exo_vcf_reader_err_row.argtypes = [C.c_void_p]
+        L.exo_vcf_filter_count.restype = C.c_int64
+        L.exo_vcf_filter_count.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_char_p, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
+        L.exo_vcf_filter_count_files.restype = C.c_int64
+        L.exo_vcf_filter_count_files.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32,
+                                                 C.c_int64, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64,
+                                                 C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+        L.exo_regroup_files_by_size.restype = C.c_int32
+        L.exo_regroup_files_by_size.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        L.exo_region_match.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Region), C.c_void_p]
+        L.exo_chrom_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p, C.c_int32, C.c_void_p]
+        L.exo_interval_match.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+    return _lib
+
+
+def _buf(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        return data
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+def header_len(data) -> int:
+    a = _buf(data)
+    return int(lib().exo_vcf_header_len(a.ctypes.data, a.size))
+
+
+def parse_region(s: str) -> Region:
+    r = Region()
+    rc = lib().exo_region_parse(s.encode(), C.byref(r))
+    if rc != 0:
+        raise ValueError(f"bad region {s!r}")
+    return r
+
+
+def parse_interval(s: str):
+    lo, hi = C.c_int64(), C.c_int64()
+    b = s.encode()
+    if not lib().exo_interval_parse(b, len(b), C.byref(lo), C.byref(hi)):
+        raise ValueError(f"bad interval {s!r}")
+    return lo.value, hi.value
+
+
+def read_batches(data, batch_size: int = 8192, projection=(0, 1)):
+    """Yield dicts {rows, chrom_offsets, chrom_values, pos} (numpy copies), one per reference batch."""
+    a = _buf(data)
+    proj = (C.c_int32 * len(projection))(*projection)
+    r = lib().exo_vcf_reader_open(a.ctypes.data, a.size, batch_size, proj, len(projection))
+    try:
+        b = VcfBatch()
+        while True:
+            rc = lib().exo_vcf_reader_next(r, C.byref(b))
+            if rc == 0:
+                return
+            if rc < 0:
+                raise ValueError(f"malformed VCF record at row {lib().exo_vcf_reader_err_row(r)}")
+            out = {"rows": int(b.rows)}
+            if 0 in projection:
+                out["chrom_offsets"] = np.ctypeslib.as_array(b.chrom_offsets, (b.rows + 1,)).copy()
+                out["chrom_values"] = np.ctypeslib.as_array(b.chrom_values, (max(b.chrom_values_len, 1),))[
+                    : b.chrom_values_len].copy()
+            if 1 in projection:
+                out["pos"] = np.ctypeslib.as_array(b.pos, (b.rows,)).copy()
+            yield out
+    finally:
+        lib().exo_vcf_reader_close(r)
+
+
+def filter_count(data, chrom=None, lo=None, hi=None, batch_size: int = 8192):
+    """(count, rows) for `chrom = <chrom> AND pos BETWEEN lo AND hi` over one VCF text."""
+    a = _buf(data)
+    has_chrom = chrom is not None
+    has_iv = lo is not None or hi is not None
+    cb = chrom.encode() if isinstance(chrom, str) else (chrom or b"")
+    rows = C.c_int64()
+    c = lib().exo_vcf_filter_count(a.ctypes.data, a.size, batch_size, cb, len(cb), int(has_chrom), int(has_iv),
+                                   1 if lo is None else lo, INT64_MAX if hi is None else hi, C.byref(rows))
+    if c < 0:
+        raise ValueError(f"oracle error {c}")
+    return int(c), int(rows.value)
+
+
+def filter_count_files(datas, chrom=None, lo=None, hi=None, target_partitions: int = 1, batch_size: int = 8192):
+    """(count, rows, partitions) over several in-memory VCF files, one worker thread per partition."""
+    arrs = [_buf(d) for d in datas]
+    n = len(arrs)
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    lens = (C.c_int64 * n)(*[a.size for a in arrs])
+    has_chrom = chrom is not None
+    has_iv = lo is not None or hi is not None
+    cb = chrom.encode() if isinstance(chrom, str) else (chrom or b"")
+    rows, parts = C.c_int64(), C.c_int32()
+    c = lib().exo_vcf_filter_count_files(ptrs, lens, n, target_partitions, batch_size, cb, len(cb), int(has_chrom),
+                                         int(has_iv), 1 if lo is None else lo, INT64_MAX if hi is None else hi,
+                                         C.byref(rows), C.byref(parts))
+    if c < 0:
+        raise ValueError(f"oracle error {c}")
+    return int(c), int(rows.value), int(parts.value)
+
+
+def regroup_files_by_size(sizes, target_partitions: int):
+    n = len(sizes)
+    s = (C.c_int64 * n)(*sizes)
+    g = (C.c_int32 * n)()
+    parts = lib().exo_regroup_files_by_size(s, n, target_partitions, g)
+    return parts, list(g)
+
+
+def region_match(offsets, values, pos, region: str):
+    rg = parse_region(region)
+    n = len(pos)
+    out = np.zeros(n, dtype=np.uint8)
+    lib().exo_region_match(offsets.ctypes.data, values.ctypes.data, pos.ctypes.data, n, C.byref(rg), out.ctypes.data)
+    return out.astype(bool)
+
+
+def chrom_match(offsets, values, lit: str):
+    n = len(offsets) - 1
+    out = np.zeros(n, dtype=np.uint8)
+    b = lit.encode()
+    lib().exo_chrom_match(offsets.ctypes.data, values.ctypes.data, n, b, len(b), out.ctypes.data)
+    return out.astype(bool)
+
+
+def interval_match(pos, interval: str):
+    lo, hi = parse_interval(interval)
+    out = np.zeros(len(pos), dtype=np.uint8)
+    lib().exo_interval_match(pos.ctypes.data, len(pos), lo, hi, out.ctypes.data)
+    return out.astype(bool)

@@ -1,0 +1,410 @@
+/*
+ * oracle/vcf_oracle.c -- CPU restatement of the reference's VCF scan -> filter -> COUNT path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under exon_b200/ may import, link or call this file; it exists so
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg can check and time
+ * the CUDA path against an independent statement of the reference algorithm.
+ *
+ * The reference (wheretrue/exon v0.32.4) is 100% Rust and cannot be compiled in this image (no cargo/rustc),
+ * and the record-level parsing lives in un-vendored crates (noodles-vcf 0.70.0, noodles-core 0.15.0,
+ * datafusion 44.0.0 / arrow 53.3.0, pinned in /root/reference/Cargo.lock).  This file therefore restates
+ *   - the reference's own call sites (cited per function, paths relative to /root/reference), and
+ *   - the published behaviour of those crates for the pieces exon delegates to them (VCF 4.2 line/field
+ *     syntax, Rust `usize::from_str`, `Region::from_str`, arrow `eq`/`gt_eq`/`lt_eq`/`and_kleene`, COUNT).
+ * Parity is pinned by tests/test_oracle_golden.py against every known-answer the reference's tests hold for
+ * this path: 621 / 191 / 219 / 211 / 382 / 11 / 0 row counts, the slt UDF truth tables,
+ * the RegionPhysicalExpr / PosIntervalPhysicalExpr unit vectors.
+ *
+ * Unpinned by any reference test (documented choices; synthetic inputs avoid them): POS "0" (error: the
+ * reference appends None into a non-nullable column, lazy_array_builder.rs:163-168 + schema_builder.rs:90),
+ * lines with fewer than 8 fields (error), empty lines (error), a trailing '\r' (kept as data), a leading '+'
+ * in POS (accepted, as Rust's usize parser does).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define EXO_OK 0
+#define EXO_END 0
+#define EXO_BATCH 1
+#define EXO_ERR_PARSE (-2)
+#define EXO_ERR_ARG (-1)
+
+/* ---------------------------------------------------------------------------------------------
+ * Header skip.  exon-core/src/datasources/vcf/file_opener/unindex_file_opener.rs:74-88:
+ * `vcf_reader.read_header()` consumes every leading line that starts with '#' (the "##" meta lines and the
+ * "#CHROM" line); records start at the first line that does not.  Returns the byte offset of that line.
+ * ------------------------------------------------------------------------------------------- */
+int64_t exo_vcf_header_len(const uint8_t *text, int64_t len) {
+    int64_t p = 0;
+    while (p < len && text[p] == '#') {
+        const uint8_t *nl = (const uint8_t *)memchr(text + p, '\n', (size_t)(len - p));
+        if (!nl) return len;
+        p = (nl - text) + 1;
+    }
+    return p;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Region literal.  noodles-core 0.15 `Region::from_str` as used at
+ * exon-core/src/physical_plan/infer_region.rs:25-42 and exon-core/src/udfs/vcf/mod.rs:85-95:
+ *   "name"            -> whole contig
+ *   "name:start"      -> [start, +inf)
+ *   "name:start-end"  -> [start, end], 1-based, both ends inclusive
+ * The name/interval split is at the last ':' whose suffix parses as an interval; otherwise the whole string
+ * is the name.  Interval::from_str as used by interval_match (udfs/vcf/mod.rs:246-252): "a-b", "a", "a-", "-b".
+ * lo = 1 / hi = INT64_MAX stand for the open ends.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    char name[256];
+    int32_t name_len;
+    int32_t has_interval;
+    int64_t lo, hi;
+} exo_region;
+
+static int parse_u64(const char *s, int n, int64_t *out) {
+    if (n <= 0) return 0;
+    int i = 0;
+    if (s[0] == '+') i = 1; /* Rust usize::from_str accepts one leading '+' */
+    if (i >= n) return 0;
+    uint64_t v = 0;
+    for (; i < n; i++) {
+        if (s[i] < '0' || s[i] > '9') return 0;
+        uint64_t d = (uint64_t)(s[i] - '0');
+        if (v > (UINT64_MAX - d) / 10) return 0;
+        v = v * 10 + d;
+    }
+    if (v > (uint64_t)INT64_MAX) return 0;
+    *out = (int64_t)v;
+    return 1;
+}
+
+int exo_interval_parse(const char *s, int n, int64_t *lo, int64_t *hi) {
+    *lo = 1;
+    *hi = INT64_MAX;
+    if (n == 0) return 1; /* unbounded */
+    const char *dash = (const char *)memchr(s, '-', (size_t)n);
+    if (!dash) {
+        if (!parse_u64(s, n, lo) || *lo < 1) return 0;
+        return 1;
+    }
+    int a = (int)(dash - s), b = n - a - 1;
+    if (a > 0 && (!parse_u64(s, a, lo) || *lo < 1)) return 0;
+    if (b > 0 && (!parse_u64(dash + 1, b, hi) || *hi < 1)) return 0;
+    return 1;
+}
+
+int exo_region_parse(const char *s, exo_region *out) {
+    int n = (int)strlen(s);
+    memset(out, 0, sizeof(*out));
+    out->lo = 1;
+    out->hi = INT64_MAX;
+    if (n == 0 || n >= (int)sizeof(out->name)) return EXO_ERR_ARG;
+    int split = -1;
+    for (int i = n - 1; i >= 0; i--)
+        if (s[i] == ':') { split = i; break; }
+    if (split > 0) {
+        int64_t lo, hi;
+        if (n - split - 1 > 0 && exo_interval_parse(s + split + 1, n - split - 1, &lo, &hi)) {
+            memcpy(out->name, s, (size_t)split);
+            out->name_len = split;
+            out->has_interval = 1;
+            out->lo = lo;
+            out->hi = hi;
+            return EXO_OK;
+        }
+    }
+    memcpy(out->name, s, (size_t)n);
+    out->name_len = n;
+    return EXO_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Batch reader.  exon-vcf/src/async_batch_stream.rs:80-109 (`read_batch`): a fresh builder per batch;
+ * `while builder.len() < batch_size { read_record; append }`; an empty builder ends the stream.
+ * `read_record` (:59-67) is noodles' lazy record: one text line, with the eight mandatory field boundaries
+ * located by scanning for '\t'.  `LazyVCFArrayBuilder::append` (exon-vcf/src/array_builder/
+ * lazy_array_builder.rs:153-448) then materialises only the projected columns:
+ *   col 0 chrom (:159-162)  bytes of field 0 appended to a GenericStringBuilder<i32> (offsets i32, values u8)
+ *   col 1 pos   (:163-168)  field 1 parsed as decimal usize -> i64; "0" -> None (-> error, column is !null)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t rows;
+    int32_t *chrom_offsets; /* rows + 1, starts at 0 for every batch (arrow-rs StringBuilder) */
+    uint8_t *chrom_values;
+    int64_t chrom_values_len;
+    int64_t *pos;
+} exo_vcf_batch;
+
+typedef struct {
+    const uint8_t *text;
+    int64_t len, cur;
+    int64_t batch_size;
+    int want_chrom, want_pos;
+    int64_t row_index; /* rows consumed so far (for error reporting) */
+    int64_t err_row;
+    int32_t *offsets;
+    uint8_t *values;
+    int64_t values_cap;
+    int64_t *pos;
+} exo_vcf_reader;
+
+exo_vcf_reader *exo_vcf_reader_open(const uint8_t *text, int64_t len, int64_t batch_size, const int32_t *projection,
+                                    int32_t n_proj) {
+    exo_vcf_reader *r = (exo_vcf_reader *)calloc(1, sizeof(*r));
+    r->text = text;
+    r->len = len;
+    r->cur = exo_vcf_header_len(text, len);
+    r->batch_size = batch_size;
+    r->err_row = -1;
+    for (int i = 0; i < n_proj; i++) {
+        if (projection[i] == 0) r->want_chrom = 1;
+        if (projection[i] == 1) r->want_pos = 1;
+    }
+    r->offsets = (int32_t *)malloc(sizeof(int32_t) * (size_t)(batch_size + 1));
+    r->values_cap = batch_size * 8; /* data_capacity = capacity * 8, lazy_array_builder.rs:79 */
+    r->values = (uint8_t *)malloc((size_t)r->values_cap);
+    r->pos = (int64_t *)malloc(sizeof(int64_t) * (size_t)batch_size);
+    return r;
+}
+
+void exo_vcf_reader_close(exo_vcf_reader *r) {
+    if (!r) return;
+    free(r->offsets);
+    free(r->values);
+    free(r->pos);
+    free(r);
+}
+
+int64_t exo_vcf_reader_err_row(const exo_vcf_reader *r) { return r->err_row; }
+
+/* one line -> (chrom bytes, pos).  Returns 0 at EOF, 1 on a record, <0 on malformed input. */
+static inline int read_record(exo_vcf_reader *r, const uint8_t **chrom, int32_t *chrom_len, int64_t *pos) {
+    if (r->cur >= r->len) return 0;
+    const uint8_t *line = r->text + r->cur;
+    int64_t rem = r->len - r->cur;
+    const uint8_t *nl = (const uint8_t *)memchr(line, '\n', (size_t)rem);
+    int64_t line_len = nl ? (nl - line) : rem;
+    r->cur += line_len + (nl ? 1 : 0);
+    /* field boundaries: the record needs 8 tab-separated fields (7 tabs) */
+    const uint8_t *t0 = (const uint8_t *)memchr(line, '\t', (size_t)line_len);
+    if (!t0) return EXO_ERR_PARSE;
+    const uint8_t *f1 = t0 + 1;
+    const uint8_t *t1 = (const uint8_t *)memchr(f1, '\t', (size_t)(line + line_len - f1));
+    if (!t1) return EXO_ERR_PARSE;
+    const uint8_t *p = t1 + 1;
+    for (int k = 2; k < 7; k++) {
+        const uint8_t *t = (const uint8_t *)memchr(p, '\t', (size_t)(line + line_len - p));
+        if (!t) return EXO_ERR_PARSE;
+        p = t + 1;
+    }
+    *chrom = line;
+    *chrom_len = (int32_t)(t0 - line);
+    if (*chrom_len == 0) return EXO_ERR_PARSE;
+    if (r->want_pos) {
+        int64_t v;
+        if (!parse_u64((const char *)f1, (int)(t1 - f1), &v)) return EXO_ERR_PARSE;
+        if (v == 0) return EXO_ERR_PARSE; /* telomere -> None into a non-nullable column */
+        *pos = v;
+    }
+    return 1;
+}
+
+int exo_vcf_reader_next(exo_vcf_reader *r, exo_vcf_batch *out) {
+    int64_t rows = 0, nvals = 0;
+    r->offsets[0] = 0;
+    while (rows < r->batch_size) {
+        const uint8_t *chrom = NULL;
+        int32_t clen = 0;
+        int64_t pos = 0;
+        int rc = read_record(r, &chrom, &clen, &pos);
+        if (rc == 0) break;
+        if (rc < 0) {
+            r->err_row = r->row_index + rows;
+            return rc;
+        }
+        if (r->want_chrom) {
+            if (nvals + clen > r->values_cap) {
+                while (nvals + clen > r->values_cap) r->values_cap *= 2;
+                r->values = (uint8_t *)realloc(r->values, (size_t)r->values_cap);
+            }
+            memcpy(r->values + nvals, chrom, (size_t)clen);
+            nvals += clen;
+            r->offsets[rows + 1] = (int32_t)nvals;
+        }
+        if (r->want_pos) r->pos[rows] = pos;
+        rows++;
+    }
+    r->row_index += rows;
+    if (rows == 0) return EXO_END;
+    out->rows = rows;
+    out->chrom_offsets = r->want_chrom ? r->offsets : NULL;
+    out->chrom_values = r->want_chrom ? r->values : NULL;
+    out->chrom_values_len = nvals;
+    out->pos = r->want_pos ? r->pos : NULL;
+    return EXO_BATCH;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * FilterExec + AggregateExec(COUNT).  Third-party (datafusion-physical-plan 44 / arrow-ord 53.3); predicate
+ * shape as mirrored by exon-core/src/physical_plan/pos_interval_physical_expr.rs:79-98
+ * (`pos >= start AND pos <= end`, inclusive) and region_physical_expr.rs:220-240 (chrom = name AND interval),
+ * and by the evaluated UDFs exon-core/src/udfs/vcf/mod.rs:65-131 (region_match), :167-196 (chrom_match),
+ * :232-274 (interval_match).  Evaluated column-at-a-time like arrow: eq -> mask, gt_eq -> mask, lt_eq -> mask,
+ * and -> mask, then the count of set bits is added to the Int64 accumulator.
+ * No nulls can occur in chrom/pos on this path (both !null), so Kleene AND degenerates to AND.
+ * ------------------------------------------------------------------------------------------- */
+int64_t exo_filter_count_batch(const exo_vcf_batch *b, const uint8_t *chrom, int32_t chrom_len, int32_t has_chrom,
+                               int32_t has_interval, int64_t lo, int64_t hi, uint8_t *mask /* rows bytes, may be NULL */) {
+    int64_t n = b->rows, cnt = 0;
+    uint8_t *m = mask ? mask : (uint8_t *)malloc((size_t)n);
+    memset(m, 1, (size_t)n);
+    if (has_chrom) {
+        for (int64_t i = 0; i < n; i++) {
+            int32_t s = b->chrom_offsets[i], e = b->chrom_offsets[i + 1];
+            m[i] = (uint8_t)((e - s) == chrom_len && memcmp(b->chrom_values + s, chrom, (size_t)chrom_len) == 0);
+        }
+    }
+    if (has_interval) {
+        for (int64_t i = 0; i < n; i++) m[i] &= (uint8_t)(b->pos[i] >= lo);
+        for (int64_t i = 0; i < n; i++) m[i] &= (uint8_t)(b->pos[i] <= hi);
+    }
+    for (int64_t i = 0; i < n; i++) cnt += m[i];
+    if (!mask) free(m);
+    return cnt;
+}
+
+/* Whole-file scan -> filter -> COUNT, batch by batch, as one DataFusion partition would run it.
+ * Returns the count (>= 0) or a negative error; *n_rows gets the number of records scanned. */
+int64_t exo_vcf_filter_count(const uint8_t *text, int64_t len, int64_t batch_size, const uint8_t *chrom,
+                             int32_t chrom_len, int32_t has_chrom, int32_t has_interval, int64_t lo, int64_t hi,
+                             int64_t *n_rows) {
+    int32_t proj[2] = {0, 1};
+    /* projection pushdown: SURVEY 2.2 #1 -- only the columns the predicate touches are materialised */
+    int32_t n_proj = 0;
+    if (has_chrom) proj[n_proj++] = 0;
+    if (has_interval) proj[n_proj++] = 1;
+    exo_vcf_reader *r = exo_vcf_reader_open(text, len, batch_size, proj, n_proj);
+    exo_vcf_batch b;
+    int64_t total = 0, rows = 0;
+    int rc;
+    while ((rc = exo_vcf_reader_next(r, &b)) == EXO_BATCH) {
+        total += exo_filter_count_batch(&b, chrom, chrom_len, has_chrom, has_interval, lo, hi, NULL);
+        rows += b.rows;
+    }
+    exo_vcf_reader_close(r);
+    if (n_rows) *n_rows = rows;
+    return rc < 0 ? rc : total;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * File -> partition assignment.  exon-core/src/datasources/exon_file_scan_config.rs:79-110
+ * (`regroup_files_by_size`): flatten, stable-sort ascending by size, partitions = min(target, #files),
+ * file i -> partition i % partitions.  out_group[i] receives the partition of input file i.
+ * Returns the number of partitions.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { int64_t size; int32_t idx; } sized_file;
+static int cmp_sized(const void *a, const void *b) {
+    const sized_file *x = (const sized_file *)a, *y = (const sized_file *)b;
+    if (x->size != y->size) return x->size < y->size ? -1 : 1;
+    return x->idx - y->idx; /* itertools sorted_by_key is stable */
+}
+int32_t exo_regroup_files_by_size(const int64_t *sizes, int32_t n_files, int32_t target_partitions, int32_t *out_group) {
+    if (n_files <= 0) return 0;
+    sized_file *f = (sized_file *)malloc(sizeof(sized_file) * (size_t)n_files);
+    for (int32_t i = 0; i < n_files; i++) { f[i].size = sizes[i]; f[i].idx = i; }
+    qsort(f, (size_t)n_files, sizeof(sized_file), cmp_sized);
+    int32_t parts = target_partitions < n_files ? target_partitions : n_files;
+    if (parts < 1) parts = 1;
+    for (int32_t i = 0; i < n_files; i++) out_group[f[i].idx] = i % parts;
+    free(f);
+    return parts;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-file driver used as the timed CPU baseline: one worker per partition, partitions =
+ * min(target_partitions, #files) exactly as VCFScan::repartitioned does
+ * (exon-core/src/datasources/vcf/scanner.rs:103-124); each worker scans its files one after another
+ * (FileStream), partial counts are summed (CoalescePartitionsExec + AggregateExec(Final)).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint8_t *const *texts;
+    const int64_t *lens;
+    const int32_t *group;
+    int32_t n_files, my_group;
+    int64_t batch_size;
+    const uint8_t *chrom;
+    int32_t chrom_len, has_chrom, has_interval;
+    int64_t lo, hi;
+    int64_t count, rows;
+    int err;
+} worker_arg;
+
+static void *worker_main(void *p) {
+    worker_arg *a = (worker_arg *)p;
+    for (int32_t i = 0; i < a->n_files; i++) {
+        if (a->group[i] != a->my_group) continue;
+        int64_t rows = 0;
+        int64_t c = exo_vcf_filter_count(a->texts[i], a->lens[i], a->batch_size, a->chrom, a->chrom_len, a->has_chrom,
+                                         a->has_interval, a->lo, a->hi, &rows);
+        if (c < 0) { a->err = (int)c; return NULL; }
+        a->count += c;
+        a->rows += rows;
+    }
+    return NULL;
+}
+
+int64_t exo_vcf_filter_count_files(const uint8_t *const *texts, const int64_t *lens, int32_t n_files,
+                                   int32_t target_partitions, int64_t batch_size, const uint8_t *chrom,
+                                   int32_t chrom_len, int32_t has_chrom, int32_t has_interval, int64_t lo, int64_t hi,
+                                   int64_t *n_rows, int32_t *n_partitions) {
+    if (n_files <= 0) { if (n_rows) *n_rows = 0; if (n_partitions) *n_partitions = 0; return 0; }
+    int32_t *group = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_files);
+    int32_t parts = exo_regroup_files_by_size(lens, n_files, target_partitions, group);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)parts);
+    worker_arg *args = (worker_arg *)calloc((size_t)parts, sizeof(worker_arg));
+    for (int32_t g = 0; g < parts; g++) {
+        worker_arg *a = &args[g];
+        a->texts = texts; a->lens = lens; a->group = group; a->n_files = n_files; a->my_group = g;
+        a->batch_size = batch_size; a->chrom = chrom; a->chrom_len = chrom_len; a->has_chrom = has_chrom;
+        a->has_interval = has_interval; a->lo = lo; a->hi = hi;
+        pthread_create(&th[g], NULL, worker_main, a);
+    }
+    int64_t total = 0, rows = 0;
+    int err = 0;
+    for (int32_t g = 0; g < parts; g++) {
+        pthread_join(th[g], NULL);
+        if (args[g].err) err = args[g].err;
+        total += args[g].count;
+        rows += args[g].rows;
+    }
+    free(th); free(args); free(group);
+    if (n_rows) *n_rows = rows;
+    if (n_partitions) *n_partitions = parts;
+    return err ? err : total;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-at-a-time region UDFs (exon-core/src/udfs/vcf/mod.rs).  region_match (:65-131):
+ * name == chrom && interval.contains(pos); chrom_match (:167-196): chrom == value; interval_match (:232-274).
+ * out[i] in {0,1}.
+ * ------------------------------------------------------------------------------------------- */
+void exo_region_match(const int32_t *offsets, const uint8_t *values, const int64_t *pos, int64_t n, const exo_region *rg,
+                      uint8_t *out) {
+    for (int64_t i = 0; i < n; i++) {
+        int32_t s = offsets[i], e = offsets[i + 1];
+        int eq = (e - s) == rg->name_len && memcmp(values + s, rg->name, (size_t)rg->name_len) == 0;
+        out[i] = (uint8_t)(eq && pos[i] >= rg->lo && pos[i] <= rg->hi);
+    }
+}
+void exo_chrom_match(const int32_t *offsets, const uint8_t *values, int64_t n, const uint8_t *lit, int32_t lit_len,
+                     uint8_t *out) {
+    for (int64_t i = 0; i < n; i++) {
+        int32_t s = offsets[i], e = offsets[i + 1];
+        out[i] = (uint8_t)((e - s) == lit_len && memcmp(values + s, lit, (size_t)lit_len) == 0);
+    }
+}
+void exo_interval_match(const int64_t *pos, int64_t n, int64_t lo, int64_t hi, uint8_t *out) {
+    for (int64_t i = 0; i < n; i++) out[i] = (uint8_t)(pos[i] >= lo && pos[i] <= hi);
+}
