@@ -25,6 +25,7 @@ SYMBOLS = [
     "exon_gpu_vcf_close", "exon_gpu_vcf_reset", "exon_gpu_vcf_feed", "exon_gpu_vcf_next_batch",
     "exon_gpu_vcf_filter_count", "exon_gpu_vcf_filter_count_async", "exon_gpu_vcf_rows", "exon_gpu_vcf_body_bytes",
     "exon_gpu_filter_agg", "exon_gpu_nccl_unique_id", "exon_gpu_nccl_init", "exon_gpu_allreduce_partial",
+    "exon_gpu_vcf_filter_count_global",
 ]
 
 
@@ -114,6 +115,7 @@ def load():
         "exon_gpu_vcf_next_batch": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)],
         "exon_gpu_vcf_filter_count": [vp, C.POINTER(Region), C.POINTER(i64)],
         "exon_gpu_vcf_filter_count_async": [vp, C.POINTER(Region), vp],
+        "exon_gpu_vcf_filter_count_global": [vp, C.POINTER(Region), C.POINTER(i64), C.POINTER(i64)],
         "exon_gpu_vcf_rows": [vp, C.POINTER(i64)],
         "exon_gpu_vcf_body_bytes": [vp, C.POINTER(i64)],
         "exon_gpu_filter_agg": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema), C.c_int, C.POINTER(Pred),

@@ -281,6 +281,13 @@ int exon_gpu_vcf_filter_count(exon_gpu_stream *s, const exon_gpu_region *region,
     return s->filter_count(region, nullptr, out_count);
 }
 
+int exon_gpu_vcf_filter_count_global(exon_gpu_stream *s, const exon_gpu_region *region, int64_t *out_local,
+                                     int64_t *out_global) {
+    if (!s || (!out_local && !out_global)) return fail(EXON_GPU_ERR_ARG, "vcf_filter_count_global: NULL argument");
+    if (int rc = ensure_device(s->ctx)) return rc;
+    return s->filter_count_global(region, out_local, out_global);
+}
+
 int exon_gpu_vcf_rows(exon_gpu_stream *s, int64_t *out_rows) {
     if (!s || !out_rows) return fail(EXON_GPU_ERR_ARG, "vcf_rows: NULL argument");
     if (int rc = ensure_device(s->ctx)) return rc;

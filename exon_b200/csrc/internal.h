@@ -47,6 +47,8 @@ struct Ctx {
 };
 
 void nccl_teardown(Ctx *c);
+// in-place sum all-reduce of n int64 in device memory, enqueued on the context's stream
+int nccl_allreduce_i64(Ctx *c, int64_t *device_buf, size_t n);
 
 // A region whose chrom bytes are owned (the caller's exon_gpu_region may go away).
 struct OwnedRegion {
@@ -83,10 +85,15 @@ struct VcfStream {
     bool cur_run_open = false;      // runs.back() lives at the tail of blocks.back() and may still grow
     int64_t tail_len = 0;           // bytes after the last '\n' of the open arena run (a partial line)
     int64_t body_bytes = 0;
+    // end of each finished file as (run index, run length at that moment): record batches never span files
+    // (FileStream opens one AsyncBatchStream per file, exon/exon-vcf/src/async_batch_stream.rs:70-109)
+    struct FileMark { size_t run; int64_t len; };
+    std::vector<FileMark> file_marks;
 
     // ---- eager (pushdown) scan bookkeeping ----
     int64_t eager_scanned = 0;      // bytes of the open run already covered by eager launches
     size_t eager_runs_done = 0;     // runs [0, eager_runs_done) fully covered
+    bool last_eager = false;        // the most recent filter_count was answered by the eager accumulator
 
     // ---- device-side tables / results ----
     ScanSeg *d_segs = nullptr;
@@ -106,6 +113,7 @@ struct VcfStream {
     int append_host(const uint8_t *p, size_t n);
     int end_file();
     int filter_count(const exon_gpu_region *region, int64_t *device_out, int64_t *host_out);
+    int filter_count_global(const exon_gpu_region *region, int64_t *out_local, int64_t *out_global);
     int launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_segs, int64_t tiles, unsigned long long *d_count,
                     unsigned long long *d_flags, bool timed);
     int build_seg_table();

@@ -71,6 +71,12 @@ void nccl_teardown(Ctx *c) {
     c->nccl_comm = nullptr;
 }
 
+int nccl_allreduce_i64(Ctx *c, int64_t *device_buf, size_t n) {
+    if (!c->nccl_comm) return fail(EXON_GPU_ERR_STATE, "all-reduce: exon_gpu_nccl_init has not been called");
+    NCCL_TRY(g_nccl.AllReduce(device_buf, device_buf, n, ncclInt64, ncclSum, (ncclComm_t)c->nccl_comm, c->stream));
+    return EXON_GPU_OK;
+}
+
 }  // namespace exon
 
 using namespace exon;

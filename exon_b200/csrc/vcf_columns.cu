@@ -213,19 +213,58 @@ __global__ void __launch_bounds__(kThreads) parse_rows(const RunDesc *runs, int 
     }
 }
 
-// pass 5b: values[voff[row] .. ) = CHROM bytes; offsets restart at 0 in every batch
-__global__ void __launch_bounds__(kThreads) gather_chrom(int64_t n_rows, int batch_rows, const uint8_t *const *line_ptr,
-                                                        const int32_t *chrom_len, const long long *voff,
-                                                        uint8_t *values, int32_t *offsets) {
+// Row index of every file end: first row of the mark's run whose line starts at or after the mark.
+struct MarkDesc {
+    int32_t run;  // index into the RunDesc table
+    int32_t pad_;
+    int64_t len;  // run bytes that belong to files up to and including the marked one
+};
+__global__ void mark_rows(const RunDesc *runs, int n_runs, const MarkDesc *marks, int n_marks,
+                          const uint8_t *const *line_ptr, int64_t n_rows, long long *out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_marks) return;
+    const int r = marks[m].run;
+    int64_t lo = runs[r].row0, hi = (r + 1 < n_runs) ? runs[r + 1].row0 : n_rows;
+    const uint8_t *lim = runs[r].base + marks[m].len;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (line_ptr[mid] < lim) lo = mid + 1;
+        else hi = mid;
+    }
+    out[m] = lo;
+}
+
+// out[i] = src[idx[i]]
+__global__ void gather_i64(const long long *src, const long long *idx, int64_t n, long long *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+// pass 5b: values[voff[row] .. ) = CHROM bytes; offsets restart at 0 in every batch.  Batches restart at every
+// file: file f covers rows [file_row0[f], file_row0[f + 1]) and owns batches file_batch0[f] .. in steps of
+// batch_rows rows.
+__global__ void __launch_bounds__(kThreads) gather_chrom(int64_t n_rows, int batch_rows, int n_files,
+                                                        const long long *file_row0, const long long *file_batch0,
+                                                        const uint8_t *const *line_ptr, const int32_t *chrom_len,
+                                                        const long long *voff, uint8_t *values, int32_t *offsets) {
     const int64_t row = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (row >= n_rows) return;
-    const int64_t batch = row / batch_rows, in_batch = row - batch * batch_rows;
-    const long long v0 = voff[batch * batch_rows];
+    int lo = 0, hi = n_files - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (file_row0[mid] <= row) lo = mid;
+        else hi = mid - 1;
+    }
+    const int64_t f0 = file_row0[lo], f1 = file_row0[lo + 1];
+    const int64_t k = (row - f0) / batch_rows;
+    const int64_t batch = file_batch0[lo] + k, b0 = f0 + k * batch_rows;
+    const int64_t in_batch = row - b0;
+    const long long v0 = voff[b0];
     const long long v = voff[row];
     const int32_t n = chrom_len[row];
     int32_t *o = offsets + batch * (batch_rows + 1);
     o[in_batch] = (int32_t)(v - v0);
-    if (row + 1 == n_rows || in_batch + 1 == batch_rows) o[in_batch + 1] = (int32_t)(v + n - v0);
+    if (row + 1 == f1 || in_batch + 1 == batch_rows) o[in_batch + 1] = (int32_t)(v + n - v0);
     const uint8_t *src = line_ptr[row];
     for (int32_t j = 0; j < n; ++j) values[v + j] = src[j];
 }
@@ -249,7 +288,8 @@ struct Columns {
     int64_t *h_pos = nullptr;
     int32_t *h_offsets = nullptr;
     uint8_t *h_values = nullptr;
-    std::vector<long long> batch_v0;  // values offset of each batch's first row (+ total at the end)
+    std::vector<long long> batch_row0;  // first row of each batch (+ n_rows at the end); batches never span files
+    std::vector<long long> batch_v0;    // values offset of each batch's first row (+ total at the end)
     std::vector<int> projection;
 
     void unref() {
@@ -349,10 +389,14 @@ int build_columns(VcfStream *s) {
         if (p == 0) c->want_chrom = true;
         if (p == 1) c->want_pos = true;
     }
-    // run table
+    c->batch_row0.assign(1, 0);
+    // run table (empty runs dropped; run_map: stream run index -> table index of the first non-empty run at or after it)
     std::vector<RunDesc> h_runs;
+    std::vector<int> run_map(s->runs.size() + 1, 0);
     int64_t n_blocks = 0;
-    for (const Run &r : s->runs) {
+    for (size_t i = 0; i < s->runs.size(); ++i) {
+        const Run &r = s->runs[i];
+        run_map[i] = (int)h_runs.size();
         if (r.len <= 0) continue;
         RunDesc d;
         d.base = r.base;
@@ -364,19 +408,33 @@ int build_columns(VcfStream *s) {
     }
     if (h_runs.empty()) return EXON_GPU_OK;  // zero rows
     const int n_runs = (int)h_runs.size();
+    // file ends that fall inside a non-empty run (an empty file adds no rows and no batch)
+    std::vector<MarkDesc> h_marks;
+    for (const auto &m : s->file_marks) {
+        if (m.run >= s->runs.size() || s->runs[m.run].len <= 0 || m.len <= 0) continue;
+        MarkDesc d;
+        d.run = run_map[m.run];
+        d.pad_ = 0;
+        d.len = std::min<int64_t>(m.len, s->runs[m.run].len);
+        h_marks.push_back(d);
+    }
+    const int n_marks = (int)h_marks.size();
 
     RunDesc *d_runs = nullptr;
+    MarkDesc *d_marks = nullptr;
     unsigned long long *d_block_rows = nullptr, *d_block_row0 = nullptr, *d_misc = nullptr;
+    long long *d_small = nullptr;  // mark rows | file_row0 | file_batch0 | batch_row0 | batch_v0
     const uint8_t **d_line_ptr = nullptr;
     int32_t *d_chrom_len = nullptr;
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
-    int rc = EXON_GPU_OK;
     auto cleanup = [&]() {
         cudaFree(d_runs);
+        cudaFree(d_marks);
         cudaFree(d_block_rows);
         cudaFree(d_block_row0);
         cudaFree(d_misc);
+        cudaFree(d_small);
         cudaFree((void *)d_line_ptr);
         cudaFree(d_chrom_len);
         cudaFree(d_tmp);
@@ -420,7 +478,6 @@ int build_columns(VcfStream *s) {
     for (int r = 0; r < n_runs; ++r) h_runs[(size_t)r].row0 = (int64_t)h_row0[(size_t)r];
     TRY_OR_CLEAN(cudaMemcpyAsync(d_runs, h_runs.data(), sizeof(RunDesc) * (size_t)n_runs, cudaMemcpyHostToDevice, st));
     c->n_rows = n_rows;
-    c->n_batches = (n_rows + c->batch_rows - 1) / c->batch_rows;
     if (n_rows == 0) {
         cleanup();
         return EXON_GPU_OK;
@@ -430,6 +487,35 @@ int build_columns(VcfStream *s) {
     index_lines<<<grid_blocks, kThreads, 0, st>>>(d_runs, n_runs, n_blocks, d_block_row0, d_line_ptr);
     ctx->launches.fetch_add(1);
     TRY_OR_CLEAN(cudaGetLastError());
+
+    // ---- file table -> batch table (batches restart at every file) ----
+    std::vector<long long> file_row0{0};
+    if (n_marks) {
+        TRY_OR_CLEAN(cudaMalloc((void **)&d_marks, sizeof(MarkDesc) * (size_t)n_marks));
+        TRY_OR_CLEAN(cudaMalloc((void **)&d_small, sizeof(long long) * (size_t)n_marks));
+        TRY_OR_CLEAN(cudaMemcpyAsync(d_marks, h_marks.data(), sizeof(MarkDesc) * (size_t)n_marks, cudaMemcpyHostToDevice, st));
+        mark_rows<<<(n_marks + 127) / 128, 128, 0, st>>>(d_runs, n_runs, d_marks, n_marks, d_line_ptr, n_rows, d_small);
+        ctx->launches.fetch_add(1);
+        TRY_OR_CLEAN(cudaGetLastError());
+        std::vector<long long> h_mark_rows((size_t)n_marks);
+        TRY_OR_CLEAN(cudaMemcpyAsync(h_mark_rows.data(), d_small, sizeof(long long) * (size_t)n_marks, cudaMemcpyDeviceToHost, st));
+        TRY_OR_CLEAN(cudaStreamSynchronize(st));
+        TRY_OR_CLEAN(cudaFree(d_small));
+        d_small = nullptr;
+        for (long long r : h_mark_rows)
+            if (r > file_row0.back() && r < n_rows) file_row0.push_back(r);
+    }
+    file_row0.push_back(n_rows);
+    const int n_files = (int)file_row0.size() - 1;
+    std::vector<long long> file_batch0((size_t)n_files + 1, 0);
+    c->batch_row0.clear();
+    for (int f = 0; f < n_files; ++f) {
+        file_batch0[(size_t)f] = (long long)c->batch_row0.size();
+        for (long long r = file_row0[(size_t)f]; r < file_row0[(size_t)f + 1]; r += c->batch_rows) c->batch_row0.push_back(r);
+    }
+    file_batch0[(size_t)n_files] = (long long)c->batch_row0.size();
+    c->n_batches = (int64_t)c->batch_row0.size();
+    c->batch_row0.push_back(n_rows);
 
     if (c->want_chrom) TRY_OR_CLEAN(cudaMalloc((void **)&d_chrom_len, sizeof(int32_t) * (size_t)(n_rows + 1)));
     if (c->want_pos) TRY_OR_CLEAN(cudaMalloc((void **)&c->d_pos, sizeof(int64_t) * (size_t)n_rows));
@@ -442,6 +528,7 @@ int build_columns(VcfStream *s) {
     TRY_OR_CLEAN(cudaGetLastError());
 
     long long total_values = 0;
+    long long *d_file_row0 = nullptr, *d_file_batch0 = nullptr, *d_batch_row0 = nullptr, *d_batch_v0 = nullptr;
     if (c->want_chrom) {
         TRY_OR_CLEAN(cudaMemsetAsync(d_chrom_len + n_rows, 0, sizeof(int32_t), st));
         TRY_OR_CLEAN(cudaMalloc((void **)&c->d_voff, sizeof(long long) * (size_t)(n_rows + 1)));
@@ -454,13 +541,21 @@ int build_columns(VcfStream *s) {
         }
         TRY_OR_CLEAN(cub::DeviceScan::ExclusiveScan(d_tmp, tmp_bytes, d_chrom_len, c->d_voff, cub::Sum(), 0ll, (int)(n_rows + 1), st));
         ctx->launches.fetch_add(1);
-        // values offset of every batch start (planning data for slicing)
-        c->batch_v0.resize((size_t)c->n_batches + 1);
-        for (int64_t b = 0; b < c->n_batches; ++b)
-            TRY_OR_CLEAN(cudaMemcpyAsync(&c->batch_v0[(size_t)b], c->d_voff + b * c->batch_rows, sizeof(long long),
-                                         cudaMemcpyDeviceToHost, st));
-        TRY_OR_CLEAN(cudaMemcpyAsync(&c->batch_v0[(size_t)c->n_batches], c->d_voff + n_rows, sizeof(long long),
-                                     cudaMemcpyDeviceToHost, st));
+        // planning tables on the device: file_row0 | file_batch0 | batch_row0 | batch_v0
+        const size_t nf = (size_t)n_files + 1, nb = (size_t)c->n_batches + 1;
+        TRY_OR_CLEAN(cudaMalloc((void **)&d_small, sizeof(long long) * (2 * nf + 2 * nb)));
+        d_file_row0 = d_small;
+        d_file_batch0 = d_small + nf;
+        d_batch_row0 = d_small + 2 * nf;
+        d_batch_v0 = d_small + 2 * nf + nb;
+        TRY_OR_CLEAN(cudaMemcpyAsync(d_file_row0, file_row0.data(), sizeof(long long) * nf, cudaMemcpyHostToDevice, st));
+        TRY_OR_CLEAN(cudaMemcpyAsync(d_file_batch0, file_batch0.data(), sizeof(long long) * nf, cudaMemcpyHostToDevice, st));
+        TRY_OR_CLEAN(cudaMemcpyAsync(d_batch_row0, c->batch_row0.data(), sizeof(long long) * nb, cudaMemcpyHostToDevice, st));
+        gather_i64<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(c->d_voff, d_batch_row0, (int64_t)nb, d_batch_v0);
+        ctx->launches.fetch_add(1);
+        TRY_OR_CLEAN(cudaGetLastError());
+        c->batch_v0.resize(nb);
+        TRY_OR_CLEAN(cudaMemcpyAsync(c->batch_v0.data(), d_batch_v0, sizeof(long long) * nb, cudaMemcpyDeviceToHost, st));
     }
     unsigned long long h_misc[4];
     TRY_OR_CLEAN(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
@@ -482,8 +577,8 @@ int build_columns(VcfStream *s) {
         }
         TRY_OR_CLEAN(cudaMalloc((void **)&c->d_values, (size_t)std::max<long long>(total_values, 1)));
         TRY_OR_CLEAN(cudaMalloc((void **)&c->d_offsets, sizeof(int32_t) * (size_t)(c->n_batches * (c->batch_rows + 1))));
-        gather_chrom<<<row_grid, kThreads, 0, st>>>(n_rows, c->batch_rows, d_line_ptr, d_chrom_len, c->d_voff, c->d_values,
-                                                    c->d_offsets);
+        gather_chrom<<<row_grid, kThreads, 0, st>>>(n_rows, c->batch_rows, n_files, d_file_row0, d_file_batch0, d_line_ptr,
+                                                    d_chrom_len, c->d_voff, c->d_values, c->d_offsets);
         ctx->launches.fetch_add(1);
         TRY_OR_CLEAN(cudaGetLastError());
     }
@@ -502,7 +597,7 @@ int build_columns(VcfStream *s) {
     }
     TRY_OR_CLEAN(cudaStreamSynchronize(st));
     cleanup();
-    return rc;
+    return EXON_GPU_OK;
 #undef TRY_OR_CLEAN
 }
 
@@ -523,8 +618,8 @@ int columns_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     memset(out, 0, sizeof(*out));
     if (c->next >= c->n_batches) return EXON_GPU_OK;  // end of stream: release == NULL
     const int64_t b = c->next++;
-    const int64_t row0 = b * c->batch_rows;
-    const int64_t rows = std::min<int64_t>(c->batch_rows, c->n_rows - row0);
+    const int64_t row0 = c->batch_row0[(size_t)b];
+    const int64_t rows = c->batch_row0[(size_t)b + 1] - row0;
     auto *p = new BatchPriv();
     p->cols = c;
     c->refs.fetch_add(1);

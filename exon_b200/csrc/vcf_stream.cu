@@ -52,6 +52,7 @@ void VcfStream::release_all() {
     for (auto &b : blocks) ctx->put_block(b);
     blocks.clear();
     runs.clear();
+    file_marks.clear();
     cur_run_open = false;
     tail_len = 0;
     body_bytes = 0;
@@ -107,6 +108,7 @@ int VcfStream::end_file() {
         if (int rc = append_host(&nl, 1)) return rc;
         body_bytes = before;
     }
+    if (!runs.empty()) file_marks.push_back(FileMark{runs.size() - 1, runs.back().len});
     hdr = kAtLineStart;
     file_open = false;
     return EXON_GPU_OK;
@@ -174,6 +176,7 @@ int VcfStream::feed_device(const uint8_t *text, size_t len, bool is_last) {
         segs_dirty = true;
     }
     if (is_last) {
+        if (!runs.empty()) file_marks.push_back(FileMark{runs.size() - 1, runs.back().len});
         hdr = kAtLineStart;
         file_open = false;
     }
@@ -307,6 +310,7 @@ int VcfStream::filter_count(const exon_gpu_region *region, int64_t *device_out, 
         r.chrom.clear();
     }
     const bool eager = has_pushdown && same_region(r, pushdown);
+    last_eager = eager;
     unsigned long long *d_count = d_res, *d_flags = d_res + 1;
     if (eager) {
         if (int rc = eager_scan(true)) return rc;
@@ -332,6 +336,24 @@ int VcfStream::filter_count(const exon_gpu_region *region, int64_t *device_out, 
         return fail(EXON_GPU_ERR_PARSE, "malformed VCF record:%s%s", (flags & kErrBadPos) ? " POS is not a positive decimal integer;" : "",
                     (flags & kErrShortLine) ? " line ended before the field being read;" : "");
     *host_out = (int64_t)h_res[0];
+    return EXON_GPU_OK;
+}
+
+int VcfStream::filter_count_global(const exon_gpu_region *region, int64_t *out_local, int64_t *out_global) {
+    int64_t *d_local = reinterpret_cast<int64_t *>(d_res + 4), *d_global = reinterpret_cast<int64_t *>(d_res + 5);
+    const int rc = filter_count(region, d_local, nullptr);
+    if (rc != EXON_GPU_OK) CUDA_TRY(cudaMemsetAsync(d_local, 0, sizeof(int64_t), ctx->stream));  // still take part
+    CUDA_TRY(cudaMemcpyAsync(d_global, d_local, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (int rc2 = nccl_allreduce_i64(ctx, d_global, 1)) return rc2;
+    CUDA_TRY(cudaMemcpyAsync(h_res, d_res, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (rc != EXON_GPU_OK) return rc;
+    const uint32_t flags = (uint32_t)h_res[last_eager ? 3 : 1];
+    if (flags)
+        return fail(EXON_GPU_ERR_PARSE, "malformed VCF record:%s%s", (flags & kErrBadPos) ? " POS is not a positive decimal integer;" : "",
+                    (flags & kErrShortLine) ? " line ended before the field being read;" : "");
+    if (out_local) *out_local = (int64_t)h_res[4];
+    if (out_global) *out_global = (int64_t)h_res[5];
     return EXON_GPU_OK;
 }
 

@@ -223,6 +223,13 @@ class VcfStream:
                                                  C.byref(out)))
         return out.value
 
+    def filter_count_global(self, region: "_abi.Region | None" = None):
+        """(local, global) counts; collective over the context's NCCL communicator."""
+        loc, glob = C.c_int64(), C.c_int64()
+        check(self.lib.exon_gpu_vcf_filter_count_global(self.handle, C.byref(region) if region is not None else None,
+                                                        C.byref(loc), C.byref(glob)))
+        return loc.value, glob.value
+
     def filter_count_async(self, region, device_out_ptr: int):
         check(self.lib.exon_gpu_vcf_filter_count_async(self.handle, C.byref(region) if region is not None else None,
                                                        C.c_void_p(device_out_ptr)))

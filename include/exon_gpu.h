@@ -208,6 +208,12 @@ int exon_gpu_filter_agg(exon_gpu_ctx *ctx, const struct ArrowArray *batch, const
 int exon_gpu_nccl_unique_id(uint8_t id[EXON_GPU_NCCL_ID_BYTES]);
 int exon_gpu_nccl_init(exon_gpu_ctx *ctx, const uint8_t id[EXON_GPU_NCCL_ID_BYTES], int n_ranks, int rank);
 int exon_gpu_allreduce_partial(exon_gpu_ctx *ctx, exon_gpu_partial *inout);
+/* AggregateExec(Partial) -> CoalescePartitionsExec -> AggregateExec(Final) for the fused COUNT in one call: the
+ * local scan leaves its int64 partial in device memory, one ncclAllReduce(sum, int64, 1) runs on the same CUDA
+ * stream, and both the local and the global count come back with a single synchronisation.  Collective: every
+ * rank of the communicator must call it (a rank whose input is malformed still takes part, then fails). */
+int exon_gpu_vcf_filter_count_global(exon_gpu_stream *s, const exon_gpu_region *region, int64_t *out_local,
+                                     int64_t *out_global);
 
 #ifdef __cplusplus
 }
