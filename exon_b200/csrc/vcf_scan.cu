@@ -8,20 +8,26 @@
 //
 // Execution model (B200): persistent grid, every WARP runs its own S-stage pipeline.  Lane 0 posts 1-D bulk
 // async copies (cp.async.bulk -> TMA engine, SASS UBLKCP) of [16 B pre-halo | tile | 48 B post-halo] into the
-// warp's shared-memory ring and arms an mbarrier with the byte count; all lanes wait on the barrier, read
-// their 16-byte chunks with conflict-free LDS.128, and test them with SWAR integer ops.  No block-wide
-// barrier exists anywhere in the kernel, so a warp that falls into the (rare) slow path never stalls its
-// neighbours.  Tiles are numbered launch-wide across all resident segments (shard bodies) and dealt
-// round-robin to warps, so one launch covers a whole partition's file group.
+// warp's shared-memory ring and arms an mbarrier with the byte count; all lanes wait on the barrier and read
+// their 16-byte chunks with conflict-free LDS.128.  No block-wide barrier exists anywhere in the kernel.
+// Tiles are numbered launch-wide across all resident segments (shard bodies) and dealt round-robin to warps,
+// so one launch covers a whole partition's file group.
 //
-// Fast path: a record can only satisfy `chrom = lit` if the bytes "\n" lit "\t" occur in the text, so the
-// hot loop is a multi-byte pattern search, not a line parser:
-//   chrom of 1 byte  -> 3-byte pattern: z = (w ^ NL) | (w>>8 ^ C) | (w>>16 ^ TAB) per 32-bit word (byte-shifted
-//                       windows via funnel shifts); a zero byte in z marks a hit (8 integer ops per word);
-//   chrom >= 2 bytes -> the last 4 pattern bytes are compared as one 32-bit window per byte position
-//                       (SHF + ISETP), the preceding bytes are verified only on a hit.
-// Slow path (hit): verify the full pattern, parse POS digits (Rust usize::from_str rules), range-test, count.
-// Dense modes (no chrom literal, or strict validation) visit every line start instead.
+// The kernel is instruction-issue bound, not latency bound (ncu: profiles/), so everything on the per-chunk
+// path is SWAR on 32-bit words with no per-byte loops:
+//   * line starts: exact '\n' flags per word (4 ops), packed into a 16-bit mask with two IDP.4A per 8 bytes;
+//   * a line is parsed by ONE lane from a 16-byte window fetched at the line start (5 LDS.32 + 4 funnel
+//     shifts): separator flags -> positions of the first two tabs; CHROM compared as masked words; the POS
+//     digits are re-fetched right-aligned (12 bytes ending at the second tab), validated and converted with
+//     IDP.4A (4 digits per 3 ops); `lo <= pos <= hi` is one 64-bit unsigned compare;
+//   * anything unusual (a field that does not fit the window, '+', > 12 digits, POS 0, a short line, a tile
+//     that touches a segment boundary) falls back to the byte-exact scalar routines below, which also own
+//     all error reporting.
+// Lazy modes (a chrom literal, not strict): a record can only satisfy `chrom = lit` if the bytes
+// '\n' lit '\t' occur in the text, so chunks are first screened with a 3-byte SWAR pattern test (1-byte names)
+// or a 4-byte window compare (longer names); only screened chunks run the line parser, and POS is parsed
+// only for rows whose CHROM matches -- the lazy-record behaviour of noodles, taken one step further.
+// Dense mode (strict, or no chrom literal) parses and validates every line.
 #include "vcf_scan.cuh"
 
 #include "common.cuh"
@@ -30,9 +36,12 @@ namespace exon {
 
 namespace {
 
-constexpr int kPre = 16;   // bytes staged before the tile (pattern bytes that precede the anchor)
-constexpr int kHalo = 48;  // bytes staged after the tile (window overhang + POS digits)
+constexpr int kPre = 16;   // bytes staged before the tile (right-aligned POS fetch may reach back 12 bytes)
+constexpr int kHalo = 48;  // bytes staged after the tile (line window + POS digits of a line that starts at the end)
 
+// ===================================================================================================
+// Byte-exact scalar routines (boundary tiles, unusual records, all error reporting)
+// ===================================================================================================
 struct TileView {
     const uint8_t *sm;  // shared-memory address of tile byte 0
     const uint8_t *g;   // global address of tile byte 0
@@ -81,24 +90,20 @@ __device__ __forceinline__ uint32_t test_pos(const TileView &t, int d, const Sca
     return (p >= a.lo) & (p <= a.hi);
 }
 
-// A candidate whose pattern ('\n' + chrom + '\t') starts at index q (the '\n').
-__device__ __forceinline__ uint32_t candidate(const TileView &t, int q, const ScanArgs &a, uint32_t &err) {
-    if (q < t.lo) return 0;  // the segment's first line has no real '\n' before it; handled by first_line()
-    for (int j = 0; j < a.pat_len; ++j)
-        if (ld_byte(t, q + j) != a.pat[j]) return 0;
-    if (!a.has_interval) return 1;
-    return test_pos(t, q + a.pat_len, a, err);
-}
-
-// Full treatment of the line starting at index ls: chrom compare (if any), POS validation, predicate.
-__device__ __forceinline__ uint32_t dense_line(const TileView &t, int ls, const ScanArgs &a, uint32_t &err) {
+// Full treatment of the line starting at index ls.  LAZY: the row is validated only as far as the predicate
+// reads it (CHROM first; POS only if CHROM matches and an interval is asked for).  Otherwise CHROM must be
+// non-empty and POS valid on every row.
+template <bool LAZY>
+__device__ __forceinline__ uint32_t line_scalar(const TileView &t, int ls, const ScanArgs &a, uint32_t &err) {
     bool chrom_ok = true;
     int d = ls;
     if (a.has_chrom) {
         for (int j = 0; j <= a.chrom_len; ++j)
             if (ld_byte(t, ls + j) != a.pat[1 + j]) { chrom_ok = false; break; }
         if (chrom_ok) d = ls + a.chrom_len + 1;
+        if (LAZY && !chrom_ok) return 0;
     }
+    if (LAZY && !a.has_interval) return 1;
     if (!chrom_ok || !a.has_chrom) {
         uint32_t c;
         while ((c = ld_byte(t, d)) != '\t') {
@@ -112,17 +117,119 @@ __device__ __forceinline__ uint32_t dense_line(const TileView &t, int ls, const 
     return chrom_ok ? (a.has_interval ? r : 1u) : 0u;
 }
 
-// First line of a segment in the key modes (validated only if its chrom matches, like every other line there).
-__device__ __forceinline__ uint32_t first_line(const TileView &t, int ls, const ScanArgs &a, uint32_t &err) {
-    for (int j = 0; j <= a.chrom_len; ++j)
-        if (ld_byte(t, ls + j) != a.pat[1 + j]) return 0;
-    if (!a.has_interval) return 1;
-    return test_pos(t, ls + a.chrom_len + 1, a, err);
+template <bool LAZY>
+__device__ __noinline__ unsigned long long line_exact(const uint8_t *sm, const uint8_t *g, int lo, int hi, int sm_lo,
+                                                      int sm_hi, int ls, const ScanArgs *ap) {
+    TileView t{sm, g, lo, hi, sm_lo, sm_hi};
+    uint32_t err = 0;
+    const uint32_t cnt = line_scalar<LAZY>(t, ls, *ap, err);
+    return (unsigned long long)cnt | ((unsigned long long)err << 32);
 }
 
-// ---- per-chunk tests -----------------------------------------------------------------------------------
-// Fast test of one 16-byte chunk (words w.x..w.w plus the following word w4): non-zero iff the chunk MAY
-// contain a pattern anchor.  Fully unrolled, registers only.
+// Careful treatment of one 16-byte chunk of a boundary tile: every '\n' inside the segment whose successor
+// byte is also inside the segment starts a line.  Returns count | (error bits << 32).
+template <int MODE>
+__device__ __noinline__ unsigned long long chunk_careful(const uint8_t *sm, const uint8_t *g, int lo, int hi, int sm_lo,
+                                                         int sm_hi, int c0, const ScanArgs *ap) {
+    constexpr bool LAZY = (MODE == kScanKey3 || MODE == kScanKey4);
+    TileView t{sm, g, lo, hi, sm_lo, sm_hi};
+    uint32_t cnt = 0, err = 0;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        uint32_t f = zero_bytes_exact(*reinterpret_cast<const uint32_t *>(sm + c0 + 4 * k) ^ kNL4);
+        while (f) {
+            const int j = (__ffs(f) - 1) >> 3;
+            f &= f - 1;
+            const int p = c0 + 4 * k + j;  // position of the '\n'
+            if (p < lo || p + 1 >= hi) continue;
+            if (MODE == kScanLines) cnt += 1;
+            else cnt += line_scalar<LAZY>(t, p + 1, *ap, err);
+        }
+    }
+    return (unsigned long long)cnt | ((unsigned long long)err << 32);
+}
+
+// ===================================================================================================
+// SWAR line parser (interior tiles: every byte of the staged window belongs to the segment)
+// ===================================================================================================
+struct LineConsts {
+    uint32_t P[4], M[4];  // (window ^ P) & M == 0  <=>  window starts with chrom + '\t'
+    uint32_t lo_lo, lo_hi, span_lo, span_hi;  // pos in [lo, lo + span]
+    int has_chrom, has_interval, wide_chrom;  // wide_chrom: the pattern reaches into window words 2..3
+};
+
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t s) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));  // shift amounts >= 32 give 0
+    return r;
+}
+
+// 0x80 flags in up to 16 bytes -> 16-bit mask, bit i = byte i flagged (IDP.4A: sum of flag * weight, flags are 128)
+__device__ __forceinline__ uint32_t pack16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    uint32_t a = __dp4a(f0, 0x08040201u, 0u);
+    a = __dp4a(f1, 0x80402010u, a);
+    uint32_t b = __dp4a(f2, 0x08040201u, 0u);
+    b = __dp4a(f3, 0x80402010u, b);
+    return (a >> 7) | (b << 1);
+}
+
+// Parses the line whose first byte is sm[ls].  Returns the predicate (0/1); sets `slow` when the line needs
+// the scalar routine instead (nothing has been decided or reported then).
+template <bool LAZY>
+__device__ __forceinline__ uint32_t line_swar(const uint8_t *sm, int ls, const LineConsts &K, bool &slow) {
+    const int a0 = ls & ~3;
+    const uint32_t sh = (uint32_t)(ls & 3) << 3;
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(sm + a0);
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+    const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh),
+                   v3 = __funnelshift_r(w3, w4, sh);
+    bool chrom_ok = true;
+    if (K.has_chrom) {
+        uint32_t d = ((v0 ^ K.P[0]) & K.M[0]) | ((v1 ^ K.P[1]) & K.M[1]);
+        if (K.wide_chrom) d |= ((v2 ^ K.P[2]) & K.M[2]) | ((v3 ^ K.P[3]) & K.M[3]);
+        chrom_ok = d == 0;
+        if (LAZY && !chrom_ok) return 0;
+    }
+    if (LAZY && !K.has_interval) return 1;
+    // separators: bytes 0x08..0x0B ('\t', '\n' and two controls that are re-checked below)
+    const uint32_t m = pack16(zero_bytes_exact((v0 & 0xFCFCFCFCu) ^ 0x08080808u), zero_bytes_exact((v1 & 0xFCFCFCFCu) ^ 0x08080808u),
+                              zero_bytes_exact((v2 & 0xFCFCFCFCu) ^ 0x08080808u), zero_bytes_exact((v3 & 0xFCFCFCFCu) ^ 0x08080808u));
+    const uint32_t m2 = m & (m - 1);
+    const int s1 = __ffs(m) - 1, s2 = __ffs(m2) - 1;
+    const int n = s2 - s1 - 1;  // digits of POS
+    if (m2 == 0 || s1 < 1 || n < 1 || n > 12 || sm[ls + s1] != '\t' || sm[ls + s2] != '\t') {
+        slow = true;
+        return 0;
+    }
+    // the 12 bytes that end right before the second tab; the first 12 - n of them are not POS
+    const int b = ls + s2 - 12;
+    const int b0 = b & ~3;
+    const uint32_t sh2 = (uint32_t)(b & 3) << 3;
+    const uint32_t *xp = reinterpret_cast<const uint32_t *>(sm + b0);
+    const uint32_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+    const uint32_t s = (uint32_t)(12 - n) << 3;
+    const uint32_t d0 = (__funnelshift_r(x0, x1, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s);
+    const uint32_t d1 = (__funnelshift_r(x1, x2, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s > 32u ? s - 32u : 0u);
+    const uint32_t d2 = (__funnelshift_r(x2, x3, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s > 64u ? s - 64u : 0u);
+    // every kept byte must be 0..9
+    const uint32_t bad = ((d0 + 0x76767676u) | d0 | (d1 + 0x76767676u) | d1 | (d2 + 0x76767676u) | d2) & 0x80808080u;
+    // 4 digits per word, most significant in byte 0
+    const uint32_t q0 = __dp4a(d0, 0x00010A64u, 0u) * 10u + (d0 >> 24);
+    const uint32_t q1 = __dp4a(d1, 0x00010A64u, 0u) * 10u + (d1 >> 24);
+    const uint32_t q2 = __dp4a(d2, 0x00010A64u, 0u) * 10u + (d2 >> 24);
+    const unsigned long long v = (unsigned long long)(q0 * 10000u + q1) * 10000ull + q2;
+    if (bad || v == 0ull) {
+        slow = true;  // '+', a non-digit, or POS 0: the scalar routine decides and reports
+        return 0;
+    }
+    const unsigned long long lo = ((unsigned long long)K.lo_hi << 32) | K.lo_lo;
+    const unsigned long long span = ((unsigned long long)K.span_hi << 32) | K.span_lo;
+    const uint32_t in = (v - lo) <= span;
+    return chrom_ok ? (K.has_interval ? in : 1u) : 0u;
+}
+
+// Screens one 16-byte chunk (words w.x..w.w plus the following word w4): non-zero iff the chunk MAY contain
+// the start of the pattern '\n' chrom '\t'.
 template <int MODE>
 __device__ __forceinline__ uint32_t chunk_may_hit(const uint4 w, const uint32_t w4, const uint32_t key,
                                                   const uint32_t c4) {
@@ -149,68 +256,12 @@ __device__ __forceinline__ uint32_t chunk_may_hit(const uint4 w, const uint32_t 
     }
 }
 
-// Exact treatment of one chunk (cold for the key modes; the whole story for the dense modes).  Re-reads the
-// chunk from shared memory so the hot loop keeps no indexable register array alive.
-// Returns count | (error bits << 32).
-template <int MODE>
-__device__ __noinline__ unsigned long long chunk_exact(const uint8_t *sm, const uint8_t *g, int lo, int hi, int sm_lo,
-                                                       int sm_hi, int c0, const ScanArgs *ap, uint32_t key,
-                                                       uint32_t c4) {
-    const ScanArgs &a = *ap;
-    TileView t{sm, g, lo, hi, sm_lo, sm_hi};
-    uint32_t cnt = 0, err = 0;
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t w0 = *reinterpret_cast<const uint32_t *>(sm + c0 + 4 * k);
-        const uint32_t w1 = *reinterpret_cast<const uint32_t *>(sm + c0 + 4 * k + 4);
-        if (MODE == kScanKey3) {
-            const uint32_t z = (w0 ^ kNL4) | (__funnelshift_r(w0, w1, 8) ^ c4) | (__funnelshift_r(w0, w1, 16) ^ kTAB4);
-            uint32_t f = zero_bytes_exact(z);
-            while (f) {
-                const int j = (__ffs(f) - 1) >> 3;
-                f &= f - 1;
-                cnt += candidate(t, c0 + 4 * k + j, a, err);
-            }
-        } else if (MODE == kScanKey4) {
-            const int back = a.pat_len - 4;  // pattern bytes that precede the 4-byte key
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t x = b ? __funnelshift_r(w0, w1, 8 * b) : w0;
-                if (x == key) cnt += candidate(t, c0 + 4 * k + b - back, a, err);
-            }
-        } else if (MODE == kScanDense) {
-            uint32_t f = zero_bytes_exact(w0 ^ kNL4);
-            while (f) {
-                const int j = (__ffs(f) - 1) >> 3;
-                f &= f - 1;
-                const int ls = c0 + 4 * k + j + 1;
-                if (ls > lo && ls < hi) cnt += dense_line(t, ls, a, err);
-            }
-        } else {  // kScanLines, ragged end of a segment: a '\n' that is the last byte starts no line
-            uint32_t f = zero_bytes_exact(w0 ^ kNL4);
-            while (f) {
-                const int j = (__ffs(f) - 1) >> 3;
-                f &= f - 1;
-                const int ls = c0 + 4 * k + j + 1;
-                cnt += (ls > lo && ls < hi);
-            }
-        }
-    }
-    return (unsigned long long)cnt | ((unsigned long long)err << 32);
-}
-
-template <int MODE>
-__device__ __noinline__ unsigned long long first_line_exact(const uint8_t *sm, const uint8_t *g, int lo, int hi,
-                                                            int sm_hi, const ScanArgs *ap) {
-    TileView t{sm, g, lo, hi, 0, sm_hi};
-    uint32_t err = 0, cnt;
-    if (MODE == kScanDense) cnt = dense_line(t, lo, *ap, err);
-    else cnt = first_line(t, lo, *ap, err);
-    return (unsigned long long)cnt | ((unsigned long long)err << 32);
-}
-
+// ===================================================================================================
+// The kernel
+// ===================================================================================================
 template <int MODE, int U, int S, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_constant__ ScanArgs a) {
+    constexpr bool LAZY = (MODE == kScanKey3 || MODE == kScanKey4);
     constexpr int TILE = 512 * U;
     constexpr int STAGE = ((kPre + TILE + kHalo + 127) / 128) * 128;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -228,93 +279,158 @@ __global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_const
     const int64_t nw = (int64_t)gridDim.x * WARPS;
     const int64_t wg = (int64_t)blockIdx.x * WARPS + warp;
 
-    // pattern constants
+    // ---- per-launch constants ----
     uint32_t key = 0, c4 = 0;
     if (MODE == kScanKey3) c4 = 0x01010101u * a.pat[1];
-    if (MODE == kScanKey4)
-        key = (uint32_t)a.pat[a.pat_len - 4] | ((uint32_t)a.pat[a.pat_len - 3] << 8) |
-              ((uint32_t)a.pat[a.pat_len - 2] << 16) | ((uint32_t)a.pat[a.pat_len - 1] << 24);
+    if (MODE == kScanKey4) key = (uint32_t)a.pat[0] | ((uint32_t)a.pat[1] << 8) | ((uint32_t)a.pat[2] << 16) | ((uint32_t)a.pat[3] << 24);
+    LineConsts K;
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t p = 0, m = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = 4 * k + j;
+                if (a.has_chrom && i <= a.chrom_len && a.chrom_len <= 14) {
+                    p |= (uint32_t)a.pat[1 + i] << (8 * j);
+                    m |= 0xFFu << (8 * j);
+                }
+            }
+            K.P[k] = p;
+            K.M[k] = m;
+        }
+        unsigned long long lo = (unsigned long long)(a.lo < 1 ? 1 : a.lo);  // every valid POS is >= 1
+        unsigned long long span = (unsigned long long)a.hi - lo;
+        if (a.hi < (long long)lo) {  // empty interval: (v - lo) <= span must never hold
+            lo = ~0ull;
+            span = 0;
+        }
+        K.lo_lo = (uint32_t)lo;
+        K.lo_hi = (uint32_t)(lo >> 32);
+        K.span_lo = (uint32_t)span;
+        K.span_hi = (uint32_t)(span >> 32);
+        K.has_chrom = a.has_chrom;
+        K.has_interval = a.has_interval;
+        K.wide_chrom = a.chrom_len > 6;
+    }
+    const bool swar_ok = !a.has_chrom || a.chrom_len <= 14;  // longer names do not fit the 16-byte window
 
-    int pc = 0;  // producer's segment cursor
+    // ---- producer: one cursor over the segment table, S tiles ahead of the consumer ----
+    int pc = 0;
+    int64_t p_tile0 = __ldg(&a.segs[0].tile0), p_next0 = __ldg(&a.segs[1].tile0);
+    // per-stage metadata captured when the tile is issued (registers: the stage loop is unrolled)
+    const uint8_t *m_g[S];
+    int m_lo[S], m_hi[S];
     auto issue = [&](int64_t T, int s) {
-        while (T >= __ldg(&a.segs[pc + 1].tile0)) ++pc;
+        while (T >= p_next0) {
+            ++pc;
+            p_tile0 = p_next0;
+            p_next0 = __ldg(&a.segs[pc + 1].tile0);
+        }
+        const uint8_t *base = a.segs[pc].base;
+        const int skip = __ldg(&a.segs[pc].skip);
+        const int64_t off = (T - p_tile0) * TILE;
+        const int64_t rem = skip + __ldg(&a.segs[pc].len) - off;
+        const int pre = off ? kPre : 0;
+        const int64_t body = (rem + 15) & ~(int64_t)15;
+        const uint32_t bytes = (uint32_t)(body < TILE + kHalo ? body : TILE + kHalo) + pre;
         if (lane == 0) {
-            const uint8_t *base = a.segs[pc].base;
-            const int64_t off = (T - __ldg(&a.segs[pc].tile0)) * TILE;
-            const int64_t rem = __ldg(&a.segs[pc].skip) + __ldg(&a.segs[pc].len) - off;
-            const int pre = off ? kPre : 0;
-            const int64_t body = (rem + 15) & ~(int64_t)15;
-            const uint32_t bytes = (uint32_t)(body < TILE + kHalo ? body : TILE + kHalo) + pre;
             mbar_arrive_expect_tx(&bars[s], bytes);
             bulk_g2s(ring + s * STAGE + (kPre - pre), base + off - pre, bytes, &bars[s]);
         }
+        m_g[s] = base + off;
+        m_lo[s] = off ? -kPre : skip;  // index of the first byte that is both staged and inside the segment
+        m_hi[s] = rem > (1 << 30) ? (1 << 30) : (int)rem;
     };
 
-#pragma unroll 1
+#pragma unroll
     for (int s = 0; s < S; ++s) {
         const int64_t T = wg + s * nw;
+        m_g[s] = nullptr;
+        m_lo[s] = m_hi[s] = 0;
         if (T < a.n_tiles) issue(T, s);
     }
 
-    uint32_t cnt = 0, err = 0;
-    int cc = 0;  // consumer's segment cursor
-    int s = 0;
+    uint32_t cnt = 0, err = 0, nl128 = 0;
     uint32_t parity = 0;
 #pragma unroll 1
-    for (int64_t T = wg; T < a.n_tiles; T += nw) {
-        while (T >= __ldg(&a.segs[cc + 1].tile0)) ++cc;
-        const int64_t off = (T - __ldg(&a.segs[cc].tile0)) * TILE;
-        const int skip = __ldg(&a.segs[cc].skip);
-        const int64_t rem = skip + __ldg(&a.segs[cc].len) - off;
-        const uint8_t *sm = ring + s * STAGE + kPre;
-        const uint8_t *g = a.segs[cc].base + off;
-        const int lo = off ? (off > (1 << 30) ? -(1 << 30) : skip - (int)off) : skip;
-        const int hi = rem > (1 << 30) ? (1 << 30) : (int)rem;
-        const int sm_lo = off ? -kPre : 0;
-        const int64_t body = (rem + 15) & ~(int64_t)15;
-        const int sm_hi = (int)(body < TILE + kHalo ? body : TILE + kHalo);
-
-        mbar_wait(&bars[s], parity);
-
-        if (off == 0 && lane == 0 && hi > lo) {
-            if (MODE == kScanLines) {
-                cnt += 1;
-            } else {
-                const unsigned long long r = first_line_exact<MODE>(sm, g, lo, hi, sm_hi, &a);
-                cnt += (uint32_t)r;
-                err |= (uint32_t)(r >> 32);
-            }
-        }
-        const bool full = hi > TILE;  // every chunk (and its successor word) lies inside the segment
+    for (int64_t T0 = wg; T0 < a.n_tiles; T0 += (int64_t)S * nw) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int c0 = (u * 32 + lane) * 16;
-            if (full || c0 < hi) {
-                if (MODE == kScanKey3 || MODE == kScanKey4) {
-                    const uint4 w = *reinterpret_cast<const uint4 *>(sm + c0);
-                    const uint32_t w4 = *reinterpret_cast<const uint32_t *>(sm + c0 + 16);
-                    if (chunk_may_hit<MODE>(w, w4, key, c4)) {
-                        const unsigned long long r = chunk_exact<MODE>(sm, g, lo, hi, sm_lo, sm_hi, c0, &a, key, c4);
-                        cnt += (uint32_t)r;
-                        err |= (uint32_t)(r >> 32);
-                    }
-                } else if (MODE == kScanLines && full && c0 >= lo) {
-                    const uint4 w = *reinterpret_cast<const uint4 *>(sm + c0);
-                    cnt += __popc(zero_bytes_exact(w.x ^ kNL4)) + __popc(zero_bytes_exact(w.y ^ kNL4)) +
-                           __popc(zero_bytes_exact(w.z ^ kNL4)) + __popc(zero_bytes_exact(w.w ^ kNL4));
+        for (int s = 0; s < S; ++s) {
+            const int64_t T = T0 + s * nw;
+            if (T >= a.n_tiles) break;
+            const uint8_t *sm = ring + s * STAGE + kPre;
+            const uint8_t *g = m_g[s];
+            const int lo = m_lo[s], hi = m_hi[s];
+            const bool first = lo >= 0;             // first tile of its segment: line 0 has no '\n' before it
+            const int seg_lo = first ? lo : -(1 << 30);
+            const int sm_lo = first ? 0 : -kPre;
+            const int sm_hi = hi < TILE + kHalo ? ((hi + 15) & ~15) : TILE + kHalo;
+
+            mbar_wait(&bars[s], parity);
+
+            if (first && lane == 0 && hi > lo) {
+                if (MODE == kScanLines) {
+                    cnt += 1;
                 } else {
-                    const unsigned long long r = chunk_exact<MODE>(sm, g, lo, hi, sm_lo, sm_hi, c0, &a, key, c4);
+                    const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, lo, &a);
                     cnt += (uint32_t)r;
                     err |= (uint32_t)(r >> 32);
                 }
             }
+            // interior: the tile starts inside the segment at a 16-byte boundary and every staged byte is segment data
+            const bool interior = hi >= TILE + kHalo && (lo <= 0) && swar_ok;
+            if (interior) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int c0 = (u * 32 + lane) * 16;
+                    const uint4 w = *reinterpret_cast<const uint4 *>(sm + c0);
+                    if (MODE == kScanLines) {
+                        nl128 = __dp4a(zero_bytes_exact(w.x ^ kNL4), 0x01010101u, nl128);
+                        nl128 = __dp4a(zero_bytes_exact(w.y ^ kNL4), 0x01010101u, nl128);
+                        nl128 = __dp4a(zero_bytes_exact(w.z ^ kNL4), 0x01010101u, nl128);
+                        nl128 = __dp4a(zero_bytes_exact(w.w ^ kNL4), 0x01010101u, nl128);
+                        continue;
+                    }
+                    if (LAZY) {
+                        const uint32_t w4 = *reinterpret_cast<const uint32_t *>(sm + c0 + 16);
+                        if (!chunk_may_hit<MODE>(w, w4, key, c4)) continue;
+                    }
+                    const uint32_t f0 = zero_bytes_exact(w.x ^ kNL4), f1 = zero_bytes_exact(w.y ^ kNL4),
+                                   f2 = zero_bytes_exact(w.z ^ kNL4), f3 = zero_bytes_exact(w.w ^ kNL4);
+                    if ((f0 | f1 | f2 | f3) == 0) continue;
+                    uint32_t m = pack16(f0, f1, f2, f3);
+                    do {
+                        const int ls = c0 + __ffs(m);  // '\n' at c0 + ffs - 1, the line starts one byte later
+                        m &= m - 1;
+                        bool slow = false;
+                        cnt += line_swar<LAZY>(sm, ls, K, slow);
+                        if (slow) {
+                            const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, ls, &a);
+                            cnt += (uint32_t)r;
+                            err |= (uint32_t)(r >> 32);
+                        }
+                    } while (m);
+                }
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < U; ++u) {
+                    const int c0 = (u * 32 + lane) * 16;
+                    if (c0 < hi && c0 + 16 > seg_lo) {
+                        const unsigned long long r = chunk_careful<MODE>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0, &a);
+                        cnt += (uint32_t)r;
+                        err |= (uint32_t)(r >> 32);
+                    }
+                }
+            }
+            __syncwarp();
+            const int64_t Tn = T + (int64_t)S * nw;
+            if (Tn < a.n_tiles) issue(Tn, s);
         }
-        __syncwarp();
-        const int64_t Tn = T + (int64_t)S * nw;
-        if (Tn < a.n_tiles) issue(Tn, s);
-        if (++s == S) { s = 0; parity ^= 1; }
+        parity ^= 1;
     }
 
+    if (MODE == kScanLines) cnt += nl128 >> 7;
     cnt = warp_sum(cnt);
     err = __reduce_or_sync(0xFFFFFFFFu, err);
     if (lane == 0) {

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Short driver for ncu captures: uploads the bench workload once and launches the fused scan a few times.
+
+    ncu --set full --clock-control none --import-source on -k regex:vcf_scan -c 6 -o gpurun_out/prof \
+        python tools/prof_run.py [--rows N] [--variant V] [--modes lazy,lazy,strict,count_star,interval]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np  # noqa: E402
+
+from exon_b200 import _abi  # noqa: E402
+from exon_b200.runtime import Context  # noqa: E402
+from synth import vcf  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=100_000_000)
+ap.add_argument("--shards", type=int, default=64)
+ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--modes", default="lazy,lazy,strict,count_star,interval")
+args = ap.parse_args()
+
+cols = vcf.columns(args.rows)
+files = vcf.shards(cols, args.shards)
+region = _abi.make_region("1", 1_000_000, 2_000_000)
+with Context(0) as ctx:
+    dbufs = []
+    lazy = ctx.open_vcf(kernel_variant=args.variant)
+    strict = ctx.open_vcf(kernel_variant=args.variant, strict=True)
+    for f in files:
+        d = ctx.device_buffer(f.size)
+        d.upload(np.ascontiguousarray(f))
+        dbufs.append(d)
+        lazy.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+        strict.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+    for m in args.modes.split(","):
+        if m == "lazy":
+            c = lazy.filter_count(region)
+        elif m == "strict":
+            c = strict.filter_count(region)
+        elif m == "count_star":
+            c = lazy.filter_count(None)
+        elif m == "interval":
+            c = lazy.filter_count(_abi.make_region(None, 1_000_000, 2_000_000))
+        else:
+            raise SystemExit(m)
+        print(m, c, f"{ctx.last_kernel_ms():.3f} ms", flush=True)
+    lazy.close()
+    strict.close()
