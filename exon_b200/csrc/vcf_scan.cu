@@ -259,15 +259,37 @@ __device__ __forceinline__ uint32_t chunk_may_hit(const uint4 w, const uint32_t 
 // ===================================================================================================
 // The kernel
 // ===================================================================================================
+constexpr int kQueue = 256;  // line starts a warp collects before it parses them (uint16 each)
+
+struct StageMeta {
+    const uint8_t *g;  // global address of tile byte 0
+    int lo;            // first tile-relative index that is staged and inside the segment (>= 0: first tile of its segment)
+    int hi;            // bytes from tile byte 0 to the end of the segment (clamped to 2^30)
+};
+
+template <int U, int S, int WARPS>
+struct SmemLayout {
+    static constexpr int TILE = 512 * U;
+    static constexpr int STAGE = ((kPre + TILE + kHalo + 127) / 128) * 128;
+    static constexpr size_t ring = 0;
+    static constexpr size_t bars = (size_t)WARPS * S * STAGE;
+    static constexpr size_t meta = bars + (size_t)WARPS * S * sizeof(uint64_t);
+    static constexpr size_t queue = meta + (size_t)WARPS * S * sizeof(StageMeta);
+    static constexpr size_t total = queue + (size_t)WARPS * kQueue * sizeof(uint16_t);
+};
+
 template <int MODE, int U, int S, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_constant__ ScanArgs a) {
     constexpr bool LAZY = (MODE == kScanKey3 || MODE == kScanKey4);
-    constexpr int TILE = 512 * U;
-    constexpr int STAGE = ((kPre + TILE + kHalo + 127) / 128) * 128;
+    using L = SmemLayout<U, S, WARPS>;
+    constexpr int TILE = L::TILE, STAGE = L::STAGE;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *ring = smem_raw + (size_t)warp * (S * STAGE);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * S * STAGE) + warp * S;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint8_t *ring = smem_raw + L::ring + (size_t)warp * (S * STAGE);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + L::bars) + warp * S;
+    StageMeta *meta = reinterpret_cast<StageMeta *>(smem_raw + L::meta) + warp * S;
+    uint16_t *queue = reinterpret_cast<uint16_t *>(smem_raw + L::queue) + warp * kQueue;
 
     if (lane == 0) {
 #pragma unroll
@@ -315,13 +337,14 @@ __global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_const
     }
     const bool swar_ok = !a.has_chrom || a.chrom_len <= 14;  // longer names do not fit the 16-byte window
 
-    // ---- producer: one cursor over the segment table, S tiles ahead of the consumer ----
+    // ---- producer (lane 0): one cursor over the segment table, S tiles ahead of the consumer ----
     int pc = 0;
-    int64_t p_tile0 = __ldg(&a.segs[0].tile0), p_next0 = __ldg(&a.segs[1].tile0);
-    // per-stage metadata captured when the tile is issued (registers: the stage loop is unrolled)
-    const uint8_t *m_g[S];
-    int m_lo[S], m_hi[S];
-    auto issue = [&](int64_t T, int s) {
+    int64_t p_tile0 = 0, p_next0 = 0;
+    if (lane == 0) {
+        p_tile0 = __ldg(&a.segs[0].tile0);
+        p_next0 = __ldg(&a.segs[1].tile0);
+    }
+    auto issue = [&](int64_t T, int s) {  // lane 0 only
         while (T >= p_next0) {
             ++pc;
             p_tile0 = p_next0;
@@ -334,100 +357,121 @@ __global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_const
         const int pre = off ? kPre : 0;
         const int64_t body = (rem + 15) & ~(int64_t)15;
         const uint32_t bytes = (uint32_t)(body < TILE + kHalo ? body : TILE + kHalo) + pre;
-        if (lane == 0) {
-            mbar_arrive_expect_tx(&bars[s], bytes);
-            bulk_g2s(ring + s * STAGE + (kPre - pre), base + off - pre, bytes, &bars[s]);
-        }
-        m_g[s] = base + off;
-        m_lo[s] = off ? -kPre : skip;  // index of the first byte that is both staged and inside the segment
-        m_hi[s] = rem > (1 << 30) ? (1 << 30) : (int)rem;
+        meta[s].g = base + off;
+        meta[s].lo = off ? -kPre : skip;
+        meta[s].hi = rem > (1 << 30) ? (1 << 30) : (int)rem;
+        mbar_arrive_expect_tx(&bars[s], bytes);
+        bulk_g2s(ring + s * STAGE + (kPre - pre), base + off - pre, bytes, &bars[s]);
     };
 
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        const int64_t T = wg + s * nw;
-        m_g[s] = nullptr;
-        m_lo[s] = m_hi[s] = 0;
-        if (T < a.n_tiles) issue(T, s);
+    if (lane == 0) {
+#pragma unroll 1
+        for (int s = 0; s < S; ++s) {
+            const int64_t T = wg + s * nw;
+            if (T < a.n_tiles) issue(T, s);
+        }
     }
+    __syncwarp();
 
     uint32_t cnt = 0, err = 0, nl128 = 0;
     uint32_t parity = 0;
+    int s = 0;
 #pragma unroll 1
-    for (int64_t T0 = wg; T0 < a.n_tiles; T0 += (int64_t)S * nw) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const int64_t T = T0 + s * nw;
-            if (T >= a.n_tiles) break;
-            const uint8_t *sm = ring + s * STAGE + kPre;
-            const uint8_t *g = m_g[s];
-            const int lo = m_lo[s], hi = m_hi[s];
-            const bool first = lo >= 0;             // first tile of its segment: line 0 has no '\n' before it
-            const int seg_lo = first ? lo : -(1 << 30);
-            const int sm_lo = first ? 0 : -kPre;
-            const int sm_hi = hi < TILE + kHalo ? ((hi + 15) & ~15) : TILE + kHalo;
+    for (int64_t T = wg; T < a.n_tiles; T += nw) {
+        const uint8_t *sm = ring + s * STAGE + kPre;
+        mbar_wait(&bars[s], parity);  // lane 0 wrote meta[s] before it armed the barrier
+        const uint8_t *g = meta[s].g;
+        const int lo = meta[s].lo, hi = meta[s].hi;
+        const bool first = lo >= 0;  // first tile of its segment: line 0 has no '\n' before it
+        const int seg_lo = first ? lo : -(1 << 30);
+        const int sm_lo = first ? 0 : -kPre;
+        const int sm_hi = hi < TILE + kHalo ? ((hi + 15) & ~15) : TILE + kHalo;
 
-            mbar_wait(&bars[s], parity);
-
-            if (first && lane == 0 && hi > lo) {
-                if (MODE == kScanLines) {
-                    cnt += 1;
-                } else {
-                    const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, lo, &a);
-                    cnt += (uint32_t)r;
-                    err |= (uint32_t)(r >> 32);
-                }
-            }
-            // interior: the tile starts inside the segment at a 16-byte boundary and every staged byte is segment data
-            const bool interior = hi >= TILE + kHalo && (lo <= 0) && swar_ok;
-            if (interior) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int c0 = (u * 32 + lane) * 16;
-                    const uint4 w = *reinterpret_cast<const uint4 *>(sm + c0);
-                    if (MODE == kScanLines) {
-                        nl128 = __dp4a(zero_bytes_exact(w.x ^ kNL4), 0x01010101u, nl128);
-                        nl128 = __dp4a(zero_bytes_exact(w.y ^ kNL4), 0x01010101u, nl128);
-                        nl128 = __dp4a(zero_bytes_exact(w.z ^ kNL4), 0x01010101u, nl128);
-                        nl128 = __dp4a(zero_bytes_exact(w.w ^ kNL4), 0x01010101u, nl128);
-                        continue;
-                    }
-                    if (LAZY) {
-                        const uint32_t w4 = *reinterpret_cast<const uint32_t *>(sm + c0 + 16);
-                        if (!chunk_may_hit<MODE>(w, w4, key, c4)) continue;
-                    }
-                    const uint32_t f0 = zero_bytes_exact(w.x ^ kNL4), f1 = zero_bytes_exact(w.y ^ kNL4),
-                                   f2 = zero_bytes_exact(w.z ^ kNL4), f3 = zero_bytes_exact(w.w ^ kNL4);
-                    if ((f0 | f1 | f2 | f3) == 0) continue;
-                    uint32_t m = pack16(f0, f1, f2, f3);
-                    do {
-                        const int ls = c0 + __ffs(m);  // '\n' at c0 + ffs - 1, the line starts one byte later
-                        m &= m - 1;
-                        bool slow = false;
-                        cnt += line_swar<LAZY>(sm, ls, K, slow);
-                        if (slow) {
-                            const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, ls, &a);
-                            cnt += (uint32_t)r;
-                            err |= (uint32_t)(r >> 32);
-                        }
-                    } while (m);
-                }
+        if (first && lane == 0 && hi > lo) {
+            if (MODE == kScanLines) {
+                cnt += 1;
             } else {
+                const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, lo, &a);
+                cnt += (uint32_t)r;
+                err |= (uint32_t)(r >> 32);
+            }
+        }
+        // interior: the tile starts inside the segment at a 16-byte boundary and every staged byte is segment data
+        const bool interior = hi >= TILE + kHalo && (lo <= 0) && swar_ok;
+        if (interior && MODE == kScanLines) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint4 w = *reinterpret_cast<const uint4 *>(sm + (u * 32 + lane) * 16);
+                nl128 = __dp4a(zero_bytes_exact(w.x ^ kNL4), 0x01010101u, nl128);
+                nl128 = __dp4a(zero_bytes_exact(w.y ^ kNL4), 0x01010101u, nl128);
+                nl128 = __dp4a(zero_bytes_exact(w.z ^ kNL4), 0x01010101u, nl128);
+                nl128 = __dp4a(zero_bytes_exact(w.w ^ kNL4), 0x01010101u, nl128);
+            }
+        } else if (interior) {
+            // 1. every lane scans its chunks and appends the line starts it finds to the warp's queue;
+            // 2. the queue is drained one line per lane, so the parser runs with (nearly) all lanes busy.
+            int qn = 0;
+            auto drain = [&]() {
+                __syncwarp();
 #pragma unroll 1
-                for (int u = 0; u < U; ++u) {
-                    const int c0 = (u * 32 + lane) * 16;
-                    if (c0 < hi && c0 + 16 > seg_lo) {
-                        const unsigned long long r = chunk_careful<MODE>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0, &a);
+                for (int i = lane; i < qn; i += 32) {
+                    const int ls = queue[i];
+                    bool slow = false;
+                    cnt += line_swar<LAZY>(sm, ls, K, slow);
+                    if (slow) {
+                        const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, ls, &a);
                         cnt += (uint32_t)r;
                         err |= (uint32_t)(r >> 32);
                     }
                 }
+                __syncwarp();
+                qn = 0;
+            };
+#pragma unroll 2
+            for (int u = 0; u < U; ++u) {
+                const int c0 = (u * 32 + lane) * 16;
+                const uint4 w = *reinterpret_cast<const uint4 *>(sm + c0);
+                uint32_t m = 0;
+                bool look = true;
+                if (LAZY) {
+                    const uint32_t w4 = *reinterpret_cast<const uint32_t *>(sm + c0 + 16);
+                    look = chunk_may_hit<MODE>(w, w4, key, c4) != 0;
+                    if (__ballot_sync(0xFFFFFFFFu, look) == 0) continue;
+                }
+                if (look)
+                    m = pack16(zero_bytes_exact(w.x ^ kNL4), zero_bytes_exact(w.y ^ kNL4), zero_bytes_exact(w.z ^ kNL4),
+                               zero_bytes_exact(w.w ^ kNL4));
+                uint32_t b;
+                while ((b = __ballot_sync(0xFFFFFFFFu, m != 0)) != 0) {
+                    if (m) {
+                        queue[qn + __popc(b & lt_mask)] = (uint16_t)(c0 + __ffs(m));  // the line starts after the '\n'
+                        m &= m - 1;
+                    }
+                    qn += __popc(b);
+                    if (qn > kQueue - 32) drain();
+                }
             }
-            __syncwarp();
+            if (qn) drain();
+        } else {
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) {
+                const int c0 = (u * 32 + lane) * 16;
+                if (c0 < hi && c0 + 16 > seg_lo) {
+                    const unsigned long long r = chunk_careful<MODE>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0, &a);
+                    cnt += (uint32_t)r;
+                    err |= (uint32_t)(r >> 32);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
             const int64_t Tn = T + (int64_t)S * nw;
             if (Tn < a.n_tiles) issue(Tn, s);
         }
-        parity ^= 1;
+        if (++s == S) {
+            s = 0;
+            parity ^= 1;
+        }
     }
 
     if (MODE == kScanLines) cnt += nl128 >> 7;
@@ -445,15 +489,13 @@ struct Variant {
 };
 constexpr Variant kVariants[] = {
     {"u4s4w8", 4, 4, 8}, {"u8s3w8", 8, 3, 8}, {"u8s4w4", 8, 4, 4},
-    {"u4s6w8", 4, 6, 8}, {"u2s6w8", 2, 6, 8}, {"u16s3w4", 16, 3, 4},
+    {"u4s3w8", 4, 3, 8}, {"u2s4w8", 2, 4, 8}, {"u16s3w4", 16, 3, 4},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 template <int MODE, int U, int S, int W>
 cudaError_t launch_one(const ScanArgs &args, int ctas, int sm_count, cudaStream_t stream) {
-    constexpr int TILE = 512 * U;
-    constexpr int STAGE = ((kPre + TILE + kHalo + 127) / 128) * 128;
-    constexpr size_t smem = (size_t)W * S * STAGE + (size_t)W * S * sizeof(uint64_t);
+    constexpr size_t smem = SmemLayout<U, S, W>::total;
     auto kern = vcf_scan_kernel<MODE, U, S, W>;
     static int occ = 0;
     if (!occ) {
@@ -493,8 +535,8 @@ cudaError_t launch_vcf_scan(const ScanArgs &args, ScanMode mode, const ScanConfi
     switch (cfg.variant) {
         case 1: return launch_mode<8, 3, 8>(args, mode, cfg.ctas, sm_count, stream);
         case 2: return launch_mode<8, 4, 4>(args, mode, cfg.ctas, sm_count, stream);
-        case 3: return launch_mode<4, 6, 8>(args, mode, cfg.ctas, sm_count, stream);
-        case 4: return launch_mode<2, 6, 8>(args, mode, cfg.ctas, sm_count, stream);
+        case 3: return launch_mode<4, 3, 8>(args, mode, cfg.ctas, sm_count, stream);
+        case 4: return launch_mode<2, 4, 8>(args, mode, cfg.ctas, sm_count, stream);
         case 5: return launch_mode<16, 3, 4>(args, mode, cfg.ctas, sm_count, stream);
         default: return launch_mode<4, 4, 8>(args, mode, cfg.ctas, sm_count, stream);
     }
