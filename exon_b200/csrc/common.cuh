@@ -39,6 +39,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+// ---- shared-memory accesses by 32-bit shared-window address (no generic -> shared conversion in the hot loops) ----
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 // ---- SWAR byte tests -------------------------------------------------------------------------------
 // 0x80 in every byte lane of x that is zero -- exact (no borrow artefacts).
 __device__ __forceinline__ uint32_t zero_bytes_exact(uint32_t x) {

@@ -173,14 +173,15 @@ __device__ __forceinline__ uint32_t pack16(uint32_t f0, uint32_t f1, uint32_t f2
     return (a >> 7) | (b << 1);
 }
 
-// Parses the line whose first byte is sm[ls].  Returns the predicate (0/1); sets `slow` when the line needs
-// the scalar routine instead (nothing has been decided or reported then).
+// Parses the line whose first byte is tile byte `ls`; `sa` is the shared-window address of tile byte 0.
+// Returns the predicate (0/1); sets `slow` when the line needs the scalar routine instead (nothing has been
+// decided or reported then).
 template <bool LAZY>
-__device__ __forceinline__ uint32_t line_swar(const uint8_t *sm, int ls, const LineConsts &K, bool &slow) {
-    const int a0 = ls & ~3;
-    const uint32_t sh = (uint32_t)(ls & 3) << 3;
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(sm + a0);
-    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+__device__ __forceinline__ uint32_t line_swar(uint32_t sa, int ls, const LineConsts &K, bool &slow) {
+    const uint32_t la = sa + (uint32_t)ls;  // address of the line's first byte
+    const uint32_t a0 = la & ~3u;
+    const uint32_t sh = (la & 3u) << 3;     // tile byte 0 is 16-byte aligned
+    const uint32_t w0 = lds32(a0), w1 = lds32(a0 + 4), w2 = lds32(a0 + 8), w3 = lds32(a0 + 12), w4 = lds32(a0 + 16);
     const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh),
                    v3 = __funnelshift_r(w3, w4, sh);
     bool chrom_ok = true;
@@ -197,35 +198,34 @@ __device__ __forceinline__ uint32_t line_swar(const uint8_t *sm, int ls, const L
     const uint32_t m2 = m & (m - 1);
     const int s1 = __ffs(m) - 1, s2 = __ffs(m2) - 1;
     const int n = s2 - s1 - 1;  // digits of POS
-    if (m2 == 0 || s1 < 1 || n < 1 || n > 12 || sm[ls + s1] != '\t' || sm[ls + s2] != '\t') {
+    if (m2 == 0 || s1 < 1 || n < 1 || n > 12 || lds8(la + s1) != '\t' || lds8(la + s2) != '\t') {
         slow = true;
         return 0;
     }
     // the 12 bytes that end right before the second tab; the first 12 - n of them are not POS
-    const int b = ls + s2 - 12;
-    const int b0 = b & ~3;
-    const uint32_t sh2 = (uint32_t)(b & 3) << 3;
-    const uint32_t *xp = reinterpret_cast<const uint32_t *>(sm + b0);
-    const uint32_t x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+    const uint32_t b = la + (uint32_t)s2 - 12u;
+    const uint32_t b0 = b & ~3u;
+    const uint32_t sh2 = (b & 3u) << 3;
+    const uint32_t x0 = lds32(b0), x1 = lds32(b0 + 4), x2 = lds32(b0 + 8), x3 = lds32(b0 + 12);
     const uint32_t s = (uint32_t)(12 - n) << 3;
     const uint32_t d0 = (__funnelshift_r(x0, x1, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s);
     const uint32_t d1 = (__funnelshift_r(x1, x2, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s > 32u ? s - 32u : 0u);
     const uint32_t d2 = (__funnelshift_r(x2, x3, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s > 64u ? s - 64u : 0u);
-    // every kept byte must be 0..9
+    // every kept byte must be 0..9, and POS 0 is not a position ('+' lands here too): the scalar routine reports
     const uint32_t bad = ((d0 + 0x76767676u) | d0 | (d1 + 0x76767676u) | d1 | (d2 + 0x76767676u) | d2) & 0x80808080u;
+    if (bad || (d0 | d1 | d2) == 0u) {
+        slow = true;
+        return 0;
+    }
+    if (!chrom_ok || !K.has_interval) return chrom_ok;  // validated; the value is not needed
     // 4 digits per word, most significant in byte 0
     const uint32_t q0 = __dp4a(d0, 0x00010A64u, 0u) * 10u + (d0 >> 24);
     const uint32_t q1 = __dp4a(d1, 0x00010A64u, 0u) * 10u + (d1 >> 24);
     const uint32_t q2 = __dp4a(d2, 0x00010A64u, 0u) * 10u + (d2 >> 24);
     const unsigned long long v = (unsigned long long)(q0 * 10000u + q1) * 10000ull + q2;
-    if (bad || v == 0ull) {
-        slow = true;  // '+', a non-digit, or POS 0: the scalar routine decides and reports
-        return 0;
-    }
     const unsigned long long lo = ((unsigned long long)K.lo_hi << 32) | K.lo_lo;
     const unsigned long long span = ((unsigned long long)K.span_hi << 32) | K.span_lo;
-    const uint32_t in = (v - lo) <= span;
-    return chrom_ok ? (K.has_interval ? in : 1u) : 0u;
+    return (v - lo) <= span;
 }
 
 // Screens one 16-byte chunk (words w.x..w.w plus the following word w4): non-zero iff the chunk MAY contain
@@ -278,8 +278,16 @@ struct SmemLayout {
     static constexpr size_t total = queue + (size_t)WARPS * kQueue * sizeof(uint16_t);
 };
 
+template <int U, int S, int WARPS>
+constexpr int ctas_per_sm() {
+    const int by_smem = (int)((227 * 1024) / SmemLayout<U, S, WARPS>::total);
+    const int by_warps = 32 / WARPS;  // at most 32 resident warps: the parser wants >= 64 registers per thread
+    const int c = by_smem < by_warps ? by_smem : by_warps;
+    return c < 1 ? 1 : c;
+}
+
 template <int MODE, int U, int S, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_constant__ ScanArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_scan_kernel(const __grid_constant__ ScanArgs a) {
     constexpr bool LAZY = (MODE == kScanKey3 || MODE == kScanKey4);
     using L = SmemLayout<U, S, WARPS>;
     constexpr int TILE = L::TILE, STAGE = L::STAGE;
@@ -289,7 +297,8 @@ __global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_const
     uint8_t *ring = smem_raw + L::ring + (size_t)warp * (S * STAGE);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + L::bars) + warp * S;
     StageMeta *meta = reinterpret_cast<StageMeta *>(smem_raw + L::meta) + warp * S;
-    uint16_t *queue = reinterpret_cast<uint16_t *>(smem_raw + L::queue) + warp * kQueue;
+    const uint32_t ring_sa = smem_u32(ring);
+    const uint32_t queue_sa = smem_u32(smem_raw + L::queue) + (uint32_t)(warp * kQueue * sizeof(uint16_t));
 
     if (lane == 0) {
 #pragma unroll
@@ -398,10 +407,11 @@ __global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_const
         }
         // interior: the tile starts inside the segment at a 16-byte boundary and every staged byte is segment data
         const bool interior = hi >= TILE + kHalo && (lo <= 0) && swar_ok;
+        const uint32_t sa = ring_sa + (uint32_t)(s * STAGE + kPre);  // shared-window address of tile byte 0
         if (interior && MODE == kScanLines) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const uint4 w = *reinterpret_cast<const uint4 *>(sm + (u * 32 + lane) * 16);
+                const uint4 w = lds128(sa + (uint32_t)((u * 32 + lane) * 16));
                 nl128 = __dp4a(zero_bytes_exact(w.x ^ kNL4), 0x01010101u, nl128);
                 nl128 = __dp4a(zero_bytes_exact(w.y ^ kNL4), 0x01010101u, nl128);
                 nl128 = __dp4a(zero_bytes_exact(w.z ^ kNL4), 0x01010101u, nl128);
@@ -415,9 +425,9 @@ __global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_const
                 __syncwarp();
 #pragma unroll 1
                 for (int i = lane; i < qn; i += 32) {
-                    const int ls = queue[i];
+                    const int ls = (int)lds16(queue_sa + 2u * (uint32_t)i);
                     bool slow = false;
-                    cnt += line_swar<LAZY>(sm, ls, K, slow);
+                    cnt += line_swar<LAZY>(sa, ls, K, slow);
                     if (slow) {
                         const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, ls, &a);
                         cnt += (uint32_t)r;
@@ -430,26 +440,31 @@ __global__ void __launch_bounds__(WARPS * 32) vcf_scan_kernel(const __grid_const
 #pragma unroll 2
             for (int u = 0; u < U; ++u) {
                 const int c0 = (u * 32 + lane) * 16;
-                const uint4 w = *reinterpret_cast<const uint4 *>(sm + c0);
+                const uint4 w = lds128(sa + (uint32_t)c0);
                 uint32_t m = 0;
                 bool look = true;
                 if (LAZY) {
-                    const uint32_t w4 = *reinterpret_cast<const uint32_t *>(sm + c0 + 16);
+                    const uint32_t w4 = lds32(sa + (uint32_t)c0 + 16u);
                     look = chunk_may_hit<MODE>(w, w4, key, c4) != 0;
                     if (__ballot_sync(0xFFFFFFFFu, look) == 0) continue;
                 }
                 if (look)
                     m = pack16(zero_bytes_exact(w.x ^ kNL4), zero_bytes_exact(w.y ^ kNL4), zero_bytes_exact(w.z ^ kNL4),
                                zero_bytes_exact(w.w ^ kNL4));
-                uint32_t b;
-                while ((b = __ballot_sync(0xFFFFFFFFu, m != 0)) != 0) {
-                    if (m) {
-                        queue[qn + __popc(b & lt_mask)] = (uint16_t)(c0 + __ffs(m));  // the line starts after the '\n'
-                        m &= m - 1;
-                    }
-                    qn += __popc(b);
-                    if (qn > kQueue - 32) drain();
+                const uint32_t b = __ballot_sync(0xFFFFFFFFu, m != 0);
+                if (m) {
+                    sts16(queue_sa + 2u * (uint32_t)(qn + __popc(b & lt_mask)), (uint32_t)(c0 + __ffs(m)));  // line = byte after '\n'
+                    m &= m - 1;
                 }
+                qn += __popc(b);
+                // further line starts in the same 16 bytes (lines shorter than 16 bytes) take the scalar routine
+                while (m) {
+                    const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0 + __ffs(m), &a);
+                    m &= m - 1;
+                    cnt += (uint32_t)r;
+                    err |= (uint32_t)(r >> 32);
+                }
+                if (qn > kQueue - 32) drain();
             }
             if (qn) drain();
         } else {
@@ -488,7 +503,7 @@ struct Variant {
     int U, S, W;
 };
 constexpr Variant kVariants[] = {
-    {"u4s4w8", 4, 4, 8}, {"u8s3w8", 8, 3, 8}, {"u8s4w4", 8, 4, 4},
+    {"u8s3w8", 8, 3, 8}, {"u4s4w8", 4, 4, 8}, {"u8s4w4", 8, 4, 4},
     {"u4s3w8", 4, 3, 8}, {"u2s4w8", 2, 4, 8}, {"u16s3w4", 16, 3, 4},
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
@@ -533,12 +548,12 @@ cudaError_t launch_vcf_scan(const ScanArgs &args, ScanMode mode, const ScanConfi
                             cudaStream_t stream) {
     if (args.n_tiles <= 0) return cudaSuccess;
     switch (cfg.variant) {
-        case 1: return launch_mode<8, 3, 8>(args, mode, cfg.ctas, sm_count, stream);
+        case 1: return launch_mode<4, 4, 8>(args, mode, cfg.ctas, sm_count, stream);
         case 2: return launch_mode<8, 4, 4>(args, mode, cfg.ctas, sm_count, stream);
         case 3: return launch_mode<4, 3, 8>(args, mode, cfg.ctas, sm_count, stream);
         case 4: return launch_mode<2, 4, 8>(args, mode, cfg.ctas, sm_count, stream);
         case 5: return launch_mode<16, 3, 4>(args, mode, cfg.ctas, sm_count, stream);
-        default: return launch_mode<4, 4, 8>(args, mode, cfg.ctas, sm_count, stream);
+        default: return launch_mode<8, 3, 8>(args, mode, cfg.ctas, sm_count, stream);
     }
 }
 

@@ -43,7 +43,7 @@ enum ScanMode {
 };
 
 struct ScanConfig {
-    int variant;       // 0: tile = 2 KiB/warp, 4 stages; see vcf_scan.cu for the table
+    int variant;       // 0: tile = 4 KiB/warp, 3 stages, 8 warps/CTA; see vcf_scan.cu for the table
     int ctas;          // 0 = occupancy * SM count
 };
 
