@@ -203,9 +203,9 @@ def run_b200(args):
     tstream = torch.cuda.Stream()
     ctx = Context(local, cuda_stream=tstream.cuda_stream)
     if world > 1:
-        ids = [ctx.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        ctx.nccl_init(ids[0], world, rank)
+        from exon_b200 import sharding
+
+        sharding.init_final_aggregate(ctx, dist, rank, world)
 
     # ---- synthetic workload: this rank's file group (seed differs per rank), pinned on the host ----
     t_gen = time.perf_counter()
