@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libexon_gpu.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_PARSE, ERR_STATE, ERR_OOM, ERR_UNSUPPORTED, ERR_NCCL = range(8)
 AGG_COUNT_STAR, AGG_COUNT, AGG_SUM, AGG_AVG = range(4)
+UDF_REGION_MATCH, UDF_CHROM_MATCH, UDF_INTERVAL_MATCH = range(3)
 INT64_MAX = (1 << 63) - 1
 NCCL_ID_BYTES = 128
 
@@ -25,7 +26,8 @@ SYMBOLS = [
     "exon_gpu_vcf_close", "exon_gpu_vcf_reset", "exon_gpu_vcf_feed", "exon_gpu_vcf_next_batch",
     "exon_gpu_vcf_filter_count", "exon_gpu_vcf_filter_count_async", "exon_gpu_vcf_rows", "exon_gpu_vcf_body_bytes",
     "exon_gpu_filter_agg", "exon_gpu_nccl_unique_id", "exon_gpu_nccl_init", "exon_gpu_allreduce_partial",
-    "exon_gpu_vcf_filter_count_global",
+    "exon_gpu_vcf_filter_count_global", "exon_gpu_filter_agg_accumulate", "exon_gpu_partial_read", "exon_gpu_memset",
+    "exon_gpu_region_udf",
 ]
 
 
@@ -120,6 +122,11 @@ def load():
         "exon_gpu_vcf_body_bytes": [vp, C.POINTER(i64)],
         "exon_gpu_filter_agg": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema), C.c_int, C.POINTER(Pred),
                                 C.POINTER(Agg), C.POINTER(Partial)],
+        "exon_gpu_filter_agg_accumulate": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema), C.POINTER(Pred),
+                                           C.POINTER(Agg), vp],
+        "exon_gpu_partial_read": [vp, vp, C.c_int, C.POINTER(Partial)],
+        "exon_gpu_memset": [vp, vp, C.c_int, C.c_size_t],
+        "exon_gpu_region_udf": [vp, C.c_int, C.POINTER(ArrowArray), C.POINTER(ArrowSchema), C.c_int, C.POINTER(Pred), vp, vp],
         "exon_gpu_nccl_unique_id": [C.c_char_p],
         "exon_gpu_nccl_init": [vp, C.c_char_p, C.c_int, C.c_int],
         "exon_gpu_allreduce_partial": [vp, C.POINTER(Partial)],

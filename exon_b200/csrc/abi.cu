@@ -187,6 +187,13 @@ int exon_gpu_memcpy_h2d(exon_gpu_ctx *c, void *dst, const void *src, size_t byte
     return EXON_GPU_OK;
 }
 
+int exon_gpu_memset(exon_gpu_ctx *c, void *p, int value, size_t bytes) {
+    if (!c || (!p && bytes)) return fail(EXON_GPU_ERR_ARG, "memset: NULL argument");
+    if (int rc = ensure_device(c)) return rc;
+    CUDA_TRY(cudaMemsetAsync(p, value, bytes, c->stream));
+    return EXON_GPU_OK;
+}
+
 // ---- VCF partition stream ---------------------------------------------------------------------------
 
 int exon_gpu_vcf_open(exon_gpu_ctx *c, const exon_gpu_vcf_opts *o, exon_gpu_stream **out) {

@@ -124,6 +124,32 @@ class Context:
         return out.count, out.sum_i64, out.sum_f64
 
 
+    def filter_agg_accumulate(self, arrow_array, arrow_schema, device_acc_ptr: int, *, chrom_col: int = -1,
+                              pos_col: int = -1, region=None, kind: int = _abi.AGG_COUNT_STAR, value_col: int = -1):
+        pred = _abi.Pred(chrom_col, pos_col, region if region is not None else _abi.Region())
+        agg = _abi.Agg(kind, value_col)
+        check(self.lib.exon_gpu_filter_agg_accumulate(self.handle, C.byref(arrow_array), C.byref(arrow_schema),
+                                                      C.byref(pred), C.byref(agg), C.c_void_p(device_acc_ptr)))
+
+    def partial_read(self, device_acc_ptr: int, sum_is_integer: bool = True):
+        out = _abi.Partial()
+        check(self.lib.exon_gpu_partial_read(self.handle, C.c_void_p(device_acc_ptr), int(sum_is_integer), C.byref(out)))
+        return out.count, out.sum_i64, out.sum_f64
+
+    def memset(self, device_ptr: int, value: int, nbytes: int):
+        check(self.lib.exon_gpu_memset(self.handle, C.c_void_p(device_ptr), value, nbytes))
+
+    def region_udf(self, kind: int, arrow_array, arrow_schema, *, on_device: bool, chrom_col: int = -1, pos_col: int = -1,
+                   region=None):
+        """(values bool[n], valid bool[n]) of region_match / chrom_match / interval_match over one batch."""
+        n = int(arrow_array.length)
+        vals, valid = np.zeros(max(n, 1), np.uint8), np.zeros(max(n, 1), np.uint8)
+        pred = _abi.Pred(chrom_col, pos_col, region if region is not None else _abi.Region())
+        check(self.lib.exon_gpu_region_udf(self.handle, kind, C.byref(arrow_array), C.byref(arrow_schema), int(on_device),
+                                           C.byref(pred), C.c_void_p(vals.ctypes.data), C.c_void_p(valid.ctypes.data)))
+        return vals[:n].astype(bool), valid[:n].astype(bool)
+
+
 class VcfBatch:
     """One record batch from exon_gpu_vcf_next_batch, imported into numpy (host columns only)."""
 

@@ -201,6 +201,24 @@ int exon_gpu_filter_agg(exon_gpu_ctx *ctx, const struct ArrowArray *batch, const
                         int buffers_on_device, const exon_gpu_pred *pred, const exon_gpu_agg *agg,
                         exon_gpu_partial *out);
 
+/* The same operators for a stream of batches whose buffers already live in DEVICE memory (what
+ * exon_gpu_vcf_next_batch yields with columns_on_device = 1): each call enqueues one kernel that adds into the
+ * caller's device-resident accumulator (zero it with exon_gpu_device_alloc + exon_gpu_memset, or reuse), nothing
+ * synchronises until exon_gpu_partial_read.  This is AggregateExec(Partial)'s accumulator living across batches. */
+int exon_gpu_filter_agg_accumulate(exon_gpu_ctx *ctx, const struct ArrowArray *batch, const struct ArrowSchema *schema,
+                                   const exon_gpu_pred *pred, const exon_gpu_agg *agg, exon_gpu_partial *device_acc);
+int exon_gpu_partial_read(exon_gpu_ctx *ctx, const exon_gpu_partial *device_acc, int sum_is_integer, exon_gpu_partial *out);
+int exon_gpu_memset(exon_gpu_ctx *ctx, void *device_ptr, int value, size_t bytes);
+
+/* Evaluated region UDFs (exon/exon-core/src/udfs/vcf/mod.rs): region_match(chrom, pos, 'name:lo-hi') :65-131,
+ * chrom_match(chrom, 'name') :167-196, interval_match(pos, 'lo-hi') :232-274.  One byte per row in HOST memory:
+ * out_values[i] in {0,1}; out_valid[i] == 0 marks a NULL result (chrom_match of a NULL chrom); may be NULL.
+ * region_match fails on a NULL operand, region_match / interval_match fail on pos < 1 (Position::try_from),
+ * interval_match maps a NULL pos to false -- all as the reference does. */
+enum { EXON_GPU_UDF_REGION_MATCH = 0, EXON_GPU_UDF_CHROM_MATCH = 1, EXON_GPU_UDF_INTERVAL_MATCH = 2 };
+int exon_gpu_region_udf(exon_gpu_ctx *ctx, int kind, const struct ArrowArray *batch, const struct ArrowSchema *schema,
+                        int buffers_on_device, const exon_gpu_pred *pred, uint8_t *out_values, uint8_t *out_valid);
+
 /* ---- multi-GPU final aggregate ---------------------------------------------------------------- */
 /* CoalescePartitionsExec + AggregateExec(Final) across GPUs: one ncclAllReduce(sum) of the partial over
  * NVLink.  The communicator is created from an id produced on rank 0 and distributed by the host. */
