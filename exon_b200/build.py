@@ -24,6 +24,7 @@ def _stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
+        build_host(verbose=verbose)
         return LIB
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -45,7 +46,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")
+    build_host(force=True, verbose=verbose)
     return LIB
+
+
+HOST_DIR = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(HOST_DIR, "libexon_host.so")
+
+
+def build_host(force: bool = False, verbose: bool = False) -> str:
+    """exon_b200/host/libexon_host.so: the C++ mirror of the reference's host-side operators (g++, links libexon_gpu)."""
+    srcs = [os.path.join(HOST_DIR, "exon_host.cpp")]
+    deps = srcs + [os.path.join(HOST_DIR, "exon_host.hpp"), os.path.join(HERE, "..", "include", "exon_gpu.h"), LIB]
+    if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in deps):
+        return HOST_LIB
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB, *srcs, "-L" + HERE, "-lexon_gpu", "-lz",
+           "-lpthread", "-Wl,-rpath,$ORIGIN/.."]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed on exon_host.cpp:\n{r.stdout}{r.stderr}")
+    return HOST_LIB
 
 
 if __name__ == "__main__":

@@ -1,0 +1,73 @@
+"""ctypes access to exon_b200/host/libexon_host.so (the C++ mirror of the reference's host-side operators)."""
+import ctypes as C
+import gzip
+import os
+import shutil
+
+from conftest import GOLDEN, ROOT
+
+HOST_LIB = os.path.join(ROOT, "exon_b200", "host", "libexon_host.so")
+
+
+def load_host():
+    L = C.CDLL(HOST_LIB)
+    L.exon_host_session_new.restype = C.c_void_p
+    L.exon_host_session_new.argtypes = [C.c_int]
+    L.exon_host_session_free.argtypes = [C.c_void_p]
+    L.exon_host_last_error.restype = C.c_char_p
+    L.exon_host_sql.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p)]
+    L.exon_host_pushdown.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    L.exon_host_gpu_launches.restype = C.c_int64
+    L.exon_host_gpu_launches.argtypes = [C.c_void_p]
+    return L
+
+
+def build_datasources(root):
+    """Lay the committed fixtures out like exon/exon-core/test-data/datasources/."""
+    os.makedirs(os.path.join(root, "vcf"))
+    with gzip.open(os.path.join(GOLDEN, "index_plain.vcf.gz")) as f, open(os.path.join(root, "vcf", "index.vcf"), "wb") as o:
+        o.write(f.read())
+    shutil.copy(os.path.join(GOLDEN, "index.vcf.gz"), os.path.join(root, "vcf", "index.vcf.gz"))
+    for s in ("1", "2"):
+        d = os.path.join(root, "vcf-partition", f"sample={s}")
+        os.makedirs(d)
+        shutil.copy(os.path.join(GOLDEN, "index.vcf.gz"), os.path.join(d, "index.vcf.gz"))
+    os.makedirs(os.path.join(root, "biobear-vcf"))
+    shutil.copy(os.path.join(GOLDEN, "biobear_vcf_file.vcf.gz"), os.path.join(root, "biobear-vcf", "vcf_file.vcf.gz"))
+    os.makedirs(os.path.join(root, "two-vcf"))
+    for n in ("a.vcf", "b.vcf"):
+        shutil.copy(os.path.join(root, "vcf", "index.vcf"), os.path.join(root, "two-vcf", n))
+    return root
+
+
+def parse_slt(text):
+    """[(kind, sql, expected_rows)] with kind in {'ok', 'error', 'query'}."""
+    out, lines, i = [], text.splitlines(), 0
+    while i < len(lines):
+        ln = lines[i].strip()
+        if not ln or ln.startswith("#"):
+            i += 1
+            continue
+        if ln.startswith("statement"):
+            kind = "ok" if ln.split()[1] == "ok" else "error"
+            i += 1
+            sql = []
+            while i < len(lines) and lines[i].strip():
+                sql.append(lines[i])
+                i += 1
+            out.append((kind, " ".join(sql), None))
+        elif ln.startswith("query"):
+            i += 1
+            sql = []
+            while lines[i].strip() != "----":
+                sql.append(lines[i])
+                i += 1
+            i += 1
+            rows = []
+            while i < len(lines) and lines[i].strip():
+                rows.append(lines[i].rstrip())
+                i += 1
+            out.append(("query", " ".join(sql), rows))
+        else:
+            raise ValueError(f"slt: cannot parse line {i + 1}: {ln}")
+    return out
