@@ -27,7 +27,7 @@ SYMBOLS = [
     "exon_gpu_vcf_filter_count", "exon_gpu_vcf_filter_count_async", "exon_gpu_vcf_rows", "exon_gpu_vcf_body_bytes",
     "exon_gpu_filter_agg", "exon_gpu_nccl_unique_id", "exon_gpu_nccl_init", "exon_gpu_allreduce_partial",
     "exon_gpu_vcf_filter_count_global", "exon_gpu_filter_agg_accumulate", "exon_gpu_partial_read", "exon_gpu_memset",
-    "exon_gpu_region_udf",
+    "exon_gpu_region_udf", "exon_gpu_filter_agg_batches", "exon_gpu_vcf_filter_agg",
 ]
 
 
@@ -124,6 +124,9 @@ def load():
                                 C.POINTER(Agg), C.POINTER(Partial)],
         "exon_gpu_filter_agg_accumulate": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema), C.POINTER(Pred),
                                            C.POINTER(Agg), vp],
+        "exon_gpu_filter_agg_batches": [vp, C.POINTER(C.POINTER(ArrowArray)), i32, C.POINTER(ArrowSchema), C.POINTER(Pred),
+                                        C.POINTER(Agg), C.POINTER(Partial)],
+        "exon_gpu_vcf_filter_agg": [vp, C.POINTER(Pred), C.POINTER(Agg), C.POINTER(Partial)],
         "exon_gpu_partial_read": [vp, vp, C.c_int, C.POINTER(Partial)],
         "exon_gpu_memset": [vp, vp, C.c_int, C.c_size_t],
         "exon_gpu_region_udf": [vp, C.c_int, C.POINTER(ArrowArray), C.POINTER(ArrowSchema), C.c_int, C.POINTER(Pred), vp, vp],

@@ -125,6 +125,7 @@ int exon_gpu_ctx_destroy(exon_gpu_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (auto &b : c->free_blocks) cudaFree(b.ptr);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->scratch_b) cudaFree(c->scratch_b);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     nccl_teardown(c);
     cudaEventDestroy(c->ev0);

@@ -29,8 +29,6 @@ namespace exon {
 
 namespace {
 
-enum ValueType { kValNone = 0, kValI64 = 1, kValF64 = 2, kValF32 = 3, kValI32 = 4 };
-
 struct FilterAggArgs {
     int64_t n_rows;
     // chrom: utf8
@@ -109,6 +107,84 @@ __global__ void __launch_bounds__(kFaThreads) filter_agg_kernel(const __grid_con
         }
     }
     // warp shuffle reduction, then one atomic per warp
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+        si += __shfl_xor_sync(0xFFFFFFFFu, si, d);
+        sf += __shfl_xor_sync(0xFFFFFFFFu, sf, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (cnt) atomicAdd(a.out, cnt);
+        if (si) atomicAdd(a.out + 1, (unsigned long long)si);
+        if (sf != 0.0) atomicAdd(reinterpret_cast<double *>(a.out + 2), sf);
+    }
+}
+
+// The same operators over MANY device-resident batches in one launch (a partition's whole column store): work is
+// cut into units of kUnitRows rows of one batch, units are dealt round-robin to a persistent grid, and every
+// thread evaluates kRowsPerThread rows whose loads are issued together (coalesced 8-byte / 4-byte accesses, four
+// independent rows in flight per thread).  The CHROM bytes are fetched only for rows whose POS and CHROM length
+// already match.
+constexpr int kRowsPerThread = 4;
+constexpr int kUnitRows = kFaThreads * kRowsPerThread;
+
+__global__ void __launch_bounds__(kFaThreads) filter_agg_multi_kernel(const __grid_constant__ FilterAggArgs a, const FaBatchDesc *descs,
+                                                                      int n_batches, int units_per_batch) {
+    unsigned long long cnt = 0;
+    long long si = 0;
+    double sf = 0.0;
+    const int64_t n_units = (int64_t)n_batches * units_per_batch;
+    for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int b = (int)(unit / units_per_batch);
+        const int64_t base = (unit - (int64_t)b * units_per_batch) * kUnitRows;
+        const FaBatchDesc *d = descs + b;
+        const int64_t n_rows = d->n_rows;
+        if (base >= n_rows) continue;
+        const int64_t *pos = d->pos + d->pos_off;
+        const int32_t *off = d->chrom_offsets + d->chrom_off;
+        int64_t pv[kRowsPerThread];
+        int32_t o0[kRowsPerThread], o1[kRowsPerThread];
+        bool in[kRowsPerThread];
+#pragma unroll
+        for (int k = 0; k < kRowsPerThread; ++k) {
+            const int64_t i = base + k * kFaThreads + threadIdx.x;
+            in[k] = i < n_rows;
+            pv[k] = 0;
+            o0[k] = o1[k] = 0;
+            if (in[k]) {
+                if (a.has_pos) pv[k] = pos[i];
+                if (a.has_chrom) {
+                    o0[k] = off[i];
+                    o1[k] = off[i + 1];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kRowsPerThread; ++k) {
+            if (!in[k]) continue;
+            const int64_t i = base + k * kFaThreads + threadIdx.x;
+            bool sel = true;
+            if (a.has_pos) sel = bit_set(d->pos_valid, i + d->pos_off) & (pv[k] >= a.lo) & (pv[k] <= a.hi);
+            if (sel && a.has_chrom) {
+                sel = bit_set(d->chrom_valid, i + d->chrom_off) && (o1[k] - o0[k]) == a.lit_len;
+                for (int32_t j = 0; sel && j < a.lit_len; ++j) sel = d->chrom_values[o0[k] + j] == a.lit[j];
+            }
+            if (!sel) continue;
+            if (a.agg_kind == EXON_GPU_AGG_COUNT_STAR) {
+                ++cnt;
+            } else {
+                const int64_t r = i + d->val_off;
+                if (!bit_set(d->val_valid, r)) continue;
+                ++cnt;
+                if (a.agg_kind != EXON_GPU_AGG_COUNT) {
+                    if (a.val_type == kValI64) si += static_cast<const int64_t *>(d->val)[r];
+                    else if (a.val_type == kValI32) si += static_cast<const int32_t *>(d->val)[r];
+                    else if (a.val_type == kValF64) sf += static_cast<const double *>(d->val)[r];
+                    else if (a.val_type == kValF32) sf += (double)static_cast<const float *>(d->val)[r];
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
@@ -267,6 +343,53 @@ int launch_agg(Ctx *c, const FilterAggArgs &a) {
 
 }  // namespace
 
+// Launches the multi-batch kernel over a descriptor table that already lives in device memory.
+int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, int64_t max_rows, const FaCommon &k,
+                            unsigned long long *d_out, bool timed) {
+    if (n_batches <= 0 || max_rows <= 0) return EXON_GPU_OK;
+    FilterAggArgs a;
+    memset(&a, 0, sizeof(a));
+    a.has_chrom = k.has_chrom;
+    a.lit_len = k.lit_len;
+    memcpy(a.lit, k.lit, sizeof(a.lit));
+    a.has_pos = k.has_pos;
+    a.lo = k.lo;
+    a.hi = k.hi;
+    a.val_type = k.val_type;
+    a.agg_kind = k.agg_kind;
+    a.out = d_out;
+    const int upb = (int)((max_rows + kUnitRows - 1) / kUnitRows);
+    const int64_t n_units = (int64_t)n_batches * upb;
+    const int grid = (int)std::min<int64_t>(n_units, (int64_t)c->sm_count * 8);
+    if (timed) CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    filter_agg_multi_kernel<<<grid, kFaThreads, 0, c->stream>>>(a, d_descs, n_batches, upb);
+    c->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    if (timed) {
+        CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+        c->timed = true;
+    }
+    return EXON_GPU_OK;
+}
+
+int fa_common_from(const exon_gpu_pred *pred, const exon_gpu_agg *agg, FaCommon &k) {
+    memset(&k, 0, sizeof(k));
+    if (pred && pred->chrom_col >= 0 && pred->region.has_chrom) {
+        if (pred->region.chrom_len < 0 || pred->region.chrom_len > kMaxChrom || (!pred->region.chrom && pred->region.chrom_len))
+            return fail(EXON_GPU_ERR_ARG, "bad chrom literal");
+        k.has_chrom = 1;
+        k.lit_len = pred->region.chrom_len;
+        memcpy(k.lit, pred->region.chrom, (size_t)k.lit_len);
+    }
+    if (pred && pred->pos_col >= 0 && pred->region.has_interval) {
+        k.has_pos = 1;
+        k.lo = pred->region.lo;
+        k.hi = pred->region.hi;
+    }
+    k.agg_kind = agg ? agg->kind : EXON_GPU_AGG_COUNT_STAR;
+    return EXON_GPU_OK;
+}
+
 }  // namespace exon
 
 using namespace exon;
@@ -304,6 +427,55 @@ int exon_gpu_filter_agg_accumulate(exon_gpu_ctx *c, const struct ArrowArray *bat
     if (int rc = prepare(c, batch, schema, 1, pred, agg, 0, 0, a)) return rc;
     a.out = reinterpret_cast<unsigned long long *>(device_acc);
     return launch_agg(c, a);
+}
+
+int exon_gpu_filter_agg_batches(exon_gpu_ctx *c, const struct ArrowArray *const *batches, int32_t n_batches,
+                                const struct ArrowSchema *schema, const exon_gpu_pred *pred, const exon_gpu_agg *agg,
+                                exon_gpu_partial *out) {
+    if (!c || (!batches && n_batches) || n_batches < 0 || !schema || !agg || !out)
+        return fail(EXON_GPU_ERR_ARG, "filter_agg_batches: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (agg->kind < EXON_GPU_AGG_COUNT_STAR || agg->kind > EXON_GPU_AGG_AVG)
+        return fail(EXON_GPU_ERR_ARG, "filter_agg_batches: unknown aggregate kind %d", agg->kind);
+    std::lock_guard<std::mutex> work(c->work_mu);
+    std::vector<FaBatchDesc> descs((size_t)n_batches);
+    FaCommon k;
+    if (int rc = fa_common_from(pred, agg, k)) return rc;
+    int64_t max_rows = 0;
+    for (int32_t b = 0; b < n_batches; ++b) {
+        if (!batches[b]) return fail(EXON_GPU_ERR_ARG, "filter_agg_batches: batch %d is NULL", b);
+        FilterAggArgs a;
+        if (int rc = prepare(c, batches[b], schema, 1, pred, agg, 0, 0, a)) return rc;
+        FaBatchDesc &d = descs[(size_t)b];
+        d.chrom_valid = a.chrom_valid;
+        d.chrom_offsets = a.chrom_offsets;
+        d.chrom_values = a.chrom_values;
+        d.chrom_off = a.chrom_off;
+        d.pos_valid = a.pos_valid;
+        d.pos = a.pos;
+        d.pos_off = a.pos_off;
+        d.val_valid = a.val_valid;
+        d.val = a.val;
+        d.val_off = a.val_off;
+        d.n_rows = a.n_rows;
+        k.val_type = a.val_type;
+        max_rows = std::max(max_rows, a.n_rows);
+    }
+    const size_t table = ((sizeof(FaBatchDesc) * (size_t)n_batches + 255) & ~(size_t)255);
+    if (int rc = c->ensure_scratch(table + 64, 64)) return rc;
+    uint8_t *scr = (uint8_t *)c->scratch;
+    unsigned long long *d_out = (unsigned long long *)(scr + table);
+    if (n_batches) CUDA_TRY(cudaMemcpyAsync(scr, descs.data(), sizeof(FaBatchDesc) * (size_t)n_batches, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, 64, c->stream));
+    if (int rc = filter_agg_multi_launch(c, (const FaBatchDesc *)scr, n_batches, max_rows, k, d_out, true)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->h_scratch, d_out, 24, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const unsigned long long *r = (const unsigned long long *)c->h_scratch;
+    out->count = (int64_t)r[0];
+    out->sum_i64 = (int64_t)r[1];
+    memcpy(&out->sum_f64, &r[2], sizeof(double));
+    if (k.val_type == kValI64 || k.val_type == kValI32) out->sum_f64 = (double)out->sum_i64;
+    return EXON_GPU_OK;
 }
 
 int exon_gpu_partial_read(exon_gpu_ctx *c, const exon_gpu_partial *device_acc, int sum_is_integer, exon_gpu_partial *out) {

@@ -31,12 +31,15 @@ struct Ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the most recent fused-scan launch
     bool timed = false;
     std::mutex mu;
+    std::mutex work_mu;  // serialises users of the context-wide scratch areas (K2 build, K3 calls)
     std::vector<DevBlock> free_blocks;
     // scratch for filter_agg / allreduce
     void *scratch = nullptr;
     size_t scratch_cap = 0;
     void *h_scratch = nullptr;
     size_t h_scratch_cap = 0;
+    void *scratch_b = nullptr;  // second device scratch area (K2 keeps per-row temporaries here while `scratch` holds tile tables)
+    size_t scratch_b_cap = 0;
     // NCCL (dlopen'ed lazily; see nccl.cu)
     void *nccl_comm = nullptr;
     int nccl_ranks = 0;
@@ -44,6 +47,7 @@ struct Ctx {
     int get_block(size_t min_bytes, DevBlock *out);
     void put_block(DevBlock b);
     int ensure_scratch(size_t dev_bytes, size_t host_bytes);
+    int ensure_scratch_b(size_t dev_bytes);
 };
 
 void nccl_teardown(Ctx *c);
@@ -121,7 +125,34 @@ struct VcfStream {
     void release_all();
 };
 
+// ---- K3 over many device-resident batches (filter_agg.cu) ----
+enum ValueType { kValNone = 0, kValI64 = 1, kValF64 = 2, kValF32 = 3, kValI32 = 4 };
+struct FaBatchDesc {
+    const uint8_t *chrom_valid;  // validity bitmaps may be NULL
+    const int32_t *chrom_offsets;
+    const uint8_t *chrom_values;
+    int64_t chrom_off;  // logical offset of row 0 in the chrom arrays
+    const uint8_t *pos_valid;
+    const int64_t *pos;
+    int64_t pos_off;
+    const uint8_t *val_valid;
+    const void *val;
+    int64_t val_off;
+    int64_t n_rows;
+};
+struct FaCommon {
+    int32_t has_chrom, lit_len;
+    uint8_t lit[kMaxChrom + 1];
+    int32_t has_pos;
+    int64_t lo, hi;
+    int32_t val_type, agg_kind;
+};
+int fa_common_from(const exon_gpu_pred *pred, const exon_gpu_agg *agg, FaCommon &k);
+int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, int64_t max_rows, const FaCommon &k,
+                            unsigned long long *d_out, bool timed);
+
 // defined in vcf_columns.cu
+int columns_filter_agg(VcfStream *s, const exon_gpu_pred *pred, const exon_gpu_agg *agg, exon_gpu_partial *out);
 void columns_free(VcfStream *s);
 int columns_next_batch(VcfStream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 

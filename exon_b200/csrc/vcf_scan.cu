@@ -31,32 +31,11 @@
 #include "vcf_scan.cuh"
 
 #include "common.cuh"
+#include "vcf_tile.cuh"
 
 namespace exon {
 
 namespace {
-
-constexpr int kPre = 16;   // bytes staged before the tile (right-aligned POS fetch may reach back 12 bytes)
-constexpr int kHalo = 48;  // bytes staged after the tile (line window + POS digits of a line that starts at the end)
-
-// ===================================================================================================
-// Byte-exact scalar routines (boundary tiles, unusual records, all error reporting)
-// ===================================================================================================
-struct TileView {
-    const uint8_t *sm;  // shared-memory address of tile byte 0
-    const uint8_t *g;   // global address of tile byte 0
-    int lo;             // smallest tile-relative index inside the segment (<= 0)
-    int hi;             // one past the largest (> 0)
-    int sm_lo, sm_hi;   // tile-relative index range present in shared memory
-};
-
-// Byte at tile-relative index i.  Outside the segment reads as '\n' (a record can neither start before the
-// segment nor continue past its end); outside the staged window falls back to a global load.
-__device__ __forceinline__ uint32_t ld_byte(const TileView &t, int i) {
-    if (i < t.lo || i >= t.hi) return '\n';
-    if (i >= t.sm_lo && i < t.sm_hi) return t.sm[i];
-    return __ldg(t.g + i);
-}
 
 // POS field starting at index d: Rust `usize::from_str` (optional '+', >= 1 digit, no other bytes) terminated
 // by '\t'; 0 is rejected (noodles maps "0" to None and the column is non-nullable).  Returns the predicate
@@ -158,21 +137,6 @@ struct LineConsts {
     int has_chrom, has_interval, wide_chrom;  // wide_chrom: the pattern reaches into window words 2..3
 };
 
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t x, uint32_t s) {
-    uint32_t r;
-    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));  // shift amounts >= 32 give 0
-    return r;
-}
-
-// 0x80 flags in up to 16 bytes -> 16-bit mask, bit i = byte i flagged (IDP.4A: sum of flag * weight, flags are 128)
-__device__ __forceinline__ uint32_t pack16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
-    uint32_t a = __dp4a(f0, 0x08040201u, 0u);
-    a = __dp4a(f1, 0x80402010u, a);
-    uint32_t b = __dp4a(f2, 0x08040201u, 0u);
-    b = __dp4a(f3, 0x80402010u, b);
-    return (a >> 7) | (b << 1);
-}
-
 // Parses the line whose first byte is tile byte `ls`; `sa` is the shared-window address of tile byte 0.
 // Returns the predicate (0/1); sets `slow` when the line needs the scalar routine instead (nothing has been
 // decided or reported then).
@@ -259,33 +223,6 @@ __device__ __forceinline__ uint32_t chunk_may_hit(const uint4 w, const uint32_t 
 // ===================================================================================================
 // The kernel
 // ===================================================================================================
-constexpr int kQueue = 256;  // line starts a warp collects before it parses them (uint16 each)
-
-struct StageMeta {
-    const uint8_t *g;  // global address of tile byte 0
-    int lo;            // first tile-relative index that is staged and inside the segment (>= 0: first tile of its segment)
-    int hi;            // bytes from tile byte 0 to the end of the segment (clamped to 2^30)
-};
-
-template <int U, int S, int WARPS>
-struct SmemLayout {
-    static constexpr int TILE = 512 * U;
-    static constexpr int STAGE = ((kPre + TILE + kHalo + 127) / 128) * 128;
-    static constexpr size_t ring = 0;
-    static constexpr size_t bars = (size_t)WARPS * S * STAGE;
-    static constexpr size_t meta = bars + (size_t)WARPS * S * sizeof(uint64_t);
-    static constexpr size_t queue = meta + (size_t)WARPS * S * sizeof(StageMeta);
-    static constexpr size_t total = queue + (size_t)WARPS * kQueue * sizeof(uint16_t);
-};
-
-template <int U, int S, int WARPS>
-constexpr int ctas_per_sm() {
-    const int by_smem = (int)((227 * 1024) / SmemLayout<U, S, WARPS>::total);
-    const int by_warps = 32 / WARPS;  // at most 32 resident warps: the parser wants >= 64 registers per thread
-    const int c = by_smem < by_warps ? by_smem : by_warps;
-    return c < 1 ? 1 : c;
-}
-
 template <int MODE, int U, int S, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_scan_kernel(const __grid_constant__ ScanArgs a) {
     constexpr bool LAZY = (MODE == kScanKey3 || MODE == kScanKey4);

@@ -379,4 +379,18 @@ int Ctx::ensure_scratch(size_t dev_bytes, size_t host_bytes) {
     return EXON_GPU_OK;
 }
 
+int Ctx::ensure_scratch_b(size_t dev_bytes) {
+    if (dev_bytes > scratch_b_cap) {
+        if (scratch_b) {
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            CUDA_TRY(cudaFree(scratch_b));
+            scratch_b = nullptr;
+            scratch_b_cap = 0;
+        }
+        CUDA_TRY(cudaMalloc(&scratch_b, dev_bytes));
+        scratch_b_cap = dev_bytes;
+    }
+    return EXON_GPU_OK;
+}
+
 }  // namespace exon

@@ -131,6 +131,18 @@ class Context:
         check(self.lib.exon_gpu_filter_agg_accumulate(self.handle, C.byref(arrow_array), C.byref(arrow_schema),
                                                       C.byref(pred), C.byref(agg), C.c_void_p(device_acc_ptr)))
 
+    def filter_agg_batches(self, batches, *, chrom_col: int = -1, pos_col: int = -1, region=None,
+                           kind: int = _abi.AGG_COUNT_STAR, value_col: int = -1):
+        """One launch over a list of device-resident VcfBatch objects (they share the first batch's schema)."""
+        n = len(batches)
+        arr = (C.POINTER(_abi.ArrowArray) * max(n, 1))(*[C.pointer(b.c_array) for b in batches])
+        pred = _abi.Pred(chrom_col, pos_col, region if region is not None else _abi.Region())
+        agg = _abi.Agg(kind, value_col)
+        out = _abi.Partial()
+        check(self.lib.exon_gpu_filter_agg_batches(self.handle, arr, n, C.byref(batches[0].c_schema), C.byref(pred),
+                                                   C.byref(agg), C.byref(out)))
+        return out.count, out.sum_i64, out.sum_f64
+
     def partial_read(self, device_acc_ptr: int, sum_is_integer: bool = True):
         out = _abi.Partial()
         check(self.lib.exon_gpu_partial_read(self.handle, C.c_void_p(device_acc_ptr), int(sum_is_integer), C.byref(out)))
@@ -269,6 +281,15 @@ class VcfStream:
         out = C.c_int64()
         check(self.lib.exon_gpu_vcf_body_bytes(self.handle, C.byref(out)))
         return out.value
+
+    def filter_agg(self, *, chrom_col: int = -1, pos_col: int = -1, region=None, kind: int = _abi.AGG_COUNT_STAR,
+                   value_col: int = -1):
+        """exon_gpu_vcf_filter_agg: (count, sum_i64, sum_f64) over every batch of this stream, columns kept in HBM."""
+        pred = _abi.Pred(chrom_col, pos_col, region if region is not None else _abi.Region())
+        agg = _abi.Agg(kind, value_col)
+        out = _abi.Partial()
+        check(self.lib.exon_gpu_vcf_filter_agg(self.handle, C.byref(pred), C.byref(agg), C.byref(out)))
+        return out.count, out.sum_i64, out.sum_f64
 
     def next_batch(self) -> VcfBatch | None:
         arr, sch = _abi.ArrowArray(), _abi.ArrowSchema()

@@ -207,6 +207,16 @@ int exon_gpu_filter_agg(exon_gpu_ctx *ctx, const struct ArrowArray *batch, const
  * synchronises until exon_gpu_partial_read.  This is AggregateExec(Partial)'s accumulator living across batches. */
 int exon_gpu_filter_agg_accumulate(exon_gpu_ctx *ctx, const struct ArrowArray *batch, const struct ArrowSchema *schema,
                                    const exon_gpu_pred *pred, const exon_gpu_agg *agg, exon_gpu_partial *device_acc);
+/* The same operators over MANY device-resident batches in one kernel launch (all batches share `schema`); the
+ * partial comes back on the host.  One launch per partition instead of one per 8192-row batch. */
+int exon_gpu_filter_agg_batches(exon_gpu_ctx *ctx, const struct ArrowArray *const *batches, int32_t n_batches,
+                                const struct ArrowSchema *schema, const exon_gpu_pred *pred, const exon_gpu_agg *agg,
+                                exon_gpu_partial *out);
+/* VCFScan -> FilterExec -> AggregateExec(Partial) with the record batches kept in HBM: builds the projected columns
+ * of everything fed so far (the batches exon_gpu_vcf_next_batch would hand out) if that has not happened yet, then
+ * filters and aggregates all of them in one launch.  pred->chrom_col / pos_col and agg->value_col are indices into
+ * the stream's projection. */
+int exon_gpu_vcf_filter_agg(exon_gpu_stream *s, const exon_gpu_pred *pred, const exon_gpu_agg *agg, exon_gpu_partial *out);
 int exon_gpu_partial_read(exon_gpu_ctx *ctx, const exon_gpu_partial *device_acc, int sum_is_integer, exon_gpu_partial *out);
 int exon_gpu_memset(exon_gpu_ctx *ctx, void *device_ptr, int value, size_t bytes);
 

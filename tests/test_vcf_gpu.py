@@ -287,3 +287,109 @@ def test_properties_large(gpu_ctx):
         assert s.filter_count(make_region(None, 1_000_000, 2_000_000)) == cols.truth_count(None, 1_000_000, 2_000_000)
         pos = np.concatenate([b.column("pos") for b in s.batches()])
         assert np.array_equal(pos, cols.pos)
+
+
+# ---- K2 specifics: ranks inside a tile, files inside one run, stream-level K3 -------------------------------------
+
+def py_rows(text: bytes):
+    """(chrom bytes, pos) of every record by plain Python splitting (for inputs the oracle rejects: < 8 fields)."""
+    rows = []
+    for ln in text.split(b"\n"):
+        if not ln or ln.startswith(b"#"):
+            continue
+        f = ln.split(b"\t")
+        rows.append((f[0], int(f[1])))
+    return rows
+
+
+def gpu_rows(ctx, feeds, batch_rows=8192, **kw):
+    with ctx.open_vcf(batch_rows=batch_rows, **kw) as s:
+        for f in feeds:
+            s.feed(f, is_last=True)
+        out, sizes = [], []
+        for b in s.batches():
+            sizes.append(b.num_rows)
+            out += list(zip([c.encode() for c in b.chrom_strings()], [int(p) for p in b.column("pos")]))
+            b.release()
+        return out, sizes
+
+
+def test_columns_short_lines_rank_exactly(gpu_ctx):
+    """Lines shorter than 16 bytes put several line starts into one 16-byte chunk: rows must keep text order."""
+    rng = np.random.default_rng(11)
+    names = [b"1", b"22", b"X", b"chr1"]
+    lines = [names[int(rng.integers(0, 4))] + b"\t" + str(int(rng.integers(1, 10 ** int(rng.integers(1, 8))))).encode() + b"\t."
+             for _ in range(50_000)]
+    text = b"#h\n" + b"\n".join(lines) + b"\n"
+    got, sizes = gpu_rows(gpu_ctx, [text], batch_rows=1000)
+    assert got == py_rows(text) and sizes == [1000] * 50
+    # > 256 line starts inside one 512-byte warp row: 2-byte names, 1-digit positions ("1\t5\t\n" = 5 bytes)
+    text2 = b"".join(b"%d\t%d\t\n" % (i % 10, 1 + i % 9) for i in range(20_000))
+    got2, _ = gpu_rows(gpu_ctx, [text2])
+    assert got2 == py_rows(text2)
+    with gpu_ctx.open_vcf() as s:
+        s.feed(text2)
+        assert s.filter_count(make_region("3", 4, 4)) == sum(1 for c, p in got2 if c == b"3" and p == 4)
+
+
+def test_columns_files_share_a_run(gpu_ctx, synth_small):
+    """Host feeds append consecutive files to the same arena run; batches must still restart at every file,
+    including empty and header-only files in between (FileStream opens one batch stream per file)."""
+    cols, files = synth_small
+    feeds = [files[0][:30_011], b"", make_vcf([]), make_vcf([("7", "77")], trailing_newline=False), files[1][:50_000 - 13],
+             make_vcf([("chrUn_KI270742v1_decoy_long_name", "5")] * 3)]
+    feeds = [bytes(f) for f in feeds]
+    feeds = [f if (not f or f.endswith(b"\n") or f.count(b"\n") < 3) else f[: f.rfind(b"\n") + 1] for f in feeds]
+    want_rows, want_sizes = [], []
+    for f in feeds:
+        for b in oracle.read_batches(f, batch_size=100):
+            want_sizes.append(b["rows"])
+            off, val = b["chrom_offsets"], b["chrom_values"].tobytes()
+            want_rows += [(val[off[i]:off[i + 1]], int(b["pos"][i])) for i in range(b["rows"])]
+    got, sizes = gpu_rows(gpu_ctx, feeds, batch_rows=100)
+    assert sizes == want_sizes and got == want_rows
+
+
+@pytest.mark.parametrize("on_device", [False, True])
+def test_stream_filter_agg_matches_fused_scan(gpu_ctx, synth_small, on_device):
+    """exon_gpu_vcf_filter_agg (K2 columns kept in HBM -> multi-batch K3, one launch) == K1 == oracle."""
+    cols, files = synth_small
+    with gpu_ctx.open_vcf(columns_on_device=on_device, batch_rows=1000) as s:
+        for f in files:
+            s.feed(f, is_last=True)
+        for chrom, lo, hi in QUERIES:
+            want = oracle.filter_count_files(files, chrom, lo, hi, target_partitions=4)[0]
+            rg = make_region(chrom, lo, hi)
+            cnt, _, _ = s.filter_agg(chrom_col=0, pos_col=1, region=rg)
+            assert cnt == want == s.filter_count(rg), (chrom, lo, hi)
+        # SUM / AVG state over pos for one contig
+        sel = (cols.contig == 0) & (cols.pos >= 1_000_000) & (cols.pos <= 2_000_000)
+        cnt, si, sf = s.filter_agg(chrom_col=0, pos_col=1, region=make_region("1", 1_000_000, 2_000_000), kind=_abi.AGG_SUM, value_col=1)
+        assert cnt == int(sel.sum()) and si == int(cols.pos[sel].sum()) and sf == float(si)
+        cnt, si, _ = s.filter_agg(kind=_abi.AGG_AVG, value_col=1)
+        assert cnt == cols.n and si == int(cols.pos.sum())
+        with pytest.raises(ExonGpuError):
+            s.filter_agg(kind=_abi.AGG_SUM, value_col=0)
+    with gpu_ctx.open_vcf(projection=(1,)) as s:  # the predicate may only read projected columns
+        s.feed(files[0])
+        assert s.filter_agg(pos_col=0, region=make_region(None, 1, 10**9))[0] == s.rows()
+        with pytest.raises(ExonGpuError):
+            s.filter_agg(chrom_col=0, region=make_region("1"))
+
+
+def test_filter_agg_batches_one_launch(gpu_ctx, synth_small):
+    """exon_gpu_filter_agg_batches over the device-resident batches of a stream: one kernel for all of them."""
+    cols, files = synth_small
+    with gpu_ctx.open_vcf(columns_on_device=True, batch_rows=4096) as s:
+        for f in files:
+            s.feed(f, is_last=True)
+        batches = list(s.batches())
+        l0 = gpu_ctx.launch_count()
+        for chrom, lo, hi in QUERIES[:6]:
+            cnt, _, _ = gpu_ctx.filter_agg_batches(batches, chrom_col=0, pos_col=1, region=make_region(chrom, lo, hi))
+            assert cnt == cols.truth_count(chrom, lo, hi)
+        assert gpu_ctx.launch_count() - l0 == 6
+        cnt, si, _ = gpu_ctx.filter_agg_batches(batches, kind=_abi.AGG_SUM, value_col=1)
+        assert cnt == cols.n and si == int(cols.pos.sum())
+        for b in batches:
+            b.release()
