@@ -28,6 +28,8 @@ SYMBOLS = [
     "exon_gpu_filter_agg", "exon_gpu_nccl_unique_id", "exon_gpu_nccl_init", "exon_gpu_allreduce_partial",
     "exon_gpu_vcf_filter_count_global", "exon_gpu_filter_agg_accumulate", "exon_gpu_partial_read", "exon_gpu_memset",
     "exon_gpu_region_udf", "exon_gpu_filter_agg_batches", "exon_gpu_vcf_filter_agg",
+    "exon_gpu_fastq_open", "exon_gpu_fastq_feed", "exon_gpu_fastq_filter_count", "exon_gpu_fastq_rows",
+    "exon_gpu_stream_close", "exon_gpu_stream_reset", "exon_gpu_stream_body_bytes",
 ]
 
 
@@ -47,6 +49,15 @@ class VcfOpts(C.Structure):
     _fields_ = [("batch_rows", C.c_int32), ("n_projection", C.c_int32), ("projection", C.POINTER(C.c_int32)),
                 ("columns_on_device", C.c_int32), ("pushdown", C.POINTER(Region)), ("strict", C.c_int32),
                 ("kernel_variant", C.c_int32)]
+
+
+class FastqOpts(C.Structure):
+    _fields_ = [("batch_rows", C.c_int32), ("n_projection", C.c_int32), ("projection", C.POINTER(C.c_int32)),
+                ("columns_on_device", C.c_int32)]
+
+
+class FastqPred(C.Structure):
+    _fields_ = [("phred_offset", C.c_int32), ("pad_", C.c_int32), ("min_mean_num", C.c_int64), ("min_mean_den", C.c_int64)]
 
 
 class ArrowSchema(C.Structure):
@@ -127,6 +138,13 @@ def load():
         "exon_gpu_filter_agg_batches": [vp, C.POINTER(C.POINTER(ArrowArray)), i32, C.POINTER(ArrowSchema), C.POINTER(Pred),
                                         C.POINTER(Agg), C.POINTER(Partial)],
         "exon_gpu_vcf_filter_agg": [vp, C.POINTER(Pred), C.POINTER(Agg), C.POINTER(Partial)],
+        "exon_gpu_fastq_open": [vp, C.POINTER(FastqOpts), C.POINTER(vp)],
+        "exon_gpu_fastq_feed": [vp, vp, C.c_size_t, C.c_int, C.c_int],
+        "exon_gpu_fastq_filter_count": [vp, C.POINTER(FastqPred), C.POINTER(i64)],
+        "exon_gpu_fastq_rows": [vp, C.POINTER(i64)],
+        "exon_gpu_stream_close": [vp],
+        "exon_gpu_stream_reset": [vp],
+        "exon_gpu_stream_body_bytes": [vp, C.POINTER(i64)],
         "exon_gpu_partial_read": [vp, vp, C.c_int, C.POINTER(Partial)],
         "exon_gpu_memset": [vp, vp, C.c_int, C.c_size_t],
         "exon_gpu_region_udf": [vp, C.c_int, C.POINTER(ArrowArray), C.POINTER(ArrowSchema), C.c_int, C.POINTER(Pred), vp, vp],

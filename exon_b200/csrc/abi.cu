@@ -113,6 +113,13 @@ int exon_gpu_ctx_create(int device, void *cuda_stream, exon_gpu_ctx **out) {
         }
         c->own_stream = true;
     }
+    {  // keep freed column stores cached in the stream-ordered pool instead of returning them to the driver
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     *out = c;

@@ -125,57 +125,76 @@ __global__ void __launch_bounds__(kFaThreads) filter_agg_kernel(const __grid_con
 // thread evaluates kRowsPerThread rows whose loads are issued together (coalesced 8-byte / 4-byte accesses, four
 // independent rows in flight per thread).  The CHROM bytes are fetched only for rows whose POS and CHROM length
 // already match.
-constexpr int kRowsPerThread = 4;
+constexpr int kRowsPerThread = 8;
 constexpr int kUnitRows = kFaThreads * kRowsPerThread;
 
+template <bool NULLS>
 __global__ void __launch_bounds__(kFaThreads) filter_agg_multi_kernel(const __grid_constant__ FilterAggArgs a, const FaBatchDesc *descs,
                                                                       int n_batches, int units_per_batch) {
     unsigned long long cnt = 0;
     long long si = 0;
     double sf = 0.0;
+    uint32_t cnt32 = 0;
+    const int lane = threadIdx.x & 31;
     const int64_t n_units = (int64_t)n_batches * units_per_batch;
+    // lo <= v <= hi as one unsigned compare: (v - lo) <= (hi - lo); an empty interval never matches
+    const unsigned long long span = a.hi >= a.lo ? (unsigned long long)a.hi - (unsigned long long)a.lo : 0ull;
+    const bool never = a.has_pos && a.hi < a.lo;
     for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int b = (int)(unit / units_per_batch);
-        const int64_t base = (unit - (int64_t)b * units_per_batch) * kUnitRows;
+        const int base = (int)(unit - (int64_t)b * units_per_batch) * kUnitRows;
         const FaBatchDesc *d = descs + b;
-        const int64_t n_rows = d->n_rows;
-        if (base >= n_rows) continue;
-        const int64_t *pos = d->pos + d->pos_off;
-        const int32_t *off = d->chrom_offsets + d->chrom_off;
+        const int64_t n64 = __ldg(&d->n_rows);
+        if (base >= n64) continue;
+        const int n = (int)(n64 - base < kUnitRows ? n64 - base : kUnitRows);  // rows of this unit
+        const int64_t pos_off = __ldg(&d->pos_off), chrom_off = __ldg(&d->chrom_off);
+        const int64_t *pos = a.has_pos ? reinterpret_cast<const int64_t *>(__ldg(reinterpret_cast<const unsigned long long *>(&d->pos))) + pos_off + base : nullptr;
+        const int32_t *off = a.has_chrom ? reinterpret_cast<const int32_t *>(__ldg(reinterpret_cast<const unsigned long long *>(&d->chrom_offsets))) + chrom_off + base : nullptr;
         int64_t pv[kRowsPerThread];
         int32_t o0[kRowsPerThread], o1[kRowsPerThread];
-        bool in[kRowsPerThread];
+        // all loads of the unit are issued before anything is consumed (8 x 8 B + 8 x 4 B in flight per thread)
 #pragma unroll
         for (int k = 0; k < kRowsPerThread; ++k) {
-            const int64_t i = base + k * kFaThreads + threadIdx.x;
-            in[k] = i < n_rows;
+            const int i = k * kFaThreads + (int)threadIdx.x;
             pv[k] = 0;
-            o0[k] = o1[k] = 0;
-            if (in[k]) {
-                if (a.has_pos) pv[k] = pos[i];
-                if (a.has_chrom) {
-                    o0[k] = off[i];
-                    o1[k] = off[i + 1];
-                }
+            o0[k] = 0;
+            if (i < n) {
+                if (a.has_pos) pv[k] = __ldg(pos + i);
+                if (a.has_chrom) o0[k] = __ldg(off + i);
+            }
+        }
+        if (a.has_chrom) {
+            // end offset of row i = start offset of row i + 1: taken from the next lane, loaded only by lane 31
+#pragma unroll
+            for (int k = 0; k < kRowsPerThread; ++k) {
+                const int i = k * kFaThreads + (int)threadIdx.x;
+                o1[k] = __shfl_down_sync(0xFFFFFFFFu, o0[k], 1);
+                if ((lane == 31 || i + 1 >= n) && i < n) o1[k] = __ldg(off + i + 1);
             }
         }
 #pragma unroll
         for (int k = 0; k < kRowsPerThread; ++k) {
-            if (!in[k]) continue;
-            const int64_t i = base + k * kFaThreads + threadIdx.x;
-            bool sel = true;
-            if (a.has_pos) sel = bit_set(d->pos_valid, i + d->pos_off) & (pv[k] >= a.lo) & (pv[k] <= a.hi);
-            if (sel && a.has_chrom) {
-                sel = bit_set(d->chrom_valid, i + d->chrom_off) && (o1[k] - o0[k]) == a.lit_len;
-                for (int32_t j = 0; sel && j < a.lit_len; ++j) sel = d->chrom_values[o0[k] + j] == a.lit[j];
-            }
+            const int i = k * kFaThreads + (int)threadIdx.x;
+            bool sel = i < n && !never;
+            if (a.has_pos) sel &= ((unsigned long long)pv[k] - (unsigned long long)a.lo) <= span;
+            if (a.has_chrom) sel &= (o1[k] - o0[k]) == a.lit_len;
             if (!sel) continue;
+            // rare from here on (rows whose POS and CHROM length already match)
+            const int64_t row = (int64_t)base + i;
+            if (NULLS && a.has_pos && !bit_set(d->pos_valid, row + pos_off)) continue;
+            if (a.has_chrom) {
+                if (NULLS && !bit_set(d->chrom_valid, row + chrom_off)) continue;
+                const uint8_t *cv = d->chrom_values + o0[k];
+                bool eq = true;
+                for (int32_t j = 0; eq && j < a.lit_len; ++j) eq = cv[j] == a.lit[j];
+                if (!eq) continue;
+            }
             if (a.agg_kind == EXON_GPU_AGG_COUNT_STAR) {
-                ++cnt;
+                ++cnt32;
             } else {
-                const int64_t r = i + d->val_off;
-                if (!bit_set(d->val_valid, r)) continue;
-                ++cnt;
+                const int64_t r = row + d->val_off;
+                if (NULLS && !bit_set(d->val_valid, r)) continue;
+                ++cnt32;
                 if (a.agg_kind != EXON_GPU_AGG_COUNT) {
                     if (a.val_type == kValI64) si += static_cast<const int64_t *>(d->val)[r];
                     else if (a.val_type == kValI32) si += static_cast<const int32_t *>(d->val)[r];
@@ -184,6 +203,8 @@ __global__ void __launch_bounds__(kFaThreads) filter_agg_multi_kernel(const __gr
                 }
             }
         }
+        cnt += cnt32;
+        cnt32 = 0;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -360,9 +381,15 @@ int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, i
     a.out = d_out;
     const int upb = (int)((max_rows + kUnitRows - 1) / kUnitRows);
     const int64_t n_units = (int64_t)n_batches * upb;
-    const int grid = (int)std::min<int64_t>(n_units, (int64_t)c->sm_count * 8);
+    static int occ = 0;  // persistent grid = exactly one resident wave
+    if (!occ) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, filter_agg_multi_kernel<true>, kFaThreads, 0));
+        if (occ < 1) occ = 1;
+    }
+    const int grid = (int)std::min<int64_t>(n_units, (int64_t)c->sm_count * occ);
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    filter_agg_multi_kernel<<<grid, kFaThreads, 0, c->stream>>>(a, d_descs, n_batches, upb);
+    if (k.has_nulls) filter_agg_multi_kernel<true><<<grid, kFaThreads, 0, c->stream>>>(a, d_descs, n_batches, upb);
+    else filter_agg_multi_kernel<false><<<grid, kFaThreads, 0, c->stream>>>(a, d_descs, n_batches, upb);
     c->launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     if (timed) {
@@ -459,6 +486,7 @@ int exon_gpu_filter_agg_batches(exon_gpu_ctx *c, const struct ArrowArray *const 
         d.val_off = a.val_off;
         d.n_rows = a.n_rows;
         k.val_type = a.val_type;
+        if (a.chrom_valid || a.pos_valid || a.val_valid) k.has_nulls = 1;
         max_rows = std::max(max_rows, a.n_rows);
     }
     const size_t table = ((sizeof(FaBatchDesc) * (size_t)n_batches + 255) & ~(size_t)255);

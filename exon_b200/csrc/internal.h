@@ -69,7 +69,17 @@ struct Run {
     bool ends_with_newline;
 };
 
+// One piece of a run that belongs to a single file (runs are cut at the recorded file ends).
+struct Piece {
+    const uint8_t *base;
+    int64_t len;
+    bool starts_file;
+};
+
+enum StreamFormat { kFmtVcf = 0, kFmtFastq = 1 };
+
 struct VcfStream {
+    int fmt = kFmtVcf;  // FASTQ streams share the arena / run / file-mark machinery; they have no header to skip
     Ctx *ctx = nullptr;
     int batch_rows = 8192;
     std::vector<int> projection;
@@ -121,6 +131,7 @@ struct VcfStream {
     int launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_segs, int64_t tiles, unsigned long long *d_count,
                     unsigned long long *d_flags, bool timed);
     int build_seg_table();
+    void cut_pieces(std::vector<Piece> &out) const;
     int eager_scan(bool final_flush);
     void release_all();
 };
@@ -146,10 +157,14 @@ struct FaCommon {
     int32_t has_pos;
     int64_t lo, hi;
     int32_t val_type, agg_kind;
+    int32_t has_nulls;  // some batch carries a validity bitmap
 };
 int fa_common_from(const exon_gpu_pred *pred, const exon_gpu_agg *agg, FaCommon &k);
 int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, int64_t max_rows, const FaCommon &k,
                             unsigned long long *d_out, bool timed);
+
+// defined in fastq_scan.cu
+int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count, int64_t *out_rows);
 
 // defined in vcf_columns.cu
 int columns_filter_agg(VcfStream *s, const exon_gpu_pred *pred, const exon_gpu_agg *agg, exon_gpu_partial *out);

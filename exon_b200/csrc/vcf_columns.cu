@@ -537,41 +537,6 @@ void fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
     out->private_data = p;
 }
 
-// One piece of a run that belongs to a single file.
-struct Piece {
-    const uint8_t *base;
-    int64_t len;
-    bool starts_file;
-};
-
-// Cuts the resident runs at the recorded file ends (a run may hold the tail of one file and the head of the
-// next when the host fed them back to back).
-void cut_pieces(const VcfStream *s, std::vector<Piece> &out) {
-    out.clear();
-    bool pending = true;
-    size_t mi = 0;
-    const auto &marks = s->file_marks;
-    for (size_t r = 0; r < s->runs.size(); ++r) {
-        const Run &run = s->runs[r];
-        int64_t at = 0;
-        while (mi < marks.size() && marks[mi].run <= r) {
-            if (marks[mi].run == r) {
-                const int64_t end = std::min<int64_t>(marks[mi].len, run.len);
-                if (end > at) {
-                    out.push_back(Piece{run.base + at, end - at, pending});
-                    at = end;
-                }
-                pending = true;  // whatever follows belongs to the next file
-            }
-            ++mi;
-        }
-        if (run.len > at) {
-            out.push_back(Piece{run.base + at, run.len - at, pending});
-            pending = false;
-        }
-    }
-}
-
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int build_columns(VcfStream *s) {
@@ -591,7 +556,7 @@ int build_columns(VcfStream *s) {
     c->batch_row0.assign(1, 0);
 
     std::vector<Piece> pieces;
-    cut_pieces(s, pieces);
+    s->cut_pieces(pieces);
     if (pieces.empty()) return EXON_GPU_OK;  // zero rows
     constexpr int kTile = 512 * kColU;
     std::vector<ScanSeg> h_segs;
@@ -697,10 +662,12 @@ int build_columns(VcfStream *s) {
     uint8_t *scb = (uint8_t *)ctx->scratch_b;
     uint32_t *d_off32 = (uint32_t *)(scb + ob_off32);
     long long *d_brow = (long long *)(scb + ob_brow), *d_bv0 = (long long *)(scb + ob_bv0);
-    if (c->want_pos) CUDA_TRY(cudaMalloc((void **)&c->d_pos, sizeof(int64_t) * (size_t)n_rows));
+    // outputs come from the device's stream-ordered pool (release threshold raised in ctx_create): a steady-state
+    // query re-uses the memory the previous query's batches released instead of paying cudaMalloc
+    if (c->want_pos) CUDA_TRY(cudaMallocAsync((void **)&c->d_pos, sizeof(int64_t) * (size_t)n_rows, st));
     if (c->want_chrom) {
-        CUDA_TRY(cudaMalloc((void **)&c->d_values, (size_t)std::max<unsigned long long>(total_values, 1)));
-        CUDA_TRY(cudaMalloc((void **)&c->d_offsets, sizeof(int32_t) * (size_t)(c->n_batches * (c->batch_rows + 1))));
+        CUDA_TRY(cudaMallocAsync((void **)&c->d_values, (size_t)std::max<unsigned long long>(total_values, 1), st));
+        CUDA_TRY(cudaMallocAsync((void **)&c->d_offsets, sizeof(int32_t) * (size_t)(c->n_batches * (c->batch_rows + 1)), st));
         CUDA_TRY(cudaMemcpyAsync(d_brow, c->batch_row0.data(), nb1 * sizeof(long long), cudaMemcpyHostToDevice, st));
     }
     a.pos = c->d_pos;

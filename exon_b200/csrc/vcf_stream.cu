@@ -2,6 +2,7 @@
 // launch of the fused scan (K1).  Host-side work here is framing only (what VCFOpener::open / read_header do,
 // exon/exon-core/src/datasources/vcf/file_opener/unindex_file_opener.rs:48-92); records are never parsed on
 // the host.
+#include <algorithm>
 #include <cstring>
 
 #include "internal.h"
@@ -58,7 +59,7 @@ void VcfStream::release_all() {
     body_bytes = 0;
     eager_scanned = 0;
     eager_runs_done = 0;
-    hdr = kAtLineStart;
+    hdr = fmt == kFmtVcf ? kAtLineStart : kBody;
     file_open = false;
     last_byte_newline = true;
     segs_dirty = true;
@@ -109,7 +110,7 @@ int VcfStream::end_file() {
         body_bytes = before;
     }
     if (!runs.empty()) file_marks.push_back(FileMark{runs.size() - 1, runs.back().len});
-    hdr = kAtLineStart;
+    hdr = fmt == kFmtVcf ? kAtLineStart : kBody;
     file_open = false;
     return EXON_GPU_OK;
 }
@@ -177,7 +178,7 @@ int VcfStream::feed_device(const uint8_t *text, size_t len, bool is_last) {
     }
     if (is_last) {
         if (!runs.empty()) file_marks.push_back(FileMark{runs.size() - 1, runs.back().len});
-        hdr = kAtLineStart;
+        hdr = fmt == kFmtVcf ? kAtLineStart : kBody;
         file_open = false;
     }
     if (has_pushdown) return eager_scan(false);
@@ -377,6 +378,34 @@ int Ctx::ensure_scratch(size_t dev_bytes, size_t host_bytes) {
         h_scratch_cap = host_bytes;
     }
     return EXON_GPU_OK;
+}
+
+// Cuts the resident runs at the recorded file ends (a run may hold the tail of one file and the head of the
+// next when the host fed them back to back).
+void VcfStream::cut_pieces(std::vector<Piece> &out) const {
+    out.clear();
+    bool pending = true;
+    size_t mi = 0;
+    const auto &marks = file_marks;
+    for (size_t r = 0; r < runs.size(); ++r) {
+        const Run &run = runs[r];
+        int64_t at = 0;
+        while (mi < marks.size() && marks[mi].run <= r) {
+            if (marks[mi].run == r) {
+                const int64_t end = std::min<int64_t>(marks[mi].len, run.len);
+                if (end > at) {
+                    out.push_back(Piece{run.base + at, end - at, pending});
+                    at = end;
+                }
+                pending = true;  // whatever follows belongs to the next file
+            }
+            ++mi;
+        }
+        if (run.len > at) {
+            out.push_back(Piece{run.base + at, run.len - at, pending});
+            pending = false;
+        }
+    }
 }
 
 int Ctx::ensure_scratch_b(size_t dev_bytes) {

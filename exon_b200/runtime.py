@@ -98,6 +98,9 @@ class Context:
     def open_vcf(self, **kw) -> "VcfStream":
         return VcfStream(self, **kw)
 
+    def open_fastq(self, **kw) -> "FastqStream":
+        return FastqStream(self, **kw)
+
     # ---- multi-GPU final aggregate ----
     def nccl_unique_id(self) -> bytes:
         buf = C.create_string_buffer(_abi.NCCL_ID_BYTES)
@@ -306,3 +309,61 @@ class VcfStream:
             if b is None:
                 return
             yield b
+
+
+class FastqStream:
+    """exon_gpu_stream opened with exon_gpu_fastq_open: one partition stream over a group of FASTQ files."""
+
+    def __init__(self, ctx: Context, *, batch_rows: int = 8192):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        opts = _abi.FastqOpts(batch_rows, 0, None, 0)
+        self.handle = C.c_void_p()
+        check(self.lib.exon_gpu_fastq_open(ctx.handle, C.byref(opts), C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.lib.exon_gpu_stream_close(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self):
+        check(self.lib.exon_gpu_stream_reset(self.handle))
+
+    def feed(self, data, *, is_last: bool = True, device_ptr: int | None = None, nbytes: int | None = None):
+        if device_ptr is not None:
+            check(self.lib.exon_gpu_fastq_feed(self.handle, C.c_void_p(device_ptr), int(nbytes), 1, int(is_last)))
+            return
+        if isinstance(data, PinnedBuffer):
+            data = data.array
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        self._last_host = data
+        check(self.lib.exon_gpu_fastq_feed(self.handle, C.c_void_p(data.ctypes.data), data.size, 0, int(is_last)))
+
+    def filter_count(self, min_mean=None, phred_offset: int = 33) -> int:
+        """records with mean(quality) > min_mean (an int, or a (num, den) pair); None -> COUNT(*)."""
+        out = C.c_int64()
+        if min_mean is None:
+            check(self.lib.exon_gpu_fastq_filter_count(self.handle, None, C.byref(out)))
+            return out.value
+        num, den = min_mean if isinstance(min_mean, tuple) else (int(min_mean), 1)
+        pred = _abi.FastqPred(phred_offset, 0, num, den)
+        check(self.lib.exon_gpu_fastq_filter_count(self.handle, C.byref(pred), C.byref(out)))
+        return out.value
+
+    def rows(self) -> int:
+        out = C.c_int64()
+        check(self.lib.exon_gpu_fastq_rows(self.handle, C.byref(out)))
+        return out.value
+
+    def body_bytes(self) -> int:
+        out = C.c_int64()
+        check(self.lib.exon_gpu_stream_body_bytes(self.handle, C.byref(out)))
+        return out.value

@@ -173,6 +173,38 @@ int exon_gpu_vcf_rows(exon_gpu_stream *s, int64_t *out_rows);
 /* Body bytes (text minus headers) resident for this stream: the algorithmic bytes of the fused scan. */
 int exon_gpu_vcf_body_bytes(exon_gpu_stream *s, int64_t *out_bytes);
 
+/* ---- FASTQ partition stream (BASELINE configs[1]) ------------------------------------ */
+/* FASTQScan::execute + FASTQOpener::open + BatchReader (exon/exon-core/src/datasources/fastq/scanner.rs:126,
+ * fastq/file_opener.rs:51, exon/exon-fastq/src/batch_reader.rs:56-82).  A FASTQ stream is an exon_gpu_stream: it
+ * shares the arena, the host/device feeds and the file framing with the VCF stream; there is no header. */
+typedef struct {
+    int32_t batch_rows;        /* session batch size (8192) */
+    int32_t n_projection;      /* must be 0 for now: the fused query below is the only consumer */
+    const int32_t *projection; /* FASTQ file schema: 0 name, 1 description, 2 sequence, 3 quality_scores (exon-fastq/src/config.rs:79-88) */
+    int32_t columns_on_device;
+} exon_gpu_fastq_opts;
+/* `mean(quality) > min_mean_num / min_mean_den` with Phred score = byte - phred_offset (33:
+ * exon/exon-core/src/udfs/sequence/quality_score_string_to_list.rs:80-93), evaluated over integers:
+ * (sum(byte) - phred_offset * len) * den > num * len; a record with an empty quality string is not selected. */
+typedef struct {
+    int32_t phred_offset;
+    int32_t pad_;
+    int64_t min_mean_num;
+    int64_t min_mean_den; /* > 0 */
+} exon_gpu_fastq_pred;
+int exon_gpu_fastq_open(exon_gpu_ctx *ctx, const exon_gpu_fastq_opts *opts, exon_gpu_stream **out);
+/* Same contract as exon_gpu_vcf_feed: consecutive byte ranges of one file, is_last ends the file. */
+int exon_gpu_fastq_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last);
+/* Fused scan -> filter -> COUNT over everything fed so far (pred == NULL: COUNT(*) = number of records).  Fails with
+ * EXON_GPU_ERR_PARSE where noodles' reader would: a definition line that does not start with '@', a third line
+ * that does not start with '+', a file that ends after the first or second line of a record. */
+int exon_gpu_fastq_filter_count(exon_gpu_stream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count);
+int exon_gpu_fastq_rows(exon_gpu_stream *s, int64_t *out_rows);
+/* Format-independent stream calls (the exon_gpu_vcf_* spellings remain valid for VCF streams). */
+int exon_gpu_stream_close(exon_gpu_stream *s);
+int exon_gpu_stream_reset(exon_gpu_stream *s);
+int exon_gpu_stream_body_bytes(exon_gpu_stream *s, int64_t *out_bytes);
+
 /* ---- columnar filter + aggregate over Arrow buffers (a8-a9) ---------------------------------------------- */
 enum { EXON_GPU_AGG_COUNT_STAR = 0, EXON_GPU_AGG_COUNT = 1, EXON_GPU_AGG_SUM = 2, EXON_GPU_AGG_AVG = 3 };
 

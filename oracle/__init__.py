@@ -186,3 +186,100 @@ def interval_match(pos, interval: str):
     out = np.zeros(len(pos), dtype=np.uint8)
     lib().exo_interval_match(pos.ctypes.data, len(pos), lo, hi, out.ctypes.data)
     return out.astype(bool)
+
+
+# ---- FASTQ (oracle/fastq_oracle.c) ---------------------------------------------------------------------------
+
+class _Utf8Col(C.Structure):
+    _fields_ = [("offsets", C.POINTER(C.c_int32)), ("values", C.POINTER(C.c_uint8)), ("valid", C.POINTER(C.c_uint8)),
+                ("values_len", C.c_int64), ("values_cap", C.c_int64)]
+
+
+class FastqBatch(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("name", _Utf8Col), ("description", _Utf8Col), ("sequence", _Utf8Col),
+                ("quality", _Utf8Col)]
+
+
+_fq_ready = False
+
+
+def _fq():
+    global _fq_ready
+    L = lib()
+    if not _fq_ready:
+        L.exo_fastq_reader_open.restype = C.c_void_p
+        L.exo_fastq_reader_open.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        L.exo_fastq_reader_next.restype = C.c_int
+        L.exo_fastq_reader_next.argtypes = [C.c_void_p, C.POINTER(FastqBatch)]
+        L.exo_fastq_reader_close.argtypes = [C.c_void_p]
+        L.exo_fastq_reader_err_record.restype = C.c_int64
+        L.exo_fastq_reader_err_record.argtypes = [C.c_void_p]
+        L.exo_fastq_filter_count.restype = C.c_int64
+        L.exo_fastq_filter_count.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                             C.POINTER(C.c_int64)]
+        L.exo_fastq_filter_count_files.restype = C.c_int64
+        L.exo_fastq_filter_count_files.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int64,
+                                                   C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
+        L.exo_quality_scores_to_list.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        _fq_ready = True
+    return L
+
+
+def _utf8_rows(col: _Utf8Col, rows: int, nullable: bool = False):
+    off = np.ctypeslib.as_array(col.offsets, (rows + 1,))
+    val = bytes(np.ctypeslib.as_array(col.values, (max(int(col.values_len), 1),))[: int(col.values_len)])
+    valid = np.ctypeslib.as_array(col.valid, (rows,))
+    return [None if (nullable and not valid[i]) else val[off[i]:off[i + 1]] for i in range(rows)]
+
+
+def fastq_read_batches(data, batch_size: int = 8192):
+    """Yield one dict per reference batch: rows, name / description (None = NULL) / sequence / quality as bytes lists."""
+    a = _buf(data)
+    L = _fq()
+    r = L.exo_fastq_reader_open(a.ctypes.data, a.size, batch_size)
+    try:
+        b = FastqBatch()
+        while True:
+            rc = L.exo_fastq_reader_next(r, C.byref(b))
+            if rc == 0:
+                return
+            if rc < 0:
+                raise ValueError(f"malformed FASTQ record {L.exo_fastq_reader_err_record(r)}")
+            n = int(b.rows)
+            yield {"rows": n, "name": _utf8_rows(b.name, n), "description": _utf8_rows(b.description, n, True),
+                   "sequence": _utf8_rows(b.sequence, n), "quality": _utf8_rows(b.quality, n)}
+    finally:
+        L.exo_fastq_reader_close(r)
+
+
+def fastq_filter_count(data, min_mean=None, phred_offset: int = 33, batch_size: int = 8192):
+    """(count, rows): records with mean(quality) > min_mean (int or (num, den)); None -> COUNT(*)."""
+    a = _buf(data)
+    num, den = (0, 1) if min_mean is None else (min_mean if isinstance(min_mean, tuple) else (int(min_mean), 1))
+    rows = C.c_int64()
+    c = _fq().exo_fastq_filter_count(a.ctypes.data, a.size, batch_size, int(min_mean is not None), phred_offset, num, den,
+                                     C.byref(rows))
+    if c < 0:
+        raise ValueError("malformed FASTQ record")
+    return int(c), int(rows.value)
+
+
+def fastq_filter_count_files(files, min_mean=None, phred_offset: int = 33, target_partitions: int = 8, batch_size: int = 8192):
+    bufs = [_buf(f) for f in files]
+    n = len(bufs)
+    ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])
+    lens = (C.c_int64 * max(n, 1))(*[b.size for b in bufs])
+    num, den = (0, 1) if min_mean is None else (min_mean if isinstance(min_mean, tuple) else (int(min_mean), 1))
+    rows = C.c_int64()
+    c = _fq().exo_fastq_filter_count_files(ptrs, lens, n, target_partitions, batch_size, int(min_mean is not None),
+                                           phred_offset, num, den, C.byref(rows))
+    if c < 0:
+        raise ValueError("malformed FASTQ record")
+    return int(c), int(rows.value)
+
+
+def quality_scores_to_list(s: bytes):
+    a = _buf(s)
+    out = np.empty(a.size, dtype=np.int32)
+    _fq().exo_quality_scores_to_list(a.ctypes.data, a.size, out.ctypes.data)
+    return out.tolist()

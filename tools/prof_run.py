@@ -45,6 +45,13 @@ with Context(0) as ctx:
             c = lazy.filter_count(None)
         elif m == "interval":
             c = lazy.filter_count(_abi.make_region(None, 1_000_000, 2_000_000))
+        elif m in ("columns", "k3"):
+            with ctx.open_vcf(projection=(0, 1), columns_on_device=True) as st:
+                for d, f in zip(dbufs, files):
+                    st.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+                b = st.next_batch()  # K2: measure, scan, emit, offsets
+                b.release()
+                c = st.filter_agg(chrom_col=0, pos_col=1, region=region)[0] if m == "k3" else st.rows()
         else:
             raise SystemExit(m)
         print(m, c, f"{ctx.last_kernel_ms():.3f} ms", flush=True)
