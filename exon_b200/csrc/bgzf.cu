@@ -1,0 +1,592 @@
+// bgzf.cu -- BGZF / gzip inflate on the device.
+//
+// Replaces the CPU DEFLATE the reference runs in front of every parser: noodles-bgzf 0.34 `AsyncReader` /
+// async-compression `GzipDecoder` at exon/exon-core/src/datasources/vcf/file_opener/unindex_file_opener.rs:59-73,
+// exon/exon-core/src/streaming_bgzf.rs:22-118 (block framing), fastq/file_opener.rs:51.  A BGZF file is a series
+// of independent gzip members of <= 64 KiB uncompressed data each (SAM spec 4.1), so members decode in parallel:
+// the host walks the member headers (18 bytes per member, no payload byte is touched), the compressed bytes go
+// to HBM as they are, and ONE WARP inflates one member straight into the stream's arena:
+//   * lane 0 runs the serial part -- bit reader over 4-byte aligned words, dynamic/fixed Huffman headers, symbol
+//     decode through a 10-bit primary table in shared memory (canonical bit-by-bit decode for longer codes) --
+//     and emits up to 32 tokens (literal | length, distance) with their output positions into shared memory;
+//   * the whole warp then executes the tokens: literals are stored by 32 lanes at once, each match is copied by
+//     all lanes (period-aware when distance < length) through L2 (st.cg / ld.cg), with a warp barrier between
+//     dependent matches;
+//   * the primary tables are filled by all lanes (each lane resolves 32 table indices with the canonical decoder).
+// Thousands of members are in flight at once (warps_per_SM x 148), which is where the throughput comes from.
+// Plain single-member gzip (not BGZF) is handled by the same kernel with one warp (serial by nature).
+// Output is bit-exact DEFLATE (RFC 1951): tests compare with zlib on the reference's .gz fixtures and on
+// synthetic shards; ISIZE of every member is checked, CRC32 is not (documented in DESIGN.md).
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace exon {
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? EXON_GPU_ERR_OOM : EXON_GPU_ERR_CUDA, "%s: %s", \
+                        #expr, cudaGetErrorString(_e));                                                  \
+    } while (0)
+
+namespace {
+
+constexpr int kInfWarps = 4;      // warps per CTA (one member per warp at a time)
+constexpr int kLitBits = 10;      // primary table of the literal/length code
+constexpr int kDistBits = 8;      // primary table of the distance code
+constexpr int kTokens = 32;
+
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+struct WarpSmem {
+    uint16_t lit_tab[1 << kLitBits];  // sym << 4 | len, 0 = code longer than kLitBits
+    uint16_t dist_tab[1 << kDistBits];
+    uint16_t lit_sym[288];            // symbols in canonical order
+    uint16_t lit_cnt[16];             // codes per length
+    uint16_t dist_sym[32];
+    uint16_t dist_cnt[16];
+    uint16_t cl_sym[19];
+    uint16_t cl_cnt[16];
+    uint8_t lens[320];                // code lengths of the block being set up (HLIT + HDIST)
+    uint32_t tok[kTokens];            // literal: 0x80000000 | byte; match: len | dist << 9
+    uint32_t tpos[kTokens];           // output position of the token inside the member
+};
+
+// LSB-first bit reader over 4-byte aligned words (lane 0 only).
+struct BitReader {
+    const uint32_t *wp;  // next aligned word
+    const uint8_t *base; // payload byte 0
+    uint64_t buf;
+    int cnt;             // valid bits in buf
+    int64_t loaded;      // bits loaded so far
+    __device__ __forceinline__ void init(const uint8_t *p) {
+        base = p;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const int mis = (int)(a & 3);
+        wp = reinterpret_cast<const uint32_t *>(a - mis);
+        buf = (uint64_t)(__ldg(wp++) >> (8 * mis));
+        cnt = 32 - 8 * mis;
+        loaded = cnt;
+    }
+    __device__ __forceinline__ void refill() {  // afterwards cnt >= 33
+        while (cnt <= 32) {
+            buf |= (uint64_t)__ldg(wp++) << cnt;
+            cnt += 32;
+            loaded += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(int n) {
+        buf >>= n;
+        cnt -= n;
+    }
+    __device__ __forceinline__ uint32_t take(int n) {
+        const uint32_t v = peek(n);
+        drop(n);
+        return v;
+    }
+    __device__ __forceinline__ int64_t bits_consumed() const { return loaded - cnt; }
+};
+
+// Canonical decode of the code that starts at bit 0 of `bits` (stream order = LSB first), at most `maxlen` bits.
+// Returns sym | len << 16, or 0xFFFFFFFF when no code of <= maxlen bits matches.
+__device__ __forceinline__ uint32_t canon_decode(uint32_t bits, const uint16_t *cnt, const uint16_t *sym, int maxlen) {
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= maxlen; ++len) {
+        code |= (int)(bits & 1u);
+        bits >>= 1;
+        const int c = cnt[len];
+        if (code - c < first) return (uint32_t)sym[index + (code - first)] | ((uint32_t)len << 16);
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return 0xFFFFFFFFu;
+}
+
+// lane 0: counts per length and the canonical symbol order from lens[0..n); returns false on an over-subscribed code
+__device__ bool canon_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym) {
+    for (int l = 0; l < 16; ++l) cnt[l] = 0;
+    for (int s = 0; s < n; ++s) cnt[lens[s]]++;
+    int left = 1;
+    for (int l = 1; l < 16; ++l) {
+        left <<= 1;
+        left -= cnt[l];
+        if (left < 0) return false;
+    }
+    uint16_t offs[16];
+    offs[1] = 0;
+    for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + cnt[l]);
+    for (int s = 0; s < n; ++s)
+        if (lens[s]) sym[offs[lens[s]]++] = (uint16_t)s;
+    cnt[0] = 0;
+    return true;
+}
+
+// all lanes: primary table[i] = sym << 4 | len for every index whose leading code has <= bits bits, else 0
+__device__ __forceinline__ void fill_primary(uint16_t *tab, int bits, const uint16_t *cnt, const uint16_t *sym, int lane) {
+    for (int i = lane; i < (1 << bits); i += 32) {
+        const uint32_t r = canon_decode((uint32_t)i, cnt, sym, bits);
+        tab[i] = r == 0xFFFFFFFFu ? (uint16_t)0 : (uint16_t)(((r & 0xFFFFu) << 4) | (r >> 16));
+    }
+}
+
+constexpr uint32_t kInfErrData = 1u;    // invalid DEFLATE data
+constexpr uint32_t kInfErrSize = 2u;    // output does not match ISIZE
+
+__global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint8_t *comp, const BgzfMember *members, int n_members,
+                                                                      uint8_t *out_base, uint32_t *flags, int *first_bad) {
+    __shared__ WarpSmem smem[kInfWarps];
+    WarpSmem &S = smem[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * kInfWarps + (threadIdx.x >> 5), nw = gridDim.x * kInfWarps;
+#pragma unroll 1
+    for (int mi = gw; mi < n_members; mi += nw) {
+        const BgzfMember M = members[mi];
+        if (M.isize == 0) continue;
+        uint8_t *out = out_base + M.out_off;
+        const uint32_t isize = M.isize;
+        BitReader br;
+        if (lane == 0) br.init(comp + M.in_off);
+        uint32_t pos = 0;     // lane 0: bytes produced
+        uint32_t err = 0;     // warp-uniform after every broadcast
+        bool last = false;
+#pragma unroll 1
+        while (!last && !err) {
+            // ---- block header (lane 0) ----
+            int btype = 0;
+            if (lane == 0) {
+                br.refill();
+                last = br.take(1) != 0;
+                btype = (int)br.take(2);
+                // a stream that runs past its payload (no final block where the member ends) is corrupt
+                if (br.base + (br.bits_consumed() >> 3) > comp + M.in_off + M.in_len) btype = 3;
+            }
+            last = __shfl_sync(0xFFFFFFFFu, (int)last, 0) != 0;
+            btype = __shfl_sync(0xFFFFFFFFu, btype, 0);
+            if (btype == 0) {
+                // stored: skip to the byte boundary, LEN / NLEN, then a cooperative byte copy
+                uint32_t len = 0, p0 = 0;
+                unsigned long long src_addr = 0;
+                if (lane == 0) {
+                    br.drop(br.cnt & 7);
+                    br.refill();
+                    len = br.take(16);
+                    const uint32_t nlen = br.take(16);
+                    if ((len ^ nlen) != 0xFFFFu || pos + len > isize) err = kInfErrData;
+                    src_addr = (unsigned long long)reinterpret_cast<uintptr_t>(br.base + (br.bits_consumed() >> 3));
+                    p0 = pos;
+                }
+                err = __shfl_sync(0xFFFFFFFFu, err, 0);
+                if (err) break;
+                len = __shfl_sync(0xFFFFFFFFu, len, 0);
+                src_addr = __shfl_sync(0xFFFFFFFFu, src_addr, 0);
+                p0 = __shfl_sync(0xFFFFFFFFu, p0, 0);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)src_addr);
+                for (uint32_t j = lane; j < len; j += 32) __stcg(out + p0 + j, __ldg(src + j));
+                if (lane == 0) {
+                    pos += len;
+                    br.init(src + len);
+                }
+                __syncwarp();
+                continue;
+            }
+            if (btype == 3) {
+                err = kInfErrData;
+                break;
+            }
+            // ---- code lengths -> S.lens (lane 0), then tables (all lanes) ----
+            int nlit = 288, ndist = 30;
+            if (lane == 0) {
+                if (btype == 1) {
+                    for (int s = 0; s < 144; ++s) S.lens[s] = 8;
+                    for (int s = 144; s < 256; ++s) S.lens[s] = 9;
+                    for (int s = 256; s < 280; ++s) S.lens[s] = 7;
+                    for (int s = 280; s < 288; ++s) S.lens[s] = 8;
+                    for (int s = 0; s < 30; ++s) S.lens[288 + s] = 5;
+                } else {
+                    br.refill();
+                    nlit = (int)br.take(5) + 257;
+                    ndist = (int)br.take(5) + 1;
+                    const int ncl = (int)br.take(4) + 4;
+                    uint8_t cl[19];
+                    for (int i = 0; i < 19; ++i) cl[i] = 0;
+                    for (int i = 0; i < ncl; ++i) {
+                        br.refill();
+                        cl[c_clen_order[i]] = (uint8_t)br.take(3);
+                    }
+                    if (nlit > 286 || ndist > 30 || !canon_build(cl, 19, S.cl_cnt, S.cl_sym)) err = kInfErrData;
+                    int i = 0;
+                    while (!err && i < nlit + ndist) {
+                        br.refill();
+                        const uint32_t r = canon_decode((uint32_t)br.buf, S.cl_cnt, S.cl_sym, 7);
+                        if (r == 0xFFFFFFFFu) {
+                            err = kInfErrData;
+                            break;
+                        }
+                        br.drop((int)(r >> 16));
+                        const int sym = (int)(r & 0xFFFFu);
+                        if (sym < 16) {
+                            S.lens[i++] = (uint8_t)sym;
+                        } else {
+                            int rep, val = 0;
+                            if (sym == 16) {
+                                if (i == 0) {
+                                    err = kInfErrData;
+                                    break;
+                                }
+                                val = S.lens[i - 1];
+                                rep = 3 + (int)br.take(2);
+                            } else if (sym == 17) {
+                                rep = 3 + (int)br.take(3);
+                            } else {
+                                rep = 11 + (int)br.take(7);
+                            }
+                            if (i + rep > nlit + ndist) {
+                                err = kInfErrData;
+                                break;
+                            }
+                            while (rep--) S.lens[i++] = (uint8_t)val;
+                        }
+                    }
+                    if (!err && S.lens[256] == 0) err = kInfErrData;  // no end-of-block code
+                    // distance lengths follow the literal/length lengths: move them to a fixed place
+                    if (!err) {
+                        uint8_t tmp[30];
+                        for (int s = 0; s < ndist; ++s) tmp[s] = S.lens[nlit + s];
+                        for (int s = nlit; s < 288; ++s) S.lens[s] = 0;
+                        for (int s = 0; s < 30; ++s) S.lens[288 + s] = s < ndist ? tmp[s] : 0;
+                    }
+                }
+                if (!err) {
+                    // an incomplete distance code with a single symbol is legal (RFC 1951 3.2.7); over-subscription is not
+                    if (!canon_build(S.lens, 288, S.lit_cnt, S.lit_sym) || !canon_build(S.lens + 288, 30, S.dist_cnt, S.dist_sym))
+                        err = kInfErrData;
+                }
+            }
+            err = __shfl_sync(0xFFFFFFFFu, err, 0);
+            if (err) break;
+            __syncwarp();
+            fill_primary(S.lit_tab, kLitBits, S.lit_cnt, S.lit_sym, lane);
+            fill_primary(S.dist_tab, kDistBits, S.dist_cnt, S.dist_sym, lane);
+            __syncwarp();
+
+            // ---- symbols: lane 0 decodes a batch of tokens, the warp executes it ----
+            bool eob = false;
+#pragma unroll 1
+            while (!eob && !err) {
+                int n = 0;
+                if (lane == 0) {
+                    while (n < kTokens) {
+                        br.refill();
+                        uint32_t e = S.lit_tab[br.peek(kLitBits)];
+                        int sym;
+                        if (e) {
+                            br.drop((int)(e & 15u));
+                            sym = (int)(e >> 4);
+                        } else {
+                            const uint32_t r = canon_decode((uint32_t)br.buf, S.lit_cnt, S.lit_sym, 15);
+                            if (r == 0xFFFFFFFFu) {
+                                err = kInfErrData;
+                                break;
+                            }
+                            br.drop((int)(r >> 16));
+                            sym = (int)(r & 0xFFFFu);
+                        }
+                        if (sym < 256) {
+                            S.tok[n] = 0x80000000u | (uint32_t)sym;
+                            S.tpos[n] = pos;
+                            pos += 1;
+                        } else if (sym == 256) {
+                            eob = true;
+                            break;
+                        } else {
+                            sym -= 257;
+                            if (sym >= 29) {
+                                err = kInfErrData;
+                                break;
+                            }
+                            const uint32_t len = c_len_base[sym] + br.take(c_len_extra[sym]);
+                            br.refill();
+                            e = S.dist_tab[br.peek(kDistBits)];
+                            int ds;
+                            if (e) {
+                                br.drop((int)(e & 15u));
+                                ds = (int)(e >> 4);
+                            } else {
+                                const uint32_t r = canon_decode((uint32_t)br.buf, S.dist_cnt, S.dist_sym, 15);
+                                if (r == 0xFFFFFFFFu) {
+                                    err = kInfErrData;
+                                    break;
+                                }
+                                br.drop((int)(r >> 16));
+                                ds = (int)(r & 0xFFFFu);
+                            }
+                            if (ds >= 30) {
+                                err = kInfErrData;
+                                break;
+                            }
+                            const uint32_t dist = c_dist_base[ds] + br.take(c_dist_extra[ds]);
+                            if (dist > pos) {
+                                err = kInfErrData;
+                                break;
+                            }
+                            S.tok[n] = len | (dist << 9);
+                            S.tpos[n] = pos;
+                            pos += len;
+                        }
+                        ++n;
+                        if (pos > isize) {
+                            err = kInfErrData;
+                            break;
+                        }
+                    }
+                }
+                n = __shfl_sync(0xFFFFFFFFu, n, 0);
+                eob = __shfl_sync(0xFFFFFFFFu, (int)eob, 0) != 0;
+                err = __shfl_sync(0xFFFFFFFFu, err, 0);
+                if (err) break;
+                __syncwarp();
+                // execute: all literals first (they depend on nothing), then the matches in order
+                uint32_t t = 0, p = 0;
+                if (lane < n) {
+                    t = S.tok[lane];
+                    p = S.tpos[lane];
+                    if (t & 0x80000000u) __stcg(out + p, (uint8_t)t);
+                }
+                uint32_t mm = __ballot_sync(0xFFFFFFFFu, lane < n && !(t & 0x80000000u));
+                __syncwarp();
+                while (mm) {
+                    const int k = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const uint32_t tk = __shfl_sync(0xFFFFFFFFu, t, k), pk = __shfl_sync(0xFFFFFFFFu, p, k);
+                    const uint32_t len = tk & 511u, dist = tk >> 9;
+                    const uint8_t *src = out + pk - dist;
+                    if (dist >= len) {
+                        for (uint32_t j = lane; j < len; j += 32) __stcg(out + pk + j, __ldcg(src + j));
+                    } else if (dist == 1) {
+                        const uint8_t b = __ldcg(src);
+                        for (uint32_t j = lane; j < len; j += 32) __stcg(out + pk + j, b);
+                    } else {
+                        for (uint32_t j = lane; j < len; j += 32) __stcg(out + pk + j, __ldcg(src + (j % dist)));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane == 0 && !err && pos != isize) err = kInfErrSize;
+        err = __shfl_sync(0xFFFFFFFFu, err, 0);
+        if (err && lane == 0) {
+            atomicOr(flags, err);
+            atomicMin(first_bad, mi);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+// Walks the gzip members of `data` (a whole file).  BGZF members carry their size in the 'BC' extra subfield; a
+// member without it (plain gzip) is taken to extend to the end of the file (single member).
+int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uint64_t *total_out) {
+    out.clear();
+    size_t p = 0;
+    uint64_t uo = 0;
+    while (p < len) {
+        if (len - p < 18 || data[p] != 0x1f || data[p + 1] != 0x8b || data[p + 2] != 8)
+            return fail(EXON_GPU_ERR_PARSE, "bgzf: bad gzip magic at byte %zu", p);
+        const uint8_t flg = data[p + 3];
+        size_t q = p + 10;
+        long bsize = -1;
+        if (flg & 4) {
+            const size_t xlen = (size_t)data[q] | ((size_t)data[q + 1] << 8);
+            q += 2;
+            if (q + xlen > len) return fail(EXON_GPU_ERR_PARSE, "bgzf: truncated extra field at byte %zu", p);
+            size_t x = q;
+            while (x + 4 <= q + xlen) {
+                const size_t slen = (size_t)data[x + 2] | ((size_t)data[x + 3] << 8);
+                if (data[x] == 'B' && data[x + 1] == 'C' && slen == 2 && x + 6 <= q + xlen) bsize = (long)data[x + 4] | ((long)data[x + 5] << 8);
+                x += 4 + slen;
+            }
+            q += xlen;
+        }
+        if (flg & 8) { while (q < len && data[q]) ++q; ++q; }   // FNAME
+        if (flg & 16) { while (q < len && data[q]) ++q; ++q; }  // FCOMMENT
+        if (flg & 2) q += 2;                                    // FHCRC
+        const size_t end = bsize >= 0 ? p + (size_t)bsize + 1 : len;
+        if (end > len || q + 8 > end) return fail(EXON_GPU_ERR_PARSE, "bgzf: truncated member at byte %zu", p);
+        BgzfMember m;
+        m.in_off = q;
+        m.in_len = (uint32_t)(end - 8 - q);
+        m.isize = (uint32_t)data[end - 4] | ((uint32_t)data[end - 3] << 8) | ((uint32_t)data[end - 2] << 16) | ((uint32_t)data[end - 1] << 24);
+        m.out_off = uo;
+        if (bsize >= 0 && m.isize > 65536u) return fail(EXON_GPU_ERR_PARSE, "bgzf: member at byte %zu claims %u bytes (> 64 KiB)", p, m.isize);
+        uo += m.isize;
+        out.push_back(m);
+        p = end;
+    }
+    *total_out = uo;
+    return EXON_GPU_OK;
+}
+
+// Enqueues the inflate of `members` (table in host memory) from d_comp into d_out on the context's stream.
+// d_table / d_flags are device scratch owned by the caller (n_members entries / 2 words).
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint8_t *d_out, uint32_t *d_flags) {
+    if (n_members <= 0) return EXON_GPU_OK;
+    static int occ = 0;
+    if (!occ) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel, kInfWarps * 32, 0));
+        if (occ < 1) occ = 1;
+    }
+    const int grid = std::min((n_members + kInfWarps - 1) / kInfWarps, occ * c->sm_count);
+    bgzf_inflate_kernel<<<grid, kInfWarps * 32, 0, c->stream>>>(d_comp, d_table, n_members, d_out, d_flags, (int *)(d_flags + 1));
+    c->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return EXON_GPU_OK;
+}
+
+
+// One whole BGZF / gzip file: members -> HBM as they are, inflated by the device into the arena, then framed like
+// a device-resident range (header skipped, last record normalised to end in '\n').
+int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
+    if (!is_last || !gz_pending.empty()) {
+        gz_pending.insert(gz_pending.end(), data, data + len);
+        if (!is_last) {
+            file_open = true;
+            return EXON_GPU_OK;
+        }
+        data = gz_pending.data();
+        len = gz_pending.size();
+    }
+    struct Clear {
+        std::vector<uint8_t> &v;
+        ~Clear() { v.clear(); }
+    } clear{gz_pending};
+    if (cur_run_open && tail_len > 0) return fail(EXON_GPU_ERR_STATE, "feed_gzip: the previous plain-text range ended mid-line");
+    std::vector<BgzfMember> members;
+    uint64_t total = 0;
+    if (len) {
+        if (int rc = bgzf_walk(data, len, members, &total)) return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    if (total > 0) {
+        // device staging
+        const size_t o_tab = (len + 16 + 255) & ~(size_t)255;
+        const size_t o_flags = o_tab + ((members.size() * sizeof(BgzfMember) + 255) & ~(size_t)255);
+        const size_t need = o_flags + 256;
+        if (need > d_gz_cap) {
+            if (d_gz) {
+                CUDA_TRY(cudaStreamSynchronize(st));
+                CUDA_TRY(cudaFree(d_gz));
+                d_gz = nullptr;
+                d_gz_cap = 0;
+            }
+            const size_t cap = std::max(need + need / 4, (size_t)8 << 20);
+            CUDA_TRY(cudaMalloc(&d_gz, cap));
+            d_gz_cap = cap;
+        }
+        uint8_t *dz = (uint8_t *)d_gz;
+        CUDA_TRY(cudaMemcpyAsync(dz, data, len, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dz + o_tab, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
+        const int init_flags[2] = {0, 0x7FFFFFFF};
+        CUDA_TRY(cudaMemcpyAsync(dz + o_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
+        // arena space: the tail of the current block if the file fits, else a fresh block (+1 for a missing final '\n')
+        if (blocks.empty() || blocks.back().used + total + 1 > blocks.back().cap) {
+            DevBlock nb;
+            if (int rc = ctx->get_block((size_t)total + 1, &nb)) return rc;
+            blocks.push_back(nb);
+        }
+        DevBlock &b = blocks.back();
+        uint8_t *dst = b.ptr + b.used;
+        if (int rc = bgzf_inflate_launch(ctx, dz, (const BgzfMember *)(dz + o_tab), (int)members.size(), dst, (uint32_t *)(dz + o_flags)))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_res + 6, dz + o_flags, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_res + 7, dst + total - 1, 1, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const uint32_t *fl = reinterpret_cast<const uint32_t *>(h_res + 6);
+        if (fl[0])
+            return fail(EXON_GPU_ERR_PARSE, "bgzf: member %d does not inflate:%s%s", (int)fl[1], (fl[0] & 1u) ? " invalid DEFLATE data;" : "",
+                        (fl[0] & 2u) ? " size differs from ISIZE;" : "");
+        uint64_t n = total;
+        if (*reinterpret_cast<const uint8_t *>(h_res + 7) != '\n') {
+            static const uint8_t nl = '\n';
+            CUDA_TRY(cudaMemcpyAsync(dst + n, &nl, 1, cudaMemcpyHostToDevice, st));
+            n += 1;
+        }
+        b.used += (n + 15) & ~(size_t)15;  // the next file starts 16-byte aligned
+        if (b.used > b.cap) b.used = b.cap;
+        cur_run_open = false;  // plain-text feeds that follow start their own block
+        tail_len = 0;
+        // frame it exactly like a device-resident range (header probe, run, file mark, eager scan)
+        hdr = fmt == kFmtVcf ? kAtLineStart : kBody;
+        const int64_t before = body_bytes;
+        if (int rc = feed_device(dst, (size_t)n, true)) return rc;
+        if (n != total) body_bytes = before + (body_bytes - before) - 1;  // the added '\n' is not a fed byte
+        return EXON_GPU_OK;
+    }
+    // an empty file (no members, or only empty members such as the BGZF EOF marker)
+    if (!runs.empty()) file_marks.push_back(FileMark{runs.size() - 1, runs.back().len});
+    hdr = fmt == kFmtVcf ? kAtLineStart : kBody;
+    file_open = false;
+    return EXON_GPU_OK;
+}
+
+}  // namespace exon
+
+// Whole-file inflate into caller memory (host or device): used by hosts that need the uncompressed bytes themselves
+// (e.g. a BAM header) and by the byte-exact parity tests against zlib.
+extern "C" int exon_gpu_gzip_inflate(exon_gpu_ctx *c, const uint8_t *data, size_t len, uint8_t *out, size_t out_cap, int out_is_device,
+                                     size_t *out_len) {
+    using namespace exon;
+    if (!c || (!data && len) || !out_len) return fail(EXON_GPU_ERR_ARG, "gzip_inflate: NULL argument");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(EXON_GPU_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    std::vector<BgzfMember> members;
+    uint64_t total = 0;
+    if (len)
+        if (int rc = bgzf_walk(data, len, members, &total)) return rc;
+    *out_len = (size_t)total;
+    if (total == 0) return EXON_GPU_OK;
+    if (!out || out_cap < total) return fail(EXON_GPU_ERR_ARG, "gzip_inflate: output buffer too small (%llu bytes needed)", (unsigned long long)total);
+    std::lock_guard<std::mutex> work(c->work_mu);
+    const size_t o_tab = (len + 16 + 255) & ~(size_t)255;
+    const size_t o_flags = o_tab + ((members.size() * sizeof(BgzfMember) + 255) & ~(size_t)255);
+    const size_t o_out = o_flags + 256;
+    if (int rc = c->ensure_scratch(o_out + (out_is_device ? 0 : (size_t)total + 16), 64)) return rc;
+    uint8_t *scr = (uint8_t *)c->scratch;
+    uint8_t *d_out = out_is_device ? out : scr + o_out;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaMemcpyAsync(scr, data, len, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(scr + o_tab, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
+    const int init_flags[2] = {0, 0x7FFFFFFF};
+    CUDA_TRY(cudaMemcpyAsync(scr + o_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), d_out, (uint32_t *)(scr + o_flags))) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev1, st));
+    c->timed = true;
+    CUDA_TRY(cudaMemcpyAsync(c->h_scratch, scr + o_flags, 8, cudaMemcpyDeviceToHost, st));
+    if (!out_is_device) CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint32_t *fl = (const uint32_t *)c->h_scratch;
+    if (fl[0])
+        return fail(EXON_GPU_ERR_PARSE, "gzip: member %d does not inflate:%s%s", (int)fl[1], (fl[0] & 1u) ? " invalid DEFLATE data;" : "",
+                    (fl[0] & 2u) ? " size differs from ISIZE;" : "");
+    return EXON_GPU_OK;
+}
+
+extern "C" int exon_gpu_stream_feed_gzip(exon_gpu_stream *s, const uint8_t *data, size_t len, int is_last) {
+    if (!s || (!data && len)) return exon::fail(EXON_GPU_ERR_ARG, "feed_gzip: NULL argument");
+    cudaError_t e = cudaSetDevice(s->ctx->device);
+    if (e != cudaSuccess) return exon::fail(EXON_GPU_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    if (s->drained) return exon::fail(EXON_GPU_ERR_STATE, "feed_gzip: the stream has already produced batches");
+    return s->feed_gzip(data, len, is_last != 0);
+}

@@ -122,6 +122,11 @@ struct VcfStream {
     // ---- column build (K2) state lives in vcf_columns.cu ----
     struct Columns *cols = nullptr;
 
+    // ---- compressed feeds (bgzf.cu): bytes of the current .gz file that arrived before its last range ----
+    std::vector<uint8_t> gz_pending;
+    void *d_gz = nullptr;      // device staging: compressed bytes | member table | flags
+    size_t d_gz_cap = 0;
+    int feed_gzip(const uint8_t *data, size_t len, bool is_last);
     int feed_host(const uint8_t *text, size_t len, bool is_last);
     int feed_device(const uint8_t *text, size_t len, bool is_last);
     int append_host(const uint8_t *p, size_t n);
@@ -162,6 +167,16 @@ struct FaCommon {
 int fa_common_from(const exon_gpu_pred *pred, const exon_gpu_agg *agg, FaCommon &k);
 int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, int64_t max_rows, const FaCommon &k,
                             unsigned long long *d_out, bool timed);
+
+// ---- BGZF inflate (bgzf.cu) ----
+struct BgzfMember {
+    uint64_t in_off;   // byte offset of the DEFLATE payload inside the compressed file
+    uint32_t in_len;   // payload bytes
+    uint32_t isize;    // uncompressed bytes (gzip trailer)
+    uint64_t out_off;  // byte offset of the member's data in the uncompressed stream
+};
+int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uint64_t *total_out);
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint8_t *d_out, uint32_t *d_flags);
 
 // defined in fastq_scan.cu
 int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count, int64_t *out_rows);

@@ -54,6 +54,7 @@ void VcfStream::release_all() {
     blocks.clear();
     runs.clear();
     file_marks.clear();
+    gz_pending.clear();
     cur_run_open = false;
     tail_len = 0;
     body_bytes = 0;

@@ -98,6 +98,20 @@ class Context:
     def open_vcf(self, **kw) -> "VcfStream":
         return VcfStream(self, **kw)
 
+    def gzip_inflate(self, data) -> np.ndarray:
+        """exon_gpu_gzip_inflate: the uncompressed bytes of a whole BGZF / gzip file, inflated on the device."""
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        n = C.c_size_t()
+        rc = self.lib.exon_gpu_gzip_inflate(self.handle, C.c_void_p(data.ctypes.data), data.size, None, 0, 0, C.byref(n))
+        if n.value == 0:
+            check(rc)
+            return np.zeros(0, np.uint8)
+        out = np.empty(n.value, dtype=np.uint8)
+        check(self.lib.exon_gpu_gzip_inflate(self.handle, C.c_void_p(data.ctypes.data), data.size, C.c_void_p(out.ctypes.data),
+                                             out.size, 0, C.byref(n)))
+        return out
+
     def open_fastq(self, **kw) -> "FastqStream":
         return FastqStream(self, **kw)
 
@@ -258,6 +272,16 @@ class VcfStream:
         self._last_host = data  # keep alive until the next synchronising call
         check(self.lib.exon_gpu_vcf_feed(self.handle, C.c_void_p(data.ctypes.data), data.size, 0, int(is_last)))
 
+    def feed_gzip(self, data, *, is_last: bool = True):
+        """Feed BGZF / gzip bytes of one file (exon_gpu_stream_feed_gzip): inflated on the device."""
+        if isinstance(data, PinnedBuffer):
+            data = data.array
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        self._last_host = data
+        check(self.lib.exon_gpu_stream_feed_gzip(self.handle, C.c_void_p(data.ctypes.data), data.size, int(is_last)))
+
     def filter_count(self, region: "_abi.Region | None" = None) -> int:
         out = C.c_int64()
         check(self.lib.exon_gpu_vcf_filter_count(self.handle, C.byref(region) if region is not None else None,
@@ -346,6 +370,16 @@ class FastqStream:
         assert data.dtype == np.uint8 and data.flags.c_contiguous
         self._last_host = data
         check(self.lib.exon_gpu_fastq_feed(self.handle, C.c_void_p(data.ctypes.data), data.size, 0, int(is_last)))
+
+    def feed_gzip(self, data, *, is_last: bool = True):
+        """Feed BGZF / gzip bytes of one file (exon_gpu_stream_feed_gzip): inflated on the device."""
+        if isinstance(data, PinnedBuffer):
+            data = data.array
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        self._last_host = data
+        check(self.lib.exon_gpu_stream_feed_gzip(self.handle, C.c_void_p(data.ctypes.data), data.size, int(is_last)))
 
     def filter_count(self, min_mean=None, phred_offset: int = 33) -> int:
         """records with mean(quality) > min_mean (an int, or a (num, den) pair); None -> COUNT(*)."""

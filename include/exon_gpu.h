@@ -200,6 +200,17 @@ int exon_gpu_fastq_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int
  * that does not start with '+', a file that ends after the first or second line of a record. */
 int exon_gpu_fastq_filter_count(exon_gpu_stream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count);
 int exon_gpu_fastq_rows(exon_gpu_stream *s, int64_t *out_rows);
+/* Compressed bytes in: consecutive byte ranges of ONE BGZF file (or a plain single-member .gz; slower, one warp) --
+ * what VCFOpener::open / FASTQOpener::open wrap in a BGZF / gzip decoder for FileCompressionType::GZIP
+ * (exon/exon-core/src/datasources/vcf/file_opener/unindex_file_opener.rs:59-73, exon-core/src/streaming_bgzf.rs:22-118).
+ * The compressed members are copied to HBM unchanged and inflated there (one warp per member) into the stream's
+ * arena; the result is framed exactly like exon_gpu_vcf_feed / exon_gpu_fastq_feed of the uncompressed text.
+ * Ranges are buffered on the host until is_last != 0 completes the file.  Works on VCF and FASTQ streams. */
+int exon_gpu_stream_feed_gzip(exon_gpu_stream *s, const uint8_t *data, size_t len, int is_last);
+/* Inflates a whole BGZF / gzip file on the device into `out` (host memory, or device memory when out_is_device != 0).
+ * *out_len receives the uncompressed size even when `out` is too small (EXON_GPU_ERR_ARG then). */
+int exon_gpu_gzip_inflate(exon_gpu_ctx *ctx, const uint8_t *data, size_t len, uint8_t *out, size_t out_cap, int out_is_device,
+                          size_t *out_len);
 /* Format-independent stream calls (the exon_gpu_vcf_* spellings remain valid for VCF streams). */
 int exon_gpu_stream_close(exon_gpu_stream *s);
 int exon_gpu_stream_reset(exon_gpu_stream *s);

@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Secondary bench lines for the BASELINE configs that are parity-test cases rather than the headline
+(configs[1] FASTQ mean-quality filter + COUNT, ...).  Same measurement rules as bench.py: inputs resident in HBM
+for `value`, CUDA events on the library's stream, W >= 3 warm-ups, input >> L2; `e2e` feeds pinned host buffers
+through the C ABI inside the timed region; the CPU arm is the oracle on all host cores.
+
+    python tools/bench_formats.py fastq [--reads 10000000] [--steps 20]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from exon_b200.runtime import Context  # noqa: E402
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return (float(json.load(open(p))["hbm_gbs"]), "measured") if os.path.exists(p) else (6650.0, "fallback")
+
+
+def timed(ctx, tstream, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    kms = []
+    l0 = ctx.launch_count()
+    e0.record(tstream)
+    for _ in range(steps):
+        out = fn()
+        kms.append(ctx.last_kernel_ms())
+    e1.record(tstream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, float(np.mean(kms)), out, (ctx.launch_count() - l0) / steps
+
+
+def bench_fastq(args):
+    import oracle
+    from synth import fastq
+
+    tstream = torch.cuda.Stream()
+    ctx = Context(0, cuda_stream=tstream.cuda_stream)
+    pins = []
+
+    def alloc(nb):
+        p = ctx.pinned(nb)
+        pins.append(p)
+        return p.array
+
+    t0 = time.perf_counter()
+    sh = fastq.shards(args.reads, args.shards, alloc=alloc)
+    gen_s = time.perf_counter() - t0
+    truth = sh.truth_count(30)
+    total = int(sum(f.size for f in sh.files))
+    dbufs = []
+    res = ctx.open_fastq()
+    for f in sh.files:
+        d = ctx.device_buffer(f.size)
+        d.upload(f)
+        dbufs.append(d)
+        res.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+    ms, kms, cnt, launches = timed(ctx, tstream, lambda: res.filter_count(30), args.steps, 3)
+    assert cnt == truth, (cnt, truth)
+
+    e2e_s = ctx.open_fastq()
+
+    def e2e():
+        e2e_s.reset()
+        for f in sh.files:
+            e2e_s.feed(f, is_last=True)
+        return e2e_s.filter_count(30)
+
+    e_ms, _, ecnt, _ = timed(ctx, tstream, e2e, max(2, args.steps // 4), 2)
+    assert ecnt == truth
+    cores = os.cpu_count() or 1
+    n_cpu = max(1, min(len(sh.files), cores))
+    t0 = time.perf_counter()
+    c_cnt, c_rows = oracle.fastq_filter_count_files(sh.files[:n_cpu], 30, target_partitions=cores)
+    cpu_s = time.perf_counter() - t0
+    peak, src = peak_gbs()
+    line = {"metric": "fastq_mean_quality_filter_count_reads_per_sec", "value": sh.n / ms * 1e3, "unit": "reads/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"FASTQ scan + WHERE mean(quality) > 30 + COUNT(*), {sh.n} synthetic {sh.read_len}-base reads in "
+                                   f"{len(sh.files)} files (BASELINE configs[1])", "l2": "input >> 126 MB L2, no flush"},
+            "e2e": {"value": sh.n / e_ms * 1e3, "unit": "reads/s", "h2d_bytes_per_step": total, "d2h_bytes_per_step": 24, "ms_per_step": e_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "fq_lines_kernel + fq_filter_kernel (two passes)", "achieved": total / kms / 1e6,
+                         "peak": peak, "peak_source": src, "unit": "GB/s", "frac": total / kms / 1e6 / peak,
+                         "algorithmic_bytes_per_step": total, "kernel_ms": kms, "traffic": None},
+            "cpu_baseline": {"value": c_rows / cpu_s, "unit": "reads/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_cpu} of {len(sh.files)} files ({c_rows} reads), one worker per file"},
+            "count": cnt, "count_matches_truth": True, "gen_seconds": gen_s}
+    res.close()
+    e2e_s.close()
+    for d in dbufs:
+        d.free()
+    for p in pins:
+        p.free()
+    ctx.close()
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("fmt", choices=["fastq"])
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--shards", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=20)
+    a = ap.parse_args()
+    {"fastq": bench_fastq}[a.fmt](a)

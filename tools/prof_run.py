@@ -18,11 +18,28 @@ from synth import vcf  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=100_000_000)
+ap.add_argument("--fastq-reads", type=int, default=0, help="profile the FASTQ fused scan instead of VCF")
 ap.add_argument("--shards", type=int, default=64)
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--modes", default="lazy,lazy,strict,count_star,interval")
 args = ap.parse_args()
 
+if args.fastq_reads:
+    from synth import fastq
+
+    sh = fastq.shards(args.fastq_reads, 32)
+    with Context(0) as ctx:
+        s = ctx.open_fastq()
+        keep = []
+        for f in sh.files:
+            d = ctx.device_buffer(f.size)
+            d.upload(np.ascontiguousarray(f))
+            keep.append(d)
+            s.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+        for _ in range(3):
+            print("fastq", s.filter_count(30), sh.truth_count(30), f"{ctx.last_kernel_ms():.3f} ms", flush=True)
+        s.close()
+    raise SystemExit(0)
 cols = vcf.columns(args.rows)
 files = vcf.shards(cols, args.shards)
 region = _abi.make_region("1", 1_000_000, 2_000_000)
