@@ -265,6 +265,7 @@ int exon_gpu_vcf_close(exon_gpu_stream *s) {
     if (s->h_res) cudaFreeHost(s->h_res);
     if (s->d_segs) cudaFree(s->d_segs);
     if (s->d_gz) cudaFree(s->d_gz);
+    if (s->d_gz_tab) cudaFree(s->d_gz_tab);
     delete s;
     return EXON_GPU_OK;
 }
@@ -282,6 +283,7 @@ int exon_gpu_vcf_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int i
     if (!s || (!text && len)) return fail(EXON_GPU_ERR_ARG, "vcf_feed: NULL argument");
     if (int rc = ensure_device(s->ctx)) return rc;
     if (s->drained) return fail(EXON_GPU_ERR_STATE, "vcf_feed: the stream has already produced batches");
+    if (int rc = s->flush_gz()) return rc;  // compressed files fed earlier come first
     return is_device_ptr ? s->feed_device(text, len, is_last != 0) : s->feed_host(text, len, is_last != 0);
 }
 
@@ -312,6 +314,8 @@ int exon_gpu_vcf_rows(exon_gpu_stream *s, int64_t *out_rows) {
 
 int exon_gpu_vcf_body_bytes(exon_gpu_stream *s, int64_t *out_bytes) {
     if (!s || !out_bytes) return fail(EXON_GPU_ERR_ARG, "vcf_body_bytes: NULL argument");
+    if (int rc = ensure_device(s->ctx)) return rc;
+    if (int rc = s->flush_gz()) return rc;
     *out_bytes = s->body_bytes;
     return EXON_GPU_OK;
 }

@@ -35,10 +35,13 @@ namespace exon {
 
 namespace {
 
-constexpr int kInfWarps = 4;      // warps per CTA (one member per warp at a time)
-constexpr int kLitBits = 10;      // primary table of the literal/length code
+constexpr int kInfWarps = 4;      // warps per CTA
+constexpr int kG = 8;             // lanes that work on one member (one decodes, all copy)
+constexpr int kGroups = 32 / kG;  // members in flight per warp
+constexpr int kLitBits = 9;       // primary table of the literal/length code
 constexpr int kDistBits = 8;      // primary table of the distance code
 constexpr int kTokens = 32;
+constexpr int kRing = 1024;       // recent output mirrored in shared memory (matches mostly reach back < 1 KiB in text)
 
 __constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 __constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -46,7 +49,7 @@ __constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49
 __constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-struct WarpSmem {
+struct MemberSmem {
     uint16_t lit_tab[1 << kLitBits];  // sym << 4 | len, 0 = code longer than kLitBits
     uint16_t dist_tab[1 << kDistBits];
     uint16_t lit_sym[288];            // symbols in canonical order
@@ -58,12 +61,13 @@ struct WarpSmem {
     uint8_t lens[320];                // code lengths of the block being set up (HLIT + HDIST)
     uint32_t tok[kTokens];            // literal: 0x80000000 | byte; match: len | dist << 9
     uint32_t tpos[kTokens];           // output position of the token inside the member
+    uint8_t ring[kRing];              // ring[p % kRing] = output byte p, for the most recent positions
 };
 
-// LSB-first bit reader over 4-byte aligned words (lane 0 only).
+// LSB-first bit reader over 4-byte aligned words (the decoding lane only).
 struct BitReader {
     const uint32_t *wp;  // next aligned word
-    const uint8_t *base; // payload byte 0
+    const uint8_t *base; // where this reader started
     uint64_t buf;
     int cnt;             // valid bits in buf
     int64_t loaded;      // bits loaded so far
@@ -113,7 +117,7 @@ __device__ __forceinline__ uint32_t canon_decode(uint32_t bits, const uint16_t *
     return 0xFFFFFFFFu;
 }
 
-// lane 0: counts per length and the canonical symbol order from lens[0..n); returns false on an over-subscribed code
+// decoding lane: counts per length and the canonical symbol order from lens[0..n); false on an over-subscribed code
 __device__ bool canon_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym) {
     for (int l = 0; l < 16; ++l) cnt[l] = 0;
     for (int s = 0; s < n; ++s) cnt[lens[s]]++;
@@ -132,9 +136,9 @@ __device__ bool canon_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t 
     return true;
 }
 
-// all lanes: primary table[i] = sym << 4 | len for every index whose leading code has <= bits bits, else 0
-__device__ __forceinline__ void fill_primary(uint16_t *tab, int bits, const uint16_t *cnt, const uint16_t *sym, int lane) {
-    for (int i = lane; i < (1 << bits); i += 32) {
+// all lanes of the group: primary table[i] = sym << 4 | len for every index whose leading code has <= bits bits, else 0
+__device__ __forceinline__ void fill_primary(uint16_t *tab, int bits, const uint16_t *cnt, const uint16_t *sym, int gl) {
+    for (int i = gl; i < (1 << bits); i += kG) {
         const uint32_t r = canon_decode((uint32_t)i, cnt, sym, bits);
         tab[i] = r == 0xFFFFFFFFu ? (uint16_t)0 : (uint16_t)(((r & 0xFFFFu) << 4) | (r >> 16));
     }
@@ -143,41 +147,47 @@ __device__ __forceinline__ void fill_primary(uint16_t *tab, int bits, const uint
 constexpr uint32_t kInfErrData = 1u;    // invalid DEFLATE data
 constexpr uint32_t kInfErrSize = 2u;    // output does not match ISIZE
 
+#define GSHFL(v) __shfl_sync(gmask, (v), 0, kG)
+
 __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint8_t *comp, const BgzfMember *members, int n_members,
-                                                                      uint8_t *out_base, uint32_t *flags, int *first_bad) {
-    __shared__ WarpSmem smem[kInfWarps];
-    WarpSmem &S = smem[threadIdx.x >> 5];
+                                                                      uint32_t *flags, int *first_bad) {
+    extern __shared__ __align__(16) uint8_t inf_smem_raw[];
+    MemberSmem *all = reinterpret_cast<MemberSmem *>(inf_smem_raw);
     const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * kInfWarps + (threadIdx.x >> 5), nw = gridDim.x * kInfWarps;
+    const int gl = lane & (kG - 1);                   // lane inside the group
+    const int group = (int)(threadIdx.x / kG);        // group inside the CTA
+    const uint32_t gmask = ((1u << kG) - 1u) << (lane & ~(kG - 1));
+    MemberSmem &S = all[group];
+    const int gg = blockIdx.x * (kInfWarps * kGroups) + group, ng = gridDim.x * (kInfWarps * kGroups);
 #pragma unroll 1
-    for (int mi = gw; mi < n_members; mi += nw) {
+    for (int mi = gg; mi < n_members; mi += ng) {
         const BgzfMember M = members[mi];
         if (M.isize == 0) continue;
-        uint8_t *out = out_base + M.out_off;
+        uint8_t *out = reinterpret_cast<uint8_t *>((uintptr_t)M.out_addr);
         const uint32_t isize = M.isize;
         BitReader br;
-        if (lane == 0) br.init(comp + M.in_off);
-        uint32_t pos = 0;     // lane 0: bytes produced
-        uint32_t err = 0;     // warp-uniform after every broadcast
+        if (gl == 0) br.init(comp + M.in_off);
+        uint32_t pos = 0;     // decoding lane: bytes produced
+        uint32_t err = 0;     // group-uniform after every broadcast
         bool last = false;
 #pragma unroll 1
         while (!last && !err) {
-            // ---- block header (lane 0) ----
+            // ---- block header (decoding lane) ----
             int btype = 0;
-            if (lane == 0) {
+            if (gl == 0) {
                 br.refill();
                 last = br.take(1) != 0;
                 btype = (int)br.take(2);
                 // a stream that runs past its payload (no final block where the member ends) is corrupt
                 if (br.base + (br.bits_consumed() >> 3) > comp + M.in_off + M.in_len) btype = 3;
             }
-            last = __shfl_sync(0xFFFFFFFFu, (int)last, 0) != 0;
-            btype = __shfl_sync(0xFFFFFFFFu, btype, 0);
+            last = GSHFL((int)last) != 0;
+            btype = GSHFL(btype);
             if (btype == 0) {
                 // stored: skip to the byte boundary, LEN / NLEN, then a cooperative byte copy
                 uint32_t len = 0, p0 = 0;
                 unsigned long long src_addr = 0;
-                if (lane == 0) {
+                if (gl == 0) {
                     br.drop(br.cnt & 7);
                     br.refill();
                     len = br.take(16);
@@ -186,27 +196,30 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                     src_addr = (unsigned long long)reinterpret_cast<uintptr_t>(br.base + (br.bits_consumed() >> 3));
                     p0 = pos;
                 }
-                err = __shfl_sync(0xFFFFFFFFu, err, 0);
+                err = GSHFL(err);
                 if (err) break;
-                len = __shfl_sync(0xFFFFFFFFu, len, 0);
-                src_addr = __shfl_sync(0xFFFFFFFFu, src_addr, 0);
-                p0 = __shfl_sync(0xFFFFFFFFu, p0, 0);
+                len = GSHFL(len);
+                src_addr = GSHFL(src_addr);
+                p0 = GSHFL(p0);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)src_addr);
-                for (uint32_t j = lane; j < len; j += 32) __stcg(out + p0 + j, __ldg(src + j));
-                if (lane == 0) {
+                for (uint32_t j = gl; j < len; j += kG) {
+                    const uint8_t b = __ldg(src + j);
+                    __stcg(out + p0 + j, b);
+                    S.ring[(p0 + j) & (kRing - 1)] = b;
+                }
+                if (gl == 0) {
                     pos += len;
                     br.init(src + len);
                 }
-                __syncwarp();
+                __syncwarp(gmask);
                 continue;
             }
             if (btype == 3) {
                 err = kInfErrData;
                 break;
             }
-            // ---- code lengths -> S.lens (lane 0), then tables (all lanes) ----
-            int nlit = 288, ndist = 30;
-            if (lane == 0) {
+            // ---- code lengths -> S.lens (decoding lane), then tables (all lanes of the group) ----
+            if (gl == 0) {
                 if (btype == 1) {
                     for (int s = 0; s < 144; ++s) S.lens[s] = 8;
                     for (int s = 144; s < 256; ++s) S.lens[s] = 9;
@@ -215,8 +228,8 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                     for (int s = 0; s < 30; ++s) S.lens[288 + s] = 5;
                 } else {
                     br.refill();
-                    nlit = (int)br.take(5) + 257;
-                    ndist = (int)br.take(5) + 1;
+                    const int nlit = (int)br.take(5) + 257;
+                    const int ndist = (int)br.take(5) + 1;
                     const int ncl = (int)br.take(4) + 4;
                     uint8_t cl[19];
                     for (int i = 0; i < 19; ++i) cl[i] = 0;
@@ -273,19 +286,20 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                         err = kInfErrData;
                 }
             }
-            err = __shfl_sync(0xFFFFFFFFu, err, 0);
+            err = GSHFL(err);
             if (err) break;
-            __syncwarp();
-            fill_primary(S.lit_tab, kLitBits, S.lit_cnt, S.lit_sym, lane);
-            fill_primary(S.dist_tab, kDistBits, S.dist_cnt, S.dist_sym, lane);
-            __syncwarp();
+            __syncwarp(gmask);
+            fill_primary(S.lit_tab, kLitBits, S.lit_cnt, S.lit_sym, gl);
+            fill_primary(S.dist_tab, kDistBits, S.dist_cnt, S.dist_sym, gl);
+            __syncwarp(gmask);
 
-            // ---- symbols: lane 0 decodes a batch of tokens, the warp executes it ----
+            // ---- symbols: the decoding lane fills a batch of tokens, the group executes it ----
             bool eob = false;
 #pragma unroll 1
             while (!eob && !err) {
                 int n = 0;
-                if (lane == 0) {
+                uint32_t batch_end = 0;
+                if (gl == 0) {
                     while (n < kTokens) {
                         br.refill();
                         uint32_t e = S.lit_tab[br.peek(kLitBits)];
@@ -350,48 +364,78 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                             break;
                         }
                     }
+                    batch_end = pos;
                 }
-                n = __shfl_sync(0xFFFFFFFFu, n, 0);
-                eob = __shfl_sync(0xFFFFFFFFu, (int)eob, 0) != 0;
-                err = __shfl_sync(0xFFFFFFFFu, err, 0);
+                n = GSHFL(n);
+                eob = GSHFL((int)eob) != 0;
+                err = GSHFL(err);
+                batch_end = GSHFL(batch_end);
                 if (err) break;
-                __syncwarp();
-                // execute: all literals first (they depend on nothing), then the matches in order
-                uint32_t t = 0, p = 0;
-                if (lane < n) {
-                    t = S.tok[lane];
-                    p = S.tpos[lane];
-                    if (t & 0x80000000u) __stcg(out + p, (uint8_t)t);
-                }
-                uint32_t mm = __ballot_sync(0xFFFFFFFFu, lane < n && !(t & 0x80000000u));
-                __syncwarp();
-                while (mm) {
-                    const int k = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const uint32_t tk = __shfl_sync(0xFFFFFFFFu, t, k), pk = __shfl_sync(0xFFFFFFFFu, p, k);
-                    const uint32_t len = tk & 511u, dist = tk >> 9;
-                    const uint8_t *src = out + pk - dist;
-                    if (dist >= len) {
-                        for (uint32_t j = lane; j < len; j += 32) __stcg(out + pk + j, __ldcg(src + j));
-                    } else if (dist == 1) {
-                        const uint8_t b = __ldcg(src);
-                        for (uint32_t j = lane; j < len; j += 32) __stcg(out + pk + j, b);
-                    } else {
-                        for (uint32_t j = lane; j < len; j += 32) __stcg(out + pk + j, __ldcg(src + (j % dist)));
+                __syncwarp(gmask);
+                // execute, strictly in output order so that the ring always holds the latest kRing positions: runs of
+                // literals are stored by up to kG lanes at once; a match whose source and destination both fit the ring
+                // (distance + length <= kRing) is copied through shared memory, older sources come from L2
+                // (st.cg / ld.cg), with a group barrier around every match.
+                const int gbase = lane & ~(kG - 1);
+                int k = 0;
+#pragma unroll 1
+                while (k < n) {
+                    const int kk = k + gl;
+                    const uint32_t t = kk < n ? S.tok[kk] : 0u;
+                    const uint32_t lit = (__ballot_sync(gmask, (t & 0x80000000u) != 0u) >> gbase) & ((1u << kG) - 1u);
+                    const int run = __ffs((int)~lit) - 1;  // literals at the head of the next kG tokens
+                    if (run > 0) {
+                        if (gl < run) {
+                            const uint32_t p = S.tpos[kk];
+                            __stcg(out + p, (uint8_t)t);
+                            S.ring[p & (kRing - 1)] = (uint8_t)t;
+                        }
+                        k += run;
+                        continue;
                     }
-                    __syncwarp();
+                    __syncwarp(gmask);  // everything before this match is in place
+                    const uint32_t tm = S.tok[k], p = S.tpos[k], len = tm & 511u, dist = tm >> 9;
+                    const uint32_t s0 = p - dist;
+                    if (dist + len <= (uint32_t)kRing) {
+                        if (dist >= len) {
+                            for (uint32_t j = gl; j < len; j += kG) {
+                                const uint8_t b = S.ring[(s0 + j) & (kRing - 1)];
+                                __stcg(out + p + j, b);
+                                S.ring[(p + j) & (kRing - 1)] = b;
+                            }
+                        } else {
+                            for (uint32_t j = gl; j < len; j += kG) {
+                                const uint8_t b = S.ring[(s0 + (j % dist)) & (kRing - 1)];
+                                __stcg(out + p + j, b);
+                                S.ring[(p + j) & (kRing - 1)] = b;
+                            }
+                        }
+                    } else {
+                        const uint8_t *src = out + s0;
+                        for (uint32_t j = gl; j < len; j += kG) {
+                            const uint8_t b = __ldcg(src + (dist >= len ? j : j % dist));
+                            __stcg(out + p + j, b);
+                            S.ring[(p + j) & (kRing - 1)] = b;
+                        }
+                    }
+                    __syncwarp(gmask);
+                    k += 1;
                 }
+                __syncwarp(gmask);
             }
         }
-        if (lane == 0 && !err && pos != isize) err = kInfErrSize;
-        err = __shfl_sync(0xFFFFFFFFu, err, 0);
-        if (err && lane == 0) {
+        if (gl == 0 && !err && pos != isize) err = kInfErrSize;
+        err = GSHFL(err);
+        if (err && gl == 0) {
             atomicOr(flags, err);
             atomicMin(first_bad, mi);
         }
-        __syncwarp();
+        __syncwarp(gmask);
     }
 }
+#undef GSHFL
+
+constexpr size_t kInfSmem = sizeof(MemberSmem) * kInfWarps * kGroups;
 
 }  // namespace
 
@@ -428,7 +472,7 @@ int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uin
         m.in_off = q;
         m.in_len = (uint32_t)(end - 8 - q);
         m.isize = (uint32_t)data[end - 4] | ((uint32_t)data[end - 3] << 8) | ((uint32_t)data[end - 2] << 16) | ((uint32_t)data[end - 1] << 24);
-        m.out_off = uo;
+        m.out_addr = uo;  // offset in the uncompressed stream; the caller rebases it to a device address
         if (bsize >= 0 && m.isize > 65536u) return fail(EXON_GPU_ERR_PARSE, "bgzf: member at byte %zu claims %u bytes (> 64 KiB)", p, m.isize);
         uo += m.isize;
         out.push_back(m);
@@ -438,25 +482,26 @@ int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uin
     return EXON_GPU_OK;
 }
 
-// Enqueues the inflate of `members` (table in host memory) from d_comp into d_out on the context's stream.
-// d_table / d_flags are device scratch owned by the caller (n_members entries / 2 words).
-int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint8_t *d_out, uint32_t *d_flags) {
+// Enqueues the inflate of `n_members` members (table in device memory; in_off relative to d_comp, out_addr absolute)
+// on the context's stream.  d_flags: two words of device scratch, {0, INT_MAX} before the launch.
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags) {
     if (n_members <= 0) return EXON_GPU_OK;
     static int occ = 0;
     if (!occ) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel, kInfWarps * 32, 0));
+        CUDA_TRY(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInfSmem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel, kInfWarps * 32, kInfSmem));
         if (occ < 1) occ = 1;
     }
-    const int grid = std::min((n_members + kInfWarps - 1) / kInfWarps, occ * c->sm_count);
-    bgzf_inflate_kernel<<<grid, kInfWarps * 32, 0, c->stream>>>(d_comp, d_table, n_members, d_out, d_flags, (int *)(d_flags + 1));
+    const int per_cta = kInfWarps * kGroups;
+    const int grid = std::min((n_members + per_cta - 1) / per_cta, occ * c->sm_count);
+    bgzf_inflate_kernel<<<grid, kInfWarps * 32, kInfSmem, c->stream>>>(d_comp, d_table, n_members, d_flags, (int *)(d_flags + 1));
     c->launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return EXON_GPU_OK;
 }
 
-
-// One whole BGZF / gzip file: members -> HBM as they are, inflated by the device into the arena, then framed like
-// a device-resident range (header skipped, last record normalised to end in '\n').
+// One whole BGZF / gzip file: the compressed bytes start their way to HBM at once; the inflate itself is deferred so
+// that the members of several files share one launch (flush_gz).
 int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
     if (!is_last || !gz_pending.empty()) {
         gz_pending.insert(gz_pending.end(), data, data + len);
@@ -474,31 +519,29 @@ int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
     if (cur_run_open && tail_len > 0) return fail(EXON_GPU_ERR_STATE, "feed_gzip: the previous plain-text range ended mid-line");
     std::vector<BgzfMember> members;
     uint64_t total = 0;
-    if (len) {
+    if (len)
         if (int rc = bgzf_walk(data, len, members, &total)) return rc;
-    }
     cudaStream_t st = ctx->stream;
+    uint8_t *dst = nullptr;
     if (total > 0) {
-        // device staging
-        const size_t o_tab = (len + 16 + 255) & ~(size_t)255;
-        const size_t o_flags = o_tab + ((members.size() * sizeof(BgzfMember) + 255) & ~(size_t)255);
-        const size_t need = o_flags + 256;
-        if (need > d_gz_cap) {
-            if (d_gz) {
-                CUDA_TRY(cudaStreamSynchronize(st));
-                CUDA_TRY(cudaFree(d_gz));
-                d_gz = nullptr;
-                d_gz_cap = 0;
+        const size_t need = ((len + 16 + 255) & ~(size_t)255);
+        if (gz_staged + need > d_gz_cap) {
+            if (int rc = flush_gz()) return rc;  // empties the staging area
+            if (need > d_gz_cap) {
+                if (d_gz) {
+                    CUDA_TRY(cudaStreamSynchronize(st));
+                    CUDA_TRY(cudaFree(d_gz));
+                    d_gz = nullptr;
+                    d_gz_cap = 0;
+                }
+                const size_t cap = std::max(need * 2, (size_t)256 << 20);
+                CUDA_TRY(cudaMalloc(&d_gz, cap));
+                d_gz_cap = cap;
             }
-            const size_t cap = std::max(need + need / 4, (size_t)8 << 20);
-            CUDA_TRY(cudaMalloc(&d_gz, cap));
-            d_gz_cap = cap;
         }
-        uint8_t *dz = (uint8_t *)d_gz;
+        uint8_t *dz = (uint8_t *)d_gz + gz_staged;
         CUDA_TRY(cudaMemcpyAsync(dz, data, len, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(dz + o_tab, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
-        const int init_flags[2] = {0, 0x7FFFFFFF};
-        CUDA_TRY(cudaMemcpyAsync(dz + o_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
+        if (!gz_pending.empty()) CUDA_TRY(cudaStreamSynchronize(st));  // the source is our own buffer, cleared on return
         // arena space: the tail of the current block if the file fits, else a fresh block (+1 for a missing final '\n')
         if (blocks.empty() || blocks.back().used + total + 1 > blocks.back().cap) {
             DevBlock nb;
@@ -506,37 +549,94 @@ int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
             blocks.push_back(nb);
         }
         DevBlock &b = blocks.back();
-        uint8_t *dst = b.ptr + b.used;
-        if (int rc = bgzf_inflate_launch(ctx, dz, (const BgzfMember *)(dz + o_tab), (int)members.size(), dst, (uint32_t *)(dz + o_flags)))
+        dst = b.ptr + b.used;
+        b.used = std::min(b.cap, b.used + (((size_t)total + 1 + 15) & ~(size_t)15));  // the next file starts 16-byte aligned
+        cur_run_open = false;  // plain-text feeds that follow start their own block
+        tail_len = 0;
+        for (BgzfMember m : members) {
+            m.in_off += gz_staged;
+            m.out_addr = (uint64_t)reinterpret_cast<uintptr_t>(dst) + m.out_addr;
+            gz_members.push_back(m);
+        }
+        gz_staged += need;
+    }
+    gz_files.push_back(GzFile{dst, total});
+    file_open = false;
+    if (gz_members.size() >= 16384) return flush_gz();
+    return EXON_GPU_OK;
+}
+
+// Inflates every pending member in one launch, then frames the files in feed order exactly like device-resident
+// ranges (header skipped on a host copy of each file's first bytes, last record normalised to end in '\n').
+int VcfStream::flush_gz() {
+    if (gz_files.empty()) return EXON_GPU_OK;
+    cudaStream_t st = ctx->stream;
+    std::vector<GzFile> files;
+    files.swap(gz_files);
+    std::vector<BgzfMember> members;
+    members.swap(gz_members);
+    gz_staged = 0;
+    constexpr size_t kProbe = 64 << 10;
+    if (!members.empty()) {
+        const size_t tab_bytes = (members.size() * sizeof(BgzfMember) + 255) & ~(size_t)255;
+        if (tab_bytes + 256 > d_gz_tab_cap) {
+            if (d_gz_tab) {
+                CUDA_TRY(cudaStreamSynchronize(st));
+                CUDA_TRY(cudaFree(d_gz_tab));
+                d_gz_tab = nullptr;
+                d_gz_tab_cap = 0;
+            }
+            CUDA_TRY(cudaMalloc(&d_gz_tab, (tab_bytes + 256) * 2));
+            d_gz_tab_cap = (tab_bytes + 256) * 2;
+        }
+        uint8_t *dt = (uint8_t *)d_gz_tab;
+        CUDA_TRY(cudaMemcpyAsync(dt, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
+        const int init_flags[2] = {0, 0x7FFFFFFF};
+        CUDA_TRY(cudaMemcpyAsync(dt + tab_bytes, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
+        if (int rc = bgzf_inflate_launch(ctx, (const uint8_t *)d_gz, (const BgzfMember *)dt, (int)members.size(), (uint32_t *)(dt + tab_bytes)))
             return rc;
-        CUDA_TRY(cudaMemcpyAsync(h_res + 6, dz + o_flags, 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h_res + 7, dst + total - 1, 1, cudaMemcpyDeviceToHost, st));
+        // flags + per file: first bytes (header probe) and the last byte, all in one round trip
+        if (int rc = ctx->ensure_scratch(0, 64 + files.size() * (kProbe + 16))) return rc;
+        uint8_t *h = (uint8_t *)ctx->h_scratch;
+        CUDA_TRY(cudaMemcpyAsync(h, dt + tab_bytes, 8, cudaMemcpyDeviceToHost, st));
+        for (size_t i = 0; i < files.size(); ++i) {
+            if (!files[i].total) continue;
+            uint8_t *slot = h + 64 + i * (kProbe + 16);
+            CUDA_TRY(cudaMemcpyAsync(slot, files[i].dst, (size_t)std::min<uint64_t>(files[i].total, kProbe), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(slot + kProbe, files[i].dst + files[i].total - 1, 1, cudaMemcpyDeviceToHost, st));
+        }
         CUDA_TRY(cudaStreamSynchronize(st));
-        const uint32_t *fl = reinterpret_cast<const uint32_t *>(h_res + 6);
+        const uint32_t *fl = reinterpret_cast<const uint32_t *>(h);
         if (fl[0])
             return fail(EXON_GPU_ERR_PARSE, "bgzf: member %d does not inflate:%s%s", (int)fl[1], (fl[0] & 1u) ? " invalid DEFLATE data;" : "",
                         (fl[0] & 2u) ? " size differs from ISIZE;" : "");
-        uint64_t n = total;
-        if (*reinterpret_cast<const uint8_t *>(h_res + 7) != '\n') {
+    }
+    // the probe area is reused by frame_device_range's slow path: copy what we need out of it first
+    struct Probe { int64_t body_off; int last; };
+    std::vector<Probe> probes(files.size(), Probe{-1, -1});
+    for (size_t i = 0; i < files.size(); ++i) {
+        if (!files[i].total) continue;
+        const uint8_t *slot = (const uint8_t *)ctx->h_scratch + 64 + i * (kProbe + 16);
+        probes[i].body_off = probe_body_offset(slot, (size_t)std::min<uint64_t>(files[i].total, kProbe), files[i].total <= kProbe);
+        probes[i].last = slot[kProbe];
+    }
+    for (size_t i = 0; i < files.size(); ++i) {
+        const GzFile &f = files[i];
+        if (!f.total) {  // an empty file (no members, or only empty members such as the BGZF EOF marker)
+            if (!runs.empty()) file_marks.push_back(FileMark{runs.size() - 1, runs.back().len});
+            continue;
+        }
+        uint64_t n = f.total;
+        if (probes[i].last != '\n') {
             static const uint8_t nl = '\n';
-            CUDA_TRY(cudaMemcpyAsync(dst + n, &nl, 1, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(f.dst + n, &nl, 1, cudaMemcpyHostToDevice, st));
             n += 1;
         }
-        b.used += (n + 15) & ~(size_t)15;  // the next file starts 16-byte aligned
-        if (b.used > b.cap) b.used = b.cap;
-        cur_run_open = false;  // plain-text feeds that follow start their own block
-        tail_len = 0;
-        // frame it exactly like a device-resident range (header probe, run, file mark, eager scan)
         hdr = fmt == kFmtVcf ? kAtLineStart : kBody;
         const int64_t before = body_bytes;
-        if (int rc = feed_device(dst, (size_t)n, true)) return rc;
-        if (n != total) body_bytes = before + (body_bytes - before) - 1;  // the added '\n' is not a fed byte
-        return EXON_GPU_OK;
+        if (int rc = frame_device_range(f.dst, (size_t)n, true, probes[i].body_off, '\n')) return rc;
+        if (n != f.total && body_bytes > before) body_bytes -= 1;  // the added '\n' is not a fed byte
     }
-    // an empty file (no members, or only empty members such as the BGZF EOF marker)
-    if (!runs.empty()) file_marks.push_back(FileMark{runs.size() - 1, runs.back().len});
-    hdr = fmt == kFmtVcf ? kAtLineStart : kBody;
-    file_open = false;
     return EXON_GPU_OK;
 }
 
@@ -565,12 +665,13 @@ extern "C" int exon_gpu_gzip_inflate(exon_gpu_ctx *c, const uint8_t *data, size_
     uint8_t *scr = (uint8_t *)c->scratch;
     uint8_t *d_out = out_is_device ? out : scr + o_out;
     cudaStream_t st = c->stream;
+    for (BgzfMember &m : members) m.out_addr += (uint64_t)reinterpret_cast<uintptr_t>(d_out);
     CUDA_TRY(cudaMemcpyAsync(scr, data, len, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(scr + o_tab, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
     const int init_flags[2] = {0, 0x7FFFFFFF};
     CUDA_TRY(cudaMemcpyAsync(scr + o_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaEventRecord(c->ev0, st));
-    if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), d_out, (uint32_t *)(scr + o_flags))) return rc;
+    if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), (uint32_t *)(scr + o_flags))) return rc;
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     CUDA_TRY(cudaMemcpyAsync(c->h_scratch, scr + o_flags, 8, cudaMemcpyDeviceToHost, st));

@@ -327,6 +327,7 @@ size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count, int64_t *out_rows) {
     Ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
+    if (int rc = s->flush_gz()) return rc;
     if (pred && (pred->min_mean_den <= 0)) return fail(EXON_GPU_ERR_ARG, "fastq_filter_count: min_mean_den must be positive");
     std::lock_guard<std::mutex> work(ctx->work_mu);
     std::vector<Piece> pieces;

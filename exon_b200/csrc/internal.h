@@ -69,6 +69,14 @@ struct Run {
     bool ends_with_newline;
 };
 
+// ---- BGZF inflate (bgzf.cu) ----
+struct BgzfMember {
+    uint64_t in_off;   // byte offset of the DEFLATE payload inside the compressed file
+    uint32_t in_len;   // payload bytes
+    uint32_t isize;    // uncompressed bytes (gzip trailer)
+    uint64_t out_addr; // bgzf_walk: byte offset in the uncompressed stream; at launch: absolute device address of the member's output
+};
+
 // One piece of a run that belongs to a single file (runs are cut at the recorded file ends).
 struct Piece {
     const uint8_t *base;
@@ -124,9 +132,20 @@ struct VcfStream {
 
     // ---- compressed feeds (bgzf.cu): bytes of the current .gz file that arrived before its last range ----
     std::vector<uint8_t> gz_pending;
-    void *d_gz = nullptr;      // device staging: compressed bytes | member table | flags
+    // whole files whose compressed bytes are on their way to HBM but whose inflate has not been launched yet: members of
+    // several files go into ONE launch so that thousands of members are in flight (bgzf.cu)
+    struct GzFile { uint8_t *dst; uint64_t total; };
+    std::vector<GzFile> gz_files;
+    std::vector<BgzfMember> gz_members;
+    size_t gz_staged = 0;      // bytes of d_gz in use
+    void *d_gz = nullptr;      // device staging for compressed bytes
     size_t d_gz_cap = 0;
+    void *d_gz_tab = nullptr;  // member table | flags
+    size_t d_gz_tab_cap = 0;
     int feed_gzip(const uint8_t *data, size_t len, bool is_last);
+    int flush_gz();
+    int frame_device_range(const uint8_t *text, size_t len, bool is_last, int64_t known_body_off, int known_last_byte);
+    int64_t probe_body_offset(const uint8_t *p, size_t n, bool whole_file) const;
     int feed_host(const uint8_t *text, size_t len, bool is_last);
     int feed_device(const uint8_t *text, size_t len, bool is_last);
     int append_host(const uint8_t *p, size_t n);
@@ -168,15 +187,8 @@ int fa_common_from(const exon_gpu_pred *pred, const exon_gpu_agg *agg, FaCommon 
 int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, int64_t max_rows, const FaCommon &k,
                             unsigned long long *d_out, bool timed);
 
-// ---- BGZF inflate (bgzf.cu) ----
-struct BgzfMember {
-    uint64_t in_off;   // byte offset of the DEFLATE payload inside the compressed file
-    uint32_t in_len;   // payload bytes
-    uint32_t isize;    // uncompressed bytes (gzip trailer)
-    uint64_t out_off;  // byte offset of the member's data in the uncompressed stream
-};
 int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uint64_t *total_out);
-int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint8_t *d_out, uint32_t *d_flags);
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags);
 
 // defined in fastq_scan.cu
 int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count, int64_t *out_rows);

@@ -719,6 +719,7 @@ int build_columns(VcfStream *s) {
 
 static int ensure_columns(VcfStream *s) {
     if (s->cols) return EXON_GPU_OK;
+    if (int rc = s->flush_gz()) return rc;
     if (s->file_open && s->tail_len > 0)
         return fail(EXON_GPU_ERR_STATE, "next_batch: the current file ends mid-line; finish it with is_last first");
     std::lock_guard<std::mutex> work(s->ctx->work_mu);

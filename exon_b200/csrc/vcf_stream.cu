@@ -55,6 +55,9 @@ void VcfStream::release_all() {
     runs.clear();
     file_marks.clear();
     gz_pending.clear();
+    gz_files.clear();
+    gz_members.clear();
+    gz_staged = 0;
     cur_run_open = false;
     tail_len = 0;
     body_bytes = 0;
@@ -145,9 +148,17 @@ int VcfStream::feed_host(const uint8_t *text, size_t len, bool is_last) {
     return EXON_GPU_OK;
 }
 
-int VcfStream::feed_device(const uint8_t *text, size_t len, bool is_last) {
+int VcfStream::feed_device(const uint8_t *text, size_t len, bool is_last) { return frame_device_range(text, len, is_last, -1, -1); }
+
+// Frames a device-resident byte range as (part of) a file: header skipped, run recorded, file end marked.
+// known_body_off >= 0: the caller already knows where the body starts inside the range (header state machine run on
+// a host copy); known_last_byte >= 0: the caller already knows the last byte of the range.
+int VcfStream::frame_device_range(const uint8_t *text, size_t len, bool is_last, int64_t known_body_off, int known_last_byte) {
     size_t off = 0;
-    if (hdr != kBody) {
+    if (known_body_off >= 0) {
+        off = (size_t)known_body_off;
+        hdr = kBody;
+    } else if (hdr != kBody) {
         // locate the end of the header by bouncing prefixes through pinned memory (records are not touched)
         const size_t kProbe = (size_t)1 << 20;
         if (int rc = ctx->ensure_scratch(0, kProbe)) return rc;
@@ -165,9 +176,14 @@ int VcfStream::feed_device(const uint8_t *text, size_t len, bool is_last) {
     if (n) {
         if (cur_run_open && tail_len > 0)
             return fail(EXON_GPU_ERR_STATE, "vcf_feed: a device range cannot follow a host range that ended mid-line");
-        CUDA_TRY(cudaMemcpyAsync(h_res + 7, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        const uint8_t last = *reinterpret_cast<const uint8_t *>(h_res + 7);
+        uint8_t last;
+        if (known_last_byte >= 0) {
+            last = (uint8_t)known_last_byte;
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(h_res + 7, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            last = *reinterpret_cast<const uint8_t *>(h_res + 7);
+        }
         if (!is_last && last != '\n')
             return fail(EXON_GPU_ERR_ARG, "vcf_feed: a non-final device range must end on a line boundary");
         cur_run_open = false;
@@ -184,6 +200,15 @@ int VcfStream::feed_device(const uint8_t *text, size_t len, bool is_last) {
     }
     if (has_pushdown) return eager_scan(false);
     return EXON_GPU_OK;
+}
+
+// header state machine over a host copy of a file's first bytes; returns the body offset, or -1 when the header
+// does not end inside [p, p + n) (and n is not the whole file)
+int64_t VcfStream::probe_body_offset(const uint8_t *p, size_t n, bool whole_file) const {
+    HdrState st = fmt == kFmtVcf ? kAtLineStart : kBody;
+    const uint8_t *q = skip_header(st, p, p + n);
+    if (st == kBody || whole_file) return (int64_t)(q - p);
+    return -1;
 }
 
 static void fill_segs(const std::vector<Run> &runs, size_t first, size_t last, int64_t first_skip_bytes,
@@ -304,6 +329,7 @@ int VcfStream::eager_scan(bool final_flush) {
 }
 
 int VcfStream::filter_count(const exon_gpu_region *region, int64_t *device_out, int64_t *host_out) {
+    if (int rc = flush_gz()) return rc;
     OwnedRegion r;
     if (int rc = r.assign(region)) return rc;
     if (r.has_interval && r.lo > r.hi) {

@@ -283,3 +283,25 @@ def quality_scores_to_list(s: bytes):
     out = np.empty(a.size, dtype=np.int32)
     _fq().exo_quality_scores_to_list(a.ctypes.data, a.size, out.ctypes.data)
     return out.tolist()
+
+
+def filter_count_gz_files(datas, chrom=None, lo=None, hi=None, target_partitions: int = 1, batch_size: int = 8192):
+    """(count, rows) over several in-memory .vcf.gz (BGZF / gzip) files: zlib inflate + the same record path,
+    one worker thread per file partition."""
+    arrs = [_buf(d) for d in datas]
+    n = len(arrs)
+    L = lib()
+    L.exo_vcf_gz_filter_count_files.restype = C.c_int64
+    L.exo_vcf_gz_filter_count_files.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int64,
+                                                C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                                C.POINTER(C.c_int64)]
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+    lens = (C.c_int64 * max(n, 1))(*[a.size for a in arrs])
+    cb = chrom.encode() if isinstance(chrom, str) else (chrom or b"")
+    rows = C.c_int64()
+    c = L.exo_vcf_gz_filter_count_files(ptrs, lens, n, target_partitions, batch_size, cb, len(cb), int(chrom is not None),
+                                        int(lo is not None or hi is not None), 1 if lo is None else lo,
+                                        INT64_MAX if hi is None else hi, C.byref(rows))
+    if c < 0:
+        raise ValueError(f"oracle error {c}")
+    return int(c), int(rows.value)

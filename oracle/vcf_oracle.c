@@ -408,3 +408,93 @@ void exo_chrom_match(const int32_t *offsets, const uint8_t *values, int64_t n, c
 void exo_interval_match(const int64_t *pos, int64_t n, int64_t lo, int64_t hi, uint8_t *out) {
     for (int64_t i = 0; i < n; i++) out[i] = (uint8_t)(pos[i] >= lo && pos[i] <= hi);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Compressed input.  VCFOpener::open wraps the byte stream in a (multi-member) gzip / BGZF decoder when the file
+ * compression type is GZIP (exon-core/src/datasources/vcf/file_opener/unindex_file_opener.rs:59-73); the records
+ * then take the same path.  zlib stands in for noodles-bgzf / flate2 (same RFC 1951/1952 format).
+ * Returns a malloc'ed buffer with the concatenated members, NULL on a corrupt stream.
+ * ------------------------------------------------------------------------------------------- */
+#include <zlib.h>
+uint8_t *exo_gunzip_all(const uint8_t *data, int64_t len, int64_t *out_len) {
+    z_stream z;
+    memset(&z, 0, sizeof(z));
+    if (inflateInit2(&z, 15 + 16) != Z_OK) return NULL;
+    int64_t cap = len * 6 + 65536, n = 0;
+    uint8_t *out = (uint8_t *)malloc((size_t)cap);
+    z.next_in = (Bytef *)data;
+    z.avail_in = (uInt)len;
+    while (z.avail_in > 0) {
+        if (cap - n < 65536) {
+            cap *= 2;
+            out = (uint8_t *)realloc(out, (size_t)cap);
+        }
+        z.next_out = out + n;
+        z.avail_out = (uInt)((cap - n) > 0x40000000 ? 0x40000000 : (cap - n));
+        const uInt before = z.avail_out;
+        int rc = inflate(&z, Z_NO_FLUSH);
+        n += before - z.avail_out;
+        if (rc == Z_STREAM_END) {
+            if (z.avail_in > 0 && inflateReset(&z) != Z_OK) { free(out); inflateEnd(&z); return NULL; }
+        } else if (rc != Z_OK) {
+            free(out);
+            inflateEnd(&z);
+            return NULL;
+        }
+    }
+    inflateEnd(&z);
+    *out_len = n;
+    return out;
+}
+
+typedef struct {
+    const uint8_t *const *datas;
+    const int64_t *lens;
+    int32_t n_files, me, parts;
+    int64_t batch_size;
+    const uint8_t *chrom;
+    int32_t chrom_len, has_chrom, has_interval;
+    int64_t lo, hi, count, rows;
+    int err;
+} gz_worker;
+
+static void *gz_worker_main(void *p) {
+    gz_worker *a = (gz_worker *)p;
+    for (int32_t i = a->me; i < a->n_files; i += a->parts) {
+        int64_t n = 0, rows = 0;
+        uint8_t *text = exo_gunzip_all(a->datas[i], a->lens[i], &n);
+        if (!text) { a->err = EXO_ERR_PARSE; return NULL; }
+        int64_t c = exo_vcf_filter_count(text, n, a->batch_size, a->chrom, a->chrom_len, a->has_chrom, a->has_interval, a->lo, a->hi, &rows);
+        free(text);
+        if (c < 0) { a->err = (int)c; return NULL; }
+        a->count += c;
+        a->rows += rows;
+    }
+    return NULL;
+}
+
+/* .vcf.gz files, one worker per file partition (files dealt round-robin) */
+int64_t exo_vcf_gz_filter_count_files(const uint8_t *const *datas, const int64_t *lens, int32_t n_files, int32_t target_partitions,
+                                      int64_t batch_size, const uint8_t *chrom, int32_t chrom_len, int32_t has_chrom,
+                                      int32_t has_interval, int64_t lo, int64_t hi, int64_t *n_rows) {
+    int32_t parts = n_files < target_partitions ? n_files : target_partitions;
+    if (parts < 1) { if (n_rows) *n_rows = 0; return 0; }
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)parts);
+    gz_worker *w = (gz_worker *)calloc((size_t)parts, sizeof(gz_worker));
+    for (int32_t g = 0; g < parts; g++) {
+        w[g].datas = datas; w[g].lens = lens; w[g].n_files = n_files; w[g].me = g; w[g].parts = parts; w[g].batch_size = batch_size;
+        w[g].chrom = chrom; w[g].chrom_len = chrom_len; w[g].has_chrom = has_chrom; w[g].has_interval = has_interval; w[g].lo = lo; w[g].hi = hi;
+        pthread_create(&th[g], NULL, gz_worker_main, &w[g]);
+    }
+    int64_t total = 0, rows = 0;
+    int err = 0;
+    for (int32_t g = 0; g < parts; g++) {
+        pthread_join(th[g], NULL);
+        if (w[g].err) err = w[g].err;
+        total += w[g].count;
+        rows += w[g].rows;
+    }
+    free(th); free(w);
+    if (n_rows) *n_rows = rows;
+    return err ? err : total;
+}
