@@ -29,7 +29,8 @@ SYMBOLS = [
     "exon_gpu_vcf_filter_count_global", "exon_gpu_filter_agg_accumulate", "exon_gpu_partial_read", "exon_gpu_memset",
     "exon_gpu_region_udf", "exon_gpu_filter_agg_batches", "exon_gpu_vcf_filter_agg",
     "exon_gpu_fastq_open", "exon_gpu_fastq_feed", "exon_gpu_fastq_filter_count", "exon_gpu_fastq_rows",
-    "exon_gpu_stream_close", "exon_gpu_stream_reset", "exon_gpu_stream_body_bytes", "exon_gpu_stream_feed_gzip", "exon_gpu_gzip_inflate",
+    "exon_gpu_stream_close", "exon_gpu_stream_reset", "exon_gpu_stream_body_bytes", "exon_gpu_stream_feed_gzip", "exon_gpu_gzip_inflate", "exon_gpu_bam_open", "exon_gpu_bam_feed",
+    "exon_gpu_bam_filter_count_by_reference", "exon_gpu_bam_group_name", "exon_gpu_allreduce_counts",
 ]
 
 
@@ -58,6 +59,10 @@ class FastqOpts(C.Structure):
 
 class FastqPred(C.Structure):
     _fields_ = [("phred_offset", C.c_int32), ("pad_", C.c_int32), ("min_mean_num", C.c_int64), ("min_mean_den", C.c_int64)]
+
+
+class BamPred(C.Structure):
+    _fields_ = [("flag_exclude", C.c_uint32), ("flag_require", C.c_uint32), ("min_mapq", C.c_int32), ("pad_", C.c_int32)]
 
 
 class ArrowSchema(C.Structure):
@@ -144,6 +149,11 @@ def load():
         "exon_gpu_fastq_rows": [vp, C.POINTER(i64)],
         "exon_gpu_stream_feed_gzip": [vp, vp, C.c_size_t, C.c_int],
         "exon_gpu_gzip_inflate": [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)],
+        "exon_gpu_bam_open": [vp, C.POINTER(vp)],
+        "exon_gpu_bam_feed": [vp, vp, C.c_size_t, C.c_int],
+        "exon_gpu_bam_filter_count_by_reference": [vp, C.POINTER(BamPred), C.POINTER(i64), i32, C.POINTER(i32), C.POINTER(i64)],
+        "exon_gpu_bam_group_name": [vp, i32, C.POINTER(C.c_char_p)],
+        "exon_gpu_allreduce_counts": [vp, C.POINTER(i64), i32],
         "exon_gpu_stream_close": [vp],
         "exon_gpu_stream_reset": [vp],
         "exon_gpu_stream_body_bytes": [vp, C.POINTER(i64)],

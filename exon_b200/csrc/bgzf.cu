@@ -39,7 +39,7 @@ constexpr int kInfWarps = 4;      // warps per CTA
 constexpr int kG = 8;             // lanes that work on one member (one decodes, all copy)
 constexpr int kGroups = 32 / kG;  // members in flight per warp
 constexpr int kLitBits = 9;       // primary table of the literal/length code
-constexpr int kDistBits = 8;      // primary table of the distance code
+constexpr int kDistBits = 7;      // primary table of the distance code
 constexpr int kTokens = 32;
 constexpr int kRing = 1024;       // recent output mirrored in shared memory (matches mostly reach back < 1 KiB in text)
 
@@ -58,9 +58,13 @@ struct MemberSmem {
     uint16_t dist_cnt[16];
     uint16_t cl_sym[19];
     uint16_t cl_cnt[16];
-    uint8_t lens[320];                // code lengths of the block being set up (HLIT + HDIST)
-    uint32_t tok[kTokens];            // literal: 0x80000000 | byte; match: len | dist << 9
-    uint32_t tpos[kTokens];           // output position of the token inside the member
+    union {                           // the code lengths are dead once the tables exist; the tokens live only afterwards
+        uint8_t lens[320];            // code lengths of the block being set up (HLIT + HDIST)
+        struct {
+            uint32_t tok[kTokens];    // literal: 0x80000000 | byte; match: len | dist << 9
+            uint32_t tpos[kTokens];   // output position of the token inside the member
+        };
+    };
     uint8_t ring[kRing];              // ring[p % kRing] = output byte p, for the most recent positions
 };
 
@@ -560,7 +564,7 @@ int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
         }
         gz_staged += need;
     }
-    gz_files.push_back(GzFile{dst, total});
+    gz_files.push_back(GzFile{dst, total, gz_members.size() - (total > 0 ? members.size() : 0), total > 0 ? members.size() : 0});
     file_open = false;
     if (gz_members.size() >= 16384) return flush_gz();
     return EXON_GPU_OK;
@@ -619,6 +623,17 @@ int VcfStream::flush_gz() {
         const uint8_t *slot = (const uint8_t *)ctx->h_scratch + 64 + i * (kProbe + 16);
         probes[i].body_off = probe_body_offset(slot, (size_t)std::min<uint64_t>(files[i].total, kProbe), files[i].total <= kProbe);
         probes[i].last = slot[kProbe];
+    }
+    if (fmt == kFmtBam) {
+        for (size_t i = 0; i < files.size(); ++i) {
+            const GzFile &f = files[i];
+            if (!f.total) continue;
+            // the probe slot is read before bam_frame_file may overwrite the pinned area: copy it
+            const uint8_t *slot = (const uint8_t *)ctx->h_scratch + 64 + i * (kProbe + 16);
+            std::vector<uint8_t> head(slot, slot + (size_t)std::min<uint64_t>(f.total, kProbe));
+            if (int rc = bam_frame_file(f.dst, f.total, head.data(), head.size(), members.data() + f.first_member, f.n_members)) return rc;
+        }
+        return EXON_GPU_OK;
     }
     for (size_t i = 0; i < files.size(); ++i) {
         const GzFile &f = files[i];

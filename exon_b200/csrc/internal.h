@@ -84,7 +84,7 @@ struct Piece {
     bool starts_file;
 };
 
-enum StreamFormat { kFmtVcf = 0, kFmtFastq = 1 };
+enum StreamFormat { kFmtVcf = 0, kFmtFastq = 1, kFmtBam = 2 };
 
 struct VcfStream {
     int fmt = kFmtVcf;  // FASTQ streams share the arena / run / file-mark machinery; they have no header to skip
@@ -134,7 +134,7 @@ struct VcfStream {
     std::vector<uint8_t> gz_pending;
     // whole files whose compressed bytes are on their way to HBM but whose inflate has not been launched yet: members of
     // several files go into ONE launch so that thousands of members are in flight (bgzf.cu)
-    struct GzFile { uint8_t *dst; uint64_t total; };
+    struct GzFile { uint8_t *dst; uint64_t total; size_t first_member, n_members; };
     std::vector<GzFile> gz_files;
     std::vector<BgzfMember> gz_members;
     size_t gz_staged = 0;      // bytes of d_gz in use
@@ -143,6 +143,17 @@ struct VcfStream {
     void *d_gz_tab = nullptr;  // member table | flags
     size_t d_gz_tab_cap = 0;
     int feed_gzip(const uint8_t *data, size_t len, bool is_last);
+    // ---- BAM streams (bam.cu): one entry per inflated file ----
+    struct BamFile {
+        uint8_t *dst = nullptr;
+        uint64_t total = 0, records_at = 0;
+        std::vector<std::string> ref_names;
+        std::vector<uint64_t> walk_starts;  // stream offsets where the speculative record walks begin (member starts)
+    };
+    std::vector<BamFile> bam_files;
+    std::vector<std::string> bam_groups;  // reference names in group order (valid after a query)
+    int bam_frame_file(uint8_t *dst, uint64_t total, const uint8_t *probe, size_t probe_len, const BgzfMember *members, size_t n_members);
+    int bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, int32_t cap, int32_t *n_groups, int64_t *total_rows);
     int flush_gz();
     int frame_device_range(const uint8_t *text, size_t len, bool is_last, int64_t known_body_off, int known_last_byte);
     int64_t probe_body_offset(const uint8_t *p, size_t n, bool whole_file) const;

@@ -2,6 +2,7 @@
 // aggregate state, the analogue of CoalescePartitionsExec + AggregateExec(Final).  NCCL is resolved with
 // dlopen at first use so that the library has no link-time dependency on a particular libnccl (the process
 // may already have torch's bundled NCCL loaded; RTLD_NOLOAD picks that one up first).
+#include <mutex>
 #include <dlfcn.h>
 
 #include <cstring>
@@ -125,6 +126,25 @@ int exon_gpu_allreduce_partial(exon_gpu_ctx *c, exon_gpu_partial *inout) {
     CUDA_TRY(cudaMemcpyAsync(c->h_scratch, c->scratch, sizeof(*inout), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     memcpy(inout, c->h_scratch, sizeof(*inout));
+    return EXON_GPU_OK;
+}
+
+// AggregateExec(Final) of a GROUP BY with a small, rank-independent group set (per-reference counts): one
+// ncclAllReduce(sum, int64, n) of the count vector.
+int exon_gpu_allreduce_counts(exon_gpu_ctx *c, int64_t *inout, int32_t n) {
+    if (!c || (!inout && n) || n < 0) return fail(EXON_GPU_ERR_ARG, "allreduce_counts: bad argument");
+    if (!c->nccl_comm) return fail(EXON_GPU_ERR_STATE, "allreduce_counts: exon_gpu_nccl_init has not been called");
+    if (n == 0) return EXON_GPU_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::lock_guard<std::mutex> work(c->work_mu);
+    const size_t bytes = (size_t)n * sizeof(int64_t);
+    if (int rc = c->ensure_scratch(bytes, bytes)) return rc;
+    memcpy(c->h_scratch, inout, bytes);
+    CUDA_TRY(cudaMemcpyAsync(c->scratch, c->h_scratch, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = nccl_allreduce_i64(c, (int64_t *)c->scratch, (size_t)n)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->h_scratch, c->scratch, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(inout, c->h_scratch, bytes);
     return EXON_GPU_OK;
 }
 

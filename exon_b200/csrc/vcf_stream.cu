@@ -56,6 +56,8 @@ void VcfStream::release_all() {
     file_marks.clear();
     gz_pending.clear();
     gz_files.clear();
+    bam_files.clear();
+    bam_groups.clear();
     gz_members.clear();
     gz_staged = 0;
     cur_run_open = false;

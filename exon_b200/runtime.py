@@ -112,6 +112,16 @@ class Context:
                                              out.size, 0, C.byref(n)))
         return out
 
+    def open_bam(self) -> "BamStream":
+        return BamStream(self)
+
+    def allreduce_counts(self, counts):
+        """exon_gpu_allreduce_counts: element-wise sum of an int64 vector over the NCCL communicator."""
+        n = len(counts)
+        buf = (C.c_int64 * max(n, 1))(*[int(x) for x in counts])
+        check(self.lib.exon_gpu_allreduce_counts(self.handle, buf, n))
+        return list(buf)[:n]
+
     def open_fastq(self, **kw) -> "FastqStream":
         return FastqStream(self, **kw)
 
@@ -401,3 +411,56 @@ class FastqStream:
         out = C.c_int64()
         check(self.lib.exon_gpu_stream_body_bytes(self.handle, C.byref(out)))
         return out.value
+
+
+class BamStream:
+    """exon_gpu_stream opened with exon_gpu_bam_open: one partition stream over a group of .bam files."""
+
+    # SAM flag bits (exon/exon-core/src/udfs/sam/samflags.rs:111-141)
+    UNMAPPED, SECONDARY, SUPPLEMENTARY = 0x4, 0x100, 0x800
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.handle = C.c_void_p()
+        check(self.lib.exon_gpu_bam_open(ctx.handle, C.byref(self.handle)))
+
+    def close(self):
+        if self.handle:
+            self.lib.exon_gpu_stream_close(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self):
+        check(self.lib.exon_gpu_stream_reset(self.handle))
+
+    def feed(self, data, *, is_last: bool = True):
+        if isinstance(data, PinnedBuffer):
+            data = data.array
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        self._last_host = data
+        check(self.lib.exon_gpu_bam_feed(self.handle, C.c_void_p(data.ctypes.data), data.size, int(is_last)))
+
+    def count_by_reference(self, *, flag_exclude: int = 0, flag_require: int = 0, min_mapq: int = -1, all_rows: bool = False):
+        """({reference name | None: count}, rows scanned): SELECT reference, COUNT(*) ... GROUP BY reference."""
+        n = C.c_int32()
+        rows = C.c_int64()
+        pred = None if all_rows else _abi.BamPred(flag_exclude, flag_require, min_mapq, 0)
+        pp = C.byref(pred) if pred is not None else None
+        rc = self.lib.exon_gpu_bam_filter_count_by_reference(self.handle, pp, None, 0, C.byref(n), C.byref(rows))
+        check(rc)
+        counts = (C.c_int64 * max(n.value, 1))()
+        check(self.lib.exon_gpu_bam_filter_count_by_reference(self.handle, pp, counts, n.value, C.byref(n), C.byref(rows)))
+        out = {}
+        for g in range(n.value):
+            nm = C.c_char_p()
+            check(self.lib.exon_gpu_bam_group_name(self.handle, g, C.byref(nm)))
+            out[nm.value.decode() if nm.value is not None else None] = int(counts[g])
+        return out, int(rows.value)

@@ -216,6 +216,31 @@ int exon_gpu_stream_close(exon_gpu_stream *s);
 int exon_gpu_stream_reset(exon_gpu_stream *s);
 int exon_gpu_stream_body_bytes(exon_gpu_stream *s, int64_t *out_bytes);
 
+/* ---- BAM partition stream (BASELINE configs[3]) ---------------------------------------- */
+/* BAMScan::execute + BAMOpener::open + BatchReader (exon/exon-core/src/datasources/bam/scanner.rs:138,
+ * bam/file_opener.rs:39, exon/exon-bam/src/batch_reader.rs:70-107).  Fed with the BGZF bytes of whole .bam files;
+ * the members are inflated on the device and the records never leave HBM. */
+int exon_gpu_bam_open(exon_gpu_ctx *ctx, exon_gpu_stream **out);
+int exon_gpu_bam_feed(exon_gpu_stream *s, const uint8_t *data, size_t len, int is_last);
+/* `(flag & flag_exclude) == 0 AND (flag & flag_require) == flag_require AND CAST(mapping_quality AS INT) >= min_mapq`:
+ * the flag tests are is_unmapped / is_secondary / ... (exon/exon-core/src/udfs/sam/samflags.rs:111-141) combined;
+ * mapping_quality is a nullable STRING column, NULL for MAPQ 255 (exon/exon-bam/src/array_builder.rs:136-143), so a
+ * record with MAPQ 255 never passes when min_mapq >= 0.  min_mapq < 0 drops the MAPQ term. */
+typedef struct {
+    uint32_t flag_exclude;
+    uint32_t flag_require;
+    int32_t min_mapq;
+    int32_t pad_;
+} exon_gpu_bam_pred;
+/* SELECT reference, COUNT(*) ... GROUP BY reference over everything fed so far.  Groups are reference NAMES in
+ * header order (first file first), followed by one group for the NULL reference (refID -1): counts[g] for
+ * g < *n_groups, `cap` = room in counts.  pred == NULL selects every record; *total_rows = records scanned.
+ * Fails with EXON_GPU_ERR_PARSE on a record chain that does not end at the end of the file. */
+int exon_gpu_bam_filter_count_by_reference(exon_gpu_stream *s, const exon_gpu_bam_pred *pred, int64_t *counts, int32_t cap,
+                                           int32_t *n_groups, int64_t *total_rows);
+/* Name of group g after a query (*name == NULL for the last group, the NULL reference). */
+int exon_gpu_bam_group_name(exon_gpu_stream *s, int32_t group, const char **name);
+
 /* ---- columnar filter + aggregate over Arrow buffers (a8-a9) ---------------------------------------------- */
 enum { EXON_GPU_AGG_COUNT_STAR = 0, EXON_GPU_AGG_COUNT = 1, EXON_GPU_AGG_SUM = 2, EXON_GPU_AGG_AVG = 3 };
 
@@ -279,6 +304,9 @@ int exon_gpu_region_udf(exon_gpu_ctx *ctx, int kind, const struct ArrowArray *ba
 int exon_gpu_nccl_unique_id(uint8_t id[EXON_GPU_NCCL_ID_BYTES]);
 int exon_gpu_nccl_init(exon_gpu_ctx *ctx, const uint8_t id[EXON_GPU_NCCL_ID_BYTES], int n_ranks, int rank);
 int exon_gpu_allreduce_partial(exon_gpu_ctx *ctx, exon_gpu_partial *inout);
+/* The same for a GROUP BY whose groups are the same on every rank (per-reference counts): one
+ * ncclAllReduce(sum, int64, n) of the host vector `inout`. */
+int exon_gpu_allreduce_counts(exon_gpu_ctx *ctx, int64_t *inout, int32_t n);
 /* AggregateExec(Partial) -> CoalescePartitionsExec -> AggregateExec(Final) for the fused COUNT in one call: the
  * local scan leaves its int64 partial in device memory, one ncclAllReduce(sum, int64, 1) runs on the same CUDA
  * stream, and both the local and the global count come back with a single synchronisation.  Collective: every

@@ -305,3 +305,72 @@ def filter_count_gz_files(datas, chrom=None, lo=None, hi=None, target_partitions
     if c < 0:
         raise ValueError(f"oracle error {c}")
     return int(c), int(rows.value)
+
+
+# ---- BAM (oracle/bam_oracle.c) -------------------------------------------------------------------------------
+
+class BamRow(C.Structure):
+    _fields_ = [("name", C.c_char * 256), ("flag", C.c_int32), ("ref_id", C.c_int32), ("mate_ref_id", C.c_int32), ("mapq", C.c_int32),
+                ("start", C.c_int64), ("end", C.c_int64), ("cigar", C.c_char * 1024), ("l_seq", C.c_int32), ("first_quals", C.c_int32 * 8)]
+
+
+class Bam:
+    """One .bam file opened by the oracle (zlib inflate + header)."""
+
+    def __init__(self, data):
+        L = lib()
+        L.exo_bam_open.restype = C.c_void_p
+        L.exo_bam_open.argtypes = [C.c_void_p, C.c_int64]
+        L.exo_bam_close.argtypes = [C.c_void_p]
+        L.exo_bam_n_ref.restype = C.c_int32
+        L.exo_bam_n_ref.argtypes = [C.c_void_p]
+        L.exo_bam_ref_name.restype = C.c_char_p
+        L.exo_bam_ref_name.argtypes = [C.c_void_p, C.c_int32]
+        L.exo_bam_scan.restype = C.c_int64
+        L.exo_bam_scan.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(C.c_int64), C.c_int64,
+                                   C.POINTER(BamRow)]
+        self._L = L
+        a = _buf(data)
+        self._h = L.exo_bam_open(a.ctypes.data, a.size)
+        if not self._h:
+            raise ValueError("not a BAM file")
+        self.refs = [L.exo_bam_ref_name(self._h, i).decode() for i in range(L.exo_bam_n_ref(self._h))]
+
+    def close(self):
+        if self._h:
+            self._L.exo_bam_close(self._h)
+            self._h = None
+
+    def count_by_reference(self, flag_exclude=0, flag_require=0, min_mapq=-1, all_rows=False):
+        counts = (C.c_int64 * (len(self.refs) + 1))()
+        n = self._L.exo_bam_scan(self._h, int(not all_rows), flag_exclude, flag_require, min_mapq, counts, -1, None)
+        if n < 0:
+            raise ValueError("malformed BAM record chain")
+        out = {nm: int(counts[i]) for i, nm in enumerate(self.refs)}
+        out[None] = int(counts[len(self.refs)])
+        return out, int(n)
+
+    def row(self, i: int):
+        r = BamRow()
+        n = self._L.exo_bam_scan(self._h, 0, 0, 0, -1, None, i, C.byref(r))
+        if n < 0 or i >= n:
+            raise IndexError(i)
+        return {"name": r.name.decode() or None, "flag": r.flag, "reference": self.refs[r.ref_id] if r.ref_id >= 0 else None,
+                "start": r.start or None, "end": r.end or None, "mapping_quality": None if r.mapq == 255 else str(r.mapq),
+                "cigar": r.cigar.decode(), "mate_reference": self.refs[r.mate_ref_id] if r.mate_ref_id >= 0 else None,
+                "l_seq": r.l_seq, "first_quals": list(r.first_quals)}
+
+
+def bam_count_by_reference_files(files, **kw):
+    """Sum of per-file group counts keyed by reference NAME (the GROUP BY merges equal names across files)."""
+    total, rows = {}, 0
+    for f in files:
+        b = Bam(f)
+        try:
+            c, n = b.count_by_reference(**kw)
+        finally:
+            b.close()
+        rows += n
+        for k, v in c.items():
+            total[k] = total.get(k, 0) + v
+    return total, rows

@@ -18,12 +18,33 @@ from synth import vcf  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=100_000_000)
+ap.add_argument("--gz-rows", type=int, default=0, help="profile the BGZF inflate on this many VCF rows")
 ap.add_argument("--fastq-reads", type=int, default=0, help="profile the FASTQ fused scan instead of VCF")
 ap.add_argument("--shards", type=int, default=64)
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--modes", default="lazy,lazy,strict,count_star,interval")
 args = ap.parse_args()
 
+if args.gz_rows:
+    import ctypes as C
+    from concurrent.futures import ThreadPoolExecutor
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from bgzf_util import bgzf_compress
+
+    cols = vcf.columns(args.gz_rows)
+    files = vcf.shards(cols, 16)
+    with ThreadPoolExecutor(16) as ex:
+        gz = b"".join(ex.map(lambda f: bgzf_compress(f.tobytes(), 6), files))
+    raw = sum(f.size for f in files)
+    with Context(0) as ctx:
+        d = ctx.device_buffer(raw + 64)
+        a = np.frombuffer(gz, dtype=np.uint8)
+        for _ in range(3):
+            n = C.c_size_t()
+            _abi.check(ctx.lib.exon_gpu_gzip_inflate(ctx.handle, C.c_void_p(a.ctypes.data), a.size, C.c_void_p(d.ptr), d.nbytes, 1, C.byref(n)))
+            print("inflate", n.value, raw, f"{ctx.last_kernel_ms():.3f} ms", flush=True)
+    raise SystemExit(0)
 if args.fastq_reads:
     from synth import fastq
 
