@@ -204,18 +204,18 @@ int VcfStream::bam_frame_file(uint8_t *dst, uint64_t total, const uint8_t *probe
         f.walk_starts.push_back(std::max(off, f.records_at));
     }
     bam_files.push_back(std::move(f));
+    bam_tables_dirty = true;
     return EXON_GPU_OK;
 }
 
-int VcfStream::bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, int32_t cap, int32_t *n_groups_out, int64_t *total_rows) {
-    if (int rc = flush_gz()) return rc;
-    Ctx *c = ctx;
-    cudaStream_t st = c->stream;
-    std::lock_guard<std::mutex> work(c->work_mu);
-    // groups = reference NAMES in order of first appearance, then the NULL reference
+// Device tables of a BAM stream: walk entries | first entry of every file (serial fallback) | refID -> group maps |
+// exits | counts | misc.  Built once per set of resident files; the verification kernel corrects entry points in
+// place, so later queries start from walks that are already right.
+int VcfStream::bam_build_tables() {
+    cudaStream_t st = ctx->stream;
     bam_groups.clear();
     std::vector<int32_t> remap;
-    std::vector<BamEntry> entries;
+    std::vector<BamEntry> entries, firsts;
     for (const BamFile &f : bam_files) {
         const int32_t remap0 = (int32_t)remap.size();
         for (const std::string &nm : f.ref_names) {
@@ -239,77 +239,98 @@ int VcfStream::bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, 
             e.last_of_file = i + 1 == f.walk_starts.size();
             e.pad_ = 0;
             entries.push_back(e);
+            if (i == 0) {
+                BamEntry s = e;
+                s.last_of_file = 1;
+                firsts.push_back(s);
+            }
         }
     }
     const int32_t n_groups = (int32_t)bam_groups.size() + 1;
     for (int32_t &r : remap)
         if (r < 0) r = n_groups - 1;
+    bam_n_entries = entries.size();
+    bam_n_firsts = firsts.size();
+    bam_n_groups = n_groups;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    bam_o_firsts = al((entries.size() + 1) * sizeof(BamEntry));
+    bam_o_remap = bam_o_firsts + al((firsts.size() + 1) * sizeof(BamEntry));
+    bam_o_exits = bam_o_remap + al(remap.size() * 4 + 4);
+    bam_o_counts = bam_o_exits + al((entries.size() + 1) * 8);
+    bam_o_misc = bam_o_counts + al((size_t)n_groups * 8);
+    const size_t need = bam_o_misc + 256;
+    if (need > d_bam_cap) {
+        if (d_bam) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaFree(d_bam));
+            d_bam = nullptr;
+            d_bam_cap = 0;
+        }
+        CUDA_TRY(cudaMalloc(&d_bam, need * 2));
+        d_bam_cap = need * 2;
+    }
+    uint8_t *d = (uint8_t *)d_bam;
+    if (!entries.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(d, entries.data(), entries.size() * sizeof(BamEntry), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d + bam_o_firsts, firsts.data(), firsts.size() * sizeof(BamEntry), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d + bam_o_remap, remap.data(), remap.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // the sources are locals
+    }
+    bam_tables_dirty = false;
+    return EXON_GPU_OK;
+}
+
+int VcfStream::bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, int32_t cap, int32_t *n_groups_out, int64_t *total_rows) {
+    if (int rc = flush_gz()) return rc;
+    Ctx *c = ctx;
+    cudaStream_t st = c->stream;
+    if (bam_tables_dirty)
+        if (int rc = bam_build_tables()) return rc;
+    const int32_t n_groups = bam_n_groups;
     if (n_groups_out) *n_groups_out = n_groups;
     if (total_rows) *total_rows = 0;
     if (counts)
         for (int32_t g = 0; g < std::min(cap, n_groups); ++g) counts[g] = 0;
     if (counts && cap < n_groups) return fail(EXON_GPU_ERR_ARG, "bam_filter_count: %d groups, room for %d", n_groups, cap);
-    if (entries.empty()) return EXON_GPU_OK;
-
-    const size_t n = entries.size();
-    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t o_ent = 0, o_remap = o_ent + al((n + 1) * sizeof(BamEntry)), o_exits = o_remap + al(remap.size() * 4),
-                 o_counts = o_exits + al(n * 8), o_misc = o_counts + al((size_t)n_groups * 8);
-    if (int rc = c->ensure_scratch(o_misc + 256, 64 + (size_t)n_groups * 8)) return rc;
-    uint8_t *scr = (uint8_t *)c->scratch;
-    CUDA_TRY(cudaMemcpyAsync(scr + o_ent, entries.data(), n * sizeof(BamEntry), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(scr + o_remap, remap.data(), remap.size() * 4, cudaMemcpyHostToDevice, st));
+    if (bam_n_entries == 0) return EXON_GPU_OK;
+    std::lock_guard<std::mutex> work(c->work_mu);
+    if (int rc = c->ensure_scratch(0, 256 + (size_t)n_groups * 8)) return rc;
+    uint8_t *d = (uint8_t *)d_bam;
     BamArgs a;
     memset(&a, 0, sizeof(a));
-    a.entries = (const BamEntry *)(scr + o_ent);
-    a.n_entries = (int32_t)n;
-    a.remap = (const int32_t *)(scr + o_remap);
-    a.exits = (uint64_t *)(scr + o_exits);
-    a.counts = (unsigned long long *)(scr + o_counts);
-    a.rows = (unsigned long long *)(scr + o_misc);
+    a.remap = (const int32_t *)(d + bam_o_remap);
+    a.exits = (uint64_t *)(d + bam_o_exits);
+    a.counts = (unsigned long long *)(d + bam_o_counts);
+    a.rows = (unsigned long long *)(d + bam_o_misc);
     a.n_groups = n_groups;
     a.has_pred = pred != nullptr;
     a.flag_exclude = pred ? pred->flag_exclude : 0;
     a.flag_require = pred ? pred->flag_require : 0;
     a.min_mapq = pred ? pred->min_mapq : -1;
-    unsigned int *d_verify = (unsigned int *)(scr + o_misc + 64);
+    unsigned int *d_verify = (unsigned int *)(d + bam_o_misc + 64);
     uint8_t *h = (uint8_t *)c->h_scratch;
     bool ok = false;
     constexpr int kRounds = 6;
     for (int round = 0; round <= kRounds && !ok; ++round) {
-        const bool serial = round == kRounds;  // last resort: one thread per file, a single chain
-        int launch_n = (int)n;
-        if (serial) {
-            // entries of the first walk of every file only, restored to the first record
-            std::vector<BamEntry> firsts;
-            for (const BamFile &f : bam_files)
-                if (!f.walk_starts.empty()) {
-                    for (const BamEntry &e : entries)
-                        if (e.base == f.dst && e.start == f.walk_starts[0]) {
-                            BamEntry s = e;
-                            s.last_of_file = 1;
-                            firsts.push_back(s);
-                            break;
-                        }
-                }
-            launch_n = (int)firsts.size();
-            CUDA_TRY(cudaMemcpyAsync(scr + o_ent, firsts.data(), firsts.size() * sizeof(BamEntry), cudaMemcpyHostToDevice, st));
-        }
+        const bool serial = round == kRounds;  // last resort: one thread per file, a single chain from the first record
+        BamEntry *ent = (BamEntry *)(serial ? d + bam_o_firsts : d);
+        const int launch_n = (int)(serial ? bam_n_firsts : bam_n_entries);
+        a.entries = ent;
         a.n_entries = launch_n;
         a.serial = serial;
-        CUDA_TRY(cudaMemsetAsync(scr + o_counts, 0, (size_t)n_groups * 8, st));
-        CUDA_TRY(cudaMemsetAsync(scr + o_misc, 0, 128, st));
+        CUDA_TRY(cudaMemsetAsync(d + bam_o_counts, 0, (size_t)n_groups * 8, st));
+        CUDA_TRY(cudaMemsetAsync(d + bam_o_misc, 0, 128, st));
         if (round == 0) CUDA_TRY(cudaEventRecord(c->ev0, st));
         bam_walk_kernel<<<(launch_n + kBamThreads - 1) / kBamThreads, kBamThreads, 0, st>>>(a);
-        bam_verify_kernel<<<(launch_n + 127) / 128, 128, 0, st>>>((BamEntry *)(scr + o_ent), launch_n, a.exits, serial ? 0 : 1, d_verify);
+        bam_verify_kernel<<<(launch_n + 127) / 128, 128, 0, st>>>(ent, launch_n, a.exits, serial ? 0 : 1, d_verify);
         if (round == 0) {
             CUDA_TRY(cudaEventRecord(c->ev1, st));
             c->timed = true;
         }
         c->launches.fetch_add(2);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(h, scr + o_misc, 128, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h + 128, scr + o_counts, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h, d + bam_o_misc, 128, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h + 128, d + bam_o_counts, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         const unsigned int *v = reinterpret_cast<const unsigned int *>(h + 64);
         if (v[0] == 0 && v[1] == 0) ok = true;

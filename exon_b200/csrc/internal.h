@@ -84,7 +84,7 @@ struct Piece {
     bool starts_file;
 };
 
-enum StreamFormat { kFmtVcf = 0, kFmtFastq = 1, kFmtBam = 2 };
+enum StreamFormat { kFmtVcf = 0, kFmtFastq = 1, kFmtBam = 2, kFmtMzml = 3 };
 
 struct VcfStream {
     int fmt = kFmtVcf;  // FASTQ streams share the arena / run / file-mark machinery; they have no header to skip
@@ -152,6 +152,12 @@ struct VcfStream {
     };
     std::vector<BamFile> bam_files;
     std::vector<std::string> bam_groups;  // reference names in group order (valid after a query)
+    bool bam_tables_dirty = true;
+    void *d_bam = nullptr;                // walk entries | per-file first entries | remap | exits | counts | misc
+    size_t d_bam_cap = 0, bam_n_entries = 0, bam_n_firsts = 0;
+    size_t bam_o_firsts = 0, bam_o_remap = 0, bam_o_exits = 0, bam_o_counts = 0, bam_o_misc = 0;
+    int32_t bam_n_groups = 1;
+    int bam_build_tables();
     int bam_frame_file(uint8_t *dst, uint64_t total, const uint8_t *probe, size_t probe_len, const BgzfMember *members, size_t n_members);
     int bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, int32_t cap, int32_t *n_groups, int64_t *total_rows);
     int flush_gz();
@@ -200,6 +206,9 @@ int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, i
 
 int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uint64_t *total_out);
 int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags);
+
+// defined in mzml.cu
+int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected, int64_t *out_spectra);
 
 // defined in fastq_scan.cu
 int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count, int64_t *out_rows);

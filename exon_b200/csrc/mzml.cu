@@ -1,0 +1,400 @@
+// mzml.cu -- mzML text -> m/z range predicate -> SUM(intensity), fused (BASELINE.json configs[4]).
+//
+// Replaces, for `SELECT SUM(i) FROM (SELECT unnest(mz.mz) m, unnest(intensity.intensity) i FROM mzml) WHERE m BETWEEN a AND b`:
+//   MzMLReader::read_spectrum        exon/exon-mzml/src/mzml_reader/parser.rs:43-109 (quick-xml events of every <spectrum>)
+//   decode_binary_array              exon/exon-mzml/src/mzml_reader/binary_conversion.rs:26-95 (base64 -> LE f32 / f64 -> f64)
+//   MzMLArrayBuilder::append         exon/exon-mzml/src/array_builder.rs:236-416 (List<Float64> per array kind, classified by
+//                                    the cvParam accessions of exon/exon-mzml/src/mzml_reader/types.rs:119-121,207-208,274-275)
+//   unnest + FilterExec + AggregateExec(Partial) sum                                 (DataFusion 44, third party)
+// Three kernels, none of which materialises a List<Float64>:
+//   M1 events   the warp-private TMA tile pipeline (tile_ring.cuh) reads the text once.  '<' and ':' never occur inside a
+//               base64 payload, so 16-byte chunks are screened for those two bytes; the few hits are classified
+//               (<spectrum, <binaryDataArray, <binary>, </binary>, accession="MS:1000xxx") and appended to an event list
+//               (segment, offset, kind packed into 64 bits), which cub then sorts into file order
+//   M2 spectra  one thread per <spectrum> event walks the events up to the next spectrum and leaves a descriptor of its
+//               m/z and intensity payloads (address, trimmed length, 32/64 bit, compression)
+//   M3 sum      one warp per spectrum: lane i decodes value i of both payloads straight from the base64 text (16 characters
+//               cover any 8-byte value: 5 aligned word loads, a 256-entry table in shared memory, byte permutes), applies
+//               lo <= mz <= hi and accumulates intensity in f64; warp shuffle reduction, one atomicAdd per warp
+// zlib-compressed arrays (MS:1000574) are reported as EXON_GPU_ERR_UNSUPPORTED for now (the oracle handles them).
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cstring>
+
+#include "common.cuh"
+#include "internal.h"
+#include "tile_ring.cuh"
+
+namespace exon {
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? EXON_GPU_ERR_OOM : EXON_GPU_ERR_CUDA, "%s: %s", \
+                        #expr, cudaGetErrorString(_e));                                                  \
+    } while (0)
+
+namespace {
+
+using MzRing = TileRing<4096, 3, 8, 16, 368, 16>;
+constexpr int kMzU = MzRing::TILE / 512;
+
+enum : uint32_t {
+    kEvSpectrum = 1, kEvBda = 2, kEvMz = 3, kEvIntensity = 4, kEvWave = 5, kEvF32 = 6, kEvF64 = 7, kEvZlib = 8, kEvNoComp = 9,
+    kEvBinStart = 10, kEvBinEnd = 11
+};
+constexpr uint32_t kMzErrFormat = 1u;   // malformed structure (a <binary> without </binary>, missing data type, bad base64)
+constexpr uint32_t kMzErrZlib = 2u;     // zlib-compressed array: not decoded on the device yet
+
+struct MzArgs {
+    const ScanSeg *segs;
+    int32_t n_segs;
+    int64_t n_tiles;
+    unsigned long long *events;   // key = seg << 44 | offset << 4 | kind
+    unsigned long long cap;
+    unsigned long long *n_events;  // [0] events appended (may exceed cap: the host retries) ... [5] <spectrum> events
+};
+
+__device__ __forceinline__ bool is_delim(uint32_t c) { return c == ' ' || c == '>' || c == '/' || c == '\n' || c == '\t' || c == '\r'; }
+
+template <class V>
+__device__ __forceinline__ bool match_at(const V &v, int p, const char *lit, int n) {
+    for (int i = 0; i < n; ++i)
+        if (view_byte(v, p + i) != (uint32_t)(uint8_t)lit[i]) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(MzRing::WARPS * 32, 2) mzml_events_kernel(const __grid_constant__ MzArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    MzRing ring;
+    ring.init(smem_raw, a.segs, a.n_tiles);
+    const int lane = ring.lane;
+    constexpr uint32_t kLT4 = 0x3C3C3C3Cu, kCOL4 = 0x3A3A3A3Au;
+#pragma unroll 1
+    for (int64_t T = ring.first_tile(); T < a.n_tiles; T += ring.nw) {
+        const MzRing::View v = ring.acquire();
+        // offset of tile byte 0 inside its segment
+        const long long tile_off = (long long)(v.g - (a.segs[v.seg].base + a.segs[v.seg].skip));
+        const unsigned long long seg_key = (unsigned long long)v.seg << 44;
+#pragma unroll 1
+        for (int u = 0; u < kMzU; ++u) {
+            const int c0 = (u * 32 + lane) * 16;
+            if (!(v.interior || c0 < v.sm_hi)) continue;
+            const uint4 w = lds128(v.sa + (uint32_t)c0);
+            uint32_t hit = zero_bytes_fast(w.x ^ kLT4) | zero_bytes_fast(w.y ^ kLT4) | zero_bytes_fast(w.z ^ kLT4) | zero_bytes_fast(w.w ^ kLT4) |
+                           zero_bytes_fast(w.x ^ kCOL4) | zero_bytes_fast(w.y ^ kCOL4) | zero_bytes_fast(w.z ^ kCOL4) | zero_bytes_fast(w.w ^ kCOL4);
+            if (!hit) continue;
+            uint32_t m = pack_flags16(zero_bytes_exact(w.x ^ kLT4) | zero_bytes_exact(w.x ^ kCOL4), zero_bytes_exact(w.y ^ kLT4) | zero_bytes_exact(w.y ^ kCOL4),
+                                      zero_bytes_exact(w.z ^ kLT4) | zero_bytes_exact(w.z ^ kCOL4), zero_bytes_exact(w.w ^ kLT4) | zero_bytes_exact(w.w ^ kCOL4));
+            while (m) {
+                const int p = c0 + __ffs(m) - 1;
+                m &= m - 1;
+                if (p < v.seg_lo || p >= v.hi) continue;
+                uint32_t kind = 0;
+                long long at = tile_off + p;
+                if (view_byte(v, p) == '<') {
+                    const uint32_t c1 = view_byte(v, p + 1);
+                    if (c1 == 's') {
+                        if (match_at(v, p + 1, "spectrum", 8) && is_delim(view_byte(v, p + 9))) kind = kEvSpectrum;
+                    } else if (c1 == 'b') {
+                        if (match_at(v, p + 1, "binary", 6)) {
+                            if (view_byte(v, p + 7) == '>') {
+                                kind = kEvBinStart;
+                                at += 8;  // the payload starts after the tag
+                            } else if (match_at(v, p + 7, "DataArray", 9) && is_delim(view_byte(v, p + 16))) {
+                                kind = kEvBda;
+                            }
+                        }
+                    } else if (c1 == '/') {
+                        if (match_at(v, p + 2, "binary>", 7)) kind = kEvBinEnd;
+                    }
+                } else {
+                    // ... accession="MS:1000xxx": p is the ':'
+                    if (match_at(v, p - 14, " accession=\"MS:1000", 19) && view_byte(v, p + 8) == '"') {
+                        const uint32_t d0 = view_byte(v, p + 5) - '0', d1 = view_byte(v, p + 6) - '0', d2 = view_byte(v, p + 7) - '0';
+                        if (d0 <= 9u && d1 <= 9u && d2 <= 9u) {
+                            const uint32_t code = d0 * 100u + d1 * 10u + d2;
+                            kind = code == 514u ? kEvMz : code == 515u ? kEvIntensity : code == 617u ? kEvWave : code == 521u ? kEvF32
+                                 : code == 523u ? kEvF64 : code == 574u ? kEvZlib : code == 576u ? kEvNoComp : 0u;
+                        }
+                    }
+                }
+                if (kind) {
+                    if (kind == kEvSpectrum) atomicAdd(a.n_events + 5, 1ull);
+                    const unsigned long long i = atomicAdd(a.n_events, 1ull);
+                    if (i < a.cap) a.events[i] = seg_key | ((unsigned long long)at << 4) | kind;
+                }
+            }
+        }
+        ring.release(T);
+    }
+}
+
+struct SpecDesc {
+    const uint8_t *mz, *in;   // trimmed base64 payloads (NULL: the spectrum has no such array)
+    uint32_t mz_len, in_len;  // characters
+    uint32_t mz_f32, in_f32;
+};
+
+__device__ __forceinline__ bool is_ws(uint8_t c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
+
+__global__ void mzml_spectra_kernel(const unsigned long long *ev, unsigned long long n, const ScanSeg *segs, SpecDesc *out,
+                                    unsigned long long *n_spec, uint32_t *flags) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (ev[i] & 15u) != kEvSpectrum) return;
+    const unsigned long long seg = ev[i] >> 44;
+    SpecDesc d;
+    d.mz = d.in = nullptr;
+    d.mz_len = d.in_len = d.mz_f32 = d.in_f32 = 0;
+    uint32_t kind = 0, f32 = 0, f64 = 0, zl = 0, nc = 0, err = 0;
+    unsigned long long start = 0;
+    bool open = false;
+    for (unsigned long long j = i + 1; j < n; ++j) {
+        const unsigned long long e = ev[j];
+        const uint32_t k = (uint32_t)(e & 15u);
+        if ((e >> 44) != seg || k == kEvSpectrum) break;
+        const unsigned long long off = (e >> 4) & ((1ull << 40) - 1ull);
+        if (k == kEvBda) { kind = f32 = f64 = zl = nc = 0; open = false; }
+        else if (k == kEvMz || k == kEvIntensity || k == kEvWave) { if (!kind) kind = k; }
+        else if (k == kEvF32) f32 = 1;
+        else if (k == kEvF64) f64 = 1;
+        else if (k == kEvZlib) zl = 1;
+        else if (k == kEvNoComp) nc = 1;
+        else if (k == kEvBinStart) { start = off; open = true; }
+        else if (k == kEvBinEnd) {
+            if (!open) { err |= kMzErrFormat; continue; }
+            open = false;
+            const uint8_t *base = segs[seg].base + segs[seg].skip;
+            const uint8_t *b0 = base + start, *b1 = base + off;
+            while (b0 < b1 && is_ws(*b0)) ++b0;   // quick-xml trim_text(true)
+            while (b1 > b0 && is_ws(b1[-1])) --b1;
+            if (b1 == b0 || (kind != kEvMz && kind != kEvIntensity)) continue;  // empty content, or an array the query does not read
+            if ((!f32 && !f64) || (!zl && !nc)) { err |= kMzErrFormat; continue; }
+            if (zl) { err |= kMzErrZlib; continue; }
+            if (((b1 - b0) & 3) != 0 || (b1 - b0) > 0x7FFFFFFFll) { err |= kMzErrFormat; continue; }
+            if (kind == kEvMz) { d.mz = b0; d.mz_len = (uint32_t)(b1 - b0); d.mz_f32 = f32 && !f64; }
+            else { d.in = b0; d.in_len = (uint32_t)(b1 - b0); d.in_f32 = f32 && !f64; }
+        }
+    }
+    if (open) err |= kMzErrFormat;
+    if (err) atomicOr(flags, err);
+    out[atomicAdd(n_spec, 1ull)] = d;
+}
+
+// value `i` (w = 4 or 8 bytes, little endian) of a base64 payload; *bad |= 0x80 on a character outside the alphabet
+__device__ __forceinline__ unsigned long long b64_value(const uint8_t *p, uint32_t i, int w, const uint8_t *lut, uint32_t &bad) {
+    const uint32_t o = i * (uint32_t)w, g0 = o / 3u, s = o - 3u * g0;
+    const uint8_t *a = p + 4u * g0;
+    const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(ai & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(ai & 3u) * 8u;
+    uint32_t cw[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) cw[k] = __ldg(wp + k);   // 16 characters at any alignment (the caller guarantees slack)
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t c = __funnelshift_r(cw[k], cw[k + 1], sh);
+        const uint32_t v0 = lut[c & 255u], v1 = lut[(c >> 8) & 255u], v2 = lut[(c >> 16) & 255u], v3 = lut[c >> 24];
+        if (k * 3 < (int)s + w) bad |= v0 | v1 | v2 | v3;   // groups past the value may be anything (the next tag)
+        const uint32_t t = ((v0 & 63u) << 18) | ((v1 & 63u) << 12) | ((v2 & 63u) << 6) | (v3 & 63u);
+        r[k] = __byte_perm(t, 0u, 0x4012u);  // decoded bytes of the group in memory order
+    }
+    const unsigned long long lo = (unsigned long long)r[0] | ((unsigned long long)r[1] << 24) | ((unsigned long long)r[2] << 48);
+    const unsigned long long hi = (unsigned long long)(r[2] >> 16) | ((unsigned long long)r[3] << 8);
+    return s == 0u ? lo : (lo >> (8u * s)) | (hi << (64u - 8u * s));
+}
+
+__device__ __forceinline__ uint32_t b64_bytes(const uint8_t *p, uint32_t len) {
+    if (!len) return 0;
+    uint32_t n = len / 4u * 3u;
+    if (p[len - 1] == '=') --n;
+    if (p[len - 2] == '=') --n;
+    return n;
+}
+
+__global__ void __launch_bounds__(256) mzml_sum_kernel(const SpecDesc *specs, unsigned long long n_spec, int has_pred, double lo, double hi,
+                                                      double *out_sum, unsigned long long *out_cnt, uint32_t *flags) {
+    __shared__ uint8_t lut[256];
+    {
+        const int c = threadIdx.x;
+        uint8_t v = 0x80;
+        if (c >= 'A' && c <= 'Z') v = (uint8_t)(c - 'A');
+        else if (c >= 'a' && c <= 'z') v = (uint8_t)(c - 'a' + 26);
+        else if (c >= '0' && c <= '9') v = (uint8_t)(c - '0' + 52);
+        else if (c == '+') v = 62;
+        else if (c == '/') v = 63;
+        else if (c == '=') v = 0;   // padding only occurs in the last group, whose padded bytes are never part of a value
+        lut[c] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    double acc = 0.0;
+    unsigned long long cnt = 0;
+    uint32_t bad = 0;
+    for (unsigned long long sidx = wid; sidx < n_spec; sidx += nw) {
+        const SpecDesc d = specs[sidx];
+        if (!d.mz || !d.in) continue;
+        const int wm = d.mz_f32 ? 4 : 8, wi = d.in_f32 ? 4 : 8;
+        const uint32_t nm = b64_bytes(d.mz, d.mz_len) / (uint32_t)wm, ni = b64_bytes(d.in, d.in_len) / (uint32_t)wi;
+        const uint32_t n = nm < ni ? nm : ni;   // the two unnested lists are zipped; the longer one's tail meets NULLs
+        for (uint32_t i = lane; i < n; i += 32) {
+            const unsigned long long mb = b64_value(d.mz, i, wm, lut, bad);
+            const double m = d.mz_f32 ? (double)__uint_as_float((uint32_t)mb) : __longlong_as_double((long long)mb);
+            if (has_pred && !(m >= lo && m <= hi)) continue;
+            const unsigned long long ib = b64_value(d.in, i, wi, lut, bad);
+            acc += d.in_f32 ? (double)__uint_as_float((uint32_t)ib) : __longlong_as_double((long long)ib);
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) {
+        acc += __shfl_xor_sync(0xFFFFFFFFu, acc, dlt);
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, dlt);
+        bad |= __shfl_xor_sync(0xFFFFFFFFu, bad, dlt);
+    }
+    if (lane == 0) {
+        if (cnt) {
+            atomicAdd(out_sum, acc);
+            atomicAdd(out_cnt, cnt);
+        }
+        if (bad & 0x80u) atomicOr(flags, kMzErrFormat);
+    }
+}
+
+size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected, int64_t *out_spectra) {
+    if (int rc = s->flush_gz()) return rc;
+    Ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    std::lock_guard<std::mutex> work(ctx->work_mu);
+    if (out_sum) *out_sum = 0.0;
+    if (out_selected) *out_selected = 0;
+    if (out_spectra) *out_spectra = 0;
+    std::vector<Piece> pieces;
+    s->cut_pieces(pieces);
+    if (pieces.empty()) return EXON_GPU_OK;
+    std::vector<ScanSeg> h_segs;
+    int64_t n_tiles = 0, n_bytes = 0;
+    for (const Piece &p : pieces) {
+        ScanSeg sg;
+        sg.skip = (int32_t)((uintptr_t)p.base & 15);
+        sg.base = p.base - sg.skip;
+        sg.len = p.len;
+        sg.tile0 = n_tiles;
+        sg.pad_ = 0;
+        n_tiles += (sg.skip + p.len + MzRing::TILE - 1) / MzRing::TILE;
+        n_bytes += p.len;
+        h_segs.push_back(sg);
+    }
+    if (h_segs.size() >= (1u << 20)) return fail(EXON_GPU_ERR_UNSUPPORTED, "mzml: too many resident ranges");
+    ScanSeg sentinel;
+    memset(&sentinel, 0, sizeof(sentinel));
+    sentinel.tile0 = n_tiles;
+    h_segs.push_back(sentinel);
+
+    static int occ = 0;
+    if (!occ) {
+        CUDA_TRY(cudaFuncSetAttribute(mzml_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MzRing::smem_bytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mzml_events_kernel, MzRing::WARPS * 32, MzRing::smem_bytes));
+        if (occ < 1) occ = 1;
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const size_t cap = (size_t)(attempt == 0 ? n_bytes / 96 + 4096 : n_bytes / 8 + 4096);
+        size_t sort_bytes = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)cap, 0, 64, st));
+        const size_t o_segs = 0, o_ev = o_segs + al256(h_segs.size() * sizeof(ScanSeg)), o_ev2 = o_ev + al256(cap * 8), o_sort = o_ev2 + al256(cap * 8),
+                     o_out = o_sort + al256(sort_bytes);
+        if (int rc = ctx->ensure_scratch(o_out + 256, 256)) return rc;
+        uint8_t *scr = (uint8_t *)ctx->scratch;
+        unsigned long long *d_out = (unsigned long long *)(scr + o_out);  // [0] n_events [1] n_spec [2] sum (f64) [3] selected [4] flags
+        CUDA_TRY(cudaMemcpyAsync(scr + o_segs, h_segs.data(), h_segs.size() * sizeof(ScanSeg), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(d_out, 0, 64, st));
+        MzArgs a;
+        a.segs = (const ScanSeg *)(scr + o_segs);
+        a.n_segs = (int32_t)h_segs.size() - 1;
+        a.n_tiles = n_tiles;
+        a.events = (unsigned long long *)(scr + o_ev);
+        a.cap = cap;
+        a.n_events = d_out;
+        int64_t grid = std::min<int64_t>((int64_t)occ * ctx->sm_count, (n_tiles + MzRing::WARPS - 1) / MzRing::WARPS);
+        if (grid < 1) grid = 1;
+        CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+        mzml_events_kernel<<<(unsigned)grid, MzRing::WARPS * 32, MzRing::smem_bytes, st>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        unsigned long long *h = (unsigned long long *)ctx->h_scratch;
+        CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const unsigned long long n_ev = h[0], n_spec_ev = h[5];
+        ctx->launches.fetch_add(1);
+        if (n_ev > cap) {
+            if (attempt == 0) continue;  // an XML-dense file: go again with room for every possible event
+            return fail(EXON_GPU_ERR_UNSUPPORTED, "mzml: event buffer overflow");
+        }
+        if (n_ev == 0) return EXON_GPU_OK;
+        if (int rc = ctx->ensure_scratch_b((size_t)(n_spec_ev + 1) * sizeof(SpecDesc))) return rc;
+        SpecDesc *d_spec = (SpecDesc *)ctx->scratch_b;
+        size_t sb = sort_bytes;
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(scr + o_sort, sb, (const unsigned long long *)(scr + o_ev), (unsigned long long *)(scr + o_ev2), (int)n_ev, 0, 64, st));
+        mzml_spectra_kernel<<<(unsigned)((n_ev + 255) / 256), 256, 0, st>>>((const unsigned long long *)(scr + o_ev2), n_ev, a.segs,
+                                                                              d_spec, d_out + 1, (uint32_t *)(d_out + 4));
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const unsigned long long n_spec = h[1];
+        if (n_spec) {
+            const int sum_grid = (int)std::min<unsigned long long>((n_spec + 7) / 8, (unsigned long long)ctx->sm_count * 8);
+            mzml_sum_kernel<<<sum_grid, 256, 0, st>>>(d_spec, n_spec, pred != nullptr, pred ? pred->mz_lo : 0.0,
+                                                       pred ? pred->mz_hi : 0.0, (double *)(d_out + 2), d_out + 3, (uint32_t *)(d_out + 4));
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev1, st));
+        ctx->timed = true;
+        ctx->launches.fetch_add(3);
+        CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const uint32_t flags = (uint32_t)h[4];
+        if (flags & kMzErrZlib) return fail(EXON_GPU_ERR_UNSUPPORTED, "mzml: zlib-compressed binary arrays (MS:1000574) are not decoded on the device yet");
+        if (flags & kMzErrFormat) return fail(EXON_GPU_ERR_PARSE, "malformed mzML: a <binary> element without data type / compression / end tag, or invalid base64");
+        if (out_sum) memcpy(out_sum, &h[2], 8);
+        if (out_selected) *out_selected = (int64_t)h[3];
+        if (out_spectra) *out_spectra = (int64_t)n_spec;
+        return EXON_GPU_OK;
+    }
+    return fail(EXON_GPU_ERR_UNSUPPORTED, "mzml: could not size the event buffers");
+}
+
+}  // namespace exon
+
+using namespace exon;
+
+extern "C" {
+
+int exon_gpu_mzml_open(exon_gpu_ctx *c, exon_gpu_stream **out) {
+    if (!c || !out) return fail(EXON_GPU_ERR_ARG, "mzml_open: NULL argument");
+    exon_gpu_vcf_opts vo;
+    memset(&vo, 0, sizeof(vo));
+    if (int rc = exon_gpu_vcf_open(c, &vo, out)) return rc;
+    (*out)->fmt = kFmtMzml;
+    (*out)->hdr = VcfStream::kBody;
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_mzml_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last) {
+    if (!s || s->fmt != kFmtMzml) return fail(EXON_GPU_ERR_ARG, "mzml_feed: not an mzML stream");
+    return exon_gpu_vcf_feed(s, text, len, is_device_ptr, is_last);
+}
+
+int exon_gpu_mzml_filter_sum(exon_gpu_stream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected, int64_t *out_spectra) {
+    if (!s || s->fmt != kFmtMzml) return fail(EXON_GPU_ERR_ARG, "mzml_filter_sum: not an mzML stream");
+    cudaError_t e = cudaSetDevice(s->ctx->device);
+    if (e != cudaSuccess) return fail(EXON_GPU_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return mzml_filter_sum(s, pred, out_sum, out_selected, out_spectra);
+}
+
+}  // extern "C"

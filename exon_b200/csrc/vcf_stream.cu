@@ -57,6 +57,7 @@ void VcfStream::release_all() {
     gz_pending.clear();
     gz_files.clear();
     bam_files.clear();
+    bam_tables_dirty = true;
     bam_groups.clear();
     gz_members.clear();
     gz_staged = 0;

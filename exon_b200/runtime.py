@@ -112,6 +112,9 @@ class Context:
                                              out.size, 0, C.byref(n)))
         return out
 
+    def open_mzml(self) -> "MzmlStream":
+        return MzmlStream(self)
+
     def open_bam(self) -> "BamStream":
         return BamStream(self)
 
@@ -464,3 +467,39 @@ class BamStream:
             check(self.lib.exon_gpu_bam_group_name(self.handle, g, C.byref(nm)))
             out[nm.value.decode() if nm.value is not None else None] = int(counts[g])
         return out, int(rows.value)
+
+
+class MzmlStream(FastqStream):
+    """exon_gpu_stream opened with exon_gpu_mzml_open (feeds / reset / close as for the text formats)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.handle = C.c_void_p()
+        check(self.lib.exon_gpu_mzml_open(ctx.handle, C.byref(self.handle)))
+
+    def feed(self, data, *, is_last: bool = True, device_ptr: int | None = None, nbytes: int | None = None):
+        if device_ptr is not None:
+            check(self.lib.exon_gpu_mzml_feed(self.handle, C.c_void_p(device_ptr), int(nbytes), 1, int(is_last)))
+            return
+        if isinstance(data, PinnedBuffer):
+            data = data.array
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        self._last_host = data
+        check(self.lib.exon_gpu_mzml_feed(self.handle, C.c_void_p(data.ctypes.data), data.size, 0, int(is_last)))
+
+    def filter_sum(self, lo=None, hi=None):
+        """(sum, peaks selected, spectra): SUM(intensity) over zipped peaks with lo <= mz <= hi (None: all)."""
+        s, n, sp = C.c_double(), C.c_int64(), C.c_int64()
+        pred = _abi.MzmlPred(float(lo), float(hi)) if lo is not None else None
+        check(self.lib.exon_gpu_mzml_filter_sum(self.handle, C.byref(pred) if pred is not None else None, C.byref(s), C.byref(n),
+                                                C.byref(sp)))
+        return s.value, n.value, sp.value
+
+    def filter_count(self, *a, **k):
+        raise NotImplementedError
+
+    def rows(self):
+        return self.filter_sum()[2]

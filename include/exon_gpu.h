@@ -241,6 +241,23 @@ int exon_gpu_bam_filter_count_by_reference(exon_gpu_stream *s, const exon_gpu_ba
 /* Name of group g after a query (*name == NULL for the last group, the NULL reference). */
 int exon_gpu_bam_group_name(exon_gpu_stream *s, int32_t group, const char **name);
 
+/* ---- mzML partition stream (BASELINE configs[4]) --------------------------------------- */
+/* MzMLScan::execute + MzMLOpener::open + BatchReader (exon/exon-core/src/datasources/mzml/scanner.rs:139,
+ * mzml/file_opener.rs:48, exon/exon-mzml/src/batch_reader.rs:54-82).  Fed like a VCF stream (plain text through
+ * exon_gpu_mzml_feed, .gz through exon_gpu_stream_feed_gzip); a range must end on a line boundary unless it is the last. */
+int exon_gpu_mzml_open(exon_gpu_ctx *ctx, exon_gpu_stream **out);
+int exon_gpu_mzml_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last);
+typedef struct {
+    double mz_lo, mz_hi; /* mz BETWEEN mz_lo AND mz_hi, both ends inclusive */
+} exon_gpu_mzml_pred;
+/* SELECT SUM(i) FROM (SELECT unnest(mz.mz) m, unnest(intensity.intensity) i FROM mzml) WHERE m BETWEEN lo AND hi over
+ * everything fed so far (pred == NULL: every zipped peak).  *out_sum is an f64 sum accumulated in device order (1e-6
+ * relative parity, north_star); *out_selected the number of peaks summed; *out_spectra the number of <spectrum>
+ * elements (COUNT(*)).  Arrays are decoded as exon/exon-mzml/src/mzml_reader/binary_conversion.rs:26-95 does
+ * (base64, little-endian f32 / f64); zlib-compressed arrays give EXON_GPU_ERR_UNSUPPORTED for now. */
+int exon_gpu_mzml_filter_sum(exon_gpu_stream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected,
+                             int64_t *out_spectra);
+
 /* ---- columnar filter + aggregate over Arrow buffers (a8-a9) ---------------------------------------------- */
 enum { EXON_GPU_AGG_COUNT_STAR = 0, EXON_GPU_AGG_COUNT = 1, EXON_GPU_AGG_SUM = 2, EXON_GPU_AGG_AVG = 3 };
 

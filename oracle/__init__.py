@@ -374,3 +374,36 @@ def bam_count_by_reference_files(files, **kw):
         for k, v in c.items():
             total[k] = total.get(k, 0) + v
     return total, rows
+
+
+# ---- mzML (oracle/mzml_oracle.c) -----------------------------------------------------------------------------
+
+class MzmlResult(C.Structure):
+    _fields_ = [("n_spectra", C.c_int64), ("n_selected", C.c_int64), ("sum", C.c_double), ("kind_sum", C.c_double * 3),
+                ("kind_count", C.c_int64 * 3)]
+
+
+def mzml_scan(data, lo=None, hi=None, spectrum: int = -1) -> MzmlResult:
+    """SUM(intensity) over peaks with lo <= mz <= hi (None: all zipped peaks), spectra count, per-kind totals."""
+    a = _buf(data)
+    L = lib()
+    L.exo_mzml_scan.restype = C.c_int
+    L.exo_mzml_scan.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int64, C.POINTER(MzmlResult)]
+    r = MzmlResult()
+    rc = L.exo_mzml_scan(a.ctypes.data, a.size, int(lo is not None), float(lo or 0.0), float(hi or 0.0), spectrum, C.byref(r))
+    if rc != 0:
+        raise ValueError("malformed mzML")
+    return r
+
+
+def mzml_decode_binary(b64: bytes, zlib_compressed: bool, f32: bool):
+    L = lib()
+    L.exo_mzml_decode_binary.restype = C.c_int64
+    L.exo_mzml_decode_binary.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.POINTER(C.c_double))]
+    out = C.POINTER(C.c_double)()
+    n = L.exo_mzml_decode_binary(b64, len(b64), int(zlib_compressed), int(f32), C.byref(out))
+    if n < 0:
+        raise ValueError("bad binary array")
+    vals = [out[i] for i in range(n)]
+    C.CDLL(None).free(out)
+    return vals
