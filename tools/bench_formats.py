@@ -257,14 +257,87 @@ def bench_bam(args):
     print(json.dumps(line), flush=True)
 
 
+def bench_mzml(args):
+    """BASELINE configs[4]: mzML scan + m/z range filter + SUM(intensity)."""
+    import math
+    from concurrent.futures import ThreadPoolExecutor
+
+    import oracle
+    from synth import mzml
+
+    tstream = torch.cuda.Stream()
+    ctx = Context(0, cuda_stream=tstream.cuda_stream)
+    pins = []
+
+    def alloc(nb):
+        p = ctx.pinned(nb)
+        pins.append(p)
+        return p.array
+
+    t0 = time.perf_counter()
+    sh = mzml.shards(args.spectra, args.shards, peaks=args.peaks, alloc=alloc)
+    gen_s = time.perf_counter() - t0
+    total = int(sum(f.size for f in sh.files))
+    dbufs = []
+    res = ctx.open_mzml()
+    for f in sh.files:
+        d = ctx.device_buffer(f.size + 64)
+        d.upload(f)
+        dbufs.append(d)
+        res.feed(None, device_ptr=d.ptr, nbytes=f.size)
+    ms, kms, (ssum, n_sel, n_sp), launches = timed(ctx, tstream, lambda: res.filter_sum(sh.lo, sh.hi), args.steps, 3)
+    assert n_sp == sh.n and n_sel == sh.truth_count and math.isclose(ssum, sh.truth_sum, rel_tol=1e-6)
+    e2e_s = ctx.open_mzml()
+
+    def e2e():
+        e2e_s.reset()
+        for f in sh.files:
+            e2e_s.feed(f)
+        return e2e_s.filter_sum(sh.lo, sh.hi)
+
+    e_ms, _, (esum, en, _), _ = timed(ctx, tstream, e2e, max(3, args.steps // 4), 2)
+    assert en == n_sel
+    cores = os.cpu_count() or 1
+    n_cpu = min(len(sh.files), cores)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        parts = list(ex.map(lambda f: oracle.mzml_scan(f, sh.lo, sh.hi).n_spectra, sh.files[:n_cpu]))
+    cpu_s = time.perf_counter() - t0
+    peak, src = peak_gbs()
+    col_bytes = 16 * sh.peaks * sh.n
+    line = {"metric": "mzml_mz_range_filter_sum_intensity_spectra_per_sec", "value": sh.n / ms * 1e3, "unit": "spectra/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"mzML m/z BETWEEN {sh.lo} AND {sh.hi} + SUM(intensity), {sh.n} synthetic spectra x {sh.peaks} peaks "
+                                   f"(f64, base64, uncompressed) in {len(sh.files)} files (BASELINE configs[4]); {total} B of text",
+                       "l2": "text >> 126 MB L2, no flush", "tolerance": "sum within 1e-6 relative of the oracle / generator truth; selected-peak count exact"},
+            "e2e": {"value": sh.n / e_ms * 1e3, "unit": "spectra/s", "h2d_bytes_per_step": total, "d2h_bytes_per_step": 192, "ms_per_step": e_ms},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "mzml_events_kernel + sort + mzml_spectra_kernel + mzml_sum_kernel", "achieved": total / kms / 1e6,
+                         "unit": "GB/s", "peak": peak, "peak_source": src, "frac": total / kms / 1e6 / peak, "kernel_ms": kms,
+                         "algorithmic_bytes_per_step": total, "columnar_bytes_per_step": col_bytes, "traffic": None},
+            "cpu_baseline": {"value": sum(parts) / cpu_s, "unit": "spectra/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_cpu} of {len(sh.files)} files ({sum(parts)} spectra): tag scan + base64 + f64 sum, one worker per file"},
+            "sum": ssum, "selected_peaks": n_sel, "sum_matches_truth_1e-6": True, "gen_seconds": gen_s}
+    res.close()
+    e2e_s.close()
+    for d in dbufs:
+        d.free()
+    for p in pins:
+        p.free()
+    ctx.close()
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("fmt", choices=["fastq", "vcfgz", "bam"])
+    ap.add_argument("fmt", choices=["fastq", "vcfgz", "bam", "mzml"])
     ap.add_argument("--rows", type=int, default=100_000_000)
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--alignments", type=int, default=25_000_000)
+    ap.add_argument("--spectra", type=int, default=1_000_000)
+    ap.add_argument("--peaks", type=int, default=200)
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--shards", type=int, default=32)
     ap.add_argument("--steps", type=int, default=20)
     a = ap.parse_args()
-    {"fastq": bench_fastq, "vcfgz": bench_vcfgz, "bam": bench_bam}[a.fmt](a)
+    {"fastq": bench_fastq, "vcfgz": bench_vcfgz, "bam": bench_bam, "mzml": bench_mzml}[a.fmt](a)
