@@ -31,7 +31,7 @@ SYMBOLS = [
     "exon_gpu_fastq_open", "exon_gpu_fastq_feed", "exon_gpu_fastq_filter_count", "exon_gpu_fastq_rows",
     "exon_gpu_stream_close", "exon_gpu_stream_reset", "exon_gpu_stream_body_bytes", "exon_gpu_stream_feed_gzip", "exon_gpu_gzip_inflate", "exon_gpu_bam_open", "exon_gpu_bam_feed",
     "exon_gpu_bam_filter_count_by_reference", "exon_gpu_bam_group_name", "exon_gpu_allreduce_counts",
-    "exon_gpu_mzml_open", "exon_gpu_mzml_feed", "exon_gpu_mzml_filter_sum",
+    "exon_gpu_mzml_open", "exon_gpu_mzml_feed", "exon_gpu_mzml_filter_sum", "exon_gpu_tabix_query", "exon_gpu_stream_feed_bgzf_chunk",
 ]
 
 
@@ -68,6 +68,10 @@ class BamPred(C.Structure):
 
 class MzmlPred(C.Structure):
     _fields_ = [("mz_lo", C.c_double), ("mz_hi", C.c_double)]
+
+
+class Chunk(C.Structure):
+    _fields_ = [("start", C.c_uint64), ("end", C.c_uint64)]
 
 
 class ArrowSchema(C.Structure):
@@ -162,6 +166,8 @@ def load():
         "exon_gpu_mzml_open": [vp, C.POINTER(vp)],
         "exon_gpu_mzml_feed": [vp, vp, C.c_size_t, C.c_int, C.c_int],
         "exon_gpu_mzml_filter_sum": [vp, C.POINTER(MzmlPred), C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)],
+        "exon_gpu_tabix_query": [vp, vp, C.c_size_t, C.POINTER(Region), C.POINTER(Chunk), i32, C.POINTER(i32)],
+        "exon_gpu_stream_feed_bgzf_chunk": [vp, vp, C.c_size_t, C.c_uint64, C.POINTER(Chunk)],
         "exon_gpu_stream_close": [vp],
         "exon_gpu_stream_reset": [vp],
         "exon_gpu_stream_body_bytes": [vp, C.POINTER(i64)],

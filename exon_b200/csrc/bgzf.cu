@@ -443,44 +443,53 @@ constexpr size_t kInfSmem = sizeof(MemberSmem) * kInfWarps * kGroups;
 
 }  // namespace
 
-// Walks the gzip members of `data` (a whole file).  BGZF members carry their size in the 'BC' extra subfield; a
-// member without it (plain gzip) is taken to extend to the end of the file (single member).
+// Parses the gzip member that starts at data[p]: payload range, ISIZE, and where the next member starts.  BGZF members
+// carry their size in the 'BC' extra subfield; a member without it (plain gzip) is taken to extend to the end of the data.
+static int bgzf_parse_member(const uint8_t *data, size_t len, size_t p, BgzfMember *m, size_t *next) {
+    if (len - p < 18 || data[p] != 0x1f || data[p + 1] != 0x8b || data[p + 2] != 8)
+        return fail(EXON_GPU_ERR_PARSE, "bgzf: bad gzip magic at byte %zu", p);
+    const uint8_t flg = data[p + 3];
+    size_t q = p + 10;
+    long bsize = -1;
+    if (flg & 4) {
+        const size_t xlen = (size_t)data[q] | ((size_t)data[q + 1] << 8);
+        q += 2;
+        if (q + xlen > len) return fail(EXON_GPU_ERR_PARSE, "bgzf: truncated extra field at byte %zu", p);
+        size_t x = q;
+        while (x + 4 <= q + xlen) {
+            const size_t slen = (size_t)data[x + 2] | ((size_t)data[x + 3] << 8);
+            if (data[x] == 'B' && data[x + 1] == 'C' && slen == 2 && x + 6 <= q + xlen) bsize = (long)data[x + 4] | ((long)data[x + 5] << 8);
+            x += 4 + slen;
+        }
+        q += xlen;
+    }
+    if (flg & 8) { while (q < len && data[q]) ++q; ++q; }   // FNAME
+    if (flg & 16) { while (q < len && data[q]) ++q; ++q; }  // FCOMMENT
+    if (flg & 2) q += 2;                                    // FHCRC
+    const size_t end = bsize >= 0 ? p + (size_t)bsize + 1 : len;
+    if (end > len || q + 8 > end) return fail(EXON_GPU_ERR_PARSE, "bgzf: truncated member at byte %zu", p);
+    m->in_off = q;
+    m->in_len = (uint32_t)(end - 8 - q);
+    m->isize = (uint32_t)data[end - 4] | ((uint32_t)data[end - 3] << 8) | ((uint32_t)data[end - 2] << 16) | ((uint32_t)data[end - 1] << 24);
+    m->out_addr = 0;
+    if (bsize >= 0 && m->isize > 65536u) return fail(EXON_GPU_ERR_PARSE, "bgzf: member at byte %zu claims %u bytes (> 64 KiB)", p, m->isize);
+    *next = end;
+    return EXON_GPU_OK;
+}
+
+// Walks the gzip members of `data` (a whole file); out_addr = offset of each member in the uncompressed stream.
 int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uint64_t *total_out) {
     out.clear();
     size_t p = 0;
     uint64_t uo = 0;
     while (p < len) {
-        if (len - p < 18 || data[p] != 0x1f || data[p + 1] != 0x8b || data[p + 2] != 8)
-            return fail(EXON_GPU_ERR_PARSE, "bgzf: bad gzip magic at byte %zu", p);
-        const uint8_t flg = data[p + 3];
-        size_t q = p + 10;
-        long bsize = -1;
-        if (flg & 4) {
-            const size_t xlen = (size_t)data[q] | ((size_t)data[q + 1] << 8);
-            q += 2;
-            if (q + xlen > len) return fail(EXON_GPU_ERR_PARSE, "bgzf: truncated extra field at byte %zu", p);
-            size_t x = q;
-            while (x + 4 <= q + xlen) {
-                const size_t slen = (size_t)data[x + 2] | ((size_t)data[x + 3] << 8);
-                if (data[x] == 'B' && data[x + 1] == 'C' && slen == 2 && x + 6 <= q + xlen) bsize = (long)data[x + 4] | ((long)data[x + 5] << 8);
-                x += 4 + slen;
-            }
-            q += xlen;
-        }
-        if (flg & 8) { while (q < len && data[q]) ++q; ++q; }   // FNAME
-        if (flg & 16) { while (q < len && data[q]) ++q; ++q; }  // FCOMMENT
-        if (flg & 2) q += 2;                                    // FHCRC
-        const size_t end = bsize >= 0 ? p + (size_t)bsize + 1 : len;
-        if (end > len || q + 8 > end) return fail(EXON_GPU_ERR_PARSE, "bgzf: truncated member at byte %zu", p);
         BgzfMember m;
-        m.in_off = q;
-        m.in_len = (uint32_t)(end - 8 - q);
-        m.isize = (uint32_t)data[end - 4] | ((uint32_t)data[end - 3] << 8) | ((uint32_t)data[end - 2] << 16) | ((uint32_t)data[end - 1] << 24);
-        m.out_addr = uo;  // offset in the uncompressed stream; the caller rebases it to a device address
-        if (bsize >= 0 && m.isize > 65536u) return fail(EXON_GPU_ERR_PARSE, "bgzf: member at byte %zu claims %u bytes (> 64 KiB)", p, m.isize);
+        size_t next = 0;
+        if (int rc = bgzf_parse_member(data, len, p, &m, &next)) return rc;
+        m.out_addr = uo;  // the caller rebases it to a device address
         uo += m.isize;
         out.push_back(m);
-        p = end;
+        p = next;
     }
     *total_out = uo;
     return EXON_GPU_OK;
@@ -570,6 +579,92 @@ int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
     return EXON_GPU_OK;
 }
 
+// Indexed scan (IndexedVCFOpener::open, exon/exon-core/src/datasources/vcf/file_opener/indexed_file_opener.rs:53-214): only
+// the members a tabix chunk covers are inflated.  `data` holds file bytes [file_off, file_off + len) and starts at a
+// member boundary at or before the chunk's first member; it must reach through the member at the chunk's end.
+int VcfStream::feed_gzip_chunk(const uint8_t *data, size_t len, uint64_t file_off, uint64_t vstart, uint64_t vend) {
+    if (cur_run_open && tail_len > 0) return fail(EXON_GPU_ERR_STATE, "feed_bgzf_chunk: the previous plain-text range ended mid-line");
+    const uint64_t c0 = vstart >> 16, c1 = vend >> 16;
+    const uint32_t u0 = (uint32_t)(vstart & 0xFFFFu), u1 = (uint32_t)(vend & 0xFFFFu);
+    if (vend < vstart || c0 < file_off) return fail(EXON_GPU_ERR_ARG, "feed_bgzf_chunk: the chunk does not lie inside the given byte range");
+    std::vector<BgzfMember> members;
+    uint64_t total = 0, end_pos = 0;
+    bool saw_end = false;
+    size_t p = 0;
+    while (p < len) {
+        BgzfMember m;
+        size_t next = 0;
+        if (int rc = bgzf_parse_member(data, len, p, &m, &next)) return rc;
+        const uint64_t at = file_off + p;
+        if (at >= c0 && at <= c1) {
+            if (at == c1) {
+                saw_end = true;
+                end_pos = total + u1;  // the chunk ends u1 bytes into this member
+                if (u1 == 0) break;     // nothing of it is needed
+                if (u1 > m.isize) return fail(EXON_GPU_ERR_ARG, "feed_bgzf_chunk: chunk end beyond its member");
+            }
+            m.out_addr = total;
+            total += m.isize;
+            members.push_back(m);
+            if (at == c1) break;
+        } else if (at > c1) {
+            break;
+        }
+        p = next;
+    }
+    if (!saw_end) {
+        if (c0 == c1 || p >= len) end_pos = total;  // the reference reads to the end of the data in this case (indexed_file_opener.rs:113-117)
+        else return fail(EXON_GPU_ERR_ARG, "feed_bgzf_chunk: no member starts at the chunk's end offset");
+    }
+    if (members.empty() || end_pos <= u0) {
+        if (!runs.empty()) file_marks.push_back(FileMark{runs.size() - 1, runs.back().len});
+        return EXON_GPU_OK;
+    }
+    if (u0 >= members[0].isize && members[0].isize) return fail(EXON_GPU_ERR_ARG, "feed_bgzf_chunk: chunk start beyond its member");
+    cudaStream_t st = ctx->stream;
+    // stage the compressed bytes of the selected members (one contiguous range of `data`)
+    const size_t lo = (size_t)(members.front().in_off >= 18 ? members.front().in_off - 18 : 0), hi = (size_t)(members.back().in_off + members.back().in_len + 8);
+    const size_t need = ((hi - lo + 16 + 255) & ~(size_t)255);
+    if (gz_staged + need > d_gz_cap) {
+        if (int rc = flush_gz()) return rc;
+        if (need > d_gz_cap) {
+            if (d_gz) {
+                CUDA_TRY(cudaStreamSynchronize(st));
+                CUDA_TRY(cudaFree(d_gz));
+                d_gz = nullptr;
+                d_gz_cap = 0;
+            }
+            const size_t cap = std::max(need * 2, (size_t)256 << 20);
+            CUDA_TRY(cudaMalloc(&d_gz, cap));
+            d_gz_cap = cap;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_gz + gz_staged, data + lo, hi - lo, cudaMemcpyHostToDevice, st));
+    if (blocks.empty() || blocks.back().used + total + 1 > blocks.back().cap) {
+        DevBlock nb;
+        if (int rc = ctx->get_block((size_t)total + 1, &nb)) return rc;
+        blocks.push_back(nb);
+    }
+    DevBlock &b = blocks.back();
+    uint8_t *dst = b.ptr + b.used;
+    b.used = std::min(b.cap, b.used + (((size_t)total + 1 + 15) & ~(size_t)15));
+    cur_run_open = false;
+    tail_len = 0;
+    const size_t first = gz_members.size();
+    for (BgzfMember m : members) {
+        m.in_off = m.in_off - lo + gz_staged;
+        m.out_addr = (uint64_t)reinterpret_cast<uintptr_t>(dst) + m.out_addr;
+        gz_members.push_back(m);
+    }
+    gz_staged += need;
+    GzFile f{dst, total, first, members.size()};
+    f.range_lo = (int64_t)u0;
+    f.range_hi = (int64_t)end_pos;
+    gz_files.push_back(f);
+    if (gz_members.size() >= 16384) return flush_gz();
+    return EXON_GPU_OK;
+}
+
 // Inflates every pending member in one launch, then frames the files in feed order exactly like device-resident
 // ranges (header skipped on a host copy of each file's first bytes, last record normalised to end in '\n').
 int VcfStream::flush_gz() {
@@ -607,7 +702,8 @@ int VcfStream::flush_gz() {
             if (!files[i].total) continue;
             uint8_t *slot = h + 64 + i * (kProbe + 16);
             CUDA_TRY(cudaMemcpyAsync(slot, files[i].dst, (size_t)std::min<uint64_t>(files[i].total, kProbe), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(slot + kProbe, files[i].dst + files[i].total - 1, 1, cudaMemcpyDeviceToHost, st));
+            const uint64_t last_at = files[i].range_lo >= 0 ? (uint64_t)files[i].range_hi - 1 : files[i].total - 1;
+            CUDA_TRY(cudaMemcpyAsync(slot + kProbe, files[i].dst + last_at, 1, cudaMemcpyDeviceToHost, st));
         }
         CUDA_TRY(cudaStreamSynchronize(st));
         const uint32_t *fl = reinterpret_cast<const uint32_t *>(h);
@@ -639,6 +735,13 @@ int VcfStream::flush_gz() {
         const GzFile &f = files[i];
         if (!f.total) {  // an empty file (no members, or only empty members such as the BGZF EOF marker)
             if (!runs.empty()) file_marks.push_back(FileMark{runs.size() - 1, runs.back().len});
+            continue;
+        }
+        if (f.range_lo >= 0) {
+            // a tabix chunk: whole records from range_lo to range_hi of the inflated members, no header inside
+            if (probes[i].last != '\n') return fail(EXON_GPU_ERR_PARSE, "feed_bgzf_chunk: the chunk does not end at a record boundary");
+            hdr = kBody;
+            if (int rc = frame_device_range(f.dst + f.range_lo, (size_t)(f.range_hi - f.range_lo), true, 0, '\n')) return rc;
             continue;
         }
         uint64_t n = f.total;

@@ -134,7 +134,12 @@ struct VcfStream {
     std::vector<uint8_t> gz_pending;
     // whole files whose compressed bytes are on their way to HBM but whose inflate has not been launched yet: members of
     // several files go into ONE launch so that thousands of members are in flight (bgzf.cu)
-    struct GzFile { uint8_t *dst; uint64_t total; size_t first_member, n_members; };
+    struct GzFile {
+        uint8_t *dst;
+        uint64_t total;
+        size_t first_member, n_members;
+        int64_t range_lo = -1, range_hi = -1;  // >= 0: only bytes [range_lo, range_hi) of the inflated members are records (tabix chunk)
+    };
     std::vector<GzFile> gz_files;
     std::vector<BgzfMember> gz_members;
     size_t gz_staged = 0;      // bytes of d_gz in use
@@ -161,6 +166,7 @@ struct VcfStream {
     int bam_frame_file(uint8_t *dst, uint64_t total, const uint8_t *probe, size_t probe_len, const BgzfMember *members, size_t n_members);
     int bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, int32_t cap, int32_t *n_groups, int64_t *total_rows);
     int flush_gz();
+    int feed_gzip_chunk(const uint8_t *data, size_t len, uint64_t file_off, uint64_t vstart, uint64_t vend);
     int frame_device_range(const uint8_t *text, size_t len, bool is_last, int64_t known_body_off, int known_last_byte);
     int64_t probe_body_offset(const uint8_t *p, size_t n, bool whole_file) const;
     int feed_host(const uint8_t *text, size_t len, bool is_last);

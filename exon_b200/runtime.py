@@ -112,6 +112,16 @@ class Context:
                                              out.size, 0, C.byref(n)))
         return out
 
+    def tabix_query(self, tbi, region: "_abi.Region"):
+        """exon_gpu_tabix_query: [(start vpos, end vpos)] of the chunks of a .tbi that can hold records of `region`."""
+        if isinstance(tbi, (bytes, bytearray, memoryview)):
+            tbi = np.frombuffer(tbi, dtype=np.uint8)
+        n = C.c_int32()
+        check(self.lib.exon_gpu_tabix_query(self.handle, C.c_void_p(tbi.ctypes.data), tbi.size, C.byref(region), None, 0, C.byref(n)))
+        out = (_abi.Chunk * max(n.value, 1))()
+        check(self.lib.exon_gpu_tabix_query(self.handle, C.c_void_p(tbi.ctypes.data), tbi.size, C.byref(region), out, n.value, C.byref(n)))
+        return [(int(out[i].start), int(out[i].end)) for i in range(n.value)]
+
     def open_mzml(self) -> "MzmlStream":
         return MzmlStream(self)
 
@@ -294,6 +304,14 @@ class VcfStream:
         assert data.dtype == np.uint8 and data.flags.c_contiguous
         self._last_host = data
         check(self.lib.exon_gpu_stream_feed_gzip(self.handle, C.c_void_p(data.ctypes.data), data.size, int(is_last)))
+
+    def feed_bgzf_chunk(self, data, chunk, file_offset: int = 0):
+        """exon_gpu_stream_feed_bgzf_chunk: bytes [file_offset, ...) of a .vcf.gz and one (start, end) virtual-position chunk."""
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        self._last_host = data
+        ch = _abi.Chunk(int(chunk[0]), int(chunk[1]))
+        check(self.lib.exon_gpu_stream_feed_bgzf_chunk(self.handle, C.c_void_p(data.ctypes.data), data.size, int(file_offset), C.byref(ch)))
 
     def filter_count(self, region: "_abi.Region | None" = None) -> int:
         out = C.c_int64()

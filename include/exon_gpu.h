@@ -211,6 +211,23 @@ int exon_gpu_stream_feed_gzip(exon_gpu_stream *s, const uint8_t *data, size_t le
  * *out_len receives the uncompressed size even when `out` is too small (EXON_GPU_ERR_ARG then). */
 int exon_gpu_gzip_inflate(exon_gpu_ctx *ctx, const uint8_t *data, size_t len, uint8_t *out, size_t out_cap, int out_is_device,
                           size_t *out_len);
+/* ---- indexed scan (a12): tabix chunks -> only the covered BGZF members are inflated --------------------------- */
+typedef struct {
+    uint64_t start, end; /* BGZF virtual positions: compressed offset << 16 | offset inside the inflated member */
+} exon_gpu_chunk;
+/* noodles::tabix::Reader::read_index + Index::query as called by get_byte_range_for_file
+ * (exon/exon-core/src/datasources/indexed_file/indexed_bgzf_file.rs:52-83): chunks of `tbi` (the bytes of the .tbi file)
+ * that can hold records of `region` (name required; 1-based inclusive interval optional), merged and sorted.
+ * A contig that is not in the index gives 0 chunks.  `out` may be NULL to ask for the count. */
+int exon_gpu_tabix_query(exon_gpu_ctx *ctx, const uint8_t *tbi, size_t len, const exon_gpu_region *region, exon_gpu_chunk *out,
+                         int32_t cap, int32_t *n_chunks);
+/* IndexedVCFOpener::open (exon/exon-core/src/datasources/vcf/file_opener/indexed_file_opener.rs:53-214): `data` holds the
+ * bytes [file_offset, file_offset + len) of a .vcf.gz -- what a ranged object-store GET returns -- starting at a member
+ * boundary at or before the chunk's first member and reaching through the member in which the chunk ends.  Only the
+ * chunk's members are inflated (on the device); the records between the two virtual positions become one file of the
+ * partition.  The region predicate itself is applied by exon_gpu_vcf_filter_count / the batches' consumer, to every
+ * record (the reference's IndexedAsyncBatchStream stops filtering after a full batch, SURVEY 2.2 #6: not reproduced). */
+int exon_gpu_stream_feed_bgzf_chunk(exon_gpu_stream *s, const uint8_t *data, size_t len, uint64_t file_offset, const exon_gpu_chunk *chunk);
 /* Format-independent stream calls (the exon_gpu_vcf_* spellings remain valid for VCF streams). */
 int exon_gpu_stream_close(exon_gpu_stream *s);
 int exon_gpu_stream_reset(exon_gpu_stream *s);
