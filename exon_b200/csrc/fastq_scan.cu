@@ -40,7 +40,7 @@ namespace exon {
 namespace {
 
 constexpr int kFqQueue = 256;
-using FqRing = TileRing<4096, 3, 8, 16, 368, kFqQueue * 2>;
+using FqRing = TileRing<4096, 2, 8, 16, 368, kFqQueue * 2>;
 constexpr int kFqU = FqRing::TILE / 512;
 
 constexpr uint32_t kFqErrPrefix = 1u;     // a definition line without '@' or a third line without '+'
@@ -60,7 +60,7 @@ struct FqArgs {
 };
 
 // ---- pass A -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FqRing::WARPS * 32, 2) fq_lines_kernel(const __grid_constant__ FqArgs a) {
+__global__ void __launch_bounds__(FqRing::WARPS * 32, 3) fq_lines_kernel(const __grid_constant__ FqArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FqRing ring;
     ring.init(smem_raw, a.segs, a.n_tiles);
@@ -176,7 +176,7 @@ __device__ __forceinline__ void fq_line_sum(const FqRing::View &v, int ls, uint3
     }
 }
 
-__global__ void __launch_bounds__(FqRing::WARPS * 32, 2) fq_filter_kernel(const __grid_constant__ FqArgs a) {
+__global__ void __launch_bounds__(FqRing::WARPS * 32, 3) fq_filter_kernel(const __grid_constant__ FqArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FqRing ring;
     ring.init(smem_raw, a.segs, a.n_tiles);

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_co
     }
 }
 
-constexpr int kColU = 8, kColS = 3, kColW = 8;  // 4 KiB tiles, the geometry K1 settled on
+constexpr int kColU = 8, kColS = 2, kColW = 8;  // 4 KiB tiles, the geometry K1 settled on
 
 template <bool EMIT>
 cudaError_t launch_cols(const ColArgs &args, int sm_count, cudaStream_t stream) {
