@@ -37,7 +37,8 @@ namespace exon {
 
 namespace {
 
-using MzRing = TileRing<4096, 3, 8, 16, 368, 16>;
+constexpr int kMzBuf = 30;  // events a warp collects in shared memory before it reserves space in the global list
+using MzRing = TileRing<4096, 2, 8, 16, 368, 16 + 8 * kMzBuf>;  // 2 stages + a small buffer: 3 CTAs per SM
 constexpr int kMzU = MzRing::TILE / 512;
 
 enum : uint32_t {
@@ -65,12 +66,31 @@ __device__ __forceinline__ bool match_at(const V &v, int p, const char *lit, int
     return true;
 }
 
-__global__ void __launch_bounds__(MzRing::WARPS * 32, 2) mzml_events_kernel(const __grid_constant__ MzArgs a) {
+__global__ void __launch_bounds__(MzRing::WARPS * 32, 3) mzml_events_kernel(const __grid_constant__ MzArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     MzRing ring;
     ring.init(smem_raw, a.segs, a.n_tiles);
     const int lane = ring.lane;
     constexpr uint32_t kLT4 = 0x3C3C3C3Cu, kCOL4 = 0x3A3A3A3Au;
+    // per-warp event buffer: [0] count (shared-memory atomic), [2..] keys; one global reservation per flush instead of one
+    // global atomic per event (the list head is a single address)
+    unsigned int *buf_n = reinterpret_cast<unsigned int *>(ring.extra);
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(ring.extra + 16);
+    if (lane == 0) *buf_n = 0;
+    __syncwarp();
+    auto flush = [&]() {
+        __syncwarp();
+        const unsigned int n = *buf_n < (unsigned)kMzBuf ? *buf_n : (unsigned)kMzBuf;
+        unsigned long long base = 0;
+        if (lane == 0 && n) base = atomicAdd(a.n_events, (unsigned long long)n);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (unsigned int i = lane; i < n; i += 32)
+            if (base + i < a.cap) a.events[base + i] = buf[i];
+        __syncwarp();
+        if (lane == 0) *buf_n = 0;
+        __syncwarp();
+    };
+    uint32_t n_spectrum = 0;
 #pragma unroll 1
     for (int64_t T = ring.first_tile(); T < a.n_tiles; T += ring.nw) {
         const MzRing::View v = ring.acquire();
@@ -80,13 +100,15 @@ __global__ void __launch_bounds__(MzRing::WARPS * 32, 2) mzml_events_kernel(cons
 #pragma unroll 1
         for (int u = 0; u < kMzU; ++u) {
             const int c0 = (u * 32 + lane) * 16;
-            if (!(v.interior || c0 < v.sm_hi)) continue;
-            const uint4 w = lds128(v.sa + (uint32_t)c0);
+            uint32_t m = 0;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (v.interior || c0 < v.sm_hi) {
+            w = lds128(v.sa + (uint32_t)c0);
             uint32_t hit = zero_bytes_fast(w.x ^ kLT4) | zero_bytes_fast(w.y ^ kLT4) | zero_bytes_fast(w.z ^ kLT4) | zero_bytes_fast(w.w ^ kLT4) |
                            zero_bytes_fast(w.x ^ kCOL4) | zero_bytes_fast(w.y ^ kCOL4) | zero_bytes_fast(w.z ^ kCOL4) | zero_bytes_fast(w.w ^ kCOL4);
-            if (!hit) continue;
-            uint32_t m = pack_flags16(zero_bytes_exact(w.x ^ kLT4) | zero_bytes_exact(w.x ^ kCOL4), zero_bytes_exact(w.y ^ kLT4) | zero_bytes_exact(w.y ^ kCOL4),
+            if (hit) m = pack_flags16(zero_bytes_exact(w.x ^ kLT4) | zero_bytes_exact(w.x ^ kCOL4), zero_bytes_exact(w.y ^ kLT4) | zero_bytes_exact(w.y ^ kCOL4),
                                       zero_bytes_exact(w.z ^ kLT4) | zero_bytes_exact(w.z ^ kCOL4), zero_bytes_exact(w.w ^ kLT4) | zero_bytes_exact(w.w ^ kCOL4));
+            }
             while (m) {
                 const int p = c0 + __ffs(m) - 1;
                 m &= m - 1;
@@ -121,14 +143,26 @@ __global__ void __launch_bounds__(MzRing::WARPS * 32, 2) mzml_events_kernel(cons
                     }
                 }
                 if (kind) {
-                    if (kind == kEvSpectrum) atomicAdd(a.n_events + 5, 1ull);
-                    const unsigned long long i = atomicAdd(a.n_events, 1ull);
-                    if (i < a.cap) a.events[i] = seg_key | ((unsigned long long)at << 4) | kind;
+                    if (kind == kEvSpectrum) ++n_spectrum;
+                    const unsigned long long key = seg_key | ((unsigned long long)at << 4) | kind;
+                    const unsigned int slot = atomicAdd(buf_n, 1u);
+                    if (slot < (unsigned)kMzBuf) {
+                        buf[slot] = key;
+                    } else {  // buffer full (an XML-dense stretch): straight to the global list
+                        const unsigned long long i = atomicAdd(a.n_events, 1ull);
+                        if (i < a.cap) a.events[i] = key;
+                    }
                 }
             }
+            __syncwarp();
+            // events beyond the buffer go straight to the global list; flush once the buffer is half full
+            if (*buf_n > (unsigned)(kMzBuf / 2)) flush();
         }
+        flush();
         ring.release(T);
     }
+    n_spectrum = warp_sum(n_spectrum);
+    if (lane == 0 && n_spectrum) atomicAdd(a.n_events + 5, (unsigned long long)n_spectrum);
 }
 
 struct SpecDesc {

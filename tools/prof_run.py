@@ -18,6 +18,8 @@ from synth import vcf  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rows", type=int, default=100_000_000)
+ap.add_argument("--mzml-spectra", type=int, default=0, help="profile the mzML path")
+ap.add_argument("--bam-alignments", type=int, default=0, help="profile the BAM path")
 ap.add_argument("--gz-rows", type=int, default=0, help="profile the BGZF inflate on this many VCF rows")
 ap.add_argument("--fastq-reads", type=int, default=0, help="profile the FASTQ fused scan instead of VCF")
 ap.add_argument("--shards", type=int, default=64)
@@ -25,6 +27,34 @@ ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--modes", default="lazy,lazy,strict,count_star,interval")
 args = ap.parse_args()
 
+if args.mzml_spectra:
+    from synth import mzml
+
+    sh = mzml.shards(args.mzml_spectra, 16)
+    with Context(0) as ctx:
+        s = ctx.open_mzml()
+        keep = []
+        for f in sh.files:
+            d = ctx.device_buffer(f.size + 64)
+            d.upload(np.ascontiguousarray(f))
+            keep.append(d)
+            s.feed(None, device_ptr=d.ptr, nbytes=f.size)
+        for _ in range(3):
+            print("mzml", s.filter_sum(sh.lo, sh.hi), sh.truth_count, f"{ctx.last_kernel_ms():.3f} ms", flush=True)
+        s.close()
+    raise SystemExit(0)
+if args.bam_alignments:
+    from synth import bam
+
+    sh = bam.shards(args.bam_alignments, 16)
+    with Context(0) as ctx:
+        s = ctx.open_bam()
+        for f in sh.files:
+            s.feed(f)
+        for _ in range(3):
+            print("bam", s.count_by_reference(flag_exclude=0x904, min_mapq=30)[1], f"{ctx.last_kernel_ms():.3f} ms", flush=True)
+        s.close()
+    raise SystemExit(0)
 if args.gz_rows:
     import ctypes as C
     from concurrent.futures import ThreadPoolExecutor
