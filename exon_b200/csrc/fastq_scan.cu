@@ -21,7 +21,10 @@
 // global memory (byte loop), so read length is not limited.
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <new>
 
 #include "common.cuh"
 #include "internal.h"
@@ -415,6 +418,561 @@ int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *o
     return EXON_GPU_OK;
 }
 
+// =====================================================================================================================
+// FASTQ text -> Arrow columns {name, description, sequence, quality_scores} in reference-sized batches.
+//
+// Replaces BatchReader::read_batch (exon/exon-fastq/src/batch_reader.rs:63-82), FASTQArrayBuilder::{append, finish}
+// (exon/exon-fastq/src/array_builder.rs:68-118: four GenericStringBuilder<i32>, description NULL when empty) and
+// ExonArrayBuilder::try_into_record_batch (exon/exon-common/src/array_builder.rs:25-36).
+//   1. lines  + scan          (as in the fused query) -> first line index of every tile / file
+//   2. index                  every '\n' knows its rank: line_start[i], line_end[i] for all lines (TMA tile pipeline)
+//   3. fields                 one thread per record: the four (offset, length) pairs, '@' / '+' validation
+//   4. 4 exclusive scans      value offsets per column (cub)
+//   5. gather                 one warp per record copies its four byte ranges to their final place and writes the
+//                             batch-relative int32 offsets and the description validity bit
+// Batches restart at every file and are zero-copy views of the column store (reference counted, Arrow release).
+// =====================================================================================================================
+namespace {
+
+struct FqIndexArgs {
+    const ScanSeg *segs;
+    int64_t n_tiles;
+    const unsigned long long *tile_prefix;
+    const uint8_t **line_start;
+    const uint8_t **line_end;
+};
+
+__global__ void __launch_bounds__(FqRing::WARPS * 32, 3) fq_index_kernel(const __grid_constant__ FqIndexArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    FqRing ring;
+    ring.init(smem_raw, a.segs, a.n_tiles);
+    const int lane = ring.lane;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int64_t T = ring.first_tile(); T < a.n_tiles; T += ring.nw) {
+        const FqRing::View v = ring.acquire();
+        // index of the line ended by the first '\n' of this tile
+        unsigned long long next_end = __ldg(&a.tile_prefix[T]) - 1ull;
+        if (v.first && v.hi > v.seg_lo) {
+            if (lane == 0) a.line_start[next_end + 1ull] = v.g + v.seg_lo;
+            next_end += 1ull;
+        }
+#pragma unroll 1
+        for (int u = 0; u < kFqU; ++u) {
+            const int c0 = (u * 32 + lane) * 16;
+            uint32_t m = 0;
+            if (v.interior || c0 < v.sm_hi) m = newline_mask16(lds128(v.sa + (uint32_t)c0));
+            if (!v.interior) {  // every '\n' inside the segment, the last byte included
+                const int j_lo = v.seg_lo - c0 > 0 ? v.seg_lo - c0 : 0;
+                const int j_hi = v.hi - c0 < 16 ? v.hi - c0 : 16;
+                m = (j_hi > j_lo) ? (m & ((1u << j_hi) - 1u) & ~((1u << j_lo) - 1u)) : 0u;
+            }
+            const uint32_t n = (uint32_t)__popc(m);
+            const uint32_t b1 = __ballot_sync(0xFFFFFFFFu, n >= 1u);
+            if (b1 == 0u) continue;
+            const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, n >= 2u);
+            uint32_t before, total;
+            if (__ballot_sync(0xFFFFFFFFu, n >= 3u) == 0u) {
+                before = (uint32_t)(__popc(b1 & lt_mask) + __popc(b2 & lt_mask));
+                total = (uint32_t)(__popc(b1) + __popc(b2));
+            } else {
+                uint32_t incl = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += x;
+                }
+                before = incl - n;
+                total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+            unsigned long long e = next_end + before;
+            uint32_t mm = m;
+            while (mm) {
+                const int p = c0 + __ffs(mm) - 1;
+                mm &= mm - 1;
+                a.line_end[e] = v.g + p;
+                if (p + 1 < v.hi) a.line_start[e + 1ull] = v.g + p + 1;
+                ++e;
+            }
+            next_end += total;
+        }
+        // a segment whose last byte is not '\n': its last line ends where the segment ends
+        if (v.hi <= FqRing::TILE && v.hi > v.seg_lo && lane == 0 && view_byte(v, v.hi - 1) != '\n') a.line_end[next_end] = v.g + v.hi;
+        ring.release(T);
+    }
+}
+
+struct FqFileTab {
+    long long rec0;    // first record of the file (global numbering)
+    long long line0;   // first line of the file (global numbering)
+    long long lines;   // lines in the file
+    long long batch0;  // first batch of the file
+};
+
+struct FqColArgs {
+    const FqFileTab *files;  // n_files + 1 entries (the last one carries rec0 = n_records)
+    int32_t n_files;
+    int64_t n_records;
+    int32_t batch_rows;
+    const uint8_t *const *line_start;
+    const uint8_t *const *line_end;
+    int32_t *lens[4];          // pass 3 out (n_records + 1 each, the last entry 0); NULL for unprojected columns
+    const long long *voff[4];  // pass 5 in
+    uint8_t *values[4];
+    int32_t *offsets[4];       // n_batches * (batch_rows + 1)
+    uint32_t *desc_valid;      // n_batches * words_per_batch, zeroed
+    int32_t words_per_batch;
+    uint32_t *flags;
+};
+
+__device__ __forceinline__ int fq_find_file(const FqFileTab *files, int n_files, long long r) {
+    int lo = 0, hi = n_files - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (files[mid].rec0 <= r) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+// the four fields of record r: pointers and lengths (name, description, sequence, quality)
+__device__ __forceinline__ uint32_t fq_record_fields(const FqColArgs &a, long long r, int f, const uint8_t *ptr[4], int32_t len[4]) {
+    const long long local = r - a.files[f].rec0;
+    const long long l0 = a.files[f].line0 + 4 * local;
+    const int avail = (int)((a.files[f].lines - 4 * local) < 4 ? (a.files[f].lines - 4 * local) : 4);
+    uint32_t err = 0;
+    const uint8_t *s = a.line_start[l0], *e = a.line_end[l0];
+    if (e - s < 1 || *s != '@') err |= kFqErrPrefix;
+    const uint8_t *sp = s + 1;
+    while (sp < e && *sp != ' ') ++sp;
+    ptr[0] = s + 1;
+    len[0] = (int32_t)((sp < e ? sp : e) - (s + 1));
+    if (len[0] < 0) len[0] = 0;
+    ptr[1] = sp < e ? sp + 1 : e;
+    len[1] = sp < e ? (int32_t)(e - (sp + 1)) : 0;
+    ptr[2] = ptr[3] = e;
+    len[2] = len[3] = 0;
+    if (avail >= 2) {
+        ptr[2] = a.line_start[l0 + 1];
+        len[2] = (int32_t)(a.line_end[l0 + 1] - ptr[2]);
+    }
+    if (avail >= 3) {
+        const uint8_t *p = a.line_start[l0 + 2];
+        if (a.line_end[l0 + 2] - p < 1 || *p != '+') err |= kFqErrPrefix;
+    } else {
+        err |= kFqErrTruncated;
+    }
+    if (avail >= 4) {
+        ptr[3] = a.line_start[l0 + 3];
+        len[3] = (int32_t)(a.line_end[l0 + 3] - ptr[3]);
+    }
+    return err;
+}
+
+__global__ void __launch_bounds__(256) fq_fields_kernel(const __grid_constant__ FqColArgs a) {
+    const long long r = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (r >= a.n_records) return;
+    const int f = fq_find_file(a.files, a.n_files, r);
+    const uint8_t *ptr[4];
+    int32_t len[4];
+    const uint32_t err = fq_record_fields(a, r, f, ptr, len);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (a.lens[k]) a.lens[k][r] = len[k];
+    if (err) atomicOr(a.flags, err);
+}
+
+__global__ void __launch_bounds__(256) fq_gather_kernel(const __grid_constant__ FqColArgs a) {
+    const long long r = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= a.n_records) return;
+    const int f = fq_find_file(a.files, a.n_files, r);
+    const uint8_t *ptr[4];
+    int32_t len[4];
+    fq_record_fields(a, r, f, ptr, len);
+    const long long local = r - a.files[f].rec0;
+    const long long b = a.files[f].batch0 + local / a.batch_rows;
+    const int in_batch = (int)(local % a.batch_rows);
+    const long long first = r - in_batch;
+    const bool last_of_batch = in_batch + 1 == a.batch_rows || r + 1 == a.files[f + 1].rec0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!a.values[k]) continue;
+        const long long v = a.voff[k][r];
+        uint8_t *dst = a.values[k] + v;
+        for (int j = lane; j < len[k]; j += 32) dst[j] = ptr[k][j];
+        if (lane == 0) {
+            const long long v0 = a.voff[k][first];
+            int32_t *o = a.offsets[k] + b * (a.batch_rows + 1);
+            o[in_batch] = (int32_t)(v - v0);
+            if (last_of_batch) o[in_batch + 1] = (int32_t)(v + len[k] - v0);
+        }
+    }
+    if (lane == 0 && a.desc_valid && len[1] > 0) atomicOr(a.desc_valid + b * a.words_per_batch + (in_batch >> 5), 1u << (in_batch & 31));
+}
+
+__global__ void fq_gather_i64(const long long *src, const long long *idx, int64_t n, long long *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+__global__ void fq_gather_u64(const unsigned long long *src, const long long *idx, int n, unsigned long long *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+}  // namespace
+
+// Column store of one FASTQ stream; batches are views into it.
+struct FqColumns {
+    std::atomic<int> refs{1};
+    bool on_device = false;
+    int device = 0;
+    int64_t n_rows = 0, n_batches = 0, next = 0;
+    int batch_rows = 8192, words_per_batch = 256;
+    std::vector<int> projection;
+    uint8_t *d_values[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t *d_offsets[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *d_valid = nullptr;
+    uint8_t *h_values[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t *h_offsets[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *h_valid = nullptr;
+    std::vector<long long> batch_row0;
+    std::vector<long long> batch_v0[4];
+    void unref() {
+        if (refs.fetch_sub(1) == 1) {
+            cudaSetDevice(device);
+            for (int k = 0; k < 4; ++k) {
+                cudaFree(d_values[k]);
+                cudaFree(d_offsets[k]);
+                cudaFreeHost(h_values[k]);
+                cudaFreeHost(h_offsets[k]);
+            }
+            cudaFree(d_valid);
+            cudaFreeHost(h_valid);
+            delete this;
+        }
+    }
+};
+
+void fq_columns_free(VcfStream *s) {
+    if (s->fq_cols) {
+        s->fq_cols->unref();
+        s->fq_cols = nullptr;
+    }
+}
+
+namespace {
+
+struct FqBatchPriv {
+    FqColumns *cols;
+    int n_children;
+    ArrowArray children[4];
+    ArrowArray *child_ptrs[4];
+    const void *child_buffers[4][3];
+    const void *struct_buffers[1];
+};
+void fq_release_child(ArrowArray *a) { a->release = nullptr; }
+void fq_release_batch(ArrowArray *a) {
+    auto *p = static_cast<FqBatchPriv *>(a->private_data);
+    for (int i = 0; i < p->n_children; ++i)
+        if (p->children[i].release) p->children[i].release(&p->children[i]);
+    p->cols->unref();
+    delete p;
+    a->release = nullptr;
+}
+struct FqSchemaPriv {
+    int n_children;
+    ArrowSchema children[4];
+    ArrowSchema *child_ptrs[4];
+};
+void fq_release_schema_child(ArrowSchema *s) { s->release = nullptr; }
+void fq_release_schema(ArrowSchema *s) {
+    auto *p = static_cast<FqSchemaPriv *>(s->private_data);
+    for (int i = 0; i < p->n_children; ++i)
+        if (p->children[i].release) p->children[i].release(&p->children[i]);
+    delete p;
+    s->release = nullptr;
+}
+// exon/exon-fastq/src/config.rs:79-88: name !null, description nullable, sequence !null, quality_scores !null, all Utf8
+void fq_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
+    static const char *names[4] = {"name", "description", "sequence", "quality_scores"};
+    auto *p = new FqSchemaPriv();
+    p->n_children = (int)projection.size();
+    for (int i = 0; i < p->n_children; ++i) {
+        ArrowSchema &c = p->children[i];
+        memset(&c, 0, sizeof(c));
+        c.format = "u";
+        c.name = names[projection[(size_t)i]];
+        c.flags = projection[(size_t)i] == 1 ? ARROW_FLAG_NULLABLE : 0;
+        c.release = fq_release_schema_child;
+        p->child_ptrs[i] = &c;
+    }
+    memset(out, 0, sizeof(*out));
+    out->format = "+s";
+    out->name = "";
+    out->n_children = p->n_children;
+    out->children = p->child_ptrs;
+    out->release = fq_release_schema;
+    out->private_data = p;
+}
+
+int fq_build_columns(VcfStream *s) {
+    Ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    auto *c = new (std::nothrow) FqColumns();
+    if (!c) return fail(EXON_GPU_ERR_OOM, "fastq_next_batch: out of host memory");
+    s->fq_cols = c;
+    c->device = ctx->device;
+    c->on_device = s->columns_on_device;
+    c->batch_rows = s->batch_rows;
+    c->words_per_batch = (s->batch_rows + 31) / 32;
+    c->projection = s->projection;
+    bool want[4] = {false, false, false, false};
+    for (int p : s->projection) want[p] = true;
+    c->batch_row0.assign(1, 0);
+
+    std::vector<Piece> pieces;
+    s->cut_pieces(pieces);
+    if (pieces.empty()) return EXON_GPU_OK;
+    std::vector<ScanSeg> h_segs;
+    std::vector<int32_t> file_first, file_next;
+    std::vector<long long> file_tiles;
+    int64_t n_tiles = 0;
+    for (const Piece &p : pieces) {
+        ScanSeg sg;
+        sg.skip = (int32_t)((uintptr_t)p.base & 15);
+        sg.base = p.base - sg.skip;
+        sg.len = p.len;
+        sg.tile0 = n_tiles;
+        sg.pad_ = 0;
+        const bool starts = p.starts_file || h_segs.empty();
+        if (starts) file_tiles.push_back(n_tiles);
+        n_tiles += (sg.skip + p.len + FqRing::TILE - 1) / FqRing::TILE;
+        file_first.push_back(starts ? (int32_t)h_segs.size() : file_first.back());
+        h_segs.push_back(sg);
+    }
+    const int n_segs = (int)h_segs.size();
+    file_next.assign((size_t)n_segs, n_segs);
+    for (int i = n_segs - 2; i >= 0; --i) file_next[(size_t)i] = file_first[(size_t)i + 1] != file_first[(size_t)i] ? i + 1 : file_next[(size_t)i + 1];
+    ScanSeg sentinel;
+    memset(&sentinel, 0, sizeof(sentinel));
+    sentinel.tile0 = n_tiles;
+    h_segs.push_back(sentinel);
+    file_tiles.push_back(n_tiles);
+    const int n_files = (int)file_tiles.size() - 1;
+
+    size_t cub_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)(n_tiles + 1), st));
+    const size_t o_segs = 0, o_lines = o_segs + al256(h_segs.size() * sizeof(ScanSeg)), o_prefix = o_lines + al256((size_t)(n_tiles + 1) * 8),
+                 o_cub = o_prefix + al256((size_t)(n_tiles + 1) * 8), o_ff = o_cub + al256(cub_bytes), o_fn = o_ff + al256((size_t)n_segs * 4),
+                 o_l0 = o_fn + al256((size_t)n_segs * 4), o_ft = o_l0 + al256((size_t)n_segs * 8), o_fp = o_ft + al256(file_tiles.size() * 8),
+                 o_ftab = o_fp + al256(file_tiles.size() * 8), o_out = o_ftab + al256(((size_t)n_files + 1) * sizeof(FqFileTab));
+    if (int rc = ctx->ensure_scratch(o_out + 256, file_tiles.size() * 8 + 64)) return rc;
+    uint8_t *scr = (uint8_t *)ctx->scratch;
+    CUDA_TRY(cudaMemcpyAsync(scr + o_segs, h_segs.data(), h_segs.size() * sizeof(ScanSeg), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(scr + o_ff, file_first.data(), (size_t)n_segs * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(scr + o_fn, file_next.data(), (size_t)n_segs * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(scr + o_ft, file_tiles.data(), file_tiles.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(scr + o_out, 0, 64, st));
+    CUDA_TRY(cudaMemsetAsync(scr + o_lines + (size_t)n_tiles * 8, 0, 8, st));
+    FqArgs a;
+    memset(&a, 0, sizeof(a));
+    a.segs = (const ScanSeg *)(scr + o_segs);
+    a.n_segs = n_segs;
+    a.n_tiles = n_tiles;
+    a.tile_lines = (unsigned long long *)(scr + o_lines);
+    a.tile_prefix = (const unsigned long long *)(scr + o_prefix);
+    a.seg_line0 = (const unsigned long long *)(scr + o_l0);
+    a.out = (unsigned long long *)(scr + o_out);
+    a.flags = (uint32_t *)(scr + o_out + 16);
+    static int occ_a = 0, occ_i = 0;
+    CUDA_TRY(fq_launch(fq_lines_kernel, a, ctx->sm_count, st, &occ_a));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(scr + o_cub, cub_bytes, a.tile_lines, (unsigned long long *)(scr + o_prefix), (int)(n_tiles + 1), st));
+    fq_segment_table<<<(n_segs + 127) / 128, 128, 0, st>>>(a.segs, n_segs, a.tile_prefix, (const int32_t *)(scr + o_ff),
+                                                           (const int32_t *)(scr + o_fn), (unsigned long long *)(scr + o_l0), a.flags);
+    fq_gather_u64<<<(unsigned)((file_tiles.size() + 127) / 128), 128, 0, st>>>(a.tile_prefix, (const long long *)(scr + o_ft), (int)file_tiles.size(),
+                                                                               (unsigned long long *)(scr + o_fp));
+    ctx->launches.fetch_add(4);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long *h_fp = (unsigned long long *)ctx->h_scratch;
+    CUDA_TRY(cudaMemcpyAsync(h_fp, scr + o_fp, file_tiles.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s->h_res, a.out, 24, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if ((uint32_t)s->h_res[2] & kFqErrTruncated) return fail(EXON_GPU_ERR_PARSE, "malformed FASTQ record: unexpected end of file inside a record;");
+    // files -> records -> batches (batches restart at every file; a file with 4k + 3 lines ends in a record without quality)
+    std::vector<FqFileTab> ftab((size_t)n_files + 1);
+    long long n_records = 0;
+    c->batch_row0.clear();
+    for (int f = 0; f < n_files; ++f) {
+        const long long lines = (long long)(h_fp[f + 1] - h_fp[f]);
+        const long long recs = (lines + 3) / 4;
+        ftab[(size_t)f] = FqFileTab{n_records, (long long)h_fp[f], lines, (long long)c->batch_row0.size()};
+        for (long long r = 0; r < recs; r += c->batch_rows) c->batch_row0.push_back(n_records + r);
+        n_records += recs;
+    }
+    ftab[(size_t)n_files] = FqFileTab{n_records, (long long)h_fp[n_files], 0, (long long)c->batch_row0.size()};
+    const long long n_lines = (long long)h_fp[n_files];
+    c->n_rows = n_records;
+    c->n_batches = (int64_t)c->batch_row0.size();
+    c->batch_row0.push_back(n_records);
+    if (n_records == 0) return EXON_GPU_OK;
+    CUDA_TRY(cudaMemcpyAsync(scr + o_ftab, ftab.data(), ftab.size() * sizeof(FqFileTab), cudaMemcpyHostToDevice, st));
+
+    // scratch B: line tables | lens x4 | voff x4 | cub temp | batch tables
+    size_t cub2 = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub2, (int32_t *)nullptr, (long long *)nullptr, (int)(n_records + 1), st));
+    const size_t nb1 = (size_t)c->n_batches + 1;
+    size_t ob = 0;
+    const size_t o_ls = ob; ob += al256((size_t)(n_lines + 1) * 8);
+    const size_t o_le = ob; ob += al256((size_t)(n_lines + 1) * 8);
+    size_t o_len[4], o_voff[4];
+    for (int k = 0; k < 4; ++k) { o_len[k] = ob; ob += al256((size_t)(n_records + 1) * 4); }
+    for (int k = 0; k < 4; ++k) { o_voff[k] = ob; ob += al256((size_t)(n_records + 1) * 8); }
+    const size_t o_cub2 = ob; ob += al256(cub2);
+    const size_t o_brow = ob; ob += al256(nb1 * 8);
+    const size_t o_bv0 = ob; ob += al256(nb1 * 8);
+    if (int rc = ctx->ensure_scratch_b(ob + 256)) return rc;
+    uint8_t *scb = (uint8_t *)ctx->scratch_b;
+    FqIndexArgs ia;
+    ia.segs = a.segs;
+    ia.n_tiles = n_tiles;
+    ia.tile_prefix = a.tile_prefix;
+    ia.line_start = (const uint8_t **)(scb + o_ls);
+    ia.line_end = (const uint8_t **)(scb + o_le);
+    {
+        constexpr size_t smem = FqRing::smem_bytes;
+        if (!occ_i) {
+            CUDA_TRY(cudaFuncSetAttribute(fq_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, fq_index_kernel, FqRing::WARPS * 32, smem));
+            if (occ_i < 1) occ_i = 1;
+        }
+        int64_t grid = std::min<int64_t>((int64_t)occ_i * ctx->sm_count, (n_tiles + FqRing::WARPS - 1) / FqRing::WARPS);
+        if (grid < 1) grid = 1;
+        fq_index_kernel<<<(unsigned)grid, FqRing::WARPS * 32, smem, st>>>(ia);
+        CUDA_TRY(cudaGetLastError());
+    }
+    FqColArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.files = (const FqFileTab *)(scr + o_ftab);
+    ca.n_files = n_files;
+    ca.n_records = n_records;
+    ca.batch_rows = c->batch_rows;
+    ca.line_start = ia.line_start;
+    ca.line_end = ia.line_end;
+    ca.words_per_batch = c->words_per_batch;
+    ca.flags = a.flags;
+    for (int k = 0; k < 4; ++k) {
+        if (!want[k]) continue;
+        ca.lens[k] = (int32_t *)(scb + o_len[k]);
+        ca.voff[k] = (const long long *)(scb + o_voff[k]);
+        CUDA_TRY(cudaMemsetAsync(scb + o_len[k] + (size_t)n_records * 4, 0, 4, st));
+    }
+    const unsigned rec_grid = (unsigned)((n_records + 255) / 256);
+    fq_fields_kernel<<<rec_grid, 256, 0, st>>>(ca);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(scb + o_brow, c->batch_row0.data(), nb1 * 8, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 4; ++k) {
+        if (!want[k]) continue;
+        size_t tb = cub2;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(scb + o_cub2, tb, (const int32_t *)(scb + o_len[k]), (long long *)(scb + o_voff[k]), (int)(n_records + 1), st));
+        fq_gather_i64<<<(unsigned)((nb1 + 255) / 256), 256, 0, st>>>((const long long *)(scb + o_voff[k]), (const long long *)(scb + o_brow), (int64_t)nb1,
+                                                                    (long long *)(scb + o_bv0));
+        c->batch_v0[k].resize(nb1);
+        CUDA_TRY(cudaMemcpyAsync(c->batch_v0[k].data(), scb + o_bv0, nb1 * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // o_bv0 is reused by the next column
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->h_res, a.out, 24, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if ((uint32_t)s->h_res[2])
+        return fail(EXON_GPU_ERR_PARSE, "malformed FASTQ record:%s%s", ((uint32_t)s->h_res[2] & kFqErrPrefix) ? " invalid name prefix or missing '+' line;" : "",
+                    ((uint32_t)s->h_res[2] & kFqErrTruncated) ? " unexpected end of file inside a record;" : "");
+    size_t total[4] = {0, 0, 0, 0};
+    const size_t off_elems = (size_t)c->n_batches * (size_t)(c->batch_rows + 1);
+    for (int k = 0; k < 4; ++k) {
+        if (!want[k]) continue;
+        total[k] = (size_t)c->batch_v0[k][(size_t)c->n_batches];
+        for (int64_t b = 0; b < c->n_batches; ++b)
+            if (c->batch_v0[k][(size_t)b + 1] - c->batch_v0[k][(size_t)b] > 0x7FFFFFFFll)
+                return fail(EXON_GPU_ERR_UNSUPPORTED, "fastq: the bytes of batch %lld overflow int32 offsets", (long long)b);
+        CUDA_TRY(cudaMallocAsync((void **)&c->d_values[k], std::max<size_t>(total[k], 1), st));
+        CUDA_TRY(cudaMallocAsync((void **)&c->d_offsets[k], off_elems * 4, st));
+        ca.values[k] = c->d_values[k];
+        ca.offsets[k] = c->d_offsets[k];
+    }
+    const size_t valid_bytes = (size_t)c->n_batches * (size_t)c->words_per_batch * 4;
+    if (want[1]) {
+        CUDA_TRY(cudaMallocAsync((void **)&c->d_valid, valid_bytes, st));
+        CUDA_TRY(cudaMemsetAsync(c->d_valid, 0, valid_bytes, st));
+        ca.desc_valid = c->d_valid;
+    }
+    fq_gather_kernel<<<(unsigned)((n_records * 32 + 255) / 256), 256, 0, st>>>(ca);
+    ctx->launches.fetch_add(4);
+    CUDA_TRY(cudaGetLastError());
+    if (!c->on_device) {
+        for (int k = 0; k < 4; ++k) {
+            if (!want[k]) continue;
+            CUDA_TRY(cudaHostAlloc((void **)&c->h_values[k], std::max<size_t>(total[k], 1), cudaHostAllocDefault));
+            CUDA_TRY(cudaHostAlloc((void **)&c->h_offsets[k], off_elems * 4, cudaHostAllocDefault));
+            CUDA_TRY(cudaMemcpyAsync(c->h_values[k], c->d_values[k], total[k], cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(c->h_offsets[k], c->d_offsets[k], off_elems * 4, cudaMemcpyDeviceToHost, st));
+        }
+        if (want[1]) {
+            CUDA_TRY(cudaHostAlloc((void **)&c->h_valid, valid_bytes, cudaHostAllocDefault));
+            CUDA_TRY(cudaMemcpyAsync(c->h_valid, c->d_valid, valid_bytes, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return EXON_GPU_OK;
+}
+
+}  // namespace
+
+int fastq_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
+    if (!s->fq_cols) {
+        if (int rc = s->flush_gz()) return rc;
+        std::lock_guard<std::mutex> work(s->ctx->work_mu);
+        if (int rc = fq_build_columns(s)) {
+            fq_columns_free(s);
+            return rc;
+        }
+        s->drained = true;
+    }
+    FqColumns *c = s->fq_cols;
+    if (out_schema) fq_fill_schema(s->projection, out_schema);
+    memset(out, 0, sizeof(*out));
+    if (c->next >= c->n_batches) return EXON_GPU_OK;  // end of stream: release == NULL
+    const int64_t b = c->next++;
+    const int64_t rows = c->batch_row0[(size_t)b + 1] - c->batch_row0[(size_t)b];
+    auto *p = new FqBatchPriv();
+    p->cols = c;
+    c->refs.fetch_add(1);
+    p->n_children = (int)s->projection.size();
+    for (int i = 0; i < p->n_children; ++i) {
+        const int k = s->projection[(size_t)i];
+        ArrowArray &a = p->children[i];
+        memset(&a, 0, sizeof(a));
+        a.length = rows;
+        a.null_count = k == 1 ? -1 : 0;  // description: not counted (the bitmap is authoritative)
+        a.n_buffers = 3;
+        p->child_buffers[i][0] = k == 1 ? (const void *)((c->on_device ? c->d_valid : c->h_valid) + b * c->words_per_batch) : nullptr;
+        p->child_buffers[i][1] = (c->on_device ? c->d_offsets[k] : c->h_offsets[k]) + b * (c->batch_rows + 1);
+        p->child_buffers[i][2] = (c->on_device ? c->d_values[k] : c->h_values[k]) + c->batch_v0[k][(size_t)b];
+        a.buffers = p->child_buffers[i];
+        a.release = fq_release_child;
+        p->child_ptrs[i] = &a;
+    }
+    p->struct_buffers[0] = nullptr;
+    out->length = rows;
+    out->n_buffers = 1;
+    out->buffers = p->struct_buffers;
+    out->n_children = p->n_children;
+    out->children = p->child_ptrs;
+    out->release = fq_release_batch;
+    out->private_data = p;
+    return EXON_GPU_OK;
+}
+
 }  // namespace exon
 
 using namespace exon;
@@ -424,13 +982,18 @@ extern "C" {
 int exon_gpu_fastq_open(exon_gpu_ctx *c, const exon_gpu_fastq_opts *o, exon_gpu_stream **out) {
     if (!c || !out) return fail(EXON_GPU_ERR_ARG, "fastq_open: NULL argument");
     *out = nullptr;
-    if (o && o->n_projection > 0)
-        return fail(EXON_GPU_ERR_UNSUPPORTED, "fastq_open: column batches are not built on the GPU yet; open with n_projection = 0 "
-                                              "and use exon_gpu_fastq_filter_count");
+    if (o && (o->n_projection < 0 || o->n_projection > 4 || (o->n_projection > 0 && !o->projection)))
+        return fail(EXON_GPU_ERR_ARG, "fastq_open: bad projection");
+    if (o)
+        for (int i = 0; i < o->n_projection; ++i)
+            if (o->projection[i] < 0 || o->projection[i] > 3) return fail(EXON_GPU_ERR_ARG, "fastq_open: projection index %d is not a FASTQ column", o->projection[i]);
     exon_gpu_vcf_opts vo;
     memset(&vo, 0, sizeof(vo));
     vo.batch_rows = o ? o->batch_rows : 0;
+    vo.columns_on_device = o ? o->columns_on_device : 0;
     if (int rc = exon_gpu_vcf_open(c, &vo, out)) return rc;
+    if (o)
+        for (int i = 0; i < o->n_projection; ++i) (*out)->projection.push_back(o->projection[i]);
     (*out)->fmt = kFmtFastq;
     (*out)->hdr = VcfStream::kBody;  // no header: every byte is record data
     return EXON_GPU_OK;
@@ -455,6 +1018,14 @@ int exon_gpu_fastq_rows(exon_gpu_stream *s, int64_t *out_rows) {
     cudaError_t e = cudaSetDevice(s->ctx->device);
     if (e != cudaSuccess) return fail(EXON_GPU_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     return fastq_filter_count(s, nullptr, nullptr, out_rows);
+}
+
+int exon_gpu_fastq_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema) {
+    if (!s || !out) return fail(EXON_GPU_ERR_ARG, "fastq_next_batch: NULL argument");
+    if (s->fmt != kFmtFastq) return fail(EXON_GPU_ERR_ARG, "fastq_next_batch: not a FASTQ stream");
+    cudaError_t e = cudaSetDevice(s->ctx->device);
+    if (e != cudaSuccess) return fail(EXON_GPU_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return fastq_next_batch(s, out, out_schema);
 }
 
 int exon_gpu_stream_close(exon_gpu_stream *s) { return exon_gpu_vcf_close(s); }

@@ -129,6 +129,7 @@ struct VcfStream {
 
     // ---- column build (K2) state lives in vcf_columns.cu ----
     struct Columns *cols = nullptr;
+    struct FqColumns *fq_cols = nullptr;  // FASTQ column store (fastq_scan.cu)
 
     // ---- compressed feeds (bgzf.cu): bytes of the current .gz file that arrived before its last range ----
     std::vector<uint8_t> gz_pending;
@@ -217,6 +218,8 @@ int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table
 int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected, int64_t *out_spectra);
 
 // defined in fastq_scan.cu
+void fq_columns_free(VcfStream *s);
+int fastq_next_batch(VcfStream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count, int64_t *out_rows);
 
 // defined in vcf_columns.cu

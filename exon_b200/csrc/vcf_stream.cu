@@ -72,6 +72,7 @@ void VcfStream::release_all() {
     segs_dirty = true;
     drained = false;
     columns_free(this);
+    fq_columns_free(this);
 }
 
 // Append body bytes that live on the host to the arena (one async H2D copy on the stream).

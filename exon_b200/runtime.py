@@ -232,6 +232,17 @@ class VcfBatch:
             return np.ctypeslib.as_array(C.cast(ch.buffers[1], C.POINTER(C.c_int64)), (max(n, 1),))[:n].copy()
         raise NotImplementedError(self.formats[i])
 
+    def strings(self, name: str):
+        """utf8 column as a list of bytes (None where the validity bitmap, if any, marks NULL)."""
+        off, val = self.column(name)
+        ch = self._arr.children[self.names.index(name)].contents
+        b = val.tobytes()
+        out = [b[off[i]:off[i + 1]] for i in range(self.num_rows)]
+        if ch.buffers[0]:
+            bits = np.ctypeslib.as_array(C.cast(ch.buffers[0], C.POINTER(C.c_uint8)), ((self.num_rows + 7) // 8,))
+            out = [x if (bits[i >> 3] >> (i & 7)) & 1 else None for i, x in enumerate(out)]
+        return out
+
     def chrom_strings(self):
         off, val = self.column("chrom")
         b = val.tobytes()
@@ -369,12 +380,30 @@ class VcfStream:
 class FastqStream:
     """exon_gpu_stream opened with exon_gpu_fastq_open: one partition stream over a group of FASTQ files."""
 
-    def __init__(self, ctx: Context, *, batch_rows: int = 8192):
+    def __init__(self, ctx: Context, *, batch_rows: int = 8192, projection=(), columns_on_device: bool = False):
         self.ctx = ctx
         self.lib = ctx.lib
-        opts = _abi.FastqOpts(batch_rows, 0, None, 0)
+        self._proj = (C.c_int32 * max(len(projection), 1))(*projection)
+        opts = _abi.FastqOpts(batch_rows, len(projection), self._proj, int(columns_on_device))
         self.handle = C.c_void_p()
         check(self.lib.exon_gpu_fastq_open(ctx.handle, C.byref(opts), C.byref(self.handle)))
+        self.columns_on_device = columns_on_device
+
+    def next_batch(self):
+        arr, sch = _abi.ArrowArray(), _abi.ArrowSchema()
+        check(self.lib.exon_gpu_fastq_next_batch(self.handle, C.byref(arr), C.byref(sch)))
+        if not arr.release:
+            if sch.release:
+                sch.release(C.byref(sch))
+            return None
+        return VcfBatch(arr, sch, self.columns_on_device)
+
+    def batches(self):
+        while True:
+            b = self.next_batch()
+            if b is None:
+                return
+            yield b
 
     def close(self):
         if self.handle:

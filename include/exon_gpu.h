@@ -179,7 +179,7 @@ int exon_gpu_vcf_body_bytes(exon_gpu_stream *s, int64_t *out_bytes);
  * shares the arena, the host/device feeds and the file framing with the VCF stream; there is no header. */
 typedef struct {
     int32_t batch_rows;        /* session batch size (8192) */
-    int32_t n_projection;      /* must be 0 for now: the fused query below is the only consumer */
+    int32_t n_projection;      /* columns exon_gpu_fastq_next_batch materialises, in output order (0 for the fused query alone) */
     const int32_t *projection; /* FASTQ file schema: 0 name, 1 description, 2 sequence, 3 quality_scores (exon-fastq/src/config.rs:79-88) */
     int32_t columns_on_device;
 } exon_gpu_fastq_opts;
@@ -200,6 +200,11 @@ int exon_gpu_fastq_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int
  * that does not start with '+', a file that ends after the first or second line of a record. */
 int exon_gpu_fastq_filter_count(exon_gpu_stream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count);
 int exon_gpu_fastq_rows(exon_gpu_stream *s, int64_t *out_rows);
+/* Columns out: BatchReader::read_batch + FASTQArrayBuilder::{append, finish} (exon/exon-fastq/src/batch_reader.rs:63-82,
+ * exon/exon-fastq/src/array_builder.rs:68-118).  A struct array of <= batch_rows rows whose children are the projected
+ * utf8 columns; `description` carries a validity bitmap (NULL when the definition line has nothing after the name).
+ * Same end-of-stream and ownership conventions as exon_gpu_vcf_next_batch. */
+int exon_gpu_fastq_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 /* Compressed bytes in: consecutive byte ranges of ONE BGZF file (or a plain single-member .gz; slower, one warp) --
  * what VCFOpener::open / FASTQOpener::open wrap in a BGZF / gzip decoder for FileCompressionType::GZIP
  * (exon/exon-core/src/datasources/vcf/file_opener/unindex_file_opener.rs:59-73, exon-core/src/streaming_bgzf.rs:22-118).

@@ -135,3 +135,65 @@ def test_properties_large(gpu_ctx):
             c = s.filter_count(t)
             assert c == sh.truth_count(t) and c <= prev
             prev = c
+
+
+# ---- column batches (FASTQArrayBuilder) --------------------------------------------------------------------------
+
+def gpu_records(ctx, feeds, batch_rows=8192, projection=(0, 1, 2, 3), gz=False):
+    names = ["name", "description", "sequence", "quality_scores"]
+    with ctx.open_fastq(batch_rows=batch_rows, projection=projection) as s:
+        for f in feeds:
+            (s.feed_gzip if gz else s.feed)(f)
+        rows, sizes = [], []
+        for b in s.batches():
+            assert b.names == [names[k] for k in projection] and b.formats == ["u"] * len(projection)
+            cols = [b.strings(n) for n in b.names]
+            rows += list(zip(*cols))
+            sizes.append(b.num_rows)
+            b.release()
+        return rows, sizes
+
+
+def oracle_records(feeds, batch_rows=8192, projection=(0, 1, 2, 3)):
+    keys = ["name", "description", "sequence", "quality"]
+    rows, sizes = [], []
+    for f in feeds:
+        for b in oracle.fastq_read_batches(f, batch_size=batch_rows):
+            rows += list(zip(*[b[keys[k]] for k in projection]))
+            sizes.append(b["rows"])
+    return rows, sizes
+
+
+def test_columns_reference_fixture(gpu_ctx):
+    with open(os.path.join(GOLDEN, "test.fastq"), "rb") as f:
+        text = f.read()
+    rows, sizes = gpu_records(gpu_ctx, [text])
+    qual = b"!''*((((***+))%%%++)(%%%%).1***-+*''))**55CCF>>>>>>CCCCCCC65"
+    seq = b"GATTTGGGGTExonAAGCAGTATCGAExonAATAGTAAATCCATTTGTExonACExonCAGTTT"
+    # slt/fastq-scan-test.slt:6-10: name, description (NULL for the second record), quality_scores, sequence
+    assert rows == [(b"SEQ_ID", b"This is a description", seq, qual), (b"SEQ_ID2", None, seq, qual)] and sizes == [2]
+    assert gpu_records(gpu_ctx, [text, text], batch_rows=1)[1] == [1, 1, 1, 1]
+
+
+def test_columns_match_oracle(gpu_ctx, synth_fq):
+    files = [bytes(f[: 316 * 5000]) for f in synth_fq.files[:3]]
+    for batch_rows, proj in [(8192, (0, 1, 2, 3)), (1000, (3, 0)), (777, (2,)), (64, (1,))]:
+        assert gpu_records(gpu_ctx, files, batch_rows, proj) == oracle_records(files, batch_rows, proj), (batch_rows, proj)
+    rng = np.random.default_rng(3)
+    texts = [rand_fastq(rng, 3000, 40), rand_fastq(rng, 500, 3, tiny=True), b"", rand_fastq(rng, 40, 20_000), b"@a\nAC\n+\nII", b"@b desc only\nAC\n+\n"]
+    assert gpu_records(gpu_ctx, texts, 100) == oracle_records(texts, 100)
+    from bgzf_util import bgzf_compress
+
+    assert gpu_records(gpu_ctx, [bgzf_compress(t) for t in texts[:2]], 100, gz=True) == oracle_records(texts[:2], 100)
+    # ragged feeds of one file
+    with gpu_ctx.open_fastq(projection=(0, 3), batch_rows=500) as s:
+        t = texts[0]
+        for o in range(0, len(t), 10_000):
+            s.feed(t[o:o + 10_000], is_last=o + 10_000 >= len(t))
+        got = [r for b in s.batches() for r in zip(b.strings("name"), b.strings("quality_scores"))]
+    assert got == oracle_records([t], 500, (0, 3))[0]
+    for bad in [b"SEQ\nACGT\n+\n!!!!\n", b"@a\nACGT\n-\n!!!!\n", b"@a\nACGT\n"]:
+        with gpu_ctx.open_fastq(projection=(0,)) as s:
+            s.feed(bad)
+            with pytest.raises(ExonGpuError):
+                s.next_batch()
