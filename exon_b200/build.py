@@ -60,7 +60,7 @@ def build_host(force: bool = False, verbose: bool = False) -> str:
     deps = srcs + [os.path.join(HOST_DIR, "exon_host.hpp"), os.path.join(HERE, "..", "include", "exon_gpu.h"), LIB]
     if not force and os.path.exists(HOST_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_LIB) for d in deps):
         return HOST_LIB
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB, *srcs, "-L" + HERE, "-lexon_gpu", "-lz",
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB, *srcs, "-L" + HERE, "-lexon_gpu",
            "-lpthread", "-Wl,-rpath,$ORIGIN/.."]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)

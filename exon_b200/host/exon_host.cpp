@@ -3,7 +3,6 @@
 
 #include <dirent.h>
 #include <sys/stat.h>
-#include <zlib.h>
 
 #include <algorithm>
 #include <cctype>
@@ -44,36 +43,6 @@ std::vector<uint8_t> read_file(const std::string &path) {
     f.seekg(0);
     f.read((char *)buf.data(), (std::streamsize)buf.size());
     return buf;
-}
-
-// gzip / BGZF (concatenated gzip members) -> bytes.  Interim host-side inflate, the role `bgzf::AsyncReader` /
-// `FileCompressionType::convert_stream` play in VCFOpener::open (unindex_file_opener.rs:59-73); inflating BGZF
-// blocks on the device is the next row of SURVEY.md section 8f.
-std::vector<uint8_t> gunzip(const std::vector<uint8_t> &in) {
-    std::vector<uint8_t> out;
-    z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    if (inflateInit2(&zs, 15 + 32) != Z_OK) throw ExonError(ExonError::Execution, "inflateInit2 failed");
-    zs.next_in = const_cast<Bytef *>(in.data());
-    zs.avail_in = (uInt)in.size();
-    std::vector<uint8_t> chunk(1 << 20);
-    for (;;) {
-        zs.next_out = chunk.data();
-        zs.avail_out = (uInt)chunk.size();
-        const int rc = inflate(&zs, Z_NO_FLUSH);
-        out.insert(out.end(), chunk.data(), chunk.data() + (chunk.size() - zs.avail_out));
-        if (rc == Z_STREAM_END) {
-            if (zs.avail_in == 0) break;
-            inflateReset(&zs);  // next gzip member (BGZF block)
-        } else if (rc != Z_OK) {
-            inflateEnd(&zs);
-            throw ExonError(ExonError::External, "invalid gzip/BGZF data");
-        } else if (zs.avail_in == 0 && zs.avail_out != 0) {
-            break;
-        }
-    }
-    inflateEnd(&zs);
-    return out;
 }
 
 void list_dir(const std::string &dir, std::vector<std::string> &out) {
@@ -441,14 +410,90 @@ struct Executor {
     ExonSession &s;
     explicit Executor(ExonSession &session) : s(session) {}
 
-    // FileStream + VCFOpener::open for one partition: every file of the group is fed into one stream handle.
-    void feed_group(exon_gpu_stream *st, const std::vector<PartitionedFile> &group, FileCompressionType c) {
+    // FileStream + VCFOpener::open / IndexedVCFOpener::open for one partition: every file of the group is fed into one
+    // stream handle.  Compressed files are inflated on the device (exon_gpu_stream_feed_gzip); an indexed scan with a
+    // .tbi next to the file asks the index for the region's chunks and feeds only those (indexed_bgzf_file.rs:52-83,
+    // indexed_file_opener.rs:53-214), otherwise the whole file is scanned with the same region predicate.
+    void feed_group(exon_gpu_stream *st, const VCFScan &plan, const std::vector<PartitionedFile> &group) {
         for (const auto &f : group) {
             std::vector<uint8_t> bytes = read_file(f.path);
-            if (c == FileCompressionType::GZIP) bytes = gunzip(bytes);
-            check(exon_gpu_vcf_feed(st, bytes.data(), bytes.size(), 0, 1));
-            check(exon_gpu_ctx_synchronize(s.ctx_));  // `bytes` goes out of scope
+            bool fed = false;
+            if (plan.compression == FileCompressionType::GZIP && plan.has_region) {
+                struct stat ts;
+                const std::string tbi = f.path + ".tbi";
+                if (stat(tbi.c_str(), &ts) == 0) {
+                    const std::vector<uint8_t> index = read_file(tbi);
+                    exon_gpu_region rg;
+                    memset(&rg, 0, sizeof(rg));
+                    rg.chrom = plan.region.name.c_str();
+                    rg.chrom_len = (int32_t)plan.region.name.size();
+                    rg.has_chrom = 1;
+                    rg.has_interval = plan.region.has_interval;
+                    rg.lo = plan.region.lo;
+                    rg.hi = plan.region.hi;
+                    int32_t n = 0;
+                    check(exon_gpu_tabix_query(s.ctx_, index.data(), index.size(), &rg, nullptr, 0, &n));
+                    std::vector<exon_gpu_chunk> chunks((size_t)std::max(n, 1));
+                    check(exon_gpu_tabix_query(s.ctx_, index.data(), index.size(), &rg, chunks.data(), n, &n));
+                    for (int32_t i = 0; i < n; ++i) {  // a ranged GET from the chunk's first member to the end of the object
+                        const uint64_t lo = chunks[(size_t)i].start >> 16;
+                        if (lo >= bytes.size()) throw ExonError(ExonError::External, "tabix chunk beyond the end of " + f.path);
+                        check(exon_gpu_stream_feed_bgzf_chunk(st, bytes.data() + lo, bytes.size() - (size_t)lo, lo, &chunks[(size_t)i]));
+                    }
+                    fed = true;
+                }
+            }
+            if (!fed) {
+                if (plan.compression == FileCompressionType::GZIP) check(exon_gpu_stream_feed_gzip(st, bytes.data(), bytes.size(), 1));
+                else check(exon_gpu_vcf_feed(st, bytes.data(), bytes.size(), 0, 1));
+            }
+            int64_t flushed = 0;
+            check(exon_gpu_stream_body_bytes(st, &flushed));  // flushes pending inflates: `bytes` goes out of scope
+            check(exon_gpu_ctx_synchronize(s.ctx_));
         }
+    }
+
+    // COUNT(*) of the other formats' table functions (fastq_scan, bam_scan, mzml_scan): every file under `path`.
+    int64_t count_other(const std::string &fn, const std::string &path, bool gz) {
+        std::vector<std::string> paths;
+        struct stat stt;
+        if (stat(path.c_str(), &stt) != 0) throw ExonError(ExonError::Execution, "Object at location " + path + " not found");
+        if (S_ISDIR(stt.st_mode)) list_dir(path, paths);
+        else paths.push_back(path);
+        std::sort(paths.begin(), paths.end());
+        exon_gpu_stream *st = nullptr;
+        if (fn == "fastq_scan") check(exon_gpu_fastq_open(s.ctx_, nullptr, &st));
+        else if (fn == "bam_scan") check(exon_gpu_bam_open(s.ctx_, &st));
+        else check(exon_gpu_mzml_open(s.ctx_, &st));
+        int64_t n = 0;
+        try {
+            for (const auto &p : paths) {
+                const std::vector<uint8_t> bytes = read_file(p);
+                const bool file_gz = gz || ends_with(p, ".gz");
+                if (fn == "bam_scan") check(exon_gpu_bam_feed(st, bytes.data(), bytes.size(), 1));
+                else if (file_gz) check(exon_gpu_stream_feed_gzip(st, bytes.data(), bytes.size(), 1));
+                else if (fn == "fastq_scan") check(exon_gpu_fastq_feed(st, bytes.data(), bytes.size(), 0, 1));
+                else check(exon_gpu_mzml_feed(st, bytes.data(), bytes.size(), 0, 1));
+                int64_t flushed = 0;
+                check(exon_gpu_stream_body_bytes(st, &flushed));
+                check(exon_gpu_ctx_synchronize(s.ctx_));
+            }
+            if (fn == "fastq_scan") {
+                check(exon_gpu_fastq_rows(st, &n));
+            } else if (fn == "bam_scan") {
+                int32_t groups = 0;
+                check(exon_gpu_bam_filter_count_by_reference(st, nullptr, nullptr, 0, &groups, &n));
+            } else {
+                double sum = 0;
+                int64_t sel = 0;
+                check(exon_gpu_mzml_filter_sum(st, nullptr, &sum, &sel, &n));
+            }
+        } catch (...) {
+            exon_gpu_stream_close(st);
+            throw;
+        }
+        exon_gpu_stream_close(st);
+        return n;
     }
 
     int64_t count(const VCFScan &plan, const Residual &r) {
@@ -482,7 +527,7 @@ struct Executor {
             exon_gpu_stream *st = nullptr;
             check(exon_gpu_vcf_open(s.ctx_, &o, &st));
             try {
-                feed_group(st, group, plan.compression);
+                feed_group(st, plan, group);
                 if (s.config.gpu_fused) {
                     int64_t n = 0;
                     check(exon_gpu_vcf_filter_count(st, any_pred ? &reg : nullptr, &n));
@@ -546,7 +591,7 @@ struct Executor {
             exon_gpu_stream *st = nullptr;
             check(exon_gpu_vcf_open(s.ctx_, &o, &st));
             try {
-                feed_group(st, group, plan.compression);
+                feed_group(st, plan, group);
                 while (limit < 0 || taken < limit) {
                     ArrowArray arr;
                     ArrowSchema sch;
@@ -749,8 +794,19 @@ ResultSet ExonSession::sql(const std::string &query) {
             while (lx.sym(","));
             lx.expect_sym(")");
         }
+        if (src == "fastq_scan" || src == "bam_scan" || src == "mzml_scan") {
+            // FASTQ / BAM / mzML ScanFunctions (fastq/udtf.rs:49, bam/udtf.rs:55, mzml/udtf.rs:47): COUNT(*) runs on the GPU
+            if (args.empty() || args[0].kind != Expr::Utf8)
+                throw ExonError(ExonError::Internal, "this function requires the path to be specified as the first argument");
+            if (!count_star || !cols.empty() || star || lx.peek().t != Tok::End)
+                throw ExonError(ExonError::NotImplemented, src + ": only SELECT COUNT(*) runs on the GPU path of this round");
+            const bool gz = args.size() > 1 && args[1].kind == Expr::Utf8 && lower(args[1].name) == "gzip";
+            Executor ex(*this);
+            rs.rows.push_back({std::to_string(ex.count_other(src, args[0].name, gz))});
+            return rs;
+        }
         if (src != "vcf_scan" && src != "vcf_indexed_scan")
-            throw ExonError(ExonError::NotImplemented, "table function " + src + " is outside the GPU VCF path");
+            throw ExonError(ExonError::NotImplemented, "table function " + src + " is outside the GPU path");
         if (args.empty() || args[0].kind != Expr::Utf8)
             throw ExonError(ExonError::Internal, "this function requires the path to be specified as the first argument");
         FileCompressionType comp = ends_with(args[0].name, ".gz") ? FileCompressionType::GZIP : FileCompressionType::UNCOMPRESSED;

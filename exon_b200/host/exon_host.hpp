@@ -15,7 +15,13 @@
 //   infer_region_from_udf                        exon/exon-core/src/physical_plan/infer_region.rs:25-42
 //   hive partition pruning                       exon/exon-core/src/physical_plan/object_store/hive_partition.rs:32-157
 //
-// Everything that touches record bytes runs on the GPU through exon_gpu_*; this layer only plans (which files,
+//   IndexedVCFOpener::open + get_byte_range_for_file
+//                                                exon/exon-core/src/datasources/vcf/file_opener/indexed_file_opener.rs:53-214,
+//                                                exon/exon-core/src/datasources/indexed_file/indexed_bgzf_file.rs:52-83
+//   fastq_scan / bam_scan / mzml_scan (COUNT(*)) exon/exon-core/src/datasources/{fastq,bam,mzml}/udtf.rs
+//
+// Everything that touches record bytes runs on the GPU through exon_gpu_* (BGZF members are inflated on the device,
+// tabix chunks restrict which members); this layer only plans (which files,
 // which partition, which predicate) and formats results.  DataFusion's SQL front end is third party and out of
 // scope: `ExonSession::sql` understands exactly the statement shapes the reference's VCF sqllogictests use.
 #pragma once

@@ -34,6 +34,30 @@ def build_datasources(root):
         shutil.copy(os.path.join(GOLDEN, "index.vcf.gz"), os.path.join(d, "index.vcf.gz"))
     os.makedirs(os.path.join(root, "biobear-vcf"))
     shutil.copy(os.path.join(GOLDEN, "biobear_vcf_file.vcf.gz"), os.path.join(root, "biobear-vcf", "vcf_file.vcf.gz"))
+    # tabix indexes next to the BGZF files (the indexed scans ask them for chunks)
+    shutil.copy(os.path.join(GOLDEN, "index.vcf.gz.tbi"), os.path.join(root, "vcf", "index.vcf.gz.tbi"))
+    for s in ("1", "2"):
+        shutil.copy(os.path.join(GOLDEN, "index.vcf.gz.tbi"), os.path.join(root, "vcf-partition", f"sample={s}", "index.vcf.gz.tbi"))
+    shutil.copy(os.path.join(GOLDEN, "biobear_vcf_file.vcf.gz.tbi"), os.path.join(root, "biobear-vcf", "vcf_file.vcf.gz.tbi"))
+    # the other formats' fixtures
+    os.makedirs(os.path.join(root, "fastq"))
+    shutil.copy(os.path.join(GOLDEN, "test.fastq"), os.path.join(root, "fastq", "test.fastq"))
+    shutil.copy(os.path.join(GOLDEN, "test_bgzip.fastq.gz"), os.path.join(root, "fastq", "test_bgzip.fastq.gz"))
+    with open(os.path.join(GOLDEN, "test.fastq"), "rb") as f, gzip.open(os.path.join(root, "fastq", "test.fastq.gz"), "wb") as o:
+        o.write(f.read())
+    for s in ("1", "2"):
+        d = os.path.join(root, "fastq-partition", f"sample={s}")
+        os.makedirs(d)
+        shutil.copy(os.path.join(GOLDEN, "test.fastq"), os.path.join(d, "test.fastq"))
+        d = os.path.join(root, "bam-partition", f"sample={s}")
+        os.makedirs(d)
+        shutil.copy(os.path.join(GOLDEN, "test.bam"), os.path.join(d, "test.bam"))
+    os.makedirs(os.path.join(root, "bam"))
+    shutil.copy(os.path.join(GOLDEN, "test.bam"), os.path.join(root, "bam", "test.bam"))
+    os.makedirs(os.path.join(root, "mzml"))
+    shutil.copy(os.path.join(GOLDEN, "test.mzML"), os.path.join(root, "mzml", "test.mzML"))
+    with open(os.path.join(GOLDEN, "test.mzML"), "rb") as f, gzip.open(os.path.join(root, "mzml", "test.mzML.gz"), "wb") as o:
+        o.write(f.read())
     os.makedirs(os.path.join(root, "two-vcf"))
     for n in ("a.vcf", "b.vcf"):
         shutil.copy(os.path.join(root, "vcf", "index.vcf"), os.path.join(root, "two-vcf", n))
