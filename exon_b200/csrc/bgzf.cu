@@ -64,8 +64,7 @@ struct MemberSmem {
     union {                           // the code lengths are dead once the tables exist; the tokens live only afterwards
         uint8_t lens[320];            // code lengths of the block being set up (HLIT + HDIST)
         struct {
-            uint32_t tok[kTokens];    // literal: 0x80000000 | byte; match: len | dist << 9
-            uint32_t tpos[kTokens];   // output position of the token inside the member
+            uint32_t tok[kTokens];    // literal: 0x80000000 | byte; match: len | dist << 9 (positions follow from the order)
         };
     };
     uint8_t ring[kRing];              // ring[p % kRing] = output byte p, for the most recent positions
@@ -305,11 +304,26 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
 #pragma unroll 1
             while (!eob && !err) {
                 int n = 0;
-                uint32_t batch_end = 0;
+                uint32_t batch_start = 0;
                 if (gl == 0) {
+                    batch_start = pos;
                     while (n < kTokens) {
                         br.refill();
                         uint32_t e = S.lit_tab[br.peek(kLitBits)];
+                        // literal run: short codes come straight from the primary table for as long as the bits left
+                        // still cover a full length / distance symbol afterwards (no refill, no range checks per byte)
+                        bool again = false;
+                        while ((e - 1u) < 4095u) {  // e != 0 and symbol < 256
+                            br.drop((int)(e & 15u));
+                            S.tok[n++] = 0x80000000u | (e >> 4);
+                            ++pos;
+                            if (n >= kTokens || br.cnt < 29) {
+                                again = true;
+                                break;
+                            }
+                            e = S.lit_tab[br.peek(kLitBits)];
+                        }
+                        if (again) continue;
                         int sym;
                         if (e) {
                             br.drop((int)(e & 15u));
@@ -325,7 +339,6 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                         }
                         if (sym < 256) {
                             S.tok[n] = 0x80000000u | (uint32_t)sym;
-                            S.tpos[n] = pos;
                             pos += 1;
                         } else if (sym == 256) {
                             eob = true;
@@ -362,7 +375,6 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                                 break;
                             }
                             S.tok[n] = len | (dist << 9);
-                            S.tpos[n] = pos;
                             pos += len;
                         }
                         ++n;
@@ -371,12 +383,12 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                             break;
                         }
                     }
-                    batch_end = pos;
+                    if (pos > isize) err = kInfErrData;
                 }
                 n = GSHFL(n);
                 eob = GSHFL((int)eob) != 0;
                 err = GSHFL(err);
-                batch_end = GSHFL(batch_end);
+                batch_start = GSHFL(batch_start);
                 if (err) break;
                 __syncwarp(gmask);
                 // execute, strictly in output order so that the ring always holds the latest kRing positions: runs of
@@ -385,6 +397,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                 // (st.cg / ld.cg), with a group barrier around every match.
                 const int gbase = lane & ~(kG - 1);
                 int k = 0;
+                uint32_t p = batch_start;  // output position of token k (group-uniform)
 #pragma unroll 1
                 while (k < n) {
                     const int kk = k + gl;
@@ -393,15 +406,15 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                     const int run = ~lit ? __ffs((int)~lit) - 1 : 32;  // literals at the head of the next kG tokens
                     if (run > 0) {
                         if (gl < run) {
-                            const uint32_t p = S.tpos[kk];
-                            __stcg(out + p, (uint8_t)t);
-                            S.ring[p & (kRing - 1)] = (uint8_t)t;
+                            __stcg(out + p + gl, (uint8_t)t);
+                            S.ring[(p + gl) & (kRing - 1)] = (uint8_t)t;
                         }
                         k += run;
+                        p += (uint32_t)run;
                         continue;
                     }
                     __syncwarp(gmask);  // everything before this match is in place
-                    const uint32_t tm = S.tok[k], p = S.tpos[k], len = tm & 511u, dist = tm >> 9;
+                    const uint32_t tm = S.tok[k], len = tm & 511u, dist = tm >> 9;
                     const uint32_t s0 = p - dist;
                     if (dist + len <= (uint32_t)kRing) {
                         if (dist >= len) {
@@ -425,6 +438,7 @@ __global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint
                             S.ring[(p + j) & (kRing - 1)] = b;
                         }
                     }
+                    p += len;
                     __syncwarp(gmask);
                     k += 1;
                 }
