@@ -122,6 +122,9 @@ class Context:
         check(self.lib.exon_gpu_tabix_query(self.handle, C.c_void_p(tbi.ctypes.data), tbi.size, C.byref(region), out, n.value, C.byref(n)))
         return [(int(out[i].start), int(out[i].end)) for i in range(n.value)]
 
+    def open_fasta(self) -> "FastaStream":
+        return FastaStream(self)
+
     def open_mzml(self) -> "MzmlStream":
         return MzmlStream(self)
 
@@ -550,3 +553,31 @@ class MzmlStream(FastqStream):
 
     def rows(self):
         return self.filter_sum()[2]
+
+
+class FastaStream(MzmlStream):
+    """exon_gpu_stream opened with exon_gpu_fasta_open: COUNT(*) of FASTA records."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.handle = C.c_void_p()
+        check(self.lib.exon_gpu_fasta_open(ctx.handle, C.byref(self.handle)))
+
+    def feed(self, data, *, is_last: bool = True, device_ptr: int | None = None, nbytes: int | None = None):
+        if device_ptr is not None:
+            check(self.lib.exon_gpu_fasta_feed(self.handle, C.c_void_p(device_ptr), int(nbytes), 1, int(is_last)))
+            return
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        self._last_host = data
+        check(self.lib.exon_gpu_fasta_feed(self.handle, C.c_void_p(data.ctypes.data), data.size, 0, int(is_last)))
+
+    def filter_sum(self, *a, **k):
+        raise NotImplementedError
+
+    def rows(self) -> int:
+        out = C.c_int64()
+        check(self.lib.exon_gpu_fasta_rows(self.handle, C.byref(out)))
+        return out.value

@@ -238,6 +238,15 @@ int exon_gpu_stream_close(exon_gpu_stream *s);
 int exon_gpu_stream_reset(exon_gpu_stream *s);
 int exon_gpu_stream_body_bytes(exon_gpu_stream *s, int64_t *out_bytes);
 
+/* ---- FASTA partition stream (BASELINE configs[0]: SELECT COUNT(*) FROM fasta_scan(...)) ---------------------------- */
+/* FASTAScan::execute + BatchReader::read_batch (exon/exon-core/src/datasources/fasta/scanner.rs,
+ * exon/exon-fasta/src/batch_reader.rs) reduced to the row count: records = '>' definition lines.  Fed like the other
+ * text formats (exon_gpu_fasta_feed, or exon_gpu_stream_feed_gzip for .gz).  Fails with EXON_GPU_ERR_PARSE when a
+ * non-empty file does not start with '>'. */
+int exon_gpu_fasta_open(exon_gpu_ctx *ctx, exon_gpu_stream **out);
+int exon_gpu_fasta_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last);
+int exon_gpu_fasta_rows(exon_gpu_stream *s, int64_t *out_rows);
+
 /* ---- BAM partition stream (BASELINE configs[3]) ---------------------------------------- */
 /* BAMScan::execute + BAMOpener::open + BatchReader (exon/exon-core/src/datasources/bam/scanner.rs:138,
  * bam/file_opener.rs:39, exon/exon-bam/src/batch_reader.rs:70-107).  Fed with the BGZF bytes of whole .bam files;

@@ -407,3 +407,15 @@ def mzml_decode_binary(b64: bytes, zlib_compressed: bool, f32: bool):
     vals = [out[i] for i in range(n)]
     C.CDLL(None).free(out)
     return vals
+
+
+def fasta_count(data) -> int:
+    """COUNT(*) of a FASTA file: definition lines (oracle/fastq_oracle.c: exo_fasta_count)."""
+    a = _buf(data)
+    L = lib()
+    L.exo_fasta_count.restype = C.c_int64
+    L.exo_fasta_count.argtypes = [C.c_void_p, C.c_int64]
+    n = L.exo_fasta_count(a.ctypes.data, a.size)
+    if n < 0:
+        raise ValueError("malformed FASTA")
+    return int(n)

@@ -255,3 +255,21 @@ int64_t exo_fastq_filter_count_files(const uint8_t *const *texts, const int64_t 
 void exo_quality_scores_to_list(const uint8_t *s, int64_t n, int32_t *out) {
     for (int64_t i = 0; i < n; i++) out[i] = (int32_t)s[i] - 33;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * FASTA row count (BASELINE configs[0]).  noodles-fasta reader as driven by exon-fasta/src/batch_reader.rs: a record is
+ * a definition line that starts with '>' plus the sequence lines up to the next definition; COUNT(*) is the number of
+ * definition lines.  A non-empty input whose first byte is not '>' fails ("invalid definition").  Pinned by
+ * slt/fasta-scan-tests.slt:72-85 (2 / 4 / gzip 2).
+ * ------------------------------------------------------------------------------------------- */
+int64_t exo_fasta_count(const uint8_t *text, int64_t len) {
+    if (len == 0) return 0;
+    if (text[0] != '>') return EXO_ERR_PARSE;
+    int64_t n = 1;
+    const uint8_t *p = text, *end = text + len;
+    while ((p = (const uint8_t *)memchr(p, '\n', (size_t)(end - p))) != NULL) {
+        ++p;
+        if (p < end && *p == '>') ++n;
+    }
+    return n;
+}

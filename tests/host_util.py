@@ -58,6 +58,14 @@ def build_datasources(root):
     shutil.copy(os.path.join(GOLDEN, "test.mzML"), os.path.join(root, "mzml", "test.mzML"))
     with open(os.path.join(GOLDEN, "test.mzML"), "rb") as f, gzip.open(os.path.join(root, "mzml", "test.mzML.gz"), "wb") as o:
         o.write(f.read())
+    os.makedirs(os.path.join(root, "fasta"))
+    shutil.copy(os.path.join(GOLDEN, "test.fasta"), os.path.join(root, "fasta", "test.fasta"))
+    with open(os.path.join(GOLDEN, "test.fasta"), "rb") as f, gzip.open(os.path.join(root, "fasta", "test.fasta.gz"), "wb") as o:
+        o.write(f.read())
+    for s in ("1", "2"):
+        d = os.path.join(root, "fasta-partition", f"sample={s}")
+        os.makedirs(d)
+        shutil.copy(os.path.join(GOLDEN, "test.fasta"), os.path.join(d, "test.fasta"))
     os.makedirs(os.path.join(root, "two-vcf"))
     for n in ("a.vcf", "b.vcf"):
         shutil.copy(os.path.join(root, "vcf", "index.vcf"), os.path.join(root, "two-vcf", n))
