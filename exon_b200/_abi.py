@@ -64,7 +64,9 @@ class FastqPred(C.Structure):
 
 
 class BamPred(C.Structure):
-    _fields_ = [("flag_exclude", C.c_uint32), ("flag_require", C.c_uint32), ("min_mapq", C.c_int32), ("pad_", C.c_int32)]
+    _fields_ = [("flag_exclude", C.c_uint32), ("flag_require", C.c_uint32), ("min_mapq", C.c_int32), ("has_region", C.c_int32),
+                ("region_ref", C.c_char_p), ("region_ref_len", C.c_int32), ("pad_", C.c_int32), ("region_lo", C.c_int64),
+                ("region_hi", C.c_int64)]
 
 
 class MzmlPred(C.Structure):

@@ -44,7 +44,7 @@ struct BamEntry {
     int32_t remap0;        // index of the file's refID -> group table in `remap`
     int32_t n_ref;
     int32_t last_of_file;  // 1: the walk must end exactly at `total`
-    int32_t pad_;
+    int32_t file_idx;      // index of the file in the stream (per-file query parameters)
 };
 
 struct BamArgs {
@@ -58,6 +58,9 @@ struct BamArgs {
     int32_t has_pred;
     uint32_t flag_exclude, flag_require;
     int32_t min_mapq;
+    int32_t has_region;            // bam_region_filter: same reference and [start, end] intersects [lo, hi]
+    const int32_t *region_ref;     // per file: refID of the region's reference in that file's header (-2: absent)
+    int64_t lo, hi;
     int32_t serial;                // 1: one thread per FILE walks entries[first .. last] as a single chain
 };
 
@@ -111,6 +114,28 @@ __global__ void __launch_bounds__(kBamThreads) bam_walk_kernel(const __grid_cons
                 sel = (flag & a.flag_exclude) == 0u && (flag & a.flag_require) == a.flag_require;
                 // mapping_quality is a nullable string column: 255 is NULL and NULL fails every comparison
                 if (a.min_mapq >= 0) sel = sel && mq != 255u && (int32_t)mq >= a.min_mapq;
+            }
+            if (sel && a.has_region) {
+                // exon-bam/src/indexed_async_batch_stream.rs:66-86: reference, start and end must be present; start = pos + 1,
+                // end = start + (reference-consuming CIGAR length) - 1; intersects = lo <= end && start <= hi
+                const int32_t pos0 = (int32_t)win_u32(w, o + 8);
+                sel = ref_id >= 0 && ref_id == a.region_ref[E.file_idx] && pos0 >= 0 && (int64_t)pos0 + 1 <= a.hi;
+                if (sel) {
+                    const uint32_t l_read_name = win_u32(w, o + 12) & 0xFFu, n_cigar = win_u32(w, o + 16) & 0xFFFFu;
+                    const uint8_t *cg = E.base + p + 36 + l_read_name;
+                    if (p + 36 + l_read_name + 4ull * n_cigar > p + 4 + (uint64_t)(uint32_t)block_size) {
+                        bad = true;
+                        break;
+                    }
+                    int64_t span = 0;
+                    for (uint32_t i = 0; i < n_cigar; ++i) {
+                        const uint32_t v = (uint32_t)cg[4 * i] | ((uint32_t)cg[4 * i + 1] << 8) | ((uint32_t)cg[4 * i + 2] << 16) | ((uint32_t)cg[4 * i + 3] << 24);
+                        const uint32_t op = v & 15u;
+                        if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += v >> 4;  // M D N = X
+                    }
+                    const int64_t start = (int64_t)pos0 + 1, end = start + span - 1;
+                    sel = end >= 1 && a.lo <= end;
+                }
             }
             if (sel) {
                 const int g = remap[ref_id < 0 ? E.n_ref : ref_id];
@@ -237,7 +262,7 @@ int VcfStream::bam_build_tables() {
             e.remap0 = remap0;
             e.n_ref = (int32_t)f.ref_names.size();
             e.last_of_file = i + 1 == f.walk_starts.size();
-            e.pad_ = 0;
+            e.file_idx = (int32_t)(&f - &bam_files[0]);
             entries.push_back(e);
             if (i == 0) {
                 BamEntry s = e;
@@ -258,7 +283,8 @@ int VcfStream::bam_build_tables() {
     bam_o_exits = bam_o_remap + al(remap.size() * 4 + 4);
     bam_o_counts = bam_o_exits + al((entries.size() + 1) * 8);
     bam_o_misc = bam_o_counts + al((size_t)n_groups * 8);
-    const size_t need = bam_o_misc + 256;
+    bam_o_region = bam_o_misc + 256;
+    const size_t need = bam_o_region + al(bam_files.size() * 4 + 4);
     if (need > d_bam_cap) {
         if (d_bam) {
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -307,6 +333,21 @@ int VcfStream::bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, 
     a.flag_exclude = pred ? pred->flag_exclude : 0;
     a.flag_require = pred ? pred->flag_require : 0;
     a.min_mapq = pred ? pred->min_mapq : -1;
+    if (pred && pred->has_region) {
+        if (!pred->region_ref || pred->region_ref_len < 0) return fail(EXON_GPU_ERR_ARG, "bam_filter_count: region without a reference name");
+        const std::string want(pred->region_ref, (size_t)pred->region_ref_len);
+        std::vector<int32_t> ids;
+        for (const BamFile &f : bam_files) {
+            auto it = std::find(f.ref_names.begin(), f.ref_names.end(), want);
+            ids.push_back(it == f.ref_names.end() ? -2 : (int32_t)(it - f.ref_names.begin()));
+        }
+        CUDA_TRY(cudaMemcpyAsync(d + bam_o_region, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        a.has_region = 1;
+        a.region_ref = (const int32_t *)(d + bam_o_region);
+        a.lo = pred->region_lo < 1 ? 1 : pred->region_lo;
+        a.hi = pred->region_hi;
+    }
     unsigned int *d_verify = (unsigned int *)(d + bam_o_misc + 64);
     uint8_t *h = (uint8_t *)c->h_scratch;
     bool ok = false;

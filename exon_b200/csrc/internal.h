@@ -161,7 +161,7 @@ struct VcfStream {
     bool bam_tables_dirty = true;
     void *d_bam = nullptr;                // walk entries | per-file first entries | remap | exits | counts | misc
     size_t d_bam_cap = 0, bam_n_entries = 0, bam_n_firsts = 0;
-    size_t bam_o_firsts = 0, bam_o_remap = 0, bam_o_exits = 0, bam_o_counts = 0, bam_o_misc = 0;
+    size_t bam_o_firsts = 0, bam_o_remap = 0, bam_o_exits = 0, bam_o_counts = 0, bam_o_misc = 0, bam_o_region = 0;
     int32_t bam_n_groups = 1;
     int bam_build_tables();
     int bam_frame_file(uint8_t *dst, uint64_t total, const uint8_t *probe, size_t probe_len, const BgzfMember *members, size_t n_members);

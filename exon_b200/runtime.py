@@ -501,11 +501,19 @@ class BamStream:
         self._last_host = data
         check(self.lib.exon_gpu_bam_feed(self.handle, C.c_void_p(data.ctypes.data), data.size, int(is_last)))
 
-    def count_by_reference(self, *, flag_exclude: int = 0, flag_require: int = 0, min_mapq: int = -1, all_rows: bool = False):
+    def count_by_reference(self, *, flag_exclude: int = 0, flag_require: int = 0, min_mapq: int = -1, all_rows: bool = False,
+                           region=None):
         """({reference name | None: count}, rows scanned): SELECT reference, COUNT(*) ... GROUP BY reference."""
         n = C.c_int32()
         rows = C.c_int64()
-        pred = None if all_rows else _abi.BamPred(flag_exclude, flag_require, min_mapq, 0)
+        pred = None
+        if not all_rows:
+            pred = _abi.BamPred(flag_exclude, flag_require, min_mapq, 0, None, 0, 0, 1, _abi.INT64_MAX)
+            if region is not None:  # (reference name, lo, hi): bam_region_filter
+                name = region[0].encode()
+                pred.has_region, pred.region_ref, pred.region_ref_len = 1, name, len(name)
+                pred.region_lo = 1 if region[1] is None else int(region[1])
+                pred.region_hi = _abi.INT64_MAX if region[2] is None else int(region[2])
         pp = C.byref(pred) if pred is not None else None
         rc = self.lib.exon_gpu_bam_filter_count_by_reference(self.handle, pp, None, 0, C.byref(n), C.byref(rows))
         check(rc)

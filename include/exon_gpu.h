@@ -261,7 +261,15 @@ typedef struct {
     uint32_t flag_exclude;
     uint32_t flag_require;
     int32_t min_mapq;
+    /* bam_region_filter('name:lo-hi', reference, start, end) -- SemiLazyRecord::intersects,
+     * exon/exon-bam/src/indexed_async_batch_stream.rs:66-86: same reference (by NAME, looked up in every file's header) and
+     * [start, end] intersects [region_lo, region_hi] (1-based, inclusive; end = start + reference-consuming CIGAR length - 1);
+     * records without a reference or a position never match. */
+    int32_t has_region;
+    const char *region_ref;
+    int32_t region_ref_len;
     int32_t pad_;
+    int64_t region_lo, region_hi;
 } exon_gpu_bam_pred;
 /* SELECT reference, COUNT(*) ... GROUP BY reference over everything fed so far.  Groups are reference NAMES in
  * header order (first file first), followed by one group for the NULL reference (refID -1): counts[g] for

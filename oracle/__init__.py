@@ -341,7 +341,13 @@ class Bam:
             self._L.exo_bam_close(self._h)
             self._h = None
 
-    def count_by_reference(self, flag_exclude=0, flag_require=0, min_mapq=-1, all_rows=False):
+    def count_by_reference(self, flag_exclude=0, flag_require=0, min_mapq=-1, all_rows=False, region=None):
+        self._L.exo_bam_set_region.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int64]
+        if region is None:
+            self._L.exo_bam_set_region(self._h, None, 1, INT64_MAX)
+        else:
+            self._L.exo_bam_set_region(self._h, region[0].encode(), 1 if region[1] is None else region[1],
+                                       INT64_MAX if region[2] is None else region[2])
         counts = (C.c_int64 * (len(self.refs) + 1))()
         n = self._L.exo_bam_scan(self._h, int(not all_rows), flag_exclude, flag_require, min_mapq, counts, -1, None)
         if n < 0:

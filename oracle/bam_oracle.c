@@ -89,6 +89,19 @@ typedef struct {
 /* walks the record chain; returns the number of records, -1 on a truncated / malformed chain.  If row_index >= 0 the
  * fields of that record are stored in *row.  counts (n_ref + 1 entries, last = NULL reference) receives the filtered
  * per-reference counts when non-NULL. */
+/* region predicate state (bam_region_filter, exon-bam/src/indexed_async_batch_stream.rs:66-86): set before exo_bam_scan */
+static _Thread_local int32_t g_region_ref = -3; /* -3: no region; -2: reference absent from this file */
+static _Thread_local int64_t g_region_lo = 1, g_region_hi = INT64_MAX;
+void exo_bam_set_region(const exo_bam *b, const char *name, int64_t lo, int64_t hi) {
+    g_region_ref = -3;
+    if (!name) return;
+    g_region_ref = -2;
+    for (int32_t i = 0; i < b->n_ref; i++)
+        if (strcmp((const char *)b->ref_name[i], name) == 0) g_region_ref = i;
+    g_region_lo = lo < 1 ? 1 : lo;
+    g_region_hi = hi;
+}
+
 int64_t exo_bam_scan(const exo_bam *b, int32_t has_pred, uint32_t flag_exclude, uint32_t flag_require, int32_t min_mapq,
                      int64_t *counts, int64_t row_index, exo_bam_row *row) {
     int64_t p = b->records_at, n = 0;
@@ -107,6 +120,19 @@ int64_t exo_bam_scan(const exo_bam *b, int32_t has_pred, uint32_t flag_exclude, 
             if (has_pred) {
                 sel = (flag & flag_exclude) == 0 && (flag & flag_require) == flag_require;
                 if (min_mapq >= 0) sel = sel && mapq != 255 && (int32_t)mapq >= min_mapq;
+                if (sel && g_region_ref != -3) {
+                    sel = ref_id >= 0 && ref_id == g_region_ref && pos >= 0;
+                    if (sel) {
+                        const uint8_t *c = r + 32 + l_read_name;
+                        int64_t span = 0;
+                        for (uint32_t i = 0; i < n_cigar; i++) {
+                            const uint32_t v = (uint32_t)rd_i32(c + 4 * i), op = v & 15;
+                            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += v >> 4;
+                        }
+                        const int64_t start = (int64_t)pos + 1, end = start + span - 1;
+                        sel = end >= 1 && g_region_lo <= end && start <= g_region_hi; /* Interval::intersects */
+                    }
+                }
             }
             if (sel) counts[ref_id < 0 ? b->n_ref : ref_id]++;
         }

@@ -27,7 +27,12 @@ def test_first_row_and_counts():
     flags = [b.row(i)["flag"] for i in range(61)]
     assert sorted(set(flags)) == [83, 97, 145, 147, 595, 659, 2177]
     assert sum(b.count_by_reference(flag_exclude=0x904)[0].values()) == sum(1 for f in flags if not f & 0x904) == 60
+    # bam_region_filter('chr1:1-12209145', reference, start, end) -> 7 (slt/bam-indexed-select-tests.slt:11-14); two files -> 14 (:22-25)
+    assert sum(b.count_by_reference(region=("chr1", 1, 12209145))[0].values()) == 7
+    assert sum(b.count_by_reference(region=("chr1", None, None))[0].values()) == 61
+    assert sum(b.count_by_reference(region=("chr2", 1, 10**9))[0].values()) == 0
     b.close()
+    assert sum(oracle.bam_count_by_reference_files([fixture(), fixture()], region=("chr1", 1, 12209145))[0].values()) == 14
     assert oracle.bam_count_by_reference_files([fixture(), fixture()], all_rows=True)[1] == 122  # the bam-partition directory
 
 

@@ -36,6 +36,11 @@ def test_reference_fixture(gpu_ctx):
     for kw in PREDS:
         assert gpu(gpu_ctx, [data], **kw) == oracle.bam_count_by_reference_files([data], **kw), kw
     assert len(counts) == 196 and None in counts
+    # bam_region_filter goldens: slt/bam-indexed-select-tests.slt:11-14 (7), :22-25 (two files: 14)
+    assert sum(gpu(gpu_ctx, [data], region=("chr1", 1, 12209145))[0].values()) == 7
+    assert sum(gpu(gpu_ctx, [data, data], region=("chr1", 1, 12209145))[0].values()) == 14
+    for rg in [("chr1", None, None), ("chr1", 12203704, 12203704), ("chr1", 12217174, None), ("chr2", 1, 10**9), ("nope", 1, 5)]:
+        assert gpu(gpu_ctx, [data], region=rg) == oracle.bam_count_by_reference_files([data], region=rg), rg
 
 
 def test_synthetic(gpu_ctx):
@@ -50,6 +55,8 @@ def test_synthetic(gpu_ctx):
             assert rows == sh.n
             assert got == sh.truth(**{k: v for k, v in kw.items() if k != "all_rows"}), kw
         assert got == oracle.bam_count_by_reference_files(sh.files, **PREDS[-1])[0]
+        for kw in [dict(region=("7", 1_000_000, 2_000_000)), dict(region=("X", 500, 50_000_000), flag_exclude=0x904, min_mapq=30), dict(region=("MT", None, None))]:
+            assert s.count_by_reference(**kw) == oracle.bam_count_by_reference_files(sh.files, **kw), kw
     # ranges of one file arrive in pieces
     with gpu_ctx.open_bam() as s:
         f = np.frombuffer(sh.files[0], dtype=np.uint8)

@@ -156,5 +156,6 @@ def test_bam_counts(gpu_ctx, seed):
     with gpu_ctx.open_bam() as s:
         for f in files:
             s.feed(f)
-        for kw in [dict(all_rows=True), dict(flag_exclude=0x904, min_mapq=30), dict(flag_require=0x10), dict(min_mapq=0)]:
+        for kw in [dict(all_rows=True), dict(flag_exclude=0x904, min_mapq=30), dict(flag_require=0x10), dict(min_mapq=0),
+                   dict(region=("c0", int(rng.integers(1, 500000)), int(rng.integers(500000, 1000000)))), dict(region=("c3", None, None), flag_exclude=4)]:
             assert s.count_by_reference(**kw) == oracle.bam_count_by_reference_files(files, **kw), (seed, kw)
