@@ -32,7 +32,8 @@ SYMBOLS = [
     "exon_gpu_stream_close", "exon_gpu_stream_reset", "exon_gpu_stream_body_bytes", "exon_gpu_stream_feed_gzip", "exon_gpu_gzip_inflate", "exon_gpu_bam_open", "exon_gpu_bam_feed",
     "exon_gpu_bam_filter_count_by_reference", "exon_gpu_bam_group_name", "exon_gpu_allreduce_counts",
     "exon_gpu_mzml_open", "exon_gpu_mzml_feed", "exon_gpu_mzml_filter_sum", "exon_gpu_tabix_query", "exon_gpu_stream_feed_bgzf_chunk",
-    "exon_gpu_fasta_open", "exon_gpu_fasta_feed", "exon_gpu_fasta_rows",
+    "exon_gpu_fasta_open", "exon_gpu_fasta_feed", "exon_gpu_fasta_rows", "exon_gpu_gff_open", "exon_gpu_gff_feed",
+    "exon_gpu_gff_filter_count",
 ]
 
 
@@ -175,6 +176,9 @@ def load():
         "exon_gpu_fasta_open": [vp, C.POINTER(vp)],
         "exon_gpu_fasta_feed": [vp, vp, C.c_size_t, C.c_int, C.c_int],
         "exon_gpu_fasta_rows": [vp, C.POINTER(i64)],
+        "exon_gpu_gff_open": [vp, C.POINTER(vp)],
+        "exon_gpu_gff_feed": [vp, vp, C.c_size_t, C.c_int, C.c_int],
+        "exon_gpu_gff_filter_count": [vp, C.POINTER(Region), C.POINTER(i64)],
         "exon_gpu_stream_close": [vp],
         "exon_gpu_stream_reset": [vp],
         "exon_gpu_stream_body_bytes": [vp, C.POINTER(i64)],

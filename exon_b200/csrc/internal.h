@@ -84,7 +84,7 @@ struct Piece {
     bool starts_file;
 };
 
-enum StreamFormat { kFmtVcf = 0, kFmtFastq = 1, kFmtBam = 2, kFmtMzml = 3, kFmtFasta = 4 };
+enum StreamFormat { kFmtVcf = 0, kFmtFastq = 1, kFmtBam = 2, kFmtMzml = 3, kFmtFasta = 4, kFmtGff = 5 };
 
 struct VcfStream {
     int fmt = kFmtVcf;  // FASTQ streams share the arena / run / file-mark machinery; they have no header to skip
@@ -213,6 +213,9 @@ int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, i
 
 int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uint64_t *total_out);
 int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags);
+
+// defined in gff_scan.cu
+int gff_filter_count(VcfStream *s, const exon_gpu_region *region, int64_t *out_count, int64_t *out_rows);
 
 // defined in fasta_scan.cu
 int fasta_rows(VcfStream *s, int64_t *out_rows);

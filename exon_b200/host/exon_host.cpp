@@ -465,6 +465,7 @@ struct Executor {
         if (fn == "fastq_scan") check(exon_gpu_fastq_open(s.ctx_, nullptr, &st));
         else if (fn == "bam_scan") check(exon_gpu_bam_open(s.ctx_, &st));
         else if (fn == "fasta_scan") check(exon_gpu_fasta_open(s.ctx_, &st));
+        else if (fn == "gff_scan") check(exon_gpu_gff_open(s.ctx_, &st));
         else check(exon_gpu_mzml_open(s.ctx_, &st));
         int64_t n = 0;
         try {
@@ -475,6 +476,7 @@ struct Executor {
                 else if (file_gz) check(exon_gpu_stream_feed_gzip(st, bytes.data(), bytes.size(), 1));
                 else if (fn == "fastq_scan") check(exon_gpu_fastq_feed(st, bytes.data(), bytes.size(), 0, 1));
                 else if (fn == "fasta_scan") check(exon_gpu_fasta_feed(st, bytes.data(), bytes.size(), 0, 1));
+                else if (fn == "gff_scan") check(exon_gpu_gff_feed(st, bytes.data(), bytes.size(), 0, 1));
                 else check(exon_gpu_mzml_feed(st, bytes.data(), bytes.size(), 0, 1));
                 int64_t flushed = 0;
                 check(exon_gpu_stream_body_bytes(st, &flushed));
@@ -484,6 +486,8 @@ struct Executor {
                 check(exon_gpu_fastq_rows(st, &n));
             } else if (fn == "fasta_scan") {
                 check(exon_gpu_fasta_rows(st, &n));
+            } else if (fn == "gff_scan") {
+                check(exon_gpu_gff_filter_count(st, nullptr, &n));
             } else if (fn == "bam_scan") {
                 int32_t groups = 0;
                 check(exon_gpu_bam_filter_count_by_reference(st, nullptr, nullptr, 0, &groups, &n));
@@ -798,7 +802,7 @@ ResultSet ExonSession::sql(const std::string &query) {
             while (lx.sym(","));
             lx.expect_sym(")");
         }
-        if (src == "fastq_scan" || src == "bam_scan" || src == "mzml_scan" || src == "fasta_scan") {
+        if (src == "fastq_scan" || src == "bam_scan" || src == "mzml_scan" || src == "fasta_scan" || src == "gff_scan") {
             // FASTQ / BAM / mzML ScanFunctions (fastq/udtf.rs:49, bam/udtf.rs:55, mzml/udtf.rs:47): COUNT(*) runs on the GPU
             if (args.empty() || args[0].kind != Expr::Utf8)
                 throw ExonError(ExonError::Internal, "this function requires the path to be specified as the first argument");

@@ -122,6 +122,9 @@ class Context:
         check(self.lib.exon_gpu_tabix_query(self.handle, C.c_void_p(tbi.ctypes.data), tbi.size, C.byref(region), out, n.value, C.byref(n)))
         return [(int(out[i].start), int(out[i].end)) for i in range(n.value)]
 
+    def open_gff(self) -> "GffStream":
+        return GffStream(self)
+
     def open_fasta(self) -> "FastaStream":
         return FastaStream(self)
 
@@ -589,3 +592,31 @@ class FastaStream(MzmlStream):
         out = C.c_int64()
         check(self.lib.exon_gpu_fasta_rows(self.handle, C.byref(out)))
         return out.value
+
+
+class GffStream(FastaStream):
+    """exon_gpu_stream opened with exon_gpu_gff_open: COUNT(*) / gff_region_filter counts of GFF records."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.handle = C.c_void_p()
+        check(self.lib.exon_gpu_gff_open(ctx.handle, C.byref(self.handle)))
+
+    def feed(self, data, *, is_last: bool = True, device_ptr: int | None = None, nbytes: int | None = None):
+        if device_ptr is not None:
+            check(self.lib.exon_gpu_gff_feed(self.handle, C.c_void_p(device_ptr), int(nbytes), 1, int(is_last)))
+            return
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        self._last_host = data
+        check(self.lib.exon_gpu_gff_feed(self.handle, C.c_void_p(data.ctypes.data), data.size, 0, int(is_last)))
+
+    def filter_count(self, region: "_abi.Region | None" = None) -> int:
+        out = C.c_int64()
+        check(self.lib.exon_gpu_gff_filter_count(self.handle, C.byref(region) if region is not None else None, C.byref(out)))
+        return out.value
+
+    def rows(self) -> int:
+        return self.filter_count(None)

@@ -247,6 +247,15 @@ int exon_gpu_fasta_open(exon_gpu_ctx *ctx, exon_gpu_stream **out);
 int exon_gpu_fasta_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last);
 int exon_gpu_fasta_rows(exon_gpu_stream *s, int64_t *out_rows);
 
+/* ---- GFF partition stream ----------------------------------------------------------------------------------------- */
+/* GFFScan + BatchReader::{read_line, filter, read_batch} (exon/exon-gff/src/batch_reader.rs:56-130) under
+ * AggregateExec count(*).  region == NULL: COUNT(*) = record lines (directives "##" and comments "#" are skipped).
+ * region: gff_region_filter semantics -- seqname == region->chrom, and the interval (1-based, inclusive), if any,
+ * contains the record's START (batch_reader.rs:70-96).  Only the fields the predicate reads are validated. */
+int exon_gpu_gff_open(exon_gpu_ctx *ctx, exon_gpu_stream **out);
+int exon_gpu_gff_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last);
+int exon_gpu_gff_filter_count(exon_gpu_stream *s, const exon_gpu_region *region, int64_t *out_count);
+
 /* ---- BAM partition stream (BASELINE configs[3]) ---------------------------------------- */
 /* BAMScan::execute + BAMOpener::open + BatchReader (exon/exon-core/src/datasources/bam/scanner.rs:138,
  * bam/file_opener.rs:39, exon/exon-bam/src/batch_reader.rs:70-107).  Fed with the BGZF bytes of whole .bam files;

@@ -425,3 +425,19 @@ def fasta_count(data) -> int:
     if n < 0:
         raise ValueError("malformed FASTA")
     return int(n)
+
+
+def gff_filter_count(data, name=None, lo=None, hi=None):
+    """(count, rows): GFF records with seqname == name and lo <= start <= hi (None drops a term)."""
+    a = _buf(data)
+    L = lib()
+    L.exo_gff_filter_count.restype = C.c_int64
+    L.exo_gff_filter_count.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                       C.POINTER(C.c_int64)]
+    nb = name.encode() if isinstance(name, str) else (name or b"")
+    rows = C.c_int64()
+    c = L.exo_gff_filter_count(a.ctypes.data, a.size, nb, len(nb), int(name is not None), int(lo is not None or hi is not None),
+                               1 if lo is None else lo, INT64_MAX if hi is None else hi, C.byref(rows))
+    if c < 0:
+        raise ValueError("malformed GFF record")
+    return int(c), int(rows.value)

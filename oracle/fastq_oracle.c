@@ -273,3 +273,47 @@ int64_t exo_fasta_count(const uint8_t *text, int64_t len) {
     }
     return n;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * GFF record count with the reference's region filter.  exon-gff/src/batch_reader.rs:56-130: every line is a noodles-gff
+ * Line -- "##..." directive, "#..." comment, otherwise a record of 9 tab-separated fields (fewer is an error, as is an
+ * empty line); BatchReader::filter (:70-96) keeps a record when seqname == region name and, if the region has an
+ * interval, the interval contains the record's START (1-based, inclusive).  has_name / has_interval select the terms.
+ * Returns the selected count (*n_rows = all records), EXO_ERR_PARSE on a malformed record.
+ * Pinned by slt/gff-scan-tests.slt:80-92 (5000 / 10000 / gzip 5000) and its first row (sq0 caat 8 13).
+ * ------------------------------------------------------------------------------------------- */
+int64_t exo_gff_filter_count(const uint8_t *text, int64_t len, const uint8_t *name, int32_t name_len, int32_t has_name,
+                             int32_t has_interval, int64_t lo, int64_t hi, int64_t *n_rows) {
+    int64_t p = 0, rows = 0, count = 0;
+    while (p < len) {
+        const uint8_t *nl = (const uint8_t *)memchr(text + p, '\n', (size_t)(len - p));
+        const int64_t e = nl ? nl - text : len;
+        const uint8_t *s = text + p;
+        const int64_t n = e - p;
+        p = e + 1;
+        if (n == 0) return EXO_ERR_PARSE;
+        if (s[0] == '#') continue;
+        const uint8_t *f[10];
+        int nf = 0;
+        f[nf++] = s;
+        for (int64_t i = 0; i < n && nf < 10; i++)
+            if (s[i] == '\t') f[nf++] = s + i + 1;
+        if (nf < 9) return EXO_ERR_PARSE;
+        if (f[1] - 1 == f[0]) return EXO_ERR_PARSE; /* empty seqname */
+        int64_t start = 0;
+        const uint8_t *q = f[3];
+        if (q >= f[4] - 1) return EXO_ERR_PARSE;
+        for (; q < f[4] - 1; q++) {
+            if (*q < '0' || *q > '9') return EXO_ERR_PARSE;
+            start = start * 10 + (*q - '0');
+        }
+        if (start < 1) return EXO_ERR_PARSE;
+        rows++;
+        int sel = 1;
+        if (has_name) sel = (f[1] - 1 - f[0]) == name_len && memcmp(f[0], name, (size_t)name_len) == 0;
+        if (sel && has_interval) sel = start >= lo && start <= hi;
+        count += sel;
+    }
+    if (n_rows) *n_rows = rows;
+    return count;
+}

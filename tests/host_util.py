@@ -66,6 +66,10 @@ def build_datasources(root):
         d = os.path.join(root, "fasta-partition", f"sample={s}")
         os.makedirs(d)
         shutil.copy(os.path.join(GOLDEN, "test.fasta"), os.path.join(d, "test.fasta"))
+    os.makedirs(os.path.join(root, "gff"))
+    with gzip.open(os.path.join(GOLDEN, "test.gff.gz")) as f, open(os.path.join(root, "gff", "test.gff"), "wb") as o:
+        o.write(f.read())
+    shutil.copy(os.path.join(GOLDEN, "test.gff.gz"), os.path.join(root, "gff", "test.gff.gz"))
     os.makedirs(os.path.join(root, "two-vcf"))
     for n in ("a.vcf", "b.vcf"):
         shutil.copy(os.path.join(root, "vcf", "index.vcf"), os.path.join(root, "two-vcf", n))
