@@ -489,6 +489,8 @@ static int bgzf_parse_member(const uint8_t *data, size_t len, size_t p, BgzfMemb
     m->in_len = (uint32_t)(end - 8 - q);
     m->isize = (uint32_t)data[end - 4] | ((uint32_t)data[end - 3] << 8) | ((uint32_t)data[end - 2] << 16) | ((uint32_t)data[end - 1] << 24);
     m->out_addr = 0;
+    m->bm_off = 0;
+    m->pad_ = 0;
     if (bsize >= 0 && m->isize > 65536u) return fail(EXON_GPU_ERR_PARSE, "bgzf: member at byte %zu claims %u bytes (> 64 KiB)", p, m->isize);
     *next = end;
     return EXON_GPU_OK;
@@ -514,7 +516,7 @@ int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uin
 
 // Enqueues the inflate of `n_members` members (table in device memory; in_off relative to d_comp, out_addr absolute)
 // on the context's stream.  d_flags: two words of device scratch, {0, INT_MAX} before the launch.
-int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags) {
+int bgzf_inflate_launch_v1(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags) {
     if (n_members <= 0) return EXON_GPU_OK;
     static int occ = 0;
     if (!occ) {
@@ -706,10 +708,11 @@ int VcfStream::flush_gz() {
             d_gz_tab_cap = (tab_bytes + 256) * 2;
         }
         uint8_t *dt = (uint8_t *)d_gz_tab;
+        const size_t bm_words = bgzf_assign_bitmap(members.data(), members.size());
         CUDA_TRY(cudaMemcpyAsync(dt, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
         const int init_flags[2] = {0, 0x7FFFFFFF};
         CUDA_TRY(cudaMemcpyAsync(dt + tab_bytes, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
-        if (int rc = bgzf_inflate_launch(ctx, (const uint8_t *)d_gz, (const BgzfMember *)dt, (int)members.size(), (uint32_t *)(dt + tab_bytes)))
+        if (int rc = bgzf_inflate_launch(ctx, (const uint8_t *)d_gz, (const BgzfMember *)dt, (int)members.size(), (uint32_t *)(dt + tab_bytes), bm_words))
             return rc;
         // flags + per file: first bytes (header probe) and the last byte, all in one round trip
         if (int rc = ctx->ensure_scratch(0, 64 + files.size() * (kProbe + 16))) return rc;
@@ -801,12 +804,13 @@ extern "C" int exon_gpu_gzip_inflate(exon_gpu_ctx *c, const uint8_t *data, size_
     uint8_t *d_out = out_is_device ? out : scr + o_out;
     cudaStream_t st = c->stream;
     for (BgzfMember &m : members) m.out_addr += (uint64_t)reinterpret_cast<uintptr_t>(d_out);
+    const size_t bm_words = bgzf_assign_bitmap(members.data(), members.size());
     CUDA_TRY(cudaMemcpyAsync(scr, data, len, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(scr + o_tab, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
     const int init_flags[2] = {0, 0x7FFFFFFF};
     CUDA_TRY(cudaMemcpyAsync(scr + o_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaEventRecord(c->ev0, st));
-    if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), (uint32_t *)(scr + o_flags))) return rc;
+    if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), (uint32_t *)(scr + o_flags), bm_words)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     CUDA_TRY(cudaMemcpyAsync(c->h_scratch, scr + o_flags, 8, cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,583 @@
+// inflate.cu -- DEFLATE (RFC 1951) on the device as two kernels (the decompression in front of
+// every parser: noodles-bgzf 0.34 `Reader` / async-compression `GzipDecoder`, see bgzf.cu for the call sites).
+//
+// Huffman decoding is serial per stream and LZ77 copying is wide but ordered; one kernel that does both leaves the
+// lanes idle in turn (the round-1 first cut: 16 lanes per member, ~8 active threads per instruction).  Here the two
+// halves are separate kernels with the layout each one wants:
+//
+//   K_dec  inflate_decode_kernel   ONE LANE PER MEMBER, 32 members per warp in lock step.  Each lane runs the bit reader
+//          (two 32-bit words + one prefetched, peek = one funnel shift), builds its own primary tables in shared
+//          memory (lit/len 2^LB entries, distance 2^DB entries; longer codes fall back to a canonical walk over
+//          per-lane arrays in local memory), and writes
+//            * every LITERAL byte straight to its final place in the output, and
+//            * every MATCH as a 3-byte token (len - 3 | (dist - 1) << 8) INTO THE FIRST THREE BYTES OF THE MATCH'S OWN
+//              OUTPUT RANGE (a match is >= 3 bytes, so the token always fits and needs no memory of its own), plus
+//              one bit per match start in a bitmap (1 bit per output byte).
+//   K_copy inflate_copy_kernel     ONE WARP PER MEMBER.  Walks the output in 1 KiB segments kept in a 4 KiB shared-memory
+//          ring: loads the segment (literals in place), turns the segment's bitmap words into a list of match
+//          positions, reads all tokens at once (one lane per match), copies every match whose source lies wholly
+//          before the segment in parallel (one lane per match, source from the ring or, beyond 3 KiB back, from L2),
+//          executes the remaining (dependent) matches in order with all 32 lanes, and writes the finished segment
+//          back with 16-byte stores.  A match that crosses the segment end is continued in the next segment.
+//
+// Output is bit-exact DEFLATE; ISIZE of every member is checked, CRC32 is not.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace exon {
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? EXON_GPU_ERR_OOM : EXON_GPU_ERR_CUDA, "%s: %s", \
+                        #expr, cudaGetErrorString(_e));                                                  \
+    } while (0)
+
+namespace {
+
+constexpr uint32_t kInfErrData = 1u;  // invalid DEFLATE data
+constexpr uint32_t kInfErrSize = 2u;  // output does not match ISIZE
+
+// ------------------------------------------------------------------------------------------------------------------
+// K_dec
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDecWarps = 2;
+
+__constant__ uint8_t c_clen_order2[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// LSB-first bit reader: `lo` holds the current word, `hi` the next, `nxt` one more (loaded ahead so that its latency
+// is off the critical path).  0 <= bp < 32 always, so peek() returns 32 valid bits.
+struct LaneBits {
+    const uint32_t *wp;  // next word to load
+    const uint32_t *w0;  // aligned word the stream started in
+    uint32_t lo, hi, nxt;
+    int bp;
+    int mis8;
+    __device__ __forceinline__ void init(const uint8_t *p) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const int mis = (int)(a & 3);
+        w0 = reinterpret_cast<const uint32_t *>(a - mis);
+        lo = __ldg(w0);
+        hi = __ldg(w0 + 1);
+        nxt = __ldg(w0 + 2);
+        wp = w0 + 3;
+        bp = 8 * mis;
+        mis8 = 8 * mis;
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, bp); }
+    __device__ __forceinline__ void skip(int n) {  // n <= 32
+        bp += n;
+        if (bp >= 32) {
+            lo = hi;
+            hi = nxt;
+            nxt = __ldg(wp++);
+            bp -= 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t take(int n) {  // n <= 16
+        const uint32_t v = peek() & ((1u << n) - 1u);
+        skip(n);
+        return v;
+    }
+    __device__ __forceinline__ int64_t bits_consumed() const { return ((int64_t)(wp - 3 - w0) << 5) + bp - mis8; }
+    __device__ __forceinline__ const uint8_t *byte_ptr() const {  // only meaningful when bp % 8 == 0
+        return reinterpret_cast<const uint8_t *>(wp - 3) + (bp >> 3);
+    }
+};
+
+// per-lane canonical code description (local memory): used to build the primary table and to decode codes longer than it
+struct Canon {
+    uint16_t sym[288];
+    uint16_t cnt[16];
+};
+
+// Builds cnt / sym from lens[0..n) and fills the primary table tab[0 .. 1 << PB): entry = sym << 4 | len, 0 = longer code.
+// false on an over-subscribed code.
+__device__ bool canon_table(const uint8_t *lens, int n, int PB, uint16_t *tab, Canon &C) {
+    uint16_t offs[16], next[16];
+#pragma unroll
+    for (int l = 0; l < 16; ++l) C.cnt[l] = 0;
+    for (int s = 0; s < n; ++s) C.cnt[lens[s]]++;
+    C.cnt[0] = 0;
+    int left = 1;
+    uint32_t code = 0;
+    offs[0] = 0;
+    offs[1] = 0;
+    next[0] = 0;
+    for (int l = 1; l < 16; ++l) {
+        left <<= 1;
+        left -= C.cnt[l];
+        if (left < 0) return false;
+        next[l] = (uint16_t)code;
+        code = (code + C.cnt[l]) << 1;
+        if (l < 15) offs[l + 1] = (uint16_t)(offs[l] + C.cnt[l]);
+    }
+    uint32_t *t32 = reinterpret_cast<uint32_t *>(tab);
+    for (int i = 0; i < (1 << PB) / 2; ++i) t32[i] = 0u;
+    for (int s = 0; s < n; ++s) {
+        const int L = lens[s];
+        if (!L) continue;
+        C.sym[offs[L]++] = (uint16_t)s;
+        const uint32_t c = next[L]++;
+        if (L <= PB) {
+            const uint32_t rev = __brev(c) >> (32 - L);
+            const uint16_t e = (uint16_t)((s << 4) | L);
+            for (uint32_t i = rev; i < (1u << PB); i += (1u << L)) tab[i] = e;
+        }
+    }
+    return true;
+}
+
+// canonical decode of the code at bit 0 of `bits` (LSB first), lengths 1..15: sym | len << 16, or 0xFFFFFFFF
+__device__ __noinline__ uint32_t canon_walk(uint32_t bits, const Canon &C) {
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= 15; ++len) {
+        code |= (int)(bits & 1u);
+        bits >>= 1;
+        const int c = C.cnt[len];
+        if (code - c < first) return (uint32_t)C.sym[index + (code - first)] | ((uint32_t)len << 16);
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return 0xFFFFFFFFu;
+}
+
+template <int LB, int DB>
+struct LaneTabs {
+    uint16_t lit[1 << LB];
+    uint16_t dist[1 << DB];
+};
+
+template <int LB, int DB>
+__global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const uint8_t *comp, const BgzfMember *members, int n_members,
+                                                                        uint32_t *bitmap, uint32_t *flags, int *first_bad) {
+    extern __shared__ __align__(16) uint8_t dec_smem_raw[];
+    LaneTabs<LB, DB> &T = reinterpret_cast<LaneTabs<LB, DB> *>(dec_smem_raw)[threadIdx.x];
+    const int gt = blockIdx.x * (kDecWarps * 32) + threadIdx.x, nt = gridDim.x * (kDecWarps * 32);
+    Canon CL, CD;  // lit/len and distance codes of the current block
+    uint8_t lens[320];
+#pragma unroll 1
+    for (int mi = gt; mi < n_members; mi += nt) {
+        const BgzfMember M = members[mi];
+        if (M.isize == 0) continue;
+        uint8_t *out = reinterpret_cast<uint8_t *>((uintptr_t)M.out_addr);
+        const uint32_t isize = M.isize;
+        const uint32_t q0 = (uint32_t)(M.out_addr & 15u);
+        uint32_t *bm = bitmap + M.bm_off;
+        uint32_t bm_wi = 0, bm_w = 0;
+        LaneBits br;
+        br.init(comp + M.in_off);
+        const int64_t in_bits = (int64_t)M.in_len * 8;
+        uint32_t pos = 0, err = 0;
+        bool last = false;
+#pragma unroll 1
+        while (!last && !err) {
+            const uint32_t hdr = br.peek();
+            last = (hdr & 1u) != 0u;
+            const int btype = (int)((hdr >> 1) & 3u);
+            br.skip(3);
+            if (br.bits_consumed() > in_bits || btype == 3) {  // a stream that runs past its payload is corrupt
+                err = kInfErrData;
+                break;
+            }
+            if (btype == 0) {
+                br.skip((8 - (br.bp & 7)) & 7);
+                const uint32_t w = br.peek();
+                br.skip(32);
+                const uint32_t len = w & 0xFFFFu;
+                if ((len ^ (w >> 16)) != 0xFFFFu || pos + len > isize || br.bits_consumed() + (int64_t)len * 8 > in_bits) {
+                    err = kInfErrData;
+                    break;
+                }
+                const uint8_t *src = br.byte_ptr();
+                for (uint32_t j = 0; j < len; ++j) out[pos + j] = __ldg(src + j);
+                pos += len;
+                br.init(src + len);
+                continue;
+            }
+            if (btype == 1) {
+                for (int s = 0; s < 144; ++s) lens[s] = 8;
+                for (int s = 144; s < 256; ++s) lens[s] = 9;
+                for (int s = 256; s < 280; ++s) lens[s] = 7;
+                for (int s = 280; s < 288; ++s) lens[s] = 8;
+                for (int s = 0; s < 30; ++s) lens[288 + s] = 5;
+                lens[318] = lens[319] = 0;
+            } else {
+                const uint32_t h = br.peek();
+                br.skip(14);
+                const int nlit = (int)(h & 31u) + 257, ndist = (int)((h >> 5) & 31u) + 1, ncl = (int)((h >> 10) & 15u) + 4;
+                uint8_t cl[19];
+#pragma unroll
+                for (int i = 0; i < 19; ++i) cl[i] = 0;
+                for (int i = 0; i < ncl; ++i) cl[c_clen_order2[i]] = (uint8_t)br.take(3);
+                // the code-length code (7-bit codes at most) borrows the literal table's place and CL's arrays
+                if (nlit > 286 || ndist > 30 || !canon_table(cl, 19, 7, T.lit, CL)) {
+                    err = kInfErrData;
+                    break;
+                }
+                int i = 0;
+                const int total = nlit + ndist;
+                while (i < total) {
+                    const uint32_t e = T.lit[br.peek() & 127u];
+                    if (!e) {
+                        err = kInfErrData;
+                        break;
+                    }
+                    br.skip((int)(e & 15u));
+                    const int sym = (int)(e >> 4);
+                    if (sym < 16) {
+                        lens[i++] = (uint8_t)sym;
+                        continue;
+                    }
+                    int rep, val = 0;
+                    if (sym == 16) {
+                        if (i == 0) {
+                            err = kInfErrData;
+                            break;
+                        }
+                        val = lens[i - 1];
+                        rep = 3 + (int)br.take(2);
+                    } else if (sym == 17) {
+                        rep = 3 + (int)br.take(3);
+                    } else {
+                        rep = 11 + (int)br.take(7);
+                    }
+                    if (i + rep > total) {
+                        err = kInfErrData;
+                        break;
+                    }
+                    while (rep--) lens[i++] = (uint8_t)val;
+                }
+                if (err) break;
+                if (lens[256] == 0) {  // no end-of-block code
+                    err = kInfErrData;
+                    break;
+                }
+                // distance lengths follow the literal/length lengths: move them to a fixed place
+                uint8_t tmp[32];
+                for (int s = 0; s < 32; ++s) tmp[s] = s < ndist ? lens[nlit + s] : (uint8_t)0;
+                for (int s = nlit; s < 288; ++s) lens[s] = 0;
+                for (int s = 0; s < 32; ++s) lens[288 + s] = tmp[s];
+            }
+            // an incomplete distance code with a single symbol is legal (RFC 1951 3.2.7); over-subscription is not
+            if (!canon_table(lens, 288, LB, T.lit, CL) || !canon_table(lens + 288, 30, DB, T.dist, CD)) {
+                err = kInfErrData;
+                break;
+            }
+            // ---- symbols ----
+#pragma unroll 1
+            while (true) {
+                uint32_t w = br.peek();
+                uint32_t e = T.lit[w & ((1u << LB) - 1u)];
+                if (!e) {
+                    const uint32_t r = canon_walk(w, CL);
+                    if (r == 0xFFFFFFFFu) {
+                        err = kInfErrData;
+                        break;
+                    }
+                    e = ((r & 0xFFFFu) << 4) | (r >> 16);
+                }
+                const int clen = (int)(e & 15u);
+                const int sym = (int)(e >> 4);
+                if (sym < 256) {
+                    br.skip(clen);
+                    if (pos >= isize) {
+                        err = kInfErrData;
+                        break;
+                    }
+                    out[pos++] = (uint8_t)sym;
+                    continue;
+                }
+                if (sym == 256) {
+                    br.skip(clen);
+                    break;
+                }
+                const int ls = sym - 257;
+                if (ls >= 29) {
+                    err = kInfErrData;
+                    break;
+                }
+                // length base / extra bits in closed form (RFC 1951 3.2.5)
+                w >>= clen;
+                int lx = ls < 8 ? 0 : (ls - 4) >> 2;
+                uint32_t len = ls < 8 ? (uint32_t)(3 + ls) : (uint32_t)(3 + ((4 + (ls & 3)) << lx));
+                if (ls == 28) {
+                    lx = 0;
+                    len = 258;
+                }
+                len += w & ((1u << lx) - 1u);
+                br.skip(clen + lx);  // <= 15 + 5
+                w = br.peek();
+                e = T.dist[w & ((1u << DB) - 1u)];
+                if (!e) {
+                    const uint32_t r = canon_walk(w, CD);
+                    if (r == 0xFFFFFFFFu) {
+                        err = kInfErrData;
+                        break;
+                    }
+                    e = ((r & 0xFFFFu) << 4) | (r >> 16);
+                }
+                const int dlen = (int)(e & 15u);
+                const int ds = (int)(e >> 4);
+                if (ds >= 30) {
+                    err = kInfErrData;
+                    break;
+                }
+                w >>= dlen;
+                const int dx = ds < 4 ? 0 : (ds - 2) >> 1;
+                const uint32_t dist = (ds < 4 ? (uint32_t)(1 + ds) : (uint32_t)(1 + ((2 + (ds & 1)) << dx))) + (w & ((1u << dx) - 1u));
+                br.skip(dlen + dx);  // <= 15 + 13
+                if (dist > pos || pos + len > isize) {
+                    err = kInfErrData;
+                    break;
+                }
+                // the token goes where the match will be, its start is marked in the bitmap
+                const uint32_t tok = (len - 3u) | ((dist - 1u) << 8);
+                out[pos] = (uint8_t)tok;
+                out[pos + 1] = (uint8_t)(tok >> 8);
+                out[pos + 2] = (uint8_t)(tok >> 16);
+                const uint32_t q = q0 + pos, wi = q >> 5;
+                if (wi != bm_wi) {
+                    if (bm_w) bm[bm_wi] = bm_w;
+                    bm_wi = wi;
+                    bm_w = 0;
+                }
+                bm_w |= 1u << (q & 31u);
+                pos += len;
+            }
+            if (!err && br.bits_consumed() > in_bits) err = kInfErrData;
+        }
+        if (bm_w) bm[bm_wi] = bm_w;
+        if (!err && pos != isize) err = kInfErrSize;
+        if (err) {
+            atomicOr(flags, err);
+            atomicMin(first_bad, mi);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K_copy
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kCopyWarps = 4;
+constexpr uint32_t kSeg = 1024;
+constexpr uint32_t kRingBytes = 4096;
+constexpr uint32_t kRingMask = kRingBytes - 1;
+constexpr int kMaxMatches = 352;  // matches that can start inside one segment (1024 / 3, rounded up)
+
+struct CopySmem {
+    __align__(16) uint8_t ring[kRingBytes];  // ring[q & kRingMask] = output byte q (q counted from the member's 16-byte aligned origin)
+    uint32_t mtok[kMaxMatches];              // ordered phase: bytes inside the segment | dist << 9; 0 = already copied
+    uint16_t mpos[kMaxMatches];              // match start inside the segment
+};
+
+__global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const BgzfMember *members, int n_members, const uint32_t *bitmap) {
+    __shared__ CopySmem smem_all[kCopyWarps];
+    CopySmem &S = smem_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * kCopyWarps + (threadIdx.x >> 5), nw = gridDim.x * kCopyWarps;
+#pragma unroll 1
+    for (int mi = gw; mi < n_members; mi += nw) {
+        const BgzfMember M = members[mi];
+        if (M.isize == 0) continue;
+        const uint32_t q0 = (uint32_t)(M.out_addr & 15u);
+        uint8_t *O = reinterpret_cast<uint8_t *>((uintptr_t)(M.out_addr - q0));
+        const uint32_t qend = q0 + M.isize;
+        const uint32_t *bm = bitmap + M.bm_off;
+        const uint32_t nseg = (qend + kSeg - 1) / kSeg;
+        uint32_t carry_len = 0, carry_dist = 0;
+#pragma unroll 1
+        for (uint32_t s = 0; s < nseg; ++s) {
+            const uint32_t segq = s * kSeg;
+            const uint32_t lq = segq + 32u * (uint32_t)lane;
+            // 1. the segment as K_dec left it (literals final, match ranges hold tokens / garbage)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t uq = lq + 16u * h;
+                if (uq < qend) *reinterpret_cast<uint4 *>(&S.ring[uq & kRingMask]) = __ldcg(reinterpret_cast<const uint4 *>(O + uq));
+            }
+            // 2. match starts of the segment
+            const uint32_t w = lq < qend ? __ldg(bm + (lq >> 5)) : 0u;
+            const int c = __popc(w);
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const int n_match = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if (n_match == 0 && carry_len == 0) {
+                __syncwarp();
+                continue;  // literals only: already final in global memory, the ring keeps them as history
+            }
+            {
+                uint32_t ww = w;
+                int i = incl - c;
+                while (ww) {
+                    S.mpos[i++] = (uint16_t)(32 * lane + __ffs((int)ww) - 1);
+                    ww &= ww - 1u;
+                }
+            }
+            __syncwarp();
+            // 3. tokens, one lane per match; matches whose source ends before the segment are copied right away
+            const uint32_t ring_lo = segq > (kRingBytes - kSeg) ? segq - (kRingBytes - kSeg) : 0u;
+            uint32_t spill_len = 0, spill_dist = 0;
+            for (int k = lane; k < n_match; k += 32) {
+                const uint32_t p = S.mpos[k], q = segq + p;
+                uint32_t b0, b1, b2;
+                if (p + 2 < kSeg) {
+                    b0 = S.ring[q & kRingMask];
+                    b1 = S.ring[(q + 1) & kRingMask];
+                    b2 = S.ring[(q + 2) & kRingMask];
+                } else {
+                    b0 = __ldcg(O + q);
+                    b1 = __ldcg(O + q + 1);
+                    b2 = __ldcg(O + q + 2);
+                }
+                const uint32_t len = b0 + 3u, dist = (b1 | (b2 << 8)) + 1u;
+                const uint32_t lseg = min(len, kSeg - p);
+                if (len > lseg) {
+                    spill_len = len - lseg;
+                    spill_dist = dist;
+                }
+                const uint32_t src = q - dist;
+                if (src + lseg <= segq) {
+                    for (uint32_t j = 0; j < lseg; ++j) {
+                        const uint32_t sq = src + j;
+                        const uint8_t b = sq >= ring_lo ? S.ring[sq & kRingMask] : __ldcg(O + sq);
+                        S.ring[(q + j) & kRingMask] = b;
+                    }
+                    S.mtok[k] = 0u;
+                } else {
+                    S.mtok[k] = lseg | (dist << 9);
+                }
+            }
+            __syncwarp();
+            // 4. the rest in output order, all lanes on one match
+            if (carry_len) {
+                const uint32_t src = segq - carry_dist;
+                for (uint32_t j = lane; j < carry_len; j += 32) {  // the only ordered copy whose source may lie behind the ring
+                    const uint32_t sq = src + (carry_dist >= carry_len ? j : j % carry_dist);
+                    S.ring[(segq + j) & kRingMask] = sq >= ring_lo ? S.ring[sq & kRingMask] : __ldcg(O + sq);
+                }
+                __syncwarp();
+            }
+#pragma unroll 1
+            for (int k = 0; k < n_match; ++k) {
+                const uint32_t t = S.mtok[k];
+                if (!t) continue;
+                const uint32_t q = segq + S.mpos[k], len = t & 511u, dist = t >> 9, src = q - dist;
+                for (uint32_t j = lane; j < len; j += 32) {
+                    const uint32_t sj = dist >= len ? j : j % dist;
+                    S.ring[(q + j) & kRingMask] = S.ring[(src + sj) & kRingMask];
+                }
+                __syncwarp();
+            }
+            // the spill of this segment's last match, if any (at most one lane has it)
+            const uint32_t sp = __ballot_sync(0xFFFFFFFFu, spill_len != 0u);
+            carry_len = 0;
+            if (sp) {
+                const int owner = __ffs((int)sp) - 1;
+                carry_len = __shfl_sync(0xFFFFFFFFu, spill_len, owner);
+                carry_dist = __shfl_sync(0xFFFFFFFFu, spill_dist, owner);
+            }
+            // 5. the finished segment back to global memory
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t uq = lq + 16u * h;
+                if (uq >= qend) continue;
+                if (uq >= q0 && uq + 16u <= qend) {
+                    __stcg(reinterpret_cast<uint4 *>(O + uq), *reinterpret_cast<const uint4 *>(&S.ring[uq & kRingMask]));
+                } else {
+                    const uint32_t a = max(uq, q0), b = min(uq + 16u, qend);
+                    for (uint32_t x = a; x < b; ++x) __stcg(O + x, S.ring[x & kRingMask]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int LB, int DB>
+int launch_decode(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_bitmap, uint32_t *d_flags) {
+    static int occ = 0;
+    constexpr size_t smem = sizeof(LaneTabs<LB, DB>) * kDecWarps * 32;
+    if (!occ) {
+        CUDA_TRY(cudaFuncSetAttribute(inflate_decode_kernel<LB, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inflate_decode_kernel<LB, DB>, kDecWarps * 32, smem));
+        if (occ < 1) occ = 1;
+    }
+    const int per_cta = kDecWarps * 32;
+    const int grid = std::min((n_members + per_cta - 1) / per_cta, occ * c->sm_count);
+    inflate_decode_kernel<LB, DB><<<grid, per_cta, smem, c->stream>>>(d_comp, d_table, n_members, d_bitmap, d_flags, (int *)(d_flags + 1));
+    c->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return EXON_GPU_OK;
+}
+
+}  // namespace
+
+// Gives every member its place in the match bitmap (1 bit per output byte, counted from the member's 16-byte aligned
+// origin, whole 32-bit words per member); returns the number of words.
+size_t bgzf_assign_bitmap(BgzfMember *m, size_t n) {
+    size_t words = 0;
+    for (size_t i = 0; i < n; ++i) {
+        m[i].bm_off = (uint32_t)words;
+        m[i].pad_ = 0;
+        if (m[i].isize) words += ((size_t)(m[i].out_addr & 15u) + m[i].isize + 31) / 32;
+    }
+    return words;
+}
+
+// Enqueues the inflate of `n_members` members (table in device memory; in_off relative to d_comp, out_addr absolute,
+// bm_off from bgzf_assign_bitmap) on the context's stream.  d_flags: two words of device scratch, {0, INT_MAX} before
+// the launch.
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words) {
+    if (n_members <= 0) return EXON_GPU_OK;
+    static const int use_v1 = [] {
+        const char *e = getenv("EXON_GPU_INFLATE_V1");
+        return e && atoi(e) ? 1 : 0;
+    }();
+    if (use_v1) return bgzf_inflate_launch_v1(c, d_comp, d_table, n_members, d_flags);
+    const size_t bm_bytes = (bitmap_words + 64) * sizeof(uint32_t);
+    if (bm_bytes > c->inf_bitmap_cap) {
+        if (c->inf_bitmap) {
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            CUDA_TRY(cudaFree(c->inf_bitmap));
+            c->inf_bitmap = nullptr;
+            c->inf_bitmap_cap = 0;
+        }
+        const size_t cap = bm_bytes + bm_bytes / 4;
+        CUDA_TRY(cudaMalloc(&c->inf_bitmap, cap));
+        c->inf_bitmap_cap = cap;
+    }
+    uint32_t *bm = (uint32_t *)c->inf_bitmap;
+    CUDA_TRY(cudaMemsetAsync(bm, 0, bm_bytes, c->stream));
+    static const int small_tabs = [] {
+        const char *e = getenv("EXON_GPU_INFLATE_TABLES");
+        return e && atoi(e) == 8 ? 1 : 0;
+    }();
+    if (small_tabs) {
+        if (int rc = launch_decode<8, 6>(c, d_comp, d_table, n_members, bm, d_flags)) return rc;
+    } else {
+        if (int rc = launch_decode<9, 7>(c, d_comp, d_table, n_members, bm, d_flags)) return rc;
+    }
+    static int occ = 0;
+    if (!occ) {
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inflate_copy_kernel, kCopyWarps * 32, 0));
+        if (occ < 1) occ = 1;
+    }
+    const int grid = std::min((n_members + kCopyWarps - 1) / kCopyWarps, occ * c->sm_count);
+    inflate_copy_kernel<<<grid, kCopyWarps * 32, 0, c->stream>>>(d_table, n_members, bm);
+    c->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return EXON_GPU_OK;
+}
+
+}  // namespace exon

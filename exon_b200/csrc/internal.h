@@ -40,6 +40,8 @@ struct Ctx {
     size_t h_scratch_cap = 0;
     void *scratch_b = nullptr;  // second device scratch area (K2 keeps per-row temporaries here while `scratch` holds tile tables)
     size_t scratch_b_cap = 0;
+    void *inf_bitmap = nullptr;  // inflate.cu: one bit per output byte of the launch in flight (match starts)
+    size_t inf_bitmap_cap = 0;
     // NCCL (dlopen'ed lazily; see nccl.cu)
     void *nccl_comm = nullptr;
     int nccl_ranks = 0;
@@ -75,6 +77,8 @@ struct BgzfMember {
     uint32_t in_len;   // payload bytes
     uint32_t isize;    // uncompressed bytes (gzip trailer)
     uint64_t out_addr; // bgzf_walk: byte offset in the uncompressed stream; at launch: absolute device address of the member's output
+    uint32_t bm_off;   // bgzf_assign_bitmap: first word of the member's match bitmap (inflate.cu)
+    uint32_t pad_;
 };
 
 // One piece of a run that belongs to a single file (runs are cut at the recorded file ends).
@@ -212,7 +216,9 @@ int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, i
                             unsigned long long *d_out, bool timed);
 
 int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uint64_t *total_out);
-int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags);
+size_t bgzf_assign_bitmap(BgzfMember *m, size_t n);
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words);
+int bgzf_inflate_launch_v1(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags);
 
 // defined in gff_scan.cu
 int gff_filter_count(VcfStream *s, const exon_gpu_region *region, int64_t *out_count, int64_t *out_rows);
