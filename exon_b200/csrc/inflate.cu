@@ -51,6 +51,8 @@ __constant__ uint8_t c_clen_order2[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 
 
 // LSB-first bit reader: `lo` holds the current word, `hi` the next, `nxt` one more (loaded ahead so that its latency
 // is off the critical path).  0 <= bp < 32 always, so peek() returns 32 valid bits.
+__device__ __forceinline__ void prefetch_line(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct LaneBits {
     const uint32_t *wp;  // next word to load
     const uint32_t *w0;  // aligned word the stream started in
@@ -67,6 +69,8 @@ struct LaneBits {
         wp = w0 + 3;
         bp = 8 * mis;
         mis8 = 8 * mis;
+        prefetch_line(w0 + 32);
+        prefetch_line(w0 + 64);
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, bp); }
     __device__ __forceinline__ void skip(int n) {  // n <= 32
@@ -76,6 +80,8 @@ struct LaneBits {
             hi = nxt;
             nxt = __ldg(wp++);
             bp -= 32;
+            // every lane streams its own member: without this, some lane of the warp misses L1 at almost every refill
+            if ((reinterpret_cast<uintptr_t>(wp) & 127u) == 0) prefetch_line(wp + 32);
         }
     }
     __device__ __forceinline__ uint32_t take(int n) {  // n <= 16
@@ -93,6 +99,8 @@ struct LaneBits {
 struct Canon {
     uint16_t sym[288];
     uint16_t cnt[16];
+    uint16_t lim[16];  // (first code of length L + cnt[L]) << (15 - L): a 15-bit MSB-first prefix below it has length <= L
+    int16_t off[16];   // index of the first symbol of length L in sym[] - first code of length L
 };
 
 // Builds cnt / sym from lens[0..n) and fills the primary table tab[0 .. 1 << PB): entry = sym << 4 | len, 0 = longer code.
@@ -113,6 +121,8 @@ __device__ bool canon_table(const uint8_t *lens, int n, int PB, uint16_t *tab, C
         left -= C.cnt[l];
         if (left < 0) return false;
         next[l] = (uint16_t)code;
+        C.lim[l] = (uint16_t)((code + C.cnt[l]) << (15 - l));
+        C.off[l] = (int16_t)((int)offs[l] - (int)code);
         code = (code + C.cnt[l]) << 1;
         if (l < 15) offs[l + 1] = (uint16_t)(offs[l] + C.cnt[l]);
     }
@@ -132,19 +142,14 @@ __device__ bool canon_table(const uint8_t *lens, int n, int PB, uint16_t *tab, C
     return true;
 }
 
-// canonical decode of the code at bit 0 of `bits` (LSB first), lengths 1..15: sym | len << 16, or 0xFFFFFFFF
-__device__ __noinline__ uint32_t canon_walk(uint32_t bits, const Canon &C) {
-    int code = 0, first = 0, index = 0;
-    for (int len = 1; len <= 15; ++len) {
-        code |= (int)(bits & 1u);
-        bits >>= 1;
-        const int c = C.cnt[len];
-        if (code - c < first) return (uint32_t)C.sym[index + (code - first)] | ((uint32_t)len << 16);
-        index += c;
-        first += c;
-        first <<= 1;
-        code <<= 1;
-    }
+// The code at bit 0 of `bits` (LSB first) is longer than PB bits: canonical decode from length PB + 1 on its 15-bit
+// MSB-first prefix.  sym | len << 16, or 0xFFFFFFFF when no code matches.
+template <int PB>
+__device__ __forceinline__ uint32_t canon_long(uint32_t bits, const Canon &C) {
+    const uint32_t c15 = __brev(bits) >> 17;
+#pragma unroll
+    for (int len = PB + 1; len <= 15; ++len)
+        if (c15 < C.lim[len]) return (uint32_t)C.sym[(int)C.off[len] + (int)(c15 >> (15 - len))] | ((uint32_t)len << 16);
     return 0xFFFFFFFFu;
 }
 
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                 uint32_t w = br.peek();
                 uint32_t e = T.lit[w & ((1u << LB) - 1u)];
                 if (!e) {
-                    const uint32_t r = canon_walk(w, CL);
+                    const uint32_t r = canon_long<LB>(w, CL);
                     if (r == 0xFFFFFFFFu) {
                         err = kInfErrData;
                         break;
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                 w = br.peek();
                 e = T.dist[w & ((1u << DB) - 1u)];
                 if (!e) {
-                    const uint32_t r = canon_walk(w, CD);
+                    const uint32_t r = canon_long<DB>(w, CD);
                     if (r == 0xFFFFFFFFu) {
                         err = kInfErrData;
                         break;
@@ -559,15 +564,18 @@ int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table
     }
     uint32_t *bm = (uint32_t *)c->inf_bitmap;
     CUDA_TRY(cudaMemsetAsync(bm, 0, bm_bytes, c->stream));
-    static const int small_tabs = [] {
+    static const int tabs = [] {
         const char *e = getenv("EXON_GPU_INFLATE_TABLES");
-        return e && atoi(e) == 8 ? 1 : 0;
+        return e ? atoi(e) : 86;
     }();
-    if (small_tabs) {
-        if (int rc = launch_decode<8, 6>(c, d_comp, d_table, n_members, bm, d_flags)) return rc;
-    } else {
-        if (int rc = launch_decode<9, 7>(c, d_comp, d_table, n_members, bm, d_flags)) return rc;
+    int rc;
+    switch (tabs) {
+        case 86: rc = launch_decode<8, 6>(c, d_comp, d_table, n_members, bm, d_flags); break;
+        case 87: rc = launch_decode<8, 7>(c, d_comp, d_table, n_members, bm, d_flags); break;
+        case 96: rc = launch_decode<9, 6>(c, d_comp, d_table, n_members, bm, d_flags); break;
+        default: rc = launch_decode<9, 7>(c, d_comp, d_table, n_members, bm, d_flags); break;
     }
+    if (rc) return rc;
     static int occ = 0;
     if (!occ) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inflate_copy_kernel, kCopyWarps * 32, 0));
