@@ -224,12 +224,18 @@ int exon_gpu_vcf_open(exon_gpu_ctx *c, const exon_gpu_vcf_opts *o, exon_gpu_stre
                 return fail(EXON_GPU_ERR_ARG, "vcf_open: projection index %d is not a VCF file-schema column",
                             o->projection[i]);
             }
-            if (o->projection[i] > 1) {
+            if (o->projection[i] > 6) {
                 delete s;
                 return fail(EXON_GPU_ERR_UNSUPPORTED,
-                            "vcf_open: column %d is not built on the GPU yet (supported: 0 chrom, 1 pos)",
-                            o->projection[i]);
+                            "vcf_open: column %d (%s) is re-serialised by the reference builder and is not built on the GPU yet "
+                            "(supported: 0 chrom, 1 pos, 2 id, 3 ref, 4 alt, 5 qual, 6 filter)",
+                            o->projection[i], o->projection[i] == 7 ? "info" : "formats");
             }
+            for (int j = 0; j < i; ++j)
+                if (o->projection[j] == o->projection[i]) {
+                    delete s;
+                    return fail(EXON_GPU_ERR_ARG, "vcf_open: column %d is projected twice", o->projection[i]);
+                }
             s->projection.push_back(o->projection[i]);
         }
         s->columns_on_device = o->columns_on_device != 0;

@@ -928,6 +928,95 @@ int fq_build_columns(VcfStream *s) {
 
 }  // namespace
 
+// Line index of a whole resident partition (steps 1 and 2 above, shared with the wide VCF column build in vcf_wide.cu):
+// line_start[i] / line_end[i] for every line in feed order (line_end points at the '\n', or at the end of a file whose last
+// line has none), the first line of every file, and `extra_per_line * (n_lines + 1) + extra_fixed` bytes of scratch_b
+// behind the two tables for the caller's per-row temporaries.  The caller holds ctx->work_mu.
+int build_line_index(VcfStream *s, size_t extra_per_line, size_t extra_fixed, LineIndex *out) {
+    Ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    out->n_lines = 0;
+    out->file_line0.assign(1, 0);
+    std::vector<Piece> pieces;
+    s->cut_pieces(pieces);
+    if (pieces.empty()) return EXON_GPU_OK;
+    std::vector<ScanSeg> h_segs;
+    std::vector<long long> file_tiles;
+    int64_t n_tiles = 0;
+    for (const Piece &p : pieces) {
+        ScanSeg sg;
+        sg.skip = (int32_t)((uintptr_t)p.base & 15);
+        sg.base = p.base - sg.skip;
+        sg.len = p.len;
+        sg.tile0 = n_tiles;
+        sg.pad_ = 0;
+        if (p.starts_file || h_segs.empty()) file_tiles.push_back(n_tiles);
+        n_tiles += (sg.skip + p.len + FqRing::TILE - 1) / FqRing::TILE;
+        h_segs.push_back(sg);
+    }
+    ScanSeg sentinel;
+    memset(&sentinel, 0, sizeof(sentinel));
+    sentinel.tile0 = n_tiles;
+    h_segs.push_back(sentinel);
+    file_tiles.push_back(n_tiles);
+    size_t cub_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)(n_tiles + 1), st));
+    const size_t o_segs = 0, o_lines = o_segs + al256(h_segs.size() * sizeof(ScanSeg)), o_prefix = o_lines + al256((size_t)(n_tiles + 1) * 8),
+                 o_cub = o_prefix + al256((size_t)(n_tiles + 1) * 8), o_ft = o_cub + al256(cub_bytes), o_fp = o_ft + al256(file_tiles.size() * 8),
+                 o_end = o_fp + al256(file_tiles.size() * 8);
+    if (int rc = ctx->ensure_scratch(o_end + 256, file_tiles.size() * 8 + 64)) return rc;
+    uint8_t *scr = (uint8_t *)ctx->scratch;
+    CUDA_TRY(cudaMemcpyAsync(scr + o_segs, h_segs.data(), h_segs.size() * sizeof(ScanSeg), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(scr + o_ft, file_tiles.data(), file_tiles.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(scr + o_lines + (size_t)n_tiles * 8, 0, 8, st));
+    FqArgs a;
+    memset(&a, 0, sizeof(a));
+    a.segs = (const ScanSeg *)(scr + o_segs);
+    a.n_segs = (int32_t)h_segs.size() - 1;
+    a.n_tiles = n_tiles;
+    a.tile_lines = (unsigned long long *)(scr + o_lines);
+    a.tile_prefix = (const unsigned long long *)(scr + o_prefix);
+    static int occ_a = 0, occ_i = 0;
+    CUDA_TRY(fq_launch(fq_lines_kernel, a, ctx->sm_count, st, &occ_a));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(scr + o_cub, cub_bytes, a.tile_lines, (unsigned long long *)(scr + o_prefix), (int)(n_tiles + 1), st));
+    fq_gather_u64<<<(unsigned)((file_tiles.size() + 127) / 128), 128, 0, st>>>(a.tile_prefix, (const long long *)(scr + o_ft), (int)file_tiles.size(),
+                                                                               (unsigned long long *)(scr + o_fp));
+    ctx->launches.fetch_add(3);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long *h_fp = (unsigned long long *)ctx->h_scratch;
+    CUDA_TRY(cudaMemcpyAsync(h_fp, scr + o_fp, file_tiles.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    out->file_line0.clear();
+    for (size_t f = 0; f < file_tiles.size(); ++f) out->file_line0.push_back((long long)h_fp[f]);
+    const long long n_lines = out->file_line0.back();
+    out->n_lines = n_lines;
+    if (n_lines == 0) return EXON_GPU_OK;
+    const size_t tab = al256((size_t)(n_lines + 1) * 8);
+    if (int rc = ctx->ensure_scratch_b(2 * tab + extra_per_line * (size_t)(n_lines + 1) + extra_fixed + 256)) return rc;
+    uint8_t *scb = (uint8_t *)ctx->scratch_b;
+    FqIndexArgs ia;
+    ia.segs = a.segs;
+    ia.n_tiles = n_tiles;
+    ia.tile_prefix = a.tile_prefix;
+    ia.line_start = (const uint8_t **)scb;
+    ia.line_end = (const uint8_t **)(scb + tab);
+    constexpr size_t smem = FqRing::smem_bytes;
+    if (!occ_i) {
+        CUDA_TRY(cudaFuncSetAttribute(fq_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_i, fq_index_kernel, FqRing::WARPS * 32, smem));
+        if (occ_i < 1) occ_i = 1;
+    }
+    int64_t grid = std::min<int64_t>((int64_t)occ_i * ctx->sm_count, (n_tiles + FqRing::WARPS - 1) / FqRing::WARPS);
+    if (grid < 1) grid = 1;
+    fq_index_kernel<<<(unsigned)grid, FqRing::WARPS * 32, smem, st>>>(ia);
+    ctx->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    out->line_start = ia.line_start;
+    out->line_end = ia.line_end;
+    out->extra = scb + 2 * tab;
+    return EXON_GPU_OK;
+}
+
 int fastq_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     if (!s->fq_cols) {
         if (int rc = s->flush_gz()) return rc;

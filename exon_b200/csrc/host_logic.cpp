@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/exon_gpu.h"
+#include "f32_parse.cuh"
 
 namespace exon {
 int fail(int code, const char *fmt, ...);
@@ -109,6 +110,16 @@ int exon_gpu_regroup_files_by_size(const int64_t *sizes, int32_t n_files, int32_
     const int32_t parts = std::min(target_partitions, n_files);
     for (int32_t i = 0; i < n_files; ++i) out_partition[order[(size_t)i]] = i % parts;
     *out_n_partitions = parts;
+    return EXON_GPU_OK;
+}
+
+// Rust f32::from_str as applied to QUAL (exon/exon-vcf/src/array_builder/lazy_array_builder.rs:205-208); f32_parse.cuh.
+int exon_gpu_parse_f32(const char *s, size_t len, float *out) {
+    if (!s || !out) return fail(EXON_GPU_ERR_ARG, "parse_f32: NULL argument");
+    if (len > 4096) return fail(EXON_GPU_ERR_UNSUPPORTED, "parse_f32: literal longer than 4096 bytes");
+    const int rc = parse_f32_rust(reinterpret_cast<const uint8_t *>(s), (int)len, out);
+    if (rc == kF32Malformed) return fail(EXON_GPU_ERR_PARSE, "parse_f32: invalid float literal '%.*s'", (int)len, s);
+    if (rc == kF32Unsupported) return fail(EXON_GPU_ERR_UNSUPPORTED, "parse_f32: more than 36 significant digits in '%.*s'", (int)len, s);
     return EXON_GPU_OK;
 }
 

@@ -234,6 +234,29 @@ void fq_columns_free(VcfStream *s);
 int fastq_next_batch(VcfStream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count, int64_t *out_rows);
 
+// Line index of a resident partition (fastq_scan.cu), used by the FASTQ and the wide VCF column builds.
+struct LineIndex {
+    const uint8_t **line_start = nullptr;  // device (scratch_b), n_lines + 1 entries
+    const uint8_t **line_end = nullptr;
+    int64_t n_lines = 0;
+    std::vector<long long> file_line0;  // first line of every file in feed order, then n_lines
+    uint8_t *extra = nullptr;           // caller's share of scratch_b
+};
+int build_line_index(VcfStream *s, size_t extra_per_line, size_t extra_fixed, LineIndex *out);
+
+// defined in vcf_wide.cu: VCF columns 2..6 (id, ref, alt, qual, filter)
+struct WideStore;
+struct WideChildSlot {
+    ArrowArray item;  // the utf8 child of a list column
+    ArrowArray *item_ptr;
+    const void *bufs[3];
+    const void *item_bufs[3];
+};
+bool wide_wanted(const std::vector<int> &projection);
+int wide_build(VcfStream *s, const std::vector<long long> &batch_row0, int64_t n_rows, WideStore **out);
+void wide_free(WideStore *w);
+void wide_export(const WideStore *w, int col, int64_t b, int64_t rows, ArrowArray *a, WideChildSlot *slot);
+
 // defined in vcf_columns.cu
 int columns_filter_agg(VcfStream *s, const exon_gpu_pred *pred, const exon_gpu_agg *agg, exon_gpu_partial *out);
 void columns_free(VcfStream *s);

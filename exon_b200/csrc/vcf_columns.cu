@@ -453,10 +453,12 @@ struct Columns {
     std::vector<long long> batch_row0;  // first row of each batch (+ n_rows at the end); batches never span files
     std::vector<long long> batch_v0;    // values offset of each batch's first row (+ total at the end)
     std::vector<int> projection;
+    WideStore *wide = nullptr;  // columns 2..6 (vcf_wide.cu)
 
     void unref() {
         if (refs.fetch_sub(1) == 1) {
             cudaSetDevice(device);
+            wide_free(wide);
             cudaFree(d_pos);
             cudaFree(d_offsets);
             cudaFree(d_values);
@@ -481,12 +483,14 @@ namespace {
 struct ChildPriv {
     const void *buffers[3];
 };
+constexpr int kMaxCols = 9;
 struct BatchPriv {
     Columns *cols;
     int n_children;
-    ArrowArray children[2];
-    ArrowArray *child_ptrs[2];
-    ChildPriv child_priv[2];
+    ArrowArray children[kMaxCols];
+    ArrowArray *child_ptrs[kMaxCols];
+    ChildPriv child_priv[kMaxCols];
+    WideChildSlot wide_slot[kMaxCols];
     const void *struct_buffers[1];
 };
 
@@ -502,8 +506,10 @@ void release_batch(ArrowArray *a) {
 
 struct SchemaPriv {
     int n_children;
-    ArrowSchema children[2];
-    ArrowSchema *child_ptrs[2];
+    ArrowSchema children[kMaxCols];
+    ArrowSchema *child_ptrs[kMaxCols];
+    ArrowSchema items[kMaxCols];  // the "item" child of list columns
+    ArrowSchema *item_ptrs[kMaxCols];
 };
 void release_schema_child(ArrowSchema *s) { s->release = nullptr; }
 void release_schema(ArrowSchema *s) {
@@ -514,17 +520,33 @@ void release_schema(ArrowSchema *s) {
     s->release = nullptr;
 }
 
-// VCFSchemaBuilder (exon/exon-core/src/datasources/vcf/schema_builder.rs:85-129): chrom Utf8 !null, pos Int64 !null
+// VCFSchemaBuilder (exon/exon-core/src/datasources/vcf/schema_builder.rs:85-129): chrom Utf8 !null, pos Int64 !null,
+// id List<item: Utf8>, ref Utf8 !null, alt List<item: Utf8>, qual Float32, filter List<item: Utf8>
 void fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
+    static const char *names[7] = {"chrom", "pos", "id", "ref", "alt", "qual", "filter"};
+    static const char *formats[7] = {"u", "l", "+l", "u", "+l", "f", "+l"};
+    static const bool nullable[7] = {false, false, true, false, true, true, true};
     auto *p = new SchemaPriv();
     p->n_children = (int)projection.size();
     for (int i = 0; i < p->n_children; ++i) {
+        const int col = projection[(size_t)i];
         ArrowSchema &c = p->children[i];
         memset(&c, 0, sizeof(c));
-        c.format = projection[(size_t)i] == 0 ? "u" : "l";
-        c.name = projection[(size_t)i] == 0 ? "chrom" : "pos";
-        c.flags = 0;  // non-nullable
+        c.format = formats[col];
+        c.name = names[col];
+        c.flags = nullable[col] ? ARROW_FLAG_NULLABLE : 0;
         c.release = release_schema_child;
+        if (formats[col][0] == '+') {
+            ArrowSchema &it = p->items[i];
+            memset(&it, 0, sizeof(it));
+            it.format = "u";
+            it.name = "item";
+            it.flags = ARROW_FLAG_NULLABLE;
+            it.release = release_schema_child;
+            p->item_ptrs[i] = &it;
+            c.n_children = 1;
+            c.children = &p->item_ptrs[i];
+        }
         p->child_ptrs[i] = &c;
     }
     memset(out, 0, sizeof(*out));
@@ -651,7 +673,8 @@ int build_columns(VcfStream *s) {
         for (long long r = file_row0[f]; r < file_row0[f + 1]; r += c->batch_rows) c->batch_row0.push_back(r);
     c->n_batches = (int64_t)c->batch_row0.size();
     c->batch_row0.push_back(n_rows);
-    if (!c->want_chrom && !c->want_pos) return EXON_GPU_OK;  // empty projection: row counts only
+    if (!c->want_chrom && !c->want_pos)  // no K2 column: row counts only (empty projection) or wide columns only
+        return wide_wanted(c->projection) ? wide_build(s, c->batch_row0, n_rows, &c->wide) : EXON_GPU_OK;
 
     // ---- outputs + scratch B: absolute u32 offsets | batch_row0 | batch_v0 ----
     const size_t nb1 = (size_t)c->n_batches + 1;
@@ -712,6 +735,7 @@ int build_columns(VcfStream *s) {
         }
         CUDA_TRY(cudaStreamSynchronize(st));
     }
+    if (wide_wanted(c->projection)) return wide_build(s, c->batch_row0, n_rows, &c->wide);
     return EXON_GPU_OK;
 }
 
@@ -807,6 +831,13 @@ int columns_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
         a.offset = 0;
         ChildPriv &cp = p->child_priv[i];
         cp.buffers[0] = nullptr;  // no validity bitmap: both columns are non-nullable
+        if (s->projection[(size_t)i] >= 2) {
+            wide_export(c->wide, s->projection[(size_t)i], b, rows, &a, &p->wide_slot[i]);
+            if (p->wide_slot[i].item_ptr) p->wide_slot[i].item.release = release_child;
+            a.release = release_child;
+            p->child_ptrs[i] = &a;
+            continue;
+        }
         if (s->projection[(size_t)i] == 0) {
             const int32_t *off = (c->on_device ? c->d_offsets : c->h_offsets) + b * (c->batch_rows + 1);
             const uint8_t *val = (c->on_device ? c->d_values : c->h_values) + c->batch_v0[(size_t)b];

@@ -1,0 +1,465 @@
+// vcf_wide.cu -- VCF text -> Arrow columns 2..6 {id: list<utf8>, ref: utf8, alt: list<utf8>, qual: f32, filter: list<utf8>}.
+//
+// Replaces LazyVCFArrayBuilder::append / finish for those columns (exon/exon-vcf/src/array_builder/
+// lazy_array_builder.rs:169-216, 451-484), with the lazy builder's own quirks kept:
+//   id      "." -> NULL, else one list item per ';'-separated id                                      (:169-179)
+//   ref     the bases, byte for byte                                                                   (:180-189)
+//   alt     "." -> NULL, else a VALID BUT EMPTY list: the builder never appends the alleles            (:190-204)
+//   qual    "." -> NULL, else Rust `f32::from_str`, correctly rounded (f32_parse.cuh)                  (:205-208)
+//   filter  always valid: "." -> [], else one item per ';'-separated filter                            (:209-216)
+// Columns 0 / 1 stay with K2 (vcf_columns.cu), whose batch table (batches restart at every file) this build shares.
+//
+// Row-parallel, on top of the partition's line index (build_line_index, fastq_scan.cu):
+//   1. measure  one thread per record: walk to the 7th tab, item / byte counts of id, ref, filter, QUAL -> f32, validity flags
+//   2. 5 exclusive scans (cub): global item / byte offsets of every row
+//   3. emit     one thread per record: batch-relative int32 list offsets, child offsets and bytes at their final place,
+//               validity bits; the batch of a row is found by binary search over the batch table
+// Batches are zero-copy views of the store.  The child arrays of batch b restart at 0: its child offsets live at
+// coff[e0(b) + b .. e0(b + 1) + b] (one extra entry per batch), its bytes at val[v0(b) ..].
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "f32_parse.cuh"
+#include "internal.h"
+
+namespace exon {
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(_e == cudaErrorMemoryAllocation ? EXON_GPU_ERR_OOM : EXON_GPU_ERR_CUDA, "%s: %s", \
+                        #expr, cudaGetErrorString(_e));                                                  \
+    } while (0)
+
+namespace {
+
+constexpr uint32_t kWErrFields = 1u;       // fewer than 8 tab-separated fields
+constexpr uint32_t kWErrQual = 2u;         // QUAL is not a float literal
+constexpr uint32_t kWErrQualDigits = 4u;   // QUAL has more than 36 significant digits
+constexpr uint32_t kWErrFieldLen = 8u;     // a field of 2 GiB or more
+
+enum { kIdE = 0, kIdB = 1, kRefB = 2, kFiE = 3, kFiB = 4, kNScan = 5 };
+
+struct WideArgs {
+    int64_t n_rows;
+    const uint8_t *const *line_start;
+    const uint8_t *const *line_end;
+    const long long *brow;  // n_batches + 1
+    int64_t n_batches;
+    int32_t batch_rows, wpb;
+    int32_t want_id, want_ref, want_alt, want_qual, want_filter;
+    int32_t *cnt[kNScan];          // measure out, n_rows + 1 entries (the last one 0); NULL when not wanted
+    const long long *pre[kNScan];  // emit in: exclusive scans of cnt
+    uint8_t *rowflags;             // measure out: bit0 id valid, bit1 alt valid, bit2 qual valid
+    float *qual;
+    int32_t *id_loff, *id_coff, *ref_off, *fi_loff, *fi_coff;
+    uint8_t *id_val, *ref_val, *fi_val;
+    uint32_t *id_valid, *alt_valid, *qual_valid;
+    uint32_t *flags;
+    unsigned long long *first_bad_row;
+};
+
+// tabs 0..6 of the line [ls, le): false when the line has fewer than 8 fields
+__device__ __forceinline__ bool find_tabs(const uint8_t *ls, const uint8_t *le, const uint8_t *tab[7]) {
+    int nt = 0;
+    for (const uint8_t *p = ls; p < le; ++p) {
+        if (__ldg(p) == '\t') {
+            tab[nt++] = p;
+            if (nt == 7) return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool is_missing(const uint8_t *f, int64_t n) { return n == 0 || (n == 1 && __ldg(f) == '.'); }
+
+// items = 1 + number of ';', bytes = n - (items - 1)
+__device__ __forceinline__ void count_items(const uint8_t *f, int32_t n, int32_t &items, int32_t &bytes) {
+    int32_t semi = 0;
+    for (int32_t i = 0; i < n; ++i) semi += __ldg(f + i) == ';';
+    items = semi + 1;
+    bytes = n - semi;
+}
+
+__global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__ WideArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= a.n_rows) return;
+    const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
+    const uint8_t *tab[7];
+    uint32_t err = 0;
+    int32_t c[kNScan] = {0, 0, 0, 0, 0};
+    uint8_t rf = 0;
+    float q = 0.0f;
+    if (!find_tabs(ls, le, tab)) {
+        err = kWErrFields;
+    } else if (tab[6] - tab[1] > 0x7FFFFFF0ll) {
+        err = kWErrFieldLen;
+    } else {
+        if (a.want_id) {
+            const uint8_t *f = tab[1] + 1;
+            const int32_t n = (int32_t)(tab[2] - f);
+            if (!is_missing(f, n)) {
+                rf |= 1u;
+                count_items(f, n, c[kIdE], c[kIdB]);
+            }
+        }
+        if (a.want_ref) c[kRefB] = (int32_t)(tab[3] - tab[2] - 1);
+        if (a.want_alt && !is_missing(tab[3] + 1, tab[4] - tab[3] - 1)) rf |= 2u;
+        if (a.want_qual) {
+            const uint8_t *f = tab[4] + 1;
+            const int64_t n = tab[5] - f;
+            if (!(n == 1 && __ldg(f) == '.')) {
+                const int rc = n > 4096 ? kF32Malformed : parse_f32_rust(f, (int)n, &q);
+                if (rc == kF32Ok) rf |= 4u;
+                else err |= rc == kF32Unsupported ? kWErrQualDigits : kWErrQual;
+            }
+        }
+        if (a.want_filter) {
+            const uint8_t *f = tab[5] + 1;
+            const int32_t n = (int32_t)(tab[6] - f);
+            if (!is_missing(f, n)) count_items(f, n, c[kFiE], c[kFiB]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kNScan; ++k)
+        if (a.cnt[k]) a.cnt[k][r] = c[k];
+    a.rowflags[r] = rf;
+    if (a.want_qual) a.qual[r] = q;
+    if (err) {
+        atomicOr(a.flags, err);
+        atomicMin(a.first_bad_row, (unsigned long long)r);
+    }
+}
+
+// writes the items of one list cell: child offsets (relative to the batch's first byte) and bytes
+__device__ __forceinline__ void emit_items(const uint8_t *f, int32_t n, int32_t *coff, uint8_t *val, long long v_abs, long long v_rel) {
+    int32_t k = 0;
+    coff[0] = (int32_t)v_rel;
+    long long w = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        const uint8_t ch = __ldg(f + i);
+        if (ch == ';') coff[++k] = (int32_t)(v_rel + w);
+        else val[v_abs + w++] = ch;
+    }
+}
+
+__global__ void __launch_bounds__(256) vw_emit_kernel(const __grid_constant__ WideArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= a.n_rows) return;
+    // batch of the row: last b with brow[b] <= r
+    int64_t lo = 0, hi = a.n_batches;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&a.brow[mid]) <= r) lo = mid;
+        else hi = mid;
+    }
+    const int64_t b = lo, r0 = __ldg(&a.brow[b]);
+    const int in_batch = (int)(r - r0);
+    const bool last = r + 1 == __ldg(&a.brow[b + 1]);
+    const uint8_t rf = a.rowflags[r];
+    const uint32_t bit = 1u << (in_batch & 31);
+    const int64_t word = b * a.wpb + (in_batch >> 5);
+    if (a.want_alt && (rf & 2u)) atomicOr(a.alt_valid + word, bit);
+    if (a.want_qual && (rf & 4u)) atomicOr(a.qual_valid + word, bit);
+    if (a.want_id && (rf & 1u)) atomicOr(a.id_valid + word, bit);
+    if (!(a.want_id || a.want_ref || a.want_filter)) return;
+    const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
+    const uint8_t *tab[7];
+    if (!find_tabs(ls, le, tab)) return;  // reported by the measure pass
+    const int64_t lrow = b * (int64_t)(a.batch_rows + 1) + in_batch;
+    if (a.want_id) {
+        const long long e = a.pre[kIdE][r], e0 = a.pre[kIdE][r0], v = a.pre[kIdB][r], v0 = a.pre[kIdB][r0];
+        a.id_loff[lrow] = (int32_t)(e - e0);
+        int32_t *coff = a.id_coff + e0 + b;
+        if (rf & 1u) emit_items(tab[1] + 1, (int32_t)(tab[2] - tab[1] - 1), coff + (e - e0), a.id_val, v, v - v0);
+        if (last) {
+            a.id_loff[lrow + 1] = (int32_t)(a.pre[kIdE][r + 1] - e0);
+            coff[a.pre[kIdE][r + 1] - e0] = (int32_t)(a.pre[kIdB][r + 1] - v0);
+        }
+    }
+    if (a.want_ref) {
+        const long long v = a.pre[kRefB][r], v0 = a.pre[kRefB][r0];
+        a.ref_off[lrow] = (int32_t)(v - v0);
+        const uint8_t *f = tab[2] + 1;
+        const int32_t n = (int32_t)(tab[3] - f);
+        for (int32_t i = 0; i < n; ++i) a.ref_val[v + i] = __ldg(f + i);
+        if (last) a.ref_off[lrow + 1] = (int32_t)(a.pre[kRefB][r + 1] - v0);
+    }
+    if (a.want_filter) {
+        const long long e = a.pre[kFiE][r], e0 = a.pre[kFiE][r0], v = a.pre[kFiB][r], v0 = a.pre[kFiB][r0];
+        a.fi_loff[lrow] = (int32_t)(e - e0);
+        int32_t *coff = a.fi_coff + e0 + b;
+        const uint8_t *f = tab[5] + 1;
+        const int32_t n = (int32_t)(tab[6] - f);
+        if (!is_missing(f, n)) emit_items(f, n, coff + (e - e0), a.fi_val, v, v - v0);
+        if (last) {
+            a.fi_loff[lrow + 1] = (int32_t)(a.pre[kFiE][r + 1] - e0);
+            coff[a.pre[kFiE][r + 1] - e0] = (int32_t)(a.pre[kFiB][r + 1] - v0);
+        }
+    }
+}
+
+__global__ void vw_gather_i64(const long long *src, const long long *idx, int64_t n, long long *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+size_t al256w(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+struct WideBuf {
+    void *d = nullptr, *h = nullptr;
+    size_t bytes = 0;
+};
+
+struct WideStore {
+    int device = 0;
+    bool on_device = false;
+    int batch_rows = 8192, wpb = 256;
+    int64_t n_batches = 0, n_rows = 0;
+    bool want[9] = {false, false, false, false, false, false, false, false, false};
+    WideBuf id_loff, id_coff, id_val, id_valid, ref_off, ref_val, alt_valid, zeros, qual, qual_valid, fi_loff, fi_coff, fi_val;
+    std::vector<long long> batch_row0, base[kNScan];  // per batch (+ total): global item / byte offset of the batch's first row
+    static constexpr int kBufs = 13;
+    void all(WideBuf *out[kBufs]) {
+        WideBuf *v[kBufs] = {&id_loff, &id_coff, &id_val, &id_valid, &ref_off, &ref_val, &alt_valid, &zeros, &qual, &qual_valid, &fi_loff, &fi_coff, &fi_val};
+        for (int i = 0; i < kBufs; ++i) out[i] = v[i];
+    }
+    template <class T>
+    const T *p(const WideBuf &b) const { return static_cast<const T *>(on_device ? b.d : b.h); }
+};
+
+void wide_free(WideStore *w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    WideBuf *b[WideStore::kBufs];
+    w->all(b);
+    for (int i = 0; i < WideStore::kBufs; ++i) {
+        cudaFree(b[i]->d);
+        cudaFreeHost(b[i]->h);
+    }
+    delete w;
+}
+
+bool wide_wanted(const std::vector<int> &projection) {
+    for (int p : projection)
+        if (p >= 2) return true;
+    return false;
+}
+
+// The caller (build_columns) holds ctx->work_mu and has computed the batch table.
+int wide_build(VcfStream *s, const std::vector<long long> &batch_row0, int64_t n_rows, WideStore **out) {
+    Ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    auto *w = new (std::nothrow) WideStore();
+    if (!w) return fail(EXON_GPU_ERR_OOM, "next_batch: out of host memory");
+    *out = w;
+    w->device = ctx->device;
+    w->on_device = s->columns_on_device;
+    w->batch_rows = s->batch_rows;
+    w->wpb = ((s->batch_rows + 63) / 64) * 2;
+    w->n_rows = n_rows;
+    w->n_batches = (int64_t)batch_row0.size() - 1;
+    w->batch_row0 = batch_row0;
+    for (int p : s->projection) w->want[p] = true;
+    for (int p = 7; p < 9; ++p)
+        if (w->want[p])
+            return fail(EXON_GPU_ERR_UNSUPPORTED, "vcf_next_batch: column %d (%s) is re-serialised by the reference builder and is not built on the device yet",
+                        p, p == 7 ? "info" : "formats");
+    if (n_rows == 0) return EXON_GPU_OK;
+    const size_t nb1 = (size_t)w->n_batches + 1, nr1 = (size_t)n_rows + 1;
+
+    // per-row temporaries in scratch_b behind the line tables: 5 counts (i32) | 5 prefixes (i64) | flags | batch table | bases
+    size_t cub_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (long long *)nullptr, (int)nr1, st));
+    const size_t per_line = kNScan * 4 + kNScan * 8 + 1;
+    const size_t fixed = (2 * kNScan + 4) * 256 + al256w(cub_bytes) + 2 * al256w(nb1 * 8) + 1024;
+    LineIndex li;
+    if (int rc = build_line_index(s, per_line, fixed, &li)) return rc;
+    if (li.n_lines != n_rows) return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: line index has %lld lines for %lld rows", (long long)li.n_lines, (long long)n_rows);
+    uint8_t *x = li.extra;
+    auto take = [&](size_t bytes) {
+        uint8_t *p = x;
+        x += al256w(bytes);
+        return p;
+    };
+    const bool need[kNScan] = {w->want[2], w->want[2], w->want[3], w->want[6], w->want[6]};
+    WideArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_rows = n_rows;
+    a.line_start = li.line_start;
+    a.line_end = li.line_end;
+    a.n_batches = w->n_batches;
+    a.batch_rows = w->batch_rows;
+    a.wpb = w->wpb;
+    a.want_id = w->want[2], a.want_ref = w->want[3], a.want_alt = w->want[4], a.want_qual = w->want[5], a.want_filter = w->want[6];
+    long long *pre[kNScan] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < kNScan; ++k) {
+        if (!need[k]) continue;
+        a.cnt[k] = (int32_t *)take(nr1 * 4);
+        pre[k] = (long long *)take(nr1 * 8);
+        a.pre[k] = pre[k];
+        CUDA_TRY(cudaMemsetAsync(a.cnt[k] + n_rows, 0, 4, st));
+    }
+    a.rowflags = take(nr1);
+    uint8_t *cub_tmp = take(cub_bytes);
+    long long *d_brow = (long long *)take(nb1 * 8), *d_base = (long long *)take(nb1 * 8);
+    unsigned long long *d_misc = (unsigned long long *)take(64);
+    a.brow = d_brow;
+    a.flags = reinterpret_cast<uint32_t *>(d_misc);
+    a.first_bad_row = d_misc + 1;
+    const unsigned long long init_misc[2] = {0ull, ~0ull};
+    CUDA_TRY(cudaMemcpyAsync(d_misc, init_misc, sizeof(init_misc), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_brow, batch_row0.data(), nb1 * 8, cudaMemcpyHostToDevice, st));
+
+    auto dev_alloc = [&](WideBuf &b, size_t bytes, bool zero) -> int {
+        b.bytes = std::max<size_t>(bytes, 8);
+        CUDA_TRY(cudaMallocAsync(&b.d, b.bytes, st));
+        if (zero) CUDA_TRY(cudaMemsetAsync(b.d, 0, b.bytes, st));
+        return EXON_GPU_OK;
+    };
+    const size_t valid_bytes = (size_t)w->n_batches * (size_t)w->wpb * 4;
+    const size_t loff_bytes = (size_t)w->n_batches * (size_t)(w->batch_rows + 1) * 4;
+    if (w->want[5]) {
+        if (int rc = dev_alloc(w->qual, (size_t)n_rows * 4, false)) return rc;
+        if (int rc = dev_alloc(w->qual_valid, valid_bytes, true)) return rc;
+        a.qual = (float *)w->qual.d;
+        a.qual_valid = (uint32_t *)w->qual_valid.d;
+    }
+
+    // ---- 1. measure ----
+    const unsigned grid = (unsigned)((n_rows + 255) / 256);
+    vw_measure_kernel<<<grid, 256, 0, st>>>(a);
+    ctx->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    // ---- 2. scans + per-batch bases ----
+    for (int k = 0; k < kNScan; ++k) {
+        if (!need[k]) continue;
+        size_t tb = cub_bytes;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, (const int32_t *)a.cnt[k], pre[k], (int)nr1, st));
+        vw_gather_i64<<<(unsigned)((nb1 + 255) / 256), 256, 0, st>>>(pre[k], d_brow, (int64_t)nb1, d_base);
+        ctx->launches.fetch_add(2);
+        w->base[k].resize(nb1);
+        CUDA_TRY(cudaMemcpyAsync(w->base[k].data(), d_base, nb1 * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // d_base is reused by the next scan
+    }
+    unsigned long long h_misc[2];
+    CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (const uint32_t e = (uint32_t)h_misc[0])
+        return fail((e & ~kWErrQualDigits) ? EXON_GPU_ERR_PARSE : EXON_GPU_ERR_UNSUPPORTED, "malformed VCF record at row %llu:%s%s%s%s", h_misc[1],
+                    (e & kWErrFields) ? " fewer than 8 tab-separated fields;" : "", (e & kWErrQual) ? " QUAL is not a float literal;" : "",
+                    (e & kWErrQualDigits) ? " QUAL has more than 36 significant digits;" : "", (e & kWErrFieldLen) ? " a field of 2 GiB or more;" : "");
+    for (int k = 0; k < kNScan; ++k) {
+        if (!need[k]) continue;
+        for (int64_t b = 0; b < w->n_batches; ++b)
+            if (w->base[k][(size_t)b + 1] - w->base[k][(size_t)b] > 0x7FFFFFFFll)
+                return fail(EXON_GPU_ERR_UNSUPPORTED, "vcf_next_batch: batch %lld overflows int32 offsets", (long long)b);
+    }
+    // ---- outputs ----
+    if (w->want[2]) {
+        if (int rc = dev_alloc(w->id_loff, loff_bytes, false)) return rc;
+        if (int rc = dev_alloc(w->id_coff, ((size_t)w->base[kIdE][nb1 - 1] + nb1) * 4, false)) return rc;
+        if (int rc = dev_alloc(w->id_val, (size_t)w->base[kIdB][nb1 - 1], false)) return rc;
+        if (int rc = dev_alloc(w->id_valid, valid_bytes, true)) return rc;
+        a.id_loff = (int32_t *)w->id_loff.d, a.id_coff = (int32_t *)w->id_coff.d, a.id_val = (uint8_t *)w->id_val.d, a.id_valid = (uint32_t *)w->id_valid.d;
+    }
+    if (w->want[3]) {
+        if (int rc = dev_alloc(w->ref_off, loff_bytes, false)) return rc;
+        if (int rc = dev_alloc(w->ref_val, (size_t)w->base[kRefB][nb1 - 1], false)) return rc;
+        a.ref_off = (int32_t *)w->ref_off.d, a.ref_val = (uint8_t *)w->ref_val.d;
+    }
+    if (w->want[4]) {
+        if (int rc = dev_alloc(w->alt_valid, valid_bytes, true)) return rc;
+        if (int rc = dev_alloc(w->zeros, (size_t)(w->batch_rows + 1) * 4, true)) return rc;
+        a.alt_valid = (uint32_t *)w->alt_valid.d;
+    }
+    if (w->want[6]) {
+        if (int rc = dev_alloc(w->fi_loff, loff_bytes, false)) return rc;
+        if (int rc = dev_alloc(w->fi_coff, ((size_t)w->base[kFiE][nb1 - 1] + nb1) * 4, false)) return rc;
+        if (int rc = dev_alloc(w->fi_val, (size_t)w->base[kFiB][nb1 - 1], false)) return rc;
+        a.fi_loff = (int32_t *)w->fi_loff.d, a.fi_coff = (int32_t *)w->fi_coff.d, a.fi_val = (uint8_t *)w->fi_val.d;
+    }
+    // ---- 3. emit ----
+    vw_emit_kernel<<<grid, 256, 0, st>>>(a);
+    ctx->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    if (!w->on_device) {
+        WideBuf *b[WideStore::kBufs];
+        w->all(b);
+        for (int i = 0; i < WideStore::kBufs; ++i) {
+            if (!b[i]->d) continue;
+            CUDA_TRY(cudaHostAlloc(&b[i]->h, b[i]->bytes, cudaHostAllocDefault));
+            CUDA_TRY(cudaMemcpyAsync(b[i]->h, b[i]->d, b[i]->bytes, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return EXON_GPU_OK;
+}
+
+// Arrow C Data Interface view of column `col` (2..6) of batch b.  The caller owns `a` and `slot` and sets the release callbacks.
+void wide_export(const WideStore *w, int col, int64_t b, int64_t rows, ArrowArray *a, WideChildSlot *slot) {
+    memset(a, 0, sizeof(*a));
+    memset(slot, 0, sizeof(*slot));
+    a->length = rows;
+    a->buffers = slot->bufs;
+    const int64_t row0 = w->batch_row0[(size_t)b];
+    const size_t loff = (size_t)b * (size_t)(w->batch_rows + 1), vw = (size_t)b * (size_t)w->wpb;
+    auto list_child = [&](int64_t n_items, const int32_t *coff, const uint8_t *val) {
+        ArrowArray &it = slot->item;
+        it.length = n_items;
+        it.null_count = 0;
+        it.n_buffers = 3;
+        slot->item_bufs[0] = nullptr;
+        slot->item_bufs[1] = coff;
+        slot->item_bufs[2] = val;
+        it.buffers = slot->item_bufs;
+        slot->item_ptr = &it;
+        a->n_children = 1;
+        a->children = &slot->item_ptr;
+        a->n_buffers = 2;
+    };
+    switch (col) {
+        case 2:
+            a->null_count = -1;
+            slot->bufs[0] = w->p<uint32_t>(w->id_valid) + vw;
+            slot->bufs[1] = w->p<int32_t>(w->id_loff) + loff;
+            list_child(w->base[kIdE][(size_t)b + 1] - w->base[kIdE][(size_t)b], w->p<int32_t>(w->id_coff) + w->base[kIdE][(size_t)b] + b,
+                       w->p<uint8_t>(w->id_val) + w->base[kIdB][(size_t)b]);
+            break;
+        case 3:
+            a->null_count = 0;
+            a->n_buffers = 3;
+            slot->bufs[0] = nullptr;
+            slot->bufs[1] = w->p<int32_t>(w->ref_off) + loff;
+            slot->bufs[2] = w->p<uint8_t>(w->ref_val) + w->base[kRefB][(size_t)b];
+            break;
+        case 4:
+            a->null_count = -1;
+            slot->bufs[0] = w->p<uint32_t>(w->alt_valid) + vw;
+            slot->bufs[1] = w->p<int32_t>(w->zeros);
+            list_child(0, w->p<int32_t>(w->zeros), w->p<uint8_t>(w->zeros));
+            break;
+        case 5:
+            a->null_count = -1;
+            a->n_buffers = 2;
+            slot->bufs[0] = w->p<uint32_t>(w->qual_valid) + vw;
+            slot->bufs[1] = w->p<float>(w->qual) + row0;
+            break;
+        default:  // 6
+            a->null_count = 0;
+            slot->bufs[0] = nullptr;
+            slot->bufs[1] = w->p<int32_t>(w->fi_loff) + loff;
+            list_child(w->base[kFiE][(size_t)b + 1] - w->base[kFiE][(size_t)b], w->p<int32_t>(w->fi_coff) + w->base[kFiE][(size_t)b] + b,
+                       w->p<uint8_t>(w->fi_val) + w->base[kFiB][(size_t)b]);
+            break;
+    }
+}
+
+}  // namespace exon

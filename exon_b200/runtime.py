@@ -249,6 +249,16 @@ class VcfBatch:
             out = [x if (bits[i >> 3] >> (i & 7)) & 1 else None for i, x in enumerate(out)]
         return out
 
+    def to_pyarrow(self):
+        """Import the batch into pyarrow through the Arrow C Data Interface (host batches only).  Ownership moves to
+        pyarrow: the library's release callback runs when the pyarrow batch is dropped."""
+        assert not self.on_device, "device-resident batch: read it with a CUDA consumer"
+        import pyarrow as pa
+
+        rb = pa.RecordBatch._import_from_c(C.addressof(self._arr), C.addressof(self._schema))
+        rb.validate(full=True)
+        return rb
+
     def chrom_strings(self):
         off, val = self.column("chrom")
         b = val.tobytes()

@@ -119,6 +119,13 @@ int exon_gpu_region_parse(const char *s, char *name_buf, size_t name_buf_len, ex
 /* Interval literal of interval_match ("a-b", "a", "a-", "-b"; udfs/vcf/mod.rs:246-252): has_chrom = 0. */
 int exon_gpu_interval_parse(const char *s, exon_gpu_region *out);
 
+/* QUAL text -> f32 exactly as the reference's builder obtains it: Rust `f32::from_str` applied by noodles-vcf 0.70
+ * `Record::quality_score` (call site exon/exon-vcf/src/array_builder/lazy_array_builder.rs:205-208): correctly rounded,
+ * "inf" / "infinity" / "nan" in any case, no hex, at least one mantissa digit.  The same routine runs inside the column
+ * kernel; this host entry exists so that it can be pinned against exact arithmetic without a device.
+ * EXON_GPU_ERR_PARSE: not a float literal; EXON_GPU_ERR_UNSUPPORTED: more than 36 significant digits. */
+int exon_gpu_parse_f32(const char *s, size_t len, float *out);
+
 /* ---- file -> partition assignment (a3) ---------------------------------------------------------------- */
 /* ExonFileScanConfig::regroup_files_by_size (exon/exon-core/src/datasources/exon_file_scan_config.rs:79-110):
  * stable sort by size ascending, partitions = min(target, n_files), file i of the sorted order -> i % partitions.
@@ -130,7 +137,7 @@ int exon_gpu_regroup_files_by_size(const int64_t *sizes, int32_t n_files, int32_
 typedef struct {
     int32_t batch_rows;        /* session batch size; reference default 8192 (exon/exon-common/src/lib.rs:27) */
     int32_t n_projection;      /* file-schema column indices to materialise, in output order ... */
-    const int32_t *projection; /* ... VCFConfig.projection (exon/exon-vcf/src/config.rs:23-64); cols 0 (chrom), 1 (pos) */
+    const int32_t *projection; /* ... VCFConfig.projection (exon/exon-vcf/src/config.rs:23-64); cols 0..6 (chrom pos id ref alt qual filter) */
     int32_t columns_on_device; /* 0: next_batch buffers are pinned host memory; 1: device memory */
     /* Optional predicate declared up front so that every feed() can be scanned while the next one is still
      * copying (fused a5-a9).  NULL = none declared; filter_count() then scans what is resident. */
@@ -157,7 +164,13 @@ int exon_gpu_vcf_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int i
  * ExonArrayBuilder::try_into_record_batch (exon/exon-vcf/src/async_batch_stream.rs:80-109,
  * exon/exon-vcf/src/array_builder/lazy_array_builder.rs:153-484, exon/exon-common/src/array_builder.rs:25-36).
  * Fills a struct array (format "+s") of <= batch_rows rows whose children are the projected columns in
- * projection order: chrom = utf8 ("u": validity NULL, int32 offsets starting at 0, bytes), pos = int64 ("l").
+ * projection order: chrom = utf8 ("u": validity NULL, int32 offsets starting at 0, bytes), pos = int64 ("l"),
+ * id / alt / filter = list<item: utf8> ("+l"), ref = utf8, qual = float32 ("f") -- with the lazy builder's own
+ * semantics (lazy_array_builder.rs:169-216): id "." -> NULL; alt "." -> NULL, anything else -> a valid EMPTY list
+ * (the builder never appends the alleles); qual "." -> NULL, else Rust f32::from_str (correctly rounded);
+ * filter always valid, "." -> [].  A record with fewer than 8 fields or a malformed QUAL fails the call
+ * (EXON_GPU_ERR_PARSE).  info (7) and formats (8) are re-serialised by the reference and are not built yet:
+ * exon_gpu_vcf_open rejects them with EXON_GPU_ERR_UNSUPPORTED.
  * End of stream: returns EXON_GPU_OK with out->release == NULL (ArrowArrayStream.get_next convention). */
 int exon_gpu_vcf_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 

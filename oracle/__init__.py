@@ -125,6 +125,58 @@ def read_batches(data, batch_size: int = 8192, projection=(0, 1)):
         lib().exo_vcf_reader_close(r)
 
 
+class VcfWide(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("id_valid", C.POINTER(C.c_uint8)), ("alt_valid", C.POINTER(C.c_uint8)),
+                ("qual_valid", C.POINTER(C.c_uint8)), ("id_count", C.POINTER(C.c_int32)), ("filter_count", C.POINTER(C.c_int32)),
+                ("ref_len", C.POINTER(C.c_int32)), ("qual", C.POINTER(C.c_float)), ("id_items", C.c_int64),
+                ("filter_items", C.c_int64), ("id_item_len", C.POINTER(C.c_int32)), ("filter_item_len", C.POINTER(C.c_int32)),
+                ("id_bytes", C.POINTER(C.c_uint8)), ("filter_bytes", C.POINTER(C.c_uint8)), ("ref_bytes", C.POINTER(C.c_uint8)),
+                ("id_bytes_len", C.c_int64), ("filter_bytes_len", C.c_int64), ("ref_bytes_len", C.c_int64), ("err_row", C.c_int64)]
+
+
+def vcf_wide_rows(data):
+    """Columns 2..6 of every record of one VCF text as the reference's lazy builder materialises them:
+    dict of per-row Python lists  id (None | [bytes]), ref (bytes), alt (None | []), qual (None | float32 bits), filter ([bytes])."""
+    a = _buf(data)
+    L = lib()
+    L.exo_vcf_wide_scan.restype = C.POINTER(VcfWide)
+    L.exo_vcf_wide_scan.argtypes = [C.c_void_p, C.c_int64]
+    L.exo_vcf_wide_free.argtypes = [C.POINTER(VcfWide)]
+    wp = L.exo_vcf_wide_scan(a.ctypes.data, a.size)
+    try:
+        w = wp.contents
+        if w.err_row >= 0:
+            raise ValueError(f"malformed VCF record at row {w.err_row}")
+        n = int(w.rows)
+
+        def arr(p, m, dt):
+            return np.ctypeslib.as_array(p, (max(int(m), 1),))[: int(m)].astype(dt) if m else np.zeros(0, dt)
+
+        def items(lens_p, bytes_p, n_items, n_bytes):
+            lens = arr(lens_p, n_items, np.int64)
+            b = arr(bytes_p, n_bytes, np.uint8).tobytes()
+            offs = np.concatenate([[0], np.cumsum(lens)])
+            return [b[offs[i]:offs[i + 1]] for i in range(len(lens))]
+
+        id_items = items(w.id_item_len, w.id_bytes, w.id_items, w.id_bytes_len)
+        fi_items = items(w.filter_item_len, w.filter_bytes, w.filter_items, w.filter_bytes_len)
+        refs = items(w.ref_len, w.ref_bytes, n, w.ref_bytes_len)
+        id_valid, alt_valid, qual_valid = arr(w.id_valid, n, bool), arr(w.alt_valid, n, bool), arr(w.qual_valid, n, bool)
+        id_count, fi_count = arr(w.id_count, n, np.int64), arr(w.filter_count, n, np.int64)
+        qual = arr(w.qual, n, np.float32).view(np.uint32)
+        out = {"id": [], "ref": refs, "alt": [[] if v else None for v in alt_valid],
+               "qual": [int(q) if v else None for q, v in zip(qual, qual_valid)], "filter": []}
+        i0 = f0 = 0
+        for r in range(n):
+            out["id"].append(id_items[i0:i0 + id_count[r]] if id_valid[r] else None)
+            i0 += int(id_count[r])
+            out["filter"].append(fi_items[f0:f0 + fi_count[r]])
+            f0 += int(fi_count[r])
+        return out
+    finally:
+        L.exo_vcf_wide_free(wp)
+
+
 def filter_count(data, chrom=None, lo=None, hi=None, batch_size: int = 8192):
     """(count, rows) for `chrom = <chrom> AND pos BETWEEN lo AND hi` over one VCF text."""
     a = _buf(data)

@@ -498,3 +498,180 @@ int64_t exo_vcf_gz_filter_count_files(const uint8_t *const *datas, const int64_t
     if (n_rows) *n_rows = rows;
     return err ? err : total;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Columns 2..6 (id, ref, alt, qual, filter).  LazyVCFArrayBuilder::append, exon-vcf/src/array_builder/
+ * lazy_array_builder.rs:169-216, over noodles-vcf 0.70 lazy `Record` accessors (un-vendored; their published
+ * behaviour: a field equal to "." reads as empty; `ids()` / `filters()` split on ';'; `quality_score()` is
+ * `str::parse::<f32>()`):
+ *   col 2 id     (:169-179)  empty -> NULL, else one list item per ';'-separated id
+ *   col 3 ref    (:180-189)  the bases copied char by char into a fresh String (bytes as they are, for ASCII)
+ *   col 4 alt    (:190-204)  empty -> NULL; else `append(true)` WITHOUT any child value: an empty list
+ *   col 5 qual   (:205-208)  "." -> NULL, else f32 (correctly rounded; Rust grammar checked here, then strtof)
+ *   col 6 filter (:209-216)  always a valid list: "." -> [], else one item per ';'-separated filter
+ * No reference test prints these five columns; the restatement is pinned only by an independent Python split of
+ * the fixtures (tests/test_vcf_wide_golden.py) and, for qual, by exact rational arithmetic.
+ * Whole file at once (the tests cut it into batches): flat arrays, all malloc'ed, freed by exo_vcf_wide_free.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t rows;
+    uint8_t *id_valid, *alt_valid, *qual_valid; /* [rows] */
+    int32_t *id_count, *filter_count, *ref_len; /* [rows] */
+    float *qual;                                /* [rows] */
+    int64_t id_items, filter_items;
+    int32_t *id_item_len, *filter_item_len; /* [items] */
+    uint8_t *id_bytes, *filter_bytes, *ref_bytes;
+    int64_t id_bytes_len, filter_bytes_len, ref_bytes_len;
+    int64_t err_row; /* -1, or the first malformed row */
+} exo_vcf_wide;
+
+static int rust_f32_grammar(const uint8_t *s, int n) {
+    int i = 0;
+    if (n > 0 && (s[0] == '+' || s[0] == '-')) i = 1;
+    if (i >= n) return 0;
+    {
+        char low[16];
+        int m = n - i;
+        if (m <= 8) {
+            for (int k = 0; k < m; k++) low[k] = (char)(s[i + k] | 0x20);
+            low[m] = 0;
+            if (!strcmp(low, "inf") || !strcmp(low, "infinity") || !strcmp(low, "nan")) return 1;
+        }
+    }
+    int digits = 0, dot = 0;
+    for (; i < n; i++) {
+        if (s[i] == '.') {
+            if (dot) return 0;
+            dot = 1;
+        } else if (s[i] >= '0' && s[i] <= '9') digits++;
+        else break;
+    }
+    if (!digits) return 0;
+    if (i < n && (s[i] == 'e' || s[i] == 'E')) {
+        i++;
+        if (i < n && (s[i] == '+' || s[i] == '-')) i++;
+        if (i >= n) return 0;
+        for (; i < n; i++)
+            if (s[i] < '0' || s[i] > '9') return 0;
+    }
+    return i == n;
+}
+
+typedef struct {
+    int32_t *len;
+    uint8_t *bytes;
+    int64_t n, cap, blen, bcap;
+} item_vec;
+static void iv_push(item_vec *v, const uint8_t *p, int32_t n) {
+    if (v->n == v->cap) {
+        v->cap = v->cap ? v->cap * 2 : 1024;
+        v->len = (int32_t *)realloc(v->len, sizeof(int32_t) * (size_t)v->cap);
+    }
+    v->len[v->n++] = n;
+    if (v->blen + n > v->bcap) {
+        while (v->blen + n > v->bcap) v->bcap = v->bcap ? v->bcap * 2 : 4096;
+        v->bytes = (uint8_t *)realloc(v->bytes, (size_t)v->bcap);
+    }
+    memcpy(v->bytes + v->blen, p, (size_t)n);
+    v->blen += n;
+}
+static int32_t split_items(item_vec *v, const uint8_t *f, int32_t n) {
+    int32_t cnt = 0, s = 0;
+    for (int32_t i = 0; i <= n; i++) {
+        if (i == n || f[i] == ';') {
+            iv_push(v, f + s, i - s);
+            s = i + 1;
+            cnt++;
+        }
+    }
+    return cnt;
+}
+
+void exo_vcf_wide_free(exo_vcf_wide *w) {
+    if (!w) return;
+    free(w->id_valid); free(w->alt_valid); free(w->qual_valid);
+    free(w->id_count); free(w->filter_count); free(w->ref_len);
+    free(w->qual);
+    free(w->id_item_len); free(w->filter_item_len);
+    free(w->id_bytes); free(w->filter_bytes); free(w->ref_bytes);
+    free(w);
+}
+
+exo_vcf_wide *exo_vcf_wide_scan(const uint8_t *text, int64_t len) {
+    exo_vcf_wide *w = (exo_vcf_wide *)calloc(1, sizeof(*w));
+    w->err_row = -1;
+    int64_t cur = exo_vcf_header_len(text, len), cap = 0;
+    item_vec ids = {0}, fis = {0}, refs = {0};
+    while (cur < len) {
+        const uint8_t *line = text + cur;
+        const uint8_t *nl = (const uint8_t *)memchr(line, '\n', (size_t)(len - cur));
+        const int64_t ll = nl ? nl - line : len - cur;
+        cur += ll + (nl ? 1 : 0);
+        const uint8_t *tab[7];
+        const uint8_t *p = line;
+        int nt = 0;
+        while (nt < 7) {
+            const uint8_t *t = (const uint8_t *)memchr(p, '\t', (size_t)(line + ll - p));
+            if (!t) break;
+            tab[nt++] = t;
+            p = t + 1;
+        }
+        if (w->rows == cap) {
+            cap = cap ? cap * 2 : 4096;
+            w->id_valid = (uint8_t *)realloc(w->id_valid, (size_t)cap);
+            w->alt_valid = (uint8_t *)realloc(w->alt_valid, (size_t)cap);
+            w->qual_valid = (uint8_t *)realloc(w->qual_valid, (size_t)cap);
+            w->id_count = (int32_t *)realloc(w->id_count, sizeof(int32_t) * (size_t)cap);
+            w->filter_count = (int32_t *)realloc(w->filter_count, sizeof(int32_t) * (size_t)cap);
+            w->ref_len = (int32_t *)realloc(w->ref_len, sizeof(int32_t) * (size_t)cap);
+            w->qual = (float *)realloc(w->qual, sizeof(float) * (size_t)cap);
+        }
+        const int64_t r = w->rows;
+        if (nt < 7) {
+            w->err_row = r;
+            break;
+        }
+#define FIELD(k) (tab[(k)-1] + 1)
+#define FLEN(k) ((int32_t)(tab[(k)] - tab[(k)-1] - 1))
+        const uint8_t *f;
+        int32_t n;
+        f = FIELD(2), n = FLEN(2);
+        if (n == 0 || (n == 1 && f[0] == '.')) {
+            w->id_valid[r] = 0;
+            w->id_count[r] = 0;
+        } else {
+            w->id_valid[r] = 1;
+            w->id_count[r] = split_items(&ids, f, n);
+        }
+        f = FIELD(3), n = FLEN(3);
+        iv_push(&refs, f, n);
+        w->ref_len[r] = n;
+        f = FIELD(4), n = FLEN(4);
+        w->alt_valid[r] = !(n == 0 || (n == 1 && f[0] == '.'));
+        f = FIELD(5), n = FLEN(5);
+        if (n == 1 && f[0] == '.') {
+            w->qual_valid[r] = 0;
+            w->qual[r] = 0.0f;
+        } else {
+            char buf[128];
+            if (n >= (int32_t)sizeof(buf) || !rust_f32_grammar(f, n)) {
+                w->err_row = r;
+                break;
+            }
+            memcpy(buf, f, (size_t)n);
+            buf[n] = 0;
+            w->qual_valid[r] = 1;
+            w->qual[r] = strtof(buf, NULL);
+        }
+        f = FIELD(6), n = FLEN(6);
+        w->filter_count[r] = (n == 0 || (n == 1 && f[0] == '.')) ? 0 : split_items(&fis, f, n);
+#undef FIELD
+#undef FLEN
+        w->rows++;
+    }
+    w->id_items = ids.n, w->id_item_len = ids.len, w->id_bytes = ids.bytes, w->id_bytes_len = ids.blen;
+    w->filter_items = fis.n, w->filter_item_len = fis.len, w->filter_bytes = fis.bytes, w->filter_bytes_len = fis.blen;
+    free(refs.len);
+    w->ref_bytes = refs.bytes, w->ref_bytes_len = refs.blen;
+    return w;
+}

@@ -1,0 +1,145 @@
+"""VCF columns 2..6 built on the device (exon_gpu_vcf_next_batch with a wide projection) against the oracle's
+restatement of LazyVCFArrayBuilder::append (/root/reference/exon/exon-vcf/src/array_builder/lazy_array_builder.rs:169-216).
+Batches are imported through the Arrow C Data Interface into pyarrow (validate(full=True)), so the nested list layout is
+checked by an independent Arrow implementation.  Bit-exact: list items, bytes, validity, f32 bit patterns."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+from bgzf_util import bgzf_compress
+from exon_b200 import _abi
+from exon_b200.runtime import ExonGpuError
+
+pytestmark = pytest.mark.gpu
+NAMES = ["chrom", "pos", "id", "ref", "alt", "qual", "filter"]
+HEADER = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+
+
+def gpu_rows(ctx, files, projection, batch_rows=8192, gz=False, on_device=False):
+    """-> (dict name -> per-row python values over all batches, list of batch row counts)"""
+    out = {NAMES[p]: [] for p in projection}
+    sizes = []
+    with ctx.open_vcf(projection=projection, batch_rows=batch_rows, columns_on_device=on_device) as s:
+        for f in files:
+            if gz:
+                s.feed_gzip(bgzf_compress(bytes(f)))
+            else:
+                s.feed(f, is_last=True)
+        for b in s.batches():
+            if on_device:
+                sizes.append(b.num_rows)
+                b.release()
+                continue
+            rb = b.to_pyarrow()
+            assert rb.schema.names == [NAMES[p] for p in projection]
+            sizes.append(rb.num_rows)
+            for p in projection:
+                col = rb.column(NAMES[p])
+                if p == 5:
+                    vals = col.to_numpy(zero_copy_only=False).astype(np.float32).view(np.uint32)
+                    valid = np.asarray(col.is_valid())
+                    out["qual"] += [int(v) if ok else None for v, ok in zip(vals, valid)]
+                elif p in (2, 4, 6):
+                    out[NAMES[p]] += [None if x is None else [i.encode() for i in x] for x in col.to_pylist()]
+                elif p in (0, 3):
+                    out[NAMES[p]] += [x.encode() for x in col.to_pylist()]
+                else:
+                    out[NAMES[p]] += col.to_pylist()
+    return out, sizes
+
+
+def oracle_rows(files, batch_rows):
+    want = {n: [] for n in NAMES}
+    sizes = []
+    for f in files:
+        w = oracle.vcf_wide_rows(f)
+        for k in ("id", "ref", "alt", "qual", "filter"):
+            want[k] += w[k]
+        for b in oracle.read_batches(f, batch_rows):
+            sizes.append(b["rows"])
+            off, val = b["chrom_offsets"], b["chrom_values"].tobytes()
+            want["chrom"] += [val[off[i]:off[i + 1]] for i in range(b["rows"])]
+            want["pos"] += [int(x) for x in b["pos"]]
+    return want, sizes
+
+
+def check(ctx, files, projection, batch_rows=8192, **kw):
+    got, sizes = gpu_rows(ctx, files, projection, batch_rows, **kw)
+    want, want_sizes = oracle_rows(files, batch_rows)
+    assert sizes == want_sizes
+    for p in projection:
+        assert got[NAMES[p]] == want[NAMES[p]], NAMES[p]
+
+
+@pytest.mark.parametrize("name", ["index_vcf", "biobear_vcf", "common_all_vcf"])
+@pytest.mark.parametrize("projection", [(2, 3, 4, 5, 6), (0, 1, 2, 3, 4, 5, 6), (5,), (6, 0, 2), (4, 3)])
+def test_fixture_columns(gpu_ctx, request, name, projection):
+    check(gpu_ctx, [request.getfixturevalue(name)], projection)
+
+
+def test_small_batches_and_file_restarts(gpu_ctx, index_vcf, biobear_vcf):
+    for batch_rows in (1, 7, 64, 100):
+        check(gpu_ctx, [biobear_vcf, index_vcf, biobear_vcf], (1, 2, 3, 4, 5, 6), batch_rows)
+
+
+def test_compressed_feed(gpu_ctx, index_vcf, biobear_vcf):
+    check(gpu_ctx, [index_vcf, biobear_vcf], (0, 2, 3, 5, 6), 50, gz=True)
+
+
+def random_vcf(rng, n):
+    quals = [".", "0", "50", "99.5", "1e3", "3.5E-2", "+7", "-0", "29.9999", "0.30000001192092896", "16777217", "inf", "1.", ".5",
+             "123456789.123456789", "1.00000017881393432617187500", "7.006492321624085e-46", "3.4028235677973366e38"]
+    rows = []
+    pos = 0
+    for _ in range(n):
+        pos += rng.randrange(1, 50)
+        ids = "." if rng.random() < 0.5 else ";".join("rs%d" % rng.randrange(1, 10 ** rng.randrange(1, 9)) for _ in range(rng.randrange(1, 4)))
+        ref = "".join(rng.choice("ACGTN") for _ in range(1 if rng.random() < 0.8 else rng.randrange(1, 40)))
+        alt = "." if rng.random() < 0.1 else ",".join("".join(rng.choice("ACGT") for _ in range(rng.randrange(1, 5))) for _ in range(rng.randrange(1, 3)))
+        flt = rng.choice([".", "PASS", "q10", "q10;s50", "LowQual;q10;s50"])
+        info = rng.choice([".", "DP=10", "DP=3;AF=0.5;DB"])
+        tail = "" if rng.random() < 0.5 else "\tGT\t0/1"
+        rows.append(f"{rng.choice(['1', '2', 'chrX'])}\t{pos}\t{ids}\t{ref}\t{alt}\t{rng.choice(quals)}\t{flt}\t{info}{tail}")
+    return (HEADER + "\n".join(rows) + ("\n" if rng.random() < 0.7 else "")).encode()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_rows(gpu_ctx, seed):
+    rng = random.Random(1000 + seed)
+    files = [random_vcf(rng, rng.choice([1, 33, 2000, 9000])) for _ in range(rng.randrange(1, 4))]
+    check(gpu_ctx, files, (0, 1, 2, 3, 4, 5, 6), rng.choice([8192, 1000, 17]))
+    check(gpu_ctx, files, tuple(rng.sample(range(2, 7), 3)), 8192)
+
+
+def test_device_resident_batches(gpu_ctx, index_vcf):
+    _, sizes = gpu_rows(gpu_ctx, [index_vcf], (2, 3, 4, 5, 6), 100, on_device=True)
+    assert sum(sizes) == 621 and sizes[:-1] == [100] * 6
+
+
+def test_errors(gpu_ctx):
+    def run(text, projection):
+        with gpu_ctx.open_vcf(projection=projection) as s:
+            s.feed(text, is_last=True)
+            return [b.to_pyarrow() for b in s.batches()]
+
+    ok = (HEADER + "1\t5\t.\tA\tC\t50\tPASS\t.\n").encode()
+    assert run(ok, (5,))[0].column("qual").to_pylist() == [50.0]
+    with pytest.raises(ExonGpuError) as e:
+        run((HEADER + "1\t5\t.\tA\tC\t50\tPASS\n").encode(), (3,))  # 7 fields
+    assert e.value.code == _abi.ERR_PARSE
+    with pytest.raises(ExonGpuError) as e:
+        run((HEADER + "1\t5\t.\tA\tC\t5x\tPASS\t.\n").encode(), (5,))
+    assert e.value.code == _abi.ERR_PARSE
+    assert run((HEADER + "1\t5\t.\tA\tC\t5x\tPASS\t.\n").encode(), (3,))[0].column("ref").to_pylist() == ["A"]  # QUAL not projected: not parsed
+    with pytest.raises(ExonGpuError) as e:
+        run((HEADER + "1\t5\t.\tA\tC\t" + "1" * 37 + "\tPASS\t.\n").encode(), (5,))
+    assert e.value.code == _abi.ERR_UNSUPPORTED
+    for col in (7, 8):
+        with pytest.raises(ExonGpuError) as e:
+            gpu_ctx.open_vcf(projection=(col,))
+        assert e.value.code == _abi.ERR_UNSUPPORTED
+    with pytest.raises(ExonGpuError):
+        gpu_ctx.open_vcf(projection=(2, 2))
+    assert run(HEADER.encode(), (2, 5)) == []  # header only: no batches
