@@ -371,6 +371,29 @@ def run_b200(args):
                                                     "rows_per_s": n_rows / ms * 1e3, "algorithmic_bytes": col_bytes,
                                                     "algorithmic_gbs": col_bytes / kk / 1e6,
                                                     "frac_of_measured_peak": col_bytes / kk / 1e6 / peak}
+        # wide columns: text -> Arrow {id, ref, alt, qual, filter} (vcf_wide.cu), device resident, second build timed
+        for rep in range(2):
+            with ctx.open_vcf(projection=(2, 3, 4, 5, 6), columns_on_device=True) as st:
+                for d, f in zip(dbufs, files):
+                    st.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+                e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+                torch.cuda.synchronize()
+                l0 = ctx.launch_count()
+                e0.record(tstream)
+                first = st.next_batch()
+                e1.record(tstream)
+                torch.cuda.synchronize()
+                w_ms, w_launches = e0.elapsed_time(e1), ctx.launch_count() - l0
+                first.release()
+                if rep == 1:
+                    batches = -(-n_rows // 8192)
+                    # id: validity + list offsets (all NULL here); ref: offsets + 1 B; alt: validity; qual: validity + f32;
+                    # filter: list offsets + child offsets + "PASS"
+                    out_bytes = 3 * n_rows // 8 + 4 * 3 * (n_rows + batches) + n_rows + 4 * n_rows + 4 * (n_rows + batches) + 4 * n_rows
+                    extra["wide_columns_2_6"] = {"ms": w_ms, "rows_per_s": n_rows / w_ms * 1e3, "launches": w_launches,
+                                                 "algorithmic_bytes": body_bytes + out_bytes,
+                                                 "algorithmic_gbs": (body_bytes + out_bytes) / w_ms / 1e6,
+                                                 "frac_of_measured_peak": (body_bytes + out_bytes) / w_ms / 1e6 / peak}
         line["extra"] = extra
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

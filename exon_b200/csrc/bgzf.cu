@@ -709,10 +709,12 @@ int VcfStream::flush_gz() {
         }
         uint8_t *dt = (uint8_t *)d_gz_tab;
         const size_t bm_words = bgzf_assign_bitmap(members.data(), members.size());
+        size_t comp_bytes = 0;
+        for (const BgzfMember &m : members) comp_bytes += m.in_len;
         CUDA_TRY(cudaMemcpyAsync(dt, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
         const int init_flags[2] = {0, 0x7FFFFFFF};
         CUDA_TRY(cudaMemcpyAsync(dt + tab_bytes, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
-        if (int rc = bgzf_inflate_launch(ctx, (const uint8_t *)d_gz, (const BgzfMember *)dt, (int)members.size(), (uint32_t *)(dt + tab_bytes), bm_words))
+        if (int rc = bgzf_inflate_launch(ctx, (const uint8_t *)d_gz, (const BgzfMember *)dt, (int)members.size(), (uint32_t *)(dt + tab_bytes), bm_words, comp_bytes))
             return rc;
         // flags + per file: first bytes (header probe) and the last byte, all in one round trip
         if (int rc = ctx->ensure_scratch(0, 64 + files.size() * (kProbe + 16))) return rc;
@@ -810,7 +812,7 @@ extern "C" int exon_gpu_gzip_inflate(exon_gpu_ctx *c, const uint8_t *data, size_
     const int init_flags[2] = {0, 0x7FFFFFFF};
     CUDA_TRY(cudaMemcpyAsync(scr + o_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaEventRecord(c->ev0, st));
-    if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), (uint32_t *)(scr + o_flags), bm_words)) return rc;
+    if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), (uint32_t *)(scr + o_flags), bm_words, len)) return rc;
     CUDA_TRY(cudaEventRecord(c->ev1, st));
     c->timed = true;
     CUDA_TRY(cudaMemcpyAsync(c->h_scratch, scr + o_flags, 8, cudaMemcpyDeviceToHost, st));

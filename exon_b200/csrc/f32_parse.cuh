@@ -18,8 +18,10 @@ namespace exon {
 
 #ifdef __CUDACC__
 #define EXON_HD __host__ __device__
+#define EXON_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define EXON_HD
+#define EXON_HD_NOINLINE
 #endif
 
 constexpr int kF32Ok = 0, kF32Malformed = 1, kF32Unsupported = 2;

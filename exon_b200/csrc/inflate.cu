@@ -95,17 +95,20 @@ struct LaneBits {
     }
 };
 
-// per-lane canonical code description (local memory): used to build the primary table and to decode codes longer than it
+// per-lane canonical code description (local memory): used to build the primary table; `sym` also serves codes longer than it
+template <int N>
 struct Canon {
-    uint16_t sym[288];
+    uint16_t sym[N];
     uint16_t cnt[16];
-    uint16_t lim[16];  // (first code of length L + cnt[L]) << (15 - L): a 15-bit MSB-first prefix below it has length <= L
-    int16_t off[16];   // index of the first symbol of length L in sym[] - first code of length L
 };
 
-// Builds cnt / sym from lens[0..n) and fills the primary table tab[0 .. 1 << PB): entry = sym << 4 | len, 0 = longer code.
+// Builds cnt / sym from lens[0..n) and fills the primary table tab[0 .. 1 << PB): entry = sym << LS | len, 0 = longer code
+// (LS = 4 for the 16-bit tables, 3 for the 8-bit distance table whose lengths are <= 7).  For lengths 8..15 it also leaves,
+// in shared memory, lim[L - 8] = (first code of length L + cnt[L]) << (15 - L) -- a 15-bit MSB-first prefix below it has
+// length <= L -- and off[L - 8] = index of the first symbol of length L in sym[] - first code of length L.
 // false on an over-subscribed code.
-__device__ bool canon_table(const uint8_t *lens, int n, int PB, uint16_t *tab, Canon &C) {
+template <class E, int LS, class CanonT>
+__device__ bool canon_table(const uint8_t *lens, int n, int PB, E *tab, CanonT &C, uint16_t *lim, int16_t *off) {
     uint16_t offs[16], next[16];
 #pragma unroll
     for (int l = 0; l < 16; ++l) C.cnt[l] = 0;
@@ -121,13 +124,15 @@ __device__ bool canon_table(const uint8_t *lens, int n, int PB, uint16_t *tab, C
         left -= C.cnt[l];
         if (left < 0) return false;
         next[l] = (uint16_t)code;
-        C.lim[l] = (uint16_t)((code + C.cnt[l]) << (15 - l));
-        C.off[l] = (int16_t)((int)offs[l] - (int)code);
+        if (lim && l >= 8) {
+            lim[l - 8] = (uint16_t)((code + C.cnt[l]) << (15 - l));
+            off[l - 8] = (int16_t)((int)offs[l] - (int)code);
+        }
         code = (code + C.cnt[l]) << 1;
         if (l < 15) offs[l + 1] = (uint16_t)(offs[l] + C.cnt[l]);
     }
     uint32_t *t32 = reinterpret_cast<uint32_t *>(tab);
-    for (int i = 0; i < (1 << PB) / 2; ++i) t32[i] = 0u;
+    for (int i = 0; i < (int)((sizeof(E) << PB) / 4); ++i) t32[i] = 0u;
     for (int s = 0; s < n; ++s) {
         const int L = lens[s];
         if (!L) continue;
@@ -135,28 +140,41 @@ __device__ bool canon_table(const uint8_t *lens, int n, int PB, uint16_t *tab, C
         const uint32_t c = next[L]++;
         if (L <= PB) {
             const uint32_t rev = __brev(c) >> (32 - L);
-            const uint16_t e = (uint16_t)((s << 4) | L);
+            const E e = (E)((s << LS) | L);
             for (uint32_t i = rev; i < (1u << PB); i += (1u << L)) tab[i] = e;
         }
     }
     return true;
 }
 
-// The code at bit 0 of `bits` (LSB first) is longer than PB bits: canonical decode from length PB + 1 on its 15-bit
-// MSB-first prefix.  sym | len << 16, or 0xFFFFFFFF when no code matches.
-template <int PB>
-__device__ __forceinline__ uint32_t canon_long(uint32_t bits, const Canon &C) {
+// The code at bit 0 of `bits` (LSB first) is longer than PB (>= 7) bits.  lim[] is non-decreasing in the length, so the
+// length is PB + 1 + the number of lengths whose limit the 15-bit MSB-first prefix has reached: no branches, the limits
+// come from shared memory in one go, and a single dependent local load fetches the symbol.
+// sym | len << 16, or 0xFFFFFFFF when no code matches.
+template <int PB, class CanonT>
+__device__ __forceinline__ uint32_t canon_long(uint32_t bits, const uint16_t *lim, const int16_t *off, const CanonT &C) {
     const uint32_t c15 = __brev(bits) >> 17;
+    const uint4 L = *reinterpret_cast<const uint4 *>(lim);
+    const uint32_t lw[4] = {L.x, L.y, L.z, L.w};
+    int len = PB + 1;
 #pragma unroll
-    for (int len = PB + 1; len <= 15; ++len)
-        if (c15 < C.lim[len]) return (uint32_t)C.sym[(int)C.off[len] + (int)(c15 >> (15 - len))] | ((uint32_t)len << 16);
-    return 0xFFFFFFFFu;
+    for (int l = PB + 1; l <= 15; ++l) {
+        const uint32_t v = (lw[(l - 8) >> 1] >> (((l - 8) & 1) * 16)) & 0xFFFFu;
+        len += c15 >= v ? 1 : 0;
+    }
+    if (len > 15) return 0xFFFFFFFFu;
+    return (uint32_t)C.sym[(int)off[len - 8] + (int)(c15 >> (15 - len))] | ((uint32_t)len << 16);
 }
 
+// per-lane tables in shared memory: 2^LB x u16 + 2^DB x u8 + 64 B of limits / offsets
 template <int LB, int DB>
 struct LaneTabs {
-    uint16_t lit[1 << LB];
-    uint16_t dist[1 << DB];
+    uint16_t lit[1 << LB];  // sym << 4 | len
+    uint8_t dist[1 << DB];  // sym << 3 | len (DB <= 7)
+    __align__(16) uint16_t llim[8];
+    __align__(16) uint16_t dlim[8];
+    int16_t loff[8];
+    int16_t doff[8];
 };
 
 template <int LB, int DB>
@@ -165,7 +183,9 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
     extern __shared__ __align__(16) uint8_t dec_smem_raw[];
     LaneTabs<LB, DB> &T = reinterpret_cast<LaneTabs<LB, DB> *>(dec_smem_raw)[threadIdx.x];
     const int gt = blockIdx.x * (kDecWarps * 32) + threadIdx.x, nt = gridDim.x * (kDecWarps * 32);
-    Canon CL, CD;  // lit/len and distance codes of the current block
+    static_assert(LB >= 7 && LB <= 9 && DB == 7, "limits / offsets in shared memory start at length 8; the 8-bit distance table holds lengths <= 7");
+    Canon<288> CL;  // lit/len code of the current block (and, while the header is read, the code-length code)
+    Canon<32> CD;   // distance code
     uint8_t lens[320];
 #pragma unroll 1
     for (int mi = gt; mi < n_members; mi += nt) {
@@ -222,7 +242,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                 for (int i = 0; i < 19; ++i) cl[i] = 0;
                 for (int i = 0; i < ncl; ++i) cl[c_clen_order2[i]] = (uint8_t)br.take(3);
                 // the code-length code (7-bit codes at most) borrows the literal table's place and CL's arrays
-                if (nlit > 286 || ndist > 30 || !canon_table(cl, 19, 7, T.lit, CL)) {
+                if (nlit > 286 || ndist > 30 || !canon_table<uint16_t, 4>(cl, 19, 7, T.lit, CL, nullptr, nullptr)) {
                     err = kInfErrData;
                     break;
                 }
@@ -271,7 +291,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                 for (int s = 0; s < 32; ++s) lens[288 + s] = tmp[s];
             }
             // an incomplete distance code with a single symbol is legal (RFC 1951 3.2.7); over-subscription is not
-            if (!canon_table(lens, 288, LB, T.lit, CL) || !canon_table(lens + 288, 30, DB, T.dist, CD)) {
+            if (!canon_table<uint16_t, 4>(lens, 288, LB, T.lit, CL, T.llim, T.loff) ||
+                !canon_table<uint8_t, 3>(lens + 288, 30, DB, T.dist, CD, T.dlim, T.doff)) {
                 err = kInfErrData;
                 break;
             }
@@ -281,7 +302,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                 uint32_t w = br.peek();
                 uint32_t e = T.lit[w & ((1u << LB) - 1u)];
                 if (!e) {
-                    const uint32_t r = canon_long<LB>(w, CL);
+                    const uint32_t r = canon_long<LB>(w, T.llim, T.loff, CL);
                     if (r == 0xFFFFFFFFu) {
                         err = kInfErrData;
                         break;
@@ -320,16 +341,16 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                 br.skip(clen + lx);  // <= 15 + 5
                 w = br.peek();
                 e = T.dist[w & ((1u << DB) - 1u)];
+                int dlen = (int)(e & 7u), ds = (int)(e >> 3);
                 if (!e) {
-                    const uint32_t r = canon_long<DB>(w, CD);
+                    const uint32_t r = canon_long<DB>(w, T.dlim, T.doff, CD);
                     if (r == 0xFFFFFFFFu) {
                         err = kInfErrData;
                         break;
                     }
-                    e = ((r & 0xFFFFu) << 4) | (r >> 16);
+                    dlen = (int)(r >> 16);
+                    ds = (int)(r & 0xFFFFu);
                 }
-                const int dlen = (int)(e & 15u);
-                const int ds = (int)(e >> 4);
                 if (ds >= 30) {
                     err = kInfErrData;
                     break;
@@ -543,7 +564,8 @@ size_t bgzf_assign_bitmap(BgzfMember *m, size_t n) {
 // Enqueues the inflate of `n_members` members (table in device memory; in_off relative to d_comp, out_addr absolute,
 // bm_off from bgzf_assign_bitmap) on the context's stream.  d_flags: two words of device scratch, {0, INT_MAX} before
 // the launch.
-int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words) {
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words,
+                        size_t comp_bytes) {
     if (n_members <= 0) return EXON_GPU_OK;
     static const int use_v1 = [] {
         const char *e = getenv("EXON_GPU_INFLATE_V1");
@@ -564,17 +586,16 @@ int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table
     }
     uint32_t *bm = (uint32_t *)c->inf_bitmap;
     CUDA_TRY(cudaMemsetAsync(bm, 0, bm_bytes, c->stream));
-    static const int tabs = [] {
+    // Table size: 9-bit literal tables decode faster (fewer long-code fallbacks, and 2 CTAs per SM leave the L1 to the
+    // input streams) but hold only 128 lanes per SM; 8-bit tables put 320 lanes on an SM.  A launch that fits one wave of
+    // the 9-bit kernel, or that is literal-heavy (compressed > 40 % of the output: BAM), takes the 9-bit tables.
+    // EXON_GPU_INFLATE_TABLES = 87 | 97 forces one.
+    static const int forced = [] {
         const char *e = getenv("EXON_GPU_INFLATE_TABLES");
-        return e ? atoi(e) : 86;
+        return e ? atoi(e) : 0;
     }();
-    int rc;
-    switch (tabs) {
-        case 86: rc = launch_decode<8, 6>(c, d_comp, d_table, n_members, bm, d_flags); break;
-        case 87: rc = launch_decode<8, 7>(c, d_comp, d_table, n_members, bm, d_flags); break;
-        case 96: rc = launch_decode<9, 6>(c, d_comp, d_table, n_members, bm, d_flags); break;
-        default: rc = launch_decode<9, 7>(c, d_comp, d_table, n_members, bm, d_flags); break;
-    }
+    const bool wide9 = forced ? forced == 97 : (n_members <= 2 * c->sm_count * kDecWarps * 32 || (double)comp_bytes > 0.4 * 32.0 * (double)bitmap_words);
+    const int rc = wide9 ? launch_decode<9, 7>(c, d_comp, d_table, n_members, bm, d_flags) : launch_decode<8, 7>(c, d_comp, d_table, n_members, bm, d_flags);
     if (rc) return rc;
     static int occ = 0;
     if (!occ) {

@@ -217,7 +217,8 @@ int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, i
 
 int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uint64_t *total_out);
 size_t bgzf_assign_bitmap(BgzfMember *m, size_t n);
-int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words);
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words,
+                        size_t comp_bytes);
 int bgzf_inflate_launch_v1(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags);
 
 // defined in gff_scan.cu
@@ -253,7 +254,7 @@ struct WideChildSlot {
     const void *item_bufs[3];
 };
 bool wide_wanted(const std::vector<int> &projection);
-int wide_build(VcfStream *s, const std::vector<long long> &batch_row0, int64_t n_rows, WideStore **out);
+int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows_io, WideStore **out);
 void wide_free(WideStore *w);
 void wide_export(const WideStore *w, int col, int64_t b, int64_t rows, ArrowArray *a, WideChildSlot *slot);
 

@@ -580,6 +580,14 @@ int build_columns(VcfStream *s) {
     std::vector<Piece> pieces;
     s->cut_pieces(pieces);
     if (pieces.empty()) return EXON_GPU_OK;  // zero rows
+    if (!c->want_chrom && !c->want_pos && wide_wanted(c->projection)) {
+        // only columns 2..6: the line index of the wide build also yields the batch table
+        int64_t n = -1;
+        if (int rc = wide_build(s, &c->batch_row0, &n, &c->wide)) return rc;
+        c->n_rows = n;
+        c->n_batches = (int64_t)c->batch_row0.size() - 1;
+        return EXON_GPU_OK;
+    }
     constexpr int kTile = 512 * kColU;
     std::vector<ScanSeg> h_segs;
     std::vector<long long> file_tiles;  // first tile of every piece that starts a file
@@ -673,8 +681,7 @@ int build_columns(VcfStream *s) {
         for (long long r = file_row0[f]; r < file_row0[f + 1]; r += c->batch_rows) c->batch_row0.push_back(r);
     c->n_batches = (int64_t)c->batch_row0.size();
     c->batch_row0.push_back(n_rows);
-    if (!c->want_chrom && !c->want_pos)  // no K2 column: row counts only (empty projection) or wide columns only
-        return wide_wanted(c->projection) ? wide_build(s, c->batch_row0, n_rows, &c->wide) : EXON_GPU_OK;
+    if (!c->want_chrom && !c->want_pos) return EXON_GPU_OK;  // empty projection: row counts only
 
     // ---- outputs + scratch B: absolute u32 offsets | batch_row0 | batch_v0 ----
     const size_t nb1 = (size_t)c->n_batches + 1;
@@ -735,7 +742,10 @@ int build_columns(VcfStream *s) {
         }
         CUDA_TRY(cudaStreamSynchronize(st));
     }
-    if (wide_wanted(c->projection)) return wide_build(s, c->batch_row0, n_rows, &c->wide);
+    if (wide_wanted(c->projection)) {
+        int64_t n = n_rows;
+        return wide_build(s, &c->batch_row0, &n, &c->wide);
+    }
     return EXON_GPU_OK;
 }
 

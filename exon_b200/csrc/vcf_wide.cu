@@ -41,7 +41,7 @@ namespace {
 constexpr uint32_t kWErrFields = 1u;       // fewer than 8 tab-separated fields
 constexpr uint32_t kWErrQual = 2u;         // QUAL is not a float literal
 constexpr uint32_t kWErrQualDigits = 4u;   // QUAL has more than 36 significant digits
-constexpr uint32_t kWErrFieldLen = 8u;     // a field of 2 GiB or more
+constexpr uint32_t kWErrFieldLen = 8u;     // a line of 2 GiB or more
 
 enum { kIdE = 0, kIdB = 1, kRefB = 2, kFiE = 3, kFiB = 4, kNScan = 5 };
 
@@ -64,14 +64,30 @@ struct WideArgs {
     unsigned long long *first_bad_row;
 };
 
-// tabs 0..6 of the line [ls, le): false when the line has fewer than 8 fields
-__device__ __forceinline__ bool find_tabs(const uint8_t *ls, const uint8_t *le, const uint8_t *tab[7]) {
+// Offsets (from ls) of tabs 0..6 of the line [ls, le); false when the line has fewer than 8 fields.  Aligned 8-byte loads,
+// exact SWAR tab flags, bytes outside the line masked off; the seven offsets stay in registers (static indices only).
+__device__ __forceinline__ bool find_tabs(const uint8_t *ls, const uint8_t *le, int32_t t[7]) {
+    const uint8_t *wp = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(ls) & ~(uintptr_t)7);
+    int32_t off = (int32_t)(wp - ls);  // <= 0
     int nt = 0;
-    for (const uint8_t *p = ls; p < le; ++p) {
-        if (__ldg(p) == '\t') {
-            tab[nt++] = p;
-            if (nt == 7) return true;
+    while (wp < le) {
+        const unsigned long long w = __ldg(reinterpret_cast<const unsigned long long *>(wp));
+        const unsigned long long x = w ^ 0x0909090909090909ull;
+        const unsigned long long y = (x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full;
+        unsigned long long m = ~(y | x | 0x7F7F7F7F7F7F7F7Full);  // 0x80 in every byte that is a tab
+        if (off < 0) m &= ~0ull << (8 * -off);
+        const long long rem = le - wp;
+        if (rem < 8) m &= (1ull << (8 * rem)) - 1ull;
+        while (m) {
+            const int32_t p = off + ((__ffsll((long long)m) - 1) >> 3);
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+                if (nt == k) t[k] = p;
+            if (++nt == 7) return true;
+            m &= m - 1ull;
         }
+        wp += 8;
+        off += 8;
     }
     return false;
 }
@@ -90,16 +106,19 @@ __global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= a.n_rows) return;
     const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
-    const uint8_t *tab[7];
+    int32_t to[7];
     uint32_t err = 0;
     int32_t c[kNScan] = {0, 0, 0, 0, 0};
     uint8_t rf = 0;
     float q = 0.0f;
-    if (!find_tabs(ls, le, tab)) {
-        err = kWErrFields;
-    } else if (tab[6] - tab[1] > 0x7FFFFFF0ll) {
+    if (le - ls > 0x7FFFFFF0ll) {
         err = kWErrFieldLen;
+    } else if (!find_tabs(ls, le, to)) {
+        err = kWErrFields;
     } else {
+        const uint8_t *tab[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) tab[k] = ls + to[k];
         if (a.want_id) {
             const uint8_t *f = tab[1] + 1;
             const int32_t n = (int32_t)(tab[2] - f);
@@ -114,9 +133,20 @@ __global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__
             const uint8_t *f = tab[4] + 1;
             const int64_t n = tab[5] - f;
             if (!(n == 1 && __ldg(f) == '.')) {
-                const int rc = n > 4096 ? kF32Malformed : parse_f32_rust(f, (int)n, &q);
-                if (rc == kF32Ok) rf |= 4u;
-                else err |= rc == kF32Unsupported ? kWErrQualDigits : kWErrQual;
+                // the usual QUAL is a short unsigned integer: exact in f32 below 2^24; everything else goes to the parser
+                uint32_t v = 0;
+                bool plain = n >= 1 && n <= 7;
+                for (int i = 0; plain && i < (int)n; ++i) {
+                    const uint32_t d = (uint32_t)__ldg(f + i) - '0';
+                    plain = d <= 9u;
+                    v = v * 10u + d;
+                }
+                if (plain) {
+                    q = (float)v;
+                    rf |= 4u;
+                } else {
+                    rf |= 8u;  // left to vw_qual_kernel
+                }
             }
         }
         if (a.want_filter) {
@@ -136,6 +166,29 @@ __global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__
     }
 }
 
+// QUAL of the rows the measure pass did not settle (anything but a short unsigned integer): the exact parser
+// (128-bit digits, 512-bit comparisons) lives in its own kernel so that it does not shape the register budget of the row pass.
+__global__ void __launch_bounds__(256) vw_qual_kernel(const __grid_constant__ WideArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= a.n_rows) return;
+    const uint8_t rf = a.rowflags[r];
+    if (!(rf & 8u)) return;
+    const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
+    int32_t to[7];
+    if (!find_tabs(ls, le, to)) return;
+    const uint8_t *f = ls + to[4] + 1;
+    const int64_t n = to[5] - to[4] - 1;
+    float q = 0.0f;
+    const int rc = n > 4096 ? kF32Malformed : parse_f32_rust(f, (int)n, &q);
+    if (rc == kF32Ok) {
+        a.qual[r] = q;
+        a.rowflags[r] = (uint8_t)((rf & ~8u) | 4u);
+    } else {
+        atomicOr(a.flags, rc == kF32Unsupported ? kWErrQualDigits : kWErrQual);
+        atomicMin(a.first_bad_row, (unsigned long long)r);
+    }
+}
+
 // writes the items of one list cell: child offsets (relative to the batch's first byte) and bytes
 __device__ __forceinline__ void emit_items(const uint8_t *f, int32_t n, int32_t *coff, uint8_t *val, long long v_abs, long long v_rel) {
     int32_t k = 0;
@@ -150,27 +203,54 @@ __device__ __forceinline__ void emit_items(const uint8_t *f, int32_t n, int32_t 
 
 __global__ void __launch_bounds__(256) vw_emit_kernel(const __grid_constant__ WideArgs a) {
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (r >= a.n_rows) return;
-    // batch of the row: last b with brow[b] <= r
-    int64_t lo = 0, hi = a.n_batches;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(&a.brow[mid]) <= r) lo = mid;
-        else hi = mid;
+    // batch of the row: last b with brow[b] <= r.  Rows of a block are consecutive: one binary search per block, then a
+    // short walk (a block spans more than two batches only when batches are tiny)
+    __shared__ long long s_b0;
+    if (threadIdx.x == 0) {
+        const int64_t rb = (int64_t)blockIdx.x * 256;
+        int64_t lo = 0, hi = a.n_batches;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(&a.brow[mid]) <= rb) lo = mid;
+            else hi = mid;
+        }
+        s_b0 = lo;
     }
-    const int64_t b = lo, r0 = __ldg(&a.brow[b]);
+    __syncthreads();
+    if (r >= a.n_rows) return;
+    int64_t b = s_b0;
+    while (__ldg(&a.brow[b + 1]) <= r) ++b;
+    const int64_t r0 = __ldg(&a.brow[b]);
     const int in_batch = (int)(r - r0);
     const bool last = r + 1 == __ldg(&a.brow[b + 1]);
     const uint8_t rf = a.rowflags[r];
     const uint32_t bit = 1u << (in_batch & 31);
     const int64_t word = b * a.wpb + (in_batch >> 5);
-    if (a.want_alt && (rf & 2u)) atomicOr(a.alt_valid + word, bit);
-    if (a.want_qual && (rf & 4u)) atomicOr(a.qual_valid + word, bit);
-    if (a.want_id && (rf & 1u)) atomicOr(a.id_valid + word, bit);
+    {
+        // validity bits: the lanes of a warp hold consecutive rows, so they fall into one or two bitmap words; one atomic per
+        // word and column instead of one per row
+        const uint32_t peers = __match_any_sync(__activemask(), word);
+        const bool leader = (threadIdx.x & 31) == __ffs((int)peers) - 1;
+        if (a.want_alt) {
+            const uint32_t v = __reduce_or_sync(peers, (rf & 2u) ? bit : 0u);
+            if (leader && v) atomicOr(a.alt_valid + word, v);
+        }
+        if (a.want_qual) {
+            const uint32_t v = __reduce_or_sync(peers, (rf & 4u) ? bit : 0u);
+            if (leader && v) atomicOr(a.qual_valid + word, v);
+        }
+        if (a.want_id) {
+            const uint32_t v = __reduce_or_sync(peers, (rf & 1u) ? bit : 0u);
+            if (leader && v) atomicOr(a.id_valid + word, v);
+        }
+    }
     if (!(a.want_id || a.want_ref || a.want_filter)) return;
     const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
+    int32_t to[7];
+    if (le - ls > 0x7FFFFFF0ll || !find_tabs(ls, le, to)) return;  // reported by the measure pass
     const uint8_t *tab[7];
-    if (!find_tabs(ls, le, tab)) return;  // reported by the measure pass
+#pragma unroll
+    for (int k = 0; k < 7; ++k) tab[k] = ls + to[k];
     const int64_t lrow = b * (int64_t)(a.batch_rows + 1) + in_batch;
     if (a.want_id) {
         const long long e = a.pre[kIdE][r], e0 = a.pre[kIdE][r0], v = a.pre[kIdB][r], v0 = a.pre[kIdB][r0];
@@ -253,8 +333,9 @@ bool wide_wanted(const std::vector<int> &projection) {
     return false;
 }
 
-// The caller (build_columns) holds ctx->work_mu and has computed the batch table.
-int wide_build(VcfStream *s, const std::vector<long long> &batch_row0, int64_t n_rows, WideStore **out) {
+// The caller (build_columns) holds ctx->work_mu.  *n_rows < 0: no K2 column is projected and the batch table is not known
+// yet; it is derived here from the line index (batches restart at every file) and handed back.
+int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows_io, WideStore **out) {
     Ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     auto *w = new (std::nothrow) WideStore();
@@ -264,25 +345,34 @@ int wide_build(VcfStream *s, const std::vector<long long> &batch_row0, int64_t n
     w->on_device = s->columns_on_device;
     w->batch_rows = s->batch_rows;
     w->wpb = ((s->batch_rows + 63) / 64) * 2;
-    w->n_rows = n_rows;
-    w->n_batches = (int64_t)batch_row0.size() - 1;
-    w->batch_row0 = batch_row0;
     for (int p : s->projection) w->want[p] = true;
     for (int p = 7; p < 9; ++p)
         if (w->want[p])
             return fail(EXON_GPU_ERR_UNSUPPORTED, "vcf_next_batch: column %d (%s) is re-serialised by the reference builder and is not built on the device yet",
                         p, p == 7 ? "info" : "formats");
+    if (*n_rows_io == 0) return EXON_GPU_OK;
+
+    // per-row temporaries in scratch_b behind the line tables: 5 counts (i32) | 5 prefixes (i64) | flags
+    const size_t per_line = kNScan * 4 + kNScan * 8 + 1;
+    LineIndex li;
+    if (int rc = build_line_index(s, per_line, (2 * kNScan + 4) * 256 + (1 << 20), &li)) return rc;
+    if (*n_rows_io < 0) {
+        batch_row0->clear();
+        for (size_t f = 0; f + 1 < li.file_line0.size(); ++f)
+            for (long long r = li.file_line0[f]; r < li.file_line0[f + 1]; r += w->batch_rows) batch_row0->push_back(r);
+        batch_row0->push_back(li.n_lines);
+        *n_rows_io = li.n_lines;
+    }
+    const int64_t n_rows = *n_rows_io;
+    if (li.n_lines != n_rows) return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: line index has %lld lines for %lld rows", (long long)li.n_lines, (long long)n_rows);
+    w->n_rows = n_rows;
+    w->n_batches = (int64_t)batch_row0->size() - 1;
+    w->batch_row0 = *batch_row0;
     if (n_rows == 0) return EXON_GPU_OK;
     const size_t nb1 = (size_t)w->n_batches + 1, nr1 = (size_t)n_rows + 1;
-
-    // per-row temporaries in scratch_b behind the line tables: 5 counts (i32) | 5 prefixes (i64) | flags | batch table | bases
     size_t cub_bytes = 0;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (long long *)nullptr, (int)nr1, st));
-    const size_t per_line = kNScan * 4 + kNScan * 8 + 1;
-    const size_t fixed = (2 * kNScan + 4) * 256 + al256w(cub_bytes) + 2 * al256w(nb1 * 8) + 1024;
-    LineIndex li;
-    if (int rc = build_line_index(s, per_line, fixed, &li)) return rc;
-    if (li.n_lines != n_rows) return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: line index has %lld lines for %lld rows", (long long)li.n_lines, (long long)n_rows);
+    if (cub_bytes > (1 << 20)) return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: scan scratch of %zu bytes", cub_bytes);
     uint8_t *x = li.extra;
     auto take = [&](size_t bytes) {
         uint8_t *p = x;
@@ -309,14 +399,22 @@ int wide_build(VcfStream *s, const std::vector<long long> &batch_row0, int64_t n
     }
     a.rowflags = take(nr1);
     uint8_t *cub_tmp = take(cub_bytes);
-    long long *d_brow = (long long *)take(nb1 * 8), *d_base = (long long *)take(nb1 * 8);
     unsigned long long *d_misc = (unsigned long long *)take(64);
+    // batch table | per-scan batch bases (small, sized by the batch count: from the pool)
+    long long *d_brow = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&d_brow, (kNScan + 1) * al256w(nb1 * 8), st));
+    struct PoolFree {
+        void *p;
+        cudaStream_t st;
+        ~PoolFree() { cudaFreeAsync(p, st); }
+    } d_brow_guard{d_brow, st};
+    auto d_base = [&](int k) { return reinterpret_cast<long long *>(reinterpret_cast<uint8_t *>(d_brow) + (size_t)(k + 1) * al256w(nb1 * 8)); };
     a.brow = d_brow;
     a.flags = reinterpret_cast<uint32_t *>(d_misc);
     a.first_bad_row = d_misc + 1;
     const unsigned long long init_misc[2] = {0ull, ~0ull};
     CUDA_TRY(cudaMemcpyAsync(d_misc, init_misc, sizeof(init_misc), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_brow, batch_row0.data(), nb1 * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_brow, batch_row0->data(), nb1 * 8, cudaMemcpyHostToDevice, st));
 
     auto dev_alloc = [&](WideBuf &b, size_t bytes, bool zero) -> int {
         b.bytes = std::max<size_t>(bytes, 8);
@@ -337,17 +435,20 @@ int wide_build(VcfStream *s, const std::vector<long long> &batch_row0, int64_t n
     const unsigned grid = (unsigned)((n_rows + 255) / 256);
     vw_measure_kernel<<<grid, 256, 0, st>>>(a);
     ctx->launches.fetch_add(1);
+    if (w->want[5]) {
+        vw_qual_kernel<<<grid, 256, 0, st>>>(a);
+        ctx->launches.fetch_add(1);
+    }
     CUDA_TRY(cudaGetLastError());
     // ---- 2. scans + per-batch bases ----
     for (int k = 0; k < kNScan; ++k) {
         if (!need[k]) continue;
         size_t tb = cub_bytes;
         CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, (const int32_t *)a.cnt[k], pre[k], (int)nr1, st));
-        vw_gather_i64<<<(unsigned)((nb1 + 255) / 256), 256, 0, st>>>(pre[k], d_brow, (int64_t)nb1, d_base);
+        vw_gather_i64<<<(unsigned)((nb1 + 255) / 256), 256, 0, st>>>(pre[k], d_brow, (int64_t)nb1, d_base(k));
         ctx->launches.fetch_add(2);
         w->base[k].resize(nb1);
-        CUDA_TRY(cudaMemcpyAsync(w->base[k].data(), d_base, nb1 * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));  // d_base is reused by the next scan
+        CUDA_TRY(cudaMemcpyAsync(w->base[k].data(), d_base(k), nb1 * 8, cudaMemcpyDeviceToHost, st));
     }
     unsigned long long h_misc[2];
     CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
@@ -355,7 +456,7 @@ int wide_build(VcfStream *s, const std::vector<long long> &batch_row0, int64_t n
     if (const uint32_t e = (uint32_t)h_misc[0])
         return fail((e & ~kWErrQualDigits) ? EXON_GPU_ERR_PARSE : EXON_GPU_ERR_UNSUPPORTED, "malformed VCF record at row %llu:%s%s%s%s", h_misc[1],
                     (e & kWErrFields) ? " fewer than 8 tab-separated fields;" : "", (e & kWErrQual) ? " QUAL is not a float literal;" : "",
-                    (e & kWErrQualDigits) ? " QUAL has more than 36 significant digits;" : "", (e & kWErrFieldLen) ? " a field of 2 GiB or more;" : "");
+                    (e & kWErrQualDigits) ? " QUAL has more than 36 significant digits;" : "", (e & kWErrFieldLen) ? " a line of 2 GiB or more;" : "");
     for (int k = 0; k < kNScan; ++k) {
         if (!need[k]) continue;
         for (int64_t b = 0; b < w->n_batches; ++b)

@@ -120,6 +120,13 @@ with Context(0) as ctx:
                 b = st.next_batch()  # K2: measure, scan, emit, offsets
                 b.release()
                 c = st.filter_agg(chrom_col=0, pos_col=1, region=region)[0] if m == "k3" else st.rows()
+        elif m == "wide":
+            with ctx.open_vcf(projection=(2, 3, 4, 5, 6), columns_on_device=True) as st:
+                for d, f in zip(dbufs, files):
+                    st.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+                b = st.next_batch()  # line index, measure, scans, emit (vcf_wide.cu)
+                b.release()
+                c = st.rows()
         else:
             raise SystemExit(m)
         print(m, c, f"{ctx.last_kernel_ms():.3f} ms", flush=True)
