@@ -271,8 +271,7 @@ int exon_gpu_vcf_close(exon_gpu_stream *s) {
     if (s->d_res) cudaFree(s->d_res);
     if (s->h_res) cudaFreeHost(s->h_res);
     if (s->d_segs) cudaFree(s->d_segs);
-    if (s->d_gz) cudaFree(s->d_gz);
-    if (s->d_gz_tab) cudaFree(s->d_gz_tab);
+    s->gz_teardown();
     if (s->d_bam) cudaFree(s->d_bam);
     delete s;
     return EXON_GPU_OK;

@@ -553,27 +553,13 @@ int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
     uint64_t total = 0;
     if (len)
         if (int rc = bgzf_walk(data, len, members, &total)) return rc;
-    cudaStream_t st = ctx->stream;
     uint8_t *dst = nullptr;
     if (total > 0) {
         const size_t need = ((len + 16 + 255) & ~(size_t)255);
-        if (gz_staged + need > d_gz_cap) {
-            if (int rc = flush_gz()) return rc;  // empties the staging area
-            if (need > d_gz_cap) {
-                if (d_gz) {
-                    CUDA_TRY(cudaStreamSynchronize(st));
-                    CUDA_TRY(cudaFree(d_gz));
-                    d_gz = nullptr;
-                    d_gz_cap = 0;
-                }
-                const size_t cap = std::max(need * 2, (size_t)256 << 20);
-                CUDA_TRY(cudaMalloc(&d_gz, cap));
-                d_gz_cap = cap;
-            }
-        }
-        uint8_t *dz = (uint8_t *)d_gz + gz_staged;
-        CUDA_TRY(cudaMemcpyAsync(dz, data, len, cudaMemcpyHostToDevice, st));
-        if (!gz_pending.empty()) CUDA_TRY(cudaStreamSynchronize(st));  // the source is our own buffer, cleared on return
+        uint8_t *dz = nullptr;
+        if (int rc = gz_stage(need, &dz)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(dz, data, len, cudaMemcpyHostToDevice, gz_copy_stream));
+        if (!gz_pending.empty()) CUDA_TRY(cudaStreamSynchronize(gz_copy_stream));  // the source is our own buffer, cleared on return
         // arena space: the tail of the current block if the file fits, else a fresh block (+1 for a missing final '\n')
         if (blocks.empty() || blocks.back().used + total + 1 > blocks.back().cap) {
             DevBlock nb;
@@ -594,7 +580,7 @@ int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
     }
     gz_files.push_back(GzFile{dst, total, gz_members.size() - (total > 0 ? members.size() : 0), total > 0 ? members.size() : 0});
     file_open = false;
-    if (gz_members.size() >= 16384) return flush_gz();
+    if (gz_members.size() >= 16384) return launch_gz();
     return EXON_GPU_OK;
 }
 
@@ -640,25 +626,12 @@ int VcfStream::feed_gzip_chunk(const uint8_t *data, size_t len, uint64_t file_of
         return EXON_GPU_OK;
     }
     if (u0 >= members[0].isize && members[0].isize) return fail(EXON_GPU_ERR_ARG, "feed_bgzf_chunk: chunk start beyond its member");
-    cudaStream_t st = ctx->stream;
     // stage the compressed bytes of the selected members (one contiguous range of `data`)
     const size_t lo = (size_t)(members.front().in_off >= 18 ? members.front().in_off - 18 : 0), hi = (size_t)(members.back().in_off + members.back().in_len + 8);
     const size_t need = ((hi - lo + 16 + 255) & ~(size_t)255);
-    if (gz_staged + need > d_gz_cap) {
-        if (int rc = flush_gz()) return rc;
-        if (need > d_gz_cap) {
-            if (d_gz) {
-                CUDA_TRY(cudaStreamSynchronize(st));
-                CUDA_TRY(cudaFree(d_gz));
-                d_gz = nullptr;
-                d_gz_cap = 0;
-            }
-            const size_t cap = std::max(need * 2, (size_t)256 << 20);
-            CUDA_TRY(cudaMalloc(&d_gz, cap));
-            d_gz_cap = cap;
-        }
-    }
-    CUDA_TRY(cudaMemcpyAsync((uint8_t *)d_gz + gz_staged, data + lo, hi - lo, cudaMemcpyHostToDevice, st));
+    uint8_t *dz = nullptr;
+    if (int rc = gz_stage(need, &dz)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dz, data + lo, hi - lo, cudaMemcpyHostToDevice, gz_copy_stream));
     if (blocks.empty() || blocks.back().used + total + 1 > blocks.back().cap) {
         DevBlock nb;
         if (int rc = ctx->get_block((size_t)total + 1, &nb)) return rc;
@@ -680,65 +653,156 @@ int VcfStream::feed_gzip_chunk(const uint8_t *data, size_t len, uint64_t file_of
     f.range_lo = (int64_t)u0;
     f.range_hi = (int64_t)end_pos;
     gz_files.push_back(f);
-    if (gz_members.size() >= 16384) return flush_gz();
+    if (gz_members.size() >= 16384) return launch_gz();
     return EXON_GPU_OK;
 }
 
-// Inflates every pending member in one launch, then frames the files in feed order exactly like device-resident
-// ranges (header skipped on a host copy of each file's first bytes, last record normalised to end in '\n').
-int VcfStream::flush_gz() {
+// Staging space for `need` compressed bytes.  When the current buffer is full its group is launched and filling moves to
+// the other buffer -- after the copy stream has been told to wait for the inflate that last read that buffer.
+int VcfStream::gz_stage(size_t need, uint8_t **out) {
+    if (!gz_copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&gz_copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&gz_copied_ev, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&gz_done_ev[i], cudaEventDisableTiming));
+    }
+    if (gz_staged + need > d_gz_buf_cap[gz_cur] && gz_staged > 0) {
+        if (int rc = launch_gz()) return rc;  // moves on to the other buffer
+    }
+    if (need > d_gz_buf_cap[gz_cur]) {
+        // grow: nothing is staged in this buffer now; an earlier inflate may still be reading it
+        if (d_gz_buf[gz_cur]) {
+            if (gz_done_armed[gz_cur]) CUDA_TRY(cudaEventSynchronize(gz_done_ev[gz_cur]));
+            CUDA_TRY(cudaFree(d_gz_buf[gz_cur]));
+            d_gz_buf[gz_cur] = nullptr;
+            d_gz_buf_cap[gz_cur] = 0;
+            gz_done_armed[gz_cur] = false;
+        }
+        const size_t cap = std::max(need * 2, (size_t)256 << 20);
+        CUDA_TRY(cudaMalloc(&d_gz_buf[gz_cur], cap));
+        d_gz_buf_cap[gz_cur] = cap;
+    }
+    if (gz_staged == 0 && gz_done_armed[gz_cur]) {
+        CUDA_TRY(cudaStreamWaitEvent(gz_copy_stream, gz_done_ev[gz_cur], 0));
+        gz_done_armed[gz_cur] = false;
+    }
+    *out = (uint8_t *)d_gz_buf[gz_cur] + gz_staged;
+    return EXON_GPU_OK;
+}
+
+void VcfStream::gz_teardown() {
+    if (gz_copy_stream) cudaStreamSynchronize(gz_copy_stream);
+    for (auto &g : gz_inflight) cudaFree(g.d_tab);
+    gz_inflight.clear();
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(d_gz_buf[i]);
+        d_gz_buf[i] = nullptr;
+        if (gz_done_ev[i]) cudaEventDestroy(gz_done_ev[i]);
+        gz_done_ev[i] = nullptr;
+    }
+    if (gz_copied_ev) cudaEventDestroy(gz_copied_ev);
+    gz_copied_ev = nullptr;
+    if (gz_copy_stream) cudaStreamDestroy(gz_copy_stream);
+    gz_copy_stream = nullptr;
+}
+
+// Enqueues the inflate of every pending member as one launch on the context's stream, behind the arrival of the group's
+// compressed bytes on the copy stream.  No host synchronisation: the next group's bytes start to travel while this one
+// inflates.  harvest_gz() checks and frames the launched groups.
+int VcfStream::launch_gz() {
     if (gz_files.empty()) return EXON_GPU_OK;
     cudaStream_t st = ctx->stream;
-    std::vector<GzFile> files;
-    files.swap(gz_files);
-    std::vector<BgzfMember> members;
-    members.swap(gz_members);
-    gz_staged = 0;
-    constexpr size_t kProbe = 64 << 10;
-    if (!members.empty()) {
-        const size_t tab_bytes = (members.size() * sizeof(BgzfMember) + 255) & ~(size_t)255;
-        if (tab_bytes + 256 > d_gz_tab_cap) {
-            if (d_gz_tab) {
-                CUDA_TRY(cudaStreamSynchronize(st));
-                CUDA_TRY(cudaFree(d_gz_tab));
-                d_gz_tab = nullptr;
-                d_gz_tab_cap = 0;
-            }
-            CUDA_TRY(cudaMalloc(&d_gz_tab, (tab_bytes + 256) * 2));
-            d_gz_tab_cap = (tab_bytes + 256) * 2;
-        }
-        uint8_t *dt = (uint8_t *)d_gz_tab;
-        const size_t bm_words = bgzf_assign_bitmap(members.data(), members.size());
+    GzGroup g;
+    g.files.swap(gz_files);
+    g.members.swap(gz_members);
+    const int buf = gz_cur;
+    if (!g.members.empty()) {
+        g.tab_bytes = (g.members.size() * sizeof(BgzfMember) + 255) & ~(size_t)255;
+        CUDA_TRY(cudaMallocAsync(&g.d_tab, g.tab_bytes + 256, st));
+        uint8_t *dt = (uint8_t *)g.d_tab;
+        const size_t bm_words = bgzf_assign_bitmap(g.members.data(), g.members.size());
         size_t comp_bytes = 0;
-        for (const BgzfMember &m : members) comp_bytes += m.in_len;
-        CUDA_TRY(cudaMemcpyAsync(dt, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
+        for (const BgzfMember &m : g.members) comp_bytes += m.in_len;
+        CUDA_TRY(cudaMemcpyAsync(dt, g.members.data(), g.members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
         const int init_flags[2] = {0, 0x7FFFFFFF};
-        CUDA_TRY(cudaMemcpyAsync(dt + tab_bytes, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
-        if (int rc = bgzf_inflate_launch(ctx, (const uint8_t *)d_gz, (const BgzfMember *)dt, (int)members.size(), (uint32_t *)(dt + tab_bytes), bm_words, comp_bytes))
+        CUDA_TRY(cudaMemcpyAsync(dt + g.tab_bytes, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(gz_copied_ev, gz_copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, gz_copied_ev, 0));
+        if (int rc = bgzf_inflate_launch(ctx, (const uint8_t *)d_gz_buf[buf], (const BgzfMember *)dt, (int)g.members.size(), (uint32_t *)(dt + g.tab_bytes),
+                                         bm_words, comp_bytes)) {
+            cudaFreeAsync(g.d_tab, st);
             return rc;
-        // flags + per file: first bytes (header probe) and the last byte, all in one round trip
-        if (int rc = ctx->ensure_scratch(0, 64 + files.size() * (kProbe + 16))) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(gz_done_ev[buf], st));
+        gz_done_armed[buf] = true;
+        gz_cur ^= 1;
+    }
+    gz_staged = 0;
+    gz_inflight.push_back(std::move(g));
+    return EXON_GPU_OK;
+}
+
+// Launches what is pending, then waits for every launched group, checks it and frames its files in feed order exactly like
+// device-resident ranges (header skipped on a host copy of each file's first bytes, last record normalised to end in '\n').
+int VcfStream::flush_gz() {
+    if (int rc = launch_gz()) return rc;
+    return harvest_gz();
+}
+
+int VcfStream::harvest_gz() {
+    if (gz_inflight.empty()) return EXON_GPU_OK;
+    cudaStream_t st = ctx->stream;
+    std::vector<GzGroup> groups;
+    groups.swap(gz_inflight);
+    struct FreeTabs {
+        std::vector<GzGroup> &g;
+        cudaStream_t st;
+        ~FreeTabs() {
+            for (auto &x : g)
+                if (x.d_tab) cudaFreeAsync(x.d_tab, st);
+        }
+    } free_tabs{groups, st};
+    constexpr size_t kProbe = 64 << 10;
+    // feed order across groups
+    std::vector<GzFile> files;
+    std::vector<BgzfMember> members;
+    for (GzGroup &g : groups) {
+        for (GzFile f : g.files) {
+            f.first_member += members.size();
+            files.push_back(f);
+        }
+        members.insert(members.end(), g.members.begin(), g.members.end());
+    }
+    {
+        // flags of every group + per file: first bytes (header probe) and the last byte, all in one round trip
+        if (int rc = ctx->ensure_scratch(0, 64 + 16 * groups.size() + files.size() * (kProbe + 16))) return rc;
         uint8_t *h = (uint8_t *)ctx->h_scratch;
-        CUDA_TRY(cudaMemcpyAsync(h, dt + tab_bytes, 8, cudaMemcpyDeviceToHost, st));
+        uint8_t *h_files = h + 64 + 16 * groups.size();
+        for (size_t gi = 0; gi < groups.size(); ++gi)
+            if (groups[gi].d_tab) CUDA_TRY(cudaMemcpyAsync(h + 64 + 16 * gi, (uint8_t *)groups[gi].d_tab + groups[gi].tab_bytes, 8, cudaMemcpyDeviceToHost, st));
         for (size_t i = 0; i < files.size(); ++i) {
             if (!files[i].total) continue;
-            uint8_t *slot = h + 64 + i * (kProbe + 16);
+            uint8_t *slot = h_files + i * (kProbe + 16);
             CUDA_TRY(cudaMemcpyAsync(slot, files[i].dst, (size_t)std::min<uint64_t>(files[i].total, kProbe), cudaMemcpyDeviceToHost, st));
             const uint64_t last_at = files[i].range_lo >= 0 ? (uint64_t)files[i].range_hi - 1 : files[i].total - 1;
             CUDA_TRY(cudaMemcpyAsync(slot + kProbe, files[i].dst + last_at, 1, cudaMemcpyDeviceToHost, st));
         }
         CUDA_TRY(cudaStreamSynchronize(st));
-        const uint32_t *fl = reinterpret_cast<const uint32_t *>(h);
-        if (fl[0])
-            return fail(EXON_GPU_ERR_PARSE, "bgzf: member %d does not inflate:%s%s", (int)fl[1], (fl[0] & 1u) ? " invalid DEFLATE data;" : "",
-                        (fl[0] & 2u) ? " size differs from ISIZE;" : "");
+        size_t member0 = 0;
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            const uint32_t *fl = reinterpret_cast<const uint32_t *>(h + 64 + 16 * gi);
+            if (groups[gi].d_tab && fl[0])
+                return fail(EXON_GPU_ERR_PARSE, "bgzf: member %d does not inflate:%s%s", (int)(member0 + fl[1]), (fl[0] & 1u) ? " invalid DEFLATE data;" : "",
+                            (fl[0] & 2u) ? " size differs from ISIZE;" : "");
+            member0 += groups[gi].members.size();
+        }
     }
+    const uint8_t *h_files = (const uint8_t *)ctx->h_scratch + 64 + 16 * groups.size();
     // the probe area is reused by frame_device_range's slow path: copy what we need out of it first
     struct Probe { int64_t body_off; int last; };
     std::vector<Probe> probes(files.size(), Probe{-1, -1});
     for (size_t i = 0; i < files.size(); ++i) {
         if (!files[i].total) continue;
-        const uint8_t *slot = (const uint8_t *)ctx->h_scratch + 64 + i * (kProbe + 16);
+        const uint8_t *slot = h_files + i * (kProbe + 16);
         probes[i].body_off = probe_body_offset(slot, (size_t)std::min<uint64_t>(files[i].total, kProbe), files[i].total <= kProbe);
         probes[i].last = slot[kProbe];
     }
@@ -747,7 +811,7 @@ int VcfStream::flush_gz() {
             const GzFile &f = files[i];
             if (!f.total) continue;
             // the probe slot is read before bam_frame_file may overwrite the pinned area: copy it
-            const uint8_t *slot = (const uint8_t *)ctx->h_scratch + 64 + i * (kProbe + 16);
+            const uint8_t *slot = h_files + i * (kProbe + 16);
             std::vector<uint8_t> head(slot, slot + (size_t)std::min<uint64_t>(f.total, kProbe));
             if (int rc = bam_frame_file(f.dst, f.total, head.data(), head.size(), members.data() + f.first_member, f.n_members)) return rc;
         }

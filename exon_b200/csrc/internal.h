@@ -147,11 +147,28 @@ struct VcfStream {
     };
     std::vector<GzFile> gz_files;
     std::vector<BgzfMember> gz_members;
-    size_t gz_staged = 0;      // bytes of d_gz in use
-    void *d_gz = nullptr;      // device staging for compressed bytes
-    size_t d_gz_cap = 0;
-    void *d_gz_tab = nullptr;  // member table | flags
-    size_t d_gz_tab_cap = 0;
+    // Compressed bytes travel on their own copy stream into one of two staging buffers while the inflate of the previous
+    // group of files runs on the context's stream out of the other (bgzf.cu).
+    size_t gz_staged = 0;                        // bytes of the current staging buffer in use
+    void *d_gz_buf[2] = {nullptr, nullptr};      // device staging for compressed bytes
+    size_t d_gz_buf_cap[2] = {0, 0};
+    int gz_cur = 0;                              // staging buffer being filled
+    cudaStream_t gz_copy_stream = nullptr;
+    cudaEvent_t gz_copied_ev = nullptr;          // copy stream: the current group's bytes have arrived
+    cudaEvent_t gz_done_ev[2] = {nullptr, nullptr};  // context stream: the inflate that read staging buffer i has finished
+    bool gz_done_armed[2] = {false, false};
+    // groups whose inflate has been launched but not yet checked / framed
+    struct GzGroup {
+        std::vector<GzFile> files;
+        std::vector<BgzfMember> members;
+        void *d_tab = nullptr;  // member table | flags (stream-ordered pool)
+        size_t tab_bytes = 0;
+    };
+    std::vector<GzGroup> gz_inflight;
+    int gz_stage(size_t need, uint8_t **out);  // `need` bytes of staging (launches the pending group / grows the buffer as needed)
+    int launch_gz();                           // enqueue the inflate of the pending files; no host synchronisation
+    int harvest_gz();                          // wait for every launched group, check it, frame its files in feed order
+    void gz_teardown();
     int feed_gzip(const uint8_t *data, size_t len, bool is_last);
     // ---- BAM streams (bam.cu): one entry per inflated file ----
     struct BamFile {

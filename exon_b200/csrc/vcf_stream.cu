@@ -56,6 +56,9 @@ void VcfStream::release_all() {
     file_marks.clear();
     gz_pending.clear();
     gz_files.clear();
+    if (gz_copy_stream) cudaStreamSynchronize(gz_copy_stream);
+    for (auto &g : gz_inflight) cudaFree(g.d_tab);  // the caller has synchronised the context stream
+    gz_inflight.clear();
     bam_files.clear();
     bam_tables_dirty = true;
     bam_groups.clear();
