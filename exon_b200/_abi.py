@@ -118,10 +118,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("EXON_GPU_LIB", LIB_PATH)  # experiment builds of the same library (tools/sweep.py)
+    if not os.path.exists(path):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python -m exon_b200.build` "
                           "(nvcc, sm_100a). exon_b200 has no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     L.exon_gpu_last_error.restype = C.c_char_p
     L.exon_gpu_version.restype = C.c_char_p

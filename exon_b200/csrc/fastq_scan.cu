@@ -43,7 +43,16 @@ namespace exon {
 namespace {
 
 constexpr int kFqQueue = 256;
-using FqRing = TileRing<4096, 2, 8, 16, 368, kFqQueue * 2>;
+#ifndef EXON_FQ_TILE
+#define EXON_FQ_TILE 4096
+#endif
+#ifndef EXON_FQ_WARPS
+#define EXON_FQ_WARPS 8
+#endif
+#ifndef EXON_FQ_MINB
+#define EXON_FQ_MINB 3
+#endif
+using FqRing = TileRing<EXON_FQ_TILE, 2, EXON_FQ_WARPS, 16, 368, kFqQueue * 2>;
 constexpr int kFqU = FqRing::TILE / 512;
 
 constexpr uint32_t kFqErrPrefix = 1u;     // a definition line without '@' or a third line without '+'
@@ -63,7 +72,7 @@ struct FqArgs {
 };
 
 // ---- pass A -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FqRing::WARPS * 32, 3) fq_lines_kernel(const __grid_constant__ FqArgs a) {
+__global__ void __launch_bounds__(FqRing::WARPS * 32, EXON_FQ_MINB) fq_lines_kernel(const __grid_constant__ FqArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FqRing ring;
     ring.init(smem_raw, a.segs, a.n_tiles);
@@ -179,7 +188,7 @@ __device__ __forceinline__ void fq_line_sum(const FqRing::View &v, int ls, uint3
     }
 }
 
-__global__ void __launch_bounds__(FqRing::WARPS * 32, 3) fq_filter_kernel(const __grid_constant__ FqArgs a) {
+__global__ void __launch_bounds__(FqRing::WARPS * 32, EXON_FQ_MINB) fq_filter_kernel(const __grid_constant__ FqArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FqRing ring;
     ring.init(smem_raw, a.segs, a.n_tiles);
@@ -442,7 +451,7 @@ struct FqIndexArgs {
     const uint8_t **line_end;
 };
 
-__global__ void __launch_bounds__(FqRing::WARPS * 32, 3) fq_index_kernel(const __grid_constant__ FqIndexArgs a) {
+__global__ void __launch_bounds__(FqRing::WARPS * 32, EXON_FQ_MINB) fq_index_kernel(const __grid_constant__ FqIndexArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FqRing ring;
     ring.init(smem_raw, a.segs, a.n_tiles);
