@@ -17,8 +17,12 @@
 // first record, and the counts stand.  Otherwise the entry points are corrected from the exits and the pass runs
 // again (records that straddle members), and after a few rounds one thread per file walks the chain serially --
 // slow, but exact for any input.
+#include <cub/device/device_scan.cuh>
+
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <new>
 #include <string>
 
 #include "common.cuh"
@@ -62,6 +66,9 @@ struct BamArgs {
     const int32_t *region_ref;     // per file: refID of the region's reference in that file's header (-2: absent)
     int64_t lo, hi;
     int32_t serial;                // 1: one thread per FILE walks entries[first .. last] as a single chain
+    unsigned long long *entry_rows;  // optional out: records each walk saw (column build)
+    const uint8_t **rec_ptr;         // optional out (with entry_row0): address of every record, in file order
+    const unsigned long long *entry_row0;
 };
 
 constexpr int kBamThreads = 128;
@@ -142,11 +149,13 @@ __global__ void __launch_bounds__(kBamThreads) bam_walk_kernel(const __grid_cons
                 if (use_smem) atomicAdd(&hist[g], 1u);
                 else atomicAdd(&a.counts[g], 1ull);
             }
+            if (a.rec_ptr) a.rec_ptr[a.entry_row0[e] + my_rows] = E.base + p;
             ++my_rows;
             p += 4 + (uint64_t)(uint32_t)block_size;
         }
         exit_at = bad ? kBadExit : p;
         a.exits[e] = exit_at;
+        if (a.entry_rows) a.entry_rows[e] = my_rows;
     }
     // rows: warp sum, one atomic per warp
 #pragma unroll
@@ -374,13 +383,699 @@ int VcfStream::bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, 
         CUDA_TRY(cudaMemcpyAsync(h + 128, d + bam_o_counts, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         const unsigned int *v = reinterpret_cast<const unsigned int *>(h + 64);
-        if (v[0] == 0 && v[1] == 0) ok = true;
-        else if (v[0] == 0 || serial)
+        if (v[0] == 0 && v[1] == 0) {
+            ok = true;
+            bam_serial_ok = serial;
+        } else if (v[0] == 0 || serial)
             return fail(EXON_GPU_ERR_PARSE, "malformed BAM record (block_size / refID out of range, or a truncated record)");
         // else: some walks began inside a record; the entry points were corrected, go again
     }
     if (total_rows) *total_rows = (int64_t) * reinterpret_cast<const unsigned long long *>(h);
     if (counts) memcpy(counts, h + 128, (size_t)n_groups * 8);
+    return EXON_GPU_OK;
+}
+
+
+// =====================================================================================================================
+// BAM records -> Arrow columns 0..9 {name, flag, reference, start, end, mapping_quality, cigar, mate_reference, sequence,
+// quality_score} in reference-sized batches (exon_gpu_bam_next_batch).
+//
+// Replaces BatchReader::read_batch (exon/exon-bam/src/batch_reader.rs:88-107), BAMArrayBuilder::{append, finish}
+// (exon/exon-bam/src/array_builder.rs:102-218) over noodles' RecordBuf, and SemiLazyRecord::alignment_end
+// (exon/exon-bam/src/indexed_async_batch_stream.rs:43-50).  Schema: SAMSchemaBuilder::default,
+// exon/exon-sam/src/schema_builder.rs:385-401.  `tags` (column 10) is not built.
+//   1. the verified speculative walks of the fused query give every member's first record; a second walk per member
+//      writes the address of every record in file order (rows per walk -> host prefix -> rec_ptr[])
+//   2. measure   one thread per record: byte lengths of the six string columns and the quality list, the fixed-width
+//                columns (flag, start, end) and the validity flags
+//   3. 7 exclusive scans (cub)
+//   4. emit      one thread per record: batch-relative int32 offsets, bytes at their final place (CIGAR rendered as
+//                decimal length + op letter, bases decoded from 4 bits, MAPQ as a decimal string, quality bytes widened
+//                i8 -> i64), validity bits
+// Batches restart at every file.  name == "*" would be NULL in a column the reference declares non-nullable (its batch
+// construction fails): reported as EXON_GPU_ERR_PARSE here too.
+// =====================================================================================================================
+namespace {
+
+enum { kBName = 0, kBRef = 1, kBMapq = 2, kBCigar = 3, kBMate = 4, kBSeq = 5, kBQual = 6, kBNVar = 7 };
+constexpr uint32_t kBErrLayout = 1u;  // the variable part does not fit the record's block_size / bad CIGAR op / bad refID
+constexpr uint32_t kBErrName = 2u;    // missing read name ("*")
+
+struct BamFileTab {
+    long long row0;    // first record of the file (global numbering); the sentinel carries n_records
+    long long batch0;  // first batch of the file
+    int32_t ref0;      // first entry of the file's reference names in ref_off / ref_len
+    int32_t n_ref;
+};
+
+struct BamColArgs {
+    int64_t n_rows;
+    const uint8_t *const *rec_ptr;
+    const BamFileTab *files;
+    int32_t n_files;
+    const int32_t *ref_off, *ref_len;  // per reference name: offset into ref_blob, length
+    const uint8_t *ref_blob;
+    const long long *brow;  // n_batches + 1
+    int64_t n_batches;
+    int32_t batch_rows, wpb;
+    int32_t want[10];
+    int32_t *cnt[kBNVar];
+    const long long *pre[kBNVar];
+    uint8_t *rowflags;  // bit0 reference valid, bit1 start valid, bit2 end valid, bit3 mapq valid, bit4 mate valid
+    int32_t *flag;
+    long long *start, *end;
+    int32_t *off[kBNVar];  // batch-relative offsets, n_batches * (batch_rows + 1) each
+    uint8_t *val[kBNVar];  // kBQual: int64 values
+    uint32_t *valid[5];    // reference, start, end, mapq, mate
+    uint32_t *flags;
+    unsigned long long *first_bad_row;
+};
+
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ int dec_digits(uint32_t v) {
+    int n = 1;
+    while (v >= 10u) {
+        v /= 10u;
+        ++n;
+    }
+    return n;
+}
+__device__ __forceinline__ int bam_find_file(const BamFileTab *files, int n_files, long long r) {
+    int lo = 0, hi = n_files - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (files[mid].row0 <= r) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+struct BamRec {
+    const uint8_t *r;  // refID field (the byte after block_size)
+    int32_t block_size, ref_id, pos, mate_ref;
+    uint32_t l_read_name, mapq, n_cigar, flag;
+    int32_t l_seq;
+    const uint8_t *name, *cigar, *seq, *qual;
+    bool ok;
+};
+__device__ __forceinline__ BamRec bam_rec(const uint8_t *p, int32_t n_ref) {
+    BamRec R;
+    R.block_size = (int32_t)ld_u32(p);
+    R.r = p + 4;
+    R.ref_id = (int32_t)ld_u32(R.r);
+    R.pos = (int32_t)ld_u32(R.r + 4);
+    R.l_read_name = R.r[8];
+    R.mapq = R.r[9];
+    R.n_cigar = (uint32_t)R.r[12] | ((uint32_t)R.r[13] << 8);
+    R.flag = (uint32_t)R.r[14] | ((uint32_t)R.r[15] << 8);
+    R.l_seq = (int32_t)ld_u32(R.r + 16);
+    R.mate_ref = (int32_t)ld_u32(R.r + 20);
+    R.name = R.r + 32;
+    R.cigar = R.name + R.l_read_name;
+    R.seq = R.cigar + 4ull * R.n_cigar;
+    R.qual = R.seq + (R.l_seq >= 0 ? (R.l_seq + 1) / 2 : 0);
+    R.ok = R.l_seq >= 0 && R.l_read_name >= 1 && 32ull + R.l_read_name + 4ull * R.n_cigar + (uint64_t)((R.l_seq + 1) / 2) + (uint64_t)R.l_seq <= (uint64_t)R.block_size &&
+           R.ref_id >= -1 && R.ref_id < n_ref && R.mate_ref >= -1 && R.mate_ref < n_ref;
+    return R;
+}
+
+__global__ void __launch_bounds__(256) bam_col_measure_kernel(const __grid_constant__ BamColArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= a.n_rows) return;
+    const int f = bam_find_file(a.files, a.n_files, r);
+    const BamFileTab F = a.files[f];
+    const BamRec R = bam_rec(a.rec_ptr[r], F.n_ref);
+    int32_t c[kBNVar] = {0, 0, 0, 0, 0, 0, 0};
+    uint8_t rf = 0;
+    uint32_t err = 0;
+    long long start = 0, end = 0;
+    if (!R.ok) {
+        err = kBErrLayout;
+    } else {
+        c[kBName] = (int32_t)R.l_read_name - 1;
+        if (R.l_read_name == 2 && R.name[0] == '*') err |= kBErrName;
+        if (R.ref_id >= 0) {
+            rf |= 1u;
+            c[kBRef] = a.ref_len[F.ref0 + R.ref_id];
+        }
+        if (R.mate_ref >= 0) {
+            rf |= 16u;
+            c[kBMate] = a.ref_len[F.ref0 + R.mate_ref];
+        }
+        if (R.mapq != 255u) {
+            rf |= 8u;
+            c[kBMapq] = dec_digits(R.mapq);
+        }
+        long long span = 0;
+        int32_t cg = 0;
+        for (uint32_t i = 0; i < R.n_cigar; ++i) {
+            const uint32_t v = ld_u32(R.cigar + 4 * i), op = v & 15u, ln = v >> 4;
+            if (op > 8u) err |= kBErrLayout;
+            if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) span += ln;  // M D N = X consume the reference
+            cg += dec_digits(ln) + 1;
+        }
+        c[kBCigar] = cg;
+        c[kBSeq] = R.l_seq;
+        bool missing = true;
+        for (int32_t i = 0; i < R.l_seq; ++i) missing = missing && R.qual[i] == 0xFFu;
+        c[kBQual] = missing ? 0 : R.l_seq;
+        if (R.pos >= 0) {  // alignment_start = pos + 1; alignment_end = start + reference span - 1 (None when that is 0)
+            rf |= 2u;
+            start = (long long)R.pos + 1;
+            end = start + span - 1;
+            if (end >= 1) rf |= 4u;
+            else end = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kBNVar; ++k)
+        if (a.cnt[k]) a.cnt[k][r] = c[k];
+    a.rowflags[r] = rf;
+    if (a.flag) a.flag[r] = (int32_t)R.flag;
+    if (a.start) a.start[r] = start;
+    if (a.end) a.end[r] = end;
+    if (err) {
+        atomicOr(a.flags, err);
+        atomicMin(a.first_bad_row, (unsigned long long)r);
+    }
+}
+
+__device__ __forceinline__ int put_dec(uint8_t *dst, uint32_t v) {
+    const int n = dec_digits(v);
+    for (int i = n - 1; i >= 0; --i) {
+        dst[i] = (uint8_t)('0' + v % 10u);
+        v /= 10u;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256) bam_col_emit_kernel(const __grid_constant__ BamColArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    __shared__ long long s_b0;
+    if (threadIdx.x == 0) {
+        const int64_t rb = (int64_t)blockIdx.x * 256;
+        int64_t lo = 0, hi = a.n_batches;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(&a.brow[mid]) <= rb) lo = mid;
+            else hi = mid;
+        }
+        s_b0 = lo;
+    }
+    __syncthreads();
+    if (r >= a.n_rows) return;
+    int64_t b = s_b0;
+    while (__ldg(&a.brow[b + 1]) <= r) ++b;
+    const int64_t r0 = __ldg(&a.brow[b]);
+    const int in_batch = (int)(r - r0);
+    const bool last = r + 1 == __ldg(&a.brow[b + 1]);
+    const uint8_t rf = a.rowflags[r];
+    {
+        const uint32_t bit = 1u << (in_batch & 31);
+        const int64_t word = b * a.wpb + (in_batch >> 5);
+        const uint32_t peers = __match_any_sync(__activemask(), word);
+        const bool leader = (threadIdx.x & 31) == __ffs((int)peers) - 1;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            if (!a.valid[k]) continue;
+            const uint32_t v = __reduce_or_sync(peers, (rf >> k) & 1u ? bit : 0u);
+            if (leader && v) atomicOr(a.valid[k] + word, v);
+        }
+    }
+    const int f = bam_find_file(a.files, a.n_files, r);
+    const BamFileTab F = a.files[f];
+    const BamRec R = bam_rec(a.rec_ptr[r], F.n_ref);
+    if (!R.ok) return;  // reported by the measure pass
+    const int64_t lrow = b * (int64_t)(a.batch_rows + 1) + in_batch;
+    auto open_cell = [&](int k, long long &v_abs) {  // offsets of the cell; returns where its bytes go
+        const long long v = a.pre[k][r], v0 = a.pre[k][r0];
+        a.off[k][lrow] = (int32_t)(v - v0);
+        if (last) a.off[k][lrow + 1] = (int32_t)(a.pre[k][r + 1] - v0);
+        v_abs = v;
+    };
+    long long v;
+    if (a.off[kBName]) {
+        open_cell(kBName, v);
+        for (uint32_t i = 0; i + 1 < R.l_read_name; ++i) a.val[kBName][v + i] = R.name[i];
+    }
+    if (a.off[kBRef]) {
+        open_cell(kBRef, v);
+        if (R.ref_id >= 0) {
+            const uint8_t *nm = a.ref_blob + a.ref_off[F.ref0 + R.ref_id];
+            const int32_t n = a.ref_len[F.ref0 + R.ref_id];
+            for (int32_t i = 0; i < n; ++i) a.val[kBRef][v + i] = nm[i];
+        }
+    }
+    if (a.off[kBMate]) {
+        open_cell(kBMate, v);
+        if (R.mate_ref >= 0) {
+            const uint8_t *nm = a.ref_blob + a.ref_off[F.ref0 + R.mate_ref];
+            const int32_t n = a.ref_len[F.ref0 + R.mate_ref];
+            for (int32_t i = 0; i < n; ++i) a.val[kBMate][v + i] = nm[i];
+        }
+    }
+    if (a.off[kBMapq]) {
+        open_cell(kBMapq, v);
+        if (R.mapq != 255u) put_dec(a.val[kBMapq] + v, R.mapq);
+    }
+    if (a.off[kBCigar]) {
+        open_cell(kBCigar, v);
+        uint8_t *dst = a.val[kBCigar] + v;
+        for (uint32_t i = 0; i < R.n_cigar; ++i) {
+            const uint32_t x = ld_u32(R.cigar + 4 * i), op = x & 15u;
+            dst += put_dec(dst, x >> 4);
+            *dst++ = (uint8_t)("MIDNSHP=X"[op > 8u ? 0u : op]);
+        }
+    }
+    if (a.off[kBSeq]) {
+        open_cell(kBSeq, v);
+        for (int32_t i = 0; i < R.l_seq; ++i) a.val[kBSeq][v + i] = (uint8_t)("=ACMGRSVTWYHKDBN"[(R.seq[i >> 1] >> ((i & 1) ? 0 : 4)) & 15]);
+    }
+    if (a.off[kBQual]) {
+        open_cell(kBQual, v);
+        const int32_t n = (int32_t)(a.pre[kBQual][r + 1] - a.pre[kBQual][r]);
+        long long *dst = reinterpret_cast<long long *>(a.val[kBQual]) + v;
+        for (int32_t i = 0; i < n; ++i) dst[i] = (long long)(int8_t)R.qual[i];
+    }
+}
+
+__global__ void bam_gather_i64(const long long *src, const long long *idx, int64_t n, long long *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+size_t bal256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+struct BamBuf {
+    void *d = nullptr, *h = nullptr;
+    size_t bytes = 0;
+};
+
+// Column store of one BAM stream; batches are views into it.
+struct BamColumns {
+    std::atomic<int> refs{1};
+    int device = 0;
+    bool on_device = false;
+    int batch_rows = 8192, wpb = 256;
+    int64_t n_rows = 0, n_batches = 0, next = 0;
+    std::vector<int> projection;
+    BamBuf off[kBNVar], val[kBNVar], valid[5], flag, start, end;
+    std::vector<long long> batch_row0, base[kBNVar];
+    template <class T>
+    const T *p(const BamBuf &b) const { return static_cast<const T *>(on_device ? b.d : b.h); }
+    void each(void (*fn)(BamBuf &)) {
+        for (int k = 0; k < kBNVar; ++k) fn(off[k]), fn(val[k]);
+        for (int k = 0; k < 5; ++k) fn(valid[k]);
+        fn(flag), fn(start), fn(end);
+    }
+    void unref() {
+        if (refs.fetch_sub(1) == 1) {
+            cudaSetDevice(device);
+            each([](BamBuf &b) {
+                cudaFree(b.d);
+                cudaFreeHost(b.h);
+            });
+            delete this;
+        }
+    }
+};
+
+void bam_columns_free(VcfStream *s) {
+    if (s->bam_cols) {
+        s->bam_cols->unref();
+        s->bam_cols = nullptr;
+    }
+}
+
+namespace {
+
+// column -> variable-length slot (-1: fixed width)
+constexpr int kColVar[10] = {kBName, -1, kBRef, -1, -1, kBMapq, kBCigar, kBMate, kBSeq, kBQual};
+// column -> validity slot (-1: never NULL)
+constexpr int kColValid[10] = {-1, -1, 0, 1, 2, 3, -1, 4, -1, -1};
+
+int bam_build_columns(VcfStream *s) {
+    Ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    auto *c = new (std::nothrow) BamColumns();
+    if (!c) return fail(EXON_GPU_ERR_OOM, "bam_next_batch: out of host memory");
+    s->bam_cols = c;
+    c->device = ctx->device;
+    c->on_device = s->columns_on_device;
+    c->batch_rows = s->batch_rows;
+    c->wpb = ((s->batch_rows + 63) / 64) * 2;
+    c->projection = s->projection;
+    c->batch_row0.assign(1, 0);
+    bool want[10] = {false, false, false, false, false, false, false, false, false, false};
+    for (int p : s->projection) want[p] = true;
+    if (s->bam_n_entries == 0) return EXON_GPU_OK;
+    uint8_t *d = (uint8_t *)s->d_bam;
+    const bool serial = s->bam_serial_ok;
+    const size_t n_ent = serial ? s->bam_n_firsts : s->bam_n_entries;
+    BamEntry *ent = (BamEntry *)(serial ? d + s->bam_o_firsts : d);
+
+    // ---- 1. rows per walk -> record addresses ----
+    unsigned long long *d_erows = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&d_erows, 2 * bal256((n_ent + 1) * 8), st));
+    struct PoolFree {
+        void *p;
+        cudaStream_t st;
+        ~PoolFree() { cudaFreeAsync(p, st); }
+    } g0{d_erows, st};
+    unsigned long long *d_erow0 = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(d_erows) + bal256((n_ent + 1) * 8));
+    BamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.entries = ent;
+    a.n_entries = (int32_t)n_ent;
+    a.remap = (const int32_t *)(d + s->bam_o_remap);
+    a.exits = (uint64_t *)(d + s->bam_o_exits);
+    a.counts = (unsigned long long *)(d + s->bam_o_counts);
+    a.rows = (unsigned long long *)(d + s->bam_o_misc);
+    a.n_groups = s->bam_n_groups;
+    a.serial = serial;
+    a.entry_rows = d_erows;
+    CUDA_TRY(cudaMemsetAsync(d + s->bam_o_misc, 0, 128, st));
+    bam_walk_kernel<<<(unsigned)((n_ent + kBamThreads - 1) / kBamThreads), kBamThreads, 0, st>>>(a);
+    ctx->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<unsigned long long> erows(n_ent), erow0(n_ent + 1);
+    CUDA_TRY(cudaMemcpyAsync(erows.data(), d_erows, n_ent * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<BamEntry> h_ent(n_ent);
+    CUDA_TRY(cudaMemcpyAsync(h_ent.data(), ent, n_ent * sizeof(BamEntry), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    erow0[0] = 0;
+    for (size_t i = 0; i < n_ent; ++i) erow0[i + 1] = erow0[i] + erows[i];
+    const int64_t n_rows = (int64_t)erow0[n_ent];
+    c->n_rows = n_rows;
+    if (n_rows == 0) return EXON_GPU_OK;
+    // files -> batches (batches restart at every file), reference-name tables
+    const int n_files = (int)s->bam_files.size();
+    std::vector<BamFileTab> ftab((size_t)n_files + 1);
+    std::vector<long long> file_rows((size_t)n_files, 0);
+    for (size_t i = 0; i < n_ent; ++i) file_rows[(size_t)h_ent[i].file_idx] += (long long)erows[i];
+    std::vector<int32_t> ref_off, ref_len;
+    std::string blob;
+    c->batch_row0.clear();
+    long long row0 = 0;
+    for (int f = 0; f < n_files; ++f) {
+        ftab[(size_t)f] = BamFileTab{row0, (long long)c->batch_row0.size(), (int32_t)ref_off.size(), (int32_t)s->bam_files[(size_t)f].ref_names.size()};
+        for (const std::string &nm : s->bam_files[(size_t)f].ref_names) {
+            ref_off.push_back((int32_t)blob.size());
+            ref_len.push_back((int32_t)nm.size());
+            blob += nm;
+        }
+        for (long long r = 0; r < file_rows[(size_t)f]; r += c->batch_rows) c->batch_row0.push_back(row0 + r);
+        row0 += file_rows[(size_t)f];
+    }
+    ftab[(size_t)n_files] = BamFileTab{row0, (long long)c->batch_row0.size(), (int32_t)ref_off.size(), 0};
+    c->n_batches = (int64_t)c->batch_row0.size();
+    c->batch_row0.push_back(n_rows);
+    const size_t nb1 = (size_t)c->n_batches + 1, nr1 = (size_t)n_rows + 1;
+
+    // scratch_b: rec_ptr | 7 counts | 7 prefixes | rowflags | cub | tables
+    size_t cub_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (long long *)nullptr, (int)nr1, st));
+    const size_t tab_bytes = bal256(ftab.size() * sizeof(BamFileTab)) + 2 * bal256(ref_off.size() * 4 + 4) + bal256(blob.size() + 1) + (kBNVar + 1) * bal256(nb1 * 8) + 256;
+    if (int rc = ctx->ensure_scratch_b(bal256(nr1 * 8) + kBNVar * (bal256(nr1 * 4) + bal256(nr1 * 8)) + bal256(nr1) + bal256(cub_bytes) + tab_bytes + 4096)) return rc;
+    uint8_t *x = (uint8_t *)ctx->scratch_b;
+    auto take = [&](size_t bytes) {
+        uint8_t *p = x;
+        x += bal256(bytes);
+        return p;
+    };
+    const uint8_t **d_rec = (const uint8_t **)take(nr1 * 8);
+    CUDA_TRY(cudaMemcpyAsync(d_erow0, erow0.data(), (n_ent + 1) * 8, cudaMemcpyHostToDevice, st));
+    a.entry_rows = nullptr;
+    a.rec_ptr = d_rec;
+    a.entry_row0 = d_erow0;
+    bam_walk_kernel<<<(unsigned)((n_ent + kBamThreads - 1) / kBamThreads), kBamThreads, 0, st>>>(a);
+    ctx->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+
+    BamColArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.n_rows = n_rows;
+    ca.rec_ptr = d_rec;
+    ca.n_files = n_files;
+    ca.n_batches = c->n_batches;
+    ca.batch_rows = c->batch_rows;
+    ca.wpb = c->wpb;
+    long long *pre[kBNVar];
+    bool need[kBNVar];
+    for (int k = 0; k < kBNVar; ++k) need[k] = false;
+    for (int col = 0; col < 10; ++col) {
+        ca.want[col] = want[col];
+        if (want[col] && kColVar[col] >= 0) need[kColVar[col]] = true;
+    }
+    for (int k = 0; k < kBNVar; ++k) {
+        pre[k] = nullptr;
+        if (!need[k]) continue;
+        ca.cnt[k] = (int32_t *)take(nr1 * 4);
+        pre[k] = (long long *)take(nr1 * 8);
+        ca.pre[k] = pre[k];
+        CUDA_TRY(cudaMemsetAsync(ca.cnt[k] + n_rows, 0, 4, st));
+    }
+    ca.rowflags = take(nr1);
+    uint8_t *cub_tmp = take(cub_bytes);
+    BamFileTab *d_ftab = (BamFileTab *)take(ftab.size() * sizeof(BamFileTab));
+    int32_t *d_roff = (int32_t *)take(ref_off.size() * 4 + 4), *d_rlen = (int32_t *)take(ref_len.size() * 4 + 4);
+    uint8_t *d_blob = take(blob.size() + 1);
+    long long *d_brow = (long long *)take(nb1 * 8);
+    long long *d_base[kBNVar];
+    for (int k = 0; k < kBNVar; ++k) d_base[k] = (long long *)take(nb1 * 8);
+    unsigned long long *d_misc = (unsigned long long *)take(64);
+    CUDA_TRY(cudaMemcpyAsync(d_ftab, ftab.data(), ftab.size() * sizeof(BamFileTab), cudaMemcpyHostToDevice, st));
+    if (!ref_off.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(d_roff, ref_off.data(), ref_off.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_rlen, ref_len.data(), ref_len.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_brow, c->batch_row0.data(), nb1 * 8, cudaMemcpyHostToDevice, st));
+    const unsigned long long init_misc[2] = {0ull, ~0ull};
+    CUDA_TRY(cudaMemcpyAsync(d_misc, init_misc, sizeof(init_misc), cudaMemcpyHostToDevice, st));
+    ca.files = d_ftab;
+    ca.ref_off = d_roff;
+    ca.ref_len = d_rlen;
+    ca.ref_blob = d_blob;
+    ca.brow = d_brow;
+    ca.flags = reinterpret_cast<uint32_t *>(d_misc);
+    ca.first_bad_row = d_misc + 1;
+
+    auto dev_alloc = [&](BamBuf &b, size_t bytes, bool zero) -> int {
+        b.bytes = std::max<size_t>(bytes, 8);
+        CUDA_TRY(cudaMallocAsync(&b.d, b.bytes, st));
+        if (zero) CUDA_TRY(cudaMemsetAsync(b.d, 0, b.bytes, st));
+        return EXON_GPU_OK;
+    };
+    if (want[1]) {
+        if (int rc = dev_alloc(c->flag, (size_t)n_rows * 4, false)) return rc;
+        ca.flag = (int32_t *)c->flag.d;
+    }
+    if (want[3]) {
+        if (int rc = dev_alloc(c->start, (size_t)n_rows * 8, false)) return rc;
+        ca.start = (long long *)c->start.d;
+    }
+    if (want[4]) {
+        if (int rc = dev_alloc(c->end, (size_t)n_rows * 8, false)) return rc;
+        ca.end = (long long *)c->end.d;
+    }
+    // ---- 2. measure ----
+    const unsigned grid = (unsigned)((n_rows + 255) / 256);
+    bam_col_measure_kernel<<<grid, 256, 0, st>>>(ca);
+    ctx->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    // ---- 3. scans ----
+    for (int k = 0; k < kBNVar; ++k) {
+        if (!need[k]) continue;
+        size_t tb = cub_bytes;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, (const int32_t *)ca.cnt[k], pre[k], (int)nr1, st));
+        bam_gather_i64<<<(unsigned)((nb1 + 255) / 256), 256, 0, st>>>(pre[k], d_brow, (int64_t)nb1, d_base[k]);
+        ctx->launches.fetch_add(2);
+        c->base[k].resize(nb1);
+        CUDA_TRY(cudaMemcpyAsync(c->base[k].data(), d_base[k], nb1 * 8, cudaMemcpyDeviceToHost, st));
+    }
+    unsigned long long h_misc[2];
+    CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (const uint32_t e = (uint32_t)h_misc[0])
+        return fail(EXON_GPU_ERR_PARSE, "malformed BAM record at row %llu:%s%s", h_misc[1],
+                    (e & kBErrLayout) ? " fields do not fit block_size, or an invalid CIGAR op / reference id;" : "",
+                    (e & kBErrName) ? " missing read name in the non-nullable name column;" : "");
+    const size_t off_bytes = (size_t)c->n_batches * (size_t)(c->batch_rows + 1) * 4;
+    const size_t valid_bytes = (size_t)c->n_batches * (size_t)c->wpb * 4;
+    for (int k = 0; k < kBNVar; ++k) {
+        if (!need[k]) continue;
+        for (int64_t b = 0; b < c->n_batches; ++b)
+            if (c->base[k][(size_t)b + 1] - c->base[k][(size_t)b] > 0x7FFFFFFFll)
+                return fail(EXON_GPU_ERR_UNSUPPORTED, "bam_next_batch: batch %lld overflows int32 offsets", (long long)b);
+        if (int rc = dev_alloc(c->off[k], off_bytes, false)) return rc;
+        if (int rc = dev_alloc(c->val[k], (size_t)c->base[k][nb1 - 1] * (k == kBQual ? 8 : 1), false)) return rc;
+        ca.off[k] = (int32_t *)c->off[k].d;
+        ca.val[k] = (uint8_t *)c->val[k].d;
+    }
+    for (int col = 0; col < 10; ++col) {
+        const int v = kColValid[col];
+        if (!want[col] || v < 0) continue;
+        if (int rc = dev_alloc(c->valid[v], valid_bytes, true)) return rc;
+        ca.valid[v] = (uint32_t *)c->valid[v].d;
+    }
+    // ---- 4. emit ----
+    bam_col_emit_kernel<<<grid, 256, 0, st>>>(ca);
+    ctx->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    if (!c->on_device) {
+        int rc = EXON_GPU_OK;
+        auto to_host = [&](BamBuf &b) {
+            if (!b.d || rc) return;
+            if (cudaHostAlloc(&b.h, b.bytes, cudaHostAllocDefault) != cudaSuccess || cudaMemcpyAsync(b.h, b.d, b.bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                rc = fail(EXON_GPU_ERR_OOM, "bam_next_batch: host copy of the columns failed");
+        };
+        for (int k = 0; k < kBNVar; ++k) to_host(c->off[k]), to_host(c->val[k]);
+        for (int k = 0; k < 5; ++k) to_host(c->valid[k]);
+        to_host(c->flag), to_host(c->start), to_host(c->end);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return EXON_GPU_OK;
+}
+
+struct BamBatchPriv {
+    BamColumns *cols;
+    int n_children;
+    ArrowArray children[10];
+    ArrowArray *child_ptrs[10];
+    const void *bufs[10][3];
+    ArrowArray item;  // quality_score's int64 child
+    ArrowArray *item_ptr;
+    const void *item_bufs[2];
+    const void *struct_buffers[1];
+};
+void bam_release_child(ArrowArray *a) { a->release = nullptr; }
+void bam_release_batch(ArrowArray *a) {
+    auto *p = static_cast<BamBatchPriv *>(a->private_data);
+    p->cols->unref();
+    delete p;
+    a->release = nullptr;
+}
+struct BamSchemaPriv {
+    int n_children;
+    ArrowSchema children[10];
+    ArrowSchema *child_ptrs[10];
+    ArrowSchema item;
+    ArrowSchema *item_ptr;
+};
+void bam_release_schema_child(ArrowSchema *s) { s->release = nullptr; }
+void bam_release_schema(ArrowSchema *s) {
+    delete static_cast<BamSchemaPriv *>(s->private_data);
+    s->release = nullptr;
+}
+// SAMSchemaBuilder::default, exon/exon-sam/src/schema_builder.rs:385-401
+void bam_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
+    static const char *names[10] = {"name", "flag", "reference", "start", "end", "mapping_quality", "cigar", "mate_reference", "sequence", "quality_score"};
+    static const char *formats[10] = {"u", "i", "u", "l", "l", "u", "u", "u", "u", "+l"};
+    static const bool nullable[10] = {false, false, true, true, true, true, false, true, false, false};
+    auto *p = new BamSchemaPriv();
+    p->n_children = (int)projection.size();
+    for (int i = 0; i < p->n_children; ++i) {
+        const int col = projection[(size_t)i];
+        ArrowSchema &c = p->children[i];
+        memset(&c, 0, sizeof(c));
+        c.format = formats[col];
+        c.name = names[col];
+        c.flags = nullable[col] ? ARROW_FLAG_NULLABLE : 0;
+        c.release = bam_release_schema_child;
+        if (col == 9) {
+            memset(&p->item, 0, sizeof(p->item));
+            p->item.format = "l";
+            p->item.name = "item";
+            p->item.flags = ARROW_FLAG_NULLABLE;
+            p->item.release = bam_release_schema_child;
+            p->item_ptr = &p->item;
+            c.n_children = 1;
+            c.children = &p->item_ptr;
+        }
+        p->child_ptrs[i] = &c;
+    }
+    memset(out, 0, sizeof(*out));
+    out->format = "+s";
+    out->name = "";
+    out->n_children = p->n_children;
+    out->children = p->child_ptrs;
+    out->release = bam_release_schema;
+    out->private_data = p;
+}
+
+}  // namespace
+
+int bam_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
+    if (!s->bam_cols) {
+        int64_t rows = 0;
+        if (int rc = s->bam_filter_count(nullptr, nullptr, 0, nullptr, &rows)) return rc;  // verified walks (and flush_gz)
+        std::lock_guard<std::mutex> work(s->ctx->work_mu);
+        if (int rc = bam_build_columns(s)) {
+            bam_columns_free(s);
+            return rc;
+        }
+        s->drained = true;
+    }
+    BamColumns *c = s->bam_cols;
+    if (out_schema) bam_fill_schema(s->projection, out_schema);
+    memset(out, 0, sizeof(*out));
+    if (c->next >= c->n_batches) return EXON_GPU_OK;  // end of stream: release == NULL
+    const int64_t b = c->next++;
+    const int64_t row0 = c->batch_row0[(size_t)b], rows = c->batch_row0[(size_t)b + 1] - row0;
+    auto *p = new BamBatchPriv();
+    memset(static_cast<void *>(p), 0, sizeof(*p));
+    p->cols = c;
+    c->refs.fetch_add(1);
+    p->n_children = (int)s->projection.size();
+    const size_t lo = (size_t)b * (size_t)(c->batch_rows + 1), vw = (size_t)b * (size_t)c->wpb;
+    for (int i = 0; i < p->n_children; ++i) {
+        const int col = s->projection[(size_t)i];
+        ArrowArray &a = p->children[i];
+        a.length = rows;
+        a.buffers = p->bufs[i];
+        a.release = bam_release_child;
+        const int vs = kColValid[col], k = kColVar[col];
+        a.null_count = vs >= 0 ? -1 : 0;
+        p->bufs[i][0] = vs >= 0 ? (const void *)(c->p<uint32_t>(c->valid[vs]) + vw) : nullptr;
+        if (col == 1) {
+            a.n_buffers = 2;
+            p->bufs[i][1] = c->p<int32_t>(c->flag) + row0;
+        } else if (col == 3 || col == 4) {
+            a.n_buffers = 2;
+            p->bufs[i][1] = c->p<long long>(col == 3 ? c->start : c->end) + row0;
+        } else if (col == 9) {
+            a.n_buffers = 2;
+            p->bufs[i][1] = c->p<int32_t>(c->off[k]) + lo;
+            p->item.length = c->base[k][(size_t)b + 1] - c->base[k][(size_t)b];
+            p->item.n_buffers = 2;
+            p->item_bufs[0] = nullptr;
+            p->item_bufs[1] = c->p<long long>(c->val[k]) + c->base[k][(size_t)b];
+            p->item.buffers = p->item_bufs;
+            p->item.release = bam_release_child;
+            p->item_ptr = &p->item;
+            a.n_children = 1;
+            a.children = &p->item_ptr;
+        } else {
+            a.n_buffers = 3;
+            p->bufs[i][1] = c->p<int32_t>(c->off[k]) + lo;
+            p->bufs[i][2] = c->p<uint8_t>(c->val[k]) + c->base[k][(size_t)b];
+        }
+        p->child_ptrs[i] = &a;
+    }
+    p->struct_buffers[0] = nullptr;
+    out->length = rows;
+    out->n_buffers = 1;
+    out->buffers = p->struct_buffers;
+    out->n_children = p->n_children;
+    out->children = p->child_ptrs;
+    out->release = bam_release_batch;
+    out->private_data = p;
     return EXON_GPU_OK;
 }
 
@@ -398,6 +1093,30 @@ int exon_gpu_bam_open(exon_gpu_ctx *c, exon_gpu_stream **out) {
     (*out)->fmt = kFmtBam;
     (*out)->hdr = VcfStream::kBody;
     return EXON_GPU_OK;
+}
+
+int exon_gpu_bam_open_columns(exon_gpu_ctx *c, const exon_gpu_bam_opts *o, exon_gpu_stream **out) {
+    if (!c || !o || !out) return fail(EXON_GPU_ERR_ARG, "bam_open_columns: NULL argument");
+    if (o->batch_rows < 0 || o->n_projection < 0 || o->n_projection > 10 || (o->n_projection > 0 && !o->projection))
+        return fail(EXON_GPU_ERR_ARG, "bam_open_columns: bad batch_rows / projection");
+    for (int i = 0; i < o->n_projection; ++i) {
+        if (o->projection[i] < 0 || o->projection[i] > 10) return fail(EXON_GPU_ERR_ARG, "bam_open_columns: projection index %d is not a BAM file-schema column", o->projection[i]);
+        if (o->projection[i] == 10) return fail(EXON_GPU_ERR_UNSUPPORTED, "bam_open_columns: column 10 (tags) is not built on the GPU yet");
+        for (int j = 0; j < i; ++j)
+            if (o->projection[j] == o->projection[i]) return fail(EXON_GPU_ERR_ARG, "bam_open_columns: column %d is projected twice", o->projection[i]);
+    }
+    if (int rc = exon_gpu_bam_open(c, out)) return rc;
+    if (o->batch_rows > 0) (*out)->batch_rows = o->batch_rows;
+    (*out)->projection.assign(o->projection, o->projection + o->n_projection);
+    (*out)->columns_on_device = o->columns_on_device != 0;
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_bam_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema) {
+    if (!s || !out || s->fmt != kFmtBam) return fail(EXON_GPU_ERR_ARG, "bam_next_batch: not a BAM stream");
+    cudaError_t e = cudaSetDevice(s->ctx->device);
+    if (e != cudaSuccess) return fail(EXON_GPU_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return bam_next_batch(s, out, out_schema);
 }
 
 int exon_gpu_bam_feed(exon_gpu_stream *s, const uint8_t *data, size_t len, int is_last) {

@@ -131,8 +131,8 @@ class Context:
     def open_mzml(self) -> "MzmlStream":
         return MzmlStream(self)
 
-    def open_bam(self) -> "BamStream":
-        return BamStream(self)
+    def open_bam(self, **kw) -> "BamStream":
+        return BamStream(self, **kw)
 
     def allreduce_counts(self, counts):
         """exon_gpu_allreduce_counts: element-wise sum of an int64 vector over the NCCL communicator."""
@@ -485,11 +485,34 @@ class BamStream:
     # SAM flag bits (exon/exon-core/src/udfs/sam/samflags.rs:111-141)
     UNMAPPED, SECONDARY, SUPPLEMENTARY = 0x4, 0x100, 0x800
 
-    def __init__(self, ctx: Context):
+    def __init__(self, ctx: Context, *, batch_rows: int = 8192, projection=None, columns_on_device: bool = False):
         self.ctx = ctx
         self.lib = ctx.lib
         self.handle = C.c_void_p()
-        check(self.lib.exon_gpu_bam_open(ctx.handle, C.byref(self.handle)))
+        self.columns_on_device = columns_on_device
+        if projection is None:
+            check(self.lib.exon_gpu_bam_open(ctx.handle, C.byref(self.handle)))
+        else:
+            self._proj = (C.c_int32 * max(len(projection), 1))(*projection)
+            opts = _abi.FastqOpts(batch_rows, len(projection), self._proj, int(columns_on_device))
+            check(self.lib.exon_gpu_bam_open_columns(ctx.handle, C.byref(opts), C.byref(self.handle)))
+
+    def next_batch(self):
+        """exon_gpu_bam_next_batch -> VcfBatch (the Arrow import helper is format-agnostic) or None at the end."""
+        arr, sch = _abi.ArrowArray(), _abi.ArrowSchema()
+        check(self.lib.exon_gpu_bam_next_batch(self.handle, C.byref(arr), C.byref(sch)))
+        if not arr.release:
+            if sch.release:
+                sch.release(C.byref(sch))
+            return None
+        return VcfBatch(arr, sch, self.columns_on_device)
+
+    def batches(self):
+        while True:
+            b = self.next_batch()
+            if b is None:
+                return
+            yield b
 
     def close(self):
         if self.handle:

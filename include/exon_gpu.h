@@ -302,6 +302,25 @@ int exon_gpu_bam_filter_count_by_reference(exon_gpu_stream *s, const exon_gpu_ba
 /* Name of group g after a query (*name == NULL for the last group, the NULL reference). */
 int exon_gpu_bam_group_name(exon_gpu_stream *s, int32_t group, const char **name);
 
+/* Columns out: BatchReader::read_batch + BAMArrayBuilder::{append, finish} (exon/exon-bam/src/batch_reader.rs:88-107,
+ * exon/exon-bam/src/array_builder.rs:102-218) with SemiLazyRecord::alignment_end (indexed_async_batch_stream.rs:43-50).
+ * File schema (SAMSchemaBuilder::default, exon/exon-sam/src/schema_builder.rs:385-401), projected by index:
+ *   0 name utf8 !null | 1 flag int32 !null | 2 reference utf8 (NULL for refID -1) | 3 start int64 (pos + 1, NULL for -1) |
+ *   4 end int64 (start + reference-consuming CIGAR length - 1; NULL without a start or when that is 0) |
+ *   5 mapping_quality utf8 (decimal string, NULL for 255) | 6 cigar utf8 ("55M13394N21M") | 7 mate_reference utf8 |
+ *   8 sequence utf8 (bases decoded from 4 bits) | 9 quality_score list<item: int64> (raw bytes as i8, [] when missing)
+ * Column 10 (tags) is not built: EXON_GPU_ERR_UNSUPPORTED.  A record whose read name is missing ("*") fails the call, as
+ * the reference's batch construction does (NULL in a non-nullable column).  Batches never span files. */
+typedef struct {
+    int32_t batch_rows;        /* session batch size; reference default 8192 */
+    int32_t n_projection;
+    const int32_t *projection;
+    int32_t columns_on_device; /* 0: batch buffers are pinned host memory; 1: device memory */
+} exon_gpu_bam_opts;
+int exon_gpu_bam_open_columns(exon_gpu_ctx *ctx, const exon_gpu_bam_opts *opts, exon_gpu_stream **out);
+/* Same contract as exon_gpu_vcf_next_batch: struct array of <= batch_rows rows, release == NULL at the end of the stream. */
+int exon_gpu_bam_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
+
 /* ---- mzML partition stream (BASELINE configs[4]) --------------------------------------- */
 /* MzMLScan::execute + MzMLOpener::open + BatchReader (exon/exon-core/src/datasources/mzml/scanner.rs:139,
  * mzml/file_opener.rs:48, exon/exon-mzml/src/batch_reader.rs:54-82).  Fed like a VCF stream (plain text through

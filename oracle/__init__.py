@@ -408,6 +408,20 @@ class Bam:
         out[None] = int(counts[len(self.refs)])
         return out, int(n)
 
+    def seq_qual(self, i: int):
+        """(sequence str, quality_score list[int]) of record i: columns 8 and 9 of the reference's BAM batches."""
+        L = self._L
+        L.exo_bam_seq_qual.restype = C.c_int32
+        L.exo_bam_seq_qual.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32)]
+        cap = 1 << 16
+        seq = C.create_string_buffer(cap + 1)
+        qual = (C.c_int64 * cap)()
+        nq = C.c_int32()
+        n = L.exo_bam_seq_qual(self._h, i, seq, cap + 1, qual, cap, C.byref(nq))
+        if n < 0:
+            raise IndexError(i)
+        return seq.value.decode(), list(qual[: nq.value])
+
     def row(self, i: int):
         r = BamRow()
         n = self._L.exo_bam_scan(self._h, 0, 0, 0, -1, None, i, C.byref(r))

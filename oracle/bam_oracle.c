@@ -167,3 +167,36 @@ int64_t exo_bam_scan(const exo_bam *b, int32_t has_pred, uint32_t flag_exclude, 
     }
     return n;
 }
+
+/* Sequence and quality scores of record `row_index`, as BAMArrayBuilder::append materialises columns 8 and 9
+ * (exon-bam/src/array_builder.rs:177-201) from a noodles RecordBuf: bases decoded from the 4-bit encoding with the SAM
+ * alphabet "=ACMGRSVTWYHKDBN" (noodles-bam 0.7x record codec, un-vendored), quality scores as the raw bytes
+ * reinterpreted as i8 and widened to i64; a quality string that is all 0xFF is "missing" and decodes to an empty list.
+ * Returns l_seq (bases written to seq, NUL terminated), -1 when the row does not exist; *n_qual = list length. */
+int32_t exo_bam_seq_qual(const exo_bam *b, int64_t row_index, char *seq, int32_t seq_cap, int64_t *qual, int32_t qual_cap, int32_t *n_qual) {
+    static const char BASES[] = "=ACMGRSVTWYHKDBN";
+    int64_t p = b->records_at, n = 0;
+    while (p < b->len) {
+        if (p + 4 > b->len) return -1;
+        const int32_t block_size = rd_i32(b->buf + p);
+        if (block_size < 32 || p + 4 + block_size > b->len) return -1;
+        if (n == row_index) {
+            const uint8_t *r = b->buf + p + 4;
+            const uint32_t l_read_name = r[8], n_cigar = rd_u16(r + 12);
+            const int32_t l_seq = rd_i32(r + 16);
+            const uint8_t *s = r + 32 + l_read_name + 4 * n_cigar, *q = s + (l_seq + 1) / 2;
+            if (l_seq < 0 || l_seq + 1 > seq_cap || l_seq > qual_cap) return -1;
+            for (int32_t i = 0; i < l_seq; i++) seq[i] = BASES[(s[i >> 1] >> ((i & 1) ? 0 : 4)) & 15];
+            seq[l_seq] = 0;
+            int missing = 1;
+            for (int32_t i = 0; i < l_seq; i++)
+                if (q[i] != 0xFF) missing = 0;
+            *n_qual = (missing || l_seq == 0) ? 0 : l_seq;
+            for (int32_t i = 0; i < *n_qual; i++) qual[i] = (int64_t)(int8_t)q[i];
+            return l_seq;
+        }
+        p += 4 + (int64_t)block_size;
+        n++;
+    }
+    return -1;
+}
