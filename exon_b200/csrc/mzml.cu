@@ -16,8 +16,14 @@
 //   M3 sum      one warp per spectrum: lane i decodes value i of both payloads straight from the base64 text (16 characters
 //               cover any 8-byte value: 5 aligned word loads, a 256-entry table in shared memory, byte permutes), applies
 //               lo <= mz <= hi and accumulates intensity in f64; warp shuffle reduction, one atomicAdd per warp
-// zlib-compressed arrays (MS:1000574) are reported as EXON_GPU_ERR_UNSUPPORTED for now (the oracle handles them).
+// zlib-compressed arrays (MS:1000574; binary_conversion.rs:44-60 wraps the base64 bytes in a flate2 ZlibDecoder) take a
+// detour: their base64 text is decoded into a staging buffer (Z2), a member table is built on the device (Z3: 2-byte zlib
+// header checked and skipped, 4-byte Adler-32 trailer dropped, output size = the spectrum's defaultArrayLength x the value
+// width) and the DEFLATE streams go through the two inflate kernels of inflate.cu; M3 then reads those values from the
+// inflated bytes instead of the base64 text.  A stream whose output differs from the declared length is an error here
+// (the reference decodes to the end of the stream whatever the attribute says).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cstring>
 
@@ -43,10 +49,11 @@ constexpr int kMzU = MzRing::TILE / 512;
 
 enum : uint32_t {
     kEvSpectrum = 1, kEvBda = 2, kEvMz = 3, kEvIntensity = 4, kEvWave = 5, kEvF32 = 6, kEvF64 = 7, kEvZlib = 8, kEvNoComp = 9,
-    kEvBinStart = 10, kEvBinEnd = 11
+    kEvBinStart = 10, kEvBinEnd = 11, kEvSpecEnd = 12  // </spectrum>: arrays after it (chromatograms) belong to no spectrum
 };
 constexpr uint32_t kMzErrFormat = 1u;   // malformed structure (a <binary> without </binary>, missing data type, bad base64)
-constexpr uint32_t kMzErrZlib = 2u;     // zlib-compressed array: not decoded on the device yet
+constexpr uint32_t kMzErrZlib = 2u;     // a zlib array without a usable defaultArrayLength, or with a bad zlib header
+constexpr uint32_t kMzHasZlib = 4u;     // (not an error) some array is zlib-compressed: the host runs the inflate detour
 
 struct MzArgs {
     const ScanSeg *segs;
@@ -130,6 +137,7 @@ __global__ void __launch_bounds__(MzRing::WARPS * 32, 3) mzml_events_kernel(cons
                         }
                     } else if (c1 == '/') {
                         if (match_at(v, p + 2, "binary>", 7)) kind = kEvBinEnd;
+                        else if (match_at(v, p + 2, "spectrum>", 9)) kind = kEvSpecEnd;
                     }
                 } else {
                     // ... accession="MS:1000xxx": p is the ':'
@@ -169,6 +177,10 @@ struct SpecDesc {
     const uint8_t *mz, *in;   // trimmed base64 payloads (NULL: the spectrum has no such array)
     uint32_t mz_len, in_len;  // characters
     uint32_t mz_f32, in_f32;
+    uint32_t mz_zl, in_zl;    // zlib-compressed
+    uint32_t n_default;       // defaultArrayLength of the <spectrum> tag (0: absent)
+    uint32_t pad_;
+    const uint8_t *mz_raw, *in_raw;  // zlib arrays: the inflated little-endian values (set by the inflate detour)
 };
 
 __device__ __forceinline__ bool is_ws(uint8_t c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
@@ -179,15 +191,30 @@ __global__ void mzml_spectra_kernel(const unsigned long long *ev, unsigned long 
     if (i >= n || (ev[i] & 15u) != kEvSpectrum) return;
     const unsigned long long seg = ev[i] >> 44;
     SpecDesc d;
-    d.mz = d.in = nullptr;
-    d.mz_len = d.in_len = d.mz_f32 = d.in_f32 = 0;
+    d.mz = d.in = d.mz_raw = d.in_raw = nullptr;
+    d.mz_len = d.in_len = d.mz_f32 = d.in_f32 = d.mz_zl = d.in_zl = d.n_default = d.pad_ = 0;
+    {
+        // defaultArrayLength="N" inside the <spectrum ...> tag (the only place a zlib array's decoded size is declared)
+        const uint8_t *t = segs[seg].base + segs[seg].skip + ((ev[i] >> 4) & ((1ull << 40) - 1ull));
+        const uint8_t *tend = segs[seg].base + segs[seg].skip + segs[seg].len;
+        const char lit[] = "defaultArrayLength=\"";
+        for (int k = 0; k < 4096 && t + k + 20 < tend && t[k] != '>'; ++k) {
+            bool m = true;
+            for (int q = 0; q < 20 && m; ++q) m = t[k + q] == (uint8_t)lit[q];
+            if (!m) continue;
+            unsigned long long v = 0;
+            for (const uint8_t *c = t + k + 20; c < tend && *c >= '0' && *c <= '9' && v < (1ull << 31); ++c) v = v * 10ull + (*c - '0');
+            d.n_default = v < (1ull << 31) ? (uint32_t)v : 0u;
+            break;
+        }
+    }
     uint32_t kind = 0, f32 = 0, f64 = 0, zl = 0, nc = 0, err = 0;
     unsigned long long start = 0;
     bool open = false;
     for (unsigned long long j = i + 1; j < n; ++j) {
         const unsigned long long e = ev[j];
         const uint32_t k = (uint32_t)(e & 15u);
-        if ((e >> 44) != seg || k == kEvSpectrum) break;
+        if ((e >> 44) != seg || k == kEvSpectrum || k == kEvSpecEnd) break;
         const unsigned long long off = (e >> 4) & ((1ull << 40) - 1ull);
         if (k == kEvBda) { kind = f32 = f64 = zl = nc = 0; open = false; }
         else if (k == kEvMz || k == kEvIntensity || k == kEvWave) { if (!kind) kind = k; }
@@ -205,10 +232,10 @@ __global__ void mzml_spectra_kernel(const unsigned long long *ev, unsigned long 
             while (b1 > b0 && is_ws(b1[-1])) --b1;
             if (b1 == b0 || (kind != kEvMz && kind != kEvIntensity)) continue;  // empty content, or an array the query does not read
             if ((!f32 && !f64) || (!zl && !nc)) { err |= kMzErrFormat; continue; }
-            if (zl) { err |= kMzErrZlib; continue; }
             if (((b1 - b0) & 3) != 0 || (b1 - b0) > 0x7FFFFFFFll) { err |= kMzErrFormat; continue; }
-            if (kind == kEvMz) { d.mz = b0; d.mz_len = (uint32_t)(b1 - b0); d.mz_f32 = f32 && !f64; }
-            else { d.in = b0; d.in_len = (uint32_t)(b1 - b0); d.in_f32 = f32 && !f64; }
+            if (zl) err |= d.n_default ? kMzHasZlib : kMzErrZlib;
+            if (kind == kEvMz) { d.mz = b0; d.mz_len = (uint32_t)(b1 - b0); d.mz_f32 = f32 && !f64; d.mz_zl = zl; }
+            else { d.in = b0; d.in_len = (uint32_t)(b1 - b0); d.in_f32 = f32 && !f64; d.in_zl = zl; }
         }
     }
     if (open) err |= kMzErrFormat;
@@ -238,6 +265,11 @@ __device__ __forceinline__ unsigned long long b64_value(const uint8_t *p, uint32
     const unsigned long long lo = (unsigned long long)r[0] | ((unsigned long long)r[1] << 24) | ((unsigned long long)r[2] << 48);
     const unsigned long long hi = (unsigned long long)(r[2] >> 16) | ((unsigned long long)r[3] << 8);
     return s == 0u ? lo : (lo >> (8u * s)) | (hi << (64u - 8u * s));
+}
+
+// value `i` of an inflated array (16-byte aligned, little endian)
+__device__ __forceinline__ unsigned long long raw_value(const uint8_t *p, uint32_t i, int w) {
+    return w == 4 ? (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(p) + i) : __ldg(reinterpret_cast<const unsigned long long *>(p) + i);
 }
 
 __device__ __forceinline__ uint32_t b64_bytes(const uint8_t *p, uint32_t len) {
@@ -272,13 +304,14 @@ __global__ void __launch_bounds__(256) mzml_sum_kernel(const SpecDesc *specs, un
         const SpecDesc d = specs[sidx];
         if (!d.mz || !d.in) continue;
         const int wm = d.mz_f32 ? 4 : 8, wi = d.in_f32 ? 4 : 8;
-        const uint32_t nm = b64_bytes(d.mz, d.mz_len) / (uint32_t)wm, ni = b64_bytes(d.in, d.in_len) / (uint32_t)wi;
+        const uint32_t nm = d.mz_zl ? d.n_default : b64_bytes(d.mz, d.mz_len) / (uint32_t)wm;
+        const uint32_t ni = d.in_zl ? d.n_default : b64_bytes(d.in, d.in_len) / (uint32_t)wi;
         const uint32_t n = nm < ni ? nm : ni;   // the two unnested lists are zipped; the longer one's tail meets NULLs
         for (uint32_t i = lane; i < n; i += 32) {
-            const unsigned long long mb = b64_value(d.mz, i, wm, lut, bad);
+            const unsigned long long mb = d.mz_zl ? raw_value(d.mz_raw, i, wm) : b64_value(d.mz, i, wm, lut, bad);
             const double m = d.mz_f32 ? (double)__uint_as_float((uint32_t)mb) : __longlong_as_double((long long)mb);
             if (has_pred && !(m >= lo && m <= hi)) continue;
-            const unsigned long long ib = b64_value(d.in, i, wi, lut, bad);
+            const unsigned long long ib = d.in_zl ? raw_value(d.in_raw, i, wi) : b64_value(d.in, i, wi, lut, bad);
             acc += d.in_f32 ? (double)__uint_as_float((uint32_t)ib) : __longlong_as_double((long long)ib);
             ++cnt;
         }
@@ -296,6 +329,97 @@ __global__ void __launch_bounds__(256) mzml_sum_kernel(const SpecDesc *specs, un
         }
         if (bad & 0x80u) atomicOr(flags, kMzErrFormat);
     }
+}
+
+
+// ---- zlib detour ----------------------------------------------------------------------------------------------------
+struct ZArr {
+    uint32_t spec, which;  // which: 0 = m/z, 1 = intensity
+};
+// Z0: the list of zlib arrays + their sizes: [0] compressed bytes (padded), [1] inflated bytes (padded to 16), [2] bitmap words
+__global__ void mzml_zlist_kernel(const SpecDesc *specs, unsigned long long n_spec, ZArr *list, unsigned long long *n_list, int32_t *sizes,
+                                  unsigned long long cap) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_spec) return;
+    const SpecDesc d = specs[i];
+    for (uint32_t which = 0; which < 2; ++which) {
+        const bool zl = which ? d.in_zl : d.mz_zl;
+        const uint8_t *p = which ? d.in : d.mz;
+        if (!zl || !p) continue;
+        const unsigned long long k = atomicAdd(n_list, 1ull);
+        if (k >= cap) continue;
+        list[k] = ZArr{(uint32_t)i, which};
+        const uint32_t comp = b64_bytes(p, which ? d.in_len : d.mz_len);
+        const uint32_t isize = d.n_default * ((which ? d.in_f32 : d.mz_f32) ? 4u : 8u);
+        sizes[k] = (int32_t)((comp + 64u + 15u) & ~15u);
+        sizes[cap + 1 + k] = (int32_t)((isize + 15u) & ~15u);
+        sizes[2 * (cap + 1) + k] = (int32_t)((isize + 31u) / 32u);
+    }
+}
+
+// Z2: one warp per zlib array: base64 text -> bytes in the staging buffer
+__global__ void __launch_bounds__(256) mzml_b64_kernel(const SpecDesc *specs, const ZArr *list, unsigned long long n_list, const long long *comp_off,
+                                                      uint8_t *comp, uint32_t *flags) {
+    __shared__ uint8_t lut[256];
+    {
+        const int c = threadIdx.x;
+        uint8_t v = 0x80;
+        if (c >= 'A' && c <= 'Z') v = (uint8_t)(c - 'A');
+        else if (c >= 'a' && c <= 'z') v = (uint8_t)(c - 'a' + 26);
+        else if (c >= '0' && c <= '9') v = (uint8_t)(c - '0' + 52);
+        else if (c == '+') v = 62;
+        else if (c == '/') v = 63;
+        else if (c == '=') v = 0;
+        lut[c] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    uint32_t bad = 0;
+    for (unsigned long long k = wid; k < n_list; k += nw) {
+        const SpecDesc d = specs[list[k].spec];
+        const uint8_t *p = list[k].which ? d.in : d.mz;
+        const uint32_t len = list[k].which ? d.in_len : d.mz_len, nbytes = b64_bytes(p, len);
+        uint8_t *dst = comp + comp_off[k];
+        for (uint32_t g = lane; g < len / 4u; g += 32) {
+            const uint32_t v0 = lut[p[4 * g]], v1 = lut[p[4 * g + 1]], v2 = lut[p[4 * g + 2]], v3 = lut[p[4 * g + 3]];
+            bad |= v0 | v1 | v2 | v3;
+            const uint32_t t = ((v0 & 63u) << 18) | ((v1 & 63u) << 12) | ((v2 & 63u) << 6) | (v3 & 63u);
+            const uint32_t o = 3u * g;
+            if (o < nbytes) dst[o] = (uint8_t)(t >> 16);
+            if (o + 1 < nbytes) dst[o + 1] = (uint8_t)(t >> 8);
+            if (o + 2 < nbytes) dst[o + 2] = (uint8_t)t;
+        }
+    }
+    bad = __reduce_or_sync(0xFFFFFFFFu, bad);
+    if (lane == 0 && (bad & 0x80u)) atomicOr(flags, kMzErrFormat);
+}
+
+// Z3: member table of the inflate kernels + the descriptors' pointers to the inflated values.  RFC 1950: CMF (deflate, window
+// <= 32 KiB), FLG (check bits, no preset dictionary), DEFLATE data, Adler-32.
+__global__ void mzml_ztable_kernel(SpecDesc *specs, const ZArr *list, unsigned long long n_list, const long long *comp_off, const long long *out_off,
+                                   const long long *bm_off, const uint8_t *comp, uint8_t *out, BgzfMember *table, uint32_t *flags) {
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_list) return;
+    SpecDesc &d = specs[list[k].spec];
+    const bool in = list[k].which != 0;
+    const uint32_t nbytes = b64_bytes(in ? d.in : d.mz, in ? d.in_len : d.mz_len);
+    const uint32_t isize = d.n_default * ((in ? d.in_f32 : d.mz_f32) ? 4u : 8u);
+    const uint8_t *z = comp + comp_off[k];
+    BgzfMember m;
+    m.in_off = (uint64_t)comp_off[k] + 2u;
+    m.in_len = nbytes >= 6u ? nbytes - 6u : 0u;
+    m.isize = isize;
+    m.out_addr = (uint64_t)reinterpret_cast<uintptr_t>(out + out_off[k]);
+    m.bm_off = (uint32_t)bm_off[k];
+    m.pad_ = 0;
+    if (nbytes < 6u || (z[0] & 0x0Fu) != 8u || (z[0] >> 4) > 7u || (((uint32_t)z[0] << 8) | z[1]) % 31u != 0u || (z[1] & 0x20u)) {
+        atomicOr(flags, kMzErrZlib);
+        m.isize = 0;  // skipped by the inflate kernels
+    }
+    table[k] = m;
+    if (in) d.in_raw = out + out_off[k];
+    else d.mz_raw = out + out_off[k];
 }
 
 size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -381,6 +505,67 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
         CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         const unsigned long long n_spec = h[1];
+        if ((uint32_t)h[4] & kMzErrFormat) return fail(EXON_GPU_ERR_PARSE, "malformed mzML: a <binary> element without data type / compression / end tag, or invalid base64");
+        if ((uint32_t)h[4] & kMzErrZlib)
+            return fail(EXON_GPU_ERR_PARSE, "mzml: a zlib-compressed binary array (MS:1000574) without defaultArrayLength on its <spectrum>");
+        void *z_pool[2] = {nullptr, nullptr};
+        struct ZFree {
+            void **p;
+            cudaStream_t st;
+            ~ZFree() {
+                for (int i = 0; i < 2; ++i)
+                    if (p[i]) cudaFreeAsync(p[i], st);
+            }
+        } z_free{z_pool, st};
+        if (n_spec && ((uint32_t)h[4] & kMzHasZlib)) {
+            // ---- zlib detour: list -> sizes -> scans -> base64 decode -> member table -> inflate ----
+            const unsigned long long zcap = 2 * n_spec;
+            size_t cub2 = 0;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub2, (int32_t *)nullptr, (long long *)nullptr, (int)(zcap + 1), st));
+            const size_t o_list = 0, o_sizes = o_list + al256(zcap * sizeof(ZArr)), o_offs = o_sizes + al256(3 * (zcap + 1) * 4), o_cub = o_offs + al256(3 * (zcap + 1) * 8),
+                         o_tab = o_cub + al256(cub2), o_misc = o_tab + al256(zcap * sizeof(BgzfMember)), z_bytes = o_misc + 256;
+            CUDA_TRY(cudaMallocAsync(&z_pool[0], z_bytes, st));
+            uint8_t *zb = (uint8_t *)z_pool[0];
+            ZArr *d_list = (ZArr *)(zb + o_list);
+            int32_t *d_sizes = (int32_t *)(zb + o_sizes);
+            long long *d_offs = (long long *)(zb + o_offs);
+            unsigned long long *d_zmisc = (unsigned long long *)(zb + o_misc);  // [0] n_list | [2] inflate flags (2 x u32)
+            CUDA_TRY(cudaMemsetAsync(d_sizes, 0, 3 * (zcap + 1) * 4, st));
+            CUDA_TRY(cudaMemsetAsync(d_zmisc, 0, 64, st));
+            mzml_zlist_kernel<<<(unsigned)((n_spec + 255) / 256), 256, 0, st>>>(d_spec, n_spec, d_list, d_zmisc, d_sizes, zcap);
+            for (int q = 0; q < 3; ++q) {
+                size_t tb = cub2;
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(zb + o_cub, tb, (const int32_t *)(d_sizes + q * (zcap + 1)), d_offs + q * (zcap + 1), (int)(zcap + 1), st));
+            }
+            long long h_tot[3];
+            unsigned long long h_nz = 0;
+            for (int q = 0; q < 3; ++q) CUDA_TRY(cudaMemcpyAsync(&h_tot[q], d_offs + q * (zcap + 1) + zcap, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(&h_nz, d_zmisc, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            ctx->launches.fetch_add(5);
+            if (h_nz > zcap) return fail(EXON_GPU_ERR_STATE, "mzml: zlib array list overflow");
+            if (h_nz) {
+                const size_t comp_total = (size_t)h_tot[0] + 512, out_total = (size_t)h_tot[1] + 64;
+                CUDA_TRY(cudaMallocAsync(&z_pool[1], al256(comp_total) + out_total, st));
+                uint8_t *d_comp = (uint8_t *)z_pool[1], *d_raw = d_comp + al256(comp_total);
+                const int b64_grid = (int)std::min<unsigned long long>((h_nz + 7) / 8, (unsigned long long)ctx->sm_count * 8);
+                mzml_b64_kernel<<<b64_grid, 256, 0, st>>>(d_spec, d_list, h_nz, d_offs, d_comp, (uint32_t *)(d_out + 4));
+                mzml_ztable_kernel<<<(unsigned)((h_nz + 127) / 128), 128, 0, st>>>(d_spec, d_list, h_nz, d_offs, d_offs + (zcap + 1), d_offs + 2 * (zcap + 1), d_comp,
+                                                                                    d_raw, (BgzfMember *)(zb + o_tab), (uint32_t *)(d_out + 4));
+                CUDA_TRY(cudaGetLastError());
+                const int init_flags[2] = {0, 0x7FFFFFFF};
+                CUDA_TRY(cudaMemcpyAsync(d_zmisc + 2, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
+                if (int rc = bgzf_inflate_launch(ctx, d_comp, (const BgzfMember *)(zb + o_tab), (int)h_nz, (uint32_t *)(d_zmisc + 2), (size_t)h_tot[2], (size_t)h_tot[0]))
+                    return rc;
+                ctx->launches.fetch_add(2);
+                uint32_t h_inf[2] = {0, 0};
+                CUDA_TRY(cudaMemcpyAsync(h_inf, d_zmisc + 2, 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                if (h_inf[0])
+                    return fail(EXON_GPU_ERR_PARSE, "mzml: a zlib-compressed binary array does not inflate:%s%s", (h_inf[0] & 1u) ? " invalid DEFLATE data;" : "",
+                                (h_inf[0] & 2u) ? " its size differs from defaultArrayLength x value width;" : "");
+            }
+        }
         if (n_spec) {
             const int sum_grid = (int)std::min<unsigned long long>((n_spec + 7) / 8, (unsigned long long)ctx->sm_count * 8);
             mzml_sum_kernel<<<sum_grid, 256, 0, st>>>(d_spec, n_spec, pred != nullptr, pred ? pred->mz_lo : 0.0,
@@ -393,7 +578,8 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
         CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         const uint32_t flags = (uint32_t)h[4];
-        if (flags & kMzErrZlib) return fail(EXON_GPU_ERR_UNSUPPORTED, "mzml: zlib-compressed binary arrays (MS:1000574) are not decoded on the device yet");
+        if (flags & kMzErrZlib)
+            return fail(EXON_GPU_ERR_PARSE, "mzml: a zlib-compressed binary array (MS:1000574) without defaultArrayLength on its <spectrum>, or with an invalid zlib header");
         if (flags & kMzErrFormat) return fail(EXON_GPU_ERR_PARSE, "malformed mzML: a <binary> element without data type / compression / end tag, or invalid base64");
         if (out_sum) memcpy(out_sum, &h[2], 8);
         if (out_selected) *out_selected = (int64_t)h[3];

@@ -334,7 +334,8 @@ typedef struct {
  * everything fed so far (pred == NULL: every zipped peak).  *out_sum is an f64 sum accumulated in device order (1e-6
  * relative parity, north_star); *out_selected the number of peaks summed; *out_spectra the number of <spectrum>
  * elements (COUNT(*)).  Arrays are decoded as exon/exon-mzml/src/mzml_reader/binary_conversion.rs:26-95 does
- * (base64, little-endian f32 / f64); zlib-compressed arrays give EXON_GPU_ERR_UNSUPPORTED for now. */
+ * (base64, optional zlib -- inflated on the device --, little-endian f32 / f64).  A zlib-compressed array is sized by the
+ * defaultArrayLength of its <spectrum>; without it, or when the stream inflates to another size: EXON_GPU_ERR_PARSE. */
 int exon_gpu_mzml_filter_sum(exon_gpu_stream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected,
                              int64_t *out_spectra);
 

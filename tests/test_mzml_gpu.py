@@ -40,11 +40,16 @@ def test_reference_fixtures(gpu_ctx):
     assert sp == 2 and n == 0 and s == 0.0        # 2 spectra (slt/mzml-functions.slt:46-49); neither has an m/z array
     assert gpu(gpu_ctx, [bgzf_compress(t)], gz=True)[2] == 2 and gpu(gpu_ctx, [gzip.compress(t)], gz=True)[2] == 2
     assert gpu(gpu_ctx, [t, t])[2] == 4
-    # pyoteomics: spectrum 0 is uncompressed (f64 m/z, f32 intensity), spectrum 1 is zlib -> the device path refuses it
+    # pyoteomics: spectrum 0 is uncompressed (f64 m/z, f32 intensity), spectrum 1 is zlib-compressed f32 / f32: base64 ->
+    # device inflate -> values.  Its per-spectrum sums are the fixture facts of SURVEY appendix A (17 648 193.83 / 69 381 842.12)
     p = fixture("pyoteomics.mzML.gz")
-    with pytest.raises(ExonGpuError) as e:
-        gpu(gpu_ctx, [p], 500.0, 600.0)
-    assert e.value.code == _abi.ERR_UNSUPPORTED
+    for lo, hi in RANGES + [(None, None)]:
+        r = oracle.mzml_scan(p, lo, hi)
+        s, n, sp = gpu(gpu_ctx, [p], lo, hi)
+        assert sp == 2 and n == r.n_selected and close(s, r.sum), (lo, hi)
+    s, n, sp = gpu(gpu_ctx, [p])
+    assert n == 2 * 19914 and close(s, 2 * 69381842.11895752)
+    assert gpu(gpu_ctx, [bgzf_compress(p)], 500.0, 600.0, gz=True)[1] == oracle.mzml_scan(p, 500.0, 600.0).n_selected
     cut = p.index(b"<spectrum ", p.index(b"<spectrum ") + 10)
     first = p[:cut] + b"</spectrumList></run></mzML>\n"   # the document with its first spectrum only
     for lo, hi in RANGES:
@@ -121,3 +126,57 @@ def test_feeds_and_f32(gpu_ctx):
     if bad != doc:
         with pytest.raises(ExonGpuError):
             gpu(gpu_ctx, [bad], 0.0, 5000.0)
+
+
+def zlib_variant(text: bytes, every: int = 2) -> bytes:
+    """Re-encode every `every`-th binary array of a synthetic document with zlib (MS:1000576 -> MS:1000574), as pyteomics /
+    ProteoWizard writers do; sizes stay declared by defaultArrayLength."""
+    import base64
+    import re
+    import zlib
+
+    out, pos, k = [], 0, 0
+    for m in re.finditer(rb'<binaryDataArray [^>]*>.*?</binaryDataArray>', text, re.S):
+        out.append(text[pos:m.start()])
+        pos = m.end()
+        blk = m.group(0)
+        k += 1
+        if k % every == 0:
+            b = re.search(rb"<binary>(.*?)</binary>", blk, re.S)
+            payload = base64.b64encode(zlib.compress(base64.b64decode(b.group(1).strip()), 6))
+            blk = blk[:b.start(1)] + payload + blk[b.end(1):]
+            blk = blk.replace(b"MS:1000576", b"MS:1000574")
+            blk = re.sub(rb'encodedLength="\d+"', b'encodedLength="%d"' % len(payload), blk)
+        out.append(blk)
+    out.append(text[pos:])
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("every", [1, 2, 3])
+def test_zlib_arrays_synthetic(gpu_ctx, every):
+    from synth import mzml
+
+    sh = mzml.shards(600, 2, peaks=150)
+    files = [zlib_variant(bytes(f), every) for f in sh.files]
+    assert b"MS:1000574" in files[0]
+    for lo, hi in RANGES[:3] + [(None, None)]:
+        want = [oracle.mzml_scan(f, lo, hi) for f in files]
+        plain = [oracle.mzml_scan(bytes(f), lo, hi) for f in sh.files]
+        assert [w.n_selected for w in want] == [w.n_selected for w in plain]
+        s, n, sp = gpu(gpu_ctx, files, lo, hi)
+        assert sp == sh.n and n == sum(w.n_selected for w in want) and close(s, sum(w.sum for w in want))
+
+
+def test_zlib_array_errors(gpu_ctx):
+    from synth import mzml
+
+    f = zlib_variant(bytes(mzml.shards(20, 1, peaks=30).files[0]), 1)
+    bad = f.replace(b'defaultArrayLength="30"', b'defaultArrayLength="31"')   # declared size differs from the stream
+    with pytest.raises(ExonGpuError) as e:
+        gpu(gpu_ctx, [bad])
+    assert e.value.code == _abi.ERR_PARSE
+    import re
+    nodefault = re.sub(rb' defaultArrayLength="\d+"', b"", f)
+    with pytest.raises(ExonGpuError) as e:
+        gpu(gpu_ctx, [nodefault])
+    assert e.value.code == _abi.ERR_PARSE
