@@ -66,6 +66,16 @@ struct MzArgs {
 
 __device__ __forceinline__ bool is_delim(uint32_t c) { return c == ' ' || c == '>' || c == '/' || c == '\n' || c == '\t' || c == '\r'; }
 
+// four characters as the little-endian word an unaligned load yields
+__host__ __device__ constexpr uint32_t cc4(char a, char b, char c, char d) {
+    return (uint32_t)(uint8_t)a | ((uint32_t)(uint8_t)b << 8) | ((uint32_t)(uint8_t)c << 16) | ((uint32_t)(uint8_t)d << 24);
+}
+// 32-bit load from shared memory at any alignment
+__device__ __forceinline__ uint32_t lds_unaligned32(uint32_t sa) {
+    const uint32_t a0 = sa & ~3u;
+    return __funnelshift_r(lds32(a0), lds32(a0 + 4), (sa & 3u) * 8u);
+}
+
 template <class V>
 __device__ __forceinline__ bool match_at(const V &v, int p, const char *lit, int n) {
     for (int i = 0; i < n; ++i)
@@ -122,7 +132,29 @@ __global__ void __launch_bounds__(MzRing::WARPS * 32, 3) mzml_events_kernel(cons
                 if (p < v.seg_lo || p >= v.hi) continue;
                 uint32_t kind = 0;
                 long long at = tile_off + p;
-                if (view_byte(v, p) == '<') {
+                const int lo_ok = v.seg_lo > v.sm_lo ? v.seg_lo : v.sm_lo, hi_ok = v.hi < v.sm_hi ? v.hi : v.sm_hi;
+                const uint32_t pa = v.sa + (uint32_t)p;  // shared-window address of the hit (two's complement for p < 0)
+                const bool is_lt = view_byte(v, p) == '<';
+                if (is_lt && p + 20 <= hi_ok) {
+                    // fast path: the tag name as unaligned words from the staged bytes; most '<' open a tag we do not track
+                    const uint32_t w0 = lds_unaligned32(pa);
+                    if (w0 == cc4('<', 's', 'p', 'e')) {
+                        if (lds_unaligned32(pa + 4) == cc4('c', 't', 'r', 'u') && lds8(pa + 8) == 'm' && is_delim(lds8(pa + 9))) kind = kEvSpectrum;
+                    } else if (w0 == cc4('<', 'b', 'i', 'n')) {
+                        const uint32_t w1 = lds_unaligned32(pa + 4);
+                        if (w1 == cc4('a', 'r', 'y', '>')) {
+                            kind = kEvBinStart;
+                            at += 8;  // the payload starts after the tag
+                        } else if (w1 == cc4('a', 'r', 'y', 'D') && lds_unaligned32(pa + 8) == cc4('a', 't', 'a', 'A') && lds_unaligned32(pa + 12) == cc4('r', 'r', 'a', 'y') &&
+                                   is_delim(lds8(pa + 16))) {
+                            kind = kEvBda;
+                        }
+                    } else if (w0 == cc4('<', '/', 'b', 'i')) {
+                        if (lds_unaligned32(pa + 4) == cc4('n', 'a', 'r', 'y') && lds8(pa + 8) == '>') kind = kEvBinEnd;
+                    } else if (w0 == cc4('<', '/', 's', 'p')) {
+                        if (lds_unaligned32(pa + 4) == cc4('e', 'c', 't', 'r') && (lds_unaligned32(pa + 8) & 0x00FFFFFFu) == cc4('u', 'm', '>', 0)) kind = kEvSpecEnd;
+                    }
+                } else if (is_lt) {
                     const uint32_t c1 = view_byte(v, p + 1);
                     if (c1 == 's') {
                         if (match_at(v, p + 1, "spectrum", 8) && is_delim(view_byte(v, p + 9))) kind = kEvSpectrum;
@@ -138,6 +170,18 @@ __global__ void __launch_bounds__(MzRing::WARPS * 32, 3) mzml_events_kernel(cons
                     } else if (c1 == '/') {
                         if (match_at(v, p + 2, "binary>", 7)) kind = kEvBinEnd;
                         else if (match_at(v, p + 2, "spectrum>", 9)) kind = kEvSpecEnd;
+                    }
+                } else if (p - 14 >= lo_ok && p + 9 <= hi_ok) {
+                    // ... accession="MS:1000xxx": p is the ':'; 16 bytes before and 8 after it as unaligned words
+                    if (lds_unaligned32(pa - 2) == cc4('M', 'S', ':', '1') && lds_unaligned32(pa - 6) == cc4('o', 'n', '=', '"') &&
+                        lds_unaligned32(pa - 10) == cc4('e', 's', 's', 'i') && lds_unaligned32(pa - 14) == cc4(' ', 'a', 'c', 'c') &&
+                        (lds_unaligned32(pa + 2) & 0x00FFFFFFu) == cc4('0', '0', '0', 0) && lds8(pa + 8) == '"') {
+                        const uint32_t d0 = lds8(pa + 5) - '0', d1 = lds8(pa + 6) - '0', d2 = lds8(pa + 7) - '0';
+                        if (d0 <= 9u && d1 <= 9u && d2 <= 9u) {
+                            const uint32_t code = d0 * 100u + d1 * 10u + d2;
+                            kind = code == 514u ? kEvMz : code == 515u ? kEvIntensity : code == 617u ? kEvWave : code == 521u ? kEvF32
+                                 : code == 523u ? kEvF64 : code == 574u ? kEvZlib : code == 576u ? kEvNoComp : 0u;
+                        }
                     }
                 } else {
                     // ... accession="MS:1000xxx": p is the ':'
