@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "scan_i64.cuh"
 
 namespace exon {
 
@@ -798,7 +799,7 @@ int bam_build_columns(VcfStream *s) {
 
     // scratch_b: rec_ptr | 7 counts | 7 prefixes | rowflags | cub | tables
     size_t cub_bytes = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (long long *)nullptr, (int)nr1, st));
+    CUDA_TRY(exclusive_sum_i32_i64(nullptr, cub_bytes, (const int32_t *)nullptr, (long long *)nullptr, (int)nr1, st));
     const size_t tab_bytes = bal256(ftab.size() * sizeof(BamFileTab)) + 2 * bal256(ref_off.size() * 4 + 4) + bal256(blob.size() + 1) + (kBNVar + 1) * bal256(nb1 * 8) + 256;
     if (int rc = ctx->ensure_scratch_b(bal256(nr1 * 8) + kBNVar * (bal256(nr1 * 4) + bal256(nr1 * 8)) + bal256(nr1) + bal256(cub_bytes) + tab_bytes + 4096)) return rc;
     uint8_t *x = (uint8_t *)ctx->scratch_b;
@@ -892,7 +893,7 @@ int bam_build_columns(VcfStream *s) {
     for (int k = 0; k < kBNVar; ++k) {
         if (!need[k]) continue;
         size_t tb = cub_bytes;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, (const int32_t *)ca.cnt[k], pre[k], (int)nr1, st));
+        CUDA_TRY(exclusive_sum_i32_i64(cub_tmp, tb, (const int32_t *)ca.cnt[k], pre[k], (int)nr1, st));
         bam_gather_i64<<<(unsigned)((nb1 + 255) / 256), 256, 0, st>>>(pre[k], d_brow, (int64_t)nb1, d_base[k]);
         ctx->launches.fetch_add(2);
         c->base[k].resize(nb1);

@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "scan_i64.cuh"
 #include "tile_ring.cuh"
 
 namespace exon {
@@ -830,7 +831,7 @@ int fq_build_columns(VcfStream *s) {
 
     // scratch B: line tables | lens x4 | voff x4 | cub temp | batch tables
     size_t cub2 = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub2, (int32_t *)nullptr, (long long *)nullptr, (int)(n_records + 1), st));
+    CUDA_TRY(exclusive_sum_i32_i64(nullptr, cub2, (const int32_t *)nullptr, (long long *)nullptr, (int)(n_records + 1), st));
     const size_t nb1 = (size_t)c->n_batches + 1;
     size_t ob = 0;
     const size_t o_ls = ob; ob += al256((size_t)(n_lines + 1) * 8);
@@ -884,7 +885,7 @@ int fq_build_columns(VcfStream *s) {
     for (int k = 0; k < 4; ++k) {
         if (!want[k]) continue;
         size_t tb = cub2;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(scb + o_cub2, tb, (const int32_t *)(scb + o_len[k]), (long long *)(scb + o_voff[k]), (int)(n_records + 1), st));
+        CUDA_TRY(exclusive_sum_i32_i64(scb + o_cub2, tb, (const int32_t *)(scb + o_len[k]), (long long *)(scb + o_voff[k]), (int)(n_records + 1), st));
         fq_gather_i64<<<(unsigned)((nb1 + 255) / 256), 256, 0, st>>>((const long long *)(scb + o_voff[k]), (const long long *)(scb + o_brow), (int64_t)nb1,
                                                                     (long long *)(scb + o_bv0));
         c->batch_v0[k].resize(nb1);

@@ -29,6 +29,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "scan_i64.cuh"
 #include "tile_ring.cuh"
 
 namespace exon {
@@ -237,21 +238,23 @@ __global__ void mzml_spectra_kernel(const unsigned long long *ev, unsigned long 
     SpecDesc d;
     d.mz = d.in = d.mz_raw = d.in_raw = nullptr;
     d.mz_len = d.in_len = d.mz_f32 = d.in_f32 = d.mz_zl = d.in_zl = d.n_default = d.pad_ = 0;
-    {
-        // defaultArrayLength="N" inside the <spectrum ...> tag (the only place a zlib array's decoded size is declared)
+    // defaultArrayLength="N" inside the <spectrum ...> tag (the only place a zlib array's decoded size is declared); parsed
+    // only when the spectrum turns out to hold a zlib array
+    auto default_array_length = [&]() -> uint32_t {
         const uint8_t *t = segs[seg].base + segs[seg].skip + ((ev[i] >> 4) & ((1ull << 40) - 1ull));
         const uint8_t *tend = segs[seg].base + segs[seg].skip + segs[seg].len;
         const char lit[] = "defaultArrayLength=\"";
         for (int k = 0; k < 4096 && t + k + 20 < tend && t[k] != '>'; ++k) {
+            if (t[k] != 'd') continue;
             bool m = true;
-            for (int q = 0; q < 20 && m; ++q) m = t[k + q] == (uint8_t)lit[q];
+            for (int q = 1; q < 20 && m; ++q) m = t[k + q] == (uint8_t)lit[q];
             if (!m) continue;
             unsigned long long v = 0;
             for (const uint8_t *c = t + k + 20; c < tend && *c >= '0' && *c <= '9' && v < (1ull << 31); ++c) v = v * 10ull + (*c - '0');
-            d.n_default = v < (1ull << 31) ? (uint32_t)v : 0u;
-            break;
+            return v < (1ull << 31) ? (uint32_t)v : 0u;
         }
-    }
+        return 0u;
+    };
     uint32_t kind = 0, f32 = 0, f64 = 0, zl = 0, nc = 0, err = 0;
     unsigned long long start = 0;
     bool open = false;
@@ -277,7 +280,10 @@ __global__ void mzml_spectra_kernel(const unsigned long long *ev, unsigned long 
             if (b1 == b0 || (kind != kEvMz && kind != kEvIntensity)) continue;  // empty content, or an array the query does not read
             if ((!f32 && !f64) || (!zl && !nc)) { err |= kMzErrFormat; continue; }
             if (((b1 - b0) & 3) != 0 || (b1 - b0) > 0x7FFFFFFFll) { err |= kMzErrFormat; continue; }
-            if (zl) err |= d.n_default ? kMzHasZlib : kMzErrZlib;
+            if (zl) {
+                if (!d.n_default) d.n_default = default_array_length();
+                err |= d.n_default ? kMzHasZlib : kMzErrZlib;
+            }
             if (kind == kEvMz) { d.mz = b0; d.mz_len = (uint32_t)(b1 - b0); d.mz_f32 = f32 && !f64; d.mz_zl = zl; }
             else { d.in = b0; d.in_len = (uint32_t)(b1 - b0); d.in_f32 = f32 && !f64; d.in_zl = zl; }
         }
@@ -542,7 +548,11 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
         if (int rc = ctx->ensure_scratch_b((size_t)(n_spec_ev + 1) * sizeof(SpecDesc))) return rc;
         SpecDesc *d_spec = (SpecDesc *)ctx->scratch_b;
         size_t sb = sort_bytes;
-        CUDA_TRY(cub::DeviceRadixSort::SortKeys(scr + o_sort, sb, (const unsigned long long *)(scr + o_ev), (unsigned long long *)(scr + o_ev2), (int)n_ev, 0, 64, st));
+        int seg_bits = 1;
+        while ((1ull << seg_bits) < h_segs.size()) ++seg_bits;
+        // nothing lives above the segment index (the kind bits stay in: <binary></binary> puts two events at one offset)
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(scr + o_sort, sb, (const unsigned long long *)(scr + o_ev), (unsigned long long *)(scr + o_ev2), (int)n_ev, 0,
+                                                44 + seg_bits, st));
         mzml_spectra_kernel<<<(unsigned)((n_ev + 255) / 256), 256, 0, st>>>((const unsigned long long *)(scr + o_ev2), n_ev, a.segs,
                                                                               d_spec, d_out + 1, (uint32_t *)(d_out + 4));
         CUDA_TRY(cudaGetLastError());
@@ -565,7 +575,7 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
             // ---- zlib detour: list -> sizes -> scans -> base64 decode -> member table -> inflate ----
             const unsigned long long zcap = 2 * n_spec;
             size_t cub2 = 0;
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub2, (int32_t *)nullptr, (long long *)nullptr, (int)(zcap + 1), st));
+            CUDA_TRY(exclusive_sum_i32_i64(nullptr, cub2, (const int32_t *)nullptr, (long long *)nullptr, (int)(zcap + 1), st));
             const size_t o_list = 0, o_sizes = o_list + al256(zcap * sizeof(ZArr)), o_offs = o_sizes + al256(3 * (zcap + 1) * 4), o_cub = o_offs + al256(3 * (zcap + 1) * 8),
                          o_tab = o_cub + al256(cub2), o_misc = o_tab + al256(zcap * sizeof(BgzfMember)), z_bytes = o_misc + 256;
             CUDA_TRY(cudaMallocAsync(&z_pool[0], z_bytes, st));
@@ -579,7 +589,7 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
             mzml_zlist_kernel<<<(unsigned)((n_spec + 255) / 256), 256, 0, st>>>(d_spec, n_spec, d_list, d_zmisc, d_sizes, zcap);
             for (int q = 0; q < 3; ++q) {
                 size_t tb = cub2;
-                CUDA_TRY(cub::DeviceScan::ExclusiveSum(zb + o_cub, tb, (const int32_t *)(d_sizes + q * (zcap + 1)), d_offs + q * (zcap + 1), (int)(zcap + 1), st));
+                CUDA_TRY(exclusive_sum_i32_i64(zb + o_cub, tb, (const int32_t *)(d_sizes + q * (zcap + 1)), d_offs + q * (zcap + 1), (int)(zcap + 1), st));
             }
             long long h_tot[3];
             unsigned long long h_nz = 0;

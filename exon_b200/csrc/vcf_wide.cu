@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "f32_parse.cuh"
 #include "internal.h"
+#include "scan_i64.cuh"
 
 namespace exon {
 
@@ -159,7 +160,12 @@ __global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__
     for (int k = 0; k < kNScan; ++k)
         if (a.cnt[k]) a.cnt[k][r] = c[k];
     a.rowflags[r] = rf;
-    if (a.want_qual) a.qual[r] = q;
+    if (a.want_qual) {
+        a.qual[r] = q;
+        // rows left to vw_qual_kernel: one atomic per warp (the host launches that kernel only when the count is not zero)
+        const uint32_t pend = __ballot_sync(__activemask(), (rf & 8u) != 0u);
+        if (pend && (threadIdx.x & 31) == __ffs((int)pend) - 1) atomicAdd(a.first_bad_row + 1, (unsigned long long)__popc(pend));
+    }
     if (err) {
         atomicOr(a.flags, err);
         atomicMin(a.first_bad_row, (unsigned long long)r);
@@ -371,7 +377,7 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     if (n_rows == 0) return EXON_GPU_OK;
     const size_t nb1 = (size_t)w->n_batches + 1, nr1 = (size_t)n_rows + 1;
     size_t cub_bytes = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (int32_t *)nullptr, (long long *)nullptr, (int)nr1, st));
+    CUDA_TRY(exclusive_sum_i32_i64(nullptr, cub_bytes, (const int32_t *)nullptr, (long long *)nullptr, (int)nr1, st));
     if (cub_bytes > (1 << 20)) return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: scan scratch of %zu bytes", cub_bytes);
     uint8_t *x = li.extra;
     auto take = [&](size_t bytes) {
@@ -412,7 +418,7 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     a.brow = d_brow;
     a.flags = reinterpret_cast<uint32_t *>(d_misc);
     a.first_bad_row = d_misc + 1;
-    const unsigned long long init_misc[2] = {0ull, ~0ull};
+    const unsigned long long init_misc[3] = {0ull, ~0ull, 0ull};  // error flags | first bad row | rows with a QUAL left to the exact parser
     CUDA_TRY(cudaMemcpyAsync(d_misc, init_misc, sizeof(init_misc), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_brow, batch_row0->data(), nb1 * 8, cudaMemcpyHostToDevice, st));
 
@@ -435,24 +441,29 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     const unsigned grid = (unsigned)((n_rows + 255) / 256);
     vw_measure_kernel<<<grid, 256, 0, st>>>(a);
     ctx->launches.fetch_add(1);
-    if (w->want[5]) {
-        vw_qual_kernel<<<grid, 256, 0, st>>>(a);
-        ctx->launches.fetch_add(1);
-    }
+
     CUDA_TRY(cudaGetLastError());
     // ---- 2. scans + per-batch bases ----
     for (int k = 0; k < kNScan; ++k) {
         if (!need[k]) continue;
         size_t tb = cub_bytes;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, tb, (const int32_t *)a.cnt[k], pre[k], (int)nr1, st));
+        CUDA_TRY(exclusive_sum_i32_i64(cub_tmp, tb, (const int32_t *)a.cnt[k], pre[k], (int)nr1, st));
         vw_gather_i64<<<(unsigned)((nb1 + 255) / 256), 256, 0, st>>>(pre[k], d_brow, (int64_t)nb1, d_base(k));
         ctx->launches.fetch_add(2);
         w->base[k].resize(nb1);
         CUDA_TRY(cudaMemcpyAsync(w->base[k].data(), d_base(k), nb1 * 8, cudaMemcpyDeviceToHost, st));
     }
-    unsigned long long h_misc[2];
+    unsigned long long h_misc[3];
     CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (w->want[5] && h_misc[2] && !h_misc[0]) {
+        // some QUAL is not a short unsigned integer: the exact parser, then the error state again
+        vw_qual_kernel<<<grid, 256, 0, st>>>(a);
+        ctx->launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     if (const uint32_t e = (uint32_t)h_misc[0])
         return fail((e & ~kWErrQualDigits) ? EXON_GPU_ERR_PARSE : EXON_GPU_ERR_UNSUPPORTED, "malformed VCF record at row %llu:%s%s%s%s", h_misc[1],
                     (e & kWErrFields) ? " fewer than 8 tab-separated fields;" : "", (e & kWErrQual) ? " QUAL is not a float literal;" : "",

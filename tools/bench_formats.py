@@ -251,6 +251,27 @@ def bench_bam(args):
                              "sample": f"{n_cpu} of {len(sh.files)} files ({c_rows} alignments): zlib inflate + record walk, one worker per file"},
             "count_matches_truth": True, "gen_seconds": gen_s}
     s.close()
+    # column batches (exon_gpu_bam_next_batch), device resident: records already inflated in HBM -> Arrow columns; the
+    # first next_batch() builds every batch of the partition
+    cols = {}
+    for name, proj in (("flag_reference_start_end_mapq", (1, 2, 3, 4, 5)), ("all_0_9", tuple(range(10)))):
+        for rep in range(2):
+            with ctx.open_bam(projection=proj, columns_on_device=True) as cs:
+                for p in pins:
+                    cs.feed(p.array)
+                cs.count_by_reference(all_rows=True)   # inflate + verified walks: not part of the column build
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record(tstream)
+                if os.environ.get("EXON_BENCH_MEM"):
+                    print("mem before next_batch", name, rep, [x >> 20 for x in torch.cuda.mem_get_info()], file=sys.stderr, flush=True)
+                b = cs.next_batch()
+                e1.record(tstream)
+                torch.cuda.synchronize()
+                b.release()
+                if rep == 1:
+                    cols[name] = {"ms": e0.elapsed_time(e1), "alignments_per_s": sh.n / e0.elapsed_time(e1) * 1e3}
+    line["column_batches"] = cols
     for p in pins:
         p.free()
     ctx.close()
