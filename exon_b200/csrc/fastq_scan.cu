@@ -633,38 +633,6 @@ __global__ void fq_gather_u64(const unsigned long long *src, const long long *id
 
 }  // namespace
 
-// Column store of one FASTQ stream; batches are views into it.
-struct FqColumns {
-    std::atomic<int> refs{1};
-    bool on_device = false;
-    int device = 0;
-    int64_t n_rows = 0, n_batches = 0, next = 0;
-    int batch_rows = 8192, words_per_batch = 256;
-    std::vector<int> projection;
-    uint8_t *d_values[4] = {nullptr, nullptr, nullptr, nullptr};
-    int32_t *d_offsets[4] = {nullptr, nullptr, nullptr, nullptr};
-    uint32_t *d_valid = nullptr;
-    uint8_t *h_values[4] = {nullptr, nullptr, nullptr, nullptr};
-    int32_t *h_offsets[4] = {nullptr, nullptr, nullptr, nullptr};
-    uint32_t *h_valid = nullptr;
-    std::vector<long long> batch_row0;
-    std::vector<long long> batch_v0[4];
-    void unref() {
-        if (refs.fetch_sub(1) == 1) {
-            cudaSetDevice(device);
-            for (int k = 0; k < 4; ++k) {
-                cudaFree(d_values[k]);
-                cudaFree(d_offsets[k]);
-                cudaFreeHost(h_values[k]);
-                cudaFreeHost(h_offsets[k]);
-            }
-            cudaFree(d_valid);
-            cudaFreeHost(h_valid);
-            delete this;
-        }
-    }
-};
-
 void fq_columns_free(VcfStream *s) {
     if (s->fq_cols) {
         s->fq_cols->unref();
@@ -705,8 +673,11 @@ void fq_release_schema(ArrowSchema *s) {
     s->release = nullptr;
 }
 // exon/exon-fastq/src/config.rs:79-88: name !null, description nullable, sequence !null, quality_scores !null, all Utf8
-void fq_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
-    static const char *names[4] = {"name", "description", "sequence", "quality_scores"};
+void fq_fill_schema(const std::vector<int> &projection, ArrowSchema *out, bool fasta) {
+    // FASTA (exon/exon-fasta/src/config.rs:162-226): id !null, description nullable, sequence !null
+    static const char *fq_names[4] = {"name", "description", "sequence", "quality_scores"};
+    static const char *fa_names[4] = {"id", "description", "sequence", ""};
+    const char *const *names = fasta ? fa_names : fq_names;
     auto *p = new FqSchemaPriv();
     p->n_children = (int)projection.size();
     for (int i = 0; i < p->n_children; ++i) {
@@ -1031,14 +1002,14 @@ int fastq_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     if (!s->fq_cols) {
         if (int rc = s->flush_gz()) return rc;
         std::lock_guard<std::mutex> work(s->ctx->work_mu);
-        if (int rc = fq_build_columns(s)) {
+        if (int rc = s->fmt == kFmtFasta ? fasta_build_columns(s) : fq_build_columns(s)) {
             fq_columns_free(s);
             return rc;
         }
         s->drained = true;
     }
     FqColumns *c = s->fq_cols;
-    if (out_schema) fq_fill_schema(s->projection, out_schema);
+    if (out_schema) fq_fill_schema(s->projection, out_schema, s->fmt == kFmtFasta);
     memset(out, 0, sizeof(*out));
     if (c->next >= c->n_batches) return EXON_GPU_OK;  // end of stream: release == NULL
     const int64_t b = c->next++;

@@ -249,6 +249,8 @@ int gff_filter_count(VcfStream *s, const exon_gpu_region *region, int64_t *out_c
 
 // defined in fasta_scan.cu
 int fasta_rows(VcfStream *s, int64_t *out_rows);
+// defined in fasta_columns.cu: fills s->fq_cols with {id, description, sequence}
+int fasta_build_columns(VcfStream *s);
 
 // defined in mzml.cu
 int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected, int64_t *out_spectra);
@@ -257,6 +259,39 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
 void fq_columns_free(VcfStream *s);
 int fastq_next_batch(VcfStream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *out_count, int64_t *out_rows);
+
+// Column store of one FASTQ or FASTA stream (up to four utf8 columns, the second one nullable); batches are views into it.
+struct FqColumns {
+    std::atomic<int> refs{1};
+    bool on_device = false;
+    int device = 0;
+    int64_t n_rows = 0, n_batches = 0, next = 0;
+    int batch_rows = 8192, words_per_batch = 256;
+    std::vector<int> projection;
+    uint8_t *d_values[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t *d_offsets[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *d_valid = nullptr;
+    uint8_t *h_values[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t *h_offsets[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t *h_valid = nullptr;
+    std::vector<long long> batch_row0;
+    std::vector<long long> batch_v0[4];
+    void unref() {
+        if (refs.fetch_sub(1) == 1) {
+            cudaSetDevice(device);
+            for (int k = 0; k < 4; ++k) {
+                cudaFree(d_values[k]);
+                cudaFree(d_offsets[k]);
+                cudaFreeHost(h_values[k]);
+                cudaFreeHost(h_offsets[k]);
+            }
+            cudaFree(d_valid);
+            cudaFreeHost(h_valid);
+            delete this;
+        }
+    }
+};
+
 
 // Line index of a resident partition (fastq_scan.cu), used by the FASTQ and the wide VCF column builds.
 struct LineIndex {

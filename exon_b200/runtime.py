@@ -125,8 +125,8 @@ class Context:
     def open_gff(self) -> "GffStream":
         return GffStream(self)
 
-    def open_fasta(self) -> "FastaStream":
-        return FastaStream(self)
+    def open_fasta(self, **kw) -> "FastaStream":
+        return FastaStream(self, **kw)
 
     def open_mzml(self) -> "MzmlStream":
         return MzmlStream(self)
@@ -602,11 +602,39 @@ class MzmlStream(FastqStream):
 class FastaStream(MzmlStream):
     """exon_gpu_stream opened with exon_gpu_fasta_open: COUNT(*) of FASTA records."""
 
-    def __init__(self, ctx: Context):
+    def __init__(self, ctx: Context, *, batch_rows: int = 8192, projection=None, columns_on_device: bool = False):
         self.ctx = ctx
         self.lib = ctx.lib
         self.handle = C.c_void_p()
-        check(self.lib.exon_gpu_fasta_open(ctx.handle, C.byref(self.handle)))
+        self.columns_on_device = columns_on_device
+        if projection is None:
+            check(self.lib.exon_gpu_fasta_open(ctx.handle, C.byref(self.handle)))
+        else:
+            self._proj = (C.c_int32 * max(len(projection), 1))(*projection)
+            opts = _abi.FastqOpts(batch_rows, len(projection), self._proj, int(columns_on_device))
+            check(self.lib.exon_gpu_fasta_open_columns(ctx.handle, C.byref(opts), C.byref(self.handle)))
+
+    def next_batch(self):
+        arr, sch = _abi.ArrowArray(), _abi.ArrowSchema()
+        check(self.lib.exon_gpu_fasta_next_batch(self.handle, C.byref(arr), C.byref(sch)))
+        if not arr.release:
+            if sch.release:
+                sch.release(C.byref(sch))
+            return None
+        return VcfBatch(arr, sch, self.columns_on_device)
+
+    def batches(self):
+        while True:
+            b = self.next_batch()
+            if b is None:
+                return
+            yield b
+
+    def feed_gzip(self, data, *, is_last: bool = True):
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(data, dtype=np.uint8)
+        self._last_host = data
+        check(self.lib.exon_gpu_stream_feed_gzip(self.handle, C.c_void_p(data.ctypes.data), data.size, int(is_last)))
 
     def feed(self, data, *, is_last: bool = True, device_ptr: int | None = None, nbytes: int | None = None):
         if device_ptr is not None:

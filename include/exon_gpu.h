@@ -259,6 +259,14 @@ int exon_gpu_stream_body_bytes(exon_gpu_stream *s, int64_t *out_bytes);
 int exon_gpu_fasta_open(exon_gpu_ctx *ctx, exon_gpu_stream **out);
 int exon_gpu_fasta_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last);
 int exon_gpu_fasta_rows(exon_gpu_stream *s, int64_t *out_rows);
+/* Columns out: BatchReader::read_batch + FASTAArrayBuilder::{append, finish} for the Utf8 sequence type
+ * (exon/exon-fasta/src/batch_reader.rs:52-103, exon/exon-fasta/src/array_builder.rs:108-160; schema exon/exon-fasta/src/config.rs:162-226):
+ * 0 id utf8 !null (up to the first ASCII whitespace of the definition line), 1 description utf8 (the trimmed rest, NULL when
+ * there is none), 2 sequence utf8 (all sequence lines, terminators removed).  A file that does not begin with '>', a
+ * definition without a name or without any sequence line: EXON_GPU_ERR_PARSE.  A batch whose sequence bytes exceed 2^31 - 1
+ * (the reference's LargeUtf8 option) is EXON_GPU_ERR_UNSUPPORTED.  exon_gpu_fastq_opts carries batch_rows / projection. */
+int exon_gpu_fasta_open_columns(exon_gpu_ctx *ctx, const exon_gpu_fastq_opts *opts, exon_gpu_stream **out);
+int exon_gpu_fasta_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 
 /* ---- GFF partition stream ----------------------------------------------------------------------------------------- */
 /* GFFScan + BatchReader::{read_line, filter, read_batch} (exon/exon-gff/src/batch_reader.rs:56-130) under

@@ -493,6 +493,39 @@ def fasta_count(data) -> int:
     return int(n)
 
 
+class FastaRecords(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("name_len", C.POINTER(C.c_int32)), ("desc_len", C.POINTER(C.c_int32)), ("seq_len", C.POINTER(C.c_int64)),
+                ("names", C.POINTER(C.c_uint8)), ("descs", C.POINTER(C.c_uint8)), ("seqs", C.POINTER(C.c_uint8)),
+                ("names_len", C.c_int64), ("descs_len", C.c_int64), ("seqs_len", C.c_int64), ("err", C.c_int32)]
+
+
+def fasta_records(data):
+    """[(id bytes, description bytes | None, sequence bytes)] of one FASTA text, as the reference's batches hold them."""
+    a = _buf(data)
+    L = _fq()
+    L.exo_fasta_read.restype = C.POINTER(FastaRecords)
+    L.exo_fasta_read.argtypes = [C.c_void_p, C.c_int64]
+    L.exo_fasta_records_free.argtypes = [C.POINTER(FastaRecords)]
+    rp = L.exo_fasta_read(a.ctypes.data, a.size)
+    try:
+        r = rp.contents
+        if r.err:
+            raise ValueError({1: "invalid definition", 2: "missing name", 3: "invalid sequence"}[r.err])
+        names = bytes(np.ctypeslib.as_array(r.names, (max(r.names_len, 1),))[: r.names_len]) if r.names_len else b""
+        descs = bytes(np.ctypeslib.as_array(r.descs, (max(r.descs_len, 1),))[: r.descs_len]) if r.descs_len else b""
+        seqs = bytes(np.ctypeslib.as_array(r.seqs, (max(r.seqs_len, 1),))[: r.seqs_len]) if r.seqs_len else b""
+        out, n0, d0, s0 = [], 0, 0, 0
+        for i in range(r.rows):
+            nl, dl, sl = r.name_len[i], r.desc_len[i], r.seq_len[i]
+            out.append((names[n0:n0 + nl], None if dl < 0 else descs[d0:d0 + dl], seqs[s0:s0 + sl]))
+            n0 += nl
+            d0 += max(dl, 0)
+            s0 += sl
+        return out
+    finally:
+        L.exo_fasta_records_free(rp)
+
+
 def gff_filter_count(data, name=None, lo=None, hi=None):
     """(count, rows): GFF records with seqname == name and lo <= start <= hi (None drops a term)."""
     a = _buf(data)

@@ -317,3 +317,86 @@ int64_t exo_gff_filter_count(const uint8_t *text, int64_t len, const uint8_t *na
     if (n_rows) *n_rows = rows;
     return count;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * FASTA records -> {id, description, sequence}.  exon-fasta/src/batch_reader.rs:52-103 (`read_definition` +
+ * `read_sequence` of the noodles-fasta 0.4x reader, un-vendored) and FASTAArrayBuilder::append,
+ * exon-fasta/src/array_builder.rs:108-160, through noodles `Definition::from_str`: '>' prefix, name = up to the first ASCII
+ * whitespace (required), description = the rest of the line trimmed (None when the line has no whitespace); the sequence is
+ * every following line up to the next definition, line terminators ("\n" / "\r\n") removed.  Errors: first line not a
+ * definition, empty name, a definition with no sequence line ("invalid sequence", batch_reader.rs:63-65).
+ * Pinned by slt/fasta-scan-tests.slt:6-10 (`a description ATCG`, `b description2 ATCG`).
+ * Flat output, all malloc'ed: per record name_len / desc_len (-1 = NULL) / seq_len, and the three byte streams.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t rows;
+    int32_t *name_len, *desc_len;
+    int64_t *seq_len;
+    uint8_t *names, *descs, *seqs;
+    int64_t names_len, descs_len, seqs_len;
+    int32_t err;
+} exo_fasta_records;
+
+static int fa_ascii_ws(uint8_t c) { return c == ' ' || c == '\t' || c == '\n' || c == 0x0C || c == '\r'; }
+static int fa_trim_ws(uint8_t c) { return fa_ascii_ws(c) || c == 0x0B; }
+
+void exo_fasta_records_free(exo_fasta_records *r) {
+    if (!r) return;
+    free(r->name_len); free(r->desc_len); free(r->seq_len);
+    free(r->names); free(r->descs); free(r->seqs);
+    free(r);
+}
+
+exo_fasta_records *exo_fasta_read(const uint8_t *text, int64_t len) {
+    exo_fasta_records *r = (exo_fasta_records *)calloc(1, sizeof(*r));
+    int64_t cap = 0, ncap = 0, dcap = 0, scap = 0, p = 0;
+    int in_record = 0, seq_lines = 0;
+    while (p < len) {
+        const uint8_t *nl = (const uint8_t *)memchr(text + p, '\n', (size_t)(len - p));
+        const uint8_t *s = text + p, *e = nl ? nl : text + len;
+        p = (nl ? nl - text : len) + 1;
+        if (e > s && e[-1] == '\r') e--;
+        if (e > s && s[0] == '>') {
+            if (in_record && !seq_lines) { r->err = 3; return r; }
+            if (r->rows == cap) {
+                cap = cap ? cap * 2 : 1024;
+                r->name_len = (int32_t *)realloc(r->name_len, sizeof(int32_t) * (size_t)cap);
+                r->desc_len = (int32_t *)realloc(r->desc_len, sizeof(int32_t) * (size_t)cap);
+                r->seq_len = (int64_t *)realloc(r->seq_len, sizeof(int64_t) * (size_t)cap);
+            }
+            const uint8_t *q = s + 1;
+            while (q < e && !fa_ascii_ws(*q)) q++;
+            const int32_t nlen = (int32_t)(q - (s + 1));
+            if (nlen == 0) { r->err = 2; return r; }
+            if (r->names_len + nlen > ncap) { while (r->names_len + nlen > ncap) ncap = ncap ? ncap * 2 : 4096; r->names = (uint8_t *)realloc(r->names, (size_t)ncap); }
+            memcpy(r->names + r->names_len, s + 1, (size_t)nlen);
+            r->names_len += nlen;
+            r->name_len[r->rows] = nlen;
+            r->desc_len[r->rows] = -1;
+            if (q < e) {
+                const uint8_t *a = q + 1, *b = e;
+                while (a < b && fa_trim_ws(*a)) a++;
+                while (b > a && fa_trim_ws(b[-1])) b--;
+                const int32_t dlen = (int32_t)(b - a);
+                if (r->descs_len + dlen > dcap) { while (r->descs_len + dlen > dcap) dcap = dcap ? dcap * 2 : 4096; r->descs = (uint8_t *)realloc(r->descs, (size_t)dcap); }
+                if (dlen) memcpy(r->descs + r->descs_len, a, (size_t)dlen);
+                r->descs_len += dlen;
+                r->desc_len[r->rows] = dlen;
+            }
+            r->seq_len[r->rows] = 0;
+            r->rows++;
+            in_record = 1;
+            seq_lines = 0;
+        } else {
+            if (!in_record) { r->err = 1; return r; }
+            const int64_t n = e - s;
+            if (r->seqs_len + n > scap) { while (r->seqs_len + n > scap) scap = scap ? scap * 2 : 65536; r->seqs = (uint8_t *)realloc(r->seqs, (size_t)scap); }
+            if (n) memcpy(r->seqs + r->seqs_len, s, (size_t)n);
+            r->seqs_len += n;
+            r->seq_len[r->rows - 1] += n;
+            seq_lines++;
+        }
+    }
+    if (in_record && !seq_lines) r->err = 3;
+    return r;
+}
