@@ -33,7 +33,7 @@ SYMBOLS = [
     "exon_gpu_bam_filter_count_by_reference", "exon_gpu_bam_open_columns", "exon_gpu_bam_next_batch", "exon_gpu_bam_group_name", "exon_gpu_allreduce_counts",
     "exon_gpu_mzml_open", "exon_gpu_mzml_feed", "exon_gpu_mzml_filter_sum", "exon_gpu_tabix_query", "exon_gpu_stream_feed_bgzf_chunk",
     "exon_gpu_fasta_open", "exon_gpu_fasta_feed", "exon_gpu_fasta_rows", "exon_gpu_fasta_open_columns", "exon_gpu_fasta_next_batch", "exon_gpu_gff_open", "exon_gpu_gff_feed",
-    "exon_gpu_gff_filter_count",
+    "exon_gpu_gff_filter_count", "exon_gpu_gff_open_columns", "exon_gpu_gff_next_batch",
 ]
 
 
@@ -167,6 +167,8 @@ def load():
         "exon_gpu_gzip_inflate": [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)],
         "exon_gpu_fasta_open_columns": [vp, C.POINTER(FastqOpts), C.POINTER(vp)],
         "exon_gpu_fasta_next_batch": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)],
+        "exon_gpu_gff_open_columns": [vp, C.POINTER(FastqOpts), C.POINTER(vp)],
+        "exon_gpu_gff_next_batch": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)],
         "exon_gpu_bam_open": [vp, C.POINTER(vp)],
         "exon_gpu_bam_open_columns": [vp, C.POINTER(FastqOpts), C.POINTER(vp)],  # exon_gpu_bam_opts has the layout of exon_gpu_fastq_opts
         "exon_gpu_bam_next_batch": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)],

@@ -122,8 +122,8 @@ class Context:
         check(self.lib.exon_gpu_tabix_query(self.handle, C.c_void_p(tbi.ctypes.data), tbi.size, C.byref(region), out, n.value, C.byref(n)))
         return [(int(out[i].start), int(out[i].end)) for i in range(n.value)]
 
-    def open_gff(self) -> "GffStream":
-        return GffStream(self)
+    def open_gff(self, **kw) -> "GffStream":
+        return GffStream(self, **kw)
 
     def open_fasta(self, **kw) -> "FastaStream":
         return FastaStream(self, **kw)
@@ -658,11 +658,26 @@ class FastaStream(MzmlStream):
 class GffStream(FastaStream):
     """exon_gpu_stream opened with exon_gpu_gff_open: COUNT(*) / gff_region_filter counts of GFF records."""
 
-    def __init__(self, ctx: Context):
+    def __init__(self, ctx: Context, *, projection=None, columns_on_device: bool = False):
         self.ctx = ctx
         self.lib = ctx.lib
         self.handle = C.c_void_p()
-        check(self.lib.exon_gpu_gff_open(ctx.handle, C.byref(self.handle)))
+        self.columns_on_device = columns_on_device
+        if projection is None:
+            check(self.lib.exon_gpu_gff_open(ctx.handle, C.byref(self.handle)))
+        else:
+            self._proj = (C.c_int32 * max(len(projection), 1))(*projection)
+            opts = _abi.FastqOpts(0, len(projection), self._proj, int(columns_on_device))
+            check(self.lib.exon_gpu_gff_open_columns(ctx.handle, C.byref(opts), C.byref(self.handle)))
+
+    def next_batch(self):
+        arr, sch = _abi.ArrowArray(), _abi.ArrowSchema()
+        check(self.lib.exon_gpu_gff_next_batch(self.handle, C.byref(arr), C.byref(sch)))
+        if not arr.release:
+            if sch.release:
+                sch.release(C.byref(sch))
+            return None
+        return VcfBatch(arr, sch, self.columns_on_device)
 
     def feed(self, data, *, is_last: bool = True, device_ptr: int | None = None, nbytes: int | None = None):
         if device_ptr is not None:

@@ -276,6 +276,16 @@ int exon_gpu_fasta_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct
 int exon_gpu_gff_open(exon_gpu_ctx *ctx, exon_gpu_stream **out);
 int exon_gpu_gff_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int is_device_ptr, int is_last);
 int exon_gpu_gff_filter_count(exon_gpu_stream *s, const exon_gpu_region *region, int64_t *out_count);
+/* Columns out: BatchReader::read_batch + GFFArrayBuilder::{append, finish} (exon/exon-gff/src/batch_reader.rs:99-130,
+ * exon/exon-gff/src/array_builder.rs:84-200; schema exon/exon-gff/src/config.rs:81-108), columns 0..7:
+ *   0 seqname utf8 | 1 source utf8 | 2 type utf8 | 3 start int64 | 4 end int64 | 5 score float32 ("." -> NULL, else Rust
+ *   f32::from_str) | 6 strand utf8 ("+" / "-") | 7 phase utf8 ("." -> NULL, else "0" / "1" / "2")
+ * Like the reference, ONE batch per file whatever batch_rows says (read_batch has no row limit).  A strand of "." or "?" is
+ * NULL in a column the reference declares non-nullable -- its batch construction fails, and so does this call
+ * (EXON_GPU_ERR_PARSE) -- as do an empty line, fewer than 9 fields, a start / end of 0.  Column 8 (attributes) is not built
+ * (EXON_GPU_ERR_UNSUPPORTED).  exon_gpu_fastq_opts carries the projection. */
+int exon_gpu_gff_open_columns(exon_gpu_ctx *ctx, const exon_gpu_fastq_opts *opts, exon_gpu_stream **out);
+int exon_gpu_gff_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 
 /* ---- BAM partition stream (BASELINE configs[3]) ---------------------------------------- */
 /* BAMScan::execute + BAMOpener::open + BatchReader (exon/exon-core/src/datasources/bam/scanner.rs:138,

@@ -359,6 +359,22 @@ def filter_count_gz_files(datas, chrom=None, lo=None, hi=None, target_partitions
     return int(c), int(rows.value)
 
 
+def gunzip_all(data) -> np.ndarray:
+    """Every member of a gzip / BGZF file inflated with zlib in C (exo_gunzip_all): the CPU arm's decompression step."""
+    a = _buf(data)
+    L = lib()
+    L.exo_gunzip_all.restype = C.c_void_p
+    L.exo_gunzip_all.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    n = C.c_int64()
+    p = L.exo_gunzip_all(a.ctypes.data, a.size, C.byref(n))
+    if not p:
+        raise ValueError("corrupt gzip stream")
+    try:
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (max(n.value, 1),))[: n.value].copy()
+    finally:
+        C.CDLL(None).free(C.c_void_p(p))
+
+
 # ---- BAM (oracle/bam_oracle.c) -------------------------------------------------------------------------------
 
 class BamRow(C.Structure):
@@ -540,3 +556,27 @@ def gff_filter_count(data, name=None, lo=None, hi=None):
     if c < 0:
         raise ValueError("malformed GFF record")
     return int(c), int(rows.value)
+
+
+class GffRow(C.Structure):
+    _fields_ = [("seqname", C.c_char * 256), ("source", C.c_char * 256), ("type", C.c_char * 256), ("start", C.c_int64), ("end", C.c_int64),
+                ("score", C.c_float), ("score_valid", C.c_int32), ("strand", C.c_char * 4), ("phase", C.c_char * 4)]
+
+
+def gff_rows(data, limit=None):
+    """[(seqname, source, type, start, end, score f32 bits | None, strand, phase | None)] of one GFF text (columns 0..7)."""
+    a = _buf(data)
+    L = _fq()
+    L.exo_gff_row_at.restype = C.c_int32
+    L.exo_gff_row_at.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(GffRow)]
+    out, r, i = [], GffRow(), 0
+    while limit is None or i < limit:
+        rc = L.exo_gff_row_at(a.ctypes.data, a.size, i, C.byref(r))
+        if rc < 0:
+            raise ValueError("malformed GFF")
+        if rc == 0:
+            break
+        bits = int(np.array([r.score], np.float32).view(np.uint32)[0]) if r.score_valid else None
+        out.append((r.seqname, r.source, r.type, r.start, r.end, bits, r.strand, r.phase or None))
+        i += 1
+    return out

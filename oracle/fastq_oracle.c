@@ -400,3 +400,64 @@ exo_fasta_records *exo_fasta_read(const uint8_t *text, int64_t len) {
     if (in_record && !seq_lines) r->err = 3;
     return r;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * GFF records -> columns 0..7.  GFFArrayBuilder::append, exon-gff/src/array_builder.rs:84-150 over noodles-gff lazy records
+ * (un-vendored): seqname / source / type as text; start / end decimal, non-zero; score "." -> NULL else f32 (Rust grammar is
+ * checked by the caller's data; strtof here); strand "+" / "-" (anything else: error -- "." and "?" become NULL in a
+ * non-nullable column and the reference's batch construction fails); phase "." -> NULL else "0" / "1" / "2".
+ * Pinned by slt/gff-scan-tests.slt:6-10 (`sq0 caat 8 13 NULL + NULL`).  One record per call: fields of record `row`
+ * (0-based, comments and directives skipped).  Returns 1, 0 when the row does not exist, < 0 on a malformed file.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    char seqname[256], source[256], type[256];
+    int64_t start, end;
+    float score;
+    int32_t score_valid;
+    char strand[4], phase[4]; /* phase "" = NULL */
+} exo_gff_row;
+
+int32_t exo_gff_row_at(const uint8_t *text, int64_t len, int64_t row, exo_gff_row *out) {
+    int64_t p = 0, rows = 0;
+    while (p < len) {
+        const uint8_t *nl = (const uint8_t *)memchr(text + p, '\n', (size_t)(len - p));
+        const int64_t e = nl ? nl - text : len;
+        const uint8_t *s = text + p;
+        const int64_t n = e - p;
+        p = e + 1;
+        if (n == 0) return EXO_ERR_PARSE;
+        if (s[0] == '#') continue;
+        const uint8_t *f[10];
+        int nf = 0;
+        f[nf++] = s;
+        for (int64_t i = 0; i < n && nf < 10; i++)
+            if (s[i] == '\t') f[nf++] = s + i + 1;
+        if (nf < 9) return EXO_ERR_PARSE;
+        if (nf == 9) f[9] = s + n + 1;
+        if (rows++ != row) continue;
+        memset(out, 0, sizeof(*out));
+#define GFLD(k, dst) do { size_t l = (size_t)(f[(k) + 1] - f[(k)] - 1); if (l >= sizeof(dst)) return EXO_ERR_PARSE; memcpy(dst, f[(k)], l); dst[l] = 0; } while (0)
+        GFLD(0, out->seqname);
+        GFLD(1, out->source);
+        GFLD(2, out->type);
+        char num[64];
+        GFLD(3, num);
+        out->start = strtoll(num, NULL, 10);
+        GFLD(4, num);
+        out->end = strtoll(num, NULL, 10);
+        if (out->start <= 0 || out->end <= 0) return EXO_ERR_PARSE;
+        GFLD(5, num);
+        out->score_valid = strcmp(num, ".") != 0;
+        out->score = out->score_valid ? strtof(num, NULL) : 0.0f;
+        GFLD(6, out->strand);
+        if (strcmp(out->strand, "+") != 0 && strcmp(out->strand, "-") != 0) return EXO_ERR_PARSE;
+        char ph[8];
+        GFLD(7, ph);
+        if (strcmp(ph, ".") == 0) out->phase[0] = 0;
+        else if (!strcmp(ph, "0") || !strcmp(ph, "1") || !strcmp(ph, "2")) strcpy(out->phase, ph);
+        else return EXO_ERR_PARSE;
+#undef GFLD
+        return 1;
+    }
+    return 0;
+}

@@ -69,3 +69,83 @@ def test_gpu_counts(gpu_ctx):
         assert s.rows() == 1                                    # COUNT(*) does not read START
         with pytest.raises(ExonGpuError):
             s.filter_count(make_region("chr1", 1, 10))
+
+
+# ---- record batches, columns 0..7 ---------------------------------------------------------------------------------------
+
+def test_oracle_row_golden():
+    t = fixture()
+    # slt/gff-scan-tests.slt:6-10: seqname, source, start, end, score, strand, phase = sq0 caat 8 13 NULL + NULL
+    r = oracle.gff_rows(t, 1)[0]
+    assert (r[0], r[1], r[3], r[4], r[5], r[6], r[7]) == (b"sq0", b"caat", 8, 13, None, b"+", None)
+
+
+def synth_gff(rng, n):
+    scores = [".", "0", "50", "0.95", "1e-5", "12.5", "3.4028235677973366e38"]
+    lines = ["##gff-version 3"]
+    for i in range(n):
+        if i % 97 == 5:
+            lines.append("# a comment")
+        s = int(rng.integers(1, 10 ** 6))
+        lines.append("\t".join(["sq%d" % (i % 7), ["caat", "x", "ensembl havana"][i % 3], ["gene", "exon", "CDS"][i % 3], str(s), str(s + int(rng.integers(0, 5000))),
+                                scores[i % len(scores)], "+-"[i % 2], ".012"[i % 4], "ID=g%d;Name=n%d,m%d" % (i, i, i)]))
+    return ("\n".join(lines) + "\n").encode()
+
+
+def gpu_rows(ctx, files, projection=tuple(range(8)), gz=False):
+    names = ["seqname", "source", "type", "start", "end", "score", "strand", "phase"]
+    rows, sizes = [], []
+    with ctx.open_gff(projection=projection) as s:
+        for f in files:
+            (s.feed_gzip if gz else s.feed)(f)
+        while True:
+            b = s.next_batch()
+            if b is None:
+                break
+            rb = b.to_pyarrow()
+            assert rb.schema.names == [names[p] for p in projection]
+            sizes.append(rb.num_rows)
+            cols = []
+            for p in projection:
+                col = rb.column(names[p])
+                if p == 5:
+                    bits = col.to_numpy(zero_copy_only=False).astype(np.float32).view(np.uint32)
+                    cols.append([int(v) if ok else None for v, ok in zip(bits, np.asarray(col.is_valid()))])
+                elif p in (3, 4):
+                    cols.append(col.to_pylist())
+                else:
+                    cols.append([None if x is None else x.encode() for x in col.to_pylist()])
+            rows += list(zip(*cols))
+    return rows, sizes
+
+
+@pytest.mark.gpu
+def test_gpu_record_batches(gpu_ctx):
+    from exon_b200 import _abi
+    from exon_b200._abi import ExonGpuError
+
+    t = fixture()
+    rows, sizes = gpu_rows(gpu_ctx, [t])
+    assert sizes == [5000]                                  # ONE batch per file: read_batch has no row limit
+    assert rows[0] == (b"sq0", b"caat", b"gene", 8, 13, None, b"+", None)   # the slt row
+    assert rows[:300] == oracle.gff_rows(t, 300)
+    rng = np.random.default_rng(3)
+    files = [synth_gff(rng, 1500), synth_gff(rng, 3), b"##only directives\n# and comments\n", synth_gff(rng, 400)]
+    want = [r for f in files for r in oracle.gff_rows(f)]
+    rows, sizes = gpu_rows(gpu_ctx, files)
+    assert sizes == [1500, 3, 400] and rows == want
+    rows, sizes = gpu_rows(gpu_ctx, [gzip.compress(f) for f in files], gz=True)
+    assert sizes == [1500, 3, 400] and rows == want
+    for projection in ((5, 0), (7, 6, 3), (1,), (4, 2)):
+        rows, _ = gpu_rows(gpu_ctx, files, projection)
+        assert rows == [tuple(r[p] for p in projection) for r in want]
+    ok_line = "sq0\tcaat\tgene\t8\t13\t.\t+\t.\tID=a\n"
+    for bad, proj in ((ok_line.replace("\t+\t", "\t.\t"), (6,)), (ok_line.replace("\t8\t", "\t0\t"), (3,)), (ok_line.replace("\t.\t+", "\tx\t+"), (5,)),
+                      ("sq0\tcaat\tgene\t8\t13\t.\t+\t.\n", (0,)), (ok_line + "\n" + ok_line, (0,)), (ok_line.replace("+\t.", "+\t3"), (7,))):
+        with pytest.raises(ExonGpuError) as e:
+            gpu_rows(gpu_ctx, [bad.encode()], proj)
+        assert e.value.code == _abi.ERR_PARSE, bad
+    assert gpu_rows(gpu_ctx, [ok_line.replace("\t+\t", "\t.\t").encode()], (0, 3))[0] == [(b"sq0", 8)]   # strand not projected: not read
+    with pytest.raises(ExonGpuError) as e:
+        gpu_ctx.open_gff(projection=(8,))
+    assert e.value.code == _abi.ERR_UNSUPPORTED

@@ -98,6 +98,48 @@ def bench_fastq(args):
             "cpu_baseline": {"value": c_rows / cpu_s, "unit": "reads/s", "cores": cores, "kind": "port",
                              "sample": f"{n_cpu} of {len(sh.files)} files ({c_rows} reads), one worker per file"},
             "count": cnt, "count_matches_truth": True, "gen_seconds": gen_s}
+    if args.gz:
+        # the same reads as BGZF files (.fastq.gz is how FASTQ is stored; the reference's tests read gzip and bgzip twins,
+        # slt/fastq-scan-test.slt:60-69): compressed bytes in pinned host memory -> H2D -> device inflate -> fused scan, next
+        # to the CPU arm that has to inflate too (zlib + oracle, one worker per file)
+        from concurrent.futures import ThreadPoolExecutor
+
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from bgzf_util import bgzf_compress
+
+        with ThreadPoolExecutor(max_workers=os.cpu_count()) as ex:
+            gz = list(ex.map(lambda f: bgzf_compress(f.tobytes(), args.level), sh.files))
+        gpins = []
+        for g in gz:
+            p = ctx.pinned(len(g))
+            p.array[:] = np.frombuffer(g, dtype=np.uint8)
+            gpins.append(p)
+        comp = int(sum(len(g) for g in gz))
+        gz_s = ctx.open_fastq()
+
+        def e2e_gz():
+            gz_s.reset()
+            for p in gpins:
+                gz_s.feed_gzip(p.array)
+            return gz_s.filter_count(30)
+
+        g_ms, _, gcnt, _ = timed(ctx, tstream, e2e_gz, max(3, args.steps // 4), 2)
+        assert gcnt == truth
+
+        def cpu_one(g):
+            return oracle.fastq_filter_count(oracle.gunzip_all(g), 30)
+
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            rs = list(ex.map(cpu_one, gz[:n_cpu]))
+        gcpu_s = time.perf_counter() - t0
+        line["bgzf_files"] = {"e2e": {"value": sh.n / g_ms * 1e3, "unit": "reads/s", "ms_per_step": g_ms, "h2d_bytes_per_step": comp, "d2h_bytes_per_step": 24},
+                              "compressed_bytes": comp, "zlib_level": args.level,
+                              "cpu_baseline": {"value": sum(r[1] for r in rs) / gcpu_s, "unit": "reads/s", "cores": cores, "kind": "port",
+                                               "sample": f"{n_cpu} of {len(gz)} files: zlib inflate + oracle, one worker per file"}}
+        gz_s.close()
+        for p in gpins:
+            p.free()
     res.close()
     e2e_s.close()
     for d in dbufs:
@@ -360,5 +402,6 @@ if __name__ == "__main__":
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--shards", type=int, default=32)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--gz", action="store_true", help="fastq: also the BGZF-compressed variant of the workload")
     a = ap.parse_args()
     {"fastq": bench_fastq, "vcfgz": bench_vcfgz, "bam": bench_bam, "mzml": bench_mzml}[a.fmt](a)
