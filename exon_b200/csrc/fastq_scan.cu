@@ -237,12 +237,19 @@ __global__ void __launch_bounds__(FqRing::WARPS * 32, EXON_FQ_MINB) fq_filter_ke
             qn = q ? 1 : 0;
             line += 1;
         }
+        // 32 bytes per lane and step: the ballots, the rank arithmetic and the (divergent) per-line-start work below are paid
+        // once per KiB instead of once per 512 bytes
 #pragma unroll 1
-        for (int u = 0; u < kFqU; ++u) {
-            const int c0 = (u * 32 + lane) * 16;
+        for (int u = 0; u < kFqU / 2; ++u) {
+            const int c0 = (u * 32 + lane) * 32;
             uint32_t m = 0;
             if (v.interior || c0 < v.sm_hi) m = newline_mask16(lds128(v.sa + (uint32_t)c0));
-            if (!v.interior) m = clip_mask16(m, c0, v.seg_lo, v.hi);
+            if (v.interior || c0 + 16 < v.sm_hi) m |= newline_mask16(lds128(v.sa + (uint32_t)c0 + 16u)) << 16;
+            if (!v.interior) {  // '\n' at tile index p starts a line iff p >= seg_lo and p + 1 < hi
+                const int j_lo = v.seg_lo - c0 > 0 ? v.seg_lo - c0 : 0;
+                const int j_hi = v.hi - 1 - c0 < 32 ? v.hi - 1 - c0 : 32;
+                m = (j_hi > j_lo) ? (m & (j_hi >= 32 ? 0xFFFFFFFFu : (1u << j_hi) - 1u) & ~((1u << j_lo) - 1u)) : 0u;
+            }
             const uint32_t n = (uint32_t)__popc(m);
             const uint32_t b1 = __ballot_sync(0xFFFFFFFFu, n >= 1u), b2 = __ballot_sync(0xFFFFFFFFu, n >= 2u);
             if (b1 == 0u) continue;
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(FqRing::WARPS * 32, EXON_FQ_MINB) fq_filter_ke
             if (my_q >= 0) sts16(queue_sa + 2u * (uint32_t)(qn + __popc(bq & lt_mask)), (uint32_t)my_q);
             qn += __popc(bq);
             if (__ballot_sync(0xFFFFFFFFu, extra_q > 0) != 0u) {
-                // >= 2 quality lines start inside one 16-byte chunk (records shorter than 16 bytes): those beyond the
+                // >= 2 quality lines start inside one 32-byte chunk (records shorter than 32 bytes): those beyond the
                 // first are summed right here by their lane
                 uint32_t m2 = m, i2 = line + before;
                 bool seen = false;
