@@ -23,7 +23,7 @@ SYMBOLS = [
     "exon_gpu_ctx_launch_count", "exon_gpu_ctx_last_kernel_ms", "exon_gpu_ctx_synchronize", "exon_gpu_host_alloc",
     "exon_gpu_host_free", "exon_gpu_device_alloc", "exon_gpu_device_free", "exon_gpu_memcpy_h2d",
     "exon_gpu_region_parse", "exon_gpu_interval_parse", "exon_gpu_parse_f32", "exon_gpu_regroup_files_by_size", "exon_gpu_vcf_open",
-    "exon_gpu_vcf_close", "exon_gpu_vcf_reset", "exon_gpu_vcf_feed", "exon_gpu_vcf_next_batch",
+    "exon_gpu_vcf_close", "exon_gpu_vcf_reset", "exon_gpu_vcf_set_header", "exon_gpu_vcf_feed", "exon_gpu_vcf_next_batch",
     "exon_gpu_vcf_filter_count", "exon_gpu_vcf_filter_count_async", "exon_gpu_vcf_rows", "exon_gpu_vcf_body_bytes",
     "exon_gpu_filter_agg", "exon_gpu_nccl_unique_id", "exon_gpu_nccl_init", "exon_gpu_allreduce_partial",
     "exon_gpu_vcf_filter_count_global", "exon_gpu_filter_agg_accumulate", "exon_gpu_partial_read", "exon_gpu_memset",
@@ -169,6 +169,7 @@ def load():
         "exon_gpu_fasta_next_batch": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)],
         "exon_gpu_gff_open_columns": [vp, C.POINTER(FastqOpts), C.POINTER(vp)],
         "exon_gpu_gff_next_batch": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)],
+        "exon_gpu_vcf_set_header": [vp, C.c_char_p, C.c_size_t],
         "exon_gpu_bam_open": [vp, C.POINTER(vp)],
         "exon_gpu_bam_open_columns": [vp, C.POINTER(FastqOpts), C.POINTER(vp)],  # exon_gpu_bam_opts has the layout of exon_gpu_fastq_opts
         "exon_gpu_bam_next_batch": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)],

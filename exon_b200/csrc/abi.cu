@@ -224,12 +224,11 @@ int exon_gpu_vcf_open(exon_gpu_ctx *c, const exon_gpu_vcf_opts *o, exon_gpu_stre
                 return fail(EXON_GPU_ERR_ARG, "vcf_open: projection index %d is not a VCF file-schema column",
                             o->projection[i]);
             }
-            if (o->projection[i] > 6) {
+            if (o->projection[i] > 7) {
                 delete s;
                 return fail(EXON_GPU_ERR_UNSUPPORTED,
-                            "vcf_open: column %d (%s) is re-serialised by the reference builder and is not built on the GPU yet "
-                            "(supported: 0 chrom, 1 pos, 2 id, 3 ref, 4 alt, 5 qual, 6 filter)",
-                            o->projection[i], o->projection[i] == 7 ? "info" : "formats");
+                            "vcf_open: column 8 (formats) is re-serialised by the reference builder and is not built on the GPU yet "
+                            "(supported: 0 chrom, 1 pos, 2 id, 3 ref, 4 alt, 5 qual, 6 filter, 7 info)");
             }
             for (int j = 0; j < i; ++j)
                 if (o->projection[j] == o->projection[i]) {
@@ -283,6 +282,49 @@ int exon_gpu_vcf_reset(exon_gpu_stream *s) {
     CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
     s->release_all();
     CUDA_TRY(cudaMemsetAsync(s->d_res, 0, 8 * sizeof(unsigned long long), s->ctx->stream));
+    return EXON_GPU_OK;
+}
+
+// The header's ##INFO definitions, as the reference's builder gets them from the noodles Header the opener parsed
+// (VCFOpener::open, exon/exon-core/src/datasources/vcf/file_opener/unindex_file_opener.rs:74-88; LazyVCFArrayBuilder::create,
+// exon/exon-vcf/src/array_builder/lazy_array_builder.rs:70-75).  Only ID and Type are needed.
+int exon_gpu_vcf_set_header(exon_gpu_stream *s, const char *text, size_t len) {
+    if (!s || (!text && len)) return fail(EXON_GPU_ERR_ARG, "vcf_set_header: NULL argument");
+    InfoDefs defs;
+    const char *p = text, *end = text + len;
+    while (p < end) {
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+        const char *le = nl ? nl : end;
+        if (le - p > 8 && memcmp(p, "##INFO=<", 8) == 0) {
+            auto field = [&](const char *key, std::string *out) {
+                const size_t kl = strlen(key);
+                for (const char *q = p + 8; q + kl <= le; ++q) {
+                    if ((q == p + 8 || q[-1] == ',') && memcmp(q, key, kl) == 0) {
+                        const char *v = q + kl, *ve = v;
+                        while (ve < le && *ve != ',' && *ve != '>') ++ve;
+                        out->assign(v, (size_t)(ve - v));
+                        return true;
+                    }
+                    if (*q == '"') {  // quoted text (Description) may hold commas
+                        ++q;
+                        while (q < le && *q != '"') ++q;
+                    }
+                }
+                return false;
+            };
+            std::string id, type;
+            if (!field("ID=", &id) || !field("Type=", &type) || id.empty())
+                return fail(EXON_GPU_ERR_PARSE, "vcf_set_header: an ##INFO line without ID / Type");
+            int t = type == "Integer" ? 0 : type == "Float" ? 1 : type == "Flag" ? 2 : type == "Character" ? 3 : type == "String" ? 4 : -1;
+            if (t < 0) return fail(EXON_GPU_ERR_PARSE, "vcf_set_header: unknown INFO type '%s'", type.c_str());
+            defs.ids.push_back(id);
+            defs.types.push_back((uint8_t)t);
+        }
+        if (!nl) break;
+        p = nl + 1;
+    }
+    defs.set = true;
+    s->info_defs = std::move(defs);
     return EXON_GPU_OK;
 }
 

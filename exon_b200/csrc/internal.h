@@ -88,6 +88,13 @@ struct Piece {
     bool starts_file;
 };
 
+// INFO definitions of a VCF header (##INFO=<ID=..,Number=..,Type=..>): what the reference's builder takes from noodles' Header
+struct InfoDefs {
+    std::vector<std::string> ids;
+    std::vector<uint8_t> types;  // 0 Integer, 1 Float, 2 Flag, 3 Character, 4 String
+    bool set = false;
+};
+
 enum StreamFormat { kFmtVcf = 0, kFmtFastq = 1, kFmtBam = 2, kFmtMzml = 3, kFmtFasta = 4, kFmtGff = 5 };
 
 struct VcfStream {
@@ -98,6 +105,7 @@ struct VcfStream {
     bool columns_on_device = false, strict = false, has_pushdown = false, drained = false;
     int variant = 0;
     OwnedRegion pushdown;
+    InfoDefs info_defs;  // exon_gpu_vcf_set_header
 
     // ---- file framing state (what read_header + the line reader keep between feeds) ----
     enum HdrState { kAtLineStart, kInHeaderLine, kBody };

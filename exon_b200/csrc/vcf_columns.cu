@@ -523,9 +523,9 @@ void release_schema(ArrowSchema *s) {
 // VCFSchemaBuilder (exon/exon-core/src/datasources/vcf/schema_builder.rs:85-129): chrom Utf8 !null, pos Int64 !null,
 // id List<item: Utf8>, ref Utf8 !null, alt List<item: Utf8>, qual Float32, filter List<item: Utf8>
 void fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
-    static const char *names[7] = {"chrom", "pos", "id", "ref", "alt", "qual", "filter"};
-    static const char *formats[7] = {"u", "l", "+l", "u", "+l", "f", "+l"};
-    static const bool nullable[7] = {false, false, true, false, true, true, true};
+    static const char *names[8] = {"chrom", "pos", "id", "ref", "alt", "qual", "filter", "info"};
+    static const char *formats[8] = {"u", "l", "+l", "u", "+l", "f", "+l", "u"};
+    static const bool nullable[8] = {false, false, true, false, true, true, true, true};
     auto *p = new SchemaPriv();
     p->n_children = (int)projection.size();
     for (int i = 0; i < p->n_children; ++i) {

@@ -7,6 +7,7 @@
 //   alt     "." -> NULL, else a VALID BUT EMPTY list: the builder never appends the alleles            (:190-204)
 //   qual    "." -> NULL, else Rust `f32::from_str`, correctly rounded (f32_parse.cuh)                  (:205-208)
 //   filter  always valid: "." -> [], else one item per ';'-separated filter                            (:209-216)
+//   info    (string mode) the field re-serialised: equal to its text plus "=true" after every flag, see info_walk      (:217-298)
 // Columns 0 / 1 stay with K2 (vcf_columns.cu), whose batch table (batches restart at every file) this build shares.
 //
 // Row-parallel, on top of the partition's line index (build_line_index, fastq_scan.cu):
@@ -43,8 +44,11 @@ constexpr uint32_t kWErrFields = 1u;       // fewer than 8 tab-separated fields
 constexpr uint32_t kWErrQual = 2u;         // QUAL is not a float literal
 constexpr uint32_t kWErrQualDigits = 4u;   // QUAL has more than 36 significant digits
 constexpr uint32_t kWErrFieldLen = 8u;     // a line of 2 GiB or more
+constexpr uint32_t kWErrInfoValue = 16u;   // INFO: a non-flag key without a value (the reference unwraps a None there)
+constexpr uint32_t kWErrInfoKey = 32u;     // INFO: a key the header does not define
+constexpr uint32_t kWErrInfoForm = 64u;    // INFO: a value whose re-serialisation by the reference would differ from its text
 
-enum { kIdE = 0, kIdB = 1, kRefB = 2, kFiE = 3, kFiB = 4, kNScan = 5 };
+enum { kIdE = 0, kIdB = 1, kRefB = 2, kFiE = 3, kFiB = 4, kInfoB = 5, kNScan = 6 };
 
 struct WideArgs {
     int64_t n_rows;
@@ -53,7 +57,14 @@ struct WideArgs {
     const long long *brow;  // n_batches + 1
     int64_t n_batches;
     int32_t batch_rows, wpb;
-    int32_t want_id, want_ref, want_alt, want_qual, want_filter;
+    int32_t want_id, want_ref, want_alt, want_qual, want_filter, want_info;
+    // INFO definitions of the header (exon_gpu_vcf_set_header): FNV-1a hash, offset / length into the blob, type
+    const uint32_t *info_hash;
+    const int32_t *info_off, *info_len;
+    const uint8_t *info_type, *info_blob;
+    int32_t n_info;
+    int32_t *info_offs;  // batch-relative offsets, n_batches * (batch_rows + 1)
+    uint8_t *info_val;
     int32_t *cnt[kNScan];          // measure out, n_rows + 1 entries (the last one 0); NULL when not wanted
     const long long *pre[kNScan];  // emit in: exclusive scans of cnt
     uint8_t *rowflags;             // measure out: bit0 id valid, bit1 alt valid, bit2 qual valid
@@ -103,13 +114,165 @@ __device__ __forceinline__ void count_items(const uint8_t *f, int32_t n, int32_t
     bytes = n - semi;
 }
 
+
+// ---- INFO (column 7, string mode) ---------------------------------------------------------------------------------------
+// LazyVCFArrayBuilder::append :217-298 does not copy the field: it walks noodles' typed view of it (types from the header's
+// ##INFO lines) and prints every entry again -- `key=value` joined by ';', flags as `key=true`, numbers through Rust's
+// Display.  The text that comes out equals the text that went in, plus "=true" after every flag, PROVIDED every number is
+// already in the form Display would give it.  That is checked here entry by entry; a value for which it does not hold (an
+// exponent, trailing zeros, more than 6 significant digits in a fraction, '%' escapes in a string ...), a key the header
+// does not define and a flag with a value are refused (EXON_GPU_ERR_UNSUPPORTED) instead of being approximated.
+enum : uint8_t { kInfoInteger = 0, kInfoFloat = 1, kInfoFlag = 2, kInfoCharacter = 3, kInfoString = 4 };
+
+__device__ __forceinline__ uint32_t fnv1a(const uint8_t *p, int n) {
+    uint32_t h = 2166136261u;
+    for (int i = 0; i < n; ++i) h = (h ^ __ldg(p + i)) * 16777619u;
+    return h;
+}
+
+// -?(0|[1-9][0-9]*) within i32; "." is a missing element
+__device__ __forceinline__ bool canon_int(const uint8_t *p, int n) {
+    if (n == 1 && __ldg(p) == '.') return true;
+    int i = 0;
+    const bool neg = n > 0 && __ldg(p) == '-';
+    if (neg) i = 1;
+    const int nd = n - i;
+    if (nd < 1 || nd > 10) return false;
+    if (__ldg(p + i) == '0') return nd == 1 && !neg;
+    unsigned long long v = 0;
+    for (; i < n; ++i) {
+        const uint32_t d = (uint32_t)__ldg(p + i) - '0';
+        if (d > 9u) return false;
+        v = v * 10ull + d;
+    }
+    return v <= (neg ? 2147483648ull : 2147483647ull);
+}
+
+// the text Rust's Display prints for the f32 nearest to it: an integer of at most 7 digits (exact below 2^24), or a plain
+// decimal without trailing zeros whose significant digits number at most 6 (FLT_DIG: such decimals survive the round trip,
+// so the shortest representation of their f32 is the decimal itself); no sign on zero, no exponent, no leading '+'
+__device__ __forceinline__ bool canon_float(const uint8_t *p, int n) {
+    if (n == 1 && __ldg(p) == '.') return true;
+    int i = 0;
+    const bool neg = n > 0 && __ldg(p) == '-';
+    if (neg) i = 1;
+    if (i >= n) return false;
+    int int_digits = 0, sig = 0;
+    bool nonzero = false, lead_zero = false;
+    const int i0 = i;
+    for (; i < n; ++i) {
+        const uint32_t d = (uint32_t)__ldg(p + i) - '0';
+        if (d > 9u) break;
+        if (int_digits == 0 && d == 0) lead_zero = true;
+        ++int_digits;
+        if (nonzero || d) {
+            nonzero = true;
+            ++sig;
+        }
+    }
+    if (int_digits == 0 || (lead_zero && int_digits > 1)) return false;
+    (void)i0;
+    if (i == n) return nonzero ? sig <= 7 : !neg;  // integer: "0" but not "-0"
+    if (__ldg(p + i) != '.' || i + 1 >= n) return false;
+    ++i;
+    uint32_t last = 0;
+    for (; i < n; ++i) {
+        last = (uint32_t)__ldg(p + i) - '0';
+        if (last > 9u) return false;
+        if (nonzero || last) {
+            nonzero = true;
+            ++sig;
+        }
+    }
+    return last != 0u && sig <= 6;
+}
+
+// Walks one INFO field.  Returns the length of the re-serialised string; *err collects kWErrInfo*.  When `dst` is set the
+// string is written there.
+__device__ __forceinline__ int32_t info_walk(const WideArgs &a, const uint8_t *f, int32_t n, uint8_t *dst, uint32_t *err) {
+    if (n == 0 || (n == 1 && __ldg(f) == '.')) return 0;
+    int32_t out = 0, i = 0;
+    while (i <= n) {
+        // entry [i, e)
+        int32_t e = i, eq = -1;
+        while (e < n && __ldg(f + e) != ';') {
+            if (eq < 0 && __ldg(f + e) == '=') eq = e;
+            ++e;
+        }
+        const int32_t klen = (eq < 0 ? e : eq) - i;
+        const uint32_t h = fnv1a(f + i, klen);
+        int type = -1;
+        for (int k = 0; k < a.n_info; ++k) {
+            if (a.info_hash[k] != h || a.info_len[k] != klen) continue;
+            bool same = true;
+            for (int q = 0; q < klen && same; ++q) same = a.info_blob[a.info_off[k] + q] == __ldg(f + i + q);
+            if (same) {
+                type = a.info_type[k];
+                break;
+            }
+        }
+        if (type < 0) *err |= kWErrInfoKey;
+        if (type == kInfoFlag) {
+            if (eq >= 0) *err |= kWErrInfoForm;
+        } else if (type >= 0) {
+            if (eq < 0) {
+                *err |= kWErrInfoValue;
+            } else {
+                // elements of the value
+                int32_t v = eq + 1;
+                if (v == e) *err |= kWErrInfoForm;
+                while (v <= e && v < e + 1) {
+                    int32_t ve = v;
+                    while (ve < e && __ldg(f + ve) != ',') ++ve;
+                    const uint8_t *p = f + v;
+                    const int32_t m = ve - v;
+                    bool ok = true;
+                    if (type == kInfoInteger) ok = canon_int(p, m);
+                    else if (type == kInfoFloat) ok = canon_float(p, m);
+                    else if (type == kInfoCharacter) ok = m == 1;
+                    else
+                        for (int32_t q = 0; q < m && ok; ++q) ok = __ldg(p + q) != '%';
+                    if (!ok || m == 0) *err |= kWErrInfoForm;
+                    if (ve >= e) break;
+                    v = ve + 1;
+                }
+            }
+        }
+        // key[=value], "=true" for a flag, ';' between entries
+        if (dst) {
+            for (int32_t q = i; q < e; ++q) dst[out + (q - i)] = __ldg(f + q);
+            if (type == kInfoFlag && eq < 0) {
+                dst[out + (e - i)] = '=';
+                dst[out + (e - i) + 1] = 't';
+                dst[out + (e - i) + 2] = 'r';
+                dst[out + (e - i) + 3] = 'u';
+                dst[out + (e - i) + 4] = 'e';
+            }
+        }
+        out += e - i;
+        if (type == kInfoFlag && eq < 0) out += 5;
+        if (e >= n) break;
+        if (dst) dst[out] = ';';
+        ++out;
+        i = e + 1;
+    }
+    return out;
+}
+
+// end of the INFO field: the 8th tab, or the end of the line when the record has no FORMAT / sample columns
+__device__ __forceinline__ const uint8_t *info_end(const uint8_t *info, const uint8_t *le) {
+    const uint8_t *p = info;
+    while (p < le && __ldg(p) != '\t') ++p;
+    return p;
+}
+
 __global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__ WideArgs a) {
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= a.n_rows) return;
     const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
     int32_t to[7];
     uint32_t err = 0;
-    int32_t c[kNScan] = {0, 0, 0, 0, 0};
+    int32_t c[kNScan] = {0, 0, 0, 0, 0, 0};
     uint8_t rf = 0;
     float q = 0.0f;
     if (le - ls > 0x7FFFFFF0ll) {
@@ -154,6 +317,10 @@ __global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__
             const uint8_t *f = tab[5] + 1;
             const int32_t n = (int32_t)(tab[6] - f);
             if (!is_missing(f, n)) count_items(f, n, c[kFiE], c[kFiB]);
+        }
+        if (a.want_info) {
+            const uint8_t *f = tab[6] + 1;
+            c[kInfoB] = info_walk(a, f, (int32_t)(info_end(f, le) - f), nullptr, &err);
         }
     }
 #pragma unroll
@@ -250,7 +417,7 @@ __global__ void __launch_bounds__(256) vw_emit_kernel(const __grid_constant__ Wi
             if (leader && v) atomicOr(a.id_valid + word, v);
         }
     }
-    if (!(a.want_id || a.want_ref || a.want_filter)) return;
+    if (!(a.want_id || a.want_ref || a.want_filter || a.want_info)) return;
     const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
     int32_t to[7];
     if (le - ls > 0x7FFFFFF0ll || !find_tabs(ls, le, to)) return;  // reported by the measure pass
@@ -275,6 +442,14 @@ __global__ void __launch_bounds__(256) vw_emit_kernel(const __grid_constant__ Wi
         const int32_t n = (int32_t)(tab[3] - f);
         for (int32_t i = 0; i < n; ++i) a.ref_val[v + i] = __ldg(f + i);
         if (last) a.ref_off[lrow + 1] = (int32_t)(a.pre[kRefB][r + 1] - v0);
+    }
+    if (a.want_info) {
+        const long long v = a.pre[kInfoB][r], v0 = a.pre[kInfoB][r0];
+        a.info_offs[lrow] = (int32_t)(v - v0);
+        const uint8_t *f = tab[6] + 1;
+        uint32_t ignored = 0;
+        info_walk(a, f, (int32_t)(info_end(f, le) - f), a.info_val + v, &ignored);
+        if (last) a.info_offs[lrow + 1] = (int32_t)(a.pre[kInfoB][r + 1] - v0);
     }
     if (a.want_filter) {
         const long long e = a.pre[kFiE][r], e0 = a.pre[kFiE][r0], v = a.pre[kFiB][r], v0 = a.pre[kFiB][r0];
@@ -310,11 +485,11 @@ struct WideStore {
     int batch_rows = 8192, wpb = 256;
     int64_t n_batches = 0, n_rows = 0;
     bool want[9] = {false, false, false, false, false, false, false, false, false};
-    WideBuf id_loff, id_coff, id_val, id_valid, ref_off, ref_val, alt_valid, zeros, qual, qual_valid, fi_loff, fi_coff, fi_val;
+    WideBuf id_loff, id_coff, id_val, id_valid, ref_off, ref_val, alt_valid, zeros, qual, qual_valid, fi_loff, fi_coff, fi_val, info_off, info_val, info_tab;
     std::vector<long long> batch_row0, base[kNScan];  // per batch (+ total): global item / byte offset of the batch's first row
-    static constexpr int kBufs = 13;
+    static constexpr int kBufs = 16;
     void all(WideBuf *out[kBufs]) {
-        WideBuf *v[kBufs] = {&id_loff, &id_coff, &id_val, &id_valid, &ref_off, &ref_val, &alt_valid, &zeros, &qual, &qual_valid, &fi_loff, &fi_coff, &fi_val};
+        WideBuf *v[kBufs] = {&id_loff, &id_coff, &id_val, &id_valid, &ref_off, &ref_val, &alt_valid, &zeros, &qual, &qual_valid, &fi_loff, &fi_coff, &fi_val, &info_off, &info_val, &info_tab};
         for (int i = 0; i < kBufs; ++i) out[i] = v[i];
     }
     template <class T>
@@ -352,10 +527,9 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     w->batch_rows = s->batch_rows;
     w->wpb = ((s->batch_rows + 63) / 64) * 2;
     for (int p : s->projection) w->want[p] = true;
-    for (int p = 7; p < 9; ++p)
-        if (w->want[p])
-            return fail(EXON_GPU_ERR_UNSUPPORTED, "vcf_next_batch: column %d (%s) is re-serialised by the reference builder and is not built on the device yet",
-                        p, p == 7 ? "info" : "formats");
+    if (w->want[8]) return fail(EXON_GPU_ERR_UNSUPPORTED, "vcf_next_batch: column 8 (formats) is re-serialised by the reference builder and is not built on the device yet");
+    if (w->want[7] && !s->info_defs.set)
+        return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: the info column needs the header's ##INFO definitions: call exon_gpu_vcf_set_header first");
     if (*n_rows_io == 0) return EXON_GPU_OK;
 
     // per-row temporaries in scratch_b behind the line tables: 5 counts (i32) | 5 prefixes (i64) | flags
@@ -385,7 +559,7 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
         x += al256w(bytes);
         return p;
     };
-    const bool need[kNScan] = {w->want[2], w->want[2], w->want[3], w->want[6], w->want[6]};
+    const bool need[kNScan] = {w->want[2], w->want[2], w->want[3], w->want[6], w->want[6], w->want[7]};
     WideArgs a;
     memset(&a, 0, sizeof(a));
     a.n_rows = n_rows;
@@ -395,7 +569,8 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     a.batch_rows = w->batch_rows;
     a.wpb = w->wpb;
     a.want_id = w->want[2], a.want_ref = w->want[3], a.want_alt = w->want[4], a.want_qual = w->want[5], a.want_filter = w->want[6];
-    long long *pre[kNScan] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    a.want_info = w->want[7];
+    long long *pre[kNScan] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < kNScan; ++k) {
         if (!need[k]) continue;
         a.cnt[k] = (int32_t *)take(nr1 * 4);
@@ -430,6 +605,38 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     };
     const size_t valid_bytes = (size_t)w->n_batches * (size_t)w->wpb * 4;
     const size_t loff_bytes = (size_t)w->n_batches * (size_t)(w->batch_rows + 1) * 4;
+    if (w->want[7]) {
+        // the header's INFO definitions: hash | offset | length (u32 each) | type (u8) | key bytes
+        const InfoDefs &defs = s->info_defs;
+        const size_t nk = defs.ids.size();
+        std::vector<uint32_t> hs(nk), off(nk), len(nk);
+        std::string blob;
+        for (size_t k = 0; k < nk; ++k) {
+            uint32_t h = 2166136261u;
+            for (unsigned char ch : defs.ids[k]) h = (h ^ ch) * 16777619u;
+            hs[k] = h;
+            off[k] = (uint32_t)blob.size();
+            len[k] = (uint32_t)defs.ids[k].size();
+            blob += defs.ids[k];
+        }
+        const size_t o_off = al256w(nk * 4), o_len = o_off + al256w(nk * 4), o_type = o_len + al256w(nk * 4), o_blob = o_type + al256w(nk);
+        if (int rc = dev_alloc(w->info_tab, o_blob + blob.size() + 16, false)) return rc;
+        uint8_t *t = (uint8_t *)w->info_tab.d;
+        if (nk) {
+            CUDA_TRY(cudaMemcpyAsync(t, hs.data(), nk * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(t + o_off, off.data(), nk * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(t + o_len, len.data(), nk * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(t + o_type, defs.types.data(), nk, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(t + o_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaStreamSynchronize(st));  // the sources are locals
+        }
+        a.info_hash = (const uint32_t *)t;
+        a.info_off = (const int32_t *)(t + o_off);
+        a.info_len = (const int32_t *)(t + o_len);
+        a.info_type = t + o_type;
+        a.info_blob = t + o_blob;
+        a.n_info = (int32_t)nk;
+    }
     if (w->want[5]) {
         if (int rc = dev_alloc(w->qual, (size_t)n_rows * 4, false)) return rc;
         if (int rc = dev_alloc(w->qual_valid, valid_bytes, true)) return rc;
@@ -465,9 +672,11 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     if (const uint32_t e = (uint32_t)h_misc[0])
-        return fail((e & ~kWErrQualDigits) ? EXON_GPU_ERR_PARSE : EXON_GPU_ERR_UNSUPPORTED, "malformed VCF record at row %llu:%s%s%s%s", h_misc[1],
+        return fail((e & ~(kWErrQualDigits | kWErrInfoKey | kWErrInfoForm)) ? EXON_GPU_ERR_PARSE : EXON_GPU_ERR_UNSUPPORTED, "VCF record at row %llu:%s%s%s%s%s%s%s", h_misc[1],
                     (e & kWErrFields) ? " fewer than 8 tab-separated fields;" : "", (e & kWErrQual) ? " QUAL is not a float literal;" : "",
-                    (e & kWErrQualDigits) ? " QUAL has more than 36 significant digits;" : "", (e & kWErrFieldLen) ? " a line of 2 GiB or more;" : "");
+                    (e & kWErrQualDigits) ? " QUAL has more than 36 significant digits;" : "", (e & kWErrFieldLen) ? " a line of 2 GiB or more;" : "",
+                    (e & kWErrInfoValue) ? " an INFO key that is not a flag has no value;" : "", (e & kWErrInfoKey) ? " an INFO key the header does not define;" : "",
+                    (e & kWErrInfoForm) ? " an INFO value the reference would print differently (number not in Rust's Display form, '%' escape, flag with a value);" : "");
     for (int k = 0; k < kNScan; ++k) {
         if (!need[k]) continue;
         for (int64_t b = 0; b < w->n_batches; ++b)
@@ -491,6 +700,11 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
         if (int rc = dev_alloc(w->alt_valid, valid_bytes, true)) return rc;
         if (int rc = dev_alloc(w->zeros, (size_t)(w->batch_rows + 1) * 4, true)) return rc;
         a.alt_valid = (uint32_t *)w->alt_valid.d;
+    }
+    if (w->want[7]) {
+        if (int rc = dev_alloc(w->info_off, loff_bytes, false)) return rc;
+        if (int rc = dev_alloc(w->info_val, (size_t)w->base[kInfoB][nb1 - 1], false)) return rc;
+        a.info_offs = (int32_t *)w->info_off.d, a.info_val = (uint8_t *)w->info_val.d;
     }
     if (w->want[6]) {
         if (int rc = dev_alloc(w->fi_loff, loff_bytes, false)) return rc;
@@ -563,6 +777,13 @@ void wide_export(const WideStore *w, int col, int64_t b, int64_t rows, ArrowArra
             a->n_buffers = 2;
             slot->bufs[0] = w->p<uint32_t>(w->qual_valid) + vw;
             slot->bufs[1] = w->p<float>(w->qual) + row0;
+            break;
+        case 7:
+            a->null_count = 0;
+            a->n_buffers = 3;
+            slot->bufs[0] = nullptr;
+            slot->bufs[1] = w->p<int32_t>(w->info_off) + loff;
+            slot->bufs[2] = w->p<uint8_t>(w->info_val) + w->base[kInfoB][(size_t)b];
             break;
         default:  // 6
             a->null_count = 0;

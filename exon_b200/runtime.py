@@ -309,6 +309,10 @@ class VcfStream:
     def reset(self):
         check(self.lib.exon_gpu_vcf_reset(self.handle))
 
+    def set_header(self, text: bytes):
+        """exon_gpu_vcf_set_header: the header text (its ##INFO lines give the info column its types)."""
+        check(self.lib.exon_gpu_vcf_set_header(self.handle, bytes(text), len(text)))
+
     def feed(self, data, *, is_last: bool = True, device_ptr: int | None = None, nbytes: int | None = None):
         """Feed host bytes (bytes / numpy uint8 / PinnedBuffer) or a raw device range (device_ptr, nbytes)."""
         if device_ptr is not None:

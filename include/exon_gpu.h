@@ -137,7 +137,7 @@ int exon_gpu_regroup_files_by_size(const int64_t *sizes, int32_t n_files, int32_
 typedef struct {
     int32_t batch_rows;        /* session batch size; reference default 8192 (exon/exon-common/src/lib.rs:27) */
     int32_t n_projection;      /* file-schema column indices to materialise, in output order ... */
-    const int32_t *projection; /* ... VCFConfig.projection (exon/exon-vcf/src/config.rs:23-64); cols 0..6 (chrom pos id ref alt qual filter) */
+    const int32_t *projection; /* ... VCFConfig.projection (exon/exon-vcf/src/config.rs:23-64); cols 0..7 (chrom pos id ref alt qual filter info) */
     int32_t columns_on_device; /* 0: next_batch buffers are pinned host memory; 1: device memory */
     /* Optional predicate declared up front so that every feed() can be scanned while the next one is still
      * copying (fused a5-a9).  NULL = none declared; filter_count() then scans what is resident. */
@@ -152,6 +152,12 @@ int exon_gpu_vcf_open(exon_gpu_ctx *ctx, const exon_gpu_vcf_opts *opts, exon_gpu
 int exon_gpu_vcf_close(exon_gpu_stream *s);
 /* Forget everything fed so far but keep the device arena for the next query on this partition. */
 int exon_gpu_vcf_reset(exon_gpu_stream *s);
+
+/* The header text of the partition's files (only its ##INFO lines are read: ID and Type), as the reference's builder gets
+ * them from the noodles Header its opener parsed (unindex_file_opener.rs:74-88, lazy_array_builder.rs:70-75).  Required
+ * before exon_gpu_vcf_next_batch when the projection holds column 7 (info); every file of the partition is taken to
+ * share these definitions. */
+int exon_gpu_vcf_set_header(exon_gpu_stream *s, const char *text, size_t len);
 
 /* Bytes in.  Consecutive calls deliver consecutive byte ranges of ONE file (uncompressed VCF text, header
  * included -- the library skips it like `read_header`, unindex_file_opener.rs:74-88); is_last != 0 ends the
@@ -169,8 +175,13 @@ int exon_gpu_vcf_feed(exon_gpu_stream *s, const uint8_t *text, size_t len, int i
  * semantics (lazy_array_builder.rs:169-216): id "." -> NULL; alt "." -> NULL, anything else -> a valid EMPTY list
  * (the builder never appends the alleles); qual "." -> NULL, else Rust f32::from_str (correctly rounded);
  * filter always valid, "." -> [].  A record with fewer than 8 fields or a malformed QUAL fails the call
- * (EXON_GPU_ERR_PARSE).  info (7) and formats (8) are re-serialised by the reference and are not built yet:
- * exon_gpu_vcf_open rejects them with EXON_GPU_ERR_UNSUPPORTED.
+ * (EXON_GPU_ERR_PARSE).  info (7, utf8, string mode): the reference does not copy the field, it prints noodles' typed view
+ * of it again (lazy_array_builder.rs:217-298: `key=value` joined by ';', a flag as `key=true`, numbers through Rust's
+ * Display).  The column holds exactly that string whenever every number of the field already has the form Display gives
+ * it (the reference's own golden rows do, slt/vcf-select-tests.slt:6-10); a value for which that does not hold, a key
+ * the header does not define, a '%' escape in a string, a flag with a value: EXON_GPU_ERR_UNSUPPORTED, never an
+ * approximation; a non-flag key without a value fails like the reference's unwrap does (EXON_GPU_ERR_PARSE).
+ * formats (8) is not built: exon_gpu_vcf_open rejects it with EXON_GPU_ERR_UNSUPPORTED.
  * End of stream: returns EXON_GPU_OK with out->release == NULL (ArrowArrayStream.get_next convention). */
 int exon_gpu_vcf_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 

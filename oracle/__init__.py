@@ -177,6 +177,56 @@ def vcf_wide_rows(data):
         L.exo_vcf_wide_free(wp)
 
 
+def vcf_info_strings(data):
+    """Column 7 (info, string mode) of every record as LazyVCFArrayBuilder::append prints it
+    (/root/reference/exon/exon-vcf/src/array_builder/lazy_array_builder.rs:217-298): noodles' typed view of the field -- types from
+    the header's ##INFO lines -- re-serialised as `key=value` joined by ';', a flag as `key=true`, integers through i32
+    Display, floats through f32 Display (shortest digits that round-trip, never an exponent), array elements joined by ','
+    with '.' for a missing one.  Pure Python (small inputs only); pinned by slt/vcf-select-tests.slt:6-10.
+    A key the header does not define or a non-flag key without a value raises (the reference's behaviour there is
+    noodles-internal / a panic)."""
+    import re
+
+    text = bytes(_buf(data))
+    types = {}
+    for line in text.split(b"\n"):
+        if not line.startswith(b"##INFO=<"):
+            continue
+        types[re.search(rb"[<,]ID=([^,>]+)", line).group(1)] = re.search(rb",Type=([^,>]+)", line).group(1)
+    out = []
+    for line in text[header_len(text):].split(b"\n"):
+        if not line:
+            continue
+        field = line.split(b"\t")[7]
+        if field in (b".", b""):
+            out.append(b"")
+            continue
+        parts = []
+        for entry in field.split(b";"):
+            key, eq, val = entry.partition(b"=")
+            ty = types[key]
+            if ty == b"Flag":
+                if eq:
+                    raise ValueError("flag with a value")
+                parts.append(key + b"=true")
+                continue
+            if not eq:
+                raise ValueError("missing value")
+            elems = []
+            for e in val.split(b","):
+                if e == b".":
+                    elems.append(b".")
+                elif ty == b"Integer":
+                    elems.append(str(int(e)).encode())
+                elif ty == b"Float":
+                    elems.append(np.format_float_positional(np.float32(float(e)), unique=True, trim="-").encode())
+                else:
+                    elems.append(e)
+            parts.append(key + b"=" + b",".join(elems))
+        out.append(b";".join(parts))
+    return out
+
+
 def filter_count(data, chrom=None, lo=None, hi=None, batch_size: int = 8192):
     """(count, rows) for `chrom = <chrom> AND pos BETWEEN lo AND hi` over one VCF text."""
     a = _buf(data)

@@ -119,3 +119,14 @@ def test_parse_f32_grammar():
     assert np.isnan(np.array([lib_f32_bits(b"NaN")], np.uint32).view(np.float32)[0])
     assert lib_f32_bits(b"1" * 37) == ("err", _abi.ERR_UNSUPPORTED)  # 37 significant digits: refused, not approximated
     assert lib_f32_bits(b"1" + b"0" * 40) == 0x7F800000  # trailing zeros are not significant digits
+
+
+def test_info_oracle_goldens(index_vcf, biobear_vcf):
+    # slt/vcf-select-tests.slt:6-10: SELECT info FROM vcf_table LIMIT 2
+    got = oracle.vcf_info_strings(index_vcf)
+    assert got[:2] == [b"DP=1;I16=1,0,0,0,26,676,0,0,60,3600,0,0,0,0,0,0;QS=1,0;MQ0F=0", b"DP=1;I16=1,0,0,0,34,1156,0,0,60,3600,0,0,1,1,0,0;QS=1,0;MQ0F=0"]
+    assert len(got) == 621
+    assert oracle.vcf_info_strings(biobear_vcf)[2] == b"DP4=1,2,3,4;AN=4;AC=2;INDEL=true;STR=test"   # a flag is printed as key=true
+    hdr = b"##fileformat=VCFv4.2\n##INFO=<ID=AF,Number=A,Type=Float,Description=\"x, y\">\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n"
+    rows = b"1\t5\t.\tA\tC\t.\t.\tAF=0.50,1e-3,.;DP=007\n1\t6\t.\tA\tC\t.\t.\t.\n"
+    assert oracle.vcf_info_strings(hdr + rows) == [b"AF=0.5,0.001,.;DP=7", b""]   # numbers go through Display; '.' info is ""

@@ -136,10 +136,76 @@ def test_errors(gpu_ctx):
     with pytest.raises(ExonGpuError) as e:
         run((HEADER + "1\t5\t.\tA\tC\t" + "1" * 37 + "\tPASS\t.\n").encode(), (5,))
     assert e.value.code == _abi.ERR_UNSUPPORTED
-    for col in (7, 8):
-        with pytest.raises(ExonGpuError) as e:
-            gpu_ctx.open_vcf(projection=(col,))
-        assert e.value.code == _abi.ERR_UNSUPPORTED
+    with pytest.raises(ExonGpuError) as e:
+        gpu_ctx.open_vcf(projection=(8,))
+    assert e.value.code == _abi.ERR_UNSUPPORTED
     with pytest.raises(ExonGpuError):
         gpu_ctx.open_vcf(projection=(2, 2))
     assert run(HEADER.encode(), (2, 5)) == []  # header only: no batches
+
+
+# ---- column 7: info (string mode) -------------------------------------------------------------------------------------
+
+def gpu_info(ctx, text, header=None, projection=(7,), batch_rows=8192):
+    out = []
+    with ctx.open_vcf(projection=projection, batch_rows=batch_rows) as s:
+        if header is not None:
+            s.set_header(header)
+        s.feed(text, is_last=True)
+        for b in s.batches():
+            rb = b.to_pyarrow()
+            assert rb.column("info").null_count == 0
+            out += [x.encode() for x in rb.column("info").to_pylist()]
+    return out
+
+
+def header_of(text):
+    return bytes(text[:oracle.header_len(text)])
+
+
+@pytest.mark.parametrize("name", ["index_vcf", "biobear_vcf", "common_all_vcf"])
+def test_info_fixtures(gpu_ctx, request, name):
+    text = request.getfixturevalue(name)
+    want = oracle.vcf_info_strings(text)
+    assert gpu_info(gpu_ctx, text, header_of(text)) == want
+    if name == "index_vcf":   # slt/vcf-select-tests.slt:6-10 on the device-built column
+        assert want[0] == b"DP=1;I16=1,0,0,0,26,676,0,0,60,3600,0,0,0,0,0,0;QS=1,0;MQ0F=0"
+    assert gpu_info(gpu_ctx, text, header_of(text), projection=(0, 7, 5, 2), batch_rows=5) == want
+
+
+INFO_HDR = (b"##fileformat=VCFv4.2\n##INFO=<ID=AF,Number=A,Type=Float,Description=\"a, b\">\n##INFO=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n"
+            b"##INFO=<ID=DB,Number=0,Type=Flag,Description=\"f\">\n##INFO=<ID=NM,Number=1,Type=String,Description=\"s\">\n"
+            b"##INFO=<ID=CH,Number=1,Type=Character,Description=\"c\">\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+
+
+def info_text(infos, tail=""):
+    return INFO_HDR + "".join(f"1\t{i + 1}\t.\tA\tC\t.\t.\t{x}{tail}\n" for i, x in enumerate(infos)).encode()
+
+
+def test_info_canonical_values(gpu_ctx):
+    infos = [".", "DB", "DP=0", "DP=-12;DB", "AF=0.5", "AF=0.5,0.25,.", "AF=1", "AF=0", "AF=1234567", "AF=123.456", "AF=0.000123456", "AF=-2.5",
+             "NM=a b;CH=x;DP=2147483647", "DB;NM=x=y", "AF=.;DP=.", "DP=-2147483648"]
+    for tail in ("", "\tGT\t0/1"):
+        text = info_text(infos, tail)
+        want = oracle.vcf_info_strings(text)
+        assert want[1] == b"DB=true" and want[0] == b""
+        assert gpu_info(gpu_ctx, text, INFO_HDR) == want
+
+
+@pytest.mark.parametrize("bad", ["AF=0.50", "AF=1e-3", "AF=1.0", "AF=+1", "AF=00.5", "AF=0.1234567", "AF=12345678", "AF=-0", "AF=nan", "DP=007", "DP=+1",
+                                 "DP=2147483648", "DP=-0", "NM=a%3Bb", "DB=1", "XX=1", "AF=", "AF=1,,2", "CH=xy"])
+def test_info_refuses_what_the_reference_would_rewrite(gpu_ctx, bad):
+    # every one of these is printed differently by the reference (or is noodles-internal): refused, never approximated
+    with pytest.raises(ExonGpuError) as e:
+        gpu_info(gpu_ctx, info_text(["DP=1", bad]), INFO_HDR)
+    assert e.value.code == _abi.ERR_UNSUPPORTED, bad
+
+
+def test_info_errors(gpu_ctx):
+    with pytest.raises(ExonGpuError) as e:
+        gpu_info(gpu_ctx, info_text(["DP"]), INFO_HDR)          # a non-flag key without a value: the reference unwraps a None
+    assert e.value.code == _abi.ERR_PARSE
+    with pytest.raises(ExonGpuError) as e:
+        gpu_info(gpu_ctx, info_text(["DP=1"]), None)            # no header set
+    assert e.value.code == _abi.ERR_STATE
+    assert gpu_info(gpu_ctx, INFO_HDR, INFO_HDR) == []
