@@ -451,8 +451,25 @@ __global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const Bgz
                 }
             }
             __syncwarp();
-            // 3. tokens, one lane per match; matches whose source ends before the segment are copied right away
+            // 3. tokens, one lane per match; matches whose source ends before the segment are copied right away.
+            // Sources behind the ring come from global memory: their lines are requested for every match of the lane before
+            // the first copy starts, so that the L2 round trips overlap instead of being paid one match after the other.
+            // (Those bytes were written back at least three segments ago, by this warp, with st.cg; the loads below may use
+            // the L1: no line they touch is written again.)
             const uint32_t ring_lo = segq > (kRingBytes - kSeg) ? segq - (kRingBytes - kSeg) : 0u;
+            if (ring_lo > 0u) {
+                for (int k = lane; k < n_match; k += 32) {
+                    const uint32_t p = S.mpos[k], q = segq + p;
+                    if (p + 2 >= kSeg) continue;
+                    const uint32_t len = (uint32_t)S.ring[q & kRingMask] + 3u;
+                    const uint32_t dist = ((uint32_t)S.ring[(q + 1) & kRingMask] | ((uint32_t)S.ring[(q + 2) & kRingMask] << 8)) + 1u;
+                    const uint32_t src = q - dist;
+                    if (src < ring_lo && dist <= q) {
+                        prefetch_line(O + src);
+                        prefetch_line(O + src + min(len, kSeg - p) - 1u);
+                    }
+                }
+            }
             uint32_t spill_len = 0, spill_dist = 0;
             for (int k = lane; k < n_match; k += 32) {
                 const uint32_t p = S.mpos[k], q = segq + p;
@@ -476,7 +493,7 @@ __global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const Bgz
                 if (src + lseg <= segq) {
                     for (uint32_t j = 0; j < lseg; ++j) {
                         const uint32_t sq = src + j;
-                        const uint8_t b = sq >= ring_lo ? S.ring[sq & kRingMask] : __ldcg(O + sq);
+                        const uint8_t b = sq >= ring_lo ? S.ring[sq & kRingMask] : O[sq];
                         S.ring[(q + j) & kRingMask] = b;
                     }
                     S.mtok[k] = 0u;
@@ -494,16 +511,23 @@ __global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const Bgz
                 }
                 __syncwarp();
             }
+            // 32 matches at a time: every lane looks at one, the warp then walks only those that still have to be copied
 #pragma unroll 1
-            for (int k = 0; k < n_match; ++k) {
-                const uint32_t t = S.mtok[k];
-                if (!t) continue;
-                const uint32_t q = segq + S.mpos[k], len = t & 511u, dist = t >> 9, src = q - dist;
-                for (uint32_t j = lane; j < len; j += 32) {
-                    const uint32_t sj = dist >= len ? j : j % dist;
-                    S.ring[(q + j) & kRingMask] = S.ring[(src + sj) & kRingMask];
+            for (int k0 = 0; k0 < n_match; k0 += 32) {
+                const int k = k0 + lane;
+                const uint32_t t_l = k < n_match ? S.mtok[k] : 0u, p_l = k < n_match ? (uint32_t)S.mpos[k] : 0u;
+                uint32_t pend = __ballot_sync(0xFFFFFFFFu, t_l != 0u);
+                while (pend) {
+                    const int b = __ffs((int)pend) - 1;
+                    pend &= pend - 1u;
+                    const uint32_t t = __shfl_sync(0xFFFFFFFFu, t_l, b), q = segq + __shfl_sync(0xFFFFFFFFu, p_l, b);
+                    const uint32_t len = t & 511u, dist = t >> 9, src = q - dist;
+                    for (uint32_t j = lane; j < len; j += 32) {
+                        const uint32_t sj = dist >= len ? j : j % dist;
+                        S.ring[(q + j) & kRingMask] = S.ring[(src + sj) & kRingMask];
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             // the spill of this segment's last match, if any (at most one lane has it)
             const uint32_t sp = __ballot_sync(0xFFFFFFFFu, spill_len != 0u);
