@@ -224,7 +224,6 @@ int fasta_build_columns(VcfStream *s) {
     const int n_files = (int)li.file_line0.size() - 1;
     size_t cub_bytes = 0;
     CUDA_TRY(exclusive_sum_i32_i64(nullptr, cub_bytes, (const int32_t *)nullptr, (long long *)nullptr, (int)nl1, st));
-    if (cub_bytes > (1 << 20)) return fail(EXON_GPU_ERR_STATE, "fasta_next_batch: scan scratch of %zu bytes", cub_bytes);
     uint8_t *x = li.extra;
     auto take = [&](size_t bytes) {
         uint8_t *p = x;
@@ -245,7 +244,14 @@ int fasta_build_columns(VcfStream *s) {
     }
     a.lflags = take(nl1);
     a.rec_line = (long long *)take(nl1 * 8);
-    uint8_t *cub_tmp = take(cub_bytes);
+    // scan scratch grows with the row count (64-bit tile states): from the pool, not from the fixed part of scratch_b
+    uint8_t *cub_tmp = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&cub_tmp, cub_bytes + 256, st));
+    struct CubFree {
+        void *p;
+        cudaStream_t st;
+        ~CubFree() { cudaFreeAsync(p, st); }
+    } cub_guard{cub_tmp, st};
     uint32_t *d_flags = (uint32_t *)take(64);
     CUDA_TRY(cudaMemsetAsync(d_flags, 0, 64, st));
     CUDA_TRY(cudaMemsetAsync(a.lflags + n_lines, 0, 1, st));

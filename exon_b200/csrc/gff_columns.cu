@@ -318,7 +318,6 @@ int gff_build_columns(VcfStream *s) {
     const int n_files = (int)li.file_line0.size() - 1;
     size_t cub_bytes = 0;
     CUDA_TRY(exclusive_sum_i32_i64(nullptr, cub_bytes, (const int32_t *)nullptr, (long long *)nullptr, (int)nl1, st));
-    if (cub_bytes > (1 << 20)) return fail(EXON_GPU_ERR_STATE, "gff_next_batch: scan scratch of %zu bytes", cub_bytes);
     uint8_t *x = li.extra;
     auto take = [&](size_t bytes) {
         uint8_t *p = x;
@@ -345,7 +344,14 @@ int gff_build_columns(VcfStream *s) {
     if (want[3]) a.start = (long long *)take(nl1 * 8);
     if (want[4]) a.end = (long long *)take(nl1 * 8);
     if (want[5]) a.score = (float *)take(nl1 * 4);
-    uint8_t *cub_tmp = take(cub_bytes);
+    // scan scratch grows with the row count (64-bit tile states): from the pool, not from the fixed part of scratch_b
+    uint8_t *cub_tmp = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&cub_tmp, cub_bytes + 256, st));
+    struct CubFree {
+        void *p;
+        cudaStream_t st;
+        ~CubFree() { cudaFreeAsync(p, st); }
+    } cub_guard{cub_tmp, st};
     unsigned long long *d_misc = (unsigned long long *)take(64);
     const unsigned long long init_misc[3] = {0ull, ~0ull, 0ull};
     CUDA_TRY(cudaMemcpyAsync(d_misc, init_misc, sizeof(init_misc), cudaMemcpyHostToDevice, st));

@@ -318,14 +318,10 @@ __global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__
             const int32_t n = (int32_t)(tab[6] - f);
             if (!is_missing(f, n)) count_items(f, n, c[kFiE], c[kFiB]);
         }
-        if (a.want_info) {
-            const uint8_t *f = tab[6] + 1;
-            c[kInfoB] = info_walk(a, f, (int32_t)(info_end(f, le) - f), nullptr, &err);
-        }
     }
 #pragma unroll
     for (int k = 0; k < kNScan; ++k)
-        if (a.cnt[k]) a.cnt[k][r] = c[k];
+        if (k != kInfoB && a.cnt[k]) a.cnt[k][r] = c[k];  // kInfoB belongs to vw_info_measure_kernel
     a.rowflags[r] = rf;
     if (a.want_qual) {
         a.qual[r] = q;
@@ -417,7 +413,7 @@ __global__ void __launch_bounds__(256) vw_emit_kernel(const __grid_constant__ Wi
             if (leader && v) atomicOr(a.id_valid + word, v);
         }
     }
-    if (!(a.want_id || a.want_ref || a.want_filter || a.want_info)) return;
+    if (!(a.want_id || a.want_ref || a.want_filter)) return;
     const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
     int32_t to[7];
     if (le - ls > 0x7FFFFFF0ll || !find_tabs(ls, le, to)) return;  // reported by the measure pass
@@ -443,14 +439,6 @@ __global__ void __launch_bounds__(256) vw_emit_kernel(const __grid_constant__ Wi
         for (int32_t i = 0; i < n; ++i) a.ref_val[v + i] = __ldg(f + i);
         if (last) a.ref_off[lrow + 1] = (int32_t)(a.pre[kRefB][r + 1] - v0);
     }
-    if (a.want_info) {
-        const long long v = a.pre[kInfoB][r], v0 = a.pre[kInfoB][r0];
-        a.info_offs[lrow] = (int32_t)(v - v0);
-        const uint8_t *f = tab[6] + 1;
-        uint32_t ignored = 0;
-        info_walk(a, f, (int32_t)(info_end(f, le) - f), a.info_val + v, &ignored);
-        if (last) a.info_offs[lrow + 1] = (int32_t)(a.pre[kInfoB][r + 1] - v0);
-    }
     if (a.want_filter) {
         const long long e = a.pre[kFiE][r], e0 = a.pre[kFiE][r0], v = a.pre[kFiB][r], v0 = a.pre[kFiB][r0];
         a.fi_loff[lrow] = (int32_t)(e - e0);
@@ -463,6 +451,57 @@ __global__ void __launch_bounds__(256) vw_emit_kernel(const __grid_constant__ Wi
             coff[a.pre[kFiE][r + 1] - e0] = (int32_t)(a.pre[kFiB][r + 1] - v0);
         }
     }
+}
+
+// INFO lives in its own two kernels (the entry walk with its key lookups must not shape the register budget of the row
+// passes): length + checks, then -- after the scan -- offsets and bytes.
+__global__ void __launch_bounds__(256) vw_info_measure_kernel(const __grid_constant__ WideArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= a.n_rows) return;
+    const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
+    int32_t to[7];
+    int32_t n = 0;
+    uint32_t err = 0;
+    if (le - ls <= 0x7FFFFFF0ll && find_tabs(ls, le, to)) {  // a short line is reported by the row pass
+        const uint8_t *f = ls + to[6] + 1;
+        n = info_walk(a, f, (int32_t)(info_end(f, le) - f), nullptr, &err);
+    }
+    a.cnt[kInfoB][r] = n;
+    if (err) {
+        atomicOr(a.flags, err);
+        atomicMin(a.first_bad_row, (unsigned long long)r);
+    }
+}
+
+__global__ void __launch_bounds__(256) vw_info_emit_kernel(const __grid_constant__ WideArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    __shared__ long long s_b0;
+    if (threadIdx.x == 0) {
+        const int64_t rb = (int64_t)blockIdx.x * 256;
+        int64_t lo = 0, hi = a.n_batches;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(&a.brow[mid]) <= rb) lo = mid;
+            else hi = mid;
+        }
+        s_b0 = lo;
+    }
+    __syncthreads();
+    if (r >= a.n_rows) return;
+    int64_t b = s_b0;
+    while (__ldg(&a.brow[b + 1]) <= r) ++b;
+    const int64_t r0 = __ldg(&a.brow[b]);
+    const int in_batch = (int)(r - r0);
+    const int64_t lrow = b * (int64_t)(a.batch_rows + 1) + in_batch;
+    const long long v = a.pre[kInfoB][r], v0 = a.pre[kInfoB][r0];
+    a.info_offs[lrow] = (int32_t)(v - v0);
+    if (r + 1 == __ldg(&a.brow[b + 1])) a.info_offs[lrow + 1] = (int32_t)(a.pre[kInfoB][r + 1] - v0);
+    const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
+    int32_t to[7];
+    if (le - ls > 0x7FFFFFF0ll || !find_tabs(ls, le, to)) return;
+    const uint8_t *f = ls + to[6] + 1;
+    uint32_t ignored = 0;
+    info_walk(a, f, (int32_t)(info_end(f, le) - f), a.info_val + v, &ignored);
 }
 
 __global__ void vw_gather_i64(const long long *src, const long long *idx, int64_t n, long long *out) {
@@ -552,7 +591,6 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     const size_t nb1 = (size_t)w->n_batches + 1, nr1 = (size_t)n_rows + 1;
     size_t cub_bytes = 0;
     CUDA_TRY(exclusive_sum_i32_i64(nullptr, cub_bytes, (const int32_t *)nullptr, (long long *)nullptr, (int)nr1, st));
-    if (cub_bytes > (1 << 20)) return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: scan scratch of %zu bytes", cub_bytes);
     uint8_t *x = li.extra;
     auto take = [&](size_t bytes) {
         uint8_t *p = x;
@@ -579,7 +617,14 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
         CUDA_TRY(cudaMemsetAsync(a.cnt[k] + n_rows, 0, 4, st));
     }
     a.rowflags = take(nr1);
-    uint8_t *cub_tmp = take(cub_bytes);
+    // scan scratch grows with the row count (64-bit tile states): from the pool, not from the fixed part of scratch_b
+    uint8_t *cub_tmp = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&cub_tmp, cub_bytes + 256, st));
+    struct CubFree {
+        void *p;
+        cudaStream_t st;
+        ~CubFree() { cudaFreeAsync(p, st); }
+    } cub_guard{cub_tmp, st};
     unsigned long long *d_misc = (unsigned long long *)take(64);
     // batch table | per-scan batch bases (small, sized by the batch count: from the pool)
     long long *d_brow = nullptr;
@@ -648,6 +693,10 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     const unsigned grid = (unsigned)((n_rows + 255) / 256);
     vw_measure_kernel<<<grid, 256, 0, st>>>(a);
     ctx->launches.fetch_add(1);
+    if (w->want[7]) {
+        vw_info_measure_kernel<<<grid, 256, 0, st>>>(a);
+        ctx->launches.fetch_add(1);
+    }
 
     CUDA_TRY(cudaGetLastError());
     // ---- 2. scans + per-batch bases ----
@@ -715,6 +764,10 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     // ---- 3. emit ----
     vw_emit_kernel<<<grid, 256, 0, st>>>(a);
     ctx->launches.fetch_add(1);
+    if (w->want[7]) {
+        vw_info_emit_kernel<<<grid, 256, 0, st>>>(a);
+        ctx->launches.fetch_add(1);
+    }
     CUDA_TRY(cudaGetLastError());
     if (!w->on_device) {
         WideBuf *b[WideStore::kBufs];

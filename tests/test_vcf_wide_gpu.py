@@ -209,3 +209,45 @@ def test_info_errors(gpu_ctx):
         gpu_info(gpu_ctx, info_text(["DP=1"]), None)            # no header set
     assert e.value.code == _abi.ERR_STATE
     assert gpu_info(gpu_ctx, INFO_HDR, INFO_HDR) == []
+
+
+def test_large_partition_against_generator_truth(gpu_ctx):
+    """12 M rows in 8 files: sizes at which scan scratch, 64-bit offsets and the batch tables are no longer trivial (the first
+    100 M-row run of this path failed on a fixed-size scan scratch that the small cases never outgrew).  ref / qual / filter
+    are checked against the generator's integer columns, batch by batch, without going through Python lists."""
+    import pyarrow as pa
+    from synth import vcf
+
+    cols = vcf.columns(12_000_000)
+    files = vcf.shards(cols, 8)
+    bounds = vcf.shard_bounds(cols.n, 8)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    row = 0
+    with gpu_ctx.open_vcf(projection=(3, 5, 6, 2, 4)) as s:
+        for f in files:
+            s.feed(f, is_last=True)
+        sizes = []
+        for b in s.batches():
+            rb = b.to_pyarrow()
+            n = rb.num_rows
+            sizes.append(n)
+            ref = rb.column("ref")
+            off = np.frombuffer(ref.buffers()[1], dtype=np.int32, count=n + 1)
+            assert off[0] == 0 and off[-1] == n and np.array_equal(np.diff(off), np.ones(n, np.int32))   # one base per row
+            assert np.array_equal(np.frombuffer(ref.buffers()[2], dtype=np.uint8, count=n), letters[cols.ref[row:row + n]])
+            q = rb.column("qual")
+            want_q = cols.qual[row:row + n]
+            assert np.array_equal(np.asarray(q.is_valid()), want_q >= 0)
+            got_q = q.to_numpy(zero_copy_only=False)
+            assert np.array_equal(got_q[want_q >= 0], want_q[want_q >= 0].astype(np.float32))
+            assert rb.column("id").null_count == n and rb.column("alt").null_count == 0
+            flt = rb.column("filter")
+            assert pa.compute.list_value_length(flt).to_numpy().sum() == n and flt.values.to_pylist()[:2] == ["PASS", "PASS"]
+            row += n
+    assert row == cols.n
+    # batches of 8192 that restart at every file
+    want_sizes = []
+    for lo, hi in bounds:
+        k = hi - lo
+        want_sizes += [8192] * (k // 8192) + ([k % 8192] if k % 8192 else [])
+    assert sizes == want_sizes
