@@ -393,7 +393,10 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kCopyWarps = 4;
 constexpr uint32_t kSeg = 1024;
-constexpr uint32_t kRingBytes = 4096;
+#ifndef EXON_INF_RING
+#define EXON_INF_RING 4096
+#endif
+constexpr uint32_t kRingBytes = EXON_INF_RING;
 constexpr uint32_t kRingMask = kRingBytes - 1;
 constexpr int kMaxMatches = 352;  // matches that can start inside one segment (1024 / 3, rounded up)
 
