@@ -650,15 +650,28 @@ __global__ void __launch_bounds__(256) bam_col_emit_kernel(const __grid_constant
             *dst++ = (uint8_t)("MIDNSHP=X"[op > 8u ? 0u : op]);
         }
     }
+    // the long cells (bases, qualities) only get their offsets here: their bytes are written by bam_col_emit_long_kernel, one
+    // warp per record, so that the stores of a record coalesce
+    if (a.off[kBSeq]) open_cell(kBSeq, v);
+    if (a.off[kBQual]) open_cell(kBQual, v);
+}
+
+// sequence (4-bit -> letters) and quality_score (i8 -> i64) of one record per warp
+__global__ void __launch_bounds__(256) bam_col_emit_long_kernel(const __grid_constant__ BamColArgs a) {
+    const int64_t r = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= a.n_rows) return;
+    const int f = bam_find_file(a.files, a.n_files, r);
+    const BamRec R = bam_rec(a.rec_ptr[r], a.files[f].n_ref);
+    if (!R.ok) return;
     if (a.off[kBSeq]) {
-        open_cell(kBSeq, v);
-        for (int32_t i = 0; i < R.l_seq; ++i) a.val[kBSeq][v + i] = (uint8_t)("=ACMGRSVTWYHKDBN"[(R.seq[i >> 1] >> ((i & 1) ? 0 : 4)) & 15]);
+        uint8_t *dst = a.val[kBSeq] + a.pre[kBSeq][r];
+        for (int32_t i = lane; i < R.l_seq; i += 32) dst[i] = (uint8_t)("=ACMGRSVTWYHKDBN"[(R.seq[i >> 1] >> ((i & 1) ? 0 : 4)) & 15]);
     }
     if (a.off[kBQual]) {
-        open_cell(kBQual, v);
         const int32_t n = (int32_t)(a.pre[kBQual][r + 1] - a.pre[kBQual][r]);
-        long long *dst = reinterpret_cast<long long *>(a.val[kBQual]) + v;
-        for (int32_t i = 0; i < n; ++i) dst[i] = (long long)(int8_t)R.qual[i];
+        long long *dst = reinterpret_cast<long long *>(a.val[kBQual]) + a.pre[kBQual][r];
+        for (int32_t i = lane; i < n; i += 32) dst[i] = (long long)(int8_t)R.qual[i];
     }
 }
 
@@ -927,6 +940,10 @@ int bam_build_columns(VcfStream *s) {
     // ---- 4. emit ----
     bam_col_emit_kernel<<<grid, 256, 0, st>>>(ca);
     ctx->launches.fetch_add(1);
+    if (need[kBSeq] || need[kBQual]) {
+        bam_col_emit_long_kernel<<<(unsigned)((n_rows * 32 + 255) / 256), 256, 0, st>>>(ca);
+        ctx->launches.fetch_add(1);
+    }
     CUDA_TRY(cudaGetLastError());
     if (!c->on_device) {
         int rc = EXON_GPU_OK;
