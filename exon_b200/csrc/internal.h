@@ -45,6 +45,7 @@ struct Ctx {
     // NCCL (dlopen'ed lazily; see nccl.cu)
     void *nccl_comm = nullptr;
     int nccl_ranks = 0;
+    void *peer_xchg = nullptr;  // scalar all-reduce over peer memory (nccl.cu), NULL: NCCL only
 
     int get_block(size_t min_bytes, DevBlock *out);
     void put_block(DevBlock b);
@@ -55,6 +56,8 @@ struct Ctx {
 void nccl_teardown(Ctx *c);
 // in-place sum all-reduce of n int64 in device memory, enqueued on the context's stream
 int nccl_allreduce_i64(Ctx *c, int64_t *device_buf, size_t n);
+// out = sum over ranks of *in through the peers' exchange buffers (c->peer_xchg != NULL); *err is set on a timeout
+int peer_allreduce_i64(Ctx *c, const int64_t *in, int64_t *out, unsigned long long *err);
 
 // A region whose chrom bytes are owned (the caller's exon_gpu_region may go away).
 struct OwnedRegion {

@@ -5,7 +5,9 @@
 #include <mutex>
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "internal.h"
 
@@ -15,7 +17,7 @@ namespace {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclInt64 = 4, ncclFloat64 = 8, ncclSum = 0 };
+enum { ncclUint8 = 1, ncclInt32 = 2, ncclInt64 = 4, ncclFloat64 = 8, ncclSum = 0, ncclMin = 3 };
 
 struct NcclApi {
     void *handle = nullptr;
@@ -23,6 +25,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;  // optional (peer exchange setup)
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -45,6 +48,7 @@ int load_nccl() {
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
     g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(h, "ncclGroupStart");
     g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
@@ -67,7 +71,138 @@ int load_nccl() {
     } while (0)
 }  // namespace
 
+// ---- scalar all-reduce over peer memory ------------------------------------------------------------------------------
+// The final aggregate of the headline query is ONE int64 per rank.  A separate NCCL launch for it costs ~90 us per step at
+// 8 GPUs (measured: step 0.689 ms against a 0.571 ms scan); here every rank stores its partial straight into a slot of
+// every peer's exchange buffer over NVLink (CUDA IPC mappings set up once at exon_gpu_nccl_init), publishes it with a
+// sequence number behind a system-scope fence, and sums the slots of its own buffer as they arrive.
+//   slot layout (per rank): [2 parities][n ranks] x {value, seq}; parity = seq & 1 so that a rank that runs one step ahead
+//   never overwrites values a peer is still reading (it cannot run two ahead: every step needs everybody's contribution)
+// NCCL stays the fallback (setup failure on any rank, EXON_GPU_PEER_XCHG=0) and the path for vectors / float state.
+struct PeerXchg {
+    int n = 0, rank = 0;
+    unsigned long long *local = nullptr;       // this rank's slots (cudaMalloc, IPC-exported)
+    unsigned long long **d_peers = nullptr;    // device array: peer p's slots as mapped here (d_peers[rank] == local)
+    std::vector<void *> opened;                // IPC mappings to close
+    unsigned long long seq = 0;
+};
+
+__global__ void peer_allreduce_i64_kernel(unsigned long long *const *peers, int n, int rank, const long long *in, long long *out,
+                                          unsigned long long seq, unsigned long long *err) {
+    const int p = threadIdx.x;
+    const size_t par = (size_t)(seq & 1ull);
+    long long part = 0;
+    bool ok = true;
+    if (p < n) {
+        const long long v = *in;
+        volatile unsigned long long *theirs = peers[p] + (par * n + rank) * 2;
+        theirs[0] = (unsigned long long)v;
+        __threadfence_system();
+        theirs[1] = seq;
+        volatile unsigned long long *mine = peers[rank] + (par * n + p) * 2;
+        const long long t0 = clock64();
+        while (mine[1] != seq) {
+            if (clock64() - t0 > (4ll << 30)) {  // ~2 s: a peer died or never launched
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+        part = ok ? (long long)mine[0] : 0;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+    const bool all_ok = __all_sync(0xFFFFFFFFu, ok);
+    if (p == 0) {
+        *out = part;
+        if (!all_ok) *err = 1ull;
+    }
+}
+
+static void peer_xchg_teardown(Ctx *c) {
+    auto *x = static_cast<PeerXchg *>(c->peer_xchg);
+    if (!x) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void *p : x->opened) cudaIpcCloseMemHandle(p);
+    cudaFree(x->d_peers);
+    cudaFree(x->local);
+    delete x;
+    c->peer_xchg = nullptr;
+}
+
+// Collective over the communicator: every rank calls it; the exchange is enabled only when it worked everywhere.
+static void peer_xchg_setup(Ctx *c, int n, int rank) {
+    if (n < 2) return;  // every rank sees the same n: nobody waits in the collectives below
+    const char *e = getenv("EXON_GPU_PEER_XCHG");
+    bool want = !(e && atoi(e) == 0) && n <= 32 && g_nccl.AllGather;
+    auto *x = new PeerXchg();
+    x->n = n;
+    x->rank = rank;
+    int ok = want ? 1 : 0;
+    uint8_t *d_h = nullptr;
+    std::vector<uint8_t> all((size_t)n * sizeof(cudaIpcMemHandle_t));
+    if (ok && (cudaMalloc((void **)&x->local, (size_t)2 * n * 16) != cudaSuccess || cudaMemset(x->local, 0, (size_t)2 * n * 16) != cudaSuccess)) ok = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) ok = 0;  // the slots are zero before anybody can learn their address
+    if (cudaMalloc((void **)&d_h, all.size() + 64) != cudaSuccess) ok = 0, d_h = nullptr;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine, x->local) != cudaSuccess) ok = 0;
+    // handles travel with ncclAllGather (every rank takes part, whatever its own state, so that nobody is left waiting)
+    if (d_h) {
+        cudaMemcpyAsync(d_h + all.size(), &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream);
+        if (g_nccl.AllGather && g_nccl.AllGather(d_h + all.size(), d_h, sizeof(mine), ncclUint8, (ncclComm_t)c->nccl_comm, c->stream) != 0) ok = 0;
+        cudaMemcpyAsync(all.data(), d_h, all.size(), cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) ok = 0;
+    }
+    std::vector<unsigned long long *> peers((size_t)n, nullptr);
+    if (ok) {
+        for (int p = 0; p < n && ok; ++p) {
+            if (p == rank) {
+                peers[(size_t)p] = x->local;
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + (size_t)p * sizeof(h), sizeof(h));
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = 0;
+                break;
+            }
+            x->opened.push_back(ptr);
+            peers[(size_t)p] = (unsigned long long *)ptr;
+        }
+        if (ok && (cudaMalloc((void **)&x->d_peers, (size_t)n * 8) != cudaSuccess ||
+                   cudaMemcpy(x->d_peers, peers.data(), (size_t)n * 8, cudaMemcpyHostToDevice) != cudaSuccess))
+            ok = 0;
+    }
+    cudaGetLastError();  // a failed IPC call must not poison later launches
+    // agree: min over ranks of `ok` (also the barrier that orders every rank's memset before anybody's first store)
+    int agreed = 0;
+    if (d_h) {
+        cudaMemcpyAsync(d_h, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream);
+        if (g_nccl.AllReduce(d_h, d_h, 1, ncclInt32, ncclMin, (ncclComm_t)c->nccl_comm, c->stream) == 0) {
+            cudaMemcpyAsync(&agreed, d_h, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess) agreed = 0;
+        }
+        cudaFree(d_h);
+    }
+    c->peer_xchg = x;
+    if (!agreed) peer_xchg_teardown(c);
+}
+
+// out = sum over ranks of *in (device pointers), enqueued on the context's stream; *err (device) is set on a timeout
+int peer_allreduce_i64(Ctx *c, const int64_t *in, int64_t *out, unsigned long long *err) {
+    auto *x = static_cast<PeerXchg *>(c->peer_xchg);
+    ++x->seq;
+    peer_allreduce_i64_kernel<<<1, 32, 0, c->stream>>>(x->d_peers, x->n, x->rank, (const long long *)in, (long long *)out, x->seq, err);
+    c->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return EXON_GPU_OK;
+}
+
 void nccl_teardown(Ctx *c) {
+    peer_xchg_teardown(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c->nccl_comm);
     c->nccl_comm = nullptr;
 }
@@ -105,6 +240,7 @@ int exon_gpu_nccl_init(exon_gpu_ctx *c, const uint8_t id[EXON_GPU_NCCL_ID_BYTES]
     NCCL_TRY(g_nccl.CommInitRank(&comm, n_ranks, u, rank));
     c->nccl_comm = comm;
     c->nccl_ranks = n_ranks;
+    peer_xchg_setup(c, n_ranks, rank);
     return EXON_GPU_OK;
 }
 

@@ -380,10 +380,17 @@ int VcfStream::filter_count_global(const exon_gpu_region *region, int64_t *out_l
     int64_t *d_local = reinterpret_cast<int64_t *>(d_res + 4), *d_global = reinterpret_cast<int64_t *>(d_res + 5);
     const int rc = filter_count(region, d_local, nullptr);
     if (rc != EXON_GPU_OK) CUDA_TRY(cudaMemsetAsync(d_local, 0, sizeof(int64_t), ctx->stream));  // still take part
-    CUDA_TRY(cudaMemcpyAsync(d_global, d_local, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    if (int rc2 = nccl_allreduce_i64(ctx, d_global, 1)) return rc2;
+    if (ctx->peer_xchg) {
+        // one tiny kernel behind the scan: partials cross NVLink as plain stores into the peers' slots (nccl.cu)
+        CUDA_TRY(cudaMemsetAsync(d_res + 6, 0, sizeof(unsigned long long), ctx->stream));
+        if (int rc2 = peer_allreduce_i64(ctx, d_local, d_global, d_res + 6)) return rc2;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(d_global, d_local, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (int rc2 = nccl_allreduce_i64(ctx, d_global, 1)) return rc2;
+    }
     CUDA_TRY(cudaMemcpyAsync(h_res, d_res, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->peer_xchg && h_res[6]) return fail(EXON_GPU_ERR_NCCL, "peer exchange timed out: a rank did not deliver its partial");
     if (rc != EXON_GPU_OK) return rc;
     const uint32_t flags = (uint32_t)h_res[last_eager ? 3 : 1];
     if (flags)
