@@ -1,23 +1,16 @@
-// bgzf.cu -- BGZF / gzip inflate on the device.
+// bgzf.cu -- BGZF / gzip framing and the host side of the device inflate.
 //
 // Replaces the CPU DEFLATE the reference runs in front of every parser: noodles-bgzf 0.34 `AsyncReader` /
 // async-compression `GzipDecoder` at exon/exon-core/src/datasources/vcf/file_opener/unindex_file_opener.rs:59-73,
 // exon/exon-core/src/streaming_bgzf.rs:22-118 (block framing), fastq/file_opener.rs:51.  A BGZF file is a series
 // of independent gzip members of <= 64 KiB uncompressed data each (SAM spec 4.1), so members decode in parallel:
-// the host walks the member headers (18 bytes per member, no payload byte is touched), the compressed bytes go
-// to HBM as they are, and a GROUP OF 16 LANES (two members per warp) inflates one member straight into the arena:
-//   * the group's first lane runs the serial part -- bit reader over 4-byte aligned words, dynamic/fixed Huffman
-//     headers, symbol decode through a 9-bit primary table in shared memory (canonical bit-by-bit decode for longer
-//     codes) -- and emits up to 32 tokens (literal | length, distance) with their output positions;
-//   * the group then executes the tokens in output order: runs of literals are stored by up to 16 lanes at once, a
-//     match is copied by all lanes (period-aware when distance < length) through a 1 KiB shared-memory ring of the
-//     most recent output when distance + length <= 1024, else through L2 (st.cg / ld.cg); group barriers order
-//     dependent matches;
-//   * the primary tables are filled by all lanes of the group (each resolves table indices with the canonical decoder).
-// Measured on 100M-row VCF text (42k members): 8 / 16 / 32 lanes per member -> 64 / 44 / 54 ms; 16 is the default.
-// Members of several files share one launch (VcfStream::flush_gz).
-// Thousands of members are in flight at once (warps_per_SM x 148), which is where the throughput comes from.
-// Plain single-member gzip (not BGZF) is handled by the same kernel with one warp (serial by nature).
+// the host walks the member headers (18 bytes per member, no payload byte is touched; bgzf_walk), the compressed bytes
+// travel to HBM as they are on a copy stream into double-buffered staging (gz_stage), and the members of many files are
+// inflated by ONE launch of the two kernels of inflate.cu straight into the arena (launch_gz) while the next group's bytes
+// are still on their way; launched groups are checked (stream errors, ISIZE) and framed at the next query (harvest_gz).
+// Plain single-member gzip (not BGZF) takes the same path as one member.
+// The first cut of this file also held a one-kernel inflate (16 lanes per member: 44 ms per 2.75 GB); inflate.cu replaced
+// it (19 ms) and it was removed.
 // Output is bit-exact DEFLATE (RFC 1951): tests compare with zlib on the reference's .gz fixtures and on
 // synthetic shards; ISIZE of every member is checked, CRC32 is not (documented in DESIGN.md).
 #include <algorithm>
@@ -35,430 +28,6 @@ namespace exon {
             return fail(_e == cudaErrorMemoryAllocation ? EXON_GPU_ERR_OOM : EXON_GPU_ERR_CUDA, "%s: %s", \
                         #expr, cudaGetErrorString(_e));                                                  \
     } while (0)
-
-namespace {
-
-constexpr int kInfWarps = 4;      // warps per CTA
-constexpr int kG = 16;            // lanes that work on one member (one decodes, all copy)
-constexpr int kGroups = 32 / kG;  // members in flight per warp
-constexpr int kLitBits = 9;       // primary table of the literal/length code
-constexpr int kDistBits = 7;      // primary table of the distance code
-constexpr int kTokens = 32;
-constexpr int kRing = 1024;       // recent output mirrored in shared memory (matches mostly reach back < 1 KiB in text)
-
-__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-__constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-
-struct MemberSmem {
-    uint16_t lit_tab[1 << kLitBits];  // sym << 4 | len, 0 = code longer than kLitBits
-    uint16_t dist_tab[1 << kDistBits];
-    uint16_t lit_sym[288];            // symbols in canonical order
-    uint16_t lit_cnt[16];             // codes per length
-    uint16_t dist_sym[32];
-    uint16_t dist_cnt[16];
-    uint16_t cl_sym[19];
-    uint16_t cl_cnt[16];
-    union {                           // the code lengths are dead once the tables exist; the tokens live only afterwards
-        uint8_t lens[320];            // code lengths of the block being set up (HLIT + HDIST)
-        struct {
-            uint32_t tok[kTokens];    // literal: 0x80000000 | byte; match: len | dist << 9 (positions follow from the order)
-        };
-    };
-    uint8_t ring[kRing];              // ring[p % kRing] = output byte p, for the most recent positions
-};
-
-// LSB-first bit reader over 4-byte aligned words (the decoding lane only).
-struct BitReader {
-    const uint32_t *wp;  // next aligned word
-    const uint8_t *base; // where this reader started
-    uint64_t buf;
-    int cnt;             // valid bits in buf
-    int64_t loaded;      // bits loaded so far
-    __device__ __forceinline__ void init(const uint8_t *p) {
-        base = p;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-        const int mis = (int)(a & 3);
-        wp = reinterpret_cast<const uint32_t *>(a - mis);
-        buf = (uint64_t)(__ldg(wp++) >> (8 * mis));
-        cnt = 32 - 8 * mis;
-        loaded = cnt;
-    }
-    __device__ __forceinline__ void refill() {  // afterwards cnt >= 33
-        while (cnt <= 32) {
-            buf |= (uint64_t)__ldg(wp++) << cnt;
-            cnt += 32;
-            loaded += 32;
-        }
-    }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1u); }
-    __device__ __forceinline__ void drop(int n) {
-        buf >>= n;
-        cnt -= n;
-    }
-    __device__ __forceinline__ uint32_t take(int n) {
-        const uint32_t v = peek(n);
-        drop(n);
-        return v;
-    }
-    __device__ __forceinline__ int64_t bits_consumed() const { return loaded - cnt; }
-};
-
-// Canonical decode of the code that starts at bit 0 of `bits` (stream order = LSB first), at most `maxlen` bits.
-// Returns sym | len << 16, or 0xFFFFFFFF when no code of <= maxlen bits matches.
-__device__ __forceinline__ uint32_t canon_decode(uint32_t bits, const uint16_t *cnt, const uint16_t *sym, int maxlen) {
-    int code = 0, first = 0, index = 0;
-    for (int len = 1; len <= maxlen; ++len) {
-        code |= (int)(bits & 1u);
-        bits >>= 1;
-        const int c = cnt[len];
-        if (code - c < first) return (uint32_t)sym[index + (code - first)] | ((uint32_t)len << 16);
-        index += c;
-        first += c;
-        first <<= 1;
-        code <<= 1;
-    }
-    return 0xFFFFFFFFu;
-}
-
-// decoding lane: counts per length and the canonical symbol order from lens[0..n); false on an over-subscribed code
-__device__ bool canon_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym) {
-    for (int l = 0; l < 16; ++l) cnt[l] = 0;
-    for (int s = 0; s < n; ++s) cnt[lens[s]]++;
-    int left = 1;
-    for (int l = 1; l < 16; ++l) {
-        left <<= 1;
-        left -= cnt[l];
-        if (left < 0) return false;
-    }
-    uint16_t offs[16];
-    offs[1] = 0;
-    for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + cnt[l]);
-    for (int s = 0; s < n; ++s)
-        if (lens[s]) sym[offs[lens[s]]++] = (uint16_t)s;
-    cnt[0] = 0;
-    return true;
-}
-
-// all lanes of the group: primary table[i] = sym << 4 | len for every index whose leading code has <= bits bits, else 0
-__device__ __forceinline__ void fill_primary(uint16_t *tab, int bits, const uint16_t *cnt, const uint16_t *sym, int gl) {
-    for (int i = gl; i < (1 << bits); i += kG) {
-        const uint32_t r = canon_decode((uint32_t)i, cnt, sym, bits);
-        tab[i] = r == 0xFFFFFFFFu ? (uint16_t)0 : (uint16_t)(((r & 0xFFFFu) << 4) | (r >> 16));
-    }
-}
-
-constexpr uint32_t kInfErrData = 1u;    // invalid DEFLATE data
-constexpr uint32_t kInfErrSize = 2u;    // output does not match ISIZE
-
-#define GSHFL(v) __shfl_sync(gmask, (v), 0, kG)
-
-__global__ void __launch_bounds__(kInfWarps * 32) bgzf_inflate_kernel(const uint8_t *comp, const BgzfMember *members, int n_members,
-                                                                      uint32_t *flags, int *first_bad) {
-    extern __shared__ __align__(16) uint8_t inf_smem_raw[];
-    MemberSmem *all = reinterpret_cast<MemberSmem *>(inf_smem_raw);
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (kG - 1);                   // lane inside the group
-    const int group = (int)(threadIdx.x / kG);        // group inside the CTA
-    const uint32_t gmask = (kG == 32 ? 0xFFFFFFFFu : ((1u << (kG & 31)) - 1u)) << (lane & ~(kG - 1));
-    MemberSmem &S = all[group];
-    const int gg = blockIdx.x * (kInfWarps * kGroups) + group, ng = gridDim.x * (kInfWarps * kGroups);
-#pragma unroll 1
-    for (int mi = gg; mi < n_members; mi += ng) {
-        const BgzfMember M = members[mi];
-        if (M.isize == 0) continue;
-        uint8_t *out = reinterpret_cast<uint8_t *>((uintptr_t)M.out_addr);
-        const uint32_t isize = M.isize;
-        BitReader br;
-        if (gl == 0) br.init(comp + M.in_off);
-        uint32_t pos = 0;     // decoding lane: bytes produced
-        uint32_t err = 0;     // group-uniform after every broadcast
-        bool last = false;
-#pragma unroll 1
-        while (!last && !err) {
-            // ---- block header (decoding lane) ----
-            int btype = 0;
-            if (gl == 0) {
-                br.refill();
-                last = br.take(1) != 0;
-                btype = (int)br.take(2);
-                // a stream that runs past its payload (no final block where the member ends) is corrupt
-                if (br.base + (br.bits_consumed() >> 3) > comp + M.in_off + M.in_len) btype = 3;
-            }
-            last = GSHFL((int)last) != 0;
-            btype = GSHFL(btype);
-            if (btype == 0) {
-                // stored: skip to the byte boundary, LEN / NLEN, then a cooperative byte copy
-                uint32_t len = 0, p0 = 0;
-                unsigned long long src_addr = 0;
-                if (gl == 0) {
-                    br.drop(br.cnt & 7);
-                    br.refill();
-                    len = br.take(16);
-                    const uint32_t nlen = br.take(16);
-                    if ((len ^ nlen) != 0xFFFFu || pos + len > isize) err = kInfErrData;
-                    src_addr = (unsigned long long)reinterpret_cast<uintptr_t>(br.base + (br.bits_consumed() >> 3));
-                    p0 = pos;
-                }
-                err = GSHFL(err);
-                if (err) break;
-                len = GSHFL(len);
-                src_addr = GSHFL(src_addr);
-                p0 = GSHFL(p0);
-                const uint8_t *src = reinterpret_cast<const uint8_t *>((uintptr_t)src_addr);
-                for (uint32_t j = gl; j < len; j += kG) {
-                    const uint8_t b = __ldg(src + j);
-                    __stcg(out + p0 + j, b);
-                    S.ring[(p0 + j) & (kRing - 1)] = b;
-                }
-                if (gl == 0) {
-                    pos += len;
-                    br.init(src + len);
-                }
-                __syncwarp(gmask);
-                continue;
-            }
-            if (btype == 3) {
-                err = kInfErrData;
-                break;
-            }
-            // ---- code lengths -> S.lens (decoding lane), then tables (all lanes of the group) ----
-            if (gl == 0) {
-                if (btype == 1) {
-                    for (int s = 0; s < 144; ++s) S.lens[s] = 8;
-                    for (int s = 144; s < 256; ++s) S.lens[s] = 9;
-                    for (int s = 256; s < 280; ++s) S.lens[s] = 7;
-                    for (int s = 280; s < 288; ++s) S.lens[s] = 8;
-                    for (int s = 0; s < 30; ++s) S.lens[288 + s] = 5;
-                } else {
-                    br.refill();
-                    const int nlit = (int)br.take(5) + 257;
-                    const int ndist = (int)br.take(5) + 1;
-                    const int ncl = (int)br.take(4) + 4;
-                    uint8_t cl[19];
-                    for (int i = 0; i < 19; ++i) cl[i] = 0;
-                    for (int i = 0; i < ncl; ++i) {
-                        br.refill();
-                        cl[c_clen_order[i]] = (uint8_t)br.take(3);
-                    }
-                    if (nlit > 286 || ndist > 30 || !canon_build(cl, 19, S.cl_cnt, S.cl_sym)) err = kInfErrData;
-                    int i = 0;
-                    while (!err && i < nlit + ndist) {
-                        br.refill();
-                        const uint32_t r = canon_decode((uint32_t)br.buf, S.cl_cnt, S.cl_sym, 7);
-                        if (r == 0xFFFFFFFFu) {
-                            err = kInfErrData;
-                            break;
-                        }
-                        br.drop((int)(r >> 16));
-                        const int sym = (int)(r & 0xFFFFu);
-                        if (sym < 16) {
-                            S.lens[i++] = (uint8_t)sym;
-                        } else {
-                            int rep, val = 0;
-                            if (sym == 16) {
-                                if (i == 0) {
-                                    err = kInfErrData;
-                                    break;
-                                }
-                                val = S.lens[i - 1];
-                                rep = 3 + (int)br.take(2);
-                            } else if (sym == 17) {
-                                rep = 3 + (int)br.take(3);
-                            } else {
-                                rep = 11 + (int)br.take(7);
-                            }
-                            if (i + rep > nlit + ndist) {
-                                err = kInfErrData;
-                                break;
-                            }
-                            while (rep--) S.lens[i++] = (uint8_t)val;
-                        }
-                    }
-                    if (!err && S.lens[256] == 0) err = kInfErrData;  // no end-of-block code
-                    // distance lengths follow the literal/length lengths: move them to a fixed place
-                    if (!err) {
-                        uint8_t tmp[30];
-                        for (int s = 0; s < ndist; ++s) tmp[s] = S.lens[nlit + s];
-                        for (int s = nlit; s < 288; ++s) S.lens[s] = 0;
-                        for (int s = 0; s < 30; ++s) S.lens[288 + s] = s < ndist ? tmp[s] : 0;
-                    }
-                }
-                if (!err) {
-                    // an incomplete distance code with a single symbol is legal (RFC 1951 3.2.7); over-subscription is not
-                    if (!canon_build(S.lens, 288, S.lit_cnt, S.lit_sym) || !canon_build(S.lens + 288, 30, S.dist_cnt, S.dist_sym))
-                        err = kInfErrData;
-                }
-            }
-            err = GSHFL(err);
-            if (err) break;
-            __syncwarp(gmask);
-            fill_primary(S.lit_tab, kLitBits, S.lit_cnt, S.lit_sym, gl);
-            fill_primary(S.dist_tab, kDistBits, S.dist_cnt, S.dist_sym, gl);
-            __syncwarp(gmask);
-
-            // ---- symbols: the decoding lane fills a batch of tokens, the group executes it ----
-            bool eob = false;
-#pragma unroll 1
-            while (!eob && !err) {
-                int n = 0;
-                uint32_t batch_start = 0;
-                if (gl == 0) {
-                    batch_start = pos;
-                    while (n < kTokens) {
-                        br.refill();
-                        uint32_t e = S.lit_tab[br.peek(kLitBits)];
-                        // literal run: short codes come straight from the primary table for as long as the bits left
-                        // still cover a full length / distance symbol afterwards (no refill, no range checks per byte)
-                        bool again = false;
-                        while ((e - 1u) < 4095u) {  // e != 0 and symbol < 256
-                            br.drop((int)(e & 15u));
-                            S.tok[n++] = 0x80000000u | (e >> 4);
-                            ++pos;
-                            if (n >= kTokens || br.cnt < 29) {
-                                again = true;
-                                break;
-                            }
-                            e = S.lit_tab[br.peek(kLitBits)];
-                        }
-                        if (again) continue;
-                        int sym;
-                        if (e) {
-                            br.drop((int)(e & 15u));
-                            sym = (int)(e >> 4);
-                        } else {
-                            const uint32_t r = canon_decode((uint32_t)br.buf, S.lit_cnt, S.lit_sym, 15);
-                            if (r == 0xFFFFFFFFu) {
-                                err = kInfErrData;
-                                break;
-                            }
-                            br.drop((int)(r >> 16));
-                            sym = (int)(r & 0xFFFFu);
-                        }
-                        if (sym < 256) {
-                            S.tok[n] = 0x80000000u | (uint32_t)sym;
-                            pos += 1;
-                        } else if (sym == 256) {
-                            eob = true;
-                            break;
-                        } else {
-                            sym -= 257;
-                            if (sym >= 29) {
-                                err = kInfErrData;
-                                break;
-                            }
-                            const uint32_t len = c_len_base[sym] + br.take(c_len_extra[sym]);
-                            br.refill();
-                            e = S.dist_tab[br.peek(kDistBits)];
-                            int ds;
-                            if (e) {
-                                br.drop((int)(e & 15u));
-                                ds = (int)(e >> 4);
-                            } else {
-                                const uint32_t r = canon_decode((uint32_t)br.buf, S.dist_cnt, S.dist_sym, 15);
-                                if (r == 0xFFFFFFFFu) {
-                                    err = kInfErrData;
-                                    break;
-                                }
-                                br.drop((int)(r >> 16));
-                                ds = (int)(r & 0xFFFFu);
-                            }
-                            if (ds >= 30) {
-                                err = kInfErrData;
-                                break;
-                            }
-                            const uint32_t dist = c_dist_base[ds] + br.take(c_dist_extra[ds]);
-                            if (dist > pos) {
-                                err = kInfErrData;
-                                break;
-                            }
-                            S.tok[n] = len | (dist << 9);
-                            pos += len;
-                        }
-                        ++n;
-                        if (pos > isize) {
-                            err = kInfErrData;
-                            break;
-                        }
-                    }
-                    if (pos > isize) err = kInfErrData;
-                }
-                n = GSHFL(n);
-                eob = GSHFL((int)eob) != 0;
-                err = GSHFL(err);
-                batch_start = GSHFL(batch_start);
-                if (err) break;
-                __syncwarp(gmask);
-                // execute, strictly in output order so that the ring always holds the latest kRing positions: runs of
-                // literals are stored by up to kG lanes at once; a match whose source and destination both fit the ring
-                // (distance + length <= kRing) is copied through shared memory, older sources come from L2
-                // (st.cg / ld.cg), with a group barrier around every match.
-                const int gbase = lane & ~(kG - 1);
-                int k = 0;
-                uint32_t p = batch_start;  // output position of token k (group-uniform)
-#pragma unroll 1
-                while (k < n) {
-                    const int kk = k + gl;
-                    const uint32_t t = kk < n ? S.tok[kk] : 0u;
-                    const uint32_t lit = (__ballot_sync(gmask, (t & 0x80000000u) != 0u) >> gbase) & (kG == 32 ? 0xFFFFFFFFu : ((1u << (kG & 31)) - 1u));
-                    const int run = ~lit ? __ffs((int)~lit) - 1 : 32;  // literals at the head of the next kG tokens
-                    if (run > 0) {
-                        if (gl < run) {
-                            __stcg(out + p + gl, (uint8_t)t);
-                            S.ring[(p + gl) & (kRing - 1)] = (uint8_t)t;
-                        }
-                        k += run;
-                        p += (uint32_t)run;
-                        continue;
-                    }
-                    __syncwarp(gmask);  // everything before this match is in place
-                    const uint32_t tm = S.tok[k], len = tm & 511u, dist = tm >> 9;
-                    const uint32_t s0 = p - dist;
-                    if (dist + len <= (uint32_t)kRing) {
-                        if (dist >= len) {
-                            for (uint32_t j = gl; j < len; j += kG) {
-                                const uint8_t b = S.ring[(s0 + j) & (kRing - 1)];
-                                __stcg(out + p + j, b);
-                                S.ring[(p + j) & (kRing - 1)] = b;
-                            }
-                        } else {
-                            for (uint32_t j = gl; j < len; j += kG) {
-                                const uint8_t b = S.ring[(s0 + (j % dist)) & (kRing - 1)];
-                                __stcg(out + p + j, b);
-                                S.ring[(p + j) & (kRing - 1)] = b;
-                            }
-                        }
-                    } else {
-                        const uint8_t *src = out + s0;
-                        for (uint32_t j = gl; j < len; j += kG) {
-                            const uint8_t b = __ldcg(src + (dist >= len ? j : j % dist));
-                            __stcg(out + p + j, b);
-                            S.ring[(p + j) & (kRing - 1)] = b;
-                        }
-                    }
-                    p += len;
-                    __syncwarp(gmask);
-                    k += 1;
-                }
-                __syncwarp(gmask);
-            }
-        }
-        if (gl == 0 && !err && pos != isize) err = kInfErrSize;
-        err = GSHFL(err);
-        if (err && gl == 0) {
-            atomicOr(flags, err);
-            atomicMin(first_bad, mi);
-        }
-        __syncwarp(gmask);
-    }
-}
-#undef GSHFL
-
-constexpr size_t kInfSmem = sizeof(MemberSmem) * kInfWarps * kGroups;
-
-}  // namespace
 
 // Parses the gzip member that starts at data[p]: payload range, ISIZE, and where the next member starts.  BGZF members
 // carry their size in the 'BC' extra subfield; a member without it (plain gzip) is taken to extend to the end of the data.
@@ -511,24 +80,6 @@ int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uin
         p = next;
     }
     *total_out = uo;
-    return EXON_GPU_OK;
-}
-
-// Enqueues the inflate of `n_members` members (table in device memory; in_off relative to d_comp, out_addr absolute)
-// on the context's stream.  d_flags: two words of device scratch, {0, INT_MAX} before the launch.
-int bgzf_inflate_launch_v1(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags) {
-    if (n_members <= 0) return EXON_GPU_OK;
-    static int occ = 0;
-    if (!occ) {
-        CUDA_TRY(cudaFuncSetAttribute(bgzf_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInfSmem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel, kInfWarps * 32, kInfSmem));
-        if (occ < 1) occ = 1;
-    }
-    const int per_cta = kInfWarps * kGroups;
-    const int grid = std::min((n_members + per_cta - 1) / per_cta, occ * c->sm_count);
-    bgzf_inflate_kernel<<<grid, kInfWarps * 32, kInfSmem, c->stream>>>(d_comp, d_table, n_members, d_flags, (int *)(d_flags + 1));
-    c->launches.fetch_add(1);
-    CUDA_TRY(cudaGetLastError());
     return EXON_GPU_OK;
 }
 

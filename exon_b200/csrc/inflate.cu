@@ -594,11 +594,6 @@ size_t bgzf_assign_bitmap(BgzfMember *m, size_t n) {
 int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words,
                         size_t comp_bytes) {
     if (n_members <= 0) return EXON_GPU_OK;
-    static const int use_v1 = [] {
-        const char *e = getenv("EXON_GPU_INFLATE_V1");
-        return e && atoi(e) ? 1 : 0;
-    }();
-    if (use_v1) return bgzf_inflate_launch_v1(c, d_comp, d_table, n_members, d_flags);
     const size_t bm_bytes = (bitmap_words + 64) * sizeof(uint32_t);
     if (bm_bytes > c->inf_bitmap_cap) {
         if (c->inf_bitmap) {

@@ -250,7 +250,6 @@ int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uin
 size_t bgzf_assign_bitmap(BgzfMember *m, size_t n);
 int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words,
                         size_t comp_bytes);
-int bgzf_inflate_launch_v1(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags);
 
 // defined in bam.cu
 void bam_columns_free(VcfStream *s);
