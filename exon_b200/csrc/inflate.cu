@@ -6,19 +6,22 @@
 // halves are separate kernels with the layout each one wants:
 //
 //   K_dec  inflate_decode_kernel   ONE LANE PER MEMBER, 32 members per warp in lock step.  Each lane runs the bit reader
-//          (two 32-bit words + one prefetched, peek = one funnel shift), builds its own primary tables in shared
-//          memory (lit/len 2^LB entries, distance 2^DB entries; longer codes fall back to a canonical walk over
-//          per-lane arrays in local memory), and writes
+//          (two 32-bit words + one prefetched, peek = one funnel shift; the stream's next L1 line is requested ahead),
+//          builds its own tables in shared memory (lit/len 2^LB x u16, distance 2^7 x u8, plus the canonical limits and
+//          offsets of the lengths 8..15: a code longer than the primary table costs two shared loads, a branch-free
+//          length search and one dependent local load of the symbol), and writes
 //            * every LITERAL byte straight to its final place in the output, and
 //            * every MATCH as a 3-byte token (len - 3 | (dist - 1) << 8) INTO THE FIRST THREE BYTES OF THE MATCH'S OWN
 //              OUTPUT RANGE (a match is >= 3 bytes, so the token always fits and needs no memory of its own), plus
 //              one bit per match start in a bitmap (1 bit per output byte).
+//          LB = 8 puts 320 lanes on an SM, LB = 9 decodes faster per lane: chosen per launch (bgzf_inflate_launch).
 //   K_copy inflate_copy_kernel     ONE WARP PER MEMBER.  Walks the output in 1 KiB segments kept in a 4 KiB shared-memory
 //          ring: loads the segment (literals in place), turns the segment's bitmap words into a list of match
-//          positions, reads all tokens at once (one lane per match), copies every match whose source lies wholly
-//          before the segment in parallel (one lane per match, source from the ring or, beyond 3 KiB back, from L2),
-//          executes the remaining (dependent) matches in order with all 32 lanes, and writes the finished segment
-//          back with 16-byte stores.  A match that crosses the segment end is continued in the next segment.
+//          positions, requests the lines of every source that lies behind the ring, reads the tokens (one lane per
+//          match), copies every match whose source lies wholly before the segment in parallel (one lane per match),
+//          executes the remaining (dependent) matches in output order with all 32 lanes -- found 32 at a time by
+//          ballot --, and writes the finished segment back with 16-byte stores.  A match that crosses the segment end
+//          is continued in the next segment.
 //
 // Output is bit-exact DEFLATE; ISIZE of every member is checked, CRC32 is not.
 #include <algorithm>
