@@ -102,7 +102,8 @@ __global__ void peer_allreduce_i64_kernel(unsigned long long *const *peers, int 
         volatile unsigned long long *mine = peers[rank] + (par * n + p) * 2;
         const long long t0 = clock64();
         while (mine[1] != seq) {
-            if (clock64() - t0 > (4ll << 30)) {  // ~2 s: a peer died or never launched
+            if (clock64() - t0 > 240000000000ll) {  // ~2 minutes: a peer died or never launched (ranks may reach their first
+                                                    // exchange seconds apart; NCCL would wait for ever, this gives up late)
                 ok = false;
                 break;
             }
