@@ -509,8 +509,10 @@ int64_t exo_vcf_gz_filter_count_files(const uint8_t *const *datas, const int64_t
  *   col 4 alt    (:190-204)  empty -> NULL; else `append(true)` WITHOUT any child value: an empty list
  *   col 5 qual   (:205-208)  "." -> NULL, else f32 (correctly rounded; Rust grammar checked here, then strtof)
  *   col 6 filter (:209-216)  always a valid list: "." -> [], else one item per ';'-separated filter
- * No reference test prints these five columns; the restatement is pinned only by an independent Python split of
- * the fixtures (tests/test_vcf_wide_golden.py) and, for qual, by exact rational arithmetic.
+ * PARITY UNPINNED for these five columns: no reference test prints them and the reference cannot be run here, so the
+ * restatement is checked only against an independent Python split of the reference's fixtures
+ * (tests/test_vcf_wide_golden.py) and, for qual, against exact rational arithmetic (Rust's f32::from_str is specified to
+ * round correctly).  DESIGN.md section 2 says the same.
  * Whole file at once (the tests cut it into batches): flat arrays, all malloc'ed, freed by exo_vcf_wide_free.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
