@@ -1,7 +1,9 @@
 #!/usr/bin/env python
-"""bench.py -- VCF region filter (chrom='1' AND pos BETWEEN 1000000 AND 2000000) + COUNT over 100M synthetic
-variants per GPU (BASELINE.json configs[2]); one rank per GPU, weak scaling, one all-reduce of the int64 partial per
-step (exchanged over peer memory / NVLink by the library, NCCL as its fallback).
+"""bench.py -- VCF region filter (chrom='1' AND pos BETWEEN 1000000 AND 2000000) + COUNT over ONE set of 100M
+synthetic variants in 64 shard files (BASELINE.json configs[2]); one rank per GPU.  Default = strong scaling: the files
+are assigned to the ranks by the reference's own file -> partition rule (regroup_files_by_size) and the int64 partials
+are exchanged in the scan kernel's tail over peer memory / NVLink (NCCL as fallback); the weak series (every rank scans
+the whole set) is reported next to it under `other_series`.
 
     python bench.py --gpus 1 --steps 50 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
@@ -36,13 +38,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=100_000_000, help="variants per GPU (BASELINE config: 100M)")
+    ap.add_argument("--rows", type=int, default=100_000_000, help="variants in the file set (BASELINE config: 100M)")
     ap.add_argument("--shards", type=int, default=64)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): ONE --rows file set, files assigned to ranks by the reference's regroup_files_by_size "
+                         "rule; weak: every rank scans the whole set. The other series is reported under its own key.")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (exon_gpu_vcf_opts.kernel_variant)")
-    ap.add_argument("--strict", type=int, default=0)
+    ap.add_argument("--strict", type=int, default=1,
+                    help="1 (default, what INTEGRATION.md opens the stream with): every row's CHROM/POS is validated like the "
+                         "reference's builder does; 0: only rows whose CHROM matches are validated (same counts on valid input)")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extra", action="store_true", help="also time strict mode, COUNT(*) and the column build")
+    ap.add_argument("--extra", action="store_true", help="also time COUNT(*), interval-only and the column builds")
     return ap.parse_args()
 
 
@@ -113,11 +120,14 @@ def cpu_rows_per_sec(files, rows_per_file, cores, target_s, steps=1, warmup=0):
     seconds per step)."""
     import oracle
 
-    t0 = time.perf_counter()
-    oracle.filter_count_files(files[:1], *QUERY, target_partitions=1)
-    t1 = max(time.perf_counter() - t0, 1e-4)  # one file, one core
-    n = int(max(cores, min(len(files), round(target_s * cores / t1))))
-    n = min(len(files), (n // cores) * cores if n >= cores else n)
+    if target_s is None:
+        n = len(files)
+    else:
+        t0 = time.perf_counter()
+        oracle.filter_count_files(files[:1], *QUERY, target_partitions=1)
+        t1 = max(time.perf_counter() - t0, 1e-4)  # one file, one core
+        n = int(max(cores, min(len(files), round(target_s * cores / t1))))
+        n = min(len(files), (n // cores) * cores if n >= cores else n)
     sample = files[:n]
     for _ in range(warmup):
         oracle.filter_count_files(sample, *QUERY, target_partitions=cores)
@@ -131,34 +141,28 @@ def cpu_rows_per_sec(files, rows_per_file, cores, target_s, steps=1, warmup=0):
     return rows / dt, f"{n} of {len(files)} shard files ({rows} rows), {cores} worker threads, page-cache resident", dt
 
 
+def make_files(args, n_files=None, alloc=None):
+    """The synthetic file set of the workload (same on every rank): (columns, files, rows per file)."""
+    from synth import vcf
+
+    cols = vcf.columns(args.rows)
+    bounds = vcf.shard_bounds(cols.n, args.shards)
+    files = vcf.shards(cols, args.shards, alloc=alloc)
+    return cols, files, bounds
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from synth import vcf
-
     cores = os.cpu_count() or 1
-    cols = vcf.columns(args.rows)
-    bounds = vcf.shard_bounds(cols.n, args.shards)
-    # only the sampled prefix of the shard list is ever touched: materialise a bounded number of files
-    n_make = min(args.shards, max(cores, 16))
-    sub = vcf.VcfColumns(cols.contig[: bounds[n_make - 1][1]], cols.pos[: bounds[n_make - 1][1]],
-                         cols.ref[: bounds[n_make - 1][1]], cols.alt[: bounds[n_make - 1][1]],
-                         cols.qual[: bounds[n_make - 1][1]], cols.contigs)
-    files = []
-    hdr = vcf.header_text(cols.contigs)
-    import numpy as np
-
-    for lo, hi in bounds[:n_make]:
-        buf = np.empty(len(hdr) + (hi - lo) * vcf.MAX_LINE, dtype=np.uint8)
-        buf[: len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
-        w = vcf.format_rows(sub, lo, hi, buf[len(hdr):])
-        files.append(buf[: len(hdr) + w])
-    rows_per_file = [hi - lo for lo, hi in bounds[:n_make]]
-    v, sample, dt = cpu_rows_per_sec(files, rows_per_file, cores, target_s=1.5, steps=args.steps, warmup=args.warmup)
+    cols, files, bounds = make_files(args)
+    rows_per_file = [hi - lo for lo, hi in bounds]
+    # the whole file set, every step: one worker per file partition on all host cores (the reference's own parallelism)
+    v, sample, dt = cpu_rows_per_sec(files, rows_per_file, cores, target_s=None, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rows/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": workload_config(args),
             "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -170,11 +174,14 @@ def run_reference(args):
 
 
 def workload_config(args):
+    n = args.gpus
     return {"workload": f"VCF region filter chrom='1' AND pos BETWEEN 1000000 AND 2000000 + COUNT(*), "
-                        f"{args.rows} synthetic variants per GPU in {args.shards} shard files (BASELINE configs[2])",
-            "rows_per_gpu": args.rows, "shards_per_gpu": args.shards, "batch_rows": 8192,
-            "parallelism": f"file-shard x{args.gpus}, one int64 all-reduce per step (peer-memory exchange over NVLink, NCCL fallback)" if args.gpus > 1 else "1 GPU",
-            "l2": "input (~2.75 GB per GPU) is >20x the 126 MB L2; no flush needed between steps"}
+                        f"{args.rows} synthetic variants in {args.shards} shard files (BASELINE configs[2])",
+            "rows": args.rows, "shards": args.shards, "batch_rows": 8192,
+            "parallelism": (f"{args.scaling} scaling: the {args.shards} files are assigned to {n} ranks by regroup_files_by_size "
+                            f"(exon_file_scan_config.rs:79-110); the int64 partials are exchanged over peer memory (NVLink) in "
+                            f"the scan kernel's tail, NCCL as fallback") if n > 1 else "1 GPU",
+            "l2": "input per GPU (2.75 GB / N ranks) stays > 2.7x the 126 MB L2 at N = 8; no flush needed between steps"}
 
 
 # ---- GPU arm ------------------------------------------------------------------------------------------------
@@ -183,9 +190,8 @@ def run_b200(args):
     import numpy as np
     import torch
 
-    from exon_b200 import _abi
+    from exon_b200 import _abi, sharding
     from exon_b200.runtime import Context
-    from synth import vcf
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,49 +209,58 @@ def run_b200(args):
     tstream = torch.cuda.Stream()
     ctx = Context(local, cuda_stream=tstream.cuda_stream)
     if world > 1:
-        from exon_b200 import sharding
-
         sharding.init_final_aggregate(ctx, dist, rank, world)
 
-    # ---- synthetic workload: this rank's file group (seed differs per rank), pinned on the host ----
+    # ---- the synthetic file set (identical on every rank) and this rank's share of it ----
     t_gen = time.perf_counter()
-    cols = vcf.columns(args.rows, seed=vcf.SEED + rank)
-    pins = []
-
-    def alloc(nb):
-        p = ctx.pinned(nb)
-        pins.append(p)
-        return p.array
-
-    files = vcf.shards(cols, args.shards, alloc=alloc)
-    truth = cols.truth_count(*QUERY)
-    rows_per_file = [hi - lo for lo, hi in vcf.shard_bounds(cols.n, args.shards)]
-    n_rows = cols.n
-    del cols
+    cols, files, bounds = make_files(args)
+    rows_per_file = [hi - lo for lo, hi in bounds]
+    sizes = [int(f.size) for f in files]
+    mine = sharding.files_of_rank(sizes, rank, world)  # regroup_files_by_size: the reference's file -> partition rule
+    chrom_idx = [c for c, _ in cols.contigs].index(QUERY[0])
+    hit = (cols.contig == chrom_idx) & (cols.pos >= QUERY[1]) & (cols.pos <= QUERY[2])
+    truth_file = [int(hit[lo:hi].sum()) for lo, hi in bounds]
+    truth_all, truth_mine = int(sum(truth_file)), int(sum(truth_file[i] for i in mine))
+    n_rows_all, n_rows_mine = cols.n, int(sum(rows_per_file[i] for i in mine))
+    del cols, hit
     t_gen = time.perf_counter() - t_gen
     region = _abi.make_region(*QUERY)
-    total_file_bytes = int(sum(f.size for f in files))
 
-    # ---- resident copy in HBM, fed zero-copy (one run per shard file) ----
+    # ---- resident copies in HBM, fed zero-copy (one run per shard file): the whole set, and this rank's share ----
     dbufs = []
-    resident = ctx.open_vcf(projection=(0, 1), kernel_variant=args.variant, strict=bool(args.strict))
     for f in files:
         d = ctx.device_buffer(f.size)
         d.upload(f)
         dbufs.append(d)
-        resident.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
-    body_bytes = resident.body_bytes()
+
+    def open_resident(idx, strict):
+        st = ctx.open_vcf(projection=(0, 1), kernel_variant=args.variant, strict=bool(strict))
+        for i in idx:
+            st.feed(None, device_ptr=dbufs[i].ptr, nbytes=files[i].size, is_last=True)
+        return st
+
+    everything = list(range(len(files)))
+    strong = args.scaling == "strong"
+    head_idx = mine if strong else everything
+    head = open_resident(head_idx, args.strict)
+    head_bytes = head.body_bytes()
+    head_rows_total = n_rows_all if strong else world * n_rows_all  # rows ALL ranks process per step
+    head_truth_local = truth_mine if strong else truth_all
+    head_truth_global = truth_all if strong else world * truth_all
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
+    def stepper(stream):
         if world > 1:
-            return resident.filter_count_global(region)
-        c = resident.filter_count(region)
-        return c, c
+            return lambda: stream.filter_count_global(region)
+
+        def one():
+            c = stream.filter_count(region)
+            return c, c
+        return one
 
     def timed(fn, steps, warmup, sampler=None):
         barrier()  # ranks finish generating / uploading their shards at different times
@@ -253,158 +268,138 @@ def run_b200(args):
             fn()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        kms, out = [], None
+        out = None
         l0 = ctx.launch_count()
         if sampler:
             sampler.__enter__()
         ev0.record(tstream)
         for _ in range(steps):
             out = fn()
-            kms.append(ctx.last_kernel_ms())
         ev1.record(tstream)
         barrier()
         if sampler:
             sampler.__exit__()
         ms = ev0.elapsed_time(ev1)
+        # device time of each launch of the region: CUDA events the library records around the kernel on its stream
+        kms = ctx.kernel_ms_history(min(steps, 64))
         if dist is not None:
             t = torch.tensor([ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms / steps, kms, out, ctx.launch_count() - l0
 
-    sampler = ClockSampler(local)
-    ms_step, kms, (loc, glob), launches = timed(step, args.steps, max(args.warmup, 3), sampler)
-    assert loc == truth, f"rank {rank}: GPU count {loc} != generator truth {truth}"
-    truths = [truth]
-    if dist is not None:
-        t = torch.tensor([truth], device="cuda", dtype=torch.int64)
-        dist.all_reduce(t)
-        truths = [int(t.item())]
-    assert glob == truths[0], f"global count {glob} != sum of per-rank truths {truths[0]}"
-    kernel_ms = float(np.mean(kms))
-    value = world * n_rows / (ms_step * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    traffic_table = {}
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic_table = json.load(open(tp))
 
-    # ---- end to end through the C ABI with host buffers: H2D of every shard inside the timed region ----
+    def roofline_of(kms, body_bytes, ms_step, mode):
+        kernel_ms = float(np.mean(kms))
+        achieved = body_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tj = traffic_table.get(mode) if isinstance(traffic_table.get(mode), dict) else None
+        if tj and tj.get("rows") == args.rows and world == 1:
+            traffic = tj.get("dram_bytes_per_launch")
+        return {"bound": "hbm", "kernel": "vcf_scan_kernel", "mode": mode, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": body_bytes, "bytes_per_row": body_bytes / max(1, (n_rows_mine if strong else n_rows_all)),
+                "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    mode_name = {0: "lazy", 1: "strict"}
+    sampler = ClockSampler(local)
+    ms_step, kms, (loc, glob), launches = timed(stepper(head), args.steps, max(args.warmup, 3), sampler)
+    assert loc == head_truth_local, f"rank {rank}: GPU count {loc} != generator truth {head_truth_local}"
+    assert glob == head_truth_global, f"global count {glob} != generator truth {head_truth_global}"
+    value = head_rows_total / (ms_step * 1e-3)
+    roofline = roofline_of(kms, head_bytes, ms_step, mode_name[int(bool(args.strict))])
+
+    # ---- the other validation mode on the same resident bytes (same counts on valid input) ----
+    other = open_resident(head_idx, not args.strict)
+    o_ms, o_kms, (o_loc, o_glob), _ = timed(stepper(other), args.steps, 3)
+    assert o_loc == head_truth_local and o_glob == head_truth_global
+    other_mode = mode_name[int(not args.strict)]
+    modes = {roofline["mode"]: {"ms_per_step": ms_step, "value": value, "roofline": roofline},
+             other_mode: {"ms_per_step": o_ms, "value": head_rows_total / (o_ms * 1e-3),
+                          "roofline": roofline_of(o_kms, head_bytes, o_ms, other_mode)}}
+    other.close()
+
+    # ---- the other scaling series (N > 1): weak = every rank scans the whole set, strong = its share ----
+    series = None
+    if world > 1:
+        alt_idx = everything if strong else mine
+        alt = open_resident(alt_idx, args.strict)
+        a_ms, a_kms, (a_loc, a_glob), _ = timed(stepper(alt), args.steps, 3)
+        a_rows = world * n_rows_all if strong else n_rows_all
+        assert a_loc == (truth_all if strong else truth_mine) and a_glob == (world * truth_all if strong else truth_all)
+        series = {"scaling": "weak" if strong else "strong", "value": a_rows / (a_ms * 1e-3), "ms_per_step": a_ms,
+                  "kernel_ms": float(np.mean(a_kms)), "rows_per_step_all_ranks": a_rows}
+        alt.close()
+
+    # ---- end to end through the C ABI with host buffers: H2D of this rank's shard files inside the timed region ----
+    pins = []
+    e2e_files = []
+    for i in head_idx:
+        p = ctx.pinned(files[i].size)
+        p.array[:] = files[i]
+        pins.append(p)
+        e2e_files.append(p.array)
+    e2e_bytes = int(sum(f.size for f in e2e_files))
     e2e_stream = ctx.open_vcf(projection=(0, 1), kernel_variant=args.variant, strict=bool(args.strict), pushdown=region)
 
     def e2e_step():
         e2e_stream.reset()
-        for f in files:  # views of the pinned allocations, trimmed to each file's length
+        for f in e2e_files:
             e2e_stream.feed(f, is_last=True)
         if world > 1:
             return e2e_stream.filter_count_global(region)
         c = e2e_stream.filter_count(region)
         return c, c
 
-    e2e_ms, _, (eloc, eglob), _ = timed(e2e_step, max(1, min(args.e2e_steps, args.steps)), 2)
-    assert eloc == truth and eglob == glob
-    e2e = {"value": world * n_rows / (e2e_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": total_file_bytes,
-           "d2h_bytes_per_step": 64, "ms_per_step": e2e_ms, "steps": max(1, min(args.e2e_steps, args.steps)),
-           "api": "exon_gpu_vcf_feed(host pinned, per shard file) + exon_gpu_vcf_filter_count (pushdown declared)"}
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    e2e_ms, _, (eloc, eglob), _ = timed(e2e_step, e2e_steps, 2)
+    assert eloc == head_truth_local and eglob == head_truth_global
 
-    # ---- roofline of the dominant (only) kernel in the step ----
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
-    else:
-        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    achieved = body_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
-        tj = json.load(open(tp))
-        if tj.get("rows") == n_rows and tj.get("variant") == args.variant:
-            traffic = tj.get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "vcf_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": body_bytes, "bytes_per_row": body_bytes / n_rows,
-                "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step,
-                "frac_of_nominal_8TBs": achieved / 8000.0}
+    # the bare host->device copy of the same pinned bytes on every rank at once: the ceiling e2e can reach on this box
+    def h2d_only():
+        for f, i in zip(e2e_files, head_idx):
+            dbufs[i].upload_async(f)
+        ctx.synchronize()
+        return 0, 0
+
+    h2d_ms, _, _, _ = timed(h2d_only, 3, 1)
+    e2e = {"value": head_rows_total / (e2e_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": e2e_bytes,
+           "d2h_bytes_per_step": 64, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "h2d_gbs_per_gpu": e2e_bytes / e2e_ms / 1e6, "h2d_ceiling_gbs_per_gpu": e2e_bytes / h2d_ms / 1e6,
+           "h2d_ceiling_note": "bare cudaMemcpyAsync of the same pinned bytes, all ranks at once (max over ranks)",
+           "api": "exon_gpu_vcf_feed(host pinned, per shard file) + exon_gpu_vcf_filter_count" + ("_global" if world > 1 else "") + " (pushdown declared)"}
 
     line = {"metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": workload_config(args),
-            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": sampler.summary(),
+            "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "modes": modes, "clocks": sampler.summary(),
             "count": glob, "count_matches_truth": True, "gen_seconds": t_gen,
-            "kernel_variant": args.variant, "strict": int(args.strict)}
+            "kernel_variant": args.variant, "strict": int(args.strict),
+            "files_of_rank0": len(mine), "rows_of_rank0": n_rows_mine}
+    if series:
+        line["other_series"] = series
 
     if args.extra:
-        extra = {}
-        with ctx.open_vcf(projection=(0, 1), kernel_variant=args.variant, strict=True) as st:
-            for d, f in zip(dbufs, files):
-                st.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
-            for name, rg in [("strict", region), ("count_star", None), ("interval_only", _abi.make_region(None, *QUERY[1:]))]:
-                src = st if name == "strict" else resident
-                ms, k, _, _ = timed(lambda: (src.filter_count(rg),) * 2, 10, 3)
-                extra[name] = {"ms_per_step": ms, "kernel_ms": float(np.mean(k)),
-                               "gbs": body_bytes / (float(np.mean(k)) * 1e-3) / 1e9}
-        # K2: text -> Arrow {chrom, pos} batches left in device memory (second build = steady state: scratch areas
-        # warm); K3: FilterExec + COUNT over all of those batches in one launch (exon_gpu_vcf_filter_agg)
-        col_bytes = None
-        for rep in range(2):
-            with ctx.open_vcf(projection=(0, 1), columns_on_device=True) as st:
-                for d, f in zip(dbufs, files):
-                    st.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
-                e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
-                torch.cuda.synchronize()
-                l0 = ctx.launch_count()
-                e0.record(tstream)
-                first = st.next_batch()          # builds every column of the resident partition
-                e1.record(tstream)
-                torch.cuda.synchronize()
-                k2_ms, k2_launches = e0.elapsed_time(e1), ctx.launch_count() - l0
-                first.release()
-                if rep == 0:
-                    continue
-                batches = -(-n_rows // 8192)
-                col_bytes = 4 * (n_rows + batches) + 8 * n_rows + int(1.3 * n_rows)  # offsets + pos + ~chrom bytes
-                extra["k2_columns"] = {"ms": k2_ms, "rows_per_s": n_rows / k2_ms * 1e3, "launches": k2_launches,
-                                       "algorithmic_bytes": body_bytes + col_bytes,
-                                       "algorithmic_gbs": (body_bytes + col_bytes) / k2_ms / 1e6,
-                                       "frac_of_measured_peak": (body_bytes + col_bytes) / k2_ms / 1e6 / peak}
-                def k3():
-                    c, _, _ = st.filter_agg(chrom_col=0, pos_col=1, region=region)
-                    return c, c
-                ms, k, (cnt, _), nl = timed(k3, 20, 3)
-                assert cnt == truth
-                kk = float(np.mean(k))
-                extra["k3_filter_count_columns"] = {"ms_per_step": ms, "kernel_ms": kk, "launches_per_step": nl / 20,
-                                                    "rows_per_s": n_rows / ms * 1e3, "algorithmic_bytes": col_bytes,
-                                                    "algorithmic_gbs": col_bytes / kk / 1e6,
-                                                    "frac_of_measured_peak": col_bytes / kk / 1e6 / peak}
-        # wide columns: text -> Arrow {id, ref, alt, qual, filter} (vcf_wide.cu), device resident, second build timed
-        for rep in range(2):
-            with ctx.open_vcf(projection=(2, 3, 4, 5, 6), columns_on_device=True) as st:
-                for d, f in zip(dbufs, files):
-                    st.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
-                e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
-                torch.cuda.synchronize()
-                l0 = ctx.launch_count()
-                e0.record(tstream)
-                first = st.next_batch()
-                e1.record(tstream)
-                torch.cuda.synchronize()
-                w_ms, w_launches = e0.elapsed_time(e1), ctx.launch_count() - l0
-                first.release()
-                if rep == 1:
-                    batches = -(-n_rows // 8192)
-                    # id: validity + list offsets (all NULL here); ref: offsets + 1 B; alt: validity; qual: validity + f32;
-                    # filter: list offsets + child offsets + "PASS"
-                    out_bytes = 3 * n_rows // 8 + 4 * 3 * (n_rows + batches) + n_rows + 4 * n_rows + 4 * (n_rows + batches) + 4 * n_rows
-                    extra["wide_columns_2_6"] = {"ms": w_ms, "rows_per_s": n_rows / w_ms * 1e3, "launches": w_launches,
-                                                 "algorithmic_bytes": body_bytes + out_bytes,
-                                                 "algorithmic_gbs": (body_bytes + out_bytes) / w_ms / 1e6,
-                                                 "frac_of_measured_peak": (body_bytes + out_bytes) / w_ms / 1e6 / peak}
-        line["extra"] = extra
+        line["extra"] = extra_measurements(args, ctx, tstream, timed, dbufs, files, region, n_rows_all, truth_all, peak)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, sample, _ = cpu_rows_per_sec(files, rows_per_file, cores, target_s=12.0)
-        line["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample}
+        v, sample, _ = cpu_rows_per_sec(files, rows_per_file, cores, target_s=None, steps=3, warmup=2)
+        line["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample + "; 2 warm-up + 3 timed passes"}
     elif rank == 0:
         line["cpu_baseline"] = None
 
-    resident.close()
+    head.close()
     e2e_stream.close()
     for d in dbufs:
         d.free()
@@ -417,6 +412,82 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def extra_measurements(args, ctx, tstream, timed, dbufs, files, region, n_rows, truth, peak):
+    """COUNT(*), interval-only, K2 / K3 / wide column builds over the whole resident set (1 GPU)."""
+    import numpy as np
+    import torch
+
+    from exon_b200 import _abi
+
+    extra = {}
+    with ctx.open_vcf(projection=(0, 1), kernel_variant=args.variant, strict=False) as st:
+        for d, f in zip(dbufs, files):
+            st.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+        body_bytes = st.body_bytes()
+        for name, rg in [("count_star", None), ("interval_only", _abi.make_region(None, *QUERY[1:]))]:
+            ms, k, _, _ = timed(lambda: (st.filter_count(rg),) * 2, 10, 3)
+            extra[name] = {"ms_per_step": ms, "kernel_ms": float(np.mean(k)),
+                           "gbs": body_bytes / (float(np.mean(k)) * 1e-3) / 1e9}
+    # K2: text -> Arrow {chrom, pos} batches left in device memory (second build = steady state: scratch areas
+    # warm); K3: FilterExec + COUNT over all of those batches in one launch (exon_gpu_vcf_filter_agg)
+    for rep in range(2):
+        with ctx.open_vcf(projection=(0, 1), columns_on_device=True) as st:
+            for d, f in zip(dbufs, files):
+                st.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+            e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+            torch.cuda.synchronize()
+            l0 = ctx.launch_count()
+            e0.record(tstream)
+            first = st.next_batch()          # builds every column of the resident partition
+            e1.record(tstream)
+            torch.cuda.synchronize()
+            k2_ms, k2_launches = e0.elapsed_time(e1), ctx.launch_count() - l0
+            first.release()
+            if rep == 0:
+                continue
+            batches = -(-n_rows // 8192)
+            col_bytes = 4 * (n_rows + batches) + 8 * n_rows + int(1.3 * n_rows)  # offsets + pos + ~chrom bytes
+            extra["k2_columns"] = {"ms": k2_ms, "rows_per_s": n_rows / k2_ms * 1e3, "launches": k2_launches,
+                                   "algorithmic_bytes": body_bytes + col_bytes,
+                                   "algorithmic_gbs": (body_bytes + col_bytes) / k2_ms / 1e6,
+                                   "frac_of_measured_peak": (body_bytes + col_bytes) / k2_ms / 1e6 / peak}
+
+            def k3():
+                c, _, _ = st.filter_agg(chrom_col=0, pos_col=1, region=region)
+                return c, c
+            ms, k, (cnt, _), nl = timed(k3, 20, 3)
+            assert cnt == truth
+            kk = float(np.mean(k))
+            extra["k3_filter_count_columns"] = {"ms_per_step": ms, "kernel_ms": kk, "launches_per_step": nl / 20,
+                                                "rows_per_s": n_rows / ms * 1e3, "algorithmic_bytes": col_bytes,
+                                                "algorithmic_gbs": col_bytes / kk / 1e6,
+                                                "frac_of_measured_peak": col_bytes / kk / 1e6 / peak}
+    # wide columns: text -> Arrow {id, ref, alt, qual, filter} (vcf_wide.cu), device resident, second build timed
+    for rep in range(2):
+        with ctx.open_vcf(projection=(2, 3, 4, 5, 6), columns_on_device=True) as st:
+            for d, f in zip(dbufs, files):
+                st.feed(None, device_ptr=d.ptr, nbytes=f.size, is_last=True)
+            e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+            torch.cuda.synchronize()
+            l0 = ctx.launch_count()
+            e0.record(tstream)
+            first = st.next_batch()
+            e1.record(tstream)
+            torch.cuda.synchronize()
+            w_ms, w_launches = e0.elapsed_time(e1), ctx.launch_count() - l0
+            first.release()
+            if rep == 1:
+                batches = -(-n_rows // 8192)
+                # id: validity + list offsets (all NULL here); ref: offsets + 1 B; alt: validity; qual: validity + f32;
+                # filter: list offsets + child offsets + "PASS"
+                out_bytes = 3 * n_rows // 8 + 4 * 3 * (n_rows + batches) + n_rows + 4 * n_rows + 4 * (n_rows + batches) + 4 * n_rows
+                extra["wide_columns_2_6"] = {"ms": w_ms, "rows_per_s": n_rows / w_ms * 1e3, "launches": w_launches,
+                                             "algorithmic_bytes": body_bytes + out_bytes,
+                                             "algorithmic_gbs": (body_bytes + out_bytes) / w_ms / 1e6,
+                                             "frac_of_measured_peak": (body_bytes + out_bytes) / w_ms / 1e6 / peak}
+    return extra
 
 
 def main():

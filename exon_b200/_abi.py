@@ -20,8 +20,8 @@ NCCL_ID_BYTES = 128
 # Every symbol include/exon_gpu.h declares (tests/test_abi_symbols.py checks the header against this list).
 SYMBOLS = [
     "exon_gpu_last_error", "exon_gpu_version", "exon_gpu_ctx_create", "exon_gpu_ctx_destroy",
-    "exon_gpu_ctx_launch_count", "exon_gpu_ctx_last_kernel_ms", "exon_gpu_ctx_synchronize", "exon_gpu_host_alloc",
-    "exon_gpu_host_free", "exon_gpu_device_alloc", "exon_gpu_device_free", "exon_gpu_memcpy_h2d",
+    "exon_gpu_ctx_launch_count", "exon_gpu_ctx_last_kernel_ms", "exon_gpu_ctx_kernel_ms_history", "exon_gpu_ctx_synchronize", "exon_gpu_host_alloc",
+    "exon_gpu_host_free", "exon_gpu_device_alloc", "exon_gpu_device_free", "exon_gpu_memcpy_h2d", "exon_gpu_memcpy_h2d_async",
     "exon_gpu_region_parse", "exon_gpu_interval_parse", "exon_gpu_parse_f32", "exon_gpu_regroup_files_by_size", "exon_gpu_vcf_open",
     "exon_gpu_vcf_close", "exon_gpu_vcf_reset", "exon_gpu_vcf_set_header", "exon_gpu_vcf_feed", "exon_gpu_vcf_next_batch",
     "exon_gpu_vcf_filter_count", "exon_gpu_vcf_filter_count_async", "exon_gpu_vcf_rows", "exon_gpu_vcf_body_bytes",
@@ -131,12 +131,14 @@ def load():
         "exon_gpu_ctx_destroy": [vp],
         "exon_gpu_ctx_launch_count": [vp, C.POINTER(i64)],
         "exon_gpu_ctx_last_kernel_ms": [vp, C.POINTER(C.c_float)],
+        "exon_gpu_ctx_kernel_ms_history": [vp, C.POINTER(C.c_float), i32, C.POINTER(i32)],
         "exon_gpu_ctx_synchronize": [vp],
         "exon_gpu_host_alloc": [vp, C.c_size_t, C.POINTER(vp)],
         "exon_gpu_host_free": [vp, vp],
         "exon_gpu_device_alloc": [vp, C.c_size_t, C.POINTER(vp)],
         "exon_gpu_device_free": [vp, vp],
         "exon_gpu_memcpy_h2d": [vp, vp, vp, C.c_size_t],
+        "exon_gpu_memcpy_h2d_async": [vp, vp, vp, C.c_size_t],
         "exon_gpu_region_parse": [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(Region)],
         "exon_gpu_interval_parse": [C.c_char_p, C.POINTER(Region)],
         "exon_gpu_parse_f32": [C.c_char_p, C.c_size_t, C.POINTER(C.c_float)],

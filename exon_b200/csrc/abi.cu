@@ -120,8 +120,10 @@ int exon_gpu_ctx_create(int device, void *cuda_stream, exon_gpu_ctx **out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
-    cudaEventCreate(&c->ev0);
-    cudaEventCreate(&c->ev1);
+    for (int i = 0; i < Ctx::kEvRing; ++i) {
+        cudaEventCreate(&c->ev[i][0]);
+        cudaEventCreate(&c->ev[i][1]);
+    }
     *out = c;
     return EXON_GPU_OK;
 }
@@ -136,8 +138,10 @@ int exon_gpu_ctx_destroy(exon_gpu_ctx *c) {
     if (c->inf_bitmap) cudaFree(c->inf_bitmap);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     nccl_teardown(c);
-    cudaEventDestroy(c->ev0);
-    cudaEventDestroy(c->ev1);
+    for (int i = 0; i < Ctx::kEvRing; ++i) {
+        cudaEventDestroy(c->ev[i][0]);
+        cudaEventDestroy(c->ev[i][1]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return EXON_GPU_OK;
@@ -152,9 +156,29 @@ int exon_gpu_ctx_launch_count(exon_gpu_ctx *c, int64_t *out) {
 int exon_gpu_ctx_last_kernel_ms(exon_gpu_ctx *c, float *out) {
     if (!c || !out) return fail(EXON_GPU_ERR_ARG, "last_kernel_ms: NULL argument");
     if (int rc = ensure_device(c)) return rc;
-    if (!c->timed) return fail(EXON_GPU_ERR_STATE, "no fused-scan kernel has been launched on this context");
-    CUDA_TRY(cudaEventSynchronize(c->ev1));
-    CUDA_TRY(cudaEventElapsedTime(out, c->ev0, c->ev1));
+    int32_t n = 0;
+    if (int rc = exon_gpu_ctx_kernel_ms_history(c, out, 1, &n)) return rc;
+    if (n == 0) return fail(EXON_GPU_ERR_STATE, "no fused-scan kernel has been launched on this context");
+    return EXON_GPU_OK;
+}
+
+// Durations of the most recent fused-scan launches, oldest first (at most 64 are kept).  Benches read a whole timed
+// region's launches afterwards, so that no step pays for an event synchronisation.
+int exon_gpu_ctx_kernel_ms_history(exon_gpu_ctx *c, float *out, int32_t cap, int32_t *out_n) {
+    if (!c || !out_n || (!out && cap > 0) || cap < 0) return fail(EXON_GPU_ERR_ARG, "kernel_ms_history: bad argument");
+    if (int rc = ensure_device(c)) return rc;
+    int64_t count;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        count = c->ev_count;
+    }
+    int64_t n = std::min<int64_t>({count, (int64_t)Ctx::kEvRing, (int64_t)cap});
+    for (int64_t i = 0; i < n; ++i) {
+        const int slot = (int)((count - n + i) % Ctx::kEvRing);
+        CUDA_TRY(cudaEventSynchronize(c->ev[slot][1]));
+        CUDA_TRY(cudaEventElapsedTime(out + i, c->ev[slot][0], c->ev[slot][1]));
+    }
+    *out_n = (int32_t)n;
     return EXON_GPU_OK;
 }
 
@@ -193,6 +217,13 @@ int exon_gpu_memcpy_h2d(exon_gpu_ctx *c, void *dst, const void *src, size_t byte
     if (int rc = ensure_device(c)) return rc;
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return EXON_GPU_OK;
+}
+
+int exon_gpu_memcpy_h2d_async(exon_gpu_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c || (!dst && bytes) || (!src && bytes)) return fail(EXON_GPU_ERR_ARG, "memcpy_h2d_async: NULL argument");
+    if (int rc = ensure_device(c)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
     return EXON_GPU_OK;
 }
 
@@ -248,10 +279,14 @@ int exon_gpu_vcf_open(exon_gpu_ctx *c, const exon_gpu_vcf_opts *o, exon_gpu_stre
             s->has_pushdown = true;
         }
     }
-    // device + pinned result slots: [0] count, [1] flags, [2] eager accumulator, [3] eager flags
-    cudaError_t e = cudaMalloc((void **)&s->d_res, 8 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaHostAlloc((void **)&s->h_res, 8 * sizeof(unsigned long long), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_res, 0, 8 * sizeof(unsigned long long), c->stream);
+    // device accumulators + the MAPPED pinned record the scan tail publishes into (layout: internal.h)
+    cudaError_t e = cudaMalloc((void **)&s->d_res, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&s->h_res, 16 * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) {
+        memset(s->h_res, 0, 16 * sizeof(unsigned long long));
+        e = cudaHostGetDevicePointer((void **)&s->h_res_dev, s->h_res, 0);
+    }
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_res, 0, 16 * sizeof(unsigned long long), c->stream);
     if (e != cudaSuccess) {
         if (s->d_res) cudaFree(s->d_res);
         delete s;
@@ -281,7 +316,7 @@ int exon_gpu_vcf_reset(exon_gpu_stream *s) {
     if (int rc = ensure_device(s->ctx)) return rc;
     CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
     s->release_all();
-    CUDA_TRY(cudaMemsetAsync(s->d_res, 0, 8 * sizeof(unsigned long long), s->ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(s->d_res, 0, 16 * sizeof(unsigned long long), s->ctx->stream));
     return EXON_GPU_OK;
 }
 
@@ -352,6 +387,7 @@ int exon_gpu_vcf_filter_count_global(exon_gpu_stream *s, const exon_gpu_region *
                                      int64_t *out_global) {
     if (!s || (!out_local && !out_global)) return fail(EXON_GPU_ERR_ARG, "vcf_filter_count_global: NULL argument");
     if (int rc = ensure_device(s->ctx)) return rc;
+    if (!s->ctx->nccl_comm) return fail(EXON_GPU_ERR_STATE, "vcf_filter_count_global: exon_gpu_nccl_init has not been called");
     return s->filter_count_global(region, out_local, out_global);
 }
 

@@ -371,12 +371,11 @@ int VcfStream::bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, 
         a.serial = serial;
         CUDA_TRY(cudaMemsetAsync(d + bam_o_counts, 0, (size_t)n_groups * 8, st));
         CUDA_TRY(cudaMemsetAsync(d + bam_o_misc, 0, 128, st));
-        if (round == 0) CUDA_TRY(cudaEventRecord(c->ev0, st));
+        if (round == 0) CUDA_TRY(c->timed_begin(st));
         bam_walk_kernel<<<(launch_n + kBamThreads - 1) / kBamThreads, kBamThreads, 0, st>>>(a);
         bam_verify_kernel<<<(launch_n + 127) / 128, 128, 0, st>>>(ent, launch_n, a.exits, serial ? 0 : 1, d_verify);
         if (round == 0) {
-            CUDA_TRY(cudaEventRecord(c->ev1, st));
-            c->timed = true;
+            CUDA_TRY(c->timed_end(st));
         }
         c->launches.fetch_add(2);
         CUDA_TRY(cudaGetLastError());

@@ -426,10 +426,9 @@ extern "C" int exon_gpu_gzip_inflate(exon_gpu_ctx *c, const uint8_t *data, size_
     CUDA_TRY(cudaMemcpyAsync(scr + o_tab, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
     const int init_flags[2] = {0, 0x7FFFFFFF};
     CUDA_TRY(cudaMemcpyAsync(scr + o_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaEventRecord(c->ev0, st));
+    CUDA_TRY(c->timed_begin(st));
     if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), (uint32_t *)(scr + o_flags), bm_words, len)) return rc;
-    CUDA_TRY(cudaEventRecord(c->ev1, st));
-    c->timed = true;
+    CUDA_TRY(c->timed_end(st));
     CUDA_TRY(cudaMemcpyAsync(c->h_scratch, scr + o_flags, 8, cudaMemcpyDeviceToHost, st));
     if (!out_is_device) CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)total, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -125,11 +125,10 @@ int fasta_rows(VcfStream *s, int64_t *out_rows) {
     }
     int64_t grid = std::min<int64_t>((int64_t)occ * ctx->sm_count, (n_tiles + FaRing::WARPS - 1) / FaRing::WARPS);
     if (grid < 1) grid = 1;
-    CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+    CUDA_TRY(ctx->timed_begin(st));
     fasta_count_kernel<<<(unsigned)grid, FaRing::WARPS * 32, FaRing::smem_bytes, st>>>(a);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-    ctx->timed = true;
+    CUDA_TRY(ctx->timed_end(st));
     ctx->launches.fetch_add(1);
     CUDA_TRY(cudaMemcpyAsync(s->h_res, a.out, 24, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -414,15 +414,14 @@ int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *o
     a.flags = (uint32_t *)(scr + o_out + 16);
 
     static int occ_a = 0, occ_b = 0;
-    CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+    CUDA_TRY(ctx->timed_begin(st));
     CUDA_TRY(fq_launch(fq_lines_kernel, a, ctx->sm_count, st, &occ_a));
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(scr + o_cub, cub_bytes, a.tile_lines, (unsigned long long *)(scr + o_prefix), (int)(n_tiles + 1), st));
     fq_segment_table<<<(n_segs + 127) / 128, 128, 0, st>>>(a.segs, n_segs, a.tile_prefix, (const int32_t *)(scr + o_ff),
                                                            (const int32_t *)(scr + o_fn), (unsigned long long *)(scr + o_l0), a.flags);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(fq_launch(fq_filter_kernel, a, ctx->sm_count, st, &occ_b));
-    CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-    ctx->timed = true;
+    CUDA_TRY(ctx->timed_end(st));
     ctx->launches.fetch_add(4);
     CUDA_TRY(cudaMemcpyAsync(s->h_res, a.out, 24, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

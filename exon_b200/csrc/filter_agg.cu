@@ -387,14 +387,13 @@ int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, i
         if (occ < 1) occ = 1;
     }
     const int grid = (int)std::min<int64_t>(n_units, (int64_t)c->sm_count * occ);
-    if (timed) CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    if (timed) CUDA_TRY(c->timed_begin(c->stream));
     if (k.has_nulls) filter_agg_multi_kernel<true><<<grid, kFaThreads, 0, c->stream>>>(a, d_descs, n_batches, upb);
     else filter_agg_multi_kernel<false><<<grid, kFaThreads, 0, c->stream>>>(a, d_descs, n_batches, upb);
     c->launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     if (timed) {
-        CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
-        c->timed = true;
+        CUDA_TRY(c->timed_end(c->stream));
     }
     return EXON_GPU_OK;
 }

@@ -184,11 +184,10 @@ int gff_filter_count(VcfStream *s, const exon_gpu_region *region, int64_t *out_c
     }
     int64_t grid = std::min<int64_t>((int64_t)occ * ctx->sm_count, (n_tiles + GffRing::WARPS - 1) / GffRing::WARPS);
     if (grid < 1) grid = 1;
-    CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+    CUDA_TRY(ctx->timed_begin(st));
     gff_scan_kernel<<<(unsigned)grid, GffRing::WARPS * 32, GffRing::smem_bytes, st>>>(a);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-    ctx->timed = true;
+    CUDA_TRY(ctx->timed_end(st));
     ctx->launches.fetch_add(1);
     CUDA_TRY(cudaMemcpyAsync(s->h_res, a.out, 24, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -28,8 +28,25 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::atomic<int64_t> launches{0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // bracket the most recent fused-scan launch
-    bool timed = false;
+    // event pairs that bracket the most recent fused-scan launches (a ring: benches read the durations of a whole timed
+    // region afterwards instead of synchronising on every step)
+    static constexpr int kEvRing = 64;
+    cudaEvent_t ev[kEvRing][2] = {};
+    int64_t ev_count = 0;  // launches bracketed so far (guarded by mu)
+    cudaError_t timed_begin(cudaStream_t st) {
+        int slot;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            slot = (int)(ev_count % kEvRing);
+        }
+        return cudaEventRecord(ev[slot][0], st);
+    }
+    cudaError_t timed_end(cudaStream_t st) {
+        std::lock_guard<std::mutex> g(mu);
+        const cudaError_t e = cudaEventRecord(ev[ev_count % kEvRing][1], st);
+        ++ev_count;
+        return e;
+    }
     std::mutex mu;
     std::mutex work_mu;  // serialises users of the context-wide scratch areas (K2 build, K3 calls)
     std::vector<DevBlock> free_blocks;
@@ -56,8 +73,9 @@ struct Ctx {
 void nccl_teardown(Ctx *c);
 // in-place sum all-reduce of n int64 in device memory, enqueued on the context's stream
 int nccl_allreduce_i64(Ctx *c, int64_t *device_buf, size_t n);
-// out = sum over ranks of *in through the peers' exchange buffers (c->peer_xchg != NULL); *err is set on a timeout
-int peer_allreduce_i64(Ctx *c, const int64_t *in, int64_t *out, unsigned long long *err);
+// Scalar exchange over peer memory (nccl.cu): fills the peer fields of a scan tail and consumes one sequence number.
+// Returns false when the exchange is not active (single rank, setup failed somewhere, EXON_GPU_PEER_XCHG=0).
+bool peer_xchg_arm(Ctx *c, ScanTail *tail);
 
 // A region whose chrom bytes are owned (the caller's exon_gpu_region may go away).
 struct OwnedRegion {
@@ -139,8 +157,12 @@ struct VcfStream {
     bool segs_dirty = true;
     int seg_variant = -1;
     int64_t n_tiles = 0;
-    unsigned long long *d_res = nullptr;  // [0] count [1] flags [2] eager count [3] eager flags
-    unsigned long long *h_res = nullptr;  // pinned mirror
+    // device words: [0..3] ScanAcc of plain queries, [4..7] ScanAcc of the pushdown (eager) scans, [8] local count of a
+    // global query, [9] its all-reduced value (NCCL fallback), [10..15] spare
+    unsigned long long *d_res = nullptr;
+    unsigned long long *h_res = nullptr;  // MAPPED pinned: [0..7] the record the scan tail publishes (ScanHostWord), [8..15] copy targets
+    unsigned long long *h_res_dev = nullptr;  // device address of h_res
+    unsigned long long host_seq = 0;      // sequence number of the last published record
 
     // ---- column build (K2) state lives in vcf_columns.cu ----
     struct Columns *cols = nullptr;
@@ -211,8 +233,9 @@ struct VcfStream {
     int end_file();
     int filter_count(const exon_gpu_region *region, int64_t *device_out, int64_t *host_out);
     int filter_count_global(const exon_gpu_region *region, int64_t *out_local, int64_t *out_global);
-    int launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_segs, int64_t tiles, unsigned long long *d_count,
-                    unsigned long long *d_flags, bool timed);
+    int launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_segs, int64_t tiles, ScanAcc *acc, const ScanTail &tail);
+    int run_query(const exon_gpu_region *region, int64_t *device_out, bool want_host, bool global);
+    int wait_published();
     int build_seg_table();
     void cut_pieces(std::vector<Piece> &out) const;
     int eager_scan(bool final_flush);

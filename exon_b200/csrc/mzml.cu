@@ -532,7 +532,7 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
         a.n_events = d_out;
         int64_t grid = std::min<int64_t>((int64_t)occ * ctx->sm_count, (n_tiles + MzRing::WARPS - 1) / MzRing::WARPS);
         if (grid < 1) grid = 1;
-        CUDA_TRY(cudaEventRecord(ctx->ev0, st));
+        CUDA_TRY(ctx->timed_begin(st));
         mzml_events_kernel<<<(unsigned)grid, MzRing::WARPS * 32, MzRing::smem_bytes, st>>>(a);
         CUDA_TRY(cudaGetLastError());
         unsigned long long *h = (unsigned long long *)ctx->h_scratch;
@@ -626,8 +626,7 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
                                                        pred ? pred->mz_hi : 0.0, (double *)(d_out + 2), d_out + 3, (uint32_t *)(d_out + 4));
             CUDA_TRY(cudaGetLastError());
         }
-        CUDA_TRY(cudaEventRecord(ctx->ev1, st));
-        ctx->timed = true;
+        CUDA_TRY(ctx->timed_end(st));
         ctx->launches.fetch_add(3);
         CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));

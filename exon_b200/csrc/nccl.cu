@@ -73,9 +73,11 @@ int load_nccl() {
 
 // ---- scalar all-reduce over peer memory ------------------------------------------------------------------------------
 // The final aggregate of the headline query is ONE int64 per rank.  A separate NCCL launch for it costs ~90 us per step at
-// 8 GPUs (measured: step 0.689 ms against a 0.571 ms scan); here every rank stores its partial straight into a slot of
+// 8 GPUs (measured: step 0.689 ms against a 0.571 ms scan), a separate 32-thread exchange kernel + read-back still ~40 us;
+// here the LAST CTA of the scan kernel itself (vcf_scan.cu: scan_finalize) stores the rank's partial straight into a slot of
 // every peer's exchange buffer over NVLink (CUDA IPC mappings set up once at exon_gpu_nccl_init), publishes it with a
-// sequence number behind a system-scope fence, and sums the slots of its own buffer as they arrive.
+// sequence number behind a system-scope fence, sums the slots of its own buffer as they arrive and writes the result to
+// mapped host memory.  This file owns the buffers and the sequence numbers.
 //   slot layout (per rank): [2 parities][n ranks] x {value, seq}; parity = seq & 1 so that a rank that runs one step ahead
 //   never overwrites values a peer is still reading (it cannot run two ahead: every step needs everybody's contribution)
 // NCCL stays the fallback (setup failure on any rank, EXON_GPU_PEER_XCHG=0) and the path for vectors / float state.
@@ -86,39 +88,6 @@ struct PeerXchg {
     std::vector<void *> opened;                // IPC mappings to close
     unsigned long long seq = 0;
 };
-
-__global__ void peer_allreduce_i64_kernel(unsigned long long *const *peers, int n, int rank, const long long *in, long long *out,
-                                          unsigned long long seq, unsigned long long *err) {
-    const int p = threadIdx.x;
-    const size_t par = (size_t)(seq & 1ull);
-    long long part = 0;
-    bool ok = true;
-    if (p < n) {
-        const long long v = *in;
-        volatile unsigned long long *theirs = peers[p] + (par * n + rank) * 2;
-        theirs[0] = (unsigned long long)v;
-        __threadfence_system();
-        theirs[1] = seq;
-        volatile unsigned long long *mine = peers[rank] + (par * n + p) * 2;
-        const long long t0 = clock64();
-        while (mine[1] != seq) {
-            if (clock64() - t0 > 240000000000ll) {  // ~2 minutes: a peer died or never launched (ranks may reach their first
-                                                    // exchange seconds apart; NCCL would wait for ever, this gives up late)
-                ok = false;
-                break;
-            }
-        }
-        __threadfence_system();
-        part = ok ? (long long)mine[0] : 0;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
-    const bool all_ok = __all_sync(0xFFFFFFFFu, ok);
-    if (p == 0) {
-        *out = part;
-        if (!all_ok) *err = 1ull;
-    }
-}
 
 static void peer_xchg_teardown(Ctx *c) {
     auto *x = static_cast<PeerXchg *>(c->peer_xchg);
@@ -192,14 +161,17 @@ static void peer_xchg_setup(Ctx *c, int n, int rank) {
     if (!agreed) peer_xchg_teardown(c);
 }
 
-// out = sum over ranks of *in (device pointers), enqueued on the context's stream; *err (device) is set on a timeout
-int peer_allreduce_i64(Ctx *c, const int64_t *in, int64_t *out, unsigned long long *err) {
+// Fills the peer fields of a scan tail (vcf_scan.cu: scan_finalize runs the exchange inside the scan's last CTA) and
+// consumes one sequence number.  Every rank must launch exactly one tail per armed exchange, in the same order.
+bool peer_xchg_arm(Ctx *c, ScanTail *tail) {
     auto *x = static_cast<PeerXchg *>(c->peer_xchg);
-    ++x->seq;
-    peer_allreduce_i64_kernel<<<1, 32, 0, c->stream>>>(x->d_peers, x->n, x->rank, (const long long *)in, (long long *)out, x->seq, err);
-    c->launches.fetch_add(1);
-    CUDA_TRY(cudaGetLastError());
-    return EXON_GPU_OK;
+    if (!x) return false;
+    std::lock_guard<std::mutex> g(c->mu);
+    tail->n_ranks = x->n;
+    tail->rank = x->rank;
+    tail->peers = x->d_peers;
+    tail->xseq = ++x->seq;
+    return true;
 }
 
 void nccl_teardown(Ctx *c) {

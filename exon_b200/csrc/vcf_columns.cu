@@ -811,11 +811,11 @@ int columns_filter_agg(VcfStream *s, const exon_gpu_pred *pred, const exon_gpu_a
     unsigned long long *d_out = reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(c->d_descs) + table);
     CUDA_TRY(cudaMemsetAsync(d_out, 0, 64, ctx->stream));
     if (int rc = filter_agg_multi_launch(ctx, c->d_descs, (int)c->n_batches, c->batch_rows, k, d_out, true)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(s->h_res + 4, d_out, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->h_res + 8, d_out, 24, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    out->count = (int64_t)s->h_res[4];
-    out->sum_i64 = (int64_t)s->h_res[5];
-    memcpy(&out->sum_f64, &s->h_res[6], sizeof(double));
+    out->count = (int64_t)s->h_res[8];
+    out->sum_i64 = (int64_t)s->h_res[9];
+    memcpy(&out->sum_f64, &s->h_res[10], sizeof(double));
     if (k.val_type == kValI64) out->sum_f64 = (double)out->sum_i64;
     return EXON_GPU_OK;
 }

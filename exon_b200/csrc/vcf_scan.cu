@@ -9,7 +9,9 @@
 // Execution model (B200): persistent grid, every WARP runs its own S-stage pipeline.  Lane 0 posts 1-D bulk
 // async copies (cp.async.bulk -> TMA engine, SASS UBLKCP) of [16 B pre-halo | tile | 48 B post-halo] into the
 // warp's shared-memory ring and arms an mbarrier with the byte count; all lanes wait on the barrier and read
-// their 16-byte chunks with conflict-free LDS.128.  No block-wide barrier exists anywhere in the kernel.
+// their 16-byte chunks with conflict-free LDS.128.  The tile loop has no block-wide barrier; the CTA meets once, at the
+// very end, to add its partial to the query accumulator -- and the CTA that arrives last at that accumulator runs the
+// query's tail (publish to mapped host memory, exchange with the peer GPUs): one launch per query, nothing after it.
 // Tiles are numbered launch-wide across all resident segments (shard bodies) and dealt round-robin to warps,
 // so one launch covers a whole partition's file group.
 //
@@ -221,6 +223,94 @@ __device__ __forceinline__ uint32_t chunk_may_hit(const uint4 w, const uint32_t 
 }
 
 // ===================================================================================================
+// The tail: what the last CTA does after the last partial has been added (fused into K1)
+// ===================================================================================================
+// Executed by ONE full warp after every partial of the query is visible in *acc.  Publishes the partition's count,
+// exchanges it with the other ranks over peer memory and hands {local, flags, global} to the host through mapped pinned
+// memory -- one launch per query: no memset before it, no second kernel, no device-to-host copy after it.
+//   peer slots (per rank): [2 parities][n ranks] x {value, seq}; parity = seq & 1, so a rank that is one query ahead never
+//   overwrites a value a slower peer is still reading (it cannot be two ahead: every query needs everybody's partial).
+__device__ __forceinline__ void scan_finalize(ScanAcc *acc, const ScanTail &t) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long local = 0, flags = 0;
+    if (lane == 0) {
+        if (t.finalize == 1) {  // leave the accumulator zeroed for the next query on this stream
+            local = atomicExch(&acc->count, 0ull);
+            flags = atomicExch(&acc->flags, 0ull);
+            atomicExch(&acc->ticket, 0ull);
+        } else {                // pushdown accumulator: keeps growing with later feeds
+            local = atomicAdd(&acc->count, 0ull);
+            flags = atomicAdd(&acc->flags, 0ull);
+        }
+    }
+    local = __shfl_sync(0xFFFFFFFFu, local, 0);
+    flags = __shfl_sync(0xFFFFFFFFu, flags, 0);
+    unsigned long long global = local, xerr = 0;
+    if (t.n_ranks > 1) {
+        const int n = t.n_ranks, p = lane;
+        const size_t par = (size_t)(t.xseq & 1ull);
+        long long part = 0;
+        bool ok = true;
+        if (p < n) {
+            volatile unsigned long long *theirs = t.peers[p] + (par * n + t.rank) * 2;
+            theirs[0] = local;
+            __threadfence_system();
+            theirs[1] = t.xseq;
+            volatile unsigned long long *mine = t.peers[t.rank] + (par * n + p) * 2;
+            const long long t0 = clock64();
+            while (mine[1] != t.xseq) {
+                if (clock64() - t0 > 240000000000ll) {  // ~2 minutes: a peer died or never launched (ranks may reach their
+                    ok = false;                          // first exchange seconds apart); the host reports EXON_GPU_ERR_NCCL
+                    break;
+                }
+            }
+            __threadfence_system();
+            part = ok ? (long long)mine[0] : 0;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+        global = (unsigned long long)part;
+        xerr = __all_sync(0xFFFFFFFFu, ok) ? 0ull : 1ull;
+    }
+    if (lane == 0) {
+        if (t.device_out) *t.device_out = (long long)local;
+        if (t.host_out) {
+            volatile unsigned long long *h = t.host_out;
+            h[kHostLocal] = local;
+            h[kHostFlags] = flags;
+            h[kHostGlobal] = global;
+            h[kHostXchgErr] = xerr;
+            __threadfence_system();
+            h[kHostSeq] = t.host_seq;
+        }
+    }
+}
+
+// The tail on its own: queries that launch no scan (nothing resident, an unmatchable literal) or whose scans ran ahead
+// of the query (pushdown feeds) still publish / exchange through the same code.
+__global__ void __launch_bounds__(32) scan_finish_kernel(ScanAcc *acc, const ScanTail t) { scan_finalize(acc, t); }
+
+// Adds one CTA's partials to the query accumulator; in a finalising launch the CTA that arrives last runs the tail.
+// Called by warp 0 after a block-wide barrier.
+__device__ __forceinline__ void scan_block_epilogue(const ScanArgs &a, unsigned long long cnt, unsigned long long err) {
+    const int lane = threadIdx.x & 31;
+    bool last = false;
+    if (lane == 0) {
+        if (cnt) atomicAdd(&a.acc->count, cnt);
+        if (err) atomicOr(&a.acc->flags, err);
+        if (a.tail.finalize) {
+            __threadfence();
+            last = atomicAdd(&a.acc->ticket, 1ull) == (unsigned long long)gridDim.x - 1ull;
+        }
+    }
+    last = __shfl_sync(0xFFFFFFFFu, last, 0);
+    if (last) {
+        __threadfence();
+        scan_finalize(a.acc, a.tail);
+    }
+}
+
+// ===================================================================================================
 // The kernel
 // ===================================================================================================
 template <int MODE, int U, int S, int WARPS>
@@ -229,8 +319,11 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
     using L = SmemLayout<U, S, WARPS>;
     constexpr int TILE = L::TILE, STAGE = L::STAGE;
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ unsigned long long s_part[2];  // this CTA's count / error bits (the only block-wide state)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    if (threadIdx.x == 0) s_part[0] = s_part[1] = 0ull;
+    __syncthreads();
     uint8_t *ring = smem_raw + L::ring + (size_t)warp * (S * STAGE);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + L::bars) + warp * S;
     StageMeta *meta = reinterpret_cast<StageMeta *>(smem_raw + L::meta) + warp * S;
@@ -430,9 +523,11 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
     cnt = warp_sum(cnt);
     err = __reduce_or_sync(0xFFFFFFFFu, err);
     if (lane == 0) {
-        if (cnt) atomicAdd(a.out_count, (unsigned long long)cnt);
-        if (err) atomicOr(a.out_flags, err);
+        if (cnt) atomicAdd(&s_part[0], (unsigned long long)cnt);
+        if (err) atomicOr(&s_part[1], (unsigned long long)err);
     }
+    __syncthreads();  // the only barrier after the prologue: every warp has drained its tiles
+    if (warp == 0) scan_block_epilogue(a, s_part[0], s_part[1]);
 }
 
 struct Variant {
@@ -487,7 +582,11 @@ int scan_tile_bytes(int v) { return 512 * kVariants[(v >= 0 && v < kNumVariants)
 
 cudaError_t launch_vcf_scan(const ScanArgs &args, ScanMode mode, const ScanConfig &cfg, int sm_count,
                             cudaStream_t stream) {
-    if (args.n_tiles <= 0) return cudaSuccess;
+    if (args.n_tiles <= 0) {
+        if (!args.tail.finalize) return cudaSuccess;
+        scan_finish_kernel<<<1, 32, 0, stream>>>(args.acc, args.tail);
+        return cudaGetLastError();
+    }
     switch (cfg.variant) {
         case 1: return launch_mode<4, 4, 8>(args, mode, cfg.ctas, sm_count, stream);
         case 2: return launch_mode<8, 4, 4>(args, mode, cfg.ctas, sm_count, stream);

@@ -18,9 +18,36 @@ struct ScanSeg {
 
 constexpr int kMaxChrom = 255;
 
-// error bits written to ScanArgs::out_flags
+// error bits accumulated in ScanAcc::flags
 constexpr uint32_t kErrBadPos = 1u;      // POS is not a decimal usize, is 0, or overflows int64
 constexpr uint32_t kErrShortLine = 2u;   // the line ended before the field being read
+
+// Accumulator of one query in device memory.  It is zero before the first launch that adds to it; the launch that
+// finalises the query (ScanTail::finalize) leaves it zero again, so a steady-state query needs no memset.
+struct ScanAcc {
+    unsigned long long count;   // rows selected so far
+    unsigned long long flags;   // kErr* bits
+    unsigned long long ticket;  // CTAs of the finalising launch that have added their partials
+    unsigned long long pad_;
+};
+
+// Words of the result record the finalising CTA writes to MAPPED PINNED host memory (the host polls the sequence word:
+// no device-to-host copy and no stream synchronisation on the critical path of a query).
+enum ScanHostWord { kHostLocal = 0, kHostFlags = 1, kHostGlobal = 2, kHostXchgErr = 3, kHostSeq = 4, kHostWords = 8 };
+
+// What the LAST CTA of a launch does once every CTA has added its partials (vcf_scan.cu: scan_finalize): publish the
+// partition's count, exchange it with the other ranks' partials over peer memory (the final aggregate of SURVEY 8e, the
+// analogue of AggregateExec(Final) -- fused into the scan's tail, no second launch), and hand the result to the host.
+struct ScanTail {
+    int32_t finalize;              // 0: this launch only accumulates (pushdown feeds); 1: run the tail
+    int32_t n_ranks, rank;         // n_ranks >= 2: peer exchange
+    int32_t pad_;
+    long long *device_out;         // optional device copy of the local count
+    unsigned long long *host_out;  // mapped pinned record, kHostWords words (may be NULL)
+    unsigned long long host_seq;   // value written to host_out[kHostSeq] after everything else
+    unsigned long long *const *peers;  // nccl.cu: peer p's exchange slots as mapped on this device
+    unsigned long long xseq;       // sequence number of this exchange
+};
 
 struct ScanArgs {
     const ScanSeg *segs;  // device array, n_segs + 1 entries (the last one carries tile0 = n_tiles, len = 0)
@@ -31,8 +58,8 @@ struct ScanArgs {
     int32_t chrom_len;
     int32_t pat_len;             // chrom_len + 2
     uint8_t pat[kMaxChrom + 5];  // '\n' + chrom + '\t'
-    unsigned long long *out_count;
-    uint32_t *out_flags;
+    ScanAcc *acc;
+    ScanTail tail;
 };
 
 enum ScanMode {
@@ -49,7 +76,7 @@ struct ScanConfig {
 
 // bytes of body covered by one tile for `variant` (needed by the host to number tiles)
 int scan_tile_bytes(int variant);
-// Enqueue the fused scan on `stream`.  *out_count must have been zeroed on the same stream.
+// Enqueue the fused scan on `stream`.  With n_tiles == 0 and tail.finalize only the tail runs (one warp).
 cudaError_t launch_vcf_scan(const ScanArgs &args, ScanMode mode, const ScanConfig &cfg, int sm_count,
                             cudaStream_t stream);
 // registers / smem / occupancy report for DESIGN.md and tests

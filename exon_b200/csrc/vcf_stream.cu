@@ -3,6 +3,7 @@
 // exon/exon-core/src/datasources/vcf/file_opener/unindex_file_opener.rs:48-92); records are never parsed on
 // the host.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 
 #include "internal.h"
@@ -189,9 +190,9 @@ int VcfStream::frame_device_range(const uint8_t *text, size_t len, bool is_last,
         if (known_last_byte >= 0) {
             last = (uint8_t)known_last_byte;
         } else {
-            CUDA_TRY(cudaMemcpyAsync(h_res + 7, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(h_res + 12, text + len - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            last = *reinterpret_cast<const uint8_t *>(h_res + 7);
+            last = *reinterpret_cast<const uint8_t *>(h_res + 12);
         }
         if (!is_last && last != '\n')
             return fail(EXON_GPU_ERR_ARG, "vcf_feed: a non-final device range must end on a line boundary");
@@ -274,8 +275,9 @@ int VcfStream::build_seg_table() {
     return EXON_GPU_OK;
 }
 
-int VcfStream::launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_segs, int64_t tiles,
-                           unsigned long long *d_count, unsigned long long *d_flags, bool timed) {
+int VcfStream::launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_segs, int64_t tiles, ScanAcc *acc,
+                           const ScanTail &tail) {
+    if (tiles <= 0 && !tail.finalize) return EXON_GPU_OK;
     ScanArgs a;
     memset(&a, 0, sizeof(a));
     a.segs = d_table;
@@ -290,8 +292,8 @@ int VcfStream::launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_s
     a.pat[0] = '\n';
     memcpy(a.pat + 1, r.chrom.data(), r.chrom.size());
     a.pat[1 + r.chrom.size()] = '\t';
-    a.out_count = d_count;
-    a.out_flags = reinterpret_cast<uint32_t *>(d_flags);
+    a.acc = acc;
+    a.tail = tail;
     ScanMode mode;
     if (strict) mode = kScanDense;
     else if (r.has_chrom) mode = r.chrom.size() == 1 ? kScanKey3 : kScanKey4;
@@ -299,14 +301,10 @@ int VcfStream::launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_s
     ScanConfig cfg;
     cfg.variant = variant;
     cfg.ctas = 0;
-    if (tiles <= 0) return EXON_GPU_OK;
-    if (timed) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    CUDA_TRY(ctx->timed_begin(ctx->stream));
     CUDA_TRY(launch_vcf_scan(a, mode, cfg, ctx->sm_count, ctx->stream));
     ctx->launches.fetch_add(1);
-    if (timed) {
-        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-        ctx->timed = true;
-    }
+    CUDA_TRY(ctx->timed_end(ctx->stream));
     return EXON_GPU_OK;
 }
 
@@ -315,6 +313,8 @@ int VcfStream::launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_s
 int VcfStream::eager_scan(bool final_flush) {
     if (unmatchable(pushdown)) return EXON_GPU_OK;
     const int tile = scan_tile_bytes(variant);
+    ScanTail accumulate_only;
+    memset(&accumulate_only, 0, sizeof(accumulate_only));
     while (eager_runs_done < runs.size()) {
         const size_t i = eager_runs_done;
         const bool open = cur_run_open && i + 1 == runs.size();
@@ -327,7 +327,8 @@ int VcfStream::eager_scan(bool final_flush) {
             // table slots for eager launches live behind the lazy table: reuse d_segs' tail via a private buffer
             if (int rc = upload_segs(this, h)) return rc;
             segs_dirty = true;  // the lazy table was overwritten
-            if (int rc = launch_scan(pushdown, d_segs, (int)h.size() - 1, tiles, d_res + 2, d_res + 3, true)) return rc;
+            if (int rc = launch_scan(pushdown, d_segs, (int)h.size() - 1, tiles, reinterpret_cast<ScanAcc *>(d_res + 4), accumulate_only))
+                return rc;
             eager_scanned = upto;
         }
         if (open) break;  // may still grow
@@ -337,67 +338,109 @@ int VcfStream::eager_scan(bool final_flush) {
     return EXON_GPU_OK;
 }
 
-int VcfStream::filter_count(const exon_gpu_region *region, int64_t *device_out, int64_t *host_out) {
-    if (int rc = flush_gz()) return rc;
+// Waits for the record the scan tail publishes in mapped pinned memory.  The host polls the sequence word instead of
+// synchronising the stream (the wake-up of a blocking synchronise costs more than the D2H hop of one 8-byte store); the
+// stream is queried from time to time so that a failed launch turns into an error instead of a hang.
+int VcfStream::wait_published() {
+    volatile unsigned long long *h = h_res;
+    for (uint64_t spins = 1;; ++spins) {
+        if (h[kHostSeq] == host_seq) break;
+        if ((spins & 0x3FFF) == 0) {
+            const cudaError_t e = cudaStreamQuery(ctx->stream);
+            if (e == cudaSuccess) {
+                if (h[kHostSeq] == host_seq) break;
+                return fail(EXON_GPU_ERR_CUDA, "fused scan: the stream drained without publishing a result");
+            }
+            if (e != cudaErrorNotReady) return fail(EXON_GPU_ERR_CUDA, "fused scan: %s", cudaGetErrorString(e));
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return EXON_GPU_OK;
+}
+
+// One query = one launch: the scan, and in its tail the publication of the result (and, for a global query, the
+// exchange with the peer ranks).  Queries that have nothing to scan launch the tail alone, so that a rank ALWAYS takes
+// part in a global query's exchange -- a rank that skipped it would leave its peers waiting (and the sequence numbers of
+// the exchange out of step for good).
+int VcfStream::run_query(const exon_gpu_region *region, int64_t *device_out, bool want_host, bool global) {
+    ScanTail tail;
+    memset(&tail, 0, sizeof(tail));
+    tail.finalize = 1;
+    tail.device_out = reinterpret_cast<long long *>(device_out);
     OwnedRegion r;
-    if (int rc = r.assign(region)) return rc;
+    int rc = flush_gz();
+    if (rc == EXON_GPU_OK) rc = r.assign(region);
     if (r.has_interval && r.lo > r.hi) {
         // empty interval: arrow's gt_eq AND lt_eq selects nothing
         r.has_chrom = true;
         r.chrom.clear();
     }
-    const bool eager = has_pushdown && same_region(r, pushdown);
+    const bool eager = rc == EXON_GPU_OK && has_pushdown && same_region(r, pushdown);
     last_eager = eager;
-    unsigned long long *d_count = d_res, *d_flags = d_res + 1;
-    if (eager) {
-        if (int rc = eager_scan(true)) return rc;
-        d_count = d_res + 2;
-        d_flags = d_res + 3;
-        if (device_out)
-            CUDA_TRY(cudaMemcpyAsync(device_out, d_count, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    } else {
-        if (device_out) d_count = reinterpret_cast<unsigned long long *>(device_out);
-        CUDA_TRY(cudaMemsetAsync(d_res, 0, 2 * sizeof(unsigned long long), ctx->stream));
-        if (device_out) CUDA_TRY(cudaMemsetAsync(device_out, 0, sizeof(int64_t), ctx->stream));
-        if (!unmatchable(r)) {
-            if (int rc = build_seg_table()) return rc;
-            if (int rc = launch_scan(r, d_segs, (int)h_segs.size() - 1, n_tiles, d_count, d_flags, true)) return rc;
+    ScanAcc *acc = reinterpret_cast<ScanAcc *>(eager ? d_res + 4 : d_res);
+    bool scan = false;
+    if (rc == EXON_GPU_OK) {
+        if (eager) {
+            rc = eager_scan(true);
+            tail.finalize = 2;  // publish, keep accumulating
+        } else if (!unmatchable(r)) {
+            rc = build_seg_table();
+            scan = rc == EXON_GPU_OK;
         }
     }
-    if (!host_out) return EXON_GPU_OK;
-    CUDA_TRY(cudaMemcpyAsync(h_res, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(h_res + 1, d_flags, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    const uint32_t flags = (uint32_t)h_res[1];
+    bool nccl_fallback = false;
+    if (global) {
+        if (ctx->nccl_ranks > 1 && !peer_xchg_arm(ctx, &tail)) {
+            nccl_fallback = true;
+            tail.device_out = reinterpret_cast<long long *>(d_res + 8);
+        }
+    }
+    if (want_host || global) {
+        tail.host_out = h_res_dev;
+        tail.host_seq = ++host_seq;
+    }
+    if (rc != EXON_GPU_OK) {
+        // the local part failed before its launch: contribute whatever the accumulator holds (0) and report rc afterwards
+        if (global && tail.n_ranks > 1) {
+            const std::string keep = exon_gpu_last_error();
+            ScanTail t2 = tail;
+            t2.host_out = nullptr;
+            launch_scan(r, nullptr, 0, 0, acc, t2);
+            fail(rc, "%s", keep.c_str());
+        }
+        return rc;
+    }
+    if (int rc2 = launch_scan(r, scan ? d_segs : nullptr, scan ? (int)h_segs.size() - 1 : 0, scan ? n_tiles : 0, acc, tail)) return rc2;
+    if (nccl_fallback) {
+        CUDA_TRY(cudaMemcpyAsync(d_res + 9, d_res + 8, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (int rc2 = nccl_allreduce_i64(ctx, reinterpret_cast<int64_t *>(d_res + 9), 1)) return rc2;
+        CUDA_TRY(cudaMemcpyAsync(h_res + 8, d_res + 9, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    if (!(want_host || global)) return EXON_GPU_OK;
+    if (int rc2 = wait_published()) return rc2;
+    if (nccl_fallback) h_res[kHostGlobal] = h_res[8];
+    if (h_res[kHostXchgErr]) return fail(EXON_GPU_ERR_NCCL, "peer exchange timed out: a rank did not deliver its partial");
+    const uint32_t flags = (uint32_t)h_res[kHostFlags];
     if (flags)
         return fail(EXON_GPU_ERR_PARSE, "malformed VCF record:%s%s", (flags & kErrBadPos) ? " POS is not a positive decimal integer;" : "",
                     (flags & kErrShortLine) ? " line ended before the field being read;" : "");
-    *host_out = (int64_t)h_res[0];
+    return EXON_GPU_OK;
+}
+
+int VcfStream::filter_count(const exon_gpu_region *region, int64_t *device_out, int64_t *host_out) {
+    if (int rc = run_query(region, device_out, host_out != nullptr, false)) return rc;
+    if (host_out) *host_out = (int64_t)h_res[kHostLocal];
     return EXON_GPU_OK;
 }
 
 int VcfStream::filter_count_global(const exon_gpu_region *region, int64_t *out_local, int64_t *out_global) {
-    int64_t *d_local = reinterpret_cast<int64_t *>(d_res + 4), *d_global = reinterpret_cast<int64_t *>(d_res + 5);
-    const int rc = filter_count(region, d_local, nullptr);
-    if (rc != EXON_GPU_OK) CUDA_TRY(cudaMemsetAsync(d_local, 0, sizeof(int64_t), ctx->stream));  // still take part
-    if (ctx->peer_xchg) {
-        // one tiny kernel behind the scan: partials cross NVLink as plain stores into the peers' slots (nccl.cu)
-        CUDA_TRY(cudaMemsetAsync(d_res + 6, 0, sizeof(unsigned long long), ctx->stream));
-        if (int rc2 = peer_allreduce_i64(ctx, d_local, d_global, d_res + 6)) return rc2;
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(d_global, d_local, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-        if (int rc2 = nccl_allreduce_i64(ctx, d_global, 1)) return rc2;
-    }
-    CUDA_TRY(cudaMemcpyAsync(h_res, d_res, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (ctx->peer_xchg && h_res[6]) return fail(EXON_GPU_ERR_NCCL, "peer exchange timed out: a rank did not deliver its partial");
-    if (rc != EXON_GPU_OK) return rc;
-    const uint32_t flags = (uint32_t)h_res[last_eager ? 3 : 1];
-    if (flags)
-        return fail(EXON_GPU_ERR_PARSE, "malformed VCF record:%s%s", (flags & kErrBadPos) ? " POS is not a positive decimal integer;" : "",
-                    (flags & kErrShortLine) ? " line ended before the field being read;" : "");
-    if (out_local) *out_local = (int64_t)h_res[4];
-    if (out_global) *out_global = (int64_t)h_res[5];
+    if (int rc = run_query(region, nullptr, true, true)) return rc;
+    if (out_local) *out_local = (int64_t)h_res[kHostLocal];
+    if (out_global) *out_global = (int64_t)h_res[kHostGlobal];
     return EXON_GPU_OK;
 }
 

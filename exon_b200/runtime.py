@@ -49,6 +49,11 @@ class DeviceBuffer:
         assert host.dtype == np.uint8 and host.flags.c_contiguous and offset + host.size <= self.nbytes
         check(self._ctx.lib.exon_gpu_memcpy_h2d(self._ctx.handle, self.ptr + offset, host.ctypes.data, host.size))
 
+    def upload_async(self, host: np.ndarray, offset: int = 0):
+        """Enqueue the copy without waiting (pinned source; Context.synchronize() completes it)."""
+        assert host.dtype == np.uint8 and host.flags.c_contiguous and offset + host.size <= self.nbytes
+        check(self._ctx.lib.exon_gpu_memcpy_h2d_async(self._ctx.handle, self.ptr + offset, host.ctypes.data, host.size))
+
     def free(self):
         if self._ptr:
             check(self._ctx.lib.exon_gpu_device_free(self._ctx.handle, self._ptr))
@@ -85,6 +90,13 @@ class Context:
         v = C.c_float()
         check(self.lib.exon_gpu_ctx_last_kernel_ms(self.handle, C.byref(v)))
         return v.value
+
+    def kernel_ms_history(self, n: int = 64) -> list[float]:
+        """Device times of the most recent timed launches, oldest first (the library keeps 64)."""
+        buf = (C.c_float * max(n, 1))()
+        got = C.c_int32()
+        check(self.lib.exon_gpu_ctx_kernel_ms_history(self.handle, buf, n, C.byref(got)))
+        return list(buf)[: got.value]
 
     def synchronize(self):
         check(self.lib.exon_gpu_ctx_synchronize(self.handle))

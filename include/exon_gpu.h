@@ -89,6 +89,9 @@ int exon_gpu_ctx_destroy(exon_gpu_ctx *ctx);
 int exon_gpu_ctx_launch_count(exon_gpu_ctx *ctx, int64_t *out);
 /* Device time of the most recent fused-scan kernel launch, measured with CUDA events on the launching stream. */
 int exon_gpu_ctx_last_kernel_ms(exon_gpu_ctx *ctx, float *out);
+/* Device times of the most recent timed launches (oldest first, at most 64 are kept): a bench reads the launches of a
+ * whole timed region afterwards, so that no step pays for an event synchronisation.  *out_n <= cap entries are written. */
+int exon_gpu_ctx_kernel_ms_history(exon_gpu_ctx *ctx, float *out, int32_t cap, int32_t *out_n);
 int exon_gpu_ctx_synchronize(exon_gpu_ctx *ctx);
 
 /* Pinned host / device buffers for callers that want zero-staging feeds. */
@@ -97,6 +100,9 @@ int exon_gpu_host_free(exon_gpu_ctx *ctx, void *p);
 int exon_gpu_device_alloc(exon_gpu_ctx *ctx, size_t bytes, void **out);
 int exon_gpu_device_free(exon_gpu_ctx *ctx, void *p);
 int exon_gpu_memcpy_h2d(exon_gpu_ctx *ctx, void *dst_device, const void *src_host, size_t bytes);
+/* The same copy enqueued on the context's stream without waiting (src_host should be pinned and must stay valid until
+ * exon_gpu_ctx_synchronize); bench.py uses it to measure the bare host->device ceiling next to the end-to-end number. */
+int exon_gpu_memcpy_h2d_async(exon_gpu_ctx *ctx, void *dst_device, const void *src_host, size_t bytes);
 
 /* ---- region predicate (a10/a11) --------------------------------------------------------------------- */
 /* `chrom = <name> AND pos BETWEEN lo AND hi` -- 1-based, both ends inclusive
