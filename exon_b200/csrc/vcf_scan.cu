@@ -131,95 +131,144 @@ __device__ __noinline__ unsigned long long chunk_careful(const uint8_t *sm, cons
 }
 
 // ===================================================================================================
+// Pipe-aware SWAR helpers.  Measured on B200 (tools/ubench_pipes.cu, profiles/r2_ubench_pipes.txt): LOP3 / SHF / PRMT issue
+// on the ALU pipe and IMAD / IMAD.WIDE / IDP.4A on the FMA pipe, each at one warp-instruction per 2 cycles per SM
+// sub-partition, and the two pipes overlap.  K1 was ALU-bound (79 % ALU pipe, FMA idle), so byte shifts and the
+// "minus 0x01010101" of the zero-byte tests are written as multiplies: the multipliers live in registers the compiler
+// cannot see through (it would turn a constant power of two back into an ALU shift).
+// ===================================================================================================
+struct Pipes {
+    uint32_t one, m24, m16;  // 1, 2^24, 2^16
+};
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) {  // a + b (IMAD)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
+// (lo >> k) | (hi << (32 - k)) for m = 2^(32 - k): IMAD.WIDE (high half = lo >> k) + IMAD (hi * m adds hi << (32 - k))
+__device__ __forceinline__ uint32_t fma_funnel(uint32_t lo, uint32_t hi, uint32_t m) {
+    uint32_t l32, h32, r;
+    asm("{.reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t;}" : "=r"(l32), "=r"(h32) : "r"(lo), "r"(m));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "r"(m), "r"(h32));
+    return r;
+}
+constexpr uint32_t kC80 = 0x80808080u, kM01 = 0xFEFEFEFFu;  // -0x01010101
+// 0x80 in every byte lane of w that is '\n' -- exact and borrow-free: ((w ^ NL) | 0x80) - 1 clears a lane's top bit only
+// when the lane was 0x00 or 0x80, and ~w rules out 0x80 (the top bit of w ^ NL is the top bit of w).  2 ALU + 1 FMA.
+__device__ __forceinline__ uint32_t nl_flags(uint32_t w, const Pipes &P) {
+    const uint32_t t = fma_add((w ^ kNL4) | kC80, kM01, P.one);
+    return ~t & ~w & kC80;
+}
+// conservative zero-byte accumulator: h |= flags of zero bytes of z (the lowest flag of a word is exact, higher ones may be
+// borrow artefacts -- fine for a screen and for "first flag" searches).  1 FMA + 1 ALU.
+__device__ __forceinline__ uint32_t zero_acc(uint32_t h, uint32_t z, const Pipes &P) { return h | (fma_add(z, kM01, P.one) & ~z); }
+// 16 byte flags (0x80 each) -> mask with bit 7 + i set for byte i (IDP.4A x4 + IMAD: FMA pipe only)
+__device__ __forceinline__ uint32_t pack16_7(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+    uint32_t a = __dp4a(f0, 0x08040201u, 0u);
+    a = __dp4a(f1, 0x80402010u, a);
+    uint32_t b = __dp4a(f2, 0x08040201u, 0u);
+    b = __dp4a(f3, 0x80402010u, b);
+    return b * 256u + a;
+}
+
+// ===================================================================================================
 // SWAR line parser (interior tiles: every byte of the staged window belongs to the segment)
 // ===================================================================================================
 struct LineConsts {
-    uint32_t P[4], M[4];  // (window ^ P) & M == 0  <=>  window starts with chrom + '\t'
+    uint32_t P[3], M[3];  // (window ^ P) & M == 0  <=>  the line starts with chrom + '\t' (chrom of at most 11 bytes)
     uint32_t lo_lo, lo_hi, span_lo, span_hi;  // pos in [lo, lo + span]
-    int has_chrom, has_interval, wide_chrom;  // wide_chrom: the pattern reaches into window words 2..3
+    int has_chrom, has_interval, pat_words;   // pat_words: window words the pattern reaches into (1..3)
+    int p0;                                   // chrom_len + 1: where POS starts on a line whose CHROM matched
 };
 
-// Parses the line whose first byte is tile byte `ls`; `sa` is the shared-window address of tile byte 0.
-// Returns the predicate (0/1); sets `slow` when the line needs the scalar routine instead (nothing has been
-// decided or reported then).
+// Parses the line whose first byte is tile byte `ls` from a 24-byte window; `sa` is the shared-window address of tile
+// byte 0.  Returns the predicate (0/1); sets `slow` when the line needs the scalar routine instead (nothing has been decided
+// or reported then): a CHROM of more than 11 bytes, a field that leaves the window, '+', POS with a leading zero, anything
+// malformed.  STRICT: CHROM must be non-empty and POS a positive decimal on EVERY line (what the reference's builder
+// checks while it fills the columns, lazy_array_builder.rs:157-168); otherwise only a line whose CHROM matches is looked at.
 template <bool LAZY>
-__device__ __forceinline__ uint32_t line_swar(uint32_t sa, int ls, const LineConsts &K, bool &slow) {
+__device__ __forceinline__ uint32_t line_swar(uint32_t sa, int ls, const LineConsts &K, const Pipes &P, bool &slow) {
     const uint32_t la = sa + (uint32_t)ls;  // address of the line's first byte
     const uint32_t a0 = la & ~3u;
     const uint32_t sh = (la & 3u) << 3;     // tile byte 0 is 16-byte aligned
-    const uint32_t w0 = lds32(a0), w1 = lds32(a0 + 4), w2 = lds32(a0 + 8), w3 = lds32(a0 + 12), w4 = lds32(a0 + 16);
+    const uint32_t w0 = lds32(a0), w1 = lds32(a0 + 4), w2 = lds32(a0 + 8), w3 = lds32(a0 + 12), w4 = lds32(a0 + 16),
+                   w5 = lds32(a0 + 20), w6 = lds32(a0 + 24);
     const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh),
-                   v3 = __funnelshift_r(w3, w4, sh);
+                   v3 = __funnelshift_r(w3, w4, sh), v4 = __funnelshift_r(w4, w5, sh), v5 = __funnelshift_r(w5, w6, sh);
     bool chrom_ok = true;
+    int p0 = K.p0;
     if (K.has_chrom) {
-        uint32_t d = ((v0 ^ K.P[0]) & K.M[0]) | ((v1 ^ K.P[1]) & K.M[1]);
-        if (K.wide_chrom) d |= ((v2 ^ K.P[2]) & K.M[2]) | ((v3 ^ K.P[3]) & K.M[3]);
+        uint32_t d = (v0 ^ K.P[0]) & K.M[0];
+        if (K.pat_words > 1) d |= (v1 ^ K.P[1]) & K.M[1];
+        if (K.pat_words > 2) d |= (v2 ^ K.P[2]) & K.M[2];
         chrom_ok = d == 0;
         if (LAZY && !chrom_ok) return 0;
     }
     if (LAZY && !K.has_interval) return 1;
-    // separators: bytes 0x08..0x0B ('\t', '\n' and two controls that are re-checked below)
-    const uint32_t m = pack16(zero_bytes_exact((v0 & 0xFCFCFCFCu) ^ 0x08080808u), zero_bytes_exact((v1 & 0xFCFCFCFCu) ^ 0x08080808u),
-                              zero_bytes_exact((v2 & 0xFCFCFCFCu) ^ 0x08080808u), zero_bytes_exact((v3 & 0xFCFCFCFCu) ^ 0x08080808u));
-    const uint32_t m2 = m & (m - 1);
-    const int s1 = __ffs(m) - 1, s2 = __ffs(m2) - 1;
-    const int n = s2 - s1 - 1;  // digits of POS
-    if (m2 == 0 || s1 < 1 || n < 1 || n > 12 || lds8(la + s1) != '\t' || lds8(la + s2) != '\t') {
-        slow = true;
+    if (!LAZY) {
+        // first separator (bytes 0x08..0x0B) of the first 12 bytes; it must be a tab and must not be byte 0
+        const uint32_t e0 = (v0 & 0xFCFCFCFCu) ^ 0x08080808u, e1 = (v1 & 0xFCFCFCFCu) ^ 0x08080808u, e2 = (v2 & 0xFCFCFCFCu) ^ 0x08080808u;
+        const uint32_t f0 = fma_add(e0, kM01, P.one) & ~e0 & kC80, f1 = fma_add(e1, kM01, P.one) & ~e1 & kC80,
+                       f2 = fma_add(e2, kM01, P.one) & ~e2 & kC80;
+        uint32_t sm7 = __dp4a(f0, 0x08040201u, 0u);
+        sm7 = __dp4a(f1, 0x80402010u, sm7);
+        sm7 = __dp4a(f2, 0x08040201u, 0u) * 256u + sm7;
+        const int s1 = __ffs(sm7) - 8;
+        if (s1 < 1 || lds8(la + (uint32_t)s1) != '\t') {  // no separator in reach, an empty CHROM, or a line that ends early
+            slow = true;
+            return 0;
+        }
+        p0 = s1 + 1;
+    }
+    // non-digit flags of the whole window; the first one at or after p0 ends POS
+    const uint32_t d0 = v0 ^ 0x30303030u, d1 = v1 ^ 0x30303030u, d2 = v2 ^ 0x30303030u, d3 = v3 ^ 0x30303030u,
+                   d4 = v4 ^ 0x30303030u, d5 = v5 ^ 0x30303030u;
+    const uint32_t n0 = (fma_add(d0, 0x76767676u, P.one) | d0) & kC80, n1 = (fma_add(d1, 0x76767676u, P.one) | d1) & kC80,
+                   n2 = (fma_add(d2, 0x76767676u, P.one) | d2) & kC80, n3 = (fma_add(d3, 0x76767676u, P.one) | d3) & kC80,
+                   n4 = (fma_add(d4, 0x76767676u, P.one) | d4) & kC80, n5 = (fma_add(d5, 0x76767676u, P.one) | d5) & kC80;
+    uint32_t nm = pack16_7(n0, n1, n2, n3);                       // bits 7..22
+    uint32_t nh = __dp4a(n4, 0x08040201u, 0u);
+    nh = __dp4a(n5, 0x80402010u, nh);                             // bits 7..14 for bytes 16..23
+    nm += nh << 16;                                               // bits 23..30
+    const uint32_t nd = nm >> (7 + p0);
+    const int n = __ffs(nd) - 1;                                  // digits of POS
+    if (n < 1 || n > 12 || lds8(la + (uint32_t)(p0 + n)) != '\t' || lds8(la + (uint32_t)p0) == '0') {
+        slow = true;  // POS leaves the window, is empty or longer than 12 digits, starts with '+' or '0', or is not followed by a tab
         return 0;
     }
-    // the 12 bytes that end right before the second tab; the first 12 - n of them are not POS
-    const uint32_t b = la + (uint32_t)s2 - 12u;
+    if (!chrom_ok || !K.has_interval) return chrom_ok;  // validated; the value is not needed
+    // value: the 12 bytes that end right before the second tab; the first 12 - n of them are not POS
+    const uint32_t b = la + (uint32_t)(p0 + n) - 12u;
     const uint32_t b0 = b & ~3u;
     const uint32_t sh2 = (b & 3u) << 3;
     const uint32_t x0 = lds32(b0), x1 = lds32(b0 + 4), x2 = lds32(b0 + 8), x3 = lds32(b0 + 12);
     const uint32_t s = (uint32_t)(12 - n) << 3;
-    const uint32_t d0 = (__funnelshift_r(x0, x1, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s);
-    const uint32_t d1 = (__funnelshift_r(x1, x2, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s > 32u ? s - 32u : 0u);
-    const uint32_t d2 = (__funnelshift_r(x2, x3, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s > 64u ? s - 64u : 0u);
-    // every kept byte must be 0..9, and POS 0 is not a position ('+' lands here too): the scalar routine reports
-    const uint32_t bad = ((d0 + 0x76767676u) | d0 | (d1 + 0x76767676u) | d1 | (d2 + 0x76767676u) | d2) & 0x80808080u;
-    if (bad || (d0 | d1 | d2) == 0u) {
-        slow = true;
-        return 0;
-    }
-    if (!chrom_ok || !K.has_interval) return chrom_ok;  // validated; the value is not needed
+    const uint32_t q0d = (__funnelshift_r(x0, x1, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s);
+    const uint32_t q1d = (__funnelshift_r(x1, x2, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s > 32u ? s - 32u : 0u);
+    const uint32_t q2d = (__funnelshift_r(x2, x3, sh2) ^ 0x30303030u) & shl_clamp(0xFFFFFFFFu, s > 64u ? s - 64u : 0u);
     // 4 digits per word, most significant in byte 0
-    const uint32_t q0 = __dp4a(d0, 0x00010A64u, 0u) * 10u + (d0 >> 24);
-    const uint32_t q1 = __dp4a(d1, 0x00010A64u, 0u) * 10u + (d1 >> 24);
-    const uint32_t q2 = __dp4a(d2, 0x00010A64u, 0u) * 10u + (d2 >> 24);
+    const uint32_t q0 = __dp4a(q0d, 0x00010A64u, 0u) * 10u + (q0d >> 24);
+    const uint32_t q1 = __dp4a(q1d, 0x00010A64u, 0u) * 10u + (q1d >> 24);
+    const uint32_t q2 = __dp4a(q2d, 0x00010A64u, 0u) * 10u + (q2d >> 24);
     const unsigned long long v = (unsigned long long)(q0 * 10000u + q1) * 10000ull + q2;
     const unsigned long long lo = ((unsigned long long)K.lo_hi << 32) | K.lo_lo;
     const unsigned long long span = ((unsigned long long)K.span_hi << 32) | K.span_lo;
     return (v - lo) <= span;
 }
 
-// Screens one 16-byte chunk (words w.x..w.w plus the following word w4): non-zero iff the chunk MAY contain
-// the start of the pattern '\n' chrom '\t'.
-template <int MODE>
-__device__ __forceinline__ uint32_t chunk_may_hit(const uint4 w, const uint32_t w4, const uint32_t key,
-                                                  const uint32_t c4) {
+// Key4 screen (chrom of 2+ bytes): non-zero iff the 16-byte chunk (words w.x..w.w plus the following word w4) MAY contain
+// the start of the last four pattern bytes.
+__device__ __forceinline__ uint32_t chunk_may_hit_key4(const uint4 w, const uint32_t w4, const uint32_t key) {
     const uint32_t ws[5] = {w.x, w.y, w.z, w.w, w4};
-    if (MODE == kScanKey3) {
-        uint32_t h = 0;
+    bool hit = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t z = (ws[k] ^ kNL4) | (__funnelshift_r(ws[k], ws[k + 1], 8) ^ c4) |
-                               (__funnelshift_r(ws[k], ws[k + 1], 16) ^ kTAB4);
-            h |= (z - 0x01010101u) & ~z;
-        }
-        return h & 0x80808080u;
-    } else {
-        bool hit = false;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            hit |= (ws[k] == key);
-            hit |= (__funnelshift_r(ws[k], ws[k + 1], 8) == key);
-            hit |= (__funnelshift_r(ws[k], ws[k + 1], 16) == key);
-            hit |= (__funnelshift_r(ws[k], ws[k + 1], 24) == key);
-        }
-        return hit;
+    for (int k = 0; k < 4; ++k) {
+        hit |= (ws[k] == key);
+        hit |= (__funnelshift_r(ws[k], ws[k + 1], 8) == key);
+        hit |= (__funnelshift_r(ws[k], ws[k + 1], 16) == key);
+        hit |= (__funnelshift_r(ws[k], ws[k + 1], 24) == key);
     }
+    return hit;
 }
 
 // ===================================================================================================
@@ -318,6 +367,7 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
     constexpr bool LAZY = (MODE == kScanKey3 || MODE == kScanKey4);
     using L = SmemLayout<U, S, WARPS>;
     constexpr int TILE = L::TILE, STAGE = L::STAGE;
+    constexpr int kWindow = 28;  // bytes line_swar may touch from a line start (24-byte window + alignment slack)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ unsigned long long s_part[2];  // this CTA's count / error bits (the only block-wide state)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -337,22 +387,26 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
     }
     __syncwarp();
 
-    const int64_t nw = (int64_t)gridDim.x * WARPS;
-    const int64_t wg = (int64_t)blockIdx.x * WARPS + warp;
+    const uint32_t nw = gridDim.x * WARPS;
+    const uint32_t wg = blockIdx.x * WARPS + warp;
 
     // ---- per-launch constants ----
+    Pipes P;
+    P.one = a.n_segs >= 0 ? 1u : 0u;  // opaque to the compiler (see Pipes)
+    P.m24 = P.one << 24;
+    P.m16 = P.one << 16;
     uint32_t key = 0, c4 = 0;
     if (MODE == kScanKey3) c4 = 0x01010101u * a.pat[1];
     if (MODE == kScanKey4) key = (uint32_t)a.pat[0] | ((uint32_t)a.pat[1] << 8) | ((uint32_t)a.pat[2] << 16) | ((uint32_t)a.pat[3] << 24);
     LineConsts K;
     {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 3; ++k) {
             uint32_t p = 0, m = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int i = 4 * k + j;
-                if (a.has_chrom && i <= a.chrom_len && a.chrom_len <= 14) {
+                if (a.has_chrom && i <= a.chrom_len && a.chrom_len <= 11) {
                     p |= (uint32_t)a.pat[1 + i] << (8 * j);
                     m |= 0xFFu << (8 * j);
                 }
@@ -372,43 +426,45 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
         K.span_hi = (uint32_t)(span >> 32);
         K.has_chrom = a.has_chrom;
         K.has_interval = a.has_interval;
-        K.wide_chrom = a.chrom_len > 6;
+        K.pat_words = a.has_chrom ? (a.chrom_len + 4) / 4 : 0;  // chrom + '\t' bytes, in words
+        K.p0 = a.chrom_len + 1;
     }
-    const bool swar_ok = !a.has_chrom || a.chrom_len <= 14;  // longer names do not fit the 16-byte window
+    const bool swar_ok = !a.has_chrom || a.chrom_len <= 11;  // longer names do not fit the window's pattern words
 
-    // ---- producer (lane 0): one cursor over the segment table, S tiles ahead of the consumer ----
-    int pc = 0;
-    int64_t p_tile0 = 0, p_next0 = 0;
-    if (lane == 0) {
-        p_tile0 = __ldg(&a.segs[0].tile0);
-        p_next0 = __ldg(&a.segs[1].tile0);
-    }
-    auto issue = [&](int64_t T, int s) {  // lane 0 only
-        while (T >= p_next0) {
-            ++pc;
-            p_tile0 = p_next0;
-            p_next0 = __ldg(&a.segs[pc + 1].tile0);
+    // ---- producer (lane 0): tiles T = wg, wg + nw, ... tracked as (segment, tile inside the segment) in 32-bit arithmetic ----
+    const uint32_t my_tiles = a.n_tiles > (int64_t)wg ? (uint32_t)((a.n_tiles - 1 - (int64_t)wg) / nw) + 1u : 0u;
+    int pseg = -1;
+    uint32_t ptis = wg, pseg_tiles = 0;  // tile index relative to segment `pseg`, tiles of that segment
+    const uint8_t *pbase = nullptr;
+    int64_t pspan = 0;                   // skip + len of the segment
+    int pskip = 0;
+    auto issue = [&](int s) {  // lane 0 only: stage the producer's current tile into slot s, then step to the next one
+        while (ptis >= pseg_tiles) {
+            ptis -= pseg_tiles;
+            ++pseg;
+            const ScanSeg *sg = a.segs + pseg;
+            pbase = sg->base;
+            pskip = __ldg(&sg->skip);
+            pspan = pskip + __ldg(&sg->len);
+            pseg_tiles = (uint32_t)(__ldg(&sg[1].tile0) - __ldg(&sg->tile0));
         }
-        const uint8_t *base = a.segs[pc].base;
-        const int skip = __ldg(&a.segs[pc].skip);
-        const int64_t off = (T - p_tile0) * TILE;
-        const int64_t rem = skip + __ldg(&a.segs[pc].len) - off;
-        const int pre = off ? kPre : 0;
-        const int64_t body = (rem + 15) & ~(int64_t)15;
-        const uint32_t bytes = (uint32_t)(body < TILE + kHalo ? body : TILE + kHalo) + pre;
-        meta[s].g = base + off;
-        meta[s].lo = off ? -kPre : skip;
+        const int64_t off = (int64_t)ptis * TILE;
+        const int64_t rem = pspan - off;
+        const int pre = ptis ? kPre : 0;
+        const uint32_t body = rem >= TILE + kHalo ? (uint32_t)(TILE + kHalo) : ((uint32_t)rem + 15u) & ~15u;
+        const uint32_t bytes = body + pre;
+        meta[s].g = pbase + off;
+        meta[s].lo = ptis ? -kPre : pskip;
         meta[s].hi = rem > (1 << 30) ? (1 << 30) : (int)rem;
         mbar_arrive_expect_tx(&bars[s], bytes);
-        bulk_g2s(ring + s * STAGE + (kPre - pre), base + off - pre, bytes, &bars[s]);
+        bulk_g2s(ring + s * STAGE + (kPre - pre), pbase + off - pre, bytes, &bars[s]);
+        ptis += nw;
     };
 
     if (lane == 0) {
 #pragma unroll 1
-        for (int s = 0; s < S; ++s) {
-            const int64_t T = wg + s * nw;
-            if (T < a.n_tiles) issue(T, s);
-        }
+        for (int s = 0; s < S; ++s)
+            if ((uint32_t)s < my_tiles) issue(s);
     }
     __syncwarp();
 
@@ -416,7 +472,7 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
     uint32_t parity = 0;
     int s = 0;
 #pragma unroll 1
-    for (int64_t T = wg; T < a.n_tiles; T += nw) {
+    for (uint32_t it = 0; it < my_tiles; ++it) {
         const uint8_t *sm = ring + s * STAGE + kPre;
         mbar_wait(&bars[s], parity);  // lane 0 wrote meta[s] before it armed the barrier
         const uint8_t *g = meta[s].g;
@@ -435,9 +491,13 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
                 err |= (uint32_t)(r >> 32);
             }
         }
-        // interior: the tile starts inside the segment at a 16-byte boundary and every staged byte is segment data
-        const bool interior = hi >= TILE + kHalo && (lo <= 0) && swar_ok;
+        // interior: the tile starts inside the segment at a 16-byte boundary and every staged byte is segment data.
+        // edge: the segment begins and / or ends inside the staged window: same vector path, but '\n' flags outside the
+        // segment are masked and a line that starts within kWindow bytes of the segment's end takes the scalar routine.
+        const bool interior = hi >= TILE + kHalo && lo <= 0;
+        const bool edge = !interior;
         const uint32_t sa = ring_sa + (uint32_t)(s * STAGE + kPre);  // shared-window address of tile byte 0
+        const int u_end = hi >= TILE ? U : (hi + 511) >> 9;        // 512-byte rows that hold segment bytes
         if (interior && MODE == kScanLines) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -447,7 +507,7 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
                 nl128 = __dp4a(zero_bytes_exact(w.z ^ kNL4), 0x01010101u, nl128);
                 nl128 = __dp4a(zero_bytes_exact(w.w ^ kNL4), 0x01010101u, nl128);
             }
-        } else if (interior) {
+        } else if (swar_ok && MODE != kScanLines) {
             // 1. every lane scans its chunks and appends the line starts it finds to the warp's queue;
             // 2. the queue is drained one line per lane, so the parser runs with (nearly) all lanes busy.
             int qn = 0;
@@ -456,8 +516,8 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
 #pragma unroll 1
                 for (int i = lane; i < qn; i += 32) {
                     const int ls = (int)lds16(queue_sa + 2u * (uint32_t)i);
-                    bool slow = false;
-                    cnt += line_swar<LAZY>(sa, ls, K, slow);
+                    bool slow = edge && ls + kWindow > hi;  // the window would leave the segment
+                    if (!slow) cnt += line_swar<LAZY>(sa, ls, K, P, slow);
                     if (slow) {
                         const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, ls, &a);
                         cnt += (uint32_t)r;
@@ -468,28 +528,56 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
                 qn = 0;
             };
 #pragma unroll 2
-            for (int u = 0; u < U; ++u) {
+            for (int u = 0; u < u_end; ++u) {
                 const int c0 = (u * 32 + lane) * 16;
                 const uint4 w = lds128(sa + (uint32_t)c0);
-                uint32_t m = 0;
                 bool look = true;
                 if (LAZY) {
-                    const uint32_t w4 = lds32(sa + (uint32_t)c0 + 16u);
-                    look = chunk_may_hit<MODE>(w, w4, key, c4) != 0;
+                    // the word after the chunk: lane + 1 holds it in a register (the last lane reads it from the window)
+                    uint32_t w4 = __shfl_down_sync(0xFFFFFFFFu, w.x, 1);
+                    if (lane == 31) w4 = lds32(sa + (uint32_t)c0 + 16u);
+                    if (MODE == kScanKey3) {
+                        // stage 1: '\n' followed by the name byte somewhere in the chunk? (never, outside the name's block of contigs)
+                        const uint32_t ws[5] = {w.x, w.y, w.z, w.w, w4};
+                        uint32_t v[5], z[4], h = 0;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) v[k] = ws[k] ^ c4;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            z[k] = (ws[k] ^ kNL4) | fma_funnel(v[k], v[k + 1], P.m24);
+                            h = zero_acc(h, z[k], P);
+                        }
+                        look = (h & kC80) != 0;
+                        if (__ballot_sync(0xFFFFFFFFu, look) == 0) continue;
+                        // stage 2: ... and a tab right behind it (the exact 3-byte pattern, up to borrow artefacts)
+                        uint32_t h2 = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            h2 = zero_acc(h2, z[k] | fma_funnel(ws[k] ^ kTAB4, ws[k + 1] ^ kTAB4, P.m16), P);
+                        look = (h2 & kC80) != 0;
+                    } else {
+                        look = chunk_may_hit_key4(w, w4, key) != 0;
+                    }
                     if (__ballot_sync(0xFFFFFFFFu, look) == 0) continue;
                 }
-                if (look)
-                    m = pack16(zero_bytes_exact(w.x ^ kNL4), zero_bytes_exact(w.y ^ kNL4), zero_bytes_exact(w.z ^ kNL4),
-                               zero_bytes_exact(w.w ^ kNL4));
+                uint32_t m = 0;
+                if (look) m = pack16_7(nl_flags(w.x, P), nl_flags(w.y, P), nl_flags(w.z, P), nl_flags(w.w, P));
+                if (edge) {
+                    // keep '\n' at positions p with seg_lo <= p and p + 1 < hi (bit 7 + i of m is byte c0 + i)
+                    const int lo_i = seg_lo - c0, hi_i = hi - 1 - c0;  // valid i: lo_i <= i < hi_i
+                    uint32_t keep = hi_i >= 16 ? 0xFFFFu : (hi_i <= 0 ? 0u : (1u << hi_i) - 1u);
+                    if (lo_i > 0) keep &= lo_i >= 16 ? 0u : ~((1u << lo_i) - 1u);
+                    m &= keep << 7;
+                }
                 const uint32_t b = __ballot_sync(0xFFFFFFFFu, m != 0);
                 if (m) {
-                    sts16(queue_sa + 2u * (uint32_t)(qn + __popc(b & lt_mask)), (uint32_t)(c0 + __ffs(m)));  // line = byte after '\n'
+                    sts16(queue_sa + 2u * (uint32_t)(qn + __popc(b & lt_mask)), (uint32_t)(c0 + __ffs(m) - 7));  // line = byte after '\n'
                     m &= m - 1;
                 }
                 qn += __popc(b);
                 // further line starts in the same 16 bytes (lines shorter than 16 bytes) take the scalar routine
                 while (m) {
-                    const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0 + __ffs(m), &a);
+                    const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0 + __ffs(m) - 7, &a);
                     m &= m - 1;
                     cnt += (uint32_t)r;
                     err |= (uint32_t)(r >> 32);
@@ -509,10 +597,7 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
             }
         }
         __syncwarp();
-        if (lane == 0) {
-            const int64_t Tn = T + (int64_t)S * nw;
-            if (Tn < a.n_tiles) issue(Tn, s);
-        }
+        if (lane == 0 && it + S < my_tiles) issue(s);
         if (++s == S) {
             s = 0;
             parity ^= 1;
