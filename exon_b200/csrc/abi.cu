@@ -305,6 +305,7 @@ int exon_gpu_vcf_close(exon_gpu_stream *s) {
     if (s->d_res) cudaFree(s->d_res);
     if (s->h_res) cudaFreeHost(s->h_res);
     if (s->d_segs) cudaFree(s->d_segs);
+    if (s->d_tiles) cudaFree(s->d_tiles);
     s->gz_teardown();
     if (s->d_bam) cudaFree(s->d_bam);
     delete s;

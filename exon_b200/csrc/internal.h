@@ -153,6 +153,8 @@ struct VcfStream {
     // ---- device-side tables / results ----
     ScanSeg *d_segs = nullptr;
     size_t d_segs_cap = 0;
+    TileDesc *d_tiles = nullptr;  // one descriptor per tile of the current table (built on the device from d_segs)
+    size_t d_tiles_cap = 0;
     std::vector<ScanSeg> h_segs;
     bool segs_dirty = true;
     int seg_variant = -1;
@@ -233,7 +235,7 @@ struct VcfStream {
     int end_file();
     int filter_count(const exon_gpu_region *region, int64_t *device_out, int64_t *host_out);
     int filter_count_global(const exon_gpu_region *region, int64_t *out_local, int64_t *out_global);
-    int launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_segs, int64_t tiles, ScanAcc *acc, const ScanTail &tail);
+    int launch_scan(const OwnedRegion &r, const TileDesc *d_table, int n_segs, int64_t tiles, ScanAcc *acc, const ScanTail &tail);
     int run_query(const exon_gpu_region *region, int64_t *device_out, bool want_host, bool global);
     int wait_published();
     int build_seg_table();

@@ -32,6 +32,8 @@
 // Dense mode (strict, or no chrom literal) parses and validates every line.
 #include "vcf_scan.cuh"
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "vcf_tile.cuh"
 
@@ -134,12 +136,37 @@ __device__ __noinline__ unsigned long long chunk_careful(const uint8_t *sm, cons
 // Pipe-aware SWAR helpers.  Measured on B200 (tools/ubench_pipes.cu, profiles/r2_ubench_pipes.txt): LOP3 / SHF / PRMT issue
 // on the ALU pipe and IMAD / IMAD.WIDE / IDP.4A on the FMA pipe, each at one warp-instruction per 2 cycles per SM
 // sub-partition, and the two pipes overlap.  K1 was ALU-bound (79 % ALU pipe, FMA idle), so byte shifts and the
-// "minus 0x01010101" of the zero-byte tests are written as multiplies: the multipliers live in registers the compiler
-// cannot see through (it would turn a constant power of two back into an ALU shift).
+// "minus 0x01010101" of the zero-byte tests are written as multiplies, and every 3-input boolean is ONE LOP3: its
+// constants live in (uniform) registers derived from a value the compiler cannot see through -- as immediates they would
+// split each LOP3 in two (one immediate per instruction) and turn the power-of-two multiplies back into ALU shifts.
 // ===================================================================================================
-struct Pipes {
-    uint32_t one, m24, m16;  // 1, 2^24, 2^16
+constexpr uint32_t kC80 = 0x80808080u;
+struct Konst {
+    uint32_t one, m24, m16;                            // 1, 2^24, 2^16
+    uint32_t nl4, tab4, c80, m01, c30, c76, cfc, c08;  // byte patterns
 };
+__device__ __forceinline__ Konst make_konst(uint32_t one) {
+    Konst C;
+    C.one = one;
+    C.m24 = one << 24;
+    C.m16 = one << 16;
+    C.nl4 = one * kNL4;
+    C.tab4 = one * kTAB4;
+    C.c80 = one * 0x80808080u;
+    C.m01 = one * 0xFEFEFEFFu;  // -0x01010101
+    C.c30 = one * 0x30303030u;
+    C.c76 = one * 0x76767676u;
+    C.cfc = one * 0xFCFCFCFCu;
+    C.c08 = one * 0x08080808u;
+    return C;
+}
+// one LOP3 with truth table LUT over (a, b, c) = (0xF0, 0xCC, 0xAA)
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
 __device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one) {  // a + b (IMAD)
     uint32_t r;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
@@ -147,21 +174,20 @@ __device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one
 }
 // (lo >> k) | (hi << (32 - k)) for m = 2^(32 - k): IMAD.WIDE (high half = lo >> k) + IMAD (hi * m adds hi << (32 - k))
 __device__ __forceinline__ uint32_t fma_funnel(uint32_t lo, uint32_t hi, uint32_t m) {
-    uint32_t l32, h32, r;
-    asm("{.reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t;}" : "=r"(l32), "=r"(h32) : "r"(lo), "r"(m));
+    uint32_t h32, r;
+    asm("{.reg .u64 t; .reg .u32 l; mul.wide.u32 t, %1, %2; mov.b64 {l, %0}, t;}" : "=r"(h32) : "r"(lo), "r"(m));
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(hi), "r"(m), "r"(h32));
     return r;
 }
-constexpr uint32_t kC80 = 0x80808080u, kM01 = 0xFEFEFEFFu;  // -0x01010101
 // 0x80 in every byte lane of w that is '\n' -- exact and borrow-free: ((w ^ NL) | 0x80) - 1 clears a lane's top bit only
 // when the lane was 0x00 or 0x80, and ~w rules out 0x80 (the top bit of w ^ NL is the top bit of w).  2 ALU + 1 FMA.
-__device__ __forceinline__ uint32_t nl_flags(uint32_t w, const Pipes &P) {
-    const uint32_t t = fma_add((w ^ kNL4) | kC80, kM01, P.one);
-    return ~t & ~w & kC80;
+__device__ __forceinline__ uint32_t nl_flags(uint32_t w, const Konst &C) {
+    const uint32_t t = fma_add(lop3<0xBE>(w, C.nl4, C.c80), C.m01, C.one);  // ((w ^ nl) | 0x80) - 0x01..
+    return lop3<0x02>(t, w, C.c80);                                         // ~t & ~w & 0x80..
 }
 // conservative zero-byte accumulator: h |= flags of zero bytes of z (the lowest flag of a word is exact, higher ones may be
-// borrow artefacts -- fine for a screen and for "first flag" searches).  1 FMA + 1 ALU.
-__device__ __forceinline__ uint32_t zero_acc(uint32_t h, uint32_t z, const Pipes &P) { return h | (fma_add(z, kM01, P.one) & ~z); }
+// borrow artefacts -- fine for a screen and for "first flag" searches); the caller masks with 0x80808080.  1 FMA + 1 ALU.
+__device__ __forceinline__ uint32_t zero_acc(uint32_t h, uint32_t z, const Konst &C) { return lop3<0xF4>(h, fma_add(z, C.m01, C.one), z); }
 // 16 byte flags (0x80 each) -> mask with bit 7 + i set for byte i (IDP.4A x4 + IMAD: FMA pipe only)
 __device__ __forceinline__ uint32_t pack16_7(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
     uint32_t a = __dp4a(f0, 0x08040201u, 0u);
@@ -172,22 +198,23 @@ __device__ __forceinline__ uint32_t pack16_7(uint32_t f0, uint32_t f1, uint32_t 
 }
 
 // ===================================================================================================
-// SWAR line parser (interior tiles: every byte of the staged window belongs to the segment)
+// SWAR line parser (every byte of the 28-byte window read from the line start belongs to the segment)
 // ===================================================================================================
 struct LineConsts {
-    uint32_t P[3], M[3];  // (window ^ P) & M == 0  <=>  the line starts with chrom + '\t' (chrom of at most 11 bytes)
+    uint32_t P[3], M[3];  // ((window ^ P) & M) == 0  <=>  the line starts with chrom + '\t' (chrom of at most 11 bytes); M = 0 without a literal
     uint32_t lo_lo, lo_hi, span_lo, span_hi;  // pos in [lo, lo + span]
-    int has_chrom, has_interval, pat_words;   // pat_words: window words the pattern reaches into (1..3)
+    int has_chrom, has_interval;
     int p0;                                   // chrom_len + 1: where POS starts on a line whose CHROM matched
 };
 
 // Parses the line whose first byte is tile byte `ls` from a 24-byte window; `sa` is the shared-window address of tile
 // byte 0.  Returns the predicate (0/1); sets `slow` when the line needs the scalar routine instead (nothing has been decided
-// or reported then): a CHROM of more than 11 bytes, a field that leaves the window, '+', POS with a leading zero, anything
-// malformed.  STRICT: CHROM must be non-empty and POS a positive decimal on EVERY line (what the reference's builder
-// checks while it fills the columns, lazy_array_builder.rs:157-168); otherwise only a line whose CHROM matches is looked at.
+// or reported then): a CHROM of more than 11 bytes, a field that leaves the window, '+', POS with a leading zero or more
+// than 12 digits, anything malformed.  Not LAZY (strict streams, or no chrom literal): CHROM must be non-empty and POS a
+// positive decimal on EVERY line (what the reference's builder checks while it fills the columns,
+// lazy_array_builder.rs:157-168); LAZY: only a line whose CHROM matches is looked at.
 template <bool LAZY>
-__device__ __forceinline__ uint32_t line_swar(uint32_t sa, int ls, const LineConsts &K, const Pipes &P, bool &slow) {
+__device__ __forceinline__ uint32_t line_swar(uint32_t sa, int ls, const LineConsts &K, const Konst &C, bool &slow) {
     const uint32_t la = sa + (uint32_t)ls;  // address of the line's first byte
     const uint32_t a0 = la & ~3u;
     const uint32_t sh = (la & 3u) << 3;     // tile byte 0 is 16-byte aligned
@@ -195,45 +222,37 @@ __device__ __forceinline__ uint32_t line_swar(uint32_t sa, int ls, const LineCon
                    w5 = lds32(a0 + 20), w6 = lds32(a0 + 24);
     const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh),
                    v3 = __funnelshift_r(w3, w4, sh), v4 = __funnelshift_r(w4, w5, sh), v5 = __funnelshift_r(w5, w6, sh);
-    bool chrom_ok = true;
-    int p0 = K.p0;
-    if (K.has_chrom) {
-        uint32_t d = (v0 ^ K.P[0]) & K.M[0];
-        if (K.pat_words > 1) d |= (v1 ^ K.P[1]) & K.M[1];
-        if (K.pat_words > 2) d |= (v2 ^ K.P[2]) & K.M[2];
-        chrom_ok = d == 0;
-        if (LAZY && !chrom_ok) return 0;
-    }
+    const bool chrom_ok = lop3<0xFE>(lop3<0x28>(v0, K.P[0], K.M[0]), lop3<0x28>(v1, K.P[1], K.M[1]), lop3<0x28>(v2, K.P[2], K.M[2])) == 0;
+    if (LAZY && !chrom_ok) return 0;
     if (LAZY && !K.has_interval) return 1;
+    int p0 = K.p0;
+    bool ok = true;
     if (!LAZY) {
         // first separator (bytes 0x08..0x0B) of the first 12 bytes; it must be a tab and must not be byte 0
-        const uint32_t e0 = (v0 & 0xFCFCFCFCu) ^ 0x08080808u, e1 = (v1 & 0xFCFCFCFCu) ^ 0x08080808u, e2 = (v2 & 0xFCFCFCFCu) ^ 0x08080808u;
-        const uint32_t f0 = fma_add(e0, kM01, P.one) & ~e0 & kC80, f1 = fma_add(e1, kM01, P.one) & ~e1 & kC80,
-                       f2 = fma_add(e2, kM01, P.one) & ~e2 & kC80;
+        const uint32_t e0 = lop3<0x6A>(v0, C.cfc, C.c08), e1 = lop3<0x6A>(v1, C.cfc, C.c08), e2 = lop3<0x6A>(v2, C.cfc, C.c08);
+        const uint32_t f0 = lop3<0x20>(fma_add(e0, C.m01, C.one), e0, C.c80), f1 = lop3<0x20>(fma_add(e1, C.m01, C.one), e1, C.c80),
+                       f2 = lop3<0x20>(fma_add(e2, C.m01, C.one), e2, C.c80);
         uint32_t sm7 = __dp4a(f0, 0x08040201u, 0u);
         sm7 = __dp4a(f1, 0x80402010u, sm7);
         sm7 = __dp4a(f2, 0x08040201u, 0u) * 256u + sm7;
-        const int s1 = __ffs(sm7) - 8;
-        if (s1 < 1 || lds8(la + (uint32_t)s1) != '\t') {  // no separator in reach, an empty CHROM, or a line that ends early
-            slow = true;
-            return 0;
-        }
+        const int s1 = __ffs(sm7) - 8;   // -8: no separator in reach
+        ok = s1 >= 1 && lds8(la + (uint32_t)s1) == '\t';  // (s1 < 0 reads the staged bytes before the line: harmless)
         p0 = s1 + 1;
     }
     // non-digit flags of the whole window; the first one at or after p0 ends POS
-    const uint32_t d0 = v0 ^ 0x30303030u, d1 = v1 ^ 0x30303030u, d2 = v2 ^ 0x30303030u, d3 = v3 ^ 0x30303030u,
-                   d4 = v4 ^ 0x30303030u, d5 = v5 ^ 0x30303030u;
-    const uint32_t n0 = (fma_add(d0, 0x76767676u, P.one) | d0) & kC80, n1 = (fma_add(d1, 0x76767676u, P.one) | d1) & kC80,
-                   n2 = (fma_add(d2, 0x76767676u, P.one) | d2) & kC80, n3 = (fma_add(d3, 0x76767676u, P.one) | d3) & kC80,
-                   n4 = (fma_add(d4, 0x76767676u, P.one) | d4) & kC80, n5 = (fma_add(d5, 0x76767676u, P.one) | d5) & kC80;
-    uint32_t nm = pack16_7(n0, n1, n2, n3);                       // bits 7..22
+    const uint32_t d0 = v0 ^ C.c30, d1 = v1 ^ C.c30, d2 = v2 ^ C.c30, d3 = v3 ^ C.c30, d4 = v4 ^ C.c30, d5 = v5 ^ C.c30;
+    const uint32_t n0 = lop3<0xA8>(fma_add(d0, C.c76, C.one), d0, C.c80), n1 = lop3<0xA8>(fma_add(d1, C.c76, C.one), d1, C.c80),
+                   n2 = lop3<0xA8>(fma_add(d2, C.c76, C.one), d2, C.c80), n3 = lop3<0xA8>(fma_add(d3, C.c76, C.one), d3, C.c80),
+                   n4 = lop3<0xA8>(fma_add(d4, C.c76, C.one), d4, C.c80), n5 = lop3<0xA8>(fma_add(d5, C.c76, C.one), d5, C.c80);
     uint32_t nh = __dp4a(n4, 0x08040201u, 0u);
     nh = __dp4a(n5, 0x80402010u, nh);                             // bits 7..14 for bytes 16..23
-    nm += nh << 16;                                               // bits 23..30
+    const uint32_t nm = nh * 65536u + pack16_7(n0, n1, n2, n3);   // bit 7 + i: byte i is not a digit
     const uint32_t nd = nm >> (7 + p0);
-    const int n = __ffs(nd) - 1;                                  // digits of POS
-    if (n < 1 || n > 12 || lds8(la + (uint32_t)(p0 + n)) != '\t' || lds8(la + (uint32_t)p0) == '0') {
-        slow = true;  // POS leaves the window, is empty or longer than 12 digits, starts with '+' or '0', or is not followed by a tab
+    const int n = __ffs(nd) - 1;                                  // digits of POS (-1: none in reach)
+    const uint32_t c_end = lds8(la + (uint32_t)(p0 + n)), c_first = lds8(la + (uint32_t)p0);
+    ok = ok && n >= 1 && n <= 12 && c_end == '\t' && c_first != '0';
+    if (!ok) {
+        slow = true;  // POS leaves the window, is empty or longer than 12 digits, starts with '+' or '0', is not followed by a tab, ...
         return 0;
     }
     if (!chrom_ok || !K.has_interval) return chrom_ok;  // validated; the value is not needed
@@ -269,6 +288,29 @@ __device__ __forceinline__ uint32_t chunk_may_hit_key4(const uint4 w, const uint
         hit |= (__funnelshift_r(ws[k], ws[k + 1], 24) == key);
     }
     return hit;
+}
+
+// Key3 screen, stage 1: flags (top bits) where '\n' is followed by the name byte c.  z[] keeps the per-word test values
+// for stage 2.  5 + 4 + 4 ALU, 4 + 4 + 4 FMA per 16 bytes.
+__device__ __forceinline__ uint32_t key3_stage1(const uint32_t (&ws)[5], uint32_t c4, uint32_t (&z)[4], const Konst &C) {
+    uint32_t v[5], h = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = ws[k] ^ c4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        z[k] = lop3<0xBE>(ws[k], C.nl4, fma_funnel(v[k], v[k + 1], C.m24));  // (w ^ '\n') | ((w ^ c) >> 1 byte)
+        h = zero_acc(h, z[k], C);
+    }
+    return h;
+}
+// stage 2: ... and a tab right behind it (the exact 3-byte pattern, up to borrow artefacts)
+__device__ __forceinline__ uint32_t key3_stage2(const uint32_t (&ws)[5], const uint32_t (&z)[4], const Konst &C) {
+    uint32_t y[5], h = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) y[k] = ws[k] ^ C.tab4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h = zero_acc(h, z[k] | fma_funnel(y[k], y[k + 1], C.m16), C);
+    return h;
 }
 
 // ===================================================================================================
@@ -360,6 +402,32 @@ __device__ __forceinline__ void scan_block_epilogue(const ScanArgs &a, unsigned 
 }
 
 // ===================================================================================================
+// Tile descriptors: one 16-byte record per 4 KiB tile, built on the device from the segment table whenever the table
+// changes, so that the scan kernel's producer lane spends a dozen instructions per tile instead of walking the table
+// with 64-bit arithmetic (ncu, round 2: ~135 of the ~560 warp-instructions per tile were per-tile bookkeeping).
+// ===================================================================================================
+__global__ void build_tile_descs_kernel(const ScanSeg *segs, int n_segs, int64_t n_tiles, int tile, TileDesc *out) {
+    const int64_t T = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (T >= n_tiles) return;
+    int lo = 0, hi = n_segs - 1;  // last segment with tile0 <= T
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].tile0 <= T) lo = mid;
+        else hi = mid - 1;
+    }
+    const ScanSeg sg = segs[lo];
+    const int64_t t = T - sg.tile0;
+    const int64_t off = t * tile;
+    const int64_t rem = sg.skip + sg.len - off;
+    TileDesc d;
+    d.src = sg.base + off;
+    d.hi = rem > (1 << 30) ? (1 << 30) : (int32_t)rem;
+    d.lo = (int16_t)(t ? -kPre : sg.skip);
+    d.flags = (uint16_t)((rem >= tile + kHalo && (t || sg.skip == 0)) ? kTileInterior : 0);
+    out[T] = d;
+}
+
+// ===================================================================================================
 // The kernel
 // ===================================================================================================
 template <int MODE, int U, int S, int WARPS>
@@ -376,8 +444,10 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
     __syncthreads();
     uint8_t *ring = smem_raw + L::ring + (size_t)warp * (S * STAGE);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + L::bars) + warp * S;
-    StageMeta *meta = reinterpret_cast<StageMeta *>(smem_raw + L::meta) + warp * S;
+    TileDesc *meta = reinterpret_cast<TileDesc *>(smem_raw + L::meta) + warp * S;
+    static_assert(sizeof(TileDesc) == sizeof(StageMeta), "the ring's meta slots hold tile descriptors");
     const uint32_t ring_sa = smem_u32(ring);
+    const uint32_t meta_sa = smem_u32(meta);
     const uint32_t queue_sa = smem_u32(smem_raw + L::queue) + (uint32_t)(warp * kQueue * sizeof(uint16_t));
 
     if (lane == 0) {
@@ -391,10 +461,7 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
     const uint32_t wg = blockIdx.x * WARPS + warp;
 
     // ---- per-launch constants ----
-    Pipes P;
-    P.one = a.n_segs >= 0 ? 1u : 0u;  // opaque to the compiler (see Pipes)
-    P.m24 = P.one << 24;
-    P.m16 = P.one << 16;
+    const Konst C = make_konst(a.n_segs >= 0 ? 1u : 0u);  // opaque to the compiler (see Konst)
     uint32_t key = 0, c4 = 0;
     if (MODE == kScanKey3) c4 = 0x01010101u * a.pat[1];
     if (MODE == kScanKey4) key = (uint32_t)a.pat[0] | ((uint32_t)a.pat[1] << 8) | ((uint32_t)a.pat[2] << 16) | ((uint32_t)a.pat[3] << 24);
@@ -426,78 +493,147 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
         K.span_hi = (uint32_t)(span >> 32);
         K.has_chrom = a.has_chrom;
         K.has_interval = a.has_interval;
-        K.pat_words = a.has_chrom ? (a.chrom_len + 4) / 4 : 0;  // chrom + '\t' bytes, in words
         K.p0 = a.chrom_len + 1;
     }
     const bool swar_ok = !a.has_chrom || a.chrom_len <= 11;  // longer names do not fit the window's pattern words
 
-    // ---- producer (lane 0): tiles T = wg, wg + nw, ... tracked as (segment, tile inside the segment) in 32-bit arithmetic ----
+    // ---- producer (lane 0): tiles wg, wg + nw, ...; the descriptor of the next tile to stage is fetched one step ahead ----
     const uint32_t my_tiles = a.n_tiles > (int64_t)wg ? (uint32_t)((a.n_tiles - 1 - (int64_t)wg) / nw) + 1u : 0u;
-    int pseg = -1;
-    uint32_t ptis = wg, pseg_tiles = 0;  // tile index relative to segment `pseg`, tiles of that segment
-    const uint8_t *pbase = nullptr;
-    int64_t pspan = 0;                   // skip + len of the segment
-    int pskip = 0;
-    auto issue = [&](int s) {  // lane 0 only: stage the producer's current tile into slot s, then step to the next one
-        while (ptis >= pseg_tiles) {
-            ptis -= pseg_tiles;
-            ++pseg;
-            const ScanSeg *sg = a.segs + pseg;
-            pbase = sg->base;
-            pskip = __ldg(&sg->skip);
-            pspan = pskip + __ldg(&sg->len);
-            pseg_tiles = (uint32_t)(__ldg(&sg[1].tile0) - __ldg(&sg->tile0));
-        }
-        const int64_t off = (int64_t)ptis * TILE;
-        const int64_t rem = pspan - off;
-        const int pre = ptis ? kPre : 0;
-        const uint32_t body = rem >= TILE + kHalo ? (uint32_t)(TILE + kHalo) : ((uint32_t)rem + 15u) & ~15u;
+    uint32_t p_issued = 0;  // tiles staged so far
+    uint4 pd = make_uint4(0, 0, 0, 0);
+    auto fetch = [&]() {  // lane 0: descriptor of tile number p_issued of this warp
+        if (p_issued < my_tiles) pd = __ldg(reinterpret_cast<const uint4 *>(a.tiles + ((size_t)wg + (size_t)p_issued * nw)));
+    };
+    auto issue = [&](int s) {  // lane 0 only: stage the tile described by pd into slot s
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(((unsigned long long)pd.y << 32) | pd.x);
+        const int hi = (int)pd.z;
+        const int pre = (int)(int16_t)(pd.w & 0xFFFFu) < 0 ? kPre : 0;
+        const uint32_t body = hi >= TILE + kHalo ? (uint32_t)(TILE + kHalo) : ((uint32_t)hi + 15u) & ~15u;
         const uint32_t bytes = body + pre;
-        meta[s].g = pbase + off;
-        meta[s].lo = ptis ? -kPre : pskip;
-        meta[s].hi = rem > (1 << 30) ? (1 << 30) : (int)rem;
+        *reinterpret_cast<uint4 *>(&meta[s]) = pd;
         mbar_arrive_expect_tx(&bars[s], bytes);
-        bulk_g2s(ring + s * STAGE + (kPre - pre), pbase + off - pre, bytes, &bars[s]);
-        ptis += nw;
+        bulk_g2s(ring + s * STAGE + (kPre - pre), src - pre, bytes, &bars[s]);
+        ++p_issued;
     };
 
     if (lane == 0) {
 #pragma unroll 1
-        for (int s = 0; s < S; ++s)
-            if ((uint32_t)s < my_tiles) issue(s);
+        for (int s = 0; s < S; ++s) {
+            fetch();
+            if (p_issued < my_tiles) issue(s);
+        }
+        fetch();
     }
     __syncwarp();
 
     uint32_t cnt = 0, err = 0, nl128 = 0;
     uint32_t parity = 0;
     int s = 0;
+
+    // One tile through the vector path.  EDGE: the segment begins and / or ends inside the staged window: '\n' flags outside
+    // the segment are masked and a line that starts within kWindow bytes of the segment's end takes the scalar routine.
+    auto scan_tile = [&](auto edge_tag, const uint8_t *sm, const uint8_t *g, int seg_lo, int hi, int sm_lo, int sm_hi, uint32_t sa) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        const int u_end = (!EDGE || hi >= TILE) ? U : (hi + 511) >> 9;  // 512-byte rows that hold segment bytes
+        // 1. every lane scans its chunks and appends the line starts it finds to the warp's queue;
+        // 2. the queue is drained one line per lane, so the parser runs with (nearly) all lanes busy.
+        int qn = 0;
+        auto drain = [&]() {
+            __syncwarp();
+#pragma unroll 1
+            for (int i = lane; i < qn; i += 32) {
+                const int ls = (int)lds16(queue_sa + 2u * (uint32_t)i);
+                bool slow = EDGE && ls + kWindow > hi;  // the window would leave the segment
+                if (!slow) cnt += line_swar<LAZY>(sa, ls, K, C, slow);
+                if (slow) {
+                    const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, ls, &a);
+                    cnt += (uint32_t)r;
+                    err |= (uint32_t)(r >> 32);
+                }
+            }
+            __syncwarp();
+            qn = 0;
+        };
+        // line starts of one chunk (m: bit 7 + i = '\n' at byte c0 + i) -> queue; extra starts in the same 16 bytes -> scalar
+        auto push = [&](uint32_t m, int c0) {
+            if (EDGE) {
+                // keep '\n' at positions p with seg_lo <= p and p + 1 < hi
+                const int lo_i = seg_lo - c0, hi_i = hi - 1 - c0;  // valid i: lo_i <= i < hi_i
+                uint32_t keep = hi_i >= 16 ? 0xFFFFu : (hi_i <= 0 ? 0u : (1u << hi_i) - 1u);
+                if (lo_i > 0) keep &= lo_i >= 16 ? 0u : ~((1u << lo_i) - 1u);
+                m &= keep << 7;
+            }
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, m != 0);
+            if (m) {
+                sts16(queue_sa + 2u * (uint32_t)(qn + __popc(b & lt_mask)), (uint32_t)(c0 + __ffs(m) - 7));  // line = byte after '\n'
+                m &= m - 1;
+            }
+            qn += __popc(b);
+            while (m) {  // lines shorter than 16 bytes
+                const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0 + __ffs(m) - 7, &a);
+                m &= m - 1;
+                cnt += (uint32_t)r;
+                err |= (uint32_t)(r >> 32);
+            }
+            if (qn > kQueue - 32) drain();
+        };
+        if (MODE == kScanKey3) {
+            // two chunks per step: both screens are computed before the warp votes once (twice the independent work in
+            // flight, half the votes); on a hit each chunk goes through stage 2 and the line-start search on its own
+#pragma unroll 1
+            for (int u = 0; u < u_end; u += 2) {
+                const int c0 = (u * 32 + lane) * 16;
+                const bool two = u + 1 < u_end;
+                const uint4 wa = lds128(sa + (uint32_t)c0);
+                const uint4 wb = two ? lds128(sa + (uint32_t)c0 + 512u) : make_uint4(0, 0, 0, 0);
+                // the word after each chunk: lane + 1 holds it in a register (the last lane reads it from the window)
+                uint32_t wa4 = __shfl_down_sync(0xFFFFFFFFu, wa.x, 1), wb4 = __shfl_down_sync(0xFFFFFFFFu, wb.x, 1);
+                if (lane == 31) {
+                    wa4 = lds32(sa + (uint32_t)c0 + 16u);
+                    wb4 = lds32(sa + (uint32_t)c0 + 528u);
+                }
+                const uint32_t wsa[5] = {wa.x, wa.y, wa.z, wa.w, wa4}, wsb[5] = {wb.x, wb.y, wb.z, wb.w, wb4};
+                uint32_t za[4], zb[4];
+                const uint32_t ha = key3_stage1(wsa, c4, za, C), hb = key3_stage1(wsb, c4, zb, C);
+                if (__ballot_sync(0xFFFFFFFFu, ((ha | hb) & kC80) != 0) == 0) continue;
+                bool look = (ha & kC80) != 0;
+                if (__ballot_sync(0xFFFFFFFFu, look)) {
+                    look = look && (key3_stage2(wsa, za, C) & kC80) != 0;
+                    if (__ballot_sync(0xFFFFFFFFu, look))
+                        push(look ? pack16_7(nl_flags(wa.x, C), nl_flags(wa.y, C), nl_flags(wa.z, C), nl_flags(wa.w, C)) : 0u, c0);
+                }
+                look = two && (hb & kC80) != 0;
+                if (__ballot_sync(0xFFFFFFFFu, look)) {
+                    look = look && (key3_stage2(wsb, zb, C) & kC80) != 0;
+                    if (__ballot_sync(0xFFFFFFFFu, look))
+                        push(look ? pack16_7(nl_flags(wb.x, C), nl_flags(wb.y, C), nl_flags(wb.z, C), nl_flags(wb.w, C)) : 0u, c0 + 512);
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int u = 0; u < u_end; ++u) {
+                const int c0 = (u * 32 + lane) * 16;
+                const uint4 w = lds128(sa + (uint32_t)c0);
+                bool look = true;
+                if (MODE == kScanKey4) {
+                    uint32_t w4 = __shfl_down_sync(0xFFFFFFFFu, w.x, 1);
+                    if (lane == 31) w4 = lds32(sa + (uint32_t)c0 + 16u);
+                    look = chunk_may_hit_key4(w, w4, key) != 0;
+                    if (__ballot_sync(0xFFFFFFFFu, look) == 0) continue;
+                }
+                push(look ? pack16_7(nl_flags(w.x, C), nl_flags(w.y, C), nl_flags(w.z, C), nl_flags(w.w, C)) : 0u, c0);
+            }
+        }
+        if (qn) drain();
+    };
+
 #pragma unroll 1
     for (uint32_t it = 0; it < my_tiles; ++it) {
         const uint8_t *sm = ring + s * STAGE + kPre;
         mbar_wait(&bars[s], parity);  // lane 0 wrote meta[s] before it armed the barrier
-        const uint8_t *g = meta[s].g;
-        const int lo = meta[s].lo, hi = meta[s].hi;
-        const bool first = lo >= 0;  // first tile of its segment: line 0 has no '\n' before it
-        const int seg_lo = first ? lo : -(1 << 30);
-        const int sm_lo = first ? 0 : -kPre;
-        const int sm_hi = hi < TILE + kHalo ? ((hi + 15) & ~15) : TILE + kHalo;
-
-        if (first && lane == 0 && hi > lo) {
-            if (MODE == kScanLines) {
-                cnt += 1;
-            } else {
-                const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, lo, &a);
-                cnt += (uint32_t)r;
-                err |= (uint32_t)(r >> 32);
-            }
-        }
-        // interior: the tile starts inside the segment at a 16-byte boundary and every staged byte is segment data.
-        // edge: the segment begins and / or ends inside the staged window: same vector path, but '\n' flags outside the
-        // segment are masked and a line that starts within kWindow bytes of the segment's end takes the scalar routine.
-        const bool interior = hi >= TILE + kHalo && lo <= 0;
-        const bool edge = !interior;
+        const uint4 md = lds128(meta_sa + (uint32_t)s * (uint32_t)sizeof(TileDesc));
         const uint32_t sa = ring_sa + (uint32_t)(s * STAGE + kPre);  // shared-window address of tile byte 0
-        const int u_end = hi >= TILE ? U : (hi + 511) >> 9;        // 512-byte rows that hold segment bytes
+        const bool interior = (md.w >> 16) & kTileInterior;
         if (interior && MODE == kScanLines) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -507,97 +643,43 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
                 nl128 = __dp4a(zero_bytes_exact(w.z ^ kNL4), 0x01010101u, nl128);
                 nl128 = __dp4a(zero_bytes_exact(w.w ^ kNL4), 0x01010101u, nl128);
             }
-        } else if (swar_ok && MODE != kScanLines) {
-            // 1. every lane scans its chunks and appends the line starts it finds to the warp's queue;
-            // 2. the queue is drained one line per lane, so the parser runs with (nearly) all lanes busy.
-            int qn = 0;
-            auto drain = [&]() {
-                __syncwarp();
+        } else if (interior && swar_ok) {
+            scan_tile(std::false_type{}, sm, nullptr, -(1 << 30), 1 << 30, -kPre, TILE + kHalo, sa);
+        } else {
+            const uint8_t *g = reinterpret_cast<const uint8_t *>(((unsigned long long)md.y << 32) | md.x);
+            const int lo = (int)(int16_t)(md.w & 0xFFFFu), hi = (int)md.z;
+            const bool first = lo >= 0;  // first tile of its segment: line 0 has no '\n' before it
+            const int seg_lo = first ? lo : -(1 << 30);
+            const int sm_lo = first ? 0 : -kPre;
+            const int sm_hi = hi < TILE + kHalo ? ((hi + 15) & ~15) : TILE + kHalo;
+            if (first && lane == 0 && hi > lo) {
+                if (MODE == kScanLines) {
+                    cnt += 1;
+                } else {
+                    const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, lo, &a);
+                    cnt += (uint32_t)r;
+                    err |= (uint32_t)(r >> 32);
+                }
+            }
+            if (swar_ok && MODE != kScanLines) {
+                scan_tile(std::true_type{}, sm, g, seg_lo, hi, sm_lo, sm_hi, sa);
+            } else {
 #pragma unroll 1
-                for (int i = lane; i < qn; i += 32) {
-                    const int ls = (int)lds16(queue_sa + 2u * (uint32_t)i);
-                    bool slow = edge && ls + kWindow > hi;  // the window would leave the segment
-                    if (!slow) cnt += line_swar<LAZY>(sa, ls, K, P, slow);
-                    if (slow) {
-                        const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, ls, &a);
+                for (int u = 0; u < U; ++u) {
+                    const int c0 = (u * 32 + lane) * 16;
+                    if (c0 < hi && c0 + 16 > seg_lo) {
+                        const unsigned long long r = chunk_careful<MODE>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0, &a);
                         cnt += (uint32_t)r;
                         err |= (uint32_t)(r >> 32);
                     }
                 }
-                __syncwarp();
-                qn = 0;
-            };
-#pragma unroll 2
-            for (int u = 0; u < u_end; ++u) {
-                const int c0 = (u * 32 + lane) * 16;
-                const uint4 w = lds128(sa + (uint32_t)c0);
-                bool look = true;
-                if (LAZY) {
-                    // the word after the chunk: lane + 1 holds it in a register (the last lane reads it from the window)
-                    uint32_t w4 = __shfl_down_sync(0xFFFFFFFFu, w.x, 1);
-                    if (lane == 31) w4 = lds32(sa + (uint32_t)c0 + 16u);
-                    if (MODE == kScanKey3) {
-                        // stage 1: '\n' followed by the name byte somewhere in the chunk? (never, outside the name's block of contigs)
-                        const uint32_t ws[5] = {w.x, w.y, w.z, w.w, w4};
-                        uint32_t v[5], z[4], h = 0;
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) v[k] = ws[k] ^ c4;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            z[k] = (ws[k] ^ kNL4) | fma_funnel(v[k], v[k + 1], P.m24);
-                            h = zero_acc(h, z[k], P);
-                        }
-                        look = (h & kC80) != 0;
-                        if (__ballot_sync(0xFFFFFFFFu, look) == 0) continue;
-                        // stage 2: ... and a tab right behind it (the exact 3-byte pattern, up to borrow artefacts)
-                        uint32_t h2 = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            h2 = zero_acc(h2, z[k] | fma_funnel(ws[k] ^ kTAB4, ws[k + 1] ^ kTAB4, P.m16), P);
-                        look = (h2 & kC80) != 0;
-                    } else {
-                        look = chunk_may_hit_key4(w, w4, key) != 0;
-                    }
-                    if (__ballot_sync(0xFFFFFFFFu, look) == 0) continue;
-                }
-                uint32_t m = 0;
-                if (look) m = pack16_7(nl_flags(w.x, P), nl_flags(w.y, P), nl_flags(w.z, P), nl_flags(w.w, P));
-                if (edge) {
-                    // keep '\n' at positions p with seg_lo <= p and p + 1 < hi (bit 7 + i of m is byte c0 + i)
-                    const int lo_i = seg_lo - c0, hi_i = hi - 1 - c0;  // valid i: lo_i <= i < hi_i
-                    uint32_t keep = hi_i >= 16 ? 0xFFFFu : (hi_i <= 0 ? 0u : (1u << hi_i) - 1u);
-                    if (lo_i > 0) keep &= lo_i >= 16 ? 0u : ~((1u << lo_i) - 1u);
-                    m &= keep << 7;
-                }
-                const uint32_t b = __ballot_sync(0xFFFFFFFFu, m != 0);
-                if (m) {
-                    sts16(queue_sa + 2u * (uint32_t)(qn + __popc(b & lt_mask)), (uint32_t)(c0 + __ffs(m) - 7));  // line = byte after '\n'
-                    m &= m - 1;
-                }
-                qn += __popc(b);
-                // further line starts in the same 16 bytes (lines shorter than 16 bytes) take the scalar routine
-                while (m) {
-                    const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0 + __ffs(m) - 7, &a);
-                    m &= m - 1;
-                    cnt += (uint32_t)r;
-                    err |= (uint32_t)(r >> 32);
-                }
-                if (qn > kQueue - 32) drain();
-            }
-            if (qn) drain();
-        } else {
-#pragma unroll 1
-            for (int u = 0; u < U; ++u) {
-                const int c0 = (u * 32 + lane) * 16;
-                if (c0 < hi && c0 + 16 > seg_lo) {
-                    const unsigned long long r = chunk_careful<MODE>(sm, g, seg_lo, hi, sm_lo, sm_hi, c0, &a);
-                    cnt += (uint32_t)r;
-                    err |= (uint32_t)(r >> 32);
-                }
             }
         }
         __syncwarp();
-        if (lane == 0 && it + S < my_tiles) issue(s);
+        if (lane == 0 && p_issued < my_tiles) {
+            issue(s);
+            fetch();
+        }
         if (++s == S) {
             s = 0;
             parity ^= 1;
@@ -660,6 +742,13 @@ cudaError_t launch_mode(const ScanArgs &args, ScanMode mode, int ctas, int sm_co
 }
 
 }  // namespace
+
+cudaError_t launch_build_tile_descs(const ScanSeg *d_segs, int n_segs, int64_t n_tiles, int variant, TileDesc *d_out, cudaStream_t stream) {
+    if (n_tiles <= 0) return cudaSuccess;
+    const int tile = scan_tile_bytes(variant);
+    build_tile_descs_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, stream>>>(d_segs, n_segs, n_tiles, tile, d_out);
+    return cudaGetLastError();
+}
 
 int scan_variant_count() { return kNumVariants; }
 const char *scan_variant_name(int v) { return (v >= 0 && v < kNumVariants) ? kVariants[v].name : "?"; }

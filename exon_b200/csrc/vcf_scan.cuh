@@ -16,6 +16,15 @@ struct ScanSeg {
     int32_t pad_;
 };
 
+// One tile of the launch-wide tile numbering (built on the device from the segment table, vcf_scan.cu).
+struct TileDesc {
+    const uint8_t *src;  // global address of tile byte 0 (16-byte aligned)
+    int32_t hi;          // bytes from tile byte 0 to the end of the segment (clamped to 2^30)
+    int16_t lo;          // first tile of its segment: the segment's skip (0..15); otherwise -16 (the pre-halo is staged)
+    uint16_t flags;      // kTileInterior
+};
+constexpr uint16_t kTileInterior = 1;  // every staged byte is segment data and the tile starts at a 16-byte boundary inside it
+
 constexpr int kMaxChrom = 255;
 
 // error bits accumulated in ScanAcc::flags
@@ -50,7 +59,7 @@ struct ScanTail {
 };
 
 struct ScanArgs {
-    const ScanSeg *segs;  // device array, n_segs + 1 entries (the last one carries tile0 = n_tiles, len = 0)
+    const TileDesc *tiles;  // device array, n_tiles entries (launch_build_tile_descs)
     int32_t n_segs;
     int64_t n_tiles;
     int32_t has_chrom, has_interval;
@@ -79,6 +88,8 @@ int scan_tile_bytes(int variant);
 // Enqueue the fused scan on `stream`.  With n_tiles == 0 and tail.finalize only the tail runs (one warp).
 cudaError_t launch_vcf_scan(const ScanArgs &args, ScanMode mode, const ScanConfig &cfg, int sm_count,
                             cudaStream_t stream);
+// Fills d_out[0 .. n_tiles) from a segment table (n_segs + 1 entries, the last one a sentinel with tile0 = n_tiles).
+cudaError_t launch_build_tile_descs(const ScanSeg *d_segs, int n_segs, int64_t n_tiles, int variant, TileDesc *d_out, cudaStream_t stream);
 // registers / smem / occupancy report for DESIGN.md and tests
 int scan_variant_count();
 const char *scan_variant_name(int variant);

@@ -251,7 +251,17 @@ static void fill_segs(const std::vector<Run> &runs, size_t first, size_t last, i
     *n_tiles = t;
 }
 
-static int upload_segs(VcfStream *s, const std::vector<ScanSeg> &h) {
+// Uploads a segment table and derives the tile descriptors the scan kernel's producers read (vcf_scan.cu).
+static int upload_segs(VcfStream *s, const std::vector<ScanSeg> &h, int64_t n_tiles) {
+    if ((size_t)n_tiles > s->d_tiles_cap) {
+        if (s->d_tiles) {
+            CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+            CUDA_TRY(cudaFree(s->d_tiles));
+            s->d_tiles = nullptr;
+        }
+        s->d_tiles_cap = std::max<size_t>((size_t)n_tiles + (size_t)n_tiles / 4, 1024);
+        CUDA_TRY(cudaMalloc((void **)&s->d_tiles, s->d_tiles_cap * sizeof(TileDesc)));
+    }
     if (h.size() > s->d_segs_cap) {
         if (s->d_segs) {
             CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
@@ -262,6 +272,8 @@ static int upload_segs(VcfStream *s, const std::vector<ScanSeg> &h) {
         CUDA_TRY(cudaMalloc((void **)&s->d_segs, s->d_segs_cap * sizeof(ScanSeg)));
     }
     CUDA_TRY(cudaMemcpyAsync(s->d_segs, h.data(), h.size() * sizeof(ScanSeg), cudaMemcpyHostToDevice, s->ctx->stream));
+    CUDA_TRY(launch_build_tile_descs(s->d_segs, (int)h.size() - 1, n_tiles, s->variant, s->d_tiles, s->ctx->stream));
+    if (n_tiles > 0) s->ctx->launches.fetch_add(1);
     return EXON_GPU_OK;
 }
 
@@ -269,18 +281,18 @@ int VcfStream::build_seg_table() {
     const int tile = scan_tile_bytes(variant);
     if (!segs_dirty && seg_variant == variant) return EXON_GPU_OK;
     fill_segs(runs, 0, runs.size(), 0, -1, tile, h_segs, &n_tiles);
-    if (int rc = upload_segs(this, h_segs)) return rc;
+    if (int rc = upload_segs(this, h_segs, n_tiles)) return rc;
     segs_dirty = false;
     seg_variant = variant;
     return EXON_GPU_OK;
 }
 
-int VcfStream::launch_scan(const OwnedRegion &r, const ScanSeg *d_table, int n_segs, int64_t tiles, ScanAcc *acc,
+int VcfStream::launch_scan(const OwnedRegion &r, const TileDesc *d_table, int n_segs, int64_t tiles, ScanAcc *acc,
                            const ScanTail &tail) {
     if (tiles <= 0 && !tail.finalize) return EXON_GPU_OK;
     ScanArgs a;
     memset(&a, 0, sizeof(a));
-    a.segs = d_table;
+    a.tiles = d_table;
     a.n_segs = n_segs;
     a.n_tiles = tiles;
     a.has_chrom = r.has_chrom;
@@ -325,9 +337,9 @@ int VcfStream::eager_scan(bool final_flush) {
             int64_t tiles = 0;
             fill_segs(runs, i, i + 1, eager_scanned, upto, tile, h, &tiles);
             // table slots for eager launches live behind the lazy table: reuse d_segs' tail via a private buffer
-            if (int rc = upload_segs(this, h)) return rc;
+            if (int rc = upload_segs(this, h, tiles)) return rc;
             segs_dirty = true;  // the lazy table was overwritten
-            if (int rc = launch_scan(pushdown, d_segs, (int)h.size() - 1, tiles, reinterpret_cast<ScanAcc *>(d_res + 4), accumulate_only))
+            if (int rc = launch_scan(pushdown, d_tiles, (int)h.size() - 1, tiles, reinterpret_cast<ScanAcc *>(d_res + 4), accumulate_only))
                 return rc;
             eager_scanned = upto;
         }
@@ -413,7 +425,7 @@ int VcfStream::run_query(const exon_gpu_region *region, int64_t *device_out, boo
         }
         return rc;
     }
-    if (int rc2 = launch_scan(r, scan ? d_segs : nullptr, scan ? (int)h_segs.size() - 1 : 0, scan ? n_tiles : 0, acc, tail)) return rc2;
+    if (int rc2 = launch_scan(r, scan ? d_tiles : nullptr, scan ? (int)h_segs.size() - 1 : 0, scan ? n_tiles : 0, acc, tail)) return rc2;
     if (nccl_fallback) {
         CUDA_TRY(cudaMemcpyAsync(d_res + 9, d_res + 8, sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
         if (int rc2 = nccl_allreduce_i64(ctx, reinterpret_cast<int64_t *>(d_res + 9), 1)) return rc2;
