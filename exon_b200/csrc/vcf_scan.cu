@@ -423,7 +423,7 @@ __global__ void build_tile_descs_kernel(const ScanSeg *segs, int n_segs, int64_t
     d.src = sg.base + off;
     d.hi = rem > (1 << 30) ? (1 << 30) : (int32_t)rem;
     d.lo = (int16_t)(t ? -kPre : sg.skip);
-    d.flags = (uint16_t)((rem >= tile + kHalo && (t || sg.skip == 0)) ? kTileInterior : 0);
+    d.flags = (uint16_t)((rem >= tile + kHalo && t) ? kTileInterior : 0);  // a segment's first tile is never interior: its first line has no '\n' before it
     out[T] = d;
 }
 
