@@ -328,7 +328,6 @@ __device__ __forceinline__ void scan_finalize(ScanAcc *acc, const ScanTail &t) {
         if (t.finalize == 1) {  // leave the accumulator zeroed for the next query on this stream
             local = atomicExch(&acc->count, 0ull);
             flags = atomicExch(&acc->flags, 0ull);
-            atomicExch(&acc->ticket, 0ull);
         } else {                // pushdown accumulator: keeps growing with later feeds
             local = atomicAdd(&acc->count, 0ull);
             flags = atomicAdd(&acc->flags, 0ull);
@@ -381,7 +380,8 @@ __device__ __forceinline__ void scan_finalize(ScanAcc *acc, const ScanTail &t) {
 // of the query (pushdown feeds) still publish / exchange through the same code.
 __global__ void __launch_bounds__(32) scan_finish_kernel(ScanAcc *acc, const ScanTail t) { scan_finalize(acc, t); }
 
-// Adds one CTA's partials to the query accumulator; in a finalising launch the CTA that arrives last runs the tail.
+// Adds one CTA's partials to the query accumulator.  The CTA that arrives last re-arms the launch-scoped counters (CTA
+// ticket, tile ticket) for the next launch on this accumulator and, in a finalising launch, runs the tail.
 // Called by warp 0 after a block-wide barrier.
 __device__ __forceinline__ void scan_block_epilogue(const ScanArgs &a, unsigned long long cnt, unsigned long long err) {
     const int lane = threadIdx.x & 31;
@@ -389,13 +389,15 @@ __device__ __forceinline__ void scan_block_epilogue(const ScanArgs &a, unsigned 
     if (lane == 0) {
         if (cnt) atomicAdd(&a.acc->count, cnt);
         if (err) atomicOr(&a.acc->flags, err);
-        if (a.tail.finalize) {
-            __threadfence();
-            last = atomicAdd(&a.acc->ticket, 1ull) == (unsigned long long)gridDim.x - 1ull;
+        __threadfence();
+        last = atomicAdd(&a.acc->ticket, 1ull) == (unsigned long long)gridDim.x - 1ull;
+        if (last) {
+            atomicExch(&a.acc->ticket, 0ull);
+            atomicExch(&a.acc->next_tile, 0ull);
         }
     }
     last = __shfl_sync(0xFFFFFFFFu, last, 0);
-    if (last) {
+    if (last && a.tail.finalize) {
         __threadfence();
         scan_finalize(a.acc, a.tail);
     }
@@ -498,12 +500,27 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
     }
     const bool swar_ok = !a.has_chrom || a.chrom_len <= 11;  // longer names do not fit the window's pattern words
 
-    // ---- producer (lane 0): tiles wg, wg + nw, ...; the descriptor of the next tile to stage is fetched one step ahead ----
-    const uint32_t my_tiles = a.n_tiles > (int64_t)wg ? (uint32_t)((a.n_tiles - 1 - (int64_t)wg) / nw) + 1u : 0u;
-    uint32_t p_issued = 0;  // tiles staged so far
+    // ---- producer (lane 0) ----------------------------------------------------------------------------------------------
+    // Tiles [0, R * nw) are dealt round-robin (tile wg + r * nw in round r, no communication); the rest -- about an eighth of
+    // the launch -- is handed out through an atomic ticket, so that warps on faster SMs (and warps that met no slow tile) take
+    // more of the tail instead of waiting for the slowest one.  Everything is fetched ahead: while tile i is parsed, the
+    // descriptor of the tile to stage next is already in registers and the ticket after that is in flight.
+    const uint32_t n_tiles = (uint32_t)a.n_tiles, R = a.static_rounds, dyn_base = R * nw;
+    unsigned int *ticket_ctr = reinterpret_cast<unsigned int *>(&a.acc->next_tile);
+    uint32_t p_round = 0;         // static rounds handed out so far
+    uint32_t p_next = 0xFFFFFFFFu;  // tile whose descriptor is fetched next (>= n_tiles: none)
+    bool pd_valid = false;
     uint4 pd = make_uint4(0, 0, 0, 0);
-    auto fetch = [&]() {  // lane 0: descriptor of tile number p_issued of this warp
-        if (p_issued < my_tiles) pd = __ldg(reinterpret_cast<const uint4 *>(a.tiles + ((size_t)wg + (size_t)p_issued * nw)));
+    auto advance = [&]() {  // lane 0: the tile after p_next
+        if (p_round < R) p_next = wg + (p_round++) * nw;
+        else p_next = dyn_base + atomicAdd(ticket_ctr, 1u);
+    };
+    auto fetch = [&]() {  // lane 0: descriptor of tile p_next into pd, then ask for the tile after it
+        pd_valid = p_next < n_tiles;
+        if (pd_valid) {
+            pd = __ldg(reinterpret_cast<const uint4 *>(a.tiles + p_next));
+            advance();
+        }
     };
     auto issue = [&](int s) {  // lane 0 only: stage the tile described by pd into slot s
         const uint8_t *src = reinterpret_cast<const uint8_t *>(((unsigned long long)pd.y << 32) | pd.x);
@@ -514,18 +531,22 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
         *reinterpret_cast<uint4 *>(&meta[s]) = pd;
         mbar_arrive_expect_tx(&bars[s], bytes);
         bulk_g2s(ring + s * STAGE + (kPre - pre), src - pre, bytes, &bars[s]);
-        ++p_issued;
     };
 
+    int pending = 0;  // slots in flight (warp-uniform)
     if (lane == 0) {
+        advance();
+        fetch();
 #pragma unroll 1
         for (int s = 0; s < S; ++s) {
-            fetch();
-            if (p_issued < my_tiles) issue(s);
+            if (pd_valid) {
+                issue(s);
+                ++pending;
+                fetch();
+            }
         }
-        fetch();
     }
-    __syncwarp();
+    pending = __shfl_sync(0xFFFFFFFFu, pending, 0);
 
     uint32_t cnt = 0, err = 0, nl128 = 0;
     uint32_t parity = 0;
@@ -629,7 +650,7 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
     };
 
 #pragma unroll 1
-    for (uint32_t it = 0; it < my_tiles; ++it) {
+    while (pending > 0) {
         const uint8_t *sm = ring + s * STAGE + kPre;
         mbar_wait(&bars[s], parity);  // lane 0 wrote meta[s] before it armed the barrier
         const uint4 md = lds128(meta_sa + (uint32_t)s * (uint32_t)sizeof(TileDesc));
@@ -677,10 +698,13 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
             }
         }
         __syncwarp();
-        if (lane == 0 && p_issued < my_tiles) {
+        int staged = 0;
+        if (lane == 0 && pd_valid) {
             issue(s);
             fetch();
+            staged = 1;
         }
+        pending += __shfl_sync(0xFFFFFFFFu, staged, 0) - 1;
         if (++s == S) {
             s = 0;
             parity ^= 1;
@@ -727,7 +751,11 @@ cudaError_t launch_one(const ScanArgs &args, int ctas, int sm_count, cudaStream_
     const int64_t need = (args.n_tiles + W - 1) / W;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, W * 32, smem, stream>>>(args);
+    if (args.n_tiles >= (int64_t)0xF0000000u) return cudaErrorInvalidValue;  // tile numbers are 32-bit (4 KiB tiles: 15 TB per launch)
+    ScanArgs a2 = args;
+    const int64_t nw = grid * W, rounds = args.n_tiles / nw;  // full rounds of the round-robin deal
+    a2.static_rounds = (uint32_t)(rounds - (rounds + 7) / 8);  // the last eighth (at least one round) goes through the ticket
+    kern<<<(unsigned)grid, W * 32, smem, stream>>>(a2);
     return cudaGetLastError();
 }
 

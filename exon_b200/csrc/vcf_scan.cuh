@@ -36,8 +36,8 @@ constexpr uint32_t kErrShortLine = 2u;   // the line ended before the field bein
 struct ScanAcc {
     unsigned long long count;   // rows selected so far
     unsigned long long flags;   // kErr* bits
-    unsigned long long ticket;  // CTAs of the finalising launch that have added their partials
-    unsigned long long pad_;
+    unsigned long long ticket;  // CTAs of the running launch that have added their partials (the last one re-arms both tickets)
+    unsigned long long next_tile;  // tile ticket of the running launch: tiles beyond the statically dealt rounds (vcf_scan.cu)
 };
 
 // Words of the result record the finalising CTA writes to MAPPED PINNED host memory (the host polls the sequence word:
@@ -67,6 +67,7 @@ struct ScanArgs {
     int32_t chrom_len;
     int32_t pat_len;             // chrom_len + 2
     uint8_t pat[kMaxChrom + 5];  // '\n' + chrom + '\t'
+    uint32_t static_rounds;      // set by launch_vcf_scan: rounds of the round-robin tile deal before the ticket takes over
     ScanAcc *acc;
     ScanTail tail;
 };
