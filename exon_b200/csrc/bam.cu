@@ -329,7 +329,7 @@ int VcfStream::bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, 
         for (int32_t g = 0; g < std::min(cap, n_groups); ++g) counts[g] = 0;
     if (counts && cap < n_groups) return fail(EXON_GPU_ERR_ARG, "bam_filter_count: %d groups, room for %d", n_groups, cap);
     if (bam_n_entries == 0) return EXON_GPU_OK;
-    std::lock_guard<std::mutex> work(c->work_mu);
+    std::lock_guard<std::recursive_mutex> work(c->work_mu);
     if (int rc = c->ensure_scratch(0, 256 + (size_t)n_groups * 8)) return rc;
     uint8_t *d = (uint8_t *)d_bam;
     BamArgs a;
@@ -1032,7 +1032,7 @@ int bam_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     if (!s->bam_cols) {
         int64_t rows = 0;
         if (int rc = s->bam_filter_count(nullptr, nullptr, 0, nullptr, &rows)) return rc;  // verified walks (and flush_gz)
-        std::lock_guard<std::mutex> work(s->ctx->work_mu);
+        std::lock_guard<std::recursive_mutex> work(s->ctx->work_mu);
         if (int rc = bam_build_columns(s)) {
             bam_columns_free(s);
             return rc;

@@ -278,6 +278,7 @@ int VcfStream::launch_gz() {
         CUDA_TRY(cudaMemcpyAsync(dt + g.tab_bytes, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaEventRecord(gz_copied_ev, gz_copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(st, gz_copied_ev, 0));
+        std::lock_guard<std::recursive_mutex> work(ctx->work_mu);  // the match bitmap is a context-wide area
         if (int rc = bgzf_inflate_launch(ctx, (const uint8_t *)d_gz_buf[buf], (const BgzfMember *)dt, (int)g.members.size(), (uint32_t *)(dt + g.tab_bytes),
                                          bm_words, comp_bytes)) {
             cudaFreeAsync(g.d_tab, st);
@@ -301,6 +302,7 @@ int VcfStream::flush_gz() {
 
 int VcfStream::harvest_gz() {
     if (gz_inflight.empty()) return EXON_GPU_OK;
+    std::lock_guard<std::recursive_mutex> work(ctx->work_mu);  // the pinned probe area (h_scratch) is context-wide
     cudaStream_t st = ctx->stream;
     std::vector<GzGroup> groups;
     groups.swap(gz_inflight);
@@ -412,7 +414,7 @@ extern "C" int exon_gpu_gzip_inflate(exon_gpu_ctx *c, const uint8_t *data, size_
     *out_len = (size_t)total;
     if (total == 0) return EXON_GPU_OK;
     if (!out || out_cap < total) return fail(EXON_GPU_ERR_ARG, "gzip_inflate: output buffer too small (%llu bytes needed)", (unsigned long long)total);
-    std::lock_guard<std::mutex> work(c->work_mu);
+    std::lock_guard<std::recursive_mutex> work(c->work_mu);
     const size_t o_tab = (len + 16 + 255) & ~(size_t)255;
     const size_t o_flags = o_tab + ((members.size() * sizeof(BgzfMember) + 255) & ~(size_t)255);
     const size_t o_out = o_flags + 256;

@@ -82,7 +82,7 @@ int fasta_rows(VcfStream *s, int64_t *out_rows) {
     if (int rc = s->flush_gz()) return rc;
     Ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    std::lock_guard<std::mutex> work(ctx->work_mu);
+    std::lock_guard<std::recursive_mutex> work(ctx->work_mu);
     *out_rows = 0;
     std::vector<Piece> pieces;
     s->cut_pieces(pieces);

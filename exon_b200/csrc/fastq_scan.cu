@@ -349,7 +349,7 @@ int fastq_filter_count(VcfStream *s, const exon_gpu_fastq_pred *pred, int64_t *o
     cudaStream_t st = ctx->stream;
     if (int rc = s->flush_gz()) return rc;
     if (pred && (pred->min_mean_den <= 0)) return fail(EXON_GPU_ERR_ARG, "fastq_filter_count: min_mean_den must be positive");
-    std::lock_guard<std::mutex> work(ctx->work_mu);
+    std::lock_guard<std::recursive_mutex> work(ctx->work_mu);
     std::vector<Piece> pieces;
     s->cut_pieces(pieces);
     if (out_count) *out_count = 0;
@@ -1007,7 +1007,7 @@ int build_line_index(VcfStream *s, size_t extra_per_line, size_t extra_fixed, Li
 int fastq_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     if (!s->fq_cols) {
         if (int rc = s->flush_gz()) return rc;
-        std::lock_guard<std::mutex> work(s->ctx->work_mu);
+        std::lock_guard<std::recursive_mutex> work(s->ctx->work_mu);
         if (int rc = s->fmt == kFmtFasta ? fasta_build_columns(s) : fq_build_columns(s)) {
             fq_columns_free(s);
             return rc;

@@ -463,7 +463,7 @@ int exon_gpu_filter_agg_batches(exon_gpu_ctx *c, const struct ArrowArray *const 
     CUDA_TRY(cudaSetDevice(c->device));
     if (agg->kind < EXON_GPU_AGG_COUNT_STAR || agg->kind > EXON_GPU_AGG_AVG)
         return fail(EXON_GPU_ERR_ARG, "filter_agg_batches: unknown aggregate kind %d", agg->kind);
-    std::lock_guard<std::mutex> work(c->work_mu);
+    std::lock_guard<std::recursive_mutex> work(c->work_mu);
     std::vector<FaBatchDesc> descs((size_t)n_batches);
     FaCommon k;
     if (int rc = fa_common_from(pred, agg, k)) return rc;

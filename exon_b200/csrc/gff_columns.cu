@@ -543,7 +543,7 @@ void gff_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
 int gff_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     if (!s->gff_cols) {
         if (int rc = s->flush_gz()) return rc;
-        std::lock_guard<std::mutex> work(s->ctx->work_mu);
+        std::lock_guard<std::recursive_mutex> work(s->ctx->work_mu);
         if (int rc = gff_build_columns(s)) {
             gff_columns_free(s);
             return rc;

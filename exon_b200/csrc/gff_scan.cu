@@ -134,7 +134,7 @@ int gff_filter_count(VcfStream *s, const exon_gpu_region *region, int64_t *out_c
     if (int rc = s->flush_gz()) return rc;
     Ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    std::lock_guard<std::mutex> work(ctx->work_mu);
+    std::lock_guard<std::recursive_mutex> work(ctx->work_mu);
     if (out_count) *out_count = 0;
     if (out_rows) *out_rows = 0;
     OwnedRegion r;

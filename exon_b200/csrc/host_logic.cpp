@@ -50,7 +50,9 @@ extern "C" {
 
 // noodles-core Region::from_str at its reference call sites
 // (exon/exon-core/src/physical_plan/infer_region.rs:25-42, exon/exon-core/src/udfs/vcf/mod.rs:85-95):
-// the text after the LAST ':' is the interval if it parses as one, otherwise the whole string is the name.
+// the text after the LAST ':' is the interval if it parses as one, otherwise the whole string is the name.  As in
+// noodles-core 0.15 (`rsplit_once(':')`, `Interval::from_str("")` = unbounded) an EMPTY suffix parses: "chr1:" is the
+// contig "chr1" with an open interval, ":5-9" an empty name with an interval (it matches no CHROM).
 int exon_gpu_region_parse(const char *s, char *name_buf, size_t name_buf_len, exon_gpu_region *out) {
     if (!s || !name_buf || !out) return fail(EXON_GPU_ERR_ARG, "region_parse: NULL argument");
     const size_t n = strlen(s);
@@ -60,7 +62,7 @@ int exon_gpu_region_parse(const char *s, char *name_buf, size_t name_buf_len, ex
     int64_t lo = 1, hi = INT64_MAX;
     int has_interval = 0;
     const char *colon = strrchr(s, ':');
-    if (colon && colon != s && colon[1] != '\0') {
+    if (colon) {
         int64_t a, b;
         if (parse_interval(colon + 1, n - (size_t)(colon - s) - 1, &a, &b)) {
             name_len = (size_t)(colon - s);

@@ -57,23 +57,35 @@ __constant__ uint8_t c_clen_order2[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 
 __device__ __forceinline__ void prefetch_line(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct LaneBits {
-    const uint32_t *wp;  // next word to load
-    const uint32_t *w0;  // aligned word the stream started in
+    const uint32_t *wp;    // next word to load
+    const uint32_t *w0;    // aligned word the MEMBER started in (bits_consumed() counts from there, across stored blocks)
+    const uint32_t *wend;  // last word that holds payload bytes: nothing beyond it is ever read (zeros are fed instead), so a
+                           // corrupt or truncated stream cannot run off the staging buffer; the decoder notices the overrun
+                           // through overrun() / bits_consumed()
     uint32_t lo, hi, nxt;
     int bp;
     int mis8;
-    __device__ __forceinline__ void init(const uint8_t *p) {
+    __device__ __forceinline__ uint32_t load(const uint32_t *p) const { return p <= wend ? __ldg(p) : 0u; }
+    // position the reader at byte p of the same member (p >= the member's first byte)
+    __device__ __forceinline__ void seek(const uint8_t *p) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const int mis = (int)(a & 3);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(a - mis);
+        lo = load(w);
+        hi = load(w + 1);
+        nxt = load(w + 2);
+        wp = w + 3;
+        bp = 8 * mis;
+        prefetch_line(w + 32);
+        prefetch_line(w + 64);
+    }
+    __device__ __forceinline__ void init(const uint8_t *p, uint32_t payload_bytes) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(p);
         const int mis = (int)(a & 3);
         w0 = reinterpret_cast<const uint32_t *>(a - mis);
-        lo = __ldg(w0);
-        hi = __ldg(w0 + 1);
-        nxt = __ldg(w0 + 2);
-        wp = w0 + 3;
-        bp = 8 * mis;
         mis8 = 8 * mis;
-        prefetch_line(w0 + 32);
-        prefetch_line(w0 + 64);
+        wend = payload_bytes ? reinterpret_cast<const uint32_t *>((a + payload_bytes - 1) & ~(uintptr_t)3) : w0 - 1;
+        seek(p);
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, bp); }
     __device__ __forceinline__ void skip(int n) {  // n <= 32
@@ -81,7 +93,8 @@ struct LaneBits {
         if (bp >= 32) {
             lo = hi;
             hi = nxt;
-            nxt = __ldg(wp++);
+            nxt = load(wp);
+            ++wp;
             bp -= 32;
             // every lane streams its own member: without this, some lane of the warp misses L1 at almost every refill
             if ((reinterpret_cast<uintptr_t>(wp) & 127u) == 0) prefetch_line(wp + 32);
@@ -93,6 +106,8 @@ struct LaneBits {
         return v;
     }
     __device__ __forceinline__ int64_t bits_consumed() const { return ((int64_t)(wp - 3 - w0) << 5) + bp - mis8; }
+    // the word being consumed lies wholly beyond the payload: every further bit is a fed zero
+    __device__ __forceinline__ bool overrun() const { return wp - 3 > wend; }
     __device__ __forceinline__ const uint8_t *byte_ptr() const {  // only meaningful when bp % 8 == 0
         return reinterpret_cast<const uint8_t *>(wp - 3) + (bp >> 3);
     }
@@ -200,7 +215,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
         uint32_t *bm = bitmap + M.bm_off;
         uint32_t bm_wi = 0, bm_w = 0;
         LaneBits br;
-        br.init(comp + M.in_off);
+        br.init(comp + M.in_off, M.in_len);
         const int64_t in_bits = (int64_t)M.in_len * 8;
         uint32_t pos = 0, err = 0;
         bool last = false;
@@ -226,7 +241,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                 const uint8_t *src = br.byte_ptr();
                 for (uint32_t j = 0; j < len; ++j) out[pos + j] = __ldg(src + j);
                 pos += len;
-                br.init(src + len);
+                br.seek(src + len);  // bits_consumed() keeps counting from the member's start
                 continue;
             }
             if (btype == 1) {
@@ -302,6 +317,10 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
             // ---- symbols ----
 #pragma unroll 1
             while (true) {
+                if (br.overrun()) {  // the stream ran off its payload (truncated or corrupt member): stop now, not after ISIZE symbols
+                    err = kInfErrData;
+                    break;
+                }
                 uint32_t w = br.peek();
                 uint32_t e = T.lit[w & ((1u << LB) - 1u)];
                 if (!e) {

@@ -48,7 +48,7 @@ struct Ctx {
         return e;
     }
     std::mutex mu;
-    std::mutex work_mu;  // serialises users of the context-wide scratch areas (K2 build, K3 calls)
+    std::recursive_mutex work_mu;  // serialises users of the context-wide scratch areas (scratch, h_scratch, scratch_b, inf_bitmap); recursive: framing helpers that need it are reached both with and without it held
     std::vector<DevBlock> free_blocks;
     // scratch for filter_agg / allreduce
     void *scratch = nullptr;

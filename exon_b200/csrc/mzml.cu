@@ -383,6 +383,15 @@ __global__ void __launch_bounds__(256) mzml_sum_kernel(const SpecDesc *specs, un
 
 
 // ---- zlib detour ----------------------------------------------------------------------------------------------------
+// Inflated size of a zlib array: defaultArrayLength x value width, computed in 64 bits and clamped to what DEFLATE can
+// expand `comp` bytes to (at most 1032 : 1) and to 1 GiB.  defaultArrayLength is an untrusted XML attribute: an absurd
+// value must not wrap the int32 size scans (and with them the output and bitmap allocations); a clamped size differs
+// from what the stream inflates to, so the array fails the inflate kernels' size check and the query reports it.
+__device__ __forceinline__ uint32_t zarr_isize(uint32_t n_default, bool f32, uint32_t comp) {
+    const unsigned long long want = (unsigned long long)n_default * (f32 ? 4ull : 8ull);
+    const unsigned long long cap = ((1032ull * comp + 64ull) < (1ull << 30) ? (1032ull * comp + 64ull) : (1ull << 30));
+    return (uint32_t)(want < cap ? want : cap);
+}
 struct ZArr {
     uint32_t spec, which;  // which: 0 = m/z, 1 = intensity
 };
@@ -400,7 +409,7 @@ __global__ void mzml_zlist_kernel(const SpecDesc *specs, unsigned long long n_sp
         if (k >= cap) continue;
         list[k] = ZArr{(uint32_t)i, which};
         const uint32_t comp = b64_bytes(p, which ? d.in_len : d.mz_len);
-        const uint32_t isize = d.n_default * ((which ? d.in_f32 : d.mz_f32) ? 4u : 8u);
+        const uint32_t isize = zarr_isize(d.n_default, which ? d.in_f32 : d.mz_f32, comp);
         sizes[k] = (int32_t)((comp + 64u + 15u) & ~15u);
         sizes[cap + 1 + k] = (int32_t)((isize + 15u) & ~15u);
         sizes[2 * (cap + 1) + k] = (int32_t)((isize + 31u) / 32u);
@@ -454,7 +463,7 @@ __global__ void mzml_ztable_kernel(SpecDesc *specs, const ZArr *list, unsigned l
     SpecDesc &d = specs[list[k].spec];
     const bool in = list[k].which != 0;
     const uint32_t nbytes = b64_bytes(in ? d.in : d.mz, in ? d.in_len : d.mz_len);
-    const uint32_t isize = d.n_default * ((in ? d.in_f32 : d.mz_f32) ? 4u : 8u);
+    const uint32_t isize = zarr_isize(d.n_default, in ? d.in_f32 : d.mz_f32, nbytes);
     const uint8_t *z = comp + comp_off[k];
     BgzfMember m;
     m.in_off = (uint64_t)comp_off[k] + 2u;
@@ -480,7 +489,7 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
     if (int rc = s->flush_gz()) return rc;
     Ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    std::lock_guard<std::mutex> work(ctx->work_mu);
+    std::lock_guard<std::recursive_mutex> work(ctx->work_mu);
     if (out_sum) *out_sum = 0.0;
     if (out_selected) *out_selected = 0;
     if (out_spectra) *out_spectra = 0;

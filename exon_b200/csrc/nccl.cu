@@ -223,6 +223,7 @@ int exon_gpu_allreduce_partial(exon_gpu_ctx *c, exon_gpu_partial *inout) {
     if (!c || !inout) return fail(EXON_GPU_ERR_ARG, "allreduce_partial: NULL argument");
     if (!c->nccl_comm) return fail(EXON_GPU_ERR_STATE, "allreduce_partial: exon_gpu_nccl_init has not been called");
     CUDA_TRY(cudaSetDevice(c->device));
+    std::lock_guard<std::recursive_mutex> work(c->work_mu);
     if (int rc = c->ensure_scratch(64, 64)) return rc;
     static_assert(sizeof(exon_gpu_partial) == 24, "partial is {i64, i64, f64}");
     memcpy(c->h_scratch, inout, sizeof(*inout));
@@ -245,7 +246,7 @@ int exon_gpu_allreduce_counts(exon_gpu_ctx *c, int64_t *inout, int32_t n) {
     if (!c->nccl_comm) return fail(EXON_GPU_ERR_STATE, "allreduce_counts: exon_gpu_nccl_init has not been called");
     if (n == 0) return EXON_GPU_OK;
     CUDA_TRY(cudaSetDevice(c->device));
-    std::lock_guard<std::mutex> work(c->work_mu);
+    std::lock_guard<std::recursive_mutex> work(c->work_mu);
     const size_t bytes = (size_t)n * sizeof(int64_t);
     if (int rc = c->ensure_scratch(bytes, bytes)) return rc;
     memcpy(c->h_scratch, inout, bytes);

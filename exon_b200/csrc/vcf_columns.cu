@@ -756,7 +756,7 @@ static int ensure_columns(VcfStream *s) {
     if (int rc = s->flush_gz()) return rc;
     if (s->file_open && s->tail_len > 0)
         return fail(EXON_GPU_ERR_STATE, "next_batch: the current file ends mid-line; finish it with is_last first");
-    std::lock_guard<std::mutex> work(s->ctx->work_mu);
+    std::lock_guard<std::recursive_mutex> work(s->ctx->work_mu);
     if (int rc = build_columns(s)) {
         columns_free(s);
         return rc;

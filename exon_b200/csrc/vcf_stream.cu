@@ -170,6 +170,7 @@ int VcfStream::frame_device_range(const uint8_t *text, size_t len, bool is_last,
         hdr = kBody;
     } else if (hdr != kBody) {
         // locate the end of the header by bouncing prefixes through pinned memory (records are not touched)
+        std::lock_guard<std::recursive_mutex> work(ctx->work_mu);  // h_scratch is a context-wide area
         const size_t kProbe = (size_t)1 << 20;
         if (int rc = ctx->ensure_scratch(0, kProbe)) return rc;
         while (off < len && hdr != kBody) {

@@ -104,9 +104,9 @@ int exo_region_parse(const char *s, exo_region *out) {
     int split = -1;
     for (int i = n - 1; i >= 0; i--)
         if (s[i] == ':') { split = i; break; }
-    if (split > 0) {
+    if (split >= 0) { /* noodles-core 0.15: rsplit_once(':'); Interval::from_str("") is the unbounded interval */
         int64_t lo, hi;
-        if (n - split - 1 > 0 && exo_interval_parse(s + split + 1, n - split - 1, &lo, &hi)) {
+        if (exo_interval_parse(s + split + 1, n - split - 1, &lo, &hi)) {
             memcpy(out->name, s, (size_t)split);
             out->name_len = split;
             out->has_interval = 1;

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_abi.ArrowArray) == 80 and C.sizeof(_abi.ArrowSchema) == 72
 
 
-@pytest.mark.parametrize("s", ["1", "1:9999921", "chr1:1-3388930", "1:1-1", "HLA-A*01:01", "chrUn:5-", "x:-7", "a:b", "1:0-5"])
+@pytest.mark.parametrize("s", ["1", "1:9999921", "chr1:1-3388930", "1:1-1", "HLA-A*01:01", "chrUn:5-", "x:-7", "a:b", "1:0-5", "chr1:", "a:b:", ":100-200", "a::5"])
 def test_region_parse_matches_oracle(s):
     lib = _abi.load()
     buf = C.create_string_buffer(256)
@@ -44,6 +44,18 @@ def test_region_parse_matches_oracle(s):
     o = oracle.parse_region(s)
     assert (buf.value, r.has_interval, r.lo, r.hi) == (o.name[: o.name_len], o.has_interval, o.lo, o.hi)
     assert r.has_chrom == 1 and r.chrom_len == o.name_len
+
+
+def test_region_parse_empty_suffix_and_name():
+    # noodles-core 0.15 Region::from_str: rsplit_once(':') + Interval::from_str("") == unbounded
+    lib = _abi.load()
+    buf = C.create_string_buffer(256)
+    r = _abi.Region()
+    assert lib.exon_gpu_region_parse(b"chr1:", buf, 256, C.byref(r)) == 0
+    assert (buf.value, r.has_interval, r.lo, r.hi) == (b"chr1", 1, 1, _abi.INT64_MAX)
+    assert lib.exon_gpu_region_parse(b":100-200", buf, 256, C.byref(r)) == 0
+    assert (buf.value, r.chrom_len, r.has_interval, r.lo, r.hi) == (b"", 0, 1, 100, 200)
+    assert lib.exon_gpu_region_parse(b"a:b:", buf, 256, C.byref(r)) == 0 and buf.value == b"a:b" and r.has_interval == 1
 
 
 def test_interval_parse_and_errors():

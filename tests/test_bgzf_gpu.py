@@ -68,6 +68,43 @@ def test_corrupt_members_fail(gpu_ctx):
         gpu_ctx.gzip_inflate(bytes(comp[: len(comp) // 2]))  # truncated member
 
 
+def test_streams_that_run_off_their_payload_fail_cleanly(gpu_ctx):
+    """A member whose DEFLATE stream has lost its tail (no end-of-block inside the payload) and a plain gzip file cut short
+    with a garbage trailer: the reader must never read past the payload (round-1 advice: it used to run up to 6 x ISIZE
+    bytes ahead), the call fails with a parse error and the context stays usable."""
+    import struct
+
+    rng = np.random.default_rng(7)
+    text = bytes(rng.integers(32, 127, 60_000, dtype=np.uint8))  # literal-heavy: a long stream per member
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    payload = co.compress(text) + co.flush()
+    for keep in (len(payload) // 2, len(payload) - 3, 5):
+        cut = payload[:keep]
+        hdr = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(cut) + 25)
+        member = hdr + cut + struct.pack("<II", zlib.crc32(text) & 0xFFFFFFFF, len(text))  # trailer still claims the full ISIZE
+        with pytest.raises(ExonGpuError) as e:
+            gpu_ctx.gzip_inflate(member + EOF_MARKER)
+        assert e.value.code == _abi.ERR_PARSE
+    # plain gzip, truncated in the middle of the stream: the "trailer" is whatever bytes happen to be there
+    gz = gzip.compress(text, 6)
+    for keep in (len(gz) // 2, len(gz) - 9):
+        with pytest.raises(ExonGpuError) as e:
+            gpu_ctx.gzip_inflate(gz[:keep])
+        assert e.value.code in (_abi.ERR_PARSE, _abi.ERR_ARG, _abi.ERR_OOM)
+    # a stored block after which the stream is cut: the consumed-bit count must keep running across the stored block
+    co = zlib.compressobj(0, zlib.DEFLATED, -15)
+    stored = co.compress(text[:1000]) + co.flush(zlib.Z_FULL_FLUSH)
+    co2 = zlib.compressobj(6, zlib.DEFLATED, -15)
+    tail = co2.compress(text[1000:]) + co2.flush()
+    cut = stored + tail[: len(tail) // 3]
+    hdr = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(cut) + 25)
+    with pytest.raises(ExonGpuError):
+        gpu_ctx.gzip_inflate(hdr + cut + struct.pack("<II", 0, len(text)) + EOF_MARKER)
+    # and the context still works
+    good = bgzf_compress(text)
+    assert gpu_ctx.gzip_inflate(good).tobytes() == text
+
+
 def test_vcf_gz_goldens_through_the_stream(gpu_ctx, index_vcf):
     data = raw("index.vcf.gz")  # the reference's BGZF fixture
     with gpu_ctx.open_vcf() as s:
