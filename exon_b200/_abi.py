@@ -29,9 +29,9 @@ SYMBOLS = [
     "exon_gpu_vcf_filter_count_global", "exon_gpu_filter_agg_accumulate", "exon_gpu_partial_read", "exon_gpu_memset",
     "exon_gpu_region_udf", "exon_gpu_filter_agg_batches", "exon_gpu_vcf_filter_agg",
     "exon_gpu_fastq_open", "exon_gpu_fastq_feed", "exon_gpu_fastq_filter_count", "exon_gpu_fastq_rows", "exon_gpu_fastq_next_batch",
-    "exon_gpu_stream_close", "exon_gpu_stream_reset", "exon_gpu_stream_body_bytes", "exon_gpu_stream_feed_gzip", "exon_gpu_gzip_inflate", "exon_gpu_bam_open", "exon_gpu_bam_feed",
+    "exon_gpu_stream_close", "exon_gpu_stream_schema", "exon_gpu_stream_export", "exon_gpu_stream_reset", "exon_gpu_stream_body_bytes", "exon_gpu_stream_feed_gzip", "exon_gpu_gzip_inflate", "exon_gpu_bam_open", "exon_gpu_bam_feed",
     "exon_gpu_bam_filter_count_by_reference", "exon_gpu_bam_open_columns", "exon_gpu_bam_next_batch", "exon_gpu_bam_group_name", "exon_gpu_allreduce_counts",
-    "exon_gpu_mzml_open", "exon_gpu_mzml_feed", "exon_gpu_mzml_filter_sum", "exon_gpu_tabix_query", "exon_gpu_stream_feed_bgzf_chunk",
+    "exon_gpu_mzml_open", "exon_gpu_mzml_feed", "exon_gpu_mzml_filter_sum", "exon_gpu_mzml_open_columns", "exon_gpu_mzml_next_batch", "exon_gpu_tabix_query", "exon_gpu_stream_feed_bgzf_chunk",
     "exon_gpu_fasta_open", "exon_gpu_fasta_feed", "exon_gpu_fasta_rows", "exon_gpu_fasta_open_columns", "exon_gpu_fasta_next_batch", "exon_gpu_gff_open", "exon_gpu_gff_feed",
     "exon_gpu_gff_filter_count", "exon_gpu_gff_open_columns", "exon_gpu_gff_next_batch",
 ]
@@ -180,6 +180,8 @@ def load():
         "exon_gpu_bam_group_name": [vp, i32, C.POINTER(C.c_char_p)],
         "exon_gpu_allreduce_counts": [vp, C.POINTER(i64), i32],
         "exon_gpu_mzml_open": [vp, C.POINTER(vp)],
+        "exon_gpu_mzml_open_columns": [vp, C.POINTER(FastqOpts), C.POINTER(vp)],
+        "exon_gpu_mzml_next_batch": [vp, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)],
         "exon_gpu_mzml_feed": [vp, vp, C.c_size_t, C.c_int, C.c_int],
         "exon_gpu_mzml_filter_sum": [vp, C.POINTER(MzmlPred), C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)],
         "exon_gpu_tabix_query": [vp, vp, C.c_size_t, C.POINTER(Region), C.POINTER(Chunk), i32, C.POINTER(i32)],
@@ -191,6 +193,8 @@ def load():
         "exon_gpu_gff_feed": [vp, vp, C.c_size_t, C.c_int, C.c_int],
         "exon_gpu_gff_filter_count": [vp, C.POINTER(Region), C.POINTER(i64)],
         "exon_gpu_stream_close": [vp],
+        "exon_gpu_stream_schema": [vp, C.POINTER(ArrowSchema)],
+        "exon_gpu_stream_export": [vp, vp, C.c_int],
         "exon_gpu_stream_reset": [vp],
         "exon_gpu_stream_body_bytes": [vp, C.POINTER(i64)],
         "exon_gpu_partial_read": [vp, vp, C.c_int, C.POINTER(Partial)],

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libexon_gpu.so")
-SOURCES = ["abi.cu", "vcf_stream.cu", "vcf_scan.cu", "vcf_columns.cu", "vcf_wide.cu", "filter_agg.cu", "fastq_scan.cu", "bgzf.cu", "inflate.cu", "bam.cu", "mzml.cu", "fasta_scan.cu", "fasta_columns.cu", "gff_scan.cu", "gff_columns.cu", "nccl.cu", "host_logic.cpp", "tabix.cpp"]
+SOURCES = ["abi.cu", "vcf_stream.cu", "vcf_scan.cu", "vcf_columns.cu", "vcf_wide.cu", "filter_agg.cu", "fastq_scan.cu", "bgzf.cu", "inflate.cu", "bam.cu", "mzml.cu", "mzml_columns.cu", "fasta_scan.cu", "fasta_columns.cu", "gff_scan.cu", "gff_columns.cu", "nccl.cu", "host_logic.cpp", "tabix.cpp", "arrow_stream.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr", "-cudart", "static"]
 

@@ -255,12 +255,6 @@ int exon_gpu_vcf_open(exon_gpu_ctx *c, const exon_gpu_vcf_opts *o, exon_gpu_stre
                 return fail(EXON_GPU_ERR_ARG, "vcf_open: projection index %d is not a VCF file-schema column",
                             o->projection[i]);
             }
-            if (o->projection[i] > 7) {
-                delete s;
-                return fail(EXON_GPU_ERR_UNSUPPORTED,
-                            "vcf_open: column 8 (formats) is re-serialised by the reference builder and is not built on the GPU yet "
-                            "(supported: 0 chrom, 1 pos, 2 id, 3 ref, 4 alt, 5 qual, 6 filter, 7 info)");
-            }
             for (int j = 0; j < i; ++j)
                 if (o->projection[j] == o->projection[i]) {
                     delete s;
@@ -326,16 +320,20 @@ int exon_gpu_vcf_reset(exon_gpu_stream *s) {
 // exon/exon-vcf/src/array_builder/lazy_array_builder.rs:70-75).  Only ID and Type are needed.
 int exon_gpu_vcf_set_header(exon_gpu_stream *s, const char *text, size_t len) {
     if (!s || (!text && len)) return fail(EXON_GPU_ERR_ARG, "vcf_set_header: NULL argument");
-    InfoDefs defs;
+    InfoDefs defs[2];  // ##INFO, ##FORMAT
     const char *p = text, *end = text + len;
     while (p < end) {
         const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
         const char *le = nl ? nl : end;
-        if (le - p > 8 && memcmp(p, "##INFO=<", 8) == 0) {
+        int which = -1;
+        size_t skip = 0;
+        if (le - p > 8 && memcmp(p, "##INFO=<", 8) == 0) which = 0, skip = 8;
+        else if (le - p > 10 && memcmp(p, "##FORMAT=<", 10) == 0) which = 1, skip = 10;
+        if (which >= 0) {
             auto field = [&](const char *key, std::string *out) {
                 const size_t kl = strlen(key);
-                for (const char *q = p + 8; q + kl <= le; ++q) {
-                    if ((q == p + 8 || q[-1] == ',') && memcmp(q, key, kl) == 0) {
+                for (const char *q = p + skip; q + kl <= le; ++q) {
+                    if ((q == p + skip || q[-1] == ',') && memcmp(q, key, kl) == 0) {
                         const char *v = q + kl, *ve = v;
                         while (ve < le && *ve != ',' && *ve != '>') ++ve;
                         out->assign(v, (size_t)(ve - v));
@@ -348,19 +346,22 @@ int exon_gpu_vcf_set_header(exon_gpu_stream *s, const char *text, size_t len) {
                 }
                 return false;
             };
-            std::string id, type;
+            std::string id, type, number;
             if (!field("ID=", &id) || !field("Type=", &type) || id.empty())
-                return fail(EXON_GPU_ERR_PARSE, "vcf_set_header: an ##INFO line without ID / Type");
+                return fail(EXON_GPU_ERR_PARSE, "vcf_set_header: an ##INFO / ##FORMAT line without ID / Type");
+            field("Number=", &number);
             int t = type == "Integer" ? 0 : type == "Float" ? 1 : type == "Flag" ? 2 : type == "Character" ? 3 : type == "String" ? 4 : -1;
-            if (t < 0) return fail(EXON_GPU_ERR_PARSE, "vcf_set_header: unknown INFO type '%s'", type.c_str());
-            defs.ids.push_back(id);
-            defs.types.push_back((uint8_t)t);
+            if (t < 0 || (which == 1 && t == 2)) return fail(EXON_GPU_ERR_PARSE, "vcf_set_header: unknown %s type '%s'", which ? "FORMAT" : "INFO", type.c_str());
+            defs[which].ids.push_back(id);
+            defs[which].types.push_back((uint8_t)t);
+            defs[which].single.push_back(number == "1" ? 1 : 0);
         }
         if (!nl) break;
         p = nl + 1;
     }
-    defs.set = true;
-    s->info_defs = std::move(defs);
+    defs[0].set = defs[1].set = true;
+    s->info_defs = std::move(defs[0]);
+    s->format_defs = std::move(defs[1]);
     return EXON_GPU_OK;
 }
 

@@ -1028,6 +1028,8 @@ void bam_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
 
 }  // namespace
 
+void bam_stream_schema(VcfStream *s, ArrowSchema *out) { bam_fill_schema(s->projection, out); }
+
 int bam_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     if (!s->bam_cols) {
         int64_t rows = 0;

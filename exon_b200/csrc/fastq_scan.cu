@@ -1004,6 +1004,8 @@ int build_line_index(VcfStream *s, size_t extra_per_line, size_t extra_fixed, Li
     return EXON_GPU_OK;
 }
 
+void fastq_stream_schema(VcfStream *s, ArrowSchema *out) { fq_fill_schema(s->projection, out, s->fmt == kFmtFasta); }
+
 int fastq_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     if (!s->fq_cols) {
         if (int rc = s->flush_gz()) return rc;

@@ -540,6 +540,8 @@ void gff_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
 
 }  // namespace
 
+void gff_stream_schema(VcfStream *s, ArrowSchema *out) { gff_fill_schema(s->projection, out); }
+
 int gff_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     if (!s->gff_cols) {
         if (int rc = s->flush_gz()) return rc;

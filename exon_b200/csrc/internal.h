@@ -112,7 +112,8 @@ struct Piece {
 // INFO definitions of a VCF header (##INFO=<ID=..,Number=..,Type=..>): what the reference's builder takes from noodles' Header
 struct InfoDefs {
     std::vector<std::string> ids;
-    std::vector<uint8_t> types;  // 0 Integer, 1 Float, 2 Flag, 3 Character, 4 String
+    std::vector<uint8_t> types;   // 0 Integer, 1 Float, 2 Flag, 3 Character, 4 String
+    std::vector<uint8_t> single;  // Number=1: the value is one element, not a ','-separated array
     bool set = false;
 };
 
@@ -126,7 +127,7 @@ struct VcfStream {
     bool columns_on_device = false, strict = false, has_pushdown = false, drained = false;
     int variant = 0;
     OwnedRegion pushdown;
-    InfoDefs info_defs;  // exon_gpu_vcf_set_header
+    InfoDefs info_defs, format_defs;  // exon_gpu_vcf_set_header: ##INFO / ##FORMAT lines
 
     // ---- file framing state (what read_header + the line reader keep between feeds) ----
     enum HdrState { kAtLineStart, kInHeaderLine, kBody };
@@ -355,6 +356,13 @@ bool wide_wanted(const std::vector<int> &projection);
 int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows_io, WideStore **out);
 void wide_free(WideStore *w);
 void wide_export(const WideStore *w, int col, int64_t b, int64_t rows, ArrowArray *a, WideChildSlot *slot);
+
+// schema of the batches a stream produces (arrow_stream.cpp: exon_gpu_stream_schema / the Arrow C stream's get_schema)
+void vcf_stream_schema(VcfStream *s, struct ArrowSchema *out);
+void fastq_stream_schema(VcfStream *s, struct ArrowSchema *out);
+void bam_stream_schema(VcfStream *s, struct ArrowSchema *out);
+void gff_stream_schema(VcfStream *s, struct ArrowSchema *out);
+int mzml_stream_schema(VcfStream *s, struct ArrowSchema *out);
 
 // defined in vcf_columns.cu
 int columns_filter_agg(VcfStream *s, const exon_gpu_pred *pred, const exon_gpu_agg *agg, exon_gpu_partial *out);

@@ -680,3 +680,6 @@ int exon_gpu_mzml_filter_sum(exon_gpu_stream *s, const exon_gpu_mzml_pred *pred,
 }
 
 }  // extern "C"
+
+// ---- record batches (exon_gpu_mzml_next_batch) are built in mzml_columns.cu ----
+

@@ -523,9 +523,9 @@ void release_schema(ArrowSchema *s) {
 // VCFSchemaBuilder (exon/exon-core/src/datasources/vcf/schema_builder.rs:85-129): chrom Utf8 !null, pos Int64 !null,
 // id List<item: Utf8>, ref Utf8 !null, alt List<item: Utf8>, qual Float32, filter List<item: Utf8>
 void fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
-    static const char *names[8] = {"chrom", "pos", "id", "ref", "alt", "qual", "filter", "info"};
-    static const char *formats[8] = {"u", "l", "+l", "u", "+l", "f", "+l", "u"};
-    static const bool nullable[8] = {false, false, true, false, true, true, true, true};
+    static const char *names[9] = {"chrom", "pos", "id", "ref", "alt", "qual", "filter", "info", "formats"};
+    static const char *formats[9] = {"u", "l", "+l", "u", "+l", "f", "+l", "u", "u"};
+    static const bool nullable[9] = {false, false, true, false, true, true, true, true, true};
     auto *p = new SchemaPriv();
     p->n_children = (int)projection.size();
     for (int i = 0; i < p->n_children; ++i) {
@@ -819,6 +819,8 @@ int columns_filter_agg(VcfStream *s, const exon_gpu_pred *pred, const exon_gpu_a
     if (k.val_type == kValI64) out->sum_f64 = (double)out->sum_i64;
     return EXON_GPU_OK;
 }
+
+void vcf_stream_schema(VcfStream *s, ArrowSchema *out) { fill_schema(s->projection, out); }
 
 int columns_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
     if (int rc = ensure_columns(s)) return rc;

@@ -7,7 +7,8 @@
 //   alt     "." -> NULL, else a VALID BUT EMPTY list: the builder never appends the alleles            (:190-204)
 //   qual    "." -> NULL, else Rust `f32::from_str`, correctly rounded (f32_parse.cuh)                  (:205-208)
 //   filter  always valid: "." -> [], else one item per ';'-separated filter                            (:209-216)
-//   info    (string mode) the field re-serialised: equal to its text plus "=true" after every flag, see info_walk      (:217-298)
+//   info    (string mode) the field re-serialised from noodles' typed view: numbers through Rust's Display, see info_walk  (:217-298)
+//   formats (string mode) FORMAT keys + every sample's values re-serialised the same way, see formats_walk               (:310-432)
 // Columns 0 / 1 stay with K2 (vcf_columns.cu), whose batch table (batches restart at every file) this build shares.
 //
 // Row-parallel, on top of the partition's line index (build_line_index, fastq_scan.cu):
@@ -24,6 +25,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "f32_display.cuh"
 #include "f32_parse.cuh"
 #include "internal.h"
 #include "scan_i64.cuh"
@@ -46,10 +48,19 @@ constexpr uint32_t kWErrQualDigits = 4u;   // QUAL has more than 36 significant 
 constexpr uint32_t kWErrFieldLen = 8u;     // a line of 2 GiB or more
 constexpr uint32_t kWErrInfoValue = 16u;   // INFO: a non-flag key without a value (the reference unwraps a None there)
 constexpr uint32_t kWErrInfoKey = 32u;     // INFO: a key the header does not define
-constexpr uint32_t kWErrInfoForm = 64u;    // INFO: a value whose re-serialisation by the reference would differ from its text
+constexpr uint32_t kWErrInfoForm = 64u;    // INFO: a value noodles cannot parse as its declared type, or a flag with a value
+constexpr uint32_t kWErrFmtValue = 128u;   // FORMAT: a missing sample value ('.'): the reference unwraps a None there
+constexpr uint32_t kWErrFmtForm = 256u;    // FORMAT: a sample value noodles cannot parse as its declared type
 
-enum { kIdE = 0, kIdB = 1, kRefB = 2, kFiE = 3, kFiB = 4, kInfoB = 5, kNScan = 6 };
+enum { kIdE = 0, kIdB = 1, kRefB = 2, kFiE = 3, kFiB = 4, kInfoB = 5, kFmtB = 6, kNScan = 7 };
 
+struct KeyDefs;  // defined with the INFO / FORMAT walks below
+struct KeyDefsPod {  // KeyDefs by value inside the kernel argument
+    const uint32_t *hash;
+    const int32_t *off, *len;
+    const uint8_t *type, *single, *blob;
+    int32_t n;
+};
 struct WideArgs {
     int64_t n_rows;
     const uint8_t *const *line_start;
@@ -57,14 +68,11 @@ struct WideArgs {
     const long long *brow;  // n_batches + 1
     int64_t n_batches;
     int32_t batch_rows, wpb;
-    int32_t want_id, want_ref, want_alt, want_qual, want_filter, want_info;
-    // INFO definitions of the header (exon_gpu_vcf_set_header): FNV-1a hash, offset / length into the blob, type
-    const uint32_t *info_hash;
-    const int32_t *info_off, *info_len;
-    const uint8_t *info_type, *info_blob;
-    int32_t n_info;
-    int32_t *info_offs;  // batch-relative offsets, n_batches * (batch_rows + 1)
-    uint8_t *info_val;
+    int32_t want_id, want_ref, want_alt, want_qual, want_filter, want_info, want_formats;
+    // INFO / FORMAT definitions of the header (exon_gpu_vcf_set_header): FNV-1a hash, offset / length into the blob, type, Number == 1
+    KeyDefsPod info_defs, fmt_defs;
+    int32_t *info_offs, *fmt_offs;  // batch-relative offsets, n_batches * (batch_rows + 1)
+    uint8_t *info_val, *fmt_val;
     int32_t *cnt[kNScan];          // measure out, n_rows + 1 entries (the last one 0); NULL when not wanted
     const long long *pre[kNScan];  // emit in: exclusive scans of cnt
     uint8_t *rowflags;             // measure out: bit0 id valid, bit1 alt valid, bit2 qual valid
@@ -115,14 +123,17 @@ __device__ __forceinline__ void count_items(const uint8_t *f, int32_t n, int32_t
 }
 
 
-// ---- INFO (column 7, string mode) ---------------------------------------------------------------------------------------
-// LazyVCFArrayBuilder::append :217-298 does not copy the field: it walks noodles' typed view of it (types from the header's
-// ##INFO lines) and prints every entry again -- `key=value` joined by ';', flags as `key=true`, numbers through Rust's
-// Display.  The text that comes out equals the text that went in, plus "=true" after every flag, PROVIDED every number is
-// already in the form Display would give it.  That is checked here entry by entry; a value for which it does not hold (an
-// exponent, trailing zeros, more than 6 significant digits in a fraction, '%' escapes in a string ...), a key the header
-// does not define and a flag with a value are refused (EXON_GPU_ERR_UNSUPPORTED) instead of being approximated.
-enum : uint8_t { kInfoInteger = 0, kInfoFloat = 1, kInfoFlag = 2, kInfoCharacter = 3, kInfoString = 4 };
+// ---- INFO (column 7) and FORMAT / samples (column 8), string mode ----------------------------------------------------------
+// LazyVCFArrayBuilder::append :217-298 / :310-432 does not copy these fields: it walks noodles' typed view of them (types
+// from the header's ##INFO / ##FORMAT lines) and prints every value again -- integers through i32 Display, floats through
+// f32 Display (f32_display.cuh), strings percent-decoded, an INFO flag as `key=true`, a genotype allele by allele.  Most
+// values are already in the form Display gives them (checked with canon_int / canon_float) and are copied; the others are
+// parsed (Rust grammar: `+7`, `007`, `1e3`, `0.50`, `inf` ...) and printed.  What the reference cannot print is an error
+// here too: a value noodles cannot parse, and a MISSING value (`key=.`, a non-flag key without `=`, a sample value `.`), on
+// which the builder's `value_option.unwrap()` panics.
+// Key definitions: the header's; for a key the header does not define, the VCF specification's reserved key of that name
+// (a stable subset of noodles' fallback table, below); otherwise a single String.
+enum : uint8_t { kInfoInteger = 0, kInfoFloat = 1, kInfoFlag = 2, kInfoCharacter = 3, kInfoString = 4, kFmtGenotype = 5 };
 
 __device__ __forceinline__ uint32_t fnv1a(const uint8_t *p, int n) {
     uint32_t h = 2166136261u;
@@ -130,9 +141,8 @@ __device__ __forceinline__ uint32_t fnv1a(const uint8_t *p, int n) {
     return h;
 }
 
-// -?(0|[1-9][0-9]*) within i32; "." is a missing element
+// -?(0|[1-9][0-9]*) within i32: the text i32 Display prints
 __device__ __forceinline__ bool canon_int(const uint8_t *p, int n) {
-    if (n == 1 && __ldg(p) == '.') return true;
     int i = 0;
     const bool neg = n > 0 && __ldg(p) == '-';
     if (neg) i = 1;
@@ -152,14 +162,12 @@ __device__ __forceinline__ bool canon_int(const uint8_t *p, int n) {
 // decimal without trailing zeros whose significant digits number at most 6 (FLT_DIG: such decimals survive the round trip,
 // so the shortest representation of their f32 is the decimal itself); no sign on zero, no exponent, no leading '+'
 __device__ __forceinline__ bool canon_float(const uint8_t *p, int n) {
-    if (n == 1 && __ldg(p) == '.') return true;
     int i = 0;
     const bool neg = n > 0 && __ldg(p) == '-';
     if (neg) i = 1;
     if (i >= n) return false;
     int int_digits = 0, sig = 0;
     bool nonzero = false, lead_zero = false;
-    const int i0 = i;
     for (; i < n; ++i) {
         const uint32_t d = (uint32_t)__ldg(p + i) - '0';
         if (d > 9u) break;
@@ -171,7 +179,6 @@ __device__ __forceinline__ bool canon_float(const uint8_t *p, int n) {
         }
     }
     if (int_digits == 0 || (lead_zero && int_digits > 1)) return false;
-    (void)i0;
     if (i == n) return nonzero ? sig <= 7 : !neg;  // integer: "0" but not "-0"
     if (__ldg(p + i) != '.' || i + 1 >= n) return false;
     ++i;
@@ -187,11 +194,180 @@ __device__ __forceinline__ bool canon_float(const uint8_t *p, int n) {
     return last != 0u && sig <= 6;
 }
 
+// Rust `i32::from_str`: [+-]?[0-9]+ within range
+__device__ __forceinline__ bool parse_i32_rust(const uint8_t *p, int n, int32_t *out) {
+    int i = 0;
+    bool neg = false;
+    if (n > 0 && (__ldg(p) == '-' || __ldg(p) == '+')) {
+        neg = __ldg(p) == '-';
+        i = 1;
+    }
+    if (i >= n) return false;
+    unsigned long long v = 0;
+    for (; i < n; ++i) {
+        const uint32_t d = (uint32_t)__ldg(p + i) - '0';
+        if (d > 9u) return false;
+        v = v * 10ull + d;
+        if (v > 2147483648ull) return false;
+    }
+    if (!neg && v > 2147483647ull) return false;
+    *out = neg ? (int32_t)(0u - (uint32_t)v) : (int32_t)v;
+    return true;
+}
+
+struct Emit {  // byte sink: counts always, writes when dst is set
+    uint8_t *dst;
+    int32_t n;
+    __device__ __forceinline__ void put(uint8_t c) {
+        if (dst) dst[n] = c;
+        ++n;
+    }
+    __device__ __forceinline__ void copy(const uint8_t *p, int32_t m) {
+        if (dst)
+            for (int32_t q = 0; q < m; ++q) dst[n + q] = __ldg(p + q);
+        n += m;
+    }
+};
+
+__device__ __forceinline__ int hexval(uint32_t c) {
+    if (c - '0' <= 9u) return (int)(c - '0');
+    c |= 0x20u;
+    return c - 'a' <= 5u ? (int)(c - 'a' + 10) : -1;
+}
+
+// the slow half of a number: parse with Rust's grammar, print with Rust's Display (kept out of line: the exact float parser
+// and the shortest-digits printer are large, and almost no value comes here)
+__device__ __noinline__ int32_t number_reprint(int type, const uint8_t *p, int32_t m, uint8_t *out /* >= kF32DisplayMax */) {
+    if (m > 512) return -1;
+    if (type == kInfoInteger) {
+        int32_t v;
+        if (!parse_i32_rust(p, m, &v)) return -1;
+        return i32_display(v, out);
+    }
+    uint8_t tmp[64];
+    if (m > 64) return -1;  // longer literals exist (a long string of zeros) but not in practice
+    for (int32_t q = 0; q < m; ++q) tmp[q] = __ldg(p + q);
+    float f;
+    if (parse_f32_rust(tmp, m, &f) != kF32Ok) return -1;
+    return f32_display(f, out);
+}
+
+// one element [p, p + m) of a value of type `type`; false: the reference cannot print it
+__device__ __forceinline__ bool elem_emit(int type, const uint8_t *p, int32_t m, Emit &o) {
+    if (m == 0) return false;
+    if (type == kInfoInteger || type == kInfoFloat) {
+        if (type == kInfoInteger ? canon_int(p, m) : canon_float(p, m)) {
+            o.copy(p, m);
+            return true;
+        }
+        uint8_t buf[kF32DisplayMax + 8];
+        const int32_t k = number_reprint(type, p, m, buf);
+        if (k < 0) return false;
+        if (o.dst)
+            for (int32_t q = 0; q < k; ++q) o.dst[o.n + q] = buf[q];
+        o.n += k;
+        return true;
+    }
+    // Character / String: percent-decoded (noodles: percent_encoding::percent_decode_str)
+    int32_t out0 = o.n;
+    for (int32_t q = 0; q < m; ++q) {
+        uint32_t c = __ldg(p + q);
+        if (c == '%' && q + 2 < m) {
+            const int h = hexval(__ldg(p + q + 1)), l = hexval(__ldg(p + q + 2));
+            if (h >= 0 && l >= 0) {
+                c = (uint32_t)(h * 16 + l);
+                q += 2;
+            }
+        }
+        o.put((uint8_t)c);
+    }
+    return type != kInfoCharacter || o.n - out0 == 1;
+}
+
+// a whole value: one element (Number=1) or a ','-separated array whose missing elements print as '.'
+// (Character arrays skip them in FORMAT, :371-381)
+__device__ __forceinline__ bool value_emit(int type, bool single, bool skip_missing_chars, const uint8_t *p, int32_t m, Emit &o) {
+    if (m == 0 || (m == 1 && __ldg(p) == '.')) return false;  // a missing value: the builder unwraps a None
+    if (single || type == kInfoString) return elem_emit(type, p, m, o);  // (a String array joins back to its own text)
+    int32_t v = 0;
+    bool first = true;
+    while (true) {
+        int32_t ve = v;
+        while (ve < m && __ldg(p + ve) != ',') ++ve;
+        const bool missing = ve - v == 1 && __ldg(p + v) == '.';
+        if (!(missing && skip_missing_chars)) {
+            if (!first) o.put(',');
+            first = false;
+            if (missing) o.put('.');
+            else if (!elem_emit(type, p + v, ve - v, o)) return false;
+        }
+        if (ve >= m) break;
+        v = ve + 1;
+    }
+    return true;
+}
+
+// header definitions of one kind of key (INFO or FORMAT) + the specification's reserved keys as the fallback
+struct KeyDefs : KeyDefsPod {};
+struct Reserved {
+    const char *key;
+    uint8_t type, single;
+};
+// VCF 4.3 / 4.4 tables 1 and 2, the entries that do not differ between the versions noodles knows
+__constant__ Reserved c_reserved_info[] = {
+    {"AA", kInfoString, 1}, {"AC", kInfoInteger, 0}, {"AD", kInfoInteger, 0}, {"ADF", kInfoInteger, 0}, {"ADR", kInfoInteger, 0},
+    {"AF", kInfoFloat, 0}, {"AN", kInfoInteger, 1}, {"BQ", kInfoFloat, 1}, {"CIGAR", kInfoString, 0}, {"DB", kInfoFlag, 0},
+    {"DP", kInfoInteger, 1}, {"END", kInfoInteger, 1}, {"H2", kInfoFlag, 0}, {"H3", kInfoFlag, 0}, {"MQ", kInfoFloat, 1},
+    {"MQ0", kInfoInteger, 1}, {"NS", kInfoInteger, 1}, {"SB", kInfoInteger, 0}, {"SOMATIC", kInfoFlag, 0}, {"VALIDATED", kInfoFlag, 0},
+    {"1000G", kInfoFlag, 0}, {"IMPRECISE", kInfoFlag, 0}, {"NOVEL", kInfoFlag, 0}, {"SVTYPE", kInfoString, 1},
+};
+__constant__ Reserved c_reserved_format[] = {
+    {"AD", kInfoInteger, 0}, {"ADF", kInfoInteger, 0}, {"ADR", kInfoInteger, 0}, {"DP", kInfoInteger, 1}, {"EC", kInfoInteger, 0},
+    {"FT", kInfoString, 1}, {"GL", kInfoFloat, 0}, {"GP", kInfoFloat, 0}, {"GQ", kInfoInteger, 1}, {"GT", kFmtGenotype, 1},
+    {"HQ", kInfoInteger, 0}, {"MQ", kInfoInteger, 1}, {"PL", kInfoInteger, 0}, {"PP", kInfoInteger, 0}, {"PQ", kInfoInteger, 1},
+    {"PS", kInfoInteger, 1},
+};
+
+template <bool FORMAT>
+__device__ __forceinline__ void lookup_key(const KeyDefs &d, const uint8_t *k, int32_t klen, int *type, bool *single) {
+    if (FORMAT && klen == 2 && __ldg(k) == 'G' && __ldg(k + 1) == 'T') {  // GT is a genotype whatever the header calls it
+        *type = kFmtGenotype;
+        *single = true;
+        return;
+    }
+    const uint32_t h = fnv1a(k, klen);
+    for (int i = 0; i < d.n; ++i) {
+        if (d.hash[i] != h || d.len[i] != klen) continue;
+        bool same = true;
+        for (int q = 0; q < klen && same; ++q) same = d.blob[d.off[i] + q] == __ldg(k + q);
+        if (same) {
+            *type = d.type[i];
+            *single = d.single[i] != 0;
+            return;
+        }
+    }
+    const Reserved *tab = FORMAT ? c_reserved_format : c_reserved_info;
+    const int nt = FORMAT ? (int)(sizeof(c_reserved_format) / sizeof(Reserved)) : (int)(sizeof(c_reserved_info) / sizeof(Reserved));
+    for (int i = 0; i < nt; ++i) {
+        const char *r = tab[i].key;
+        int q = 0;
+        while (q < klen && r[q] && (uint8_t)r[q] == __ldg(k + q)) ++q;
+        if (q == klen && !r[q]) {
+            *type = tab[i].type;
+            *single = tab[i].single != 0;
+            return;
+        }
+    }
+    *type = kInfoString;
+    *single = true;
+}
+
 // Walks one INFO field.  Returns the length of the re-serialised string; *err collects kWErrInfo*.  When `dst` is set the
 // string is written there.
-__device__ __forceinline__ int32_t info_walk(const WideArgs &a, const uint8_t *f, int32_t n, uint8_t *dst, uint32_t *err) {
+__device__ __forceinline__ int32_t info_walk(const KeyDefs &defs, const uint8_t *f, int32_t n, uint8_t *dst, uint32_t *err) {
     if (n == 0 || (n == 1 && __ldg(f) == '.')) return 0;
-    int32_t out = 0, i = 0;
+    Emit o{dst, 0};
+    int32_t i = 0;
     while (i <= n) {
         // entry [i, e)
         int32_t e = i, eq = -1;
@@ -200,63 +376,24 @@ __device__ __forceinline__ int32_t info_walk(const WideArgs &a, const uint8_t *f
             ++e;
         }
         const int32_t klen = (eq < 0 ? e : eq) - i;
-        const uint32_t h = fnv1a(f + i, klen);
-        int type = -1;
-        for (int k = 0; k < a.n_info; ++k) {
-            if (a.info_hash[k] != h || a.info_len[k] != klen) continue;
-            bool same = true;
-            for (int q = 0; q < klen && same; ++q) same = a.info_blob[a.info_off[k] + q] == __ldg(f + i + q);
-            if (same) {
-                type = a.info_type[k];
-                break;
-            }
-        }
-        if (type < 0) *err |= kWErrInfoKey;
+        int type;
+        bool single;
+        lookup_key<false>(defs, f + i, klen, &type, &single);
+        if (i) o.put(';');
+        o.copy(f + i, klen);
+        o.put('=');
         if (type == kInfoFlag) {
-            if (eq >= 0) *err |= kWErrInfoForm;
-        } else if (type >= 0) {
-            if (eq < 0) {
-                *err |= kWErrInfoValue;
-            } else {
-                // elements of the value
-                int32_t v = eq + 1;
-                if (v == e) *err |= kWErrInfoForm;
-                while (v <= e && v < e + 1) {
-                    int32_t ve = v;
-                    while (ve < e && __ldg(f + ve) != ',') ++ve;
-                    const uint8_t *p = f + v;
-                    const int32_t m = ve - v;
-                    bool ok = true;
-                    if (type == kInfoInteger) ok = canon_int(p, m);
-                    else if (type == kInfoFloat) ok = canon_float(p, m);
-                    else if (type == kInfoCharacter) ok = m == 1;
-                    else
-                        for (int32_t q = 0; q < m && ok; ++q) ok = __ldg(p + q) != '%';
-                    if (!ok || m == 0) *err |= kWErrInfoForm;
-                    if (ve >= e) break;
-                    v = ve + 1;
-                }
-            }
+            if (eq >= 0 && eq + 1 < e) *err |= kWErrInfoForm;  // a flag with a value
+            o.put('t'), o.put('r'), o.put('u'), o.put('e');
+        } else if (eq < 0) {
+            *err |= kWErrInfoValue;
+        } else if (!value_emit(type, single, false, f + eq + 1, e - eq - 1, o)) {
+            *err |= (e - eq - 1 == 0 || (e - eq - 1 == 1 && __ldg(f + eq + 1) == '.')) ? kWErrInfoValue : kWErrInfoForm;
         }
-        // key[=value], "=true" for a flag, ';' between entries
-        if (dst) {
-            for (int32_t q = i; q < e; ++q) dst[out + (q - i)] = __ldg(f + q);
-            if (type == kInfoFlag && eq < 0) {
-                dst[out + (e - i)] = '=';
-                dst[out + (e - i) + 1] = 't';
-                dst[out + (e - i) + 2] = 'r';
-                dst[out + (e - i) + 3] = 'u';
-                dst[out + (e - i) + 4] = 'e';
-            }
-        }
-        out += e - i;
-        if (type == kInfoFlag && eq < 0) out += 5;
         if (e >= n) break;
-        if (dst) dst[out] = ';';
-        ++out;
         i = e + 1;
     }
-    return out;
+    return o.n;
 }
 
 // end of the INFO field: the 8th tab, or the end of the line when the record has no FORMAT / sample columns
@@ -264,6 +401,86 @@ __device__ __forceinline__ const uint8_t *info_end(const uint8_t *info, const ui
     const uint8_t *p = info;
     while (p < le && __ldg(p) != '\t') ++p;
     return p;
+}
+
+// A genotype [p, p + m): alleles are usize (printed again: "01" -> "1") or '.', separators '/' and '|'.  The builder prints
+// allele k (k >= 1) behind the phasing of allele k - 1 (:338-362); allele 0's phasing is noodles' inferred one -- phased iff
+// every separator is '|' -- so a diploid call prints as written and a mixed-phase polyploid call shifts its separators.
+__device__ __forceinline__ bool genotype_emit(const uint8_t *p, int32_t m, Emit &o) {
+    if (m == 0) return false;
+    bool all_phased = true;
+    for (int32_t q = 0; q < m; ++q)
+        if (__ldg(p + q) == '/') all_phased = false;
+    int32_t v = 0, k = 0;
+    uint8_t prev_sep = all_phased ? '|' : '/';
+    while (true) {
+        int32_t ve = v;
+        while (ve < m && __ldg(p + ve) != '/' && __ldg(p + ve) != '|') ++ve;
+        if (k) o.put(prev_sep);
+        if (k) prev_sep = __ldg(p + v - 1);
+        if (ve - v == 1 && __ldg(p + v) == '.') {
+            o.put('.');
+        } else {
+            if (ve == v || ve - v > 18) return false;
+            unsigned long long a = 0;
+            for (int32_t q = v; q < ve; ++q) {
+                const uint32_t d = (uint32_t)__ldg(p + q) - '0';
+                if (d > 9u) return false;
+                a = a * 10ull + d;
+            }
+            uint8_t dg[20];
+            int nd = 0;
+            do {
+                dg[nd++] = (uint8_t)('0' + a % 10ull);
+                a /= 10ull;
+            } while (a);
+            while (nd) o.put(dg[--nd]);
+        }
+        ++k;
+        if (ve >= m) break;
+        v = ve + 1;
+    }
+    return true;
+}
+
+// Column 8: `keys ':'-joined` '\t' `every sample, its values re-serialised and ':'-joined, '\t'-joined` (:310-432).  [f, f + n)
+// is the text behind the 8th tab (n == 0 or no 8th tab: a sites-only record prints "\t").  A sample with fewer values than
+// keys prints the values it has (the builder zips keys with values).
+__device__ __forceinline__ int32_t formats_walk(const KeyDefs &defs, const uint8_t *f, int32_t n, uint8_t *dst, uint32_t *err) {
+    Emit o{dst, 0};
+    int32_t ke = 0;
+    while (ke < n && __ldg(f + ke) != '\t') ++ke;  // FORMAT = [0, ke)
+    o.copy(f, ke);
+    o.put('\t');
+    int32_t v = ke + 1;
+    bool first_sample = true;
+    while (v <= n && ke < n) {
+        int32_t se = v;
+        while (se < n && __ldg(f + se) != '\t') ++se;  // sample = [v, se)
+        if (!first_sample) o.put('\t');
+        first_sample = false;
+        int32_t kv = 0, sv = v;
+        bool first_val = true;
+        while (kv < ke && sv <= se) {
+            int32_t kq = kv, sq = sv;
+            while (kq < ke && __ldg(f + kq) != ':') ++kq;
+            while (sq < se && __ldg(f + sq) != ':') ++sq;
+            int type;
+            bool single;
+            lookup_key<true>(defs, f + kv, kq - kv, &type, &single);
+            if (!first_val) o.put(':');
+            first_val = false;
+            const bool ok = type == kFmtGenotype ? (sq - sv == 1 && __ldg(f + sv) == '.' ? false : genotype_emit(f + sv, sq - sv, o))
+                                                 : value_emit(type, single, type == kInfoCharacter, f + sv, sq - sv, o);
+            if (!ok) *err |= (sq - sv == 0 || (sq - sv == 1 && __ldg(f + sv) == '.')) ? kWErrFmtValue : kWErrFmtForm;
+            if (sq >= se) break;
+            kv = kq + 1;
+            sv = sq + 1;
+        }
+        if (se >= n) break;
+        v = se + 1;
+    }
+    return o.n;
 }
 
 __global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__ WideArgs a) {
@@ -321,7 +538,7 @@ __global__ void __launch_bounds__(256) vw_measure_kernel(const __grid_constant__
     }
 #pragma unroll
     for (int k = 0; k < kNScan; ++k)
-        if (k != kInfoB && a.cnt[k]) a.cnt[k][r] = c[k];  // kInfoB belongs to vw_info_measure_kernel
+        if (k != kInfoB && k != kFmtB && a.cnt[k]) a.cnt[k][r] = c[k];  // kInfoB / kFmtB belong to vw_text_measure_kernel
     a.rowflags[r] = rf;
     if (a.want_qual) {
         a.qual[r] = q;
@@ -453,27 +670,35 @@ __global__ void __launch_bounds__(256) vw_emit_kernel(const __grid_constant__ Wi
     }
 }
 
-// INFO lives in its own two kernels (the entry walk with its key lookups must not shape the register budget of the row
-// passes): length + checks, then -- after the scan -- offsets and bytes.
-__global__ void __launch_bounds__(256) vw_info_measure_kernel(const __grid_constant__ WideArgs a) {
+// INFO and FORMAT live in their own kernels (the entry walks with their key lookups must not shape the register budget of
+// the row passes): length + checks, then -- after the scan -- offsets and bytes.  WHICH: kInfoB or kFmtB.
+template <int WHICH>
+__device__ __forceinline__ int32_t walk_row(const WideArgs &a, const uint8_t *ls, const uint8_t *le, const int32_t *to, uint8_t *dst, uint32_t *err) {
+    const uint8_t *f = ls + to[6] + 1;
+    const uint8_t *ie = info_end(f, le);
+    if (WHICH == kInfoB) return info_walk(static_cast<const KeyDefs &>(a.info_defs), f, (int32_t)(ie - f), dst, err);
+    const uint8_t *g = ie < le ? ie + 1 : le;  // behind the 8th tab
+    return formats_walk(static_cast<const KeyDefs &>(a.fmt_defs), g, (int32_t)(le - g), dst, err);
+}
+
+template <int WHICH>
+__global__ void __launch_bounds__(256) vw_text_measure_kernel(const __grid_constant__ WideArgs a) {
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= a.n_rows) return;
     const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
     int32_t to[7];
     int32_t n = 0;
     uint32_t err = 0;
-    if (le - ls <= 0x7FFFFFF0ll && find_tabs(ls, le, to)) {  // a short line is reported by the row pass
-        const uint8_t *f = ls + to[6] + 1;
-        n = info_walk(a, f, (int32_t)(info_end(f, le) - f), nullptr, &err);
-    }
-    a.cnt[kInfoB][r] = n;
+    if (le - ls <= 0x7FFFFFF0ll && find_tabs(ls, le, to)) n = walk_row<WHICH>(a, ls, le, to, nullptr, &err);  // a short line is reported by the row pass
+    a.cnt[WHICH][r] = n;
     if (err) {
         atomicOr(a.flags, err);
         atomicMin(a.first_bad_row, (unsigned long long)r);
     }
 }
 
-__global__ void __launch_bounds__(256) vw_info_emit_kernel(const __grid_constant__ WideArgs a) {
+template <int WHICH>
+__global__ void __launch_bounds__(256) vw_text_emit_kernel(const __grid_constant__ WideArgs a) {
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     __shared__ long long s_b0;
     if (threadIdx.x == 0) {
@@ -493,15 +718,16 @@ __global__ void __launch_bounds__(256) vw_info_emit_kernel(const __grid_constant
     const int64_t r0 = __ldg(&a.brow[b]);
     const int in_batch = (int)(r - r0);
     const int64_t lrow = b * (int64_t)(a.batch_rows + 1) + in_batch;
-    const long long v = a.pre[kInfoB][r], v0 = a.pre[kInfoB][r0];
-    a.info_offs[lrow] = (int32_t)(v - v0);
-    if (r + 1 == __ldg(&a.brow[b + 1])) a.info_offs[lrow + 1] = (int32_t)(a.pre[kInfoB][r + 1] - v0);
+    int32_t *offs = WHICH == kInfoB ? a.info_offs : a.fmt_offs;
+    uint8_t *val = WHICH == kInfoB ? a.info_val : a.fmt_val;
+    const long long v = a.pre[WHICH][r], v0 = a.pre[WHICH][r0];
+    offs[lrow] = (int32_t)(v - v0);
+    if (r + 1 == __ldg(&a.brow[b + 1])) offs[lrow + 1] = (int32_t)(a.pre[WHICH][r + 1] - v0);
     const uint8_t *ls = a.line_start[r], *le = a.line_end[r];
     int32_t to[7];
     if (le - ls > 0x7FFFFFF0ll || !find_tabs(ls, le, to)) return;
-    const uint8_t *f = ls + to[6] + 1;
     uint32_t ignored = 0;
-    info_walk(a, f, (int32_t)(info_end(f, le) - f), a.info_val + v, &ignored);
+    walk_row<WHICH>(a, ls, le, to, val + v, &ignored);
 }
 
 __global__ void vw_gather_i64(const long long *src, const long long *idx, int64_t n, long long *out) {
@@ -524,11 +750,13 @@ struct WideStore {
     int batch_rows = 8192, wpb = 256;
     int64_t n_batches = 0, n_rows = 0;
     bool want[9] = {false, false, false, false, false, false, false, false, false};
-    WideBuf id_loff, id_coff, id_val, id_valid, ref_off, ref_val, alt_valid, zeros, qual, qual_valid, fi_loff, fi_coff, fi_val, info_off, info_val, info_tab;
+    WideBuf id_loff, id_coff, id_val, id_valid, ref_off, ref_val, alt_valid, zeros, qual, qual_valid, fi_loff, fi_coff, fi_val, info_off, info_val, info_tab,
+        fmt_off, fmt_val, fmt_tab;
     std::vector<long long> batch_row0, base[kNScan];  // per batch (+ total): global item / byte offset of the batch's first row
-    static constexpr int kBufs = 16;
+    static constexpr int kBufs = 19;
     void all(WideBuf *out[kBufs]) {
-        WideBuf *v[kBufs] = {&id_loff, &id_coff, &id_val, &id_valid, &ref_off, &ref_val, &alt_valid, &zeros, &qual, &qual_valid, &fi_loff, &fi_coff, &fi_val, &info_off, &info_val, &info_tab};
+        WideBuf *v[kBufs] = {&id_loff, &id_coff, &id_val, &id_valid, &ref_off, &ref_val, &alt_valid, &zeros, &qual, &qual_valid, &fi_loff, &fi_coff, &fi_val, &info_off, &info_val, &info_tab,
+                             &fmt_off, &fmt_val, &fmt_tab};
         for (int i = 0; i < kBufs; ++i) out[i] = v[i];
     }
     template <class T>
@@ -566,9 +794,8 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     w->batch_rows = s->batch_rows;
     w->wpb = ((s->batch_rows + 63) / 64) * 2;
     for (int p : s->projection) w->want[p] = true;
-    if (w->want[8]) return fail(EXON_GPU_ERR_UNSUPPORTED, "vcf_next_batch: column 8 (formats) is re-serialised by the reference builder and is not built on the device yet");
-    if (w->want[7] && !s->info_defs.set)
-        return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: the info column needs the header's ##INFO definitions: call exon_gpu_vcf_set_header first");
+    if ((w->want[7] || w->want[8]) && !s->info_defs.set)
+        return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: the info / formats columns need the header's ##INFO / ##FORMAT definitions: call exon_gpu_vcf_set_header first");
     if (*n_rows_io == 0) return EXON_GPU_OK;
 
     // per-row temporaries in scratch_b behind the line tables: 5 counts (i32) | 5 prefixes (i64) | flags
@@ -597,7 +824,7 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
         x += al256w(bytes);
         return p;
     };
-    const bool need[kNScan] = {w->want[2], w->want[2], w->want[3], w->want[6], w->want[6], w->want[7]};
+    const bool need[kNScan] = {w->want[2], w->want[2], w->want[3], w->want[6], w->want[6], w->want[7], w->want[8]};
     WideArgs a;
     memset(&a, 0, sizeof(a));
     a.n_rows = n_rows;
@@ -608,7 +835,8 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     a.wpb = w->wpb;
     a.want_id = w->want[2], a.want_ref = w->want[3], a.want_alt = w->want[4], a.want_qual = w->want[5], a.want_filter = w->want[6];
     a.want_info = w->want[7];
-    long long *pre[kNScan] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    a.want_formats = w->want[8];
+    long long *pre[kNScan] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < kNScan; ++k) {
         if (!need[k]) continue;
         a.cnt[k] = (int32_t *)take(nr1 * 4);
@@ -650,9 +878,8 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     };
     const size_t valid_bytes = (size_t)w->n_batches * (size_t)w->wpb * 4;
     const size_t loff_bytes = (size_t)w->n_batches * (size_t)(w->batch_rows + 1) * 4;
-    if (w->want[7]) {
-        // the header's INFO definitions: hash | offset | length (u32 each) | type (u8) | key bytes
-        const InfoDefs &defs = s->info_defs;
+    // the header's INFO / FORMAT definitions: hash | offset | length (u32 each) | type | Number == 1 (u8 each) | key bytes
+    auto upload_defs = [&](const InfoDefs &defs, WideBuf &tab, KeyDefsPod &out) -> int {
         const size_t nk = defs.ids.size();
         std::vector<uint32_t> hs(nk), off(nk), len(nk);
         std::string blob;
@@ -664,24 +891,32 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
             len[k] = (uint32_t)defs.ids[k].size();
             blob += defs.ids[k];
         }
-        const size_t o_off = al256w(nk * 4), o_len = o_off + al256w(nk * 4), o_type = o_len + al256w(nk * 4), o_blob = o_type + al256w(nk);
-        if (int rc = dev_alloc(w->info_tab, o_blob + blob.size() + 16, false)) return rc;
-        uint8_t *t = (uint8_t *)w->info_tab.d;
+        const size_t o_off = al256w(nk * 4), o_len = o_off + al256w(nk * 4), o_type = o_len + al256w(nk * 4), o_single = o_type + al256w(nk),
+                     o_blob = o_single + al256w(nk);
+        if (int rc = dev_alloc(tab, o_blob + blob.size() + 16, false)) return rc;
+        uint8_t *t = (uint8_t *)tab.d;
         if (nk) {
             CUDA_TRY(cudaMemcpyAsync(t, hs.data(), nk * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(t + o_off, off.data(), nk * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(t + o_len, len.data(), nk * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(t + o_type, defs.types.data(), nk, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(t + o_single, defs.single.data(), nk, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(t + o_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaStreamSynchronize(st));  // the sources are locals
         }
-        a.info_hash = (const uint32_t *)t;
-        a.info_off = (const int32_t *)(t + o_off);
-        a.info_len = (const int32_t *)(t + o_len);
-        a.info_type = t + o_type;
-        a.info_blob = t + o_blob;
-        a.n_info = (int32_t)nk;
-    }
+        out.hash = (const uint32_t *)t;
+        out.off = (const int32_t *)(t + o_off);
+        out.len = (const int32_t *)(t + o_len);
+        out.type = t + o_type;
+        out.single = t + o_single;
+        out.blob = t + o_blob;
+        out.n = (int32_t)nk;
+        return EXON_GPU_OK;
+    };
+    if (w->want[7])
+        if (int rc = upload_defs(s->info_defs, w->info_tab, a.info_defs)) return rc;
+    if (w->want[8])
+        if (int rc = upload_defs(s->format_defs, w->fmt_tab, a.fmt_defs)) return rc;
     if (w->want[5]) {
         if (int rc = dev_alloc(w->qual, (size_t)n_rows * 4, false)) return rc;
         if (int rc = dev_alloc(w->qual_valid, valid_bytes, true)) return rc;
@@ -694,7 +929,11 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     vw_measure_kernel<<<grid, 256, 0, st>>>(a);
     ctx->launches.fetch_add(1);
     if (w->want[7]) {
-        vw_info_measure_kernel<<<grid, 256, 0, st>>>(a);
+        vw_text_measure_kernel<kInfoB><<<grid, 256, 0, st>>>(a);
+        ctx->launches.fetch_add(1);
+    }
+    if (w->want[8]) {
+        vw_text_measure_kernel<kFmtB><<<grid, 256, 0, st>>>(a);
         ctx->launches.fetch_add(1);
     }
 
@@ -721,11 +960,13 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     if (const uint32_t e = (uint32_t)h_misc[0])
-        return fail((e & ~(kWErrQualDigits | kWErrInfoKey | kWErrInfoForm)) ? EXON_GPU_ERR_PARSE : EXON_GPU_ERR_UNSUPPORTED, "VCF record at row %llu:%s%s%s%s%s%s%s", h_misc[1],
+        return fail((e & ~kWErrQualDigits) ? EXON_GPU_ERR_PARSE : EXON_GPU_ERR_UNSUPPORTED, "VCF record at row %llu:%s%s%s%s%s%s%s%s", h_misc[1],
                     (e & kWErrFields) ? " fewer than 8 tab-separated fields;" : "", (e & kWErrQual) ? " QUAL is not a float literal;" : "",
                     (e & kWErrQualDigits) ? " QUAL has more than 36 significant digits;" : "", (e & kWErrFieldLen) ? " a line of 2 GiB or more;" : "",
-                    (e & kWErrInfoValue) ? " an INFO key that is not a flag has no value;" : "", (e & kWErrInfoKey) ? " an INFO key the header does not define;" : "",
-                    (e & kWErrInfoForm) ? " an INFO value the reference would print differently (number not in Rust's Display form, '%' escape, flag with a value);" : "");
+                    (e & kWErrInfoValue) ? " an INFO key that is not a flag has no value (or '.'): the reference's builder unwraps a None there;" : "",
+                    (e & kWErrInfoForm) ? " an INFO value that does not parse as its declared type (or a flag with a value);" : "",
+                    (e & kWErrFmtValue) ? " a sample value is missing ('.'): the reference's builder unwraps a None there;" : "",
+                    (e & kWErrFmtForm) ? " a sample value that does not parse as its declared type;" : "");
     for (int k = 0; k < kNScan; ++k) {
         if (!need[k]) continue;
         for (int64_t b = 0; b < w->n_batches; ++b)
@@ -755,6 +996,11 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
         if (int rc = dev_alloc(w->info_val, (size_t)w->base[kInfoB][nb1 - 1], false)) return rc;
         a.info_offs = (int32_t *)w->info_off.d, a.info_val = (uint8_t *)w->info_val.d;
     }
+    if (w->want[8]) {
+        if (int rc = dev_alloc(w->fmt_off, loff_bytes, false)) return rc;
+        if (int rc = dev_alloc(w->fmt_val, (size_t)w->base[kFmtB][nb1 - 1], false)) return rc;
+        a.fmt_offs = (int32_t *)w->fmt_off.d, a.fmt_val = (uint8_t *)w->fmt_val.d;
+    }
     if (w->want[6]) {
         if (int rc = dev_alloc(w->fi_loff, loff_bytes, false)) return rc;
         if (int rc = dev_alloc(w->fi_coff, ((size_t)w->base[kFiE][nb1 - 1] + nb1) * 4, false)) return rc;
@@ -765,7 +1011,11 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
     vw_emit_kernel<<<grid, 256, 0, st>>>(a);
     ctx->launches.fetch_add(1);
     if (w->want[7]) {
-        vw_info_emit_kernel<<<grid, 256, 0, st>>>(a);
+        vw_text_emit_kernel<kInfoB><<<grid, 256, 0, st>>>(a);
+        ctx->launches.fetch_add(1);
+    }
+    if (w->want[8]) {
+        vw_text_emit_kernel<kFmtB><<<grid, 256, 0, st>>>(a);
         ctx->launches.fetch_add(1);
     }
     CUDA_TRY(cudaGetLastError());
@@ -837,6 +1087,13 @@ void wide_export(const WideStore *w, int col, int64_t b, int64_t rows, ArrowArra
             slot->bufs[0] = nullptr;
             slot->bufs[1] = w->p<int32_t>(w->info_off) + loff;
             slot->bufs[2] = w->p<uint8_t>(w->info_val) + w->base[kInfoB][(size_t)b];
+            break;
+        case 8:
+            a->null_count = 0;
+            a->n_buffers = 3;
+            slot->bufs[0] = nullptr;
+            slot->bufs[1] = w->p<int32_t>(w->fmt_off) + loff;
+            slot->bufs[2] = w->p<uint8_t>(w->fmt_val) + w->base[kFmtB][(size_t)b];
             break;
         default:  // 6
             a->null_count = 0;

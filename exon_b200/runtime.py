@@ -292,6 +292,22 @@ class VcfBatch:
         return self._schema
 
 
+class ArrowArrayStream(C.Structure):
+    _fields_ = [("get_schema", C.c_void_p), ("get_next", C.c_void_p), ("get_last_error", C.c_void_p), ("release", C.c_void_p),
+                ("private_data", C.c_void_p)]
+
+
+def export_reader(stream, take_ownership: bool = False):
+    """exon_gpu_stream_export -> pyarrow.RecordBatchReader (the Arrow C stream interface, the reference's own FFI shape)."""
+    import pyarrow as pa
+
+    c = ArrowArrayStream()
+    check(stream.lib.exon_gpu_stream_export(stream.handle, C.byref(c), int(take_ownership)))
+    if take_ownership:
+        stream.handle = C.c_void_p()
+    return pa.RecordBatchReader._import_from_c(C.addressof(c))
+
+
 class VcfStream:
     """exon_gpu_stream: one DataFusion partition stream over a group of VCF files."""
 

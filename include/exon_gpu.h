@@ -58,6 +58,17 @@ struct ArrowArray {
     void *private_data;
 };
 #endif
+/* Arrow C Stream Interface (https://arrow.apache.org/docs/format/CStreamInterface.html) */
+#ifndef ARROW_C_STREAM_INTERFACE
+#define ARROW_C_STREAM_INTERFACE
+struct ArrowArrayStream {
+    int (*get_schema)(struct ArrowArrayStream *, struct ArrowSchema *out);
+    int (*get_next)(struct ArrowArrayStream *, struct ArrowArray *out);
+    const char *(*get_last_error)(struct ArrowArrayStream *);
+    void (*release)(struct ArrowArrayStream *);
+    void *private_data;
+};
+#endif
 
 /* ---- status codes ---------------------------------------------------------------------------------- */
 enum {
@@ -265,6 +276,16 @@ int exon_gpu_tabix_query(exon_gpu_ctx *ctx, const uint8_t *tbi, size_t len, cons
 int exon_gpu_stream_feed_bgzf_chunk(exon_gpu_stream *s, const uint8_t *data, size_t len, uint64_t file_offset, const exon_gpu_chunk *chunk);
 /* Format-independent stream calls (the exon_gpu_vcf_* spellings remain valid for VCF streams). */
 int exon_gpu_stream_close(exon_gpu_stream *s);
+
+/* ---- Arrow C stream export (seam B4) --------------------------------------------------------------------------
+ * The reference's own FFI hands batches out as an FFI_ArrowArrayStream (create_dataset_stream_from_table_provider,
+ * exon/exon-core/src/ffi/mod.rs:58-73; stream object :25-49) and exon-r / exon-py read that struct.  These two calls give
+ * the same object for any stream opened with a projection (VCF, FASTQ, FASTA, BAM, GFF, mzML; host-resident columns):
+ * get_schema / get_next (release == NULL in the array = end of stream) / get_last_error / release.  get_next returns an
+ * errno value (EINVAL, ENOMEM, ENOTSUP, EIO) and get_last_error the library's message.  take_ownership != 0: releasing the
+ * Arrow stream closes the exon_gpu_stream too.  A Rust host wraps it with ArrowArrayStreamReader::from_raw. */
+int exon_gpu_stream_schema(exon_gpu_stream *s, struct ArrowSchema *out);
+int exon_gpu_stream_export(exon_gpu_stream *s, struct ArrowArrayStream *out, int take_ownership);
 int exon_gpu_stream_reset(exon_gpu_stream *s);
 int exon_gpu_stream_body_bytes(exon_gpu_stream *s, int64_t *out_bytes);
 
@@ -371,6 +392,9 @@ typedef struct {
  * elements (COUNT(*)).  Arrays are decoded as exon/exon-mzml/src/mzml_reader/binary_conversion.rs:26-95 does
  * (base64, optional zlib -- inflated on the device --, little-endian f32 / f64).  A zlib-compressed array is sized by the
  * defaultArrayLength of its <spectrum>; without it, or when the stream inflates to another size: EXON_GPU_ERR_PARSE. */
+/* Record batches of an mzML stream (MzMLArrayBuilder, exon/exon-mzml/src/array_builder.rs:236-439; schema config.rs:92-147). */
+int exon_gpu_mzml_open_columns(exon_gpu_ctx *ctx, const exon_gpu_fastq_opts *opts, exon_gpu_stream **out);
+int exon_gpu_mzml_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 int exon_gpu_mzml_filter_sum(exon_gpu_stream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected,
                              int64_t *out_spectra);
 

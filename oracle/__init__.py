@@ -177,22 +177,112 @@ def vcf_wide_rows(data):
         L.exo_vcf_wide_free(wp)
 
 
+# ---- INFO / FORMAT re-serialisation (string mode), pure Python ---------------------------------------------------------------
+# Reserved keys noodles falls back to when the header does not define a key (VCF 4.3 / 4.4 tables 1 and 2; the subset whose
+# definition does not differ between the versions): key -> (type, Number == 1)
+_RESERVED_INFO = {b"AA": (b"String", True), b"AC": (b"Integer", False), b"AD": (b"Integer", False), b"ADF": (b"Integer", False),
+                  b"ADR": (b"Integer", False), b"AF": (b"Float", False), b"AN": (b"Integer", True), b"BQ": (b"Float", True),
+                  b"CIGAR": (b"String", False), b"DB": (b"Flag", False), b"DP": (b"Integer", True), b"END": (b"Integer", True),
+                  b"H2": (b"Flag", False), b"H3": (b"Flag", False), b"MQ": (b"Float", True), b"MQ0": (b"Integer", True),
+                  b"NS": (b"Integer", True), b"SB": (b"Integer", False), b"SOMATIC": (b"Flag", False), b"VALIDATED": (b"Flag", False),
+                  b"1000G": (b"Flag", False), b"IMPRECISE": (b"Flag", False), b"NOVEL": (b"Flag", False), b"SVTYPE": (b"String", True)}
+_RESERVED_FORMAT = {b"AD": (b"Integer", False), b"ADF": (b"Integer", False), b"ADR": (b"Integer", False), b"DP": (b"Integer", True),
+                    b"EC": (b"Integer", False), b"FT": (b"String", True), b"GL": (b"Float", False), b"GP": (b"Float", False),
+                    b"GQ": (b"Integer", True), b"HQ": (b"Integer", False), b"MQ": (b"Integer", True), b"PL": (b"Integer", False),
+                    b"PP": (b"Integer", False), b"PQ": (b"Integer", True), b"PS": (b"Integer", True)}
+
+
+def _header_defs(text: bytes, kind: bytes):
+    import re
+
+    out = {}
+    for line in text.split(b"\n"):
+        if not line.startswith(b"##" + kind + b"=<"):
+            continue
+        ident = re.search(rb"[<,]ID=([^,>]+)", line).group(1)
+        num = re.search(rb",Number=([^,>]+)", line)
+        out[ident] = (re.search(rb",Type=([^,>]+)", line).group(1), num is not None and num.group(1) == b"1")
+    return out
+
+
+def rust_f32_display(x) -> bytes:
+    """`f32::to_string()`: shortest digits that round-trip, positional, "NaN" / "inf" / "-inf", "-0"."""
+    v = np.float32(x)
+    if np.isnan(v):
+        return b"NaN"
+    if np.isinf(v):
+        return b"inf" if v > 0 else b"-inf"
+    if v == 0:
+        return b"-0" if np.signbit(v) else b"0"
+    return np.format_float_positional(v, unique=True, trim="-").encode()
+
+
+def _rust_f32_parse(e: bytes) -> float:
+    import re
+
+    t = e.decode("ascii")
+    low = t.lower().lstrip("+-")
+    if low in ("inf", "infinity", "nan"):
+        return float(t)
+    if not re.fullmatch(r"[+-]?(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?", t):
+        raise ValueError(f"not an f32 literal: {t!r}")
+    return float(t)
+
+
+def _percent_decode(e: bytes) -> bytes:
+    out, i = bytearray(), 0
+    while i < len(e):
+        if e[i] == 0x25 and i + 2 < len(e) and all(c in b"0123456789abcdefABCDEF" for c in e[i + 1:i + 3]):
+            out.append(int(e[i + 1:i + 3], 16))
+            i += 3
+        else:
+            out.append(e[i])
+            i += 1
+    return bytes(out)
+
+
+def _elem(ty: bytes, e: bytes) -> bytes:
+    import re
+
+    if not e:
+        raise ValueError("empty element")
+    if ty == b"Integer":
+        if not re.fullmatch(rb"[+-]?\d+", e) or not -2**31 <= int(e) < 2**31:
+            raise ValueError(f"not an i32: {e!r}")
+        return str(int(e)).encode()
+    if ty == b"Float":
+        return rust_f32_display(_rust_f32_parse(e))
+    d = _percent_decode(e)
+    if ty == b"Character" and len(d) != 1:
+        raise ValueError("not a character")
+    return d
+
+
+def _value(ty: bytes, single: bool, val: bytes, skip_missing_chars: bool = False) -> bytes:
+    if val in (b"", b"."):
+        raise ValueError("missing value: the reference's builder unwraps a None")
+    if single or ty == b"String":
+        return _elem(ty, val)
+    elems = []
+    for e in val.split(b","):
+        if e == b".":
+            if not (skip_missing_chars and ty == b"Character"):
+                elems.append(b".")
+        else:
+            elems.append(_elem(ty, e))
+    return b",".join(elems)
+
+
 def vcf_info_strings(data):
     """Column 7 (info, string mode) of every record as LazyVCFArrayBuilder::append prints it
     (/root/reference/exon/exon-vcf/src/array_builder/lazy_array_builder.rs:217-298): noodles' typed view of the field -- types from
-    the header's ##INFO lines -- re-serialised as `key=value` joined by ';', a flag as `key=true`, integers through i32
-    Display, floats through f32 Display (shortest digits that round-trip, never an exponent), array elements joined by ','
-    with '.' for a missing one.  Pure Python (small inputs only); pinned by slt/vcf-select-tests.slt:6-10.
-    A key the header does not define or a non-flag key without a value raises (the reference's behaviour there is
-    noodles-internal / a panic)."""
-    import re
-
+    the header's ##INFO lines, else the specification's reserved keys, else one String -- re-serialised as `key=value` joined by
+    ';', a flag as `key=true`, integers through i32 Display, floats through f32 Display (shortest digits that round-trip, never
+    an exponent), strings percent-decoded, array elements joined by ',' with '.' for a missing one.  Pure Python (small inputs
+    only); pinned by slt/vcf-select-tests.slt:6-10.  A missing value (`key=.`, a non-flag key without `=`) raises: the
+    reference's builder unwraps a None there."""
     text = bytes(_buf(data))
-    types = {}
-    for line in text.split(b"\n"):
-        if not line.startswith(b"##INFO=<"):
-            continue
-        types[re.search(rb"[<,]ID=([^,>]+)", line).group(1)] = re.search(rb",Type=([^,>]+)", line).group(1)
+    types = _header_defs(text, b"INFO")
     out = []
     for line in text[header_len(text):].split(b"\n"):
         if not line:
@@ -204,26 +294,67 @@ def vcf_info_strings(data):
         parts = []
         for entry in field.split(b";"):
             key, eq, val = entry.partition(b"=")
-            ty = types[key]
+            ty, single = types.get(key) or _RESERVED_INFO.get(key) or (b"String", True)
             if ty == b"Flag":
-                if eq:
+                if val:
                     raise ValueError("flag with a value")
                 parts.append(key + b"=true")
                 continue
             if not eq:
                 raise ValueError("missing value")
-            elems = []
-            for e in val.split(b","):
-                if e == b".":
-                    elems.append(b".")
-                elif ty == b"Integer":
-                    elems.append(str(int(e)).encode())
-                elif ty == b"Float":
-                    elems.append(np.format_float_positional(np.float32(float(e)), unique=True, trim="-").encode())
-                else:
-                    elems.append(e)
-            parts.append(key + b"=" + b",".join(elems))
+            parts.append(key + b"=" + _value(ty, single, val))
         out.append(b";".join(parts))
+    return out
+
+
+def _genotype(val: bytes) -> bytes:
+    import re
+
+    if val in (b"", b"."):
+        raise ValueError("missing genotype")
+    alleles = re.split(rb"[/|]", val)
+    seps = [bytes([c]) for c in val if c in b"/|"]
+    out = []
+    prev = b"|" if all(s == b"|" for s in seps) else b"/"   # noodles' inferred phasing of the first allele
+    for k, a in enumerate(alleles):
+        if a != b"." and not a.isdigit():
+            raise ValueError(f"bad allele {a!r}")
+        txt = b"." if a == b"." else str(int(a)).encode()
+        if k:
+            out.append(prev + txt)
+            prev = seps[k - 1]
+        else:
+            out.append(txt)
+    return b"".join(out)
+
+
+def vcf_formats_strings(data):
+    """Column 8 (formats, string mode) as LazyVCFArrayBuilder::append prints it (lazy_array_builder.rs:310-432): the FORMAT keys
+    joined by ':', a tab, and every sample with its values re-serialised (genotype allele by allele, numbers through Rust's
+    Display) and joined by ':', samples joined by tabs.  A sites-only record gives "\t".  Pinned by the first row of
+    slt/vcf-select-tests.slt:12-15 (`GT:PL:PG\t0/0:0,3,26:0`).  A missing sample value ('.') raises: the builder unwraps a None."""
+    text = bytes(_buf(data))
+    types = _header_defs(text, b"FORMAT")
+    out = []
+    for line in text[header_len(text):].split(b"\n"):
+        if not line:
+            continue
+        f = line.split(b"\t")
+        if len(f) < 9 or not f[8]:
+            out.append(b"\t")
+            continue
+        keys = f[8].split(b":")
+        samples = []
+        for smp in f[9:]:
+            vals = []
+            for key, val in zip(keys, smp.split(b":")):
+                if key == b"GT":
+                    vals.append(_genotype(val))
+                    continue
+                ty, single = types.get(key) or _RESERVED_FORMAT.get(key) or (b"String", True)
+                vals.append(_value(ty, single, val, skip_missing_chars=True))
+            samples.append(b":".join(vals))
+        out.append(f[8] + b"\t" + b"\t".join(samples))
     return out
 
 
