@@ -259,8 +259,8 @@ def test_state_errors(gpu_ctx):
         s.feed(make_vcf([("1", "5"), ("1", "6")]))
         assert s.filter_count(make_region("1")) == 2
     with pytest.raises(ExonGpuError) as e:
-        gpu_ctx.open_vcf(projection=(8,))
-    assert e.value.code == _abi.ERR_UNSUPPORTED
+        gpu_ctx.open_vcf(projection=(9,))     # 0..8 are the VCF file-schema columns
+    assert e.value.code == _abi.ERR_ARG
 
 
 # ---- size-independent properties at a larger size ------------------------------------------------------------
