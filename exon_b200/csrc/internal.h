@@ -219,6 +219,7 @@ struct VcfStream {
     bool bam_serial_ok = false;           // the last verified pass was the serial one (one chain per file)
     struct BamColumns *bam_cols = nullptr;  // column store of exon_gpu_bam_next_batch (bam.cu)
     struct GffColumns *gff_cols = nullptr;  // column store of exon_gpu_gff_next_batch (gff_columns.cu)
+    struct MzColumns *mz_cols = nullptr;    // column store of exon_gpu_mzml_next_batch (mzml_columns.cu)
     void *d_bam = nullptr;                // walk entries | per-file first entries | remap | exits | counts | misc
     size_t d_bam_cap = 0, bam_n_entries = 0, bam_n_firsts = 0;
     size_t bam_o_firsts = 0, bam_o_remap = 0, bam_o_exits = 0, bam_o_counts = 0, bam_o_misc = 0, bam_o_region = 0;
@@ -280,6 +281,9 @@ int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table
 // defined in bam.cu
 void bam_columns_free(VcfStream *s);
 int bam_next_batch(VcfStream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
+
+// defined in mzml_columns.cu
+void mzml_columns_free(VcfStream *s);
 
 // defined in gff_columns.cu
 void gff_columns_free(VcfStream *s);

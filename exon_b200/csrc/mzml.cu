@@ -29,6 +29,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "mzml.cuh"
 #include "scan_i64.cuh"
 #include "tile_ring.cuh"
 
@@ -218,31 +219,32 @@ __global__ void __launch_bounds__(MzRing::WARPS * 32, 3) mzml_events_kernel(cons
     if (lane == 0 && n_spectrum) atomicAdd(a.n_events + 5, (unsigned long long)n_spectrum);
 }
 
-struct SpecDesc {
-    const uint8_t *mz, *in;   // trimmed base64 payloads (NULL: the spectrum has no such array)
-    uint32_t mz_len, in_len;  // characters
-    uint32_t mz_f32, in_f32;
-    uint32_t mz_zl, in_zl;    // zlib-compressed
-    uint32_t n_default;       // defaultArrayLength of the <spectrum> tag (0: absent)
-    uint32_t pad_;
-    const uint8_t *mz_raw, *in_raw;  // zlib arrays: the inflated little-endian values (set by the inflate detour)
-};
+// (SpecDesc lives in mzml.cuh: the column build of mzml_columns.cu reads the same descriptors)
 
 __device__ __forceinline__ bool is_ws(uint8_t c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r'; }
 
-__global__ void mzml_spectra_kernel(const unsigned long long *ev, unsigned long long n, const ScanSeg *segs, SpecDesc *out,
-                                    unsigned long long *n_spec, uint32_t *flags) {
+// 1 for every <spectrum> event (its exclusive scan is the spectrum's rank in file order)
+__global__ void mzml_spec_flags_kernel(const unsigned long long *ev, unsigned long long n, int32_t *flag) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) flag[i] = i < n && (ev[i] & 15u) == kEvSpectrum ? 1 : 0;
+}
+
+__global__ void mzml_spectra_kernel(const unsigned long long *ev, unsigned long long n, const ScanSeg *segs, const long long *rank, SpecDesc *out,
+                                    uint32_t *flags) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || (ev[i] & 15u) != kEvSpectrum) return;
     const unsigned long long seg = ev[i] >> 44;
     SpecDesc d;
-    d.mz = d.in = d.mz_raw = d.in_raw = nullptr;
-    d.mz_len = d.in_len = d.mz_f32 = d.in_f32 = d.mz_zl = d.in_zl = d.n_default = d.pad_ = 0;
+    memset(&d, 0, sizeof(d));
+    const uint8_t *base = segs[seg].base + segs[seg].skip;
+    d.seg = (uint32_t)seg;
+    d.tag = base + ((ev[i] >> 4) & ((1ull << 40) - 1ull));
+    d.end = base + segs[seg].len;  // until a </spectrum> event says otherwise
     // defaultArrayLength="N" inside the <spectrum ...> tag (the only place a zlib array's decoded size is declared); parsed
     // only when the spectrum turns out to hold a zlib array
     auto default_array_length = [&]() -> uint32_t {
-        const uint8_t *t = segs[seg].base + segs[seg].skip + ((ev[i] >> 4) & ((1ull << 40) - 1ull));
-        const uint8_t *tend = segs[seg].base + segs[seg].skip + segs[seg].len;
+        const uint8_t *t = d.tag;
+        const uint8_t *tend = base + segs[seg].len;
         const char lit[] = "defaultArrayLength=\"";
         for (int k = 0; k < 4096 && t + k + 20 < tend && t[k] != '>'; ++k) {
             if (t[k] != 'd') continue;
@@ -261,8 +263,12 @@ __global__ void mzml_spectra_kernel(const unsigned long long *ev, unsigned long 
     for (unsigned long long j = i + 1; j < n; ++j) {
         const unsigned long long e = ev[j];
         const uint32_t k = (uint32_t)(e & 15u);
-        if ((e >> 44) != seg || k == kEvSpectrum || k == kEvSpecEnd) break;
+        if ((e >> 44) != seg || k == kEvSpectrum) break;
         const unsigned long long off = (e >> 4) & ((1ull << 40) - 1ull);
+        if (k == kEvSpecEnd) {
+            d.end = base + off;
+            break;
+        }
         if (k == kEvBda) { kind = f32 = f64 = zl = nc = 0; open = false; }
         else if (k == kEvMz || k == kEvIntensity || k == kEvWave) { if (!kind) kind = k; }
         else if (k == kEvF32) f32 = 1;
@@ -273,77 +279,39 @@ __global__ void mzml_spectra_kernel(const unsigned long long *ev, unsigned long 
         else if (k == kEvBinEnd) {
             if (!open) { err |= kMzErrFormat; continue; }
             open = false;
-            const uint8_t *base = segs[seg].base + segs[seg].skip;
             const uint8_t *b0 = base + start, *b1 = base + off;
             while (b0 < b1 && is_ws(*b0)) ++b0;   // quick-xml trim_text(true)
             while (b1 > b0 && is_ws(b1[-1])) --b1;
-            if (b1 == b0 || (kind != kEvMz && kind != kEvIntensity)) continue;  // empty content, or an array the query does not read
+            if (!kind) continue;  // no array type
+            if (b1 == b0) {       // <binary/> or empty content: the builder appends an EMPTY list for the array (array_builder.rs:276-296)
+                const int a = kind == kEvMz ? 0 : kind == kEvIntensity ? 1 : 2;
+                d.arr[a] = b0;
+                d.len[a] = 0;
+                d.f32[a] = d.zl[a] = 0;
+                continue;
+            }
             if ((!f32 && !f64) || (!zl && !nc)) { err |= kMzErrFormat; continue; }
             if (((b1 - b0) & 3) != 0 || (b1 - b0) > 0x7FFFFFFFll) { err |= kMzErrFormat; continue; }
             if (zl) {
                 if (!d.n_default) d.n_default = default_array_length();
                 err |= d.n_default ? kMzHasZlib : kMzErrZlib;
             }
-            if (kind == kEvMz) { d.mz = b0; d.mz_len = (uint32_t)(b1 - b0); d.mz_f32 = f32 && !f64; d.mz_zl = zl; }
-            else { d.in = b0; d.in_len = (uint32_t)(b1 - b0); d.in_f32 = f32 && !f64; d.in_zl = zl; }
+            const int a = kind == kEvMz ? 0 : kind == kEvIntensity ? 1 : 2;
+            d.arr[a] = b0;
+            d.len[a] = (uint32_t)(b1 - b0);
+            d.f32[a] = f32 && !f64;
+            d.zl[a] = zl;
         }
     }
     if (open) err |= kMzErrFormat;
     if (err) atomicOr(flags, err);
-    out[atomicAdd(n_spec, 1ull)] = d;
-}
-
-// value `i` (w = 4 or 8 bytes, little endian) of a base64 payload; *bad |= 0x80 on a character outside the alphabet
-__device__ __forceinline__ unsigned long long b64_value(const uint8_t *p, uint32_t i, int w, const uint8_t *lut, uint32_t &bad) {
-    const uint32_t o = i * (uint32_t)w, g0 = o / 3u, s = o - 3u * g0;
-    const uint8_t *a = p + 4u * g0;
-    const uintptr_t ai = reinterpret_cast<uintptr_t>(a);
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(ai & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(ai & 3u) * 8u;
-    uint32_t cw[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) cw[k] = __ldg(wp + k);   // 16 characters at any alignment (the caller guarantees slack)
-    uint32_t r[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t c = __funnelshift_r(cw[k], cw[k + 1], sh);
-        const uint32_t v0 = lut[c & 255u], v1 = lut[(c >> 8) & 255u], v2 = lut[(c >> 16) & 255u], v3 = lut[c >> 24];
-        if (k * 3 < (int)s + w) bad |= v0 | v1 | v2 | v3;   // groups past the value may be anything (the next tag)
-        const uint32_t t = ((v0 & 63u) << 18) | ((v1 & 63u) << 12) | ((v2 & 63u) << 6) | (v3 & 63u);
-        r[k] = __byte_perm(t, 0u, 0x4012u);  // decoded bytes of the group in memory order
-    }
-    const unsigned long long lo = (unsigned long long)r[0] | ((unsigned long long)r[1] << 24) | ((unsigned long long)r[2] << 48);
-    const unsigned long long hi = (unsigned long long)(r[2] >> 16) | ((unsigned long long)r[3] << 8);
-    return s == 0u ? lo : (lo >> (8u * s)) | (hi << (64u - 8u * s));
-}
-
-// value `i` of an inflated array (16-byte aligned, little endian)
-__device__ __forceinline__ unsigned long long raw_value(const uint8_t *p, uint32_t i, int w) {
-    return w == 4 ? (unsigned long long)__ldg(reinterpret_cast<const uint32_t *>(p) + i) : __ldg(reinterpret_cast<const unsigned long long *>(p) + i);
-}
-
-__device__ __forceinline__ uint32_t b64_bytes(const uint8_t *p, uint32_t len) {
-    if (!len) return 0;
-    uint32_t n = len / 4u * 3u;
-    if (p[len - 1] == '=') --n;
-    if (p[len - 2] == '=') --n;
-    return n;
+    out[rank[i]] = d;
 }
 
 __global__ void __launch_bounds__(256) mzml_sum_kernel(const SpecDesc *specs, unsigned long long n_spec, int has_pred, double lo, double hi,
                                                       double *out_sum, unsigned long long *out_cnt, uint32_t *flags) {
     __shared__ uint8_t lut[256];
-    {
-        const int c = threadIdx.x;
-        uint8_t v = 0x80;
-        if (c >= 'A' && c <= 'Z') v = (uint8_t)(c - 'A');
-        else if (c >= 'a' && c <= 'z') v = (uint8_t)(c - 'a' + 26);
-        else if (c >= '0' && c <= '9') v = (uint8_t)(c - '0' + 52);
-        else if (c == '+') v = 62;
-        else if (c == '/') v = 63;
-        else if (c == '=') v = 0;   // padding only occurs in the last group, whose padded bytes are never part of a value
-        lut[c] = v;
-    }
+    b64_lut_init(lut);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const unsigned long long wid = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -352,17 +320,17 @@ __global__ void __launch_bounds__(256) mzml_sum_kernel(const SpecDesc *specs, un
     uint32_t bad = 0;
     for (unsigned long long sidx = wid; sidx < n_spec; sidx += nw) {
         const SpecDesc d = specs[sidx];
-        if (!d.mz || !d.in) continue;
-        const int wm = d.mz_f32 ? 4 : 8, wi = d.in_f32 ? 4 : 8;
-        const uint32_t nm = d.mz_zl ? d.n_default : b64_bytes(d.mz, d.mz_len) / (uint32_t)wm;
-        const uint32_t ni = d.in_zl ? d.n_default : b64_bytes(d.in, d.in_len) / (uint32_t)wi;
+        if (!d.arr[0] || !d.arr[1]) continue;
+        const int wm = d.f32[0] ? 4 : 8, wi = d.f32[1] ? 4 : 8;
+        const uint32_t nm = d.zl[0] ? d.n_default : b64_bytes(d.arr[0], d.len[0]) / (uint32_t)wm;
+        const uint32_t ni = d.zl[1] ? d.n_default : b64_bytes(d.arr[1], d.len[1]) / (uint32_t)wi;
         const uint32_t n = nm < ni ? nm : ni;   // the two unnested lists are zipped; the longer one's tail meets NULLs
         for (uint32_t i = lane; i < n; i += 32) {
-            const unsigned long long mb = d.mz_zl ? raw_value(d.mz_raw, i, wm) : b64_value(d.mz, i, wm, lut, bad);
-            const double m = d.mz_f32 ? (double)__uint_as_float((uint32_t)mb) : __longlong_as_double((long long)mb);
+            const unsigned long long mb = d.zl[0] ? raw_value(d.raw[0], i, wm) : b64_value(d.arr[0], i, wm, lut, bad);
+            const double m = d.f32[0] ? (double)__uint_as_float((uint32_t)mb) : __longlong_as_double((long long)mb);
             if (has_pred && !(m >= lo && m <= hi)) continue;
-            const unsigned long long ib = d.in_zl ? raw_value(d.in_raw, i, wi) : b64_value(d.in, i, wi, lut, bad);
-            acc += d.in_f32 ? (double)__uint_as_float((uint32_t)ib) : __longlong_as_double((long long)ib);
+            const unsigned long long ib = d.zl[1] ? raw_value(d.raw[1], i, wi) : b64_value(d.arr[1], i, wi, lut, bad);
+            acc += d.f32[1] ? (double)__uint_as_float((uint32_t)ib) : __longlong_as_double((long long)ib);
             ++cnt;
         }
     }
@@ -393,7 +361,7 @@ __device__ __forceinline__ uint32_t zarr_isize(uint32_t n_default, bool f32, uin
     return (uint32_t)(want < cap ? want : cap);
 }
 struct ZArr {
-    uint32_t spec, which;  // which: 0 = m/z, 1 = intensity
+    uint32_t spec, which;  // which: 0 = m/z, 1 = intensity, 2 = wavelength
 };
 // Z0: the list of zlib arrays + their sizes: [0] compressed bytes (padded), [1] inflated bytes (padded to 16), [2] bitmap words
 __global__ void mzml_zlist_kernel(const SpecDesc *specs, unsigned long long n_spec, ZArr *list, unsigned long long *n_list, int32_t *sizes,
@@ -401,15 +369,15 @@ __global__ void mzml_zlist_kernel(const SpecDesc *specs, unsigned long long n_sp
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_spec) return;
     const SpecDesc d = specs[i];
-    for (uint32_t which = 0; which < 2; ++which) {
-        const bool zl = which ? d.in_zl : d.mz_zl;
-        const uint8_t *p = which ? d.in : d.mz;
+    for (uint32_t which = 0; which < 3; ++which) {
+        const bool zl = d.zl[which] != 0;
+        const uint8_t *p = d.arr[which];
         if (!zl || !p) continue;
         const unsigned long long k = atomicAdd(n_list, 1ull);
         if (k >= cap) continue;
         list[k] = ZArr{(uint32_t)i, which};
-        const uint32_t comp = b64_bytes(p, which ? d.in_len : d.mz_len);
-        const uint32_t isize = zarr_isize(d.n_default, which ? d.in_f32 : d.mz_f32, comp);
+        const uint32_t comp = b64_bytes(p, d.len[which]);
+        const uint32_t isize = zarr_isize(d.n_default, d.f32[which] != 0, comp);
         sizes[k] = (int32_t)((comp + 64u + 15u) & ~15u);
         sizes[cap + 1 + k] = (int32_t)((isize + 15u) & ~15u);
         sizes[2 * (cap + 1) + k] = (int32_t)((isize + 31u) / 32u);
@@ -437,8 +405,8 @@ __global__ void __launch_bounds__(256) mzml_b64_kernel(const SpecDesc *specs, co
     uint32_t bad = 0;
     for (unsigned long long k = wid; k < n_list; k += nw) {
         const SpecDesc d = specs[list[k].spec];
-        const uint8_t *p = list[k].which ? d.in : d.mz;
-        const uint32_t len = list[k].which ? d.in_len : d.mz_len, nbytes = b64_bytes(p, len);
+        const uint8_t *p = d.arr[list[k].which];
+        const uint32_t len = d.len[list[k].which], nbytes = b64_bytes(p, len);
         uint8_t *dst = comp + comp_off[k];
         for (uint32_t g = lane; g < len / 4u; g += 32) {
             const uint32_t v0 = lut[p[4 * g]], v1 = lut[p[4 * g + 1]], v2 = lut[p[4 * g + 2]], v3 = lut[p[4 * g + 3]];
@@ -461,9 +429,9 @@ __global__ void mzml_ztable_kernel(SpecDesc *specs, const ZArr *list, unsigned l
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_list) return;
     SpecDesc &d = specs[list[k].spec];
-    const bool in = list[k].which != 0;
-    const uint32_t nbytes = b64_bytes(in ? d.in : d.mz, in ? d.in_len : d.mz_len);
-    const uint32_t isize = zarr_isize(d.n_default, in ? d.in_f32 : d.mz_f32, nbytes);
+    const uint32_t which = list[k].which;
+    const uint32_t nbytes = b64_bytes(d.arr[which], d.len[which]);
+    const uint32_t isize = zarr_isize(d.n_default, d.f32[which] != 0, nbytes);
     const uint8_t *z = comp + comp_off[k];
     BgzfMember m;
     m.in_off = (uint64_t)comp_off[k] + 2u;
@@ -477,26 +445,44 @@ __global__ void mzml_ztable_kernel(SpecDesc *specs, const ZArr *list, unsigned l
         m.isize = 0;  // skipped by the inflate kernels
     }
     table[k] = m;
-    if (in) d.in_raw = out + out_off[k];
-    else d.mz_raw = out + out_off[k];
+    d.raw[which] = out + out_off[k];
 }
 
 size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
-int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected, int64_t *out_spectra) {
-    if (int rc = s->flush_gz()) return rc;
+MzScan::~MzScan() {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (void *p : z_pool)
+        if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// rank of the first spectrum whose resident range is >= seg0[f] (descriptors are in file order: seg is non-decreasing)
+__global__ void mzml_file_bounds_kernel(const SpecDesc *specs, unsigned long long n_spec, const uint32_t *seg0, int n_files, long long *out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_files) return;
+    unsigned long long lo = 0, hi = n_spec;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (specs[mid].seg < seg0[f]) lo = mid + 1;
+        else hi = mid;
+    }
+    out[f] = (long long)lo;
+}
+
+int mzml_scan_spectra(VcfStream *s, MzScan *out) {
     Ctx *ctx = s->ctx;
     cudaStream_t st = ctx->stream;
-    std::lock_guard<std::recursive_mutex> work(ctx->work_mu);
-    if (out_sum) *out_sum = 0.0;
-    if (out_selected) *out_selected = 0;
-    if (out_spectra) *out_spectra = 0;
+    out->ctx = ctx;
+    out->n_spec = 0;
+    out->file_spec0.assign(1, 0);
     std::vector<Piece> pieces;
     s->cut_pieces(pieces);
     if (pieces.empty()) return EXON_GPU_OK;
     std::vector<ScanSeg> h_segs;
+    std::vector<uint32_t> file_seg0;  // first resident range of every file
     int64_t n_tiles = 0, n_bytes = 0;
     for (const Piece &p : pieces) {
         ScanSeg sg;
@@ -507,6 +493,7 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
         sg.pad_ = 0;
         n_tiles += (sg.skip + p.len + MzRing::TILE - 1) / MzRing::TILE;
         n_bytes += p.len;
+        if (p.starts_file || h_segs.empty()) file_seg0.push_back((uint32_t)h_segs.size());
         h_segs.push_back(sg);
     }
     if (h_segs.size() >= (1u << 20)) return fail(EXON_GPU_ERR_UNSUPPORTED, "mzml: too many resident ranges");
@@ -523,13 +510,16 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
         const size_t cap = (size_t)(attempt == 0 ? n_bytes / 96 + 4096 : n_bytes / 8 + 4096);
-        size_t sort_bytes = 0;
+        size_t sort_bytes = 0, scan_bytes = 0;
         CUDA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)cap, 0, 64, st));
+        CUDA_TRY(exclusive_sum_i32_i64(nullptr, scan_bytes, (const int32_t *)nullptr, (long long *)nullptr, (int)(cap + 1), st));
         const size_t o_segs = 0, o_ev = o_segs + al256(h_segs.size() * sizeof(ScanSeg)), o_ev2 = o_ev + al256(cap * 8), o_sort = o_ev2 + al256(cap * 8),
-                     o_out = o_sort + al256(sort_bytes);
-        if (int rc = ctx->ensure_scratch(o_out + 256, 256)) return rc;
+                     o_flag = o_sort + al256(std::max(sort_bytes, scan_bytes)), o_rank = o_flag + al256((cap + 1) * 4), o_files = o_rank + al256((cap + 1) * 8),
+                     o_out = o_files + al256(file_seg0.size() * 12 + 16);
+        if (int rc = ctx->ensure_scratch(o_out + 256, 256 + file_seg0.size() * 8)) return rc;
         uint8_t *scr = (uint8_t *)ctx->scratch;
-        unsigned long long *d_out = (unsigned long long *)(scr + o_out);  // [0] n_events [1] n_spec [2] sum (f64) [3] selected [4] flags
+        unsigned long long *d_out = (unsigned long long *)(scr + o_out);
+        out->d_out = d_out;
         CUDA_TRY(cudaMemcpyAsync(scr + o_segs, h_segs.data(), h_segs.size() * sizeof(ScanSeg), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemsetAsync(d_out, 0, 64, st));
         MzArgs a;
@@ -541,20 +531,21 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
         a.n_events = d_out;
         int64_t grid = std::min<int64_t>((int64_t)occ * ctx->sm_count, (n_tiles + MzRing::WARPS - 1) / MzRing::WARPS);
         if (grid < 1) grid = 1;
-        CUDA_TRY(ctx->timed_begin(st));
+        if (attempt == 0) CUDA_TRY(ctx->timed_begin(st));
         mzml_events_kernel<<<(unsigned)grid, MzRing::WARPS * 32, MzRing::smem_bytes, st>>>(a);
         CUDA_TRY(cudaGetLastError());
         unsigned long long *h = (unsigned long long *)ctx->h_scratch;
         CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        const unsigned long long n_ev = h[0], n_spec_ev = h[5];
+        const unsigned long long n_ev = h[0], n_spec = h[5];
         ctx->launches.fetch_add(1);
         if (n_ev > cap) {
             if (attempt == 0) continue;  // an XML-dense file: go again with room for every possible event
             return fail(EXON_GPU_ERR_UNSUPPORTED, "mzml: event buffer overflow");
         }
-        if (n_ev == 0) return EXON_GPU_OK;
-        if (int rc = ctx->ensure_scratch_b((size_t)(n_spec_ev + 1) * sizeof(SpecDesc))) return rc;
+        out->file_spec0.assign(file_seg0.size() + 1, 0);
+        if (n_ev == 0 || n_spec == 0) return EXON_GPU_OK;
+        if (int rc = ctx->ensure_scratch_b((size_t)(n_spec + 1) * sizeof(SpecDesc))) return rc;
         SpecDesc *d_spec = (SpecDesc *)ctx->scratch_b;
         size_t sb = sort_bytes;
         int seg_bits = 1;
@@ -562,33 +553,38 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
         // nothing lives above the segment index (the kind bits stay in: <binary></binary> puts two events at one offset)
         CUDA_TRY(cub::DeviceRadixSort::SortKeys(scr + o_sort, sb, (const unsigned long long *)(scr + o_ev), (unsigned long long *)(scr + o_ev2), (int)n_ev, 0,
                                                 44 + seg_bits, st));
-        mzml_spectra_kernel<<<(unsigned)((n_ev + 255) / 256), 256, 0, st>>>((const unsigned long long *)(scr + o_ev2), n_ev, a.segs,
-                                                                              d_spec, d_out + 1, (uint32_t *)(d_out + 4));
+        // file order: a spectrum's slot is the number of <spectrum> events before it
+        int32_t *d_flag = (int32_t *)(scr + o_flag);
+        long long *d_rank = (long long *)(scr + o_rank);
+        mzml_spec_flags_kernel<<<(unsigned)((n_ev + 256) / 256), 256, 0, st>>>((const unsigned long long *)(scr + o_ev2), n_ev, d_flag);
+        size_t tb = scan_bytes;
+        CUDA_TRY(exclusive_sum_i32_i64(scr + o_sort, tb, (const int32_t *)d_flag, d_rank, (int)(n_ev + 1), st));
+        mzml_spectra_kernel<<<(unsigned)((n_ev + 255) / 256), 256, 0, st>>>((const unsigned long long *)(scr + o_ev2), n_ev, a.segs, d_rank, d_spec,
+                                                                              (uint32_t *)(d_out + 4));
         CUDA_TRY(cudaGetLastError());
+        // where every file's spectra start
+        uint32_t *d_seg0 = (uint32_t *)(scr + o_files);
+        long long *d_f0 = (long long *)(scr + o_files + al256(file_seg0.size() * 4));
+        CUDA_TRY(cudaMemcpyAsync(d_seg0, file_seg0.data(), file_seg0.size() * 4, cudaMemcpyHostToDevice, st));
+        mzml_file_bounds_kernel<<<(unsigned)((file_seg0.size() + 127) / 128), 128, 0, st>>>(d_spec, n_spec, d_seg0, (int)file_seg0.size(), d_f0);
         CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h + 32, d_f0, file_seg0.size() * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        const unsigned long long n_spec = h[1];
+        ctx->launches.fetch_add(5);
+        for (size_t f = 0; f < file_seg0.size(); ++f) out->file_spec0[f] = (long long)h[32 + f];
+        out->file_spec0[file_seg0.size()] = (long long)n_spec;
         if ((uint32_t)h[4] & kMzErrFormat) return fail(EXON_GPU_ERR_PARSE, "malformed mzML: a <binary> element without data type / compression / end tag, or invalid base64");
         if ((uint32_t)h[4] & kMzErrZlib)
             return fail(EXON_GPU_ERR_PARSE, "mzml: a zlib-compressed binary array (MS:1000574) without defaultArrayLength on its <spectrum>");
-        void *z_pool[2] = {nullptr, nullptr};
-        struct ZFree {
-            void **p;
-            cudaStream_t st;
-            ~ZFree() {
-                for (int i = 0; i < 2; ++i)
-                    if (p[i]) cudaFreeAsync(p[i], st);
-            }
-        } z_free{z_pool, st};
-        if (n_spec && ((uint32_t)h[4] & kMzHasZlib)) {
+        if ((uint32_t)h[4] & kMzHasZlib) {
             // ---- zlib detour: list -> sizes -> scans -> base64 decode -> member table -> inflate ----
-            const unsigned long long zcap = 2 * n_spec;
+            const unsigned long long zcap = 3 * n_spec;
             size_t cub2 = 0;
             CUDA_TRY(exclusive_sum_i32_i64(nullptr, cub2, (const int32_t *)nullptr, (long long *)nullptr, (int)(zcap + 1), st));
             const size_t o_list = 0, o_sizes = o_list + al256(zcap * sizeof(ZArr)), o_offs = o_sizes + al256(3 * (zcap + 1) * 4), o_cub = o_offs + al256(3 * (zcap + 1) * 8),
                          o_tab = o_cub + al256(cub2), o_misc = o_tab + al256(zcap * sizeof(BgzfMember)), z_bytes = o_misc + 256;
-            CUDA_TRY(cudaMallocAsync(&z_pool[0], z_bytes, st));
-            uint8_t *zb = (uint8_t *)z_pool[0];
+            CUDA_TRY(cudaMallocAsync(&out->z_pool[0], z_bytes, st));
+            uint8_t *zb = (uint8_t *)out->z_pool[0];
             ZArr *d_list = (ZArr *)(zb + o_list);
             int32_t *d_sizes = (int32_t *)(zb + o_sizes);
             long long *d_offs = (long long *)(zb + o_offs);
@@ -597,8 +593,8 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
             CUDA_TRY(cudaMemsetAsync(d_zmisc, 0, 64, st));
             mzml_zlist_kernel<<<(unsigned)((n_spec + 255) / 256), 256, 0, st>>>(d_spec, n_spec, d_list, d_zmisc, d_sizes, zcap);
             for (int q = 0; q < 3; ++q) {
-                size_t tb = cub2;
-                CUDA_TRY(exclusive_sum_i32_i64(zb + o_cub, tb, (const int32_t *)(d_sizes + q * (zcap + 1)), d_offs + q * (zcap + 1), (int)(zcap + 1), st));
+                size_t tb2 = cub2;
+                CUDA_TRY(exclusive_sum_i32_i64(zb + o_cub, tb2, (const int32_t *)(d_sizes + q * (zcap + 1)), d_offs + q * (zcap + 1), (int)(zcap + 1), st));
             }
             long long h_tot[3];
             unsigned long long h_nz = 0;
@@ -609,8 +605,8 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
             if (h_nz > zcap) return fail(EXON_GPU_ERR_STATE, "mzml: zlib array list overflow");
             if (h_nz) {
                 const size_t comp_total = (size_t)h_tot[0] + 512, out_total = (size_t)h_tot[1] + 64;
-                CUDA_TRY(cudaMallocAsync(&z_pool[1], al256(comp_total) + out_total, st));
-                uint8_t *d_comp = (uint8_t *)z_pool[1], *d_raw = d_comp + al256(comp_total);
+                CUDA_TRY(cudaMallocAsync(&out->z_pool[1], al256(comp_total) + out_total, st));
+                uint8_t *d_comp = (uint8_t *)out->z_pool[1], *d_raw = d_comp + al256(comp_total);
                 const int b64_grid = (int)std::min<unsigned long long>((h_nz + 7) / 8, (unsigned long long)ctx->sm_count * 8);
                 mzml_b64_kernel<<<b64_grid, 256, 0, st>>>(d_spec, d_list, h_nz, d_offs, d_comp, (uint32_t *)(d_out + 4));
                 mzml_ztable_kernel<<<(unsigned)((h_nz + 127) / 128), 128, 0, st>>>(d_spec, d_list, h_nz, d_offs, d_offs + (zcap + 1), d_offs + 2 * (zcap + 1), d_comp,
@@ -623,32 +619,49 @@ int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_su
                 ctx->launches.fetch_add(2);
                 uint32_t h_inf[2] = {0, 0};
                 CUDA_TRY(cudaMemcpyAsync(h_inf, d_zmisc + 2, 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaStreamSynchronize(st));
                 if (h_inf[0])
                     return fail(EXON_GPU_ERR_PARSE, "mzml: a zlib-compressed binary array does not inflate:%s%s", (h_inf[0] & 1u) ? " invalid DEFLATE data;" : "",
                                 (h_inf[0] & 2u) ? " its size differs from defaultArrayLength x value width;" : "");
+                if ((uint32_t)h[4] & kMzErrZlib) return fail(EXON_GPU_ERR_PARSE, "mzml: a zlib-compressed binary array with an invalid zlib header");
+                if ((uint32_t)h[4] & kMzErrFormat) return fail(EXON_GPU_ERR_PARSE, "malformed mzML: invalid base64 in a zlib-compressed binary array");
             }
         }
-        if (n_spec) {
-            const int sum_grid = (int)std::min<unsigned long long>((n_spec + 7) / 8, (unsigned long long)ctx->sm_count * 8);
-            mzml_sum_kernel<<<sum_grid, 256, 0, st>>>(d_spec, n_spec, pred != nullptr, pred ? pred->mz_lo : 0.0,
-                                                       pred ? pred->mz_hi : 0.0, (double *)(d_out + 2), d_out + 3, (uint32_t *)(d_out + 4));
-            CUDA_TRY(cudaGetLastError());
-        }
-        CUDA_TRY(ctx->timed_end(st));
-        ctx->launches.fetch_add(3);
-        CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        const uint32_t flags = (uint32_t)h[4];
-        if (flags & kMzErrZlib)
-            return fail(EXON_GPU_ERR_PARSE, "mzml: a zlib-compressed binary array (MS:1000574) without defaultArrayLength on its <spectrum>, or with an invalid zlib header");
-        if (flags & kMzErrFormat) return fail(EXON_GPU_ERR_PARSE, "malformed mzML: a <binary> element without data type / compression / end tag, or invalid base64");
-        if (out_sum) memcpy(out_sum, &h[2], 8);
-        if (out_selected) *out_selected = (int64_t)h[3];
-        if (out_spectra) *out_spectra = (int64_t)n_spec;
+        out->n_spec = n_spec;
+        out->d_spec = d_spec;
         return EXON_GPU_OK;
     }
-    return fail(EXON_GPU_ERR_UNSUPPORTED, "mzml: could not size the event buffers");
+    return fail(EXON_GPU_ERR_STATE, "mzml: unreachable");
+}
+
+int mzml_filter_sum(VcfStream *s, const exon_gpu_mzml_pred *pred, double *out_sum, int64_t *out_selected, int64_t *out_spectra) {
+    if (int rc = s->flush_gz()) return rc;
+    Ctx *ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    std::lock_guard<std::recursive_mutex> work(ctx->work_mu);
+    if (out_sum) *out_sum = 0.0;
+    if (out_selected) *out_selected = 0;
+    if (out_spectra) *out_spectra = 0;
+    MzScan sc;
+    if (int rc = mzml_scan_spectra(s, &sc)) return rc;
+    if (!sc.n_spec) return EXON_GPU_OK;
+    unsigned long long *d_out = sc.d_out;
+    unsigned long long *h = (unsigned long long *)ctx->h_scratch;
+    const int sum_grid = (int)std::min<unsigned long long>((sc.n_spec + 7) / 8, (unsigned long long)ctx->sm_count * 8);
+    mzml_sum_kernel<<<sum_grid, 256, 0, st>>>(sc.d_spec, sc.n_spec, pred != nullptr, pred ? pred->mz_lo : 0.0, pred ? pred->mz_hi : 0.0, (double *)(d_out + 2),
+                                               d_out + 3, (uint32_t *)(d_out + 4));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(ctx->timed_end(st));
+    ctx->launches.fetch_add(1);
+    CUDA_TRY(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint32_t flags = (uint32_t)h[4];
+    if (flags & kMzErrFormat) return fail(EXON_GPU_ERR_PARSE, "malformed mzML: a <binary> element without data type / compression / end tag, or invalid base64");
+    if (out_sum) memcpy(out_sum, &h[2], 8);
+    if (out_selected) *out_selected = (int64_t)h[3];
+    if (out_spectra) *out_spectra = (int64_t)sc.n_spec;
+    return EXON_GPU_OK;
 }
 
 }  // namespace exon

@@ -79,6 +79,7 @@ void VcfStream::release_all() {
     fq_columns_free(this);
     bam_columns_free(this);
     gff_columns_free(this);
+    mzml_columns_free(this);
 }
 
 // Append body bytes that live on the host to the arena (one async H2D copy on the stream).

@@ -140,8 +140,8 @@ class Context:
     def open_fasta(self, **kw) -> "FastaStream":
         return FastaStream(self, **kw)
 
-    def open_mzml(self) -> "MzmlStream":
-        return MzmlStream(self)
+    def open_mzml(self, **kw) -> "MzmlStream":
+        return MzmlStream(self, **kw)
 
     def open_bam(self, **kw) -> "BamStream":
         return BamStream(self, **kw)
@@ -598,11 +598,34 @@ class BamStream:
 class MzmlStream(FastqStream):
     """exon_gpu_stream opened with exon_gpu_mzml_open (feeds / reset / close as for the text formats)."""
 
-    def __init__(self, ctx: Context):
+    def __init__(self, ctx: Context, *, batch_rows: int = 8192, projection=None, columns_on_device: bool = False):
         self.ctx = ctx
         self.lib = ctx.lib
         self.handle = C.c_void_p()
-        check(self.lib.exon_gpu_mzml_open(ctx.handle, C.byref(self.handle)))
+        self.columns_on_device = columns_on_device
+        if projection is None:
+            check(self.lib.exon_gpu_mzml_open(ctx.handle, C.byref(self.handle)))
+        else:
+            self._proj = (C.c_int32 * max(len(projection), 1))(*projection)
+            opts = _abi.FastqOpts(batch_rows, len(projection), self._proj, int(columns_on_device))
+            check(self.lib.exon_gpu_mzml_open_columns(ctx.handle, C.byref(opts), C.byref(self.handle)))
+
+    def next_batch(self):
+        """exon_gpu_mzml_next_batch -> VcfBatch (import it with to_pyarrow(): the columns are nested) or None at the end."""
+        arr, sch = _abi.ArrowArray(), _abi.ArrowSchema()
+        check(self.lib.exon_gpu_mzml_next_batch(self.handle, C.byref(arr), C.byref(sch)))
+        if not arr.release:
+            if sch.release:
+                sch.release(C.byref(sch))
+            return None
+        return VcfBatch(arr, sch, self.columns_on_device)
+
+    def batches(self):
+        while True:
+            b = self.next_batch()
+            if b is None:
+                return
+            yield b
 
     def feed(self, data, *, is_last: bool = True, device_ptr: int | None = None, nbytes: int | None = None):
         if device_ptr is not None:

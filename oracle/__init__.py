@@ -678,6 +678,53 @@ def mzml_decode_binary(b64: bytes, zlib_compressed: bool, f32: bool):
     return vals
 
 
+def mzml_rows(data):
+    """Every <spectrum> as MzMLArrayBuilder::append materialises it (/root/reference/exon/exon-mzml/src/array_builder.rs:330-416):
+    {id, mz, intensity, wavelength (list of f64 | None), cv_params [(accession, name, value | None)], precursor_mz, precursor_charge}.
+    Pure Python on xml.etree (small inputs only): the spectrum's own cvParam children; arrays decoded as
+    binary_conversion.rs:26-95 does (base64 -> optional zlib -> LE f32 / f64 -> f64), an empty <binary> gives [];
+    MS:1000744 / MS:1000041 of the first selected ion of the first precursor."""
+    import base64
+    import struct
+    import xml.etree.ElementTree as ET
+    import zlib
+
+    ns = "{http://psi.hupo.org/ms/mzml}"
+    text = bytes(_buf(data))
+    root = ET.fromstring(text)
+    if not root.tag.startswith(ns):
+        ns = ""
+    out = []
+    for sp in root.iter(ns + "spectrum"):
+        row = {"id": sp.get("id"), "mz": None, "intensity": None, "wavelength": None, "precursor_mz": None, "precursor_charge": None}
+        row["cv_params"] = [(c.get("accession"), c.get("name"), c.get("value") or None) for c in sp.findall(ns + "cvParam")]
+        for bda in sp.iter(ns + "binaryDataArray"):
+            acc = [c.get("accession") for c in bda.findall(ns + "cvParam")]
+            kind = next((k for a in acc for k, code in (("mz", "MS:1000514"), ("intensity", "MS:1000515"), ("wavelength", "MS:1000617")) if a == code), None)
+            b = bda.find(ns + "binary")
+            if kind is None or b is None:
+                continue
+            txt = (b.text or "").strip()
+            if not txt:
+                row[kind] = []
+                continue
+            raw = base64.b64decode(txt)
+            if "MS:1000574" in acc:
+                raw = zlib.decompress(raw)
+            w, f = (4, "f") if ("MS:1000521" in acc and "MS:1000523" not in acc) else (8, "d")
+            row[kind] = [float(x) for x in struct.unpack("<%d%s" % (len(raw) // w, f), raw[: len(raw) // w * w])]
+        pl = sp.find(ns + "precursorList")
+        if pl is not None:
+            ion = pl.findall(ns + "precursor")[0].find(ns + "selectedIonList").findall(ns + "selectedIon")[0]
+            for c in ion.findall(ns + "cvParam"):
+                if c.get("accession") == "MS:1000744" and c.get("value") is not None and row["precursor_mz"] is None:
+                    row["precursor_mz"] = float(c.get("value"))
+                if c.get("accession") == "MS:1000041" and c.get("value") is not None and row["precursor_charge"] is None:
+                    row["precursor_charge"] = int(c.get("value"))
+        out.append(row)
+    return out
+
+
 def fasta_count(data) -> int:
     """COUNT(*) of a FASTA file: definition lines (oracle/fastq_oracle.c: exo_fasta_count)."""
     a = _buf(data)
