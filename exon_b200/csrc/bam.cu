@@ -26,6 +26,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "f32_display.cuh"
 #include "internal.h"
 #include "scan_i64.cuh"
 
@@ -417,9 +418,11 @@ int VcfStream::bam_filter_count(const exon_gpu_bam_pred *pred, int64_t *counts, 
 // =====================================================================================================================
 namespace {
 
-enum { kBName = 0, kBRef = 1, kBMapq = 2, kBCigar = 3, kBMate = 4, kBSeq = 5, kBQual = 6, kBNVar = 7 };
+enum { kBName = 0, kBRef = 1, kBMapq = 2, kBCigar = 3, kBMate = 4, kBSeq = 5, kBQual = 6, kBPlain = 7, kBTagN = 7, kBTagB = 8, kBNVar = 9 };
 constexpr uint32_t kBErrLayout = 1u;  // the variable part does not fit the record's block_size / bad CIGAR op / bad refID
 constexpr uint32_t kBErrName = 2u;    // missing read name ("*")
+constexpr uint32_t kBErrTag = 4u;     // an auxiliary field with an unknown type, or one that runs past the record
+constexpr uint32_t kBErrTagFloat = 8u;  // a B:f element of 9e13 or more in magnitude: "{:.2}" of it is not printed here
 
 struct BamFileTab {
     long long row0;    // first record of the file (global numbering); the sentinel carries n_records
@@ -438,9 +441,12 @@ struct BamColArgs {
     const long long *brow;  // n_batches + 1
     int64_t n_batches;
     int32_t batch_rows, wpb;
-    int32_t want[10];
+    int32_t want[11];
     int32_t *cnt[kBNVar];
     const long long *pre[kBNVar];
+    // tags (column 10): list offsets in the batch layout; per entry (index entry + batch): tag / value string offsets
+    int32_t *tags_loff, *tag_off, *tval_off;
+    uint8_t *tag_val, *tval_val;
     uint8_t *rowflags;  // bit0 reference valid, bit1 start valid, bit2 end valid, bit3 mapq valid, bit4 mate valid
     int32_t *flag;
     long long *start, *end;
@@ -501,19 +507,170 @@ __device__ __forceinline__ BamRec bam_rec(const uint8_t *p, int32_t n_ref) {
     return R;
 }
 
+// ---- tags (column 10) ------------------------------------------------------------------------------------------------
+// TagsMapBuilder::append (exon/exon-sam/src/tag_builder.rs:497-741, the default `tags` type List<Struct{tag, value: Utf8}>):
+// every auxiliary field in record order, its value as text -- integers through i64 Display (:527-538), A as the character,
+// Z / H as their text, f through f32 Display (:566-576), B integer arrays joined by "," (:590-680) and B:f arrays as
+// "{:.2}" joined by ", " (:682-698).
+struct TagSink {
+    uint8_t *dst;
+    int32_t n;
+    __device__ __forceinline__ void put(uint8_t c) {
+        if (dst) dst[n] = c;
+        ++n;
+    }
+    __device__ void put_i64(long long v) {
+        uint8_t d[20];
+        int nd = 0;
+        unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+        do {
+            d[nd++] = (uint8_t)('0' + u % 10ull);
+            u /= 10ull;
+        } while (u);
+        if (v < 0) put('-');
+        while (nd) put(d[--nd]);
+    }
+};
+// Rust `format!("{:.2}", v)` for f32: the exact value rounded half-to-even at two decimals.  |v| * 100 is exact in a double
+// (24 + 7 bits), rint() rounds to nearest-even; false when the magnitude is beyond what is printed here.
+__device__ bool put_f32_2(float v, TagSink &o) {
+    if (v != v) {
+        o.put('N'), o.put('a'), o.put('N');
+        return true;
+    }
+    const bool neg = (__float_as_uint(v) >> 31) != 0u;
+    if (neg) o.put('-');
+    const float av = fabsf(v);
+    if (av > 3.0e38f) {
+        o.put('i'), o.put('n'), o.put('f');
+        return true;
+    }
+    const double x = (double)av * 100.0;
+    if (x >= 9.0e15) return false;
+    const unsigned long long r = (unsigned long long)rint(x);
+    o.put_i64((long long)(r / 100ull));
+    o.put('.');
+    o.put((uint8_t)('0' + (r / 10ull) % 10ull));
+    o.put((uint8_t)('0' + r % 10ull));
+    return true;
+}
+__device__ __forceinline__ int bam_aux_width(uint8_t t) {
+    return (t == 'c' || t == 'C' || t == 'A') ? 1 : (t == 's' || t == 'S') ? 2 : (t == 'i' || t == 'I' || t == 'f') ? 4 : 0;
+}
+__device__ __forceinline__ long long bam_aux_int(const uint8_t *p, uint8_t t) {
+    switch (t) {
+        case 'c': return (long long)(int8_t)p[0];
+        case 'C': return (long long)p[0];
+        case 's': return (long long)(int16_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8));
+        case 'S': return (long long)((uint32_t)p[0] | ((uint32_t)p[1] << 8));
+        case 'i': return (long long)(int32_t)ld_u32(p);
+        default: return (long long)ld_u32(p);
+    }
+}
+struct TagOut {
+    int32_t *tag_off, *tval_off;  // entries of the record's first field
+    uint8_t *tag_val, *tval_val;  // batch bases
+    int32_t ent0, byte0;          // entries / value bytes of the batch before this record
+};
+// Walks the auxiliary fields [p, end): *n = fields, *bytes = value text bytes.  Returns error bits.
+__device__ uint32_t bam_tags_walk(const uint8_t *p, const uint8_t *end, int32_t *n, int32_t *bytes, const TagOut *o) {
+    int32_t ne = 0, nb = 0;
+    uint32_t err = 0;
+    while (p < end) {
+        if (end - p < 4) {
+            err |= kBErrTag;
+            break;
+        }
+        const uint8_t t = p[2];
+        if (o) {
+            o->tag_off[ne] = 2 * (o->ent0 + ne);
+            o->tag_val[2 * (o->ent0 + ne)] = p[0];
+            o->tag_val[2 * (o->ent0 + ne) + 1] = p[1];
+            o->tval_off[ne] = o->byte0 + nb;
+        }
+        TagSink sk{o ? o->tval_val + o->byte0 + nb : nullptr, 0};
+        p += 3;
+        if (t == 'A') {  // `*c as char` then to_string: bytes of 0x80 and above become two UTF-8 bytes
+            if (p[0] < 0x80) {
+                sk.put(p[0]);
+            } else {
+                sk.put((uint8_t)(0xC0 | (p[0] >> 6)));
+                sk.put((uint8_t)(0x80 | (p[0] & 0x3F)));
+            }
+            p += 1;
+        } else if (t == 'c' || t == 'C' || t == 's' || t == 'S' || t == 'i' || t == 'I') {
+            const int w = bam_aux_width(t);
+            if (end - p < w) {
+                err |= kBErrTag;
+                break;
+            }
+            sk.put_i64(bam_aux_int(p, t));
+            p += w;
+        } else if (t == 'f') {
+            if (end - p < 4) {
+                err |= kBErrTag;
+                break;
+            }
+            uint8_t buf[kF32DisplayMax];
+            const int k = f32_display(__uint_as_float(ld_u32(p)), buf);
+            for (int q = 0; q < k; ++q) sk.put(buf[q]);
+            p += 4;
+        } else if (t == 'Z' || t == 'H') {
+            while (p < end && *p) sk.put(*p++);
+            if (p >= end) {
+                err |= kBErrTag;
+                break;
+            }
+            ++p;
+        } else if (t == 'B') {
+            if (end - p < 5) {
+                err |= kBErrTag;
+                break;
+            }
+            const uint8_t st = p[0];
+            const uint32_t cnt = ld_u32(p + 1);
+            const int w = st == 'A' ? 0 : bam_aux_width(st);
+            p += 5;
+            if (!w || (uint64_t)cnt * (uint64_t)w > (uint64_t)(end - p)) {
+                err |= kBErrTag;
+                break;
+            }
+            for (uint32_t i = 0; i < cnt; ++i) {
+                if (st == 'f') {
+                    if (i) sk.put(','), sk.put(' ');
+                    if (!put_f32_2(__uint_as_float(ld_u32(p)), sk)) err |= kBErrTagFloat;
+                } else {
+                    if (i) sk.put(',');
+                    sk.put_i64(bam_aux_int(p, st));
+                }
+                p += w;
+            }
+        } else {
+            err |= kBErrTag;
+            break;
+        }
+        nb += sk.n;
+        ++ne;
+    }
+    *n = ne;
+    *bytes = nb;
+    return err;
+}
+
 __global__ void __launch_bounds__(256) bam_col_measure_kernel(const __grid_constant__ BamColArgs a) {
     const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (r >= a.n_rows) return;
     const int f = bam_find_file(a.files, a.n_files, r);
     const BamFileTab F = a.files[f];
     const BamRec R = bam_rec(a.rec_ptr[r], F.n_ref);
-    int32_t c[kBNVar] = {0, 0, 0, 0, 0, 0, 0};
+    int32_t c[kBNVar] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint8_t rf = 0;
     uint32_t err = 0;
     long long start = 0, end = 0;
     if (!R.ok) {
         err = kBErrLayout;
     } else {
+        if (a.want[10]) err |= bam_tags_walk(R.qual + R.l_seq, R.r + R.block_size, &c[kBTagN], &c[kBTagB], nullptr);
         c[kBName] = (int32_t)R.l_read_name - 1;
         if (R.l_read_name == 2 && R.name[0] == '*') err |= kBErrName;
         if (R.ref_id >= 0) {
@@ -653,6 +810,25 @@ __global__ void __launch_bounds__(256) bam_col_emit_kernel(const __grid_constant
     // warp per record, so that the stores of a record coalesce
     if (a.off[kBSeq]) open_cell(kBSeq, v);
     if (a.off[kBQual]) open_cell(kBQual, v);
+    if (a.tags_loff) {
+        const long long e = a.pre[kBTagN][r], e0 = a.pre[kBTagN][r0], y = a.pre[kBTagB][r], y0 = a.pre[kBTagB][r0];
+        a.tags_loff[lrow] = (int32_t)(e - e0);
+        TagOut o;
+        o.tag_off = a.tag_off + e + b;
+        o.tval_off = a.tval_off + e + b;
+        o.tag_val = a.tag_val + 2 * e0;
+        o.tval_val = a.tval_val + y0;
+        o.ent0 = (int32_t)(e - e0);
+        o.byte0 = (int32_t)(y - y0);
+        if (last) {
+            const long long e1 = a.pre[kBTagN][r + 1];
+            a.tags_loff[lrow + 1] = (int32_t)(e1 - e0);
+            a.tag_off[e1 + b] = (int32_t)(2 * (e1 - e0));
+            a.tval_off[e1 + b] = (int32_t)(a.pre[kBTagB][r + 1] - y0);
+        }
+        int32_t n, nb;
+        bam_tags_walk(R.qual + R.l_seq, R.r + R.block_size, &n, &nb, &o);
+    }
 }
 
 // sequence (4-bit -> letters) and quality_score (i8 -> i64) of one record per warp
@@ -696,7 +872,7 @@ struct BamColumns {
     int batch_rows = 8192, wpb = 256;
     int64_t n_rows = 0, n_batches = 0, next = 0;
     std::vector<int> projection;
-    BamBuf off[kBNVar], val[kBNVar], valid[5], flag, start, end;
+    BamBuf off[kBNVar], val[kBNVar], valid[5], flag, start, end, tags_loff, tag_off, tval_off, tag_val, tval_val;
     std::vector<long long> batch_row0, base[kBNVar];
     template <class T>
     const T *p(const BamBuf &b) const { return static_cast<const T *>(on_device ? b.d : b.h); }
@@ -704,6 +880,7 @@ struct BamColumns {
         for (int k = 0; k < kBNVar; ++k) fn(off[k]), fn(val[k]);
         for (int k = 0; k < 5; ++k) fn(valid[k]);
         fn(flag), fn(start), fn(end);
+        fn(tags_loff), fn(tag_off), fn(tval_off), fn(tag_val), fn(tval_val);
     }
     void unref() {
         if (refs.fetch_sub(1) == 1) {
@@ -743,7 +920,7 @@ int bam_build_columns(VcfStream *s) {
     c->wpb = ((s->batch_rows + 63) / 64) * 2;
     c->projection = s->projection;
     c->batch_row0.assign(1, 0);
-    bool want[10] = {false, false, false, false, false, false, false, false, false, false};
+    bool want[11] = {false, false, false, false, false, false, false, false, false, false, false};
     for (int p : s->projection) want[p] = true;
     if (s->bam_n_entries == 0) return EXON_GPU_OK;
     uint8_t *d = (uint8_t *)s->d_bam;
@@ -844,6 +1021,8 @@ int bam_build_columns(VcfStream *s) {
         ca.want[col] = want[col];
         if (want[col] && kColVar[col] >= 0) need[kColVar[col]] = true;
     }
+    ca.want[10] = want[10];
+    need[kBTagN] = need[kBTagB] = want[10];
     for (int k = 0; k < kBNVar; ++k) {
         pre[k] = nullptr;
         if (!need[k]) continue;
@@ -915,9 +1094,11 @@ int bam_build_columns(VcfStream *s) {
     CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (const uint32_t e = (uint32_t)h_misc[0])
-        return fail(EXON_GPU_ERR_PARSE, "malformed BAM record at row %llu:%s%s", h_misc[1],
+        return fail((e & kBErrTagFloat) && !(e & ~kBErrTagFloat) ? EXON_GPU_ERR_UNSUPPORTED : EXON_GPU_ERR_PARSE, "malformed BAM record at row %llu:%s%s%s%s", h_misc[1],
                     (e & kBErrLayout) ? " fields do not fit block_size, or an invalid CIGAR op / reference id;" : "",
-                    (e & kBErrName) ? " missing read name in the non-nullable name column;" : "");
+                    (e & kBErrName) ? " missing read name in the non-nullable name column;" : "",
+                    (e & kBErrTag) ? " an auxiliary field with an unknown type or one that runs past the record;" : "",
+                    (e & kBErrTagFloat) ? " a B:f element too large for the \"{:.2}\" printer;" : "");
     const size_t off_bytes = (size_t)c->n_batches * (size_t)(c->batch_rows + 1) * 4;
     const size_t valid_bytes = (size_t)c->n_batches * (size_t)c->wpb * 4;
     for (int k = 0; k < kBNVar; ++k) {
@@ -925,10 +1106,21 @@ int bam_build_columns(VcfStream *s) {
         for (int64_t b = 0; b < c->n_batches; ++b)
             if (c->base[k][(size_t)b + 1] - c->base[k][(size_t)b] > 0x7FFFFFFFll)
                 return fail(EXON_GPU_ERR_UNSUPPORTED, "bam_next_batch: batch %lld overflows int32 offsets", (long long)b);
+        if (k >= kBPlain) continue;  // the tags column has its own layout (below)
         if (int rc = dev_alloc(c->off[k], off_bytes, false)) return rc;
         if (int rc = dev_alloc(c->val[k], (size_t)c->base[k][nb1 - 1] * (k == kBQual ? 8 : 1), false)) return rc;
         ca.off[k] = (int32_t *)c->off[k].d;
         ca.val[k] = (uint8_t *)c->val[k].d;
+    }
+    if (want[10]) {
+        const size_t n_ent_t = (size_t)c->base[kBTagN][nb1 - 1];
+        if (int rc = dev_alloc(c->tags_loff, off_bytes, false)) return rc;
+        if (int rc = dev_alloc(c->tag_off, (n_ent_t + nb1) * 4, false)) return rc;
+        if (int rc = dev_alloc(c->tval_off, (n_ent_t + nb1) * 4, false)) return rc;
+        if (int rc = dev_alloc(c->tag_val, 2 * n_ent_t, false)) return rc;
+        if (int rc = dev_alloc(c->tval_val, (size_t)c->base[kBTagB][nb1 - 1], false)) return rc;
+        ca.tags_loff = (int32_t *)c->tags_loff.d, ca.tag_off = (int32_t *)c->tag_off.d, ca.tval_off = (int32_t *)c->tval_off.d;
+        ca.tag_val = (uint8_t *)c->tag_val.d, ca.tval_val = (uint8_t *)c->tval_val.d;
     }
     for (int col = 0; col < 10; ++col) {
         const int v = kColValid[col];
@@ -954,6 +1146,7 @@ int bam_build_columns(VcfStream *s) {
         for (int k = 0; k < kBNVar; ++k) to_host(c->off[k]), to_host(c->val[k]);
         for (int k = 0; k < 5; ++k) to_host(c->valid[k]);
         to_host(c->flag), to_host(c->start), to_host(c->end);
+        to_host(c->tags_loff), to_host(c->tag_off), to_host(c->tval_off), to_host(c->tag_val), to_host(c->tval_val);
         if (rc) return rc;
     }
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -963,9 +1156,13 @@ int bam_build_columns(VcfStream *s) {
 struct BamBatchPriv {
     BamColumns *cols;
     int n_children;
-    ArrowArray children[10];
-    ArrowArray *child_ptrs[10];
-    const void *bufs[10][3];
+    ArrowArray children[11];
+    ArrowArray *child_ptrs[11];
+    const void *bufs[11][3];
+    // tags: list -> struct -> {tag utf8, value utf8}
+    ArrowArray tag_struct, tag_name, tag_value;
+    ArrowArray *tag_struct_ptr, *tag_kids[2];
+    const void *tag_struct_bufs[1], *tag_name_bufs[3], *tag_value_bufs[3];
     ArrowArray item;  // quality_score's int64 child
     ArrowArray *item_ptr;
     const void *item_bufs[2];
@@ -980,10 +1177,12 @@ void bam_release_batch(ArrowArray *a) {
 }
 struct BamSchemaPriv {
     int n_children;
-    ArrowSchema children[10];
-    ArrowSchema *child_ptrs[10];
+    ArrowSchema children[11];
+    ArrowSchema *child_ptrs[11];
     ArrowSchema item;
     ArrowSchema *item_ptr;
+    ArrowSchema tag_struct, tag_name, tag_value;
+    ArrowSchema *tag_struct_ptr, *tag_kids[2];
 };
 void bam_release_schema_child(ArrowSchema *s) { s->release = nullptr; }
 void bam_release_schema(ArrowSchema *s) {
@@ -992,9 +1191,9 @@ void bam_release_schema(ArrowSchema *s) {
 }
 // SAMSchemaBuilder::default, exon/exon-sam/src/schema_builder.rs:385-401
 void bam_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
-    static const char *names[10] = {"name", "flag", "reference", "start", "end", "mapping_quality", "cigar", "mate_reference", "sequence", "quality_score"};
-    static const char *formats[10] = {"u", "i", "u", "l", "l", "u", "u", "u", "u", "+l"};
-    static const bool nullable[10] = {false, false, true, true, true, true, false, true, false, false};
+    static const char *names[11] = {"name", "flag", "reference", "start", "end", "mapping_quality", "cigar", "mate_reference", "sequence", "quality_score", "tags"};
+    static const char *formats[11] = {"u", "i", "u", "l", "l", "u", "u", "u", "u", "+l", "+l"};
+    static const bool nullable[11] = {false, false, true, true, true, true, false, true, false, false, true};
     auto *p = new BamSchemaPriv();
     p->n_children = (int)projection.size();
     for (int i = 0; i < p->n_children; ++i) {
@@ -1014,6 +1213,25 @@ void bam_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
             p->item_ptr = &p->item;
             c.n_children = 1;
             c.children = &p->item_ptr;
+        }
+        if (col == 10) {  // TagsMapBuilder::new, exon/exon-sam/src/tag_builder.rs:480-495: List<item: Struct{tag: Utf8 !null, value: Utf8}>
+            auto init = [](ArrowSchema &x, const char *fmt, const char *name, bool nullable_) {
+                memset(&x, 0, sizeof(x));
+                x.format = fmt;
+                x.name = name;
+                x.flags = nullable_ ? ARROW_FLAG_NULLABLE : 0;
+                x.release = bam_release_schema_child;
+            };
+            init(p->tag_struct, "+s", "item", true);
+            init(p->tag_name, "u", "tag", false);
+            init(p->tag_value, "u", "value", true);
+            p->tag_kids[0] = &p->tag_name;
+            p->tag_kids[1] = &p->tag_value;
+            p->tag_struct.n_children = 2;
+            p->tag_struct.children = p->tag_kids;
+            p->tag_struct_ptr = &p->tag_struct;
+            c.n_children = 1;
+            c.children = &p->tag_struct_ptr;
         }
         p->child_ptrs[i] = &c;
     }
@@ -1059,10 +1277,38 @@ int bam_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
         a.length = rows;
         a.buffers = p->bufs[i];
         a.release = bam_release_child;
-        const int vs = kColValid[col], k = kColVar[col];
+        const int vs = col < 10 ? kColValid[col] : -1, k = col < 10 ? kColVar[col] : -1;
         a.null_count = vs >= 0 ? -1 : 0;
         p->bufs[i][0] = vs >= 0 ? (const void *)(c->p<uint32_t>(c->valid[vs]) + vw) : nullptr;
-        if (col == 1) {
+        if (col == 10) {
+            const long long e0 = c->base[kBTagN][(size_t)b], n_ent_b = c->base[kBTagN][(size_t)b + 1] - e0;
+            a.n_buffers = 2;
+            p->bufs[i][1] = c->p<int32_t>(c->tags_loff) + lo;
+            auto init = [](ArrowArray &x, int64_t len, int nb, const void **bufs) {
+                memset(&x, 0, sizeof(x));
+                x.length = len;
+                x.n_buffers = nb;
+                x.buffers = bufs;
+                x.release = bam_release_child;
+            };
+            init(p->tag_struct, n_ent_b, 1, p->tag_struct_bufs);
+            init(p->tag_name, n_ent_b, 3, p->tag_name_bufs);
+            init(p->tag_value, n_ent_b, 3, p->tag_value_bufs);
+            p->tag_struct_bufs[0] = nullptr;
+            p->tag_name_bufs[0] = nullptr;
+            p->tag_name_bufs[1] = c->p<int32_t>(c->tag_off) + e0 + b;
+            p->tag_name_bufs[2] = c->p<uint8_t>(c->tag_val) + 2 * e0;
+            p->tag_value_bufs[0] = nullptr;
+            p->tag_value_bufs[1] = c->p<int32_t>(c->tval_off) + e0 + b;
+            p->tag_value_bufs[2] = c->p<uint8_t>(c->tval_val) + c->base[kBTagB][(size_t)b];
+            p->tag_kids[0] = &p->tag_name;
+            p->tag_kids[1] = &p->tag_value;
+            p->tag_struct.n_children = 2;
+            p->tag_struct.children = p->tag_kids;
+            p->tag_struct_ptr = &p->tag_struct;
+            a.n_children = 1;
+            a.children = &p->tag_struct_ptr;
+        } else if (col == 1) {
             a.n_buffers = 2;
             p->bufs[i][1] = c->p<int32_t>(c->flag) + row0;
         } else if (col == 3 || col == 4) {
@@ -1116,11 +1362,10 @@ int exon_gpu_bam_open(exon_gpu_ctx *c, exon_gpu_stream **out) {
 
 int exon_gpu_bam_open_columns(exon_gpu_ctx *c, const exon_gpu_bam_opts *o, exon_gpu_stream **out) {
     if (!c || !o || !out) return fail(EXON_GPU_ERR_ARG, "bam_open_columns: NULL argument");
-    if (o->batch_rows < 0 || o->n_projection < 0 || o->n_projection > 10 || (o->n_projection > 0 && !o->projection))
+    if (o->batch_rows < 0 || o->n_projection < 0 || o->n_projection > 11 || (o->n_projection > 0 && !o->projection))
         return fail(EXON_GPU_ERR_ARG, "bam_open_columns: bad batch_rows / projection");
     for (int i = 0; i < o->n_projection; ++i) {
         if (o->projection[i] < 0 || o->projection[i] > 10) return fail(EXON_GPU_ERR_ARG, "bam_open_columns: projection index %d is not a BAM file-schema column", o->projection[i]);
-        if (o->projection[i] == 10) return fail(EXON_GPU_ERR_UNSUPPORTED, "bam_open_columns: column 10 (tags) is not built on the GPU yet");
         for (int j = 0; j < i; ++j)
             if (o->projection[j] == o->projection[i]) return fail(EXON_GPU_ERR_ARG, "bam_open_columns: column %d is projected twice", o->projection[i]);
     }

@@ -9,7 +9,13 @@
 //   * strand "+" | "-" as text; "." and "?" are appended as NULL into a column the schema declares NON-nullable, so the
 //     reference's batch construction fails for such a file when strand is projected -- reported as EXON_GPU_ERR_PARSE here
 //   * "##" directives and "#" comments are not records; an empty line and a line with fewer than 9 fields are errors
-// `attributes` (column 8, Map<Utf8, List<Utf8>>) is not built: EXON_GPU_ERR_UNSUPPORTED.
+//   * attributes (column 8, Map<Utf8, List<Utf8>>): noodles-gff 0.41 lazy attributes -- `key=value` fields split at ';', a
+//     value that holds ',' is an array (split at ','), keys and values percent-decoded -- appended exactly as
+//     GFFArrayBuilder::append does (array_builder.rs:142-160), INCLUDING its off-by-one: for a plain string value the builder
+//     closes the value list BEFORE it appends the string (`values().append(true)` precedes `values().values().append_value`),
+//     so every string value lands in the list of the NEXT entry of the batch (the first list is empty, the last string
+//     dangles behind the last offset); array values are appended before their list is closed and so stay -- together with a
+//     string left pending by the entry before them.  What a DataFusion query sees through the reference is what is built here.
 //
 // Row-parallel on the partition's line index (build_line_index, fastq_scan.cu):
 //   1. measure  one thread per line: record or not, the eight tab offsets (aligned 8-byte SWAR), byte lengths of the five
@@ -40,15 +46,17 @@ namespace exon {
 namespace {
 
 constexpr uint32_t kGErrFields = 1u, kGErrEmptyLine = 2u, kGErrPos = 4u, kGErrScore = 8u, kGErrStrand = 16u, kGErrPhase = 32u,
-                   kGErrStrandNull = 64u, kGErrSeqname = 128u;
+                   kGErrStrandNull = 64u, kGErrSeqname = 128u, kGErrAttr = 256u;
 
-enum { kGRow = 0, kGSeq = 1, kGSrc = 2, kGType = 3, kGStrand = 4, kGPhase = 5, kGN = 6 };
+// scan slots: rows, the five string columns' bytes, and for attributes: entries, key bytes, value strings, value bytes
+enum { kGRow = 0, kGSeq = 1, kGSrc = 2, kGType = 3, kGStrand = 4, kGPhase = 5, kGAttrN = 6, kGKeyB = 7, kGStrN = 8, kGStrB = 9, kGN = 10 };
+constexpr int kGStrCols = 6;  // slots [kGSeq, kGStrCols) are plain string columns
 
 struct GffColArgs {
     int64_t n_lines;
     const uint8_t *const *line_start;
     const uint8_t *const *line_end;
-    int32_t want[8];
+    int32_t want[9];
     int32_t *cnt[kGN];
     const long long *pre[kGN];
     uint8_t *lflags;  // bit0 record, bit1 score valid, bit2 phase valid, bit3 score pending (exact parser)
@@ -63,9 +71,81 @@ struct GffColArgs {
     int32_t *off[kGN];  // [kGSeq..kGPhase]: n_rows + n_batches entries, batch b's offsets start at brow[b] + b
     uint8_t *val[kGN];
     uint32_t *score_valid, *phase_valid;
+    // attributes: map offsets (index row + batch), key offsets / list offsets (index entry + batch), string offsets (index string + batch)
+    int32_t *map_off, *key_off, *list_off, *str_off;
+    uint8_t *key_val, *str_val;
     uint32_t *flags;
     unsigned long long *misc;  // [1] first bad line, [2] scores left to the exact parser
 };
+
+__device__ __forceinline__ int gff_hex(uint32_t c) {
+    if (c - '0' <= 9u) return (int)(c - '0');
+    c |= 0x20u;
+    return c - 'a' <= 5u ? (int)(c - 'a' + 10) : -1;
+}
+// percent-decoded copy of [p, p + n) (noodles percent_decode); returns the decoded length, writes when dst is set
+__device__ __forceinline__ int32_t gff_pct(const uint8_t *p, int32_t n, uint8_t *dst) {
+    int32_t o = 0;
+    for (int32_t q = 0; q < n; ++q) {
+        uint32_t c = __ldg(p + q);
+        if (c == '%' && q + 2 < n) {
+            const int h = gff_hex(__ldg(p + q + 1)), l = gff_hex(__ldg(p + q + 2));
+            if (h >= 0 && l >= 0) {
+                c = (uint32_t)(h * 16 + l);
+                q += 2;
+            }
+        }
+        if (dst) dst[o] = (uint8_t)c;
+        ++o;
+    }
+    return o;
+}
+
+// where the emit pass writes one record's attributes (NULL: measure pass)
+struct GffAttrOut {
+    int32_t *key_off, *list_off, *str_off;  // entries of the record's first key / first string
+    uint8_t *key_val, *str_val;             // the batch's byte bases
+    int32_t key0, str0;                     // byte offsets (batch-relative) of the record's first key / string
+    int32_t strn0;                          // strings of the batch before this record
+};
+// Walks the attributes field [f, f + n): c[] = entries, key bytes, strings, string bytes.  false: a field without '='.
+__device__ bool gff_attr_walk(const uint8_t *f, int32_t n, int32_t c[4], const GffAttrOut *o) {
+    int32_t ne = 0, kb = 0, ns = 0, sb = 0;
+    if (!(n == 1 && __ldg(f) == '.')) {
+        int32_t i = 0;
+        while (i < n) {
+            int32_t e = i, eq = -1;
+            while (e < n && __ldg(f + e) != ';') {
+                if (eq < 0 && __ldg(f + e) == '=') eq = e;
+                ++e;
+            }
+            if (eq < 0) return false;
+            const int32_t klen = gff_pct(f + i, eq - i, o ? o->key_val + o->key0 + kb : nullptr);
+            if (o) o->key_off[ne] = o->key0 + kb;
+            kb += klen;
+            bool is_array = false;
+            for (int32_t q = eq + 1; q < e && !is_array; ++q) is_array = __ldg(f + q) == ',';
+            // the builder closes a STRING value's list before it appends the string (see the file header)
+            if (o && !is_array) o->list_off[ne + 1] = o->strn0 + ns;
+            int32_t v = eq + 1;
+            while (true) {
+                int32_t ve = v;
+                while (ve < e && __ldg(f + ve) != ',') ++ve;
+                const int32_t m = gff_pct(f + v, ve - v, o ? o->str_val + o->str0 + sb : nullptr);
+                if (o) o->str_off[ns] = o->str0 + sb;
+                sb += m;
+                ++ns;
+                if (ve >= e) break;
+                v = ve + 1;
+            }
+            if (o && is_array) o->list_off[ne + 1] = o->strn0 + ns;
+            ++ne;
+            i = e + 1;
+        }
+    }
+    c[0] = ne, c[1] = kb, c[2] = ns, c[3] = sb;
+    return true;
+}
 
 // offsets (from ls) of the first N tabs of [ls, le); false when there are fewer
 template <int N>
@@ -112,7 +192,7 @@ __global__ void __launch_bounds__(256) gff_measure_kernel(const __grid_constant_
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= a.n_lines) return;
     const uint8_t *ls = a.line_start[i], *le = a.line_end[i];
-    int32_t c[kGN] = {0, 0, 0, 0, 0, 0};
+    int32_t c[kGN] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint8_t f = 0;
     uint32_t err = 0;
     long long start = 0, end = 0;
@@ -167,6 +247,7 @@ __global__ void __launch_bounds__(256) gff_measure_kernel(const __grid_constant_
                     err |= kGErrPhase;
                 }
             }
+            if (a.want[8] && !gff_attr_walk(ls + t[7] + 1, (int32_t)(le - ls) - t[7] - 1, c + kGAttrN, nullptr)) err |= kGErrAttr;
         }
     }
 #pragma unroll
@@ -230,9 +311,31 @@ __global__ void __launch_bounds__(256) gff_emit_kernel(const __grid_constant__ G
     int32_t t[8];
     if (!find_tabs_n<8>(ls, le, t)) return;
     const long long lend = a.bline[b + 1];  // first line of the next file: prefix there = end of this batch
-    const int fs[kGN] = {0, 0, t[0] + 1, t[1] + 1, t[5] + 1, t[6] + 1};
+    const int fs[kGStrCols] = {0, 0, t[0] + 1, t[1] + 1, t[5] + 1, t[6] + 1};
+    if (a.map_off) {
+        const long long *PE = a.pre[kGAttrN], *PK = a.pre[kGKeyB], *PS = a.pre[kGStrN], *PB = a.pre[kGStrB];
+        int32_t *mo = a.map_off + r0 + b;
+        mo[in_batch] = (int32_t)(PE[i] - PE[l0]);
+        GffAttrOut o;
+        o.key_off = a.key_off + PE[i] + b;
+        o.list_off = a.list_off + PE[i] + b;
+        o.str_off = a.str_off + PS[i] + b;
+        o.key_val = a.key_val + PK[l0];
+        o.str_val = a.str_val + PB[l0];
+        o.key0 = (int32_t)(PK[i] - PK[l0]);
+        o.str0 = (int32_t)(PB[i] - PB[l0]);
+        o.strn0 = (int32_t)(PS[i] - PS[l0]);
+        if (in_batch == 0) a.list_off[PE[l0] + b] = 0;  // offsets[0] of the batch's value lists
+        if (last) {
+            mo[in_batch + 1] = (int32_t)(PE[lend] - PE[l0]);
+            a.key_off[PE[lend] + b] = (int32_t)(PK[lend] - PK[l0]);
+            a.str_off[PS[lend] + b] = (int32_t)(PB[lend] - PB[l0]);
+        }
+        int32_t cc[4];
+        gff_attr_walk(ls + t[7] + 1, (int32_t)(le - ls) - t[7] - 1, cc, &o);
+    }
 #pragma unroll
-    for (int k = kGSeq; k < kGN; ++k) {
+    for (int k = kGSeq; k < kGStrCols; ++k) {
         if (!a.off[k]) continue;
         const long long *P = a.pre[k];
         int32_t *o = a.off[k] + r0 + b;
@@ -264,7 +367,7 @@ struct GffColumns {
     bool on_device = false;
     int64_t n_rows = 0, n_batches = 0, next = 0;
     std::vector<int> projection;
-    GffBuf off[kGN], val[kGN], start, end, score, score_valid, phase_valid;
+    GffBuf off[kGN], val[kGN], start, end, score, score_valid, phase_valid, map_off, key_off, list_off, str_off, key_val, str_val;
     std::vector<long long> batch_row0, bit0, base[kGN];
     template <class T>
     const T *p(const GffBuf &b) const { return static_cast<const T *>(on_device ? b.d : b.h); }
@@ -272,6 +375,7 @@ struct GffColumns {
     void each(F fn) {
         for (int k = 0; k < kGN; ++k) fn(off[k]), fn(val[k]);
         fn(start), fn(end), fn(score), fn(score_valid), fn(phase_valid);
+        fn(map_off), fn(key_off), fn(list_off), fn(str_off), fn(key_val), fn(str_val);
     }
     void unref() {
         if (refs.fetch_sub(1) == 1) {
@@ -305,7 +409,7 @@ int gff_build_columns(VcfStream *s) {
     c->device = ctx->device;
     c->on_device = s->columns_on_device;
     c->projection = s->projection;
-    bool want[8] = {false, false, false, false, false, false, false, false};
+    bool want[9] = {false, false, false, false, false, false, false, false, false};
     for (int p : s->projection) want[p] = true;
     c->batch_row0.assign(1, 0);
 
@@ -329,8 +433,8 @@ int gff_build_columns(VcfStream *s) {
     a.n_lines = n_lines;
     a.line_start = li.line_start;
     a.line_end = li.line_end;
-    for (int k = 0; k < 8; ++k) a.want[k] = want[k];
-    bool need[kGN] = {true, want[0], want[1], want[2], want[6], want[7]};
+    for (int k = 0; k < 9; ++k) a.want[k] = want[k];
+    bool need[kGN] = {true, want[0], want[1], want[2], want[6], want[7], want[8], want[8], want[8], want[8]};
     long long *pre[kGN];
     for (int k = 0; k < kGN; ++k) {
         pre[k] = nullptr;
@@ -395,10 +499,11 @@ int gff_build_columns(VcfStream *s) {
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     if (const uint32_t e = (uint32_t)h_misc[0])
-        return fail(EXON_GPU_ERR_PARSE, "malformed GFF at line %llu:%s%s%s%s%s%s%s%s", h_misc[1], (e & kGErrFields) ? " fewer than 9 tab-separated fields;" : "",
+        return fail(EXON_GPU_ERR_PARSE, "malformed GFF at line %llu:%s%s%s%s%s%s%s%s%s", h_misc[1], (e & kGErrFields) ? " fewer than 9 tab-separated fields;" : "",
                     (e & kGErrEmptyLine) ? " empty line;" : "", (e & kGErrPos) ? " start / end is not a positive decimal integer;" : "",
                     (e & kGErrScore) ? " score is not a float literal;" : "", (e & kGErrStrand) ? " invalid strand;" : "", (e & kGErrPhase) ? " invalid phase;" : "",
-                    (e & kGErrStrandNull) ? " strand '.' / '?' is NULL in the reference's non-nullable strand column;" : "", (e & kGErrSeqname) ? " empty seqname;" : "");
+                    (e & kGErrStrandNull) ? " strand '.' / '?' is NULL in the reference's non-nullable strand column;" : "", (e & kGErrSeqname) ? " empty seqname;" : "",
+                    (e & kGErrAttr) ? " an attribute without '=';" : "");
     // one batch per non-empty file (read_batch has no row limit)
     std::vector<long long> brow, bline;
     for (int f = 0; f < n_files; ++f)
@@ -444,12 +549,23 @@ int gff_build_columns(VcfStream *s) {
         if (zero) CUDA_TRY(cudaMemsetAsync(b.d, 0, b.bytes, st));
         return EXON_GPU_OK;
     };
-    for (int k = kGSeq; k < kGN; ++k) {
+    for (int k = kGSeq; k < kGStrCols; ++k) {
         if (!need[k]) continue;
         if (int rc = dev_alloc(c->off[k], ((size_t)n_rows + nb1) * 4, false)) return rc;
         if (int rc = dev_alloc(c->val[k], (size_t)c->base[k][nb1 - 1], false)) return rc;
         a.off[k] = (int32_t *)c->off[k].d;
         a.val[k] = (uint8_t *)c->val[k].d;
+    }
+    if (want[8]) {
+        const size_t n_ent = (size_t)c->base[kGAttrN][nb1 - 1], n_str = (size_t)c->base[kGStrN][nb1 - 1];
+        if (int rc = dev_alloc(c->map_off, ((size_t)n_rows + nb1) * 4, false)) return rc;
+        if (int rc = dev_alloc(c->key_off, (n_ent + nb1) * 4, false)) return rc;
+        if (int rc = dev_alloc(c->list_off, (n_ent + nb1) * 4, true)) return rc;
+        if (int rc = dev_alloc(c->str_off, (n_str + nb1) * 4, false)) return rc;
+        if (int rc = dev_alloc(c->key_val, (size_t)c->base[kGKeyB][nb1 - 1], false)) return rc;
+        if (int rc = dev_alloc(c->str_val, (size_t)c->base[kGStrB][nb1 - 1], false)) return rc;
+        a.map_off = (int32_t *)c->map_off.d, a.key_off = (int32_t *)c->key_off.d, a.list_off = (int32_t *)c->list_off.d, a.str_off = (int32_t *)c->str_off.d;
+        a.key_val = (uint8_t *)c->key_val.d, a.str_val = (uint8_t *)c->str_val.d;
     }
     long long *o_start = nullptr, *o_end = nullptr;
     float *o_score = nullptr;
@@ -490,10 +606,14 @@ int gff_build_columns(VcfStream *s) {
 struct GffBatchPriv {
     GffColumns *cols;
     int n_children;
-    ArrowArray children[8];
-    ArrowArray *child_ptrs[8];
-    const void *bufs[8][3];
+    ArrowArray children[9];
+    ArrowArray *child_ptrs[9];
+    const void *bufs[9][3];
     const void *struct_buffers[1];
+    // attributes: map -> entries struct -> {keys utf8, values list -> item utf8}
+    ArrowArray entries, keys, values, items;
+    ArrowArray *entries_ptr, *kv_ptrs[2], *items_ptr;
+    const void *entries_bufs[1], *keys_bufs[3], *values_bufs[2], *items_bufs[3];
 };
 void gff_release_child(ArrowArray *a) { a->release = nullptr; }
 void gff_release_batch(ArrowArray *a) {
@@ -504,8 +624,10 @@ void gff_release_batch(ArrowArray *a) {
 }
 struct GffSchemaPriv {
     int n_children;
-    ArrowSchema children[8];
-    ArrowSchema *child_ptrs[8];
+    ArrowSchema children[9];
+    ArrowSchema *child_ptrs[9];
+    ArrowSchema entries, keys, values, items;
+    ArrowSchema *entries_ptr, *kv_ptrs[2], *items_ptr;
 };
 void gff_release_schema_child(ArrowSchema *s) { s->release = nullptr; }
 void gff_release_schema(ArrowSchema *s) {
@@ -514,9 +636,9 @@ void gff_release_schema(ArrowSchema *s) {
 }
 // new_gff_schema_builder, exon/exon-gff/src/config.rs:81-108
 void gff_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
-    static const char *names[8] = {"seqname", "source", "type", "start", "end", "score", "strand", "phase"};
-    static const char *formats[8] = {"u", "u", "u", "l", "l", "f", "u", "u"};
-    static const bool nullable[8] = {false, true, false, false, false, true, false, true};
+    static const char *names[9] = {"seqname", "source", "type", "start", "end", "score", "strand", "phase", "attributes"};
+    static const char *formats[9] = {"u", "u", "u", "l", "l", "f", "u", "u", "+m"};
+    static const bool nullable[9] = {false, true, false, false, false, true, false, true, true};
     auto *p = new GffSchemaPriv();
     p->n_children = (int)projection.size();
     for (int i = 0; i < p->n_children; ++i) {
@@ -527,6 +649,30 @@ void gff_fill_schema(const std::vector<int> &projection, ArrowSchema *out) {
         c.name = names[col];
         c.flags = nullable[col] ? ARROW_FLAG_NULLABLE : 0;
         c.release = gff_release_schema_child;
+        if (col == 8) {
+            // Field::new_map("attributes", "entries", keys: Utf8 !null, values: List<item: Utf8>, sorted = false, nullable = true)
+            auto init = [](ArrowSchema &x, const char *fmt, const char *name, bool nullable_) {
+                memset(&x, 0, sizeof(x));
+                x.format = fmt;
+                x.name = name;
+                x.flags = nullable_ ? ARROW_FLAG_NULLABLE : 0;
+                x.release = gff_release_schema_child;
+            };
+            init(p->entries, "+s", "entries", false);
+            init(p->keys, "u", "keys", false);
+            init(p->values, "+l", "values", true);
+            init(p->items, "u", "item", true);
+            p->items_ptr = &p->items;
+            p->values.n_children = 1;
+            p->values.children = &p->items_ptr;
+            p->kv_ptrs[0] = &p->keys;
+            p->kv_ptrs[1] = &p->values;
+            p->entries.n_children = 2;
+            p->entries.children = p->kv_ptrs;
+            p->entries_ptr = &p->entries;
+            c.n_children = 1;
+            c.children = &p->entries_ptr;
+        }
         p->child_ptrs[i] = &c;
     }
     memset(out, 0, sizeof(*out));
@@ -570,7 +716,42 @@ int gff_next_batch(VcfStream *s, ArrowArray *out, ArrowSchema *out_schema) {
         a.buffers = p->bufs[i];
         a.release = gff_release_child;
         p->bufs[i][0] = nullptr;
-        if (col == 3 || col == 4) {
+        if (col == 8) {
+            const long long e0 = c->base[kGAttrN][(size_t)b], n_ent = c->base[kGAttrN][(size_t)b + 1] - e0;
+            const long long s0 = c->base[kGStrN][(size_t)b], n_str = c->base[kGStrN][(size_t)b + 1] - s0;
+            a.n_buffers = 2;
+            p->bufs[i][1] = c->p<int32_t>(c->map_off) + row0 + b;
+            auto init = [](ArrowArray &x, int64_t len, int nb, const void **bufs) {
+                memset(&x, 0, sizeof(x));
+                x.length = len;
+                x.n_buffers = nb;
+                x.buffers = bufs;
+                x.release = gff_release_child;
+            };
+            init(p->entries, n_ent, 1, p->entries_bufs);
+            init(p->keys, n_ent, 3, p->keys_bufs);
+            init(p->values, n_ent, 2, p->values_bufs);
+            init(p->items, n_str, 3, p->items_bufs);  // every string of the batch, the dangling last one included
+            p->entries_bufs[0] = nullptr;
+            p->keys_bufs[0] = nullptr;
+            p->keys_bufs[1] = c->p<int32_t>(c->key_off) + e0 + b;
+            p->keys_bufs[2] = c->p<uint8_t>(c->key_val) + c->base[kGKeyB][(size_t)b];
+            p->values_bufs[0] = nullptr;
+            p->values_bufs[1] = c->p<int32_t>(c->list_off) + e0 + b;
+            p->items_bufs[0] = nullptr;
+            p->items_bufs[1] = c->p<int32_t>(c->str_off) + s0 + b;
+            p->items_bufs[2] = c->p<uint8_t>(c->str_val) + c->base[kGStrB][(size_t)b];
+            p->items_ptr = &p->items;
+            p->values.n_children = 1;
+            p->values.children = &p->items_ptr;
+            p->kv_ptrs[0] = &p->keys;
+            p->kv_ptrs[1] = &p->values;
+            p->entries.n_children = 2;
+            p->entries.children = p->kv_ptrs;
+            p->entries_ptr = &p->entries;
+            a.n_children = 1;
+            a.children = &p->entries_ptr;
+        } else if (col == 3 || col == 4) {
             a.n_buffers = 2;
             p->bufs[i][1] = c->p<long long>(col == 3 ? c->start : c->end) + row0;
         } else if (col == 5) {
@@ -612,7 +793,6 @@ int exon_gpu_gff_open_columns(exon_gpu_ctx *c, const exon_gpu_fastq_opts *o, exo
     if (o->n_projection < 0 || o->n_projection > 9 || (o->n_projection > 0 && !o->projection)) return fail(EXON_GPU_ERR_ARG, "gff_open_columns: bad projection");
     for (int i = 0; i < o->n_projection; ++i) {
         if (o->projection[i] < 0 || o->projection[i] > 8) return fail(EXON_GPU_ERR_ARG, "gff_open_columns: projection index %d is not a GFF file-schema column", o->projection[i]);
-        if (o->projection[i] == 8) return fail(EXON_GPU_ERR_UNSUPPORTED, "gff_open_columns: column 8 (attributes) is not built on the GPU yet");
         for (int j = 0; j < i; ++j)
             if (o->projection[j] == o->projection[i]) return fail(EXON_GPU_ERR_ARG, "gff_open_columns: column %d is projected twice", o->projection[i]);
     }

@@ -154,7 +154,7 @@ int exon_gpu_regroup_files_by_size(const int64_t *sizes, int32_t n_files, int32_
 typedef struct {
     int32_t batch_rows;        /* session batch size; reference default 8192 (exon/exon-common/src/lib.rs:27) */
     int32_t n_projection;      /* file-schema column indices to materialise, in output order ... */
-    const int32_t *projection; /* ... VCFConfig.projection (exon/exon-vcf/src/config.rs:23-64); cols 0..7 (chrom pos id ref alt qual filter info) */
+    const int32_t *projection; /* ... VCFConfig.projection (exon/exon-vcf/src/config.rs:23-64); cols 0..8 (chrom pos id ref alt qual filter info formats) */
     int32_t columns_on_device; /* 0: next_batch buffers are pinned host memory; 1: device memory */
     /* Optional predicate declared up front so that every feed() can be scanned while the next one is still
      * copying (fused a5-a9).  NULL = none declared; filter_count() then scans what is resident. */
@@ -320,8 +320,12 @@ int exon_gpu_gff_filter_count(exon_gpu_stream *s, const exon_gpu_region *region,
  *   f32::from_str) | 6 strand utf8 ("+" / "-") | 7 phase utf8 ("." -> NULL, else "0" / "1" / "2")
  * Like the reference, ONE batch per file whatever batch_rows says (read_batch has no row limit).  A strand of "." or "?" is
  * NULL in a column the reference declares non-nullable -- its batch construction fails, and so does this call
- * (EXON_GPU_ERR_PARSE) -- as do an empty line, fewer than 9 fields, a start / end of 0.  Column 8 (attributes) is not built
- * (EXON_GPU_ERR_UNSUPPORTED).  exon_gpu_fastq_opts carries the projection. */
+ * (EXON_GPU_ERR_PARSE) -- as do an empty line, fewer than 9 fields, a start / end of 0.
+ *   8 attributes map<utf8, list<utf8>> ("+m"; entries struct{keys, values: list<item>}): `key=v1,v2;...`, keys and values
+ *   percent-decoded, one map entry per attribute in line order.  The reference's builder (array_builder.rs:150-176) closes a
+ *   single-valued attribute's list BEFORE appending its string, so that string lands in the NEXT entry's list (the last
+ *   one is left for the next row's first entry, the file's last one is dropped); batches come out exactly like that.
+ * exon_gpu_fastq_opts carries the projection. */
 int exon_gpu_gff_open_columns(exon_gpu_ctx *ctx, const exon_gpu_fastq_opts *opts, exon_gpu_stream **out);
 int exon_gpu_gff_next_batch(exon_gpu_stream *s, struct ArrowArray *out, struct ArrowSchema *out_schema);
 
@@ -365,8 +369,13 @@ int exon_gpu_bam_group_name(exon_gpu_stream *s, int32_t group, const char **name
  *   4 end int64 (start + reference-consuming CIGAR length - 1; NULL without a start or when that is 0) |
  *   5 mapping_quality utf8 (decimal string, NULL for 255) | 6 cigar utf8 ("55M13394N21M") | 7 mate_reference utf8 |
  *   8 sequence utf8 (bases decoded from 4 bits) | 9 quality_score list<item: int64> (raw bytes as i8, [] when missing)
- * Column 10 (tags) is not built: EXON_GPU_ERR_UNSUPPORTED.  A record whose read name is missing ("*") fails the call, as
- * the reference's batch construction does (NULL in a non-nullable column).  Batches never span files. */
+ *   10 tags list<item: struct{tag utf8 !null, value utf8}> (TagsMapBuilder, exon/exon-sam/src/tag_builder.rs:480-741, the
+ *   default bam_parse_tags = false form): every auxiliary field in record order, its value as text -- integers in
+ *   decimal, A as the character, Z / H as written, f through Rust's f32 Display, B integer arrays joined by ",", B:f
+ *   arrays as "{:.2}" joined by ", " (an element of 9e13 or more in magnitude: EXON_GPU_ERR_UNSUPPORTED).
+ * A record whose read name is missing ("*") fails the call, as the reference's batch construction does (NULL in a
+ * non-nullable column); so does an auxiliary field of unknown type or one that overruns its record.  Batches never span
+ * files. */
 typedef struct {
     int32_t batch_rows;        /* session batch size; reference default 8192 */
     int32_t n_projection;

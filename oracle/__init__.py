@@ -630,6 +630,70 @@ class Bam:
                 "l_seq": r.l_seq, "first_quals": list(r.first_quals)}
 
 
+def _rust_f32_fixed2(x) -> str:
+    """Rust `format!("{:.2}", x)` for an f32: the exact value, round-half-even at two decimals (core::fmt float_to_decimal_exact)."""
+    x = float(np.float32(x))
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "inf" if x > 0 else "-inf"
+    return format(x, ".2f")  # CPython formats the exact binary value, ties to even, and keeps the sign of -0.0
+
+
+def bam_tags(data):
+    """Per record, the `tags` column (column 10) of the reference's BAM / SAM batches in its default List<Struct{tag, value}> form:
+    [(tag, value text), ...] in record order.  Follows TagsMapBuilder::append (/root/reference/exon/exon-sam/src/tag_builder.rs:497-741):
+    integers through i64 Display, A as its character, Z / H as text, f through f32 Display, B integer arrays joined by ",",
+    B:f arrays as "{:.2}" joined by ", ".  Pinned by sam-select-tests.slt:47-53 (same builder, same data model)."""
+    import struct
+
+    raw = bytes(gunzip_all(data))
+    if raw[:4] != b"BAM\x01":
+        raise ValueError("not a BAM file")
+    p = 8 + struct.unpack_from("<i", raw, 4)[0]
+    n_ref = struct.unpack_from("<i", raw, p)[0]
+    p += 4
+    for _ in range(n_ref):
+        p += 4 + struct.unpack_from("<i", raw, p)[0] + 4
+    ints = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I"}
+    out = []
+    while p + 4 <= len(raw):
+        bs = struct.unpack_from("<i", raw, p)[0]
+        rec = raw[p + 4: p + 4 + bs]
+        p += 4 + bs
+        l_name, n_cig, l_seq = rec[8], struct.unpack_from("<H", rec, 12)[0], struct.unpack_from("<i", rec, 16)[0]
+        q = 32 + l_name + 4 * n_cig + (l_seq + 1) // 2 + l_seq
+        row = []
+        while q < len(rec):
+            tag, ty = rec[q: q + 2].decode("latin-1"), chr(rec[q + 2])
+            q += 3
+            if ty == "A":
+                val, q = chr(rec[q]), q + 1
+            elif ty in ints:
+                val = str(struct.unpack_from(ints[ty], rec, q)[0])
+                q += struct.calcsize(ints[ty])
+            elif ty == "f":
+                val = rust_f32_display(struct.unpack_from("<f", rec, q)[0]).decode()
+                q += 4
+            elif ty in "ZH":
+                e = rec.index(b"\x00", q)
+                val, q = rec[q:e].decode("latin-1"), e + 1
+            elif ty == "B":
+                st, cnt = chr(rec[q]), struct.unpack_from("<I", rec, q + 1)[0]
+                q += 5
+                if st == "f":
+                    val = ", ".join(_rust_f32_fixed2(v) for v in struct.unpack_from("<%df" % cnt, rec, q))
+                    q += 4 * cnt
+                else:
+                    val = ",".join(str(v) for v in struct.unpack_from("<%d%s" % (cnt, ints[st][1]), rec, q))
+                    q += cnt * struct.calcsize(ints[st])
+            else:
+                raise ValueError("unknown auxiliary field type %r" % ty)
+            row.append((tag, val))
+        out.append(row)
+    return out
+
+
 def bam_count_by_reference_files(files, **kw):
     """Sum of per-file group counts keyed by reference NAME (the GROUP BY merges equal names across files)."""
     total, rows = {}, 0
@@ -676,6 +740,46 @@ def mzml_decode_binary(b64: bytes, zlib_compressed: bool, f32: bool):
     vals = [out[i] for i in range(n)]
     C.CDLL(None).free(out)
     return vals
+
+
+def gff_attributes(data, reference_quirk: bool = True):
+    """Column 8 (attributes, Map<Utf8, List<Utf8>>) of every record of ONE GFF file (= one batch) as GFFArrayBuilder::append
+    builds it (/root/reference/exon/exon-gff/src/array_builder.rs:142-160) from noodles-gff 0.41 lazy attributes: fields split
+    at ';', `key=value`, a value with ',' is an array, keys and values percent-decoded.  Returns, per record, [(key, [values])].
+    reference_quirk: for a plain string value the builder calls `values().append(true)` BEFORE it appends the string, so the
+    string lands in the NEXT entry's list (simulated here with the builder's own pending-values state); False gives the
+    lists one would expect, for comparison."""
+    text = bytes(_buf(data))
+    rows, pending = [], []
+    for line in text.split(b"\n"):
+        if not line or line.startswith(b"#"):
+            continue
+        f = line.split(b"\t")
+        if len(f) < 9:
+            raise ValueError("fewer than 9 fields")
+        row = []
+        field = f[8]
+        if field != b".":
+            parts = field.split(b";")
+            if parts and parts[-1] == b"":
+                parts.pop()
+            for part in parts:
+                if b"=" not in part:
+                    raise ValueError("attribute without '='")
+                k, v = part.split(b"=", 1)
+                key = _percent_decode(k).decode()
+                vals = [_percent_decode(x).decode() for x in v.split(b",")]
+                if not reference_quirk:
+                    row.append((key, vals))
+                elif b"," in v:           # Array: values appended, then the list is closed
+                    pending += vals
+                    row.append((key, pending))
+                    pending = []
+                else:                      # String: the list is closed first, then the value is appended
+                    row.append((key, pending))
+                    pending = list(vals)
+        rows.append(row)
+    return rows
 
 
 def mzml_rows(data):

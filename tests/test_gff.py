@@ -147,5 +147,53 @@ def test_gpu_record_batches(gpu_ctx):
         assert e.value.code == _abi.ERR_PARSE, bad
     assert gpu_rows(gpu_ctx, [ok_line.replace("\t+\t", "\t.\t").encode()], (0, 3))[0] == [(b"sq0", 8)]   # strand not projected: not read
     with pytest.raises(ExonGpuError) as e:
-        gpu_ctx.open_gff(projection=(8,))
-    assert e.value.code == _abi.ERR_UNSUPPORTED
+        gpu_ctx.open_gff(projection=(9,))
+    assert e.value.code == _abi.ERR_ARG
+
+
+def gpu_attributes(ctx, files, projection=(8,)):
+    out = []
+    with ctx.open_gff(projection=projection) as s:
+        for f in files:
+            s.feed(f)
+        while True:
+            b = s.next_batch()
+            if b is None:
+                break
+            rb = b.to_pyarrow()
+            out.append([[(k, v) for k, v in row] for row in rb.column("attributes").to_pylist()])
+    return out
+
+
+@pytest.mark.gpu
+def test_gpu_attributes_map(gpu_ctx):
+    """Column 8: Map<Utf8, List<Utf8>> built like GFFArrayBuilder::append (array_builder.rs:142-160) -- with the builder's
+    off-by-one for plain string values (the list is closed before the value is appended), which oracle.gff_attributes
+    simulates with the builder's own state.  The fixture's rows are all `gene_id=caat1;gene_name=gene0`."""
+    from exon_b200 import _abi
+    from exon_b200._abi import ExonGpuError
+
+    t = fixture()
+    want = oracle.gff_attributes(t)
+    assert want[0] == [("gene_id", []), ("gene_name", ["caat1"])] and want[1] == [("gene_id", ["gene0"]), ("gene_name", ["caat1"])]
+    assert oracle.gff_attributes(t, reference_quirk=False)[0] == [("gene_id", ["caat1"]), ("gene_name", ["gene0"])]
+    got = gpu_attributes(gpu_ctx, [t])
+    assert len(got) == 1 and got[0] == want
+    lines = ["ID=a;Parent=p1,p2;Note=x%3By%2Cz", ".", "ID=b;Dbxref=GO:1,GO:2,GO:3;empty=", "k%3D1=v;Alias=one,two;Name=last;", "ID=c"]
+    f1 = "##gff-version 3\n" + "".join(f"sq{i}\tsrc\tgene\t{i + 1}\t{i + 9}\t.\t+\t.\t{x}\n" for i, x in enumerate(lines))
+    f2 = "sq9\tsrc\tgene\t1\t2\t.\t-\t.\tID=second;Tags=a,b\n"
+    files = [f1.encode(), f2.encode()]
+    want = [oracle.gff_attributes(f) for f in files]          # one batch per file; the builder (and its quirk) restarts per batch
+    assert want[0][0] == [("ID", []), ("Parent", ["a", "p1", "p2"]), ("Note", [])] and want[0][1] == []
+    assert want[0][2][0] == ("ID", ["x;y,z"]) and want[0][3][0] == ("k=1", [""])
+    got = gpu_attributes(gpu_ctx, files)
+    assert got == want
+    rb_rows = []
+    with gpu_ctx.open_gff(projection=(0, 8, 3)) as s:          # next to other columns
+        s.feed(files[0])
+        rb = s.next_batch().to_pyarrow()
+        rb_rows = rb.to_pylist()
+    assert [r["seqname"] for r in rb_rows] == [f"sq{i}" for i in range(5)] and [[tuple(kv) for kv in r["attributes"]] for r in rb_rows] == want[0]
+    with pytest.raises(ExonGpuError) as e:
+        gpu_attributes(gpu_ctx, [b"sq0\tsrc\tgene\t1\t2\t.\t+\t.\tID=a;novalue\n"])
+    assert e.value.code == _abi.ERR_PARSE
