@@ -135,7 +135,7 @@ int exon_gpu_ctx_destroy(exon_gpu_ctx *c) {
     for (auto &b : c->free_blocks) cudaFree(b.ptr);
     if (c->scratch) cudaFree(c->scratch);
     if (c->scratch_b) cudaFree(c->scratch_b);
-    if (c->inf_bitmap) cudaFree(c->inf_bitmap);
+    if (c->inf_tokens) cudaFree(c->inf_tokens);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     nccl_teardown(c);
     for (int i = 0; i < Ctx::kEvRing; ++i) {

@@ -58,7 +58,7 @@ static int bgzf_parse_member(const uint8_t *data, size_t len, size_t p, BgzfMemb
     m->in_len = (uint32_t)(end - 8 - q);
     m->isize = (uint32_t)data[end - 4] | ((uint32_t)data[end - 3] << 8) | ((uint32_t)data[end - 2] << 16) | ((uint32_t)data[end - 1] << 24);
     m->out_addr = 0;
-    m->bm_off = 0;
+    m->tok_off = 0;
     m->pad_ = 0;
     if (bsize >= 0 && m->isize > 65536u) return fail(EXON_GPU_ERR_PARSE, "bgzf: member at byte %zu claims %u bytes (> 64 KiB)", p, m->isize);
     *next = end;
@@ -270,7 +270,7 @@ int VcfStream::launch_gz() {
         g.tab_bytes = (g.members.size() * sizeof(BgzfMember) + 255) & ~(size_t)255;
         CUDA_TRY(cudaMallocAsync(&g.d_tab, g.tab_bytes + 256, st));
         uint8_t *dt = (uint8_t *)g.d_tab;
-        const size_t bm_words = bgzf_assign_bitmap(g.members.data(), g.members.size());
+        const size_t tok_units = bgzf_assign_tokens(g.members.data(), g.members.size());
         size_t comp_bytes = 0;
         for (const BgzfMember &m : g.members) comp_bytes += m.in_len;
         CUDA_TRY(cudaMemcpyAsync(dt, g.members.data(), g.members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
@@ -278,9 +278,9 @@ int VcfStream::launch_gz() {
         CUDA_TRY(cudaMemcpyAsync(dt + g.tab_bytes, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaEventRecord(gz_copied_ev, gz_copy_stream));
         CUDA_TRY(cudaStreamWaitEvent(st, gz_copied_ev, 0));
-        std::lock_guard<std::recursive_mutex> work(ctx->work_mu);  // the match bitmap is a context-wide area
+        std::lock_guard<std::recursive_mutex> work(ctx->work_mu);  // the token scratch is a context-wide area
         if (int rc = bgzf_inflate_launch(ctx, (const uint8_t *)d_gz_buf[buf], (const BgzfMember *)dt, (int)g.members.size(), (uint32_t *)(dt + g.tab_bytes),
-                                         bm_words, comp_bytes)) {
+                                         tok_units, comp_bytes)) {
             cudaFreeAsync(g.d_tab, st);
             return rc;
         }
@@ -423,13 +423,13 @@ extern "C" int exon_gpu_gzip_inflate(exon_gpu_ctx *c, const uint8_t *data, size_
     uint8_t *d_out = out_is_device ? out : scr + o_out;
     cudaStream_t st = c->stream;
     for (BgzfMember &m : members) m.out_addr += (uint64_t)reinterpret_cast<uintptr_t>(d_out);
-    const size_t bm_words = bgzf_assign_bitmap(members.data(), members.size());
+    const size_t tok_units = bgzf_assign_tokens(members.data(), members.size());
     CUDA_TRY(cudaMemcpyAsync(scr, data, len, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(scr + o_tab, members.data(), members.size() * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
     const int init_flags[2] = {0, 0x7FFFFFFF};
     CUDA_TRY(cudaMemcpyAsync(scr + o_flags, init_flags, sizeof(init_flags), cudaMemcpyHostToDevice, st));
     CUDA_TRY(c->timed_begin(st));
-    if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), (uint32_t *)(scr + o_flags), bm_words, len)) return rc;
+    if (int rc = bgzf_inflate_launch(c, scr, (const BgzfMember *)(scr + o_tab), (int)members.size(), (uint32_t *)(scr + o_flags), tok_units, len)) return rc;
     CUDA_TRY(c->timed_end(st));
     CUDA_TRY(cudaMemcpyAsync(c->h_scratch, scr + o_flags, 8, cudaMemcpyDeviceToHost, st));
     if (!out_is_device) CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)total, cudaMemcpyDeviceToHost, st));

@@ -1,29 +1,34 @@
 // inflate.cu -- DEFLATE (RFC 1951) on the device as two kernels (the decompression in front of
 // every parser: noodles-bgzf 0.34 `Reader` / async-compression `GzipDecoder`, see bgzf.cu for the call sites).
 //
-// Huffman decoding is serial per stream and LZ77 copying is wide but ordered; one kernel that does both leaves the
-// lanes idle in turn (the round-1 first cut: 16 lanes per member, ~8 active threads per instruction).  Here the two
-// halves are separate kernels with the layout each one wants:
+// Huffman decoding is serial per stream and wants tens of thousands of streams in flight; LZ77 copying is wide but ordered
+// and wants a stream's recent output on chip.  One kernel that does both starves one half or the other, so the two halves
+// are separate kernels joined by a COMPACT TOKEN STREAM in device memory (round 2; round 1 wrote literals and 3-byte tokens
+// in place into the output and marked match starts in a bitmap: 16.9 GB of DRAM traffic for 3.3 GB of algorithmic bytes,
+// profiles/r1_ncu_full_bgzf_inflate.txt -- every sector of the output was written partially, read back, and written again):
 //
-//   K_dec  inflate_decode_kernel   ONE LANE PER MEMBER, 32 members per warp in lock step.  Each lane runs the bit reader
-//          (two 32-bit words + one prefetched, peek = one funnel shift; the stream's next L1 line is requested ahead),
-//          builds its own tables in shared memory (lit/len 2^LB x u16, distance 2^7 x u8, plus the canonical limits and
-//          offsets of the lengths 8..15: a code longer than the primary table costs two shared loads, a branch-free
-//          length search and one dependent local load of the symbol), and writes
-//            * every LITERAL byte straight to its final place in the output, and
-//            * every MATCH as a 3-byte token (len - 3 | (dist - 1) << 8) INTO THE FIRST THREE BYTES OF THE MATCH'S OWN
-//              OUTPUT RANGE (a match is >= 3 bytes, so the token always fits and needs no memory of its own), plus
-//              one bit per match start in a bitmap (1 bit per output byte).
-//          LB = 8 puts 320 lanes on an SM, LB = 9 decodes faster per lane: chosen per launch (bgzf_inflate_launch).
-//   K_copy inflate_copy_kernel     ONE WARP PER MEMBER.  Walks the output in 1 KiB segments kept in a 4 KiB shared-memory
-//          ring: loads the segment (literals in place), turns the segment's bitmap words into a list of match
-//          positions, requests the lines of every source that lies behind the ring, reads the tokens (one lane per
-//          match), copies every match whose source lies wholly before the segment in parallel (one lane per match),
-//          executes the remaining (dependent) matches in output order with all 32 lanes -- found 32 at a time by
-//          ballot --, and writes the finished segment back with 16-byte stores.  A match that crosses the segment end
-//          is continued in the next segment.
+//   member token area (bgzf_token_units(isize) 16-byte units, assigned by bgzf_assign_tokens):
+//       unit 0              header {n_tokens, n_literals, 0, 0}
+//       units 1 ..          literal bytes, in output order, growing upwards
+//       .. last unit        32-bit tokens in groups of four, group k in unit (last - k):
+//                           literals before the match (0..255) | match length (0 = none, 3..258) << 8 | (distance - 1) << 17
+//       (literals + 4 x tokens never meet: a match is worth >= 3 output bytes, so the area holds 4/3 of ISIZE + slack)
 //
-// Output is bit-exact DEFLATE; ISIZE of every member is checked, CRC32 is not.
+//   K_dec  inflate_decode_kernel   ONE LANE PER MEMBER, 32 members per warp in lock step.  Each lane pulls its stream through
+//          registers in 16-byte loads issued one chunk ahead (the L1 left beside the tables is far smaller than 320 lanes x
+//          one line: per-word loads missed it constantly in round 1), keeps a 64-bit bit buffer, builds its own tables in
+//          shared memory -- element i of lane l at [i][l], so that the 32 lanes of a lookup fall into different banks
+//          -- and collects literals and tokens in registers, sixteen bytes / four tokens per 16-byte store.
+//   K_copy inflate_copy_kernel     ONE WARP PER MEMBER with the member's last RB bytes of output in a shared-memory ring.
+//          32 tokens at a time (fewer when they span more than kSpan bytes): one packed warp scan gives every lane its output
+//          and literal-stream positions; the group's literal bytes are read coalesced and scattered into the ring; matches
+//          whose source lies behind the ring come from global memory (written there by this warp at least RB - kSpan bytes
+//          ago); the rest resolve in rounds -- a lane copies as soon as its source lies below the first unfinished match of
+//          the group, so independent matches go 32 at a time and a chain costs one round per link.  Finished output leaves
+//          the ring in 16-byte stores, 512 bytes per warp instruction.
+//
+// DRAM traffic per launch: compressed in + tokens out (K_dec), tokens in + output out (K_copy).  Output is bit-exact DEFLATE;
+// ISIZE of every member is checked, CRC32 is not.
 #include <algorithm>
 #include <cstdlib>
 
@@ -48,69 +53,130 @@ constexpr uint32_t kInfErrSize = 2u;  // output does not match ISIZE
 // ------------------------------------------------------------------------------------------------------------------
 // K_dec
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kDecWarps = 2;
+constexpr int kDecWarps = 4;
 
 __constant__ uint8_t c_clen_order2[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// LSB-first bit reader: `lo` holds the current word, `hi` the next, `nxt` one more (loaded ahead so that its latency
-// is off the critical path).  0 <= bp < 32 always, so peek() returns 32 valid bits.
 __device__ __forceinline__ void prefetch_line(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// The stream is read 16 bytes at a time, eight times per 128-byte line and microseconds apart: it has to STAY in the L2 in
+// between (an evict-first hint -- L1::no_allocate turns into one -- made every one of the eight a DRAM access), and it is of
+// no use in the L1, which is far smaller than the lines 288 lanes are reading.
+__device__ __forceinline__ uint4 ld_stream16(const uint4 *p) { return __ldcg(p); }
+// one whole 32-byte sector per store: a sector written in two halves makes the L2 fetch it from DRAM first (round 1 and the
+// first cut of this file read 5x the compressed bytes that way)
+__device__ __forceinline__ void st_sector(void *p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]),
+                 "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
 
+constexpr int kInWords = 16;  // a lane's input FIFO in shared memory: four 16-byte chunks
+
+// LSB-first bit reader.  `bb` holds `cnt` valid bits; refill() brings cnt to 33..64 one 32-bit word at a time.  The words
+// come out of a small per-lane FIFO in shared memory (word w of the stream at fifo[w % kInWords][lane]); `nxtw` is the next
+// one, fetched ahead so that the shared-memory latency is off the refill's critical path.
+//
+// The FIFO is fed 16 bytes at a time, and the feeding is what the structure is about: a warp's scoreboards do not know
+// lanes apart, so a load that some lanes issue in one round makes the next round's read of the same registers wait for it,
+// whichever lanes read.  The symbol loop therefore tops the FIFO up at a FIXED place every second round: topup() first
+// moves the chunk requested two rounds ago from registers to shared memory, then requests the next one for every lane
+// whose level has fallen below eight words.  A round consumes at most 48 bits, so between two top-ups a lane takes at most
+// three words and the level never falls below two.  Outside the symbol loop (block headers, stored blocks) fill() loads
+// synchronously.
+//
+// Chunks that lie wholly beyond the payload are never read (zeros are fed instead), so a corrupt or truncated stream cannot
+// run off the staging buffer; `spent` says that the reader is certainly past the payload.
 struct LaneBits {
-    const uint32_t *wp;    // next word to load
-    const uint32_t *w0;    // aligned word the MEMBER started in (bits_consumed() counts from there, across stored blocks)
-    const uint32_t *wend;  // last word that holds payload bytes: nothing beyond it is ever read (zeros are fed instead), so a
-                           // corrupt or truncated stream cannot run off the staging buffer; the decoder notices the overrun
-                           // through overrun() / bits_consumed()
-    uint32_t lo, hi, nxt;
-    int bp;
-    int mis8;
-    __device__ __forceinline__ uint32_t load(const uint32_t *p) const { return p <= wend ? __ldg(p) : 0u; }
-    // position the reader at byte p of the same member (p >= the member's first byte)
-    __device__ __forceinline__ void seek(const uint8_t *p) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-        const int mis = (int)(a & 3);
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(a - mis);
-        lo = load(w);
-        hi = load(w + 1);
-        nxt = load(w + 2);
-        wp = w + 3;
-        bp = 8 * mis;
-        prefetch_line(w + 32);
-        prefetch_line(w + 64);
-    }
-    __device__ __forceinline__ void init(const uint8_t *p, uint32_t payload_bytes) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-        const int mis = (int)(a & 3);
-        w0 = reinterpret_cast<const uint32_t *>(a - mis);
-        mis8 = 8 * mis;
-        wend = payload_bytes ? reinterpret_cast<const uint32_t *>((a + payload_bytes - 1) & ~(uintptr_t)3) : w0 - 1;
-        seek(p);
-    }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, bp); }
-    __device__ __forceinline__ void skip(int n) {  // n <= 32
-        bp += n;
-        if (bp >= 32) {
-            lo = hi;
-            hi = nxt;
-            nxt = load(wp);
-            ++wp;
-            bp -= 32;
-            // every lane streams its own member: without this, some lane of the warp misses L1 at almost every refill
-            if ((reinterpret_cast<uintptr_t>(wp) & 127u) == 0) prefetch_line(wp + 32);
+    uint32_t *fifo;     // &W.in[0][lane]
+    const uint4 *np;    // next chunk to request
+    const uint4 *endp;  // the chunk that holds the payload's last byte
+    uint4 fl;           // chunk in flight
+    uint32_t lo, hi;    // the word being consumed and the one after it
+    uint32_t nxtw;      // the one after that, fetched ahead
+    uint32_t rd, wr;    // words fetched from / written to the FIFO
+    int bp;             // bits of `lo` already consumed; refill() brings it below 32, so that peek() returns 32 valid bits
+    int skew;           // bits of the first word that precede the payload
+    bool infl, spent;
+    __device__ __forceinline__ uint4 load(const uint4 *p) const { return p <= endp ? ld_stream16(p) : make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ void land() {
+        if (infl) {
+            fifo[((wr + 0u) & (kInWords - 1)) * 32] = fl.x;
+            fifo[((wr + 1u) & (kInWords - 1)) * 32] = fl.y;
+            fifo[((wr + 2u) & (kInWords - 1)) * 32] = fl.z;
+            fifo[((wr + 3u) & (kInWords - 1)) * 32] = fl.w;
+            wr += 4u;
+            infl = false;
         }
     }
-    __device__ __forceinline__ uint32_t take(int n) {  // n <= 16
+    __device__ __forceinline__ void request() {
+        if (wr - rd < 8u) {
+            fl = load(np);
+            spent = spent || np > endp + 5;  // more than the FIFO and the three words in registers hold together lies beyond the payload
+            ++np;
+            infl = true;
+        }
+    }
+    __device__ __forceinline__ void topup() {
+        land();
+        request();
+    }
+    __device__ __forceinline__ void fill() {  // synchronous: block headers and stored blocks
+        land();
+        while (wr - rd < 8u) {
+            request();
+            land();
+        }
+    }
+    __device__ __forceinline__ void next_word() {
+        lo = hi;
+        hi = nxtw;
+        nxtw = fifo[(rd & (kInWords - 1)) * 32];
+        ++rd;
+    }
+    __device__ __forceinline__ void init(uint32_t *lane_fifo, const uint8_t *p, uint32_t payload_bytes) {
+        fifo = lane_fifo;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const int mis = (int)(a & 15);
+        const uint4 *c0 = reinterpret_cast<const uint4 *>(a - mis);
+        endp = payload_bytes ? reinterpret_cast<const uint4 *>((a + payload_bytes - 1) & ~(uintptr_t)15) : c0 - 1;
+        np = c0;
+        rd = wr = 0u;
+        infl = spent = false;
+        fill();
+        rd = (uint32_t)(mis >> 2);  // the words before the payload are never fetched
+        next_word();
+        next_word();
+        next_word();                // lo = the payload's first word
+        skew = 32 * (mis >> 2) + 8 * (mis & 3);
+        bp = 8 * (mis & 3);
+    }
+    // inside the symbol loop (topup() keeps the FIFO ahead): no branch -- a few lanes need a word in any given round, and a
+    // divergent branch would cost the warp more than the four predicated instructions do
+    __device__ __forceinline__ void refill() {
+        const bool need = bp >= 32;
+        lo = need ? hi : lo;
+        hi = need ? nxtw : hi;
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(fifo) + (rd & (kInWords - 1)) * 128u;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.u32 %0, [%1];\n\t}" : "+r"(nxtw) : "r"(a), "r"((uint32_t)need));
+        rd += need ? 1u : 0u;
+        bp -= need ? 32 : 0;
+    }
+    __device__ __forceinline__ void refill_sync() {  // anywhere else
+        if (bp >= 32) {
+            if (wr - rd < 2u) fill();
+            next_word();
+            bp -= 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(lo, hi, bp); }  // bp < 32
+    __device__ __forceinline__ void skip(int n) { bp += n; }                                   // n <= 32 - (bits used since the last refill)
+    __device__ __forceinline__ uint32_t take(int n) {                                          // n <= 16, after a refill
         const uint32_t v = peek() & ((1u << n) - 1u);
         skip(n);
         return v;
     }
-    __device__ __forceinline__ int64_t bits_consumed() const { return ((int64_t)(wp - 3 - w0) << 5) + bp - mis8; }
-    // the word being consumed lies wholly beyond the payload: every further bit is a fed zero
-    __device__ __forceinline__ bool overrun() const { return wp - 3 > wend; }
-    __device__ __forceinline__ const uint8_t *byte_ptr() const {  // only meaningful when bp % 8 == 0
-        return reinterpret_cast<const uint8_t *>(wp - 3) + (bp >> 3);
-    }
+    // three words have been fetched beyond the consumed ones (lo, hi, nxtw)
+    __device__ __forceinline__ int64_t bits_consumed() const { return (int64_t)(rd - 3u) * 32 + bp - skew; }
 };
 
 // per-lane canonical code description (local memory): used to build the primary table; `sym` also serves codes longer than it
@@ -120,12 +186,12 @@ struct Canon {
     uint16_t cnt[16];
 };
 
-// Builds cnt / sym from lens[0..n) and fills the primary table tab[0 .. 1 << PB): entry = sym << LS | len, 0 = longer code
-// (LS = 4 for the 16-bit tables, 3 for the 8-bit distance table whose lengths are <= 7).  For lengths 8..15 it also leaves,
-// in shared memory, lim[L - 8] = (first code of length L + cnt[L]) << (15 - L) -- a 15-bit MSB-first prefix below it has
-// length <= L -- and off[L - 8] = index of the first symbol of length L in sym[] - first code of length L.
-// false on an over-subscribed code.
-template <class E, int LS, class CanonT>
+// Builds cnt / sym from lens[0..n) and fills the lane's primary table (element i at tab[i * 32]), 1 << PB entries:
+// entry = sym << LS | len, 0 = longer code (LS = 4 for the 16-bit tables, 3 for the 8-bit distance table whose lengths are
+// <= 7).  For lengths 7..15 it also leaves lim[L - 7] = (first code of length L + cnt[L]) << (15 - L) -- a 15-bit MSB-first
+// prefix below it has length <= L -- and off[L - 7] = index of the first symbol of length L in sym[] - first code of length
+// L.  false on an over-subscribed code.
+template <class E, int LS, class Enc, class CanonT>
 __device__ bool canon_table(const uint8_t *lens, int n, int PB, E *tab, CanonT &C, uint16_t *lim, int16_t *off) {
     uint16_t offs[16], next[16];
 #pragma unroll
@@ -142,15 +208,14 @@ __device__ bool canon_table(const uint8_t *lens, int n, int PB, E *tab, CanonT &
         left -= C.cnt[l];
         if (left < 0) return false;
         next[l] = (uint16_t)code;
-        if (lim && l >= 8) {
-            lim[l - 8] = (uint16_t)((code + C.cnt[l]) << (15 - l));
-            off[l - 8] = (int16_t)((int)offs[l] - (int)code);
+        if (lim && l >= 7) {
+            lim[l - 7] = (uint16_t)((code + C.cnt[l]) << (15 - l));
+            off[l - 7] = (int16_t)((int)offs[l] - (int)code);
         }
         code = (code + C.cnt[l]) << 1;
         if (l < 15) offs[l + 1] = (uint16_t)(offs[l] + C.cnt[l]);
     }
-    uint32_t *t32 = reinterpret_cast<uint32_t *>(tab);
-    for (int i = 0; i < (int)((sizeof(E) << PB) / 4); ++i) t32[i] = 0u;
+    for (int i = 0; i < (1 << PB); ++i) tab[i * 32] = (E)0;
     for (int s = 0; s < n; ++s) {
         const int L = lens[s];
         if (!L) continue;
@@ -158,90 +223,192 @@ __device__ bool canon_table(const uint8_t *lens, int n, int PB, E *tab, CanonT &
         const uint32_t c = next[L]++;
         if (L <= PB) {
             const uint32_t rev = __brev(c) >> (32 - L);
-            const E e = (E)((s << LS) | L);
-            for (uint32_t i = rev; i < (1u << PB); i += (1u << L)) tab[i] = e;
+            const E e = (E)((Enc()((uint32_t)s) << LS) | L);
+            for (uint32_t i = rev; i < (1u << PB); i += (1u << L)) tab[i * 32] = e;
         }
     }
     return true;
 }
 
-// The code at bit 0 of `bits` (LSB first) is longer than PB (>= 7) bits.  lim[] is non-decreasing in the length, so the
-// length is PB + 1 + the number of lengths whose limit the 15-bit MSB-first prefix has reached: no branches, the limits
-// come from shared memory in one go, and a single dependent local load fetches the symbol.
-// sym | len << 16, or 0xFFFFFFFF when no code matches.
+// The code at bit 0 of `bits` (LSB first) is longer than PB (>= 6) bits.  lim[] is non-decreasing in the length, so the
+// length is PB + 1 + the number of lengths whose limit the 15-bit MSB-first prefix has reached: no branches, and a single
+// dependent local load fetches the symbol.  sym | len << 16, or 0xFFFFFFFF when no code matches.
 template <int PB, class CanonT>
 __device__ __forceinline__ uint32_t canon_long(uint32_t bits, const uint16_t *lim, const int16_t *off, const CanonT &C) {
     const uint32_t c15 = __brev(bits) >> 17;
-    const uint4 L = *reinterpret_cast<const uint4 *>(lim);
-    const uint32_t lw[4] = {L.x, L.y, L.z, L.w};
     int len = PB + 1;
 #pragma unroll
-    for (int l = PB + 1; l <= 15; ++l) {
-        const uint32_t v = (lw[(l - 8) >> 1] >> (((l - 8) & 1) * 16)) & 0xFFFFu;
-        len += c15 >= v ? 1 : 0;
-    }
+    for (int l = PB + 1; l <= 15; ++l) len += c15 >= (uint32_t)lim[l - 7] ? 1 : 0;
     if (len > 15) return 0xFFFFFFFFu;
-    return (uint32_t)C.sym[(int)off[len - 8] + (int)(c15 >> (15 - len))] | ((uint32_t)len << 16);
+    return (uint32_t)C.sym[(int)off[len - 7] + (int)(c15 >> (15 - len))] | ((uint32_t)len << 16);
 }
 
-// per-lane tables in shared memory: 2^LB x u16 + 2^DB x u8 + 64 B of limits / offsets
+// one warp's shared memory: the primary tables, the input FIFOs and the output staging, all interleaved by lane (element i
+// of lane l at [i][l]: the 32 lanes of an access fall into different banks -- two lanes per bank word for the 16-bit table,
+// four for the 8-bit one).  The long-code limits / offsets are per-lane local memory (Limits): a code longer than the
+// primary table is rare, and the 2 KiB they took is what lets a ninth warp fit on the SM.
 template <int LB, int DB>
-struct LaneTabs {
-    uint16_t lit[1 << LB];  // sym << 4 | len
-    uint8_t dist[1 << DB];  // sym << 3 | len (DB <= 7)
-    __align__(16) uint16_t llim[8];
-    __align__(16) uint16_t dlim[8];
-    int16_t loff[8];
-    int16_t doff[8];
+struct WarpTabs {
+    uint16_t lit[1 << LB][32];  // sym << 4 | len
+    uint8_t dist[1 << DB][32];  // sym << 3 | len (DB <= 7)
+    uint32_t in[kInWords][32];
+    uint32_t tok[16][32];
+    uint32_t lw[16][32];
+};
+struct Limits {  // lengths 7..15
+    uint16_t llim[10];
+    uint16_t dlim[10];
+    int16_t loff[10];
+    int16_t doff[10];
+};
+
+// What a lane has produced and not yet stored: literal bytes (the word being filled in a register, finished words in a ring of
+// 16 in shared memory) and tokens (a ring of 16).  32 bytes / eight tokens leave as one sector store -- not when a lane
+// happens to have them (some lane of the warp always does: the whole warp would step through the store sequence every
+// round) but at a fixed place every eight rounds, where each lane stores the sector it has complete, if any.  A round adds at
+// most one literal and one token, so the rings never hold more than 7 + 8 entries.
+struct LaneOut {
+    uint32_t *tokq, *litq;  // &W.tok[0][lane], &W.lw[0][lane]
+    uint8_t *lit_dst;       // next 32 bytes of the literal stream
+    uint8_t *tok_dst;       // next (lower) group of eight tokens
+    uint32_t acc;
+    uint32_t n_lit, n_tok;  // produced
+    uint32_t f_lw, f_tok;   // literal words / tokens stored (multiples of 8)
+    uint32_t run;           // literals since the last token
+    __device__ __forceinline__ void push_byte(uint32_t b) {
+        acc = __byte_perm(acc, b, 0x4321);  // bytes enter at the top: four of them later the word reads in stream order
+        ++n_lit;
+        if ((n_lit & 3u) == 0u) litq[(((n_lit >> 2) - 1u) & 15u) * 32] = acc;
+    }
+    __device__ __forceinline__ void push_token_raw(uint32_t t) {
+        tokq[(n_tok & 15u) * 32] = t;
+        ++n_tok;
+    }
+    __device__ __forceinline__ void literal(uint32_t b) {
+        push_byte(b);
+        if (++run == 255u) {
+            push_token_raw(255u);
+            run = 0;
+        }
+    }
+    __device__ __forceinline__ void match(uint32_t len, uint32_t dist) {
+        push_token_raw(run | (len << 8) | ((dist - 1u) << 17));
+        run = 0;
+    }
+    __device__ __forceinline__ void store_if_complete() {
+        if (n_tok - f_tok >= 8u) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = tokq[((f_tok + i) & 15u) * 32];
+            st_sector(tok_dst, w);
+            tok_dst -= 32;
+            f_tok += 8u;
+        }
+        if ((n_lit >> 2) - f_lw >= 8u) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = litq[((f_lw + i) & 15u) * 32];
+            st_sector(lit_dst, w);
+            lit_dst += 32;
+            f_lw += 8u;
+        }
+    }
+    __device__ void drain() {  // outside the symbol loop's rhythm (stored blocks, block ends)
+        while (n_tok - f_tok >= 8u || (n_lit >> 2) - f_lw >= 8u) store_if_complete();
+    }
+    // the pending literals become a token, partial sectors are padded with zeros (a zero token copies nothing)
+    __device__ void finish(uint4 *hdr, bool ok) {
+        if (run) push_token_raw(run);
+        run = 0;
+        const uint32_t nl = n_lit, nt = n_tok;
+        drain();
+        while (n_lit & 31u) push_byte(0u);
+        while (n_tok & 7u) push_token_raw(0u);
+        drain();
+        *hdr = make_uint4(ok ? nt : 0u, ok ? nl : 0u, 0u, 0u);
+    }
+};
+
+// Literal/length table payload (12 bits above the 4-bit code length): what the symbol loop needs, ready to use.
+//   0x000..0x0FF literal byte | 0x100 end of block | 0x200 invalid symbol (286, 287)
+//   0x800 | big << 6 | lx << 3 | m : a length, = 3 + (m << lx) + lx extra bits (+ 255 when `big`: symbol 285 = 258)
+__device__ __forceinline__ uint32_t litlen_payload(uint32_t s) {
+    if (s <= 256u) return s;
+    const uint32_t ls = s - 257u;
+    if (ls >= 29u) return 0x200u;
+    if (ls == 28u) return 0x800u | 0x40u;
+    if (ls < 8u) return 0x800u | ls;
+    return 0x800u | (((ls - 4u) >> 2) << 3) | (4u + (ls & 3u));
+}
+struct PlainSym {
+    __device__ __forceinline__ uint32_t operator()(uint32_t s) const { return s; }
+};
+struct LitLenSym {
+    __device__ __forceinline__ uint32_t operator()(uint32_t s) const { return litlen_payload(s); }
 };
 
 template <int LB, int DB>
-__global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const uint8_t *comp, const BgzfMember *members, int n_members,
-                                                                        uint32_t *bitmap, uint32_t *flags, int *first_bad) {
+__global__ void __launch_bounds__(kDecWarps * 32, LB == 7 ? 4 : 2) inflate_decode_kernel(const uint8_t *comp, const BgzfMember *members, int n_members, int lanes_per_warp,
+                                                                                       uint4 *tokens, uint32_t *flags, int *first_bad) {
     extern __shared__ __align__(16) uint8_t dec_smem_raw[];
-    LaneTabs<LB, DB> &T = reinterpret_cast<LaneTabs<LB, DB> *>(dec_smem_raw)[threadIdx.x];
-    const int gt = blockIdx.x * (kDecWarps * 32) + threadIdx.x, nt = gridDim.x * (kDecWarps * 32);
-    static_assert(LB >= 7 && LB <= 9 && DB == 7, "limits / offsets in shared memory start at length 8; the 8-bit distance table holds lengths <= 7");
+    WarpTabs<LB, DB> &W = reinterpret_cast<WarpTabs<LB, DB> *>(dec_smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    uint16_t *const lit = &W.lit[0][lane];
+    uint8_t *const dtab = &W.dist[0][lane];
+    // With fewer members than the machine holds lanes, the members are spread over MORE warps with fewer working lanes each:
+    // a warp's round costs the sum of the paths its lanes take, and the SM hides one warp's latency behind the others.
+    if (lane >= lanes_per_warp) return;
+    const int gt = (blockIdx.x * kDecWarps + (threadIdx.x >> 5)) * lanes_per_warp + lane, nt = gridDim.x * kDecWarps * lanes_per_warp;
+    static_assert(LB >= 7 && LB <= 9 && DB >= 6 && DB <= 7, "limits / offsets start at length 7; the 8-bit distance table holds lengths <= 7");
     Canon<288> CL;  // lit/len code of the current block (and, while the header is read, the code-length code)
     Canon<32> CD;   // distance code
+    Limits LM;
     uint8_t lens[320];
 #pragma unroll 1
     for (int mi = gt; mi < n_members; mi += nt) {
         const BgzfMember M = members[mi];
         if (M.isize == 0) continue;
-        uint8_t *out = reinterpret_cast<uint8_t *>((uintptr_t)M.out_addr);
         const uint32_t isize = M.isize;
-        const uint32_t q0 = (uint32_t)(M.out_addr & 15u);
-        uint32_t *bm = bitmap + M.bm_off;
-        uint32_t bm_wi = 0, bm_w = 0;
+        uint4 *area = tokens + M.tok_off;
+        LaneOut out;
+        out.tokq = &W.tok[0][lane];
+        out.litq = &W.lw[0][lane];
+        out.lit_dst = reinterpret_cast<uint8_t *>(area + 2);
+        out.tok_dst = reinterpret_cast<uint8_t *>(area + bgzf_token_units(isize) - 2);
+        out.acc = 0u;
+        out.n_lit = out.n_tok = out.run = out.f_lw = out.f_tok = 0u;
         LaneBits br;
-        br.init(comp + M.in_off, M.in_len);
+        br.init(&W.in[0][lane], comp + M.in_off, M.in_len);
         const int64_t in_bits = (int64_t)M.in_len * 8;
         uint32_t pos = 0, err = 0;
         bool last = false;
 #pragma unroll 1
         while (!last && !err) {
+            br.refill_sync();
             const uint32_t hdr = br.peek();
             last = (hdr & 1u) != 0u;
             const int btype = (int)((hdr >> 1) & 3u);
             br.skip(3);
-            if (br.bits_consumed() > in_bits || btype == 3) {  // a stream that runs past its payload is corrupt
+            if (br.spent || br.bits_consumed() > in_bits || btype == 3) {  // a stream that runs past its payload is corrupt
                 err = kInfErrData;
                 break;
             }
             if (btype == 0) {
                 br.skip((8 - (br.bp & 7)) & 7);
-                const uint32_t w = br.peek();
-                br.skip(32);
-                const uint32_t len = w & 0xFFFFu;
-                if ((len ^ (w >> 16)) != 0xFFFFu || pos + len > isize || br.bits_consumed() + (int64_t)len * 8 > in_bits) {
+                br.refill_sync();
+                const uint32_t len = br.take(16);
+                br.refill_sync();
+                const uint32_t nlen = br.take(16);
+                if ((len ^ nlen) != 0xFFFFu || pos + len > isize || br.bits_consumed() + (int64_t)len * 8 > in_bits) {
                     err = kInfErrData;
                     break;
                 }
-                const uint8_t *src = br.byte_ptr();
-                for (uint32_t j = 0; j < len; ++j) out[pos + j] = __ldg(src + j);
+                for (uint32_t j = 0; j < len; ++j) {
+                    br.refill_sync();
+                    out.literal(br.take(8));
+                    out.drain();
+                }
                 pos += len;
-                br.seek(src + len);  // bits_consumed() keeps counting from the member's start
                 continue;
             }
             if (btype == 1) {
@@ -252,22 +419,27 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                 for (int s = 0; s < 30; ++s) lens[288 + s] = 5;
                 lens[318] = lens[319] = 0;
             } else {
+                br.refill_sync();
                 const uint32_t h = br.peek();
                 br.skip(14);
                 const int nlit = (int)(h & 31u) + 257, ndist = (int)((h >> 5) & 31u) + 1, ncl = (int)((h >> 10) & 15u) + 4;
                 uint8_t cl[19];
 #pragma unroll
                 for (int i = 0; i < 19; ++i) cl[i] = 0;
-                for (int i = 0; i < ncl; ++i) cl[c_clen_order2[i]] = (uint8_t)br.take(3);
+                for (int i = 0; i < ncl; ++i) {
+                    br.refill_sync();
+                    cl[c_clen_order2[i]] = (uint8_t)br.take(3);
+                }
                 // the code-length code (7-bit codes at most) borrows the literal table's place and CL's arrays
-                if (nlit > 286 || ndist > 30 || !canon_table<uint16_t, 4>(cl, 19, 7, T.lit, CL, nullptr, nullptr)) {
+                if (nlit > 286 || ndist > 30 || !canon_table<uint16_t, 4, PlainSym>(cl, 19, 7, lit, CL, nullptr, nullptr)) {
                     err = kInfErrData;
                     break;
                 }
                 int i = 0;
                 const int total = nlit + ndist;
                 while (i < total) {
-                    const uint32_t e = T.lit[br.peek() & 127u];
+                    br.refill_sync();
+                    const uint32_t e = lit[(br.peek() & 127u) * 32];
                     if (!e) {
                         err = kInfErrData;
                         break;
@@ -279,6 +451,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                         continue;
                     }
                     int rep, val = 0;
+                    br.refill_sync();  // peek() wants bp < 32
                     if (sym == 16) {
                         if (i == 0) {
                             err = kInfErrData;
@@ -309,100 +482,88 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
                 for (int s = 0; s < 32; ++s) lens[288 + s] = tmp[s];
             }
             // an incomplete distance code with a single symbol is legal (RFC 1951 3.2.7); over-subscription is not
-            if (!canon_table<uint16_t, 4>(lens, 288, LB, T.lit, CL, T.llim, T.loff) ||
-                !canon_table<uint8_t, 3>(lens + 288, 30, DB, T.dist, CD, T.dlim, T.doff)) {
+            if (!canon_table<uint16_t, 4, LitLenSym>(lens, 288, LB, lit, CL, LM.llim, LM.loff) || !canon_table<uint8_t, 3, PlainSym>(lens + 288, 30, DB, dtab, CD, LM.dlim, LM.doff)) {
                 err = kInfErrData;
                 break;
             }
-            // ---- symbols ----
+            // ---- symbols: two per trip, the FIFO topped up once per trip, finished sectors stored every fourth trip ----
+            br.fill();
+            bool eob = false;
+            uint32_t trip = 0;
 #pragma unroll 1
-            while (true) {
-                if (br.overrun()) {  // the stream ran off its payload (truncated or corrupt member): stop now, not after ISIZE symbols
-                    err = kInfErrData;
-                    break;
-                }
-                uint32_t w = br.peek();
-                uint32_t e = T.lit[w & ((1u << LB) - 1u)];
-                if (!e) {
-                    const uint32_t r = canon_long<LB>(w, T.llim, T.loff, CL);
-                    if (r == 0xFFFFFFFFu) {
-                        err = kInfErrData;
+            while (!eob && !br.spent) {
+                br.topup();
+                if ((++trip & 3u) == 0u) out.store_if_complete();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (eob) break;
+                    br.refill();  // bp < 32: a literal/length code and its extra bits (<= 20) are there
+                    uint32_t w = br.peek();
+                    uint32_t e = lit[(w & ((1u << LB) - 1u)) * 32];
+                    if (!e) {
+                        const uint32_t r = canon_long<LB>(w, LM.llim, LM.loff, CL);
+                        if (r == 0xFFFFFFFFu) {
+                            err = kInfErrData;
+                            eob = true;
+                            break;
+                        }
+                        e = (litlen_payload(r & 0xFFFFu) << 4) | (r >> 16);
+                    }
+                    const int clen = (int)(e & 15u);
+                    const uint32_t pay = e >> 4;
+                    if (pay < 0x100u) {
+                        br.skip(clen);
+                        if (pos >= isize) {
+                            err = kInfErrData;
+                            eob = true;
+                            break;
+                        }
+                        ++pos;
+                        out.literal(pay);
+                        continue;
+                    }
+                    if (!(pay & 0x800u)) {  // end of block, or a symbol that does not exist
+                        br.skip(clen);
+                        if (pay != 0x100u) err = kInfErrData;
+                        eob = true;
                         break;
                     }
-                    e = ((r & 0xFFFFu) << 4) | (r >> 16);
-                }
-                const int clen = (int)(e & 15u);
-                const int sym = (int)(e >> 4);
-                if (sym < 256) {
-                    br.skip(clen);
-                    if (pos >= isize) {
+                    // length = 3 + (m << lx) + extra (+ 255 for symbol 285), RFC 1951 3.2.5
+                    const uint32_t lx = (pay >> 3) & 7u;
+                    const uint32_t len = 3u + ((pay & 7u) << lx) + ((w >> clen) & ((1u << lx) - 1u)) + ((pay >> 6) & 1u) * 255u;
+                    br.skip(clen + (int)lx);  // <= 15 + 5
+                    br.refill();              // bp < 32 again: a distance code and its extra bits (<= 28)
+                    w = br.peek();
+                    e = dtab[(w & ((1u << DB) - 1u)) * 32];
+                    int dlen = (int)(e & 7u), ds = (int)(e >> 3);
+                    if (!e) {
+                        const uint32_t r = canon_long<DB>(w, LM.dlim, LM.doff, CD);
+                        if (r == 0xFFFFFFFFu) {
+                            err = kInfErrData;
+                            eob = true;
+                            break;
+                        }
+                        dlen = (int)(r >> 16);
+                        ds = (int)(r & 0xFFFFu);
+                    }
+                    const int dx = (max(ds, 2) - 2) >> 1;
+                    const uint32_t dist = 1u + ((uint32_t)(ds < 2 ? ds : 2 + (ds & 1)) << dx) + ((w >> dlen) & ((1u << dx) - 1u));
+                    br.skip(dlen + dx);  // <= 15 + 13
+                    if (ds >= 30 || dist > pos || pos + len > isize) {
                         err = kInfErrData;
+                        eob = true;
                         break;
                     }
-                    out[pos++] = (uint8_t)sym;
-                    continue;
+                    out.match(len, dist);
+                    pos += len;
                 }
-                if (sym == 256) {
-                    br.skip(clen);
-                    break;
-                }
-                const int ls = sym - 257;
-                if (ls >= 29) {
-                    err = kInfErrData;
-                    break;
-                }
-                // length base / extra bits in closed form (RFC 1951 3.2.5)
-                w >>= clen;
-                int lx = ls < 8 ? 0 : (ls - 4) >> 2;
-                uint32_t len = ls < 8 ? (uint32_t)(3 + ls) : (uint32_t)(3 + ((4 + (ls & 3)) << lx));
-                if (ls == 28) {
-                    lx = 0;
-                    len = 258;
-                }
-                len += w & ((1u << lx) - 1u);
-                br.skip(clen + lx);  // <= 15 + 5
-                w = br.peek();
-                e = T.dist[w & ((1u << DB) - 1u)];
-                int dlen = (int)(e & 7u), ds = (int)(e >> 3);
-                if (!e) {
-                    const uint32_t r = canon_long<DB>(w, T.dlim, T.doff, CD);
-                    if (r == 0xFFFFFFFFu) {
-                        err = kInfErrData;
-                        break;
-                    }
-                    dlen = (int)(r >> 16);
-                    ds = (int)(r & 0xFFFFu);
-                }
-                if (ds >= 30) {
-                    err = kInfErrData;
-                    break;
-                }
-                w >>= dlen;
-                const int dx = ds < 4 ? 0 : (ds - 2) >> 1;
-                const uint32_t dist = (ds < 4 ? (uint32_t)(1 + ds) : (uint32_t)(1 + ((2 + (ds & 1)) << dx))) + (w & ((1u << dx) - 1u));
-                br.skip(dlen + dx);  // <= 15 + 13
-                if (dist > pos || pos + len > isize) {
-                    err = kInfErrData;
-                    break;
-                }
-                // the token goes where the match will be, its start is marked in the bitmap
-                const uint32_t tok = (len - 3u) | ((dist - 1u) << 8);
-                out[pos] = (uint8_t)tok;
-                out[pos + 1] = (uint8_t)(tok >> 8);
-                out[pos + 2] = (uint8_t)(tok >> 16);
-                const uint32_t q = q0 + pos, wi = q >> 5;
-                if (wi != bm_wi) {
-                    if (bm_w) bm[bm_wi] = bm_w;
-                    bm_wi = wi;
-                    bm_w = 0;
-                }
-                bm_w |= 1u << (q & 31u);
-                pos += len;
             }
-            if (!err && br.bits_consumed() > in_bits) err = kInfErrData;
+            out.drain();
+            br.land();
+            if (!err && (br.spent || br.bits_consumed() > in_bits)) err = kInfErrData;
         }
-        if (bm_w) bm[bm_wi] = bm_w;
         if (!err && pos != isize) err = kInfErrSize;
+        out.finish(area, err == 0);
         if (err) {
             atomicOr(flags, err);
             atomicMin(first_bad, mi);
@@ -414,183 +575,209 @@ __global__ void __launch_bounds__(kDecWarps * 32) inflate_decode_kernel(const ui
 // K_copy
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kCopyWarps = 4;
-constexpr uint32_t kSeg = 1024;
 #ifndef EXON_INF_RING
-#define EXON_INF_RING 4096
+#define EXON_INF_RING 8192
 #endif
-constexpr uint32_t kRingBytes = EXON_INF_RING;
-constexpr uint32_t kRingMask = kRingBytes - 1;
-constexpr int kMaxMatches = 352;  // matches that can start inside one segment (1024 / 3, rounded up)
+constexpr uint32_t kRing = EXON_INF_RING;   // bytes of output a warp keeps in shared memory
+constexpr uint32_t kRingMask = kRing - 1;
+constexpr uint32_t kSpan = kRing / 4;       // most output bytes one group of tokens may produce (one token: <= 513)
+constexpr uint32_t kNear = kRing - kSpan - 64;  // a source at most this far behind the group's first byte is read from the ring
+constexpr uint32_t kFlush = 512;            // finished bytes leave the ring as soon as there are this many
+static_assert(kSpan >= 1024 && kNear >= kFlush + 16 + 128, "ring too small");
 
-struct CopySmem {
-    __align__(16) uint8_t ring[kRingBytes];  // ring[q & kRingMask] = output byte q (q counted from the member's 16-byte aligned origin)
-    uint32_t mtok[kMaxMatches];              // ordered phase: bytes inside the segment | dist << 9; 0 = already copied
-    uint16_t mpos[kMaxMatches];              // match start inside the segment
-};
+__device__ __forceinline__ uint32_t member_token(const uint32_t *tokw, uint32_t last_sector, uint32_t i) {
+    return __ldg(tokw + 8u * (last_sector - (i >> 3)) + (i & 7u));
+}
 
-__global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const BgzfMember *members, int n_members, const uint32_t *bitmap) {
-    __shared__ CopySmem smem_all[kCopyWarps];
-    CopySmem &S = smem_all[threadIdx.x >> 5];
+__global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const BgzfMember *members, int n_members, const uint4 *tokens) {
+    extern __shared__ __align__(16) uint8_t copy_smem_raw[];
+    uint8_t *const ring = copy_smem_raw + (size_t)(threadIdx.x >> 5) * kRing;  // ring[q & kRingMask] = output byte q (q counted from the member's 16-byte aligned origin)
+    const uint32_t *const ringw = reinterpret_cast<const uint32_t *>(ring);
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * kCopyWarps + (threadIdx.x >> 5), nw = gridDim.x * kCopyWarps;
+    constexpr uint32_t kFull = 0xFFFFFFFFu;
 #pragma unroll 1
     for (int mi = gw; mi < n_members; mi += nw) {
         const BgzfMember M = members[mi];
         if (M.isize == 0) continue;
+        const uint4 *area = tokens + M.tok_off;
+        const uint32_t n_tok = __ldg(reinterpret_cast<const uint32_t *>(area));
+        if (n_tok == 0) continue;  // the decoder gave up on this member
+        const uint8_t *lits = reinterpret_cast<const uint8_t *>(area + 2);
+        const uint32_t *tokw = reinterpret_cast<const uint32_t *>(area);
+        const uint32_t last_sector = bgzf_token_units(M.isize) / 2u - 1u;
         const uint32_t q0 = (uint32_t)(M.out_addr & 15u);
         uint8_t *O = reinterpret_cast<uint8_t *>((uintptr_t)(M.out_addr - q0));
-        const uint32_t qend = q0 + M.isize;
-        const uint32_t *bm = bitmap + M.bm_off;
-        const uint32_t nseg = (qend + kSeg - 1) / kSeg;
-        uint32_t carry_len = 0, carry_dist = 0;
+        const uint32_t *Ow = reinterpret_cast<const uint32_t *>(O);
+        uint32_t outq = q0;    // next output position
+        uint32_t flushed = 0;  // everything below has left the ring (a multiple of 16)
+        uint32_t lit_off = 0, ti = 0;
+        uint32_t cur = lane < (int)n_tok ? member_token(tokw, last_sector, (uint32_t)lane) : 0u;
+        uint32_t nxt = 32u + lane < n_tok ? member_token(tokw, last_sector, 32u + lane) : 0u;
+        __syncwarp();
 #pragma unroll 1
-        for (uint32_t s = 0; s < nseg; ++s) {
-            const uint32_t segq = s * kSeg;
-            const uint32_t lq = segq + 32u * (uint32_t)lane;
-            // 1. the segment as K_dec left it (literals final, match ranges hold tokens / garbage)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t uq = lq + 16u * h;
-                if (uq < qend) *reinterpret_cast<uint4 *>(&S.ring[uq & kRingMask]) = __ldcg(reinterpret_cast<const uint4 *>(O + uq));
-            }
-            // 2. match starts of the segment
-            const uint32_t w = lq < qend ? __ldg(bm + (lq >> 5)) : 0u;
-            const int c = __popc(w);
-            int incl = c;
+        while (ti < n_tok) {
+            // ---- positions: one scan of (literals + match bytes) | literals << 16 ----
+            const uint32_t L = cur & 255u, ml = (cur >> 8) & 511u, dist = (cur >> 17) + 1u;
+            const uint32_t v = (L + ml) | (L << 16);
+            uint32_t inc = v;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += o;
+                const uint32_t o = __shfl_up_sync(kFull, inc, d);
+                if (lane >= d) inc += o;
             }
-            const int n_match = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            if (n_match == 0 && carry_len == 0) {
-                __syncwarp();
-                continue;  // literals only: already final in global memory, the ring keeps them as history
+            const int n = __popc(__ballot_sync(kFull, (inc & 0xFFFFu) <= kSpan));  // >= 1; lanes n.. wait for the next group
+            const uint32_t tot = __shfl_sync(kFull, inc, n - 1);
+            const uint32_t gs = tot & 0xFFFFu, gl = tot >> 16;
+            const bool mine = lane < n;
+            const uint32_t exc = inc - v;
+            const uint32_t o = outq + (exc & 0xFFFFu), lo = exc >> 16, ms = o + L;
+            const uint32_t src = ms - dist;
+            const uint32_t ring_lo = outq > kNear ? outq - kNear : 0u;  // <= flushed - 128: everything below is in global memory
+            const bool has = mine && ml != 0u;
+            // a match whose source ends before the group's first byte depends on nothing the group produces; the long ones
+            // go the cooperative way all the same (one lane would spend 64 steps on 258 bytes while 31 wait)
+            const bool indep = has && src + ml <= outq && ml <= 32u;
+            if (has && src < ring_lo) {
+                prefetch_line(O + src);
+                prefetch_line(O + src + ml - 1u);
             }
-            {
-                uint32_t ww = w;
-                int i = incl - c;
-                while (ww) {
-                    S.mpos[i++] = (uint16_t)(32 * lane + __ffs((int)ww) - 1);
-                    ww &= ww - 1u;
-                }
-            }
-            __syncwarp();
-            // 3. tokens, one lane per match; matches whose source ends before the segment are copied right away.
-            // Sources behind the ring come from global memory: their lines are requested for every match of the lane before
-            // the first copy starts, so that the L2 round trips overlap instead of being paid one match after the other.
-            // (Those bytes were written back at least three segments ago, by this warp, with st.cg; the loads below may use
-            // the L1: no line they touch is written again.)
-            const uint32_t ring_lo = segq > (kRingBytes - kSeg) ? segq - (kRingBytes - kSeg) : 0u;
-            if (ring_lo > 0u) {
-                for (int k = lane; k < n_match; k += 32) {
-                    const uint32_t p = S.mpos[k], q = segq + p;
-                    if (p + 2 >= kSeg) continue;
-                    const uint32_t len = (uint32_t)S.ring[q & kRingMask] + 3u;
-                    const uint32_t dist = ((uint32_t)S.ring[(q + 1) & kRingMask] | ((uint32_t)S.ring[(q + 2) & kRingMask] << 8)) + 1u;
-                    const uint32_t src = q - dist;
-                    if (src < ring_lo && dist <= q) {
-                        prefetch_line(O + src);
-                        prefetch_line(O + src + min(len, kSeg - p) - 1u);
-                    }
-                }
-            }
-            uint32_t spill_len = 0, spill_dist = 0;
-            for (int k = lane; k < n_match; k += 32) {
-                const uint32_t p = S.mpos[k], q = segq + p;
-                uint32_t b0, b1, b2;
-                if (p + 2 < kSeg) {
-                    b0 = S.ring[q & kRingMask];
-                    b1 = S.ring[(q + 1) & kRingMask];
-                    b2 = S.ring[(q + 2) & kRingMask];
-                } else {
-                    b0 = __ldcg(O + q);
-                    b1 = __ldcg(O + q + 1);
-                    b2 = __ldcg(O + q + 2);
-                }
-                const uint32_t len = b0 + 3u, dist = (b1 | (b2 << 8)) + 1u;
-                const uint32_t lseg = min(len, kSeg - p);
-                if (len > lseg) {
-                    spill_len = len - lseg;
-                    spill_dist = dist;
-                }
-                const uint32_t src = q - dist;
-                if (src + lseg <= segq) {
-                    for (uint32_t j = 0; j < lseg; ++j) {
-                        const uint32_t sq = src + j;
-                        const uint8_t b = sq >= ring_lo ? S.ring[sq & kRingMask] : O[sq];
-                        S.ring[(q + j) & kRingMask] = b;
-                    }
-                    S.mtok[k] = 0u;
-                } else {
-                    S.mtok[k] = lseg | (dist << 9);
-                }
-            }
-            __syncwarp();
-            // 4. the rest in output order, all lanes on one match
-            if (carry_len) {
-                const uint32_t src = segq - carry_dist;
-                for (uint32_t j = lane; j < carry_len; j += 32) {  // the only ordered copy whose source may lie behind the ring
-                    const uint32_t sq = src + (carry_dist >= carry_len ? j : j % carry_dist);
-                    S.ring[(segq + j) & kRingMask] = sq >= ring_lo ? S.ring[sq & kRingMask] : __ldcg(O + sq);
-                }
-                __syncwarp();
-            }
-            // 32 matches at a time: every lane looks at one, the warp then walks only those that still have to be copied
-#pragma unroll 1
-            for (int k0 = 0; k0 < n_match; k0 += 32) {
-                const int k = k0 + lane;
-                const uint32_t t_l = k < n_match ? S.mtok[k] : 0u, p_l = k < n_match ? (uint32_t)S.mpos[k] : 0u;
-                uint32_t pend = __ballot_sync(0xFFFFFFFFu, t_l != 0u);
-                while (pend) {
-                    const int b = __ffs((int)pend) - 1;
-                    pend &= pend - 1u;
-                    const uint32_t t = __shfl_sync(0xFFFFFFFFu, t_l, b), q = segq + __shfl_sync(0xFFFFFFFFu, p_l, b);
-                    const uint32_t len = t & 511u, dist = t >> 9, src = q - dist;
-                    for (uint32_t j = lane; j < len; j += 32) {
-                        const uint32_t sj = dist >= len ? j : j % dist;
-                        S.ring[(q + j) & kRingMask] = S.ring[(src + sj) & kRingMask];
-                    }
-                    __syncwarp();
-                }
-            }
-            // the spill of this segment's last match, if any (at most one lane has it)
-            const uint32_t sp = __ballot_sync(0xFFFFFFFFu, spill_len != 0u);
-            carry_len = 0;
-            if (sp) {
-                const int owner = __ffs((int)sp) - 1;
-                carry_len = __shfl_sync(0xFFFFFFFFu, spill_len, owner);
-                carry_dist = __shfl_sync(0xFFFFFFFFu, spill_dist, owner);
-            }
-            // 5. the finished segment back to global memory
+            if (gl) prefetch_line(lits + lit_off + 256u);
+            // ---- literals: read in stream order, each byte finds its token by binary search over the literal offsets ----
+            for (uint32_t j0 = 0; j0 < gl; j0 += 32u) {
+                const uint32_t j = j0 + lane;
+                const uint32_t b = j < gl ? __ldg(lits + lit_off + j) : 0u;
+                int t = 0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t uq = lq + 16u * h;
-                if (uq >= qend) continue;
-                if (uq >= q0 && uq + 16u <= qend) {
-                    __stcg(reinterpret_cast<uint4 *>(O + uq), *reinterpret_cast<const uint4 *>(&S.ring[uq & kRingMask]));
-                } else {
-                    const uint32_t a = max(uq, q0), b = min(uq + 16u, qend);
-                    for (uint32_t x = a; x < b; ++x) __stcg(O + x, S.ring[x & kRingMask]);
+                for (int s = 16; s >= 1; s >>= 1) {
+                    const int c = t + s;
+                    const uint32_t lc = __shfl_sync(kFull, lo, c & 31);
+                    if (c < n && lc <= j) t = c;
                 }
+                const uint32_t dst = __shfl_sync(kFull, o, t) + j - __shfl_sync(kFull, lo, t);
+                if (j < gl) ring[dst & kRingMask] = (uint8_t)b;
+            }
+            // ---- independent matches, one lane each; a source behind the ring left for global memory long ago ----
+            // head bytes up to the first aligned destination word, whole words (each one funnel shift of two source words),
+            // tail bytes: half the shared-memory stores of a bytewise copy
+            if (indep) {
+                const bool far = src < ring_lo;  // (then the whole source lies below flushed: ring_lo <= flushed - 128 and ml <= 32)
+                const uint32_t head = min((0u - ms) & 3u, ml);
+                const uint32_t sh = (src & 3u) * 8u;
+                uint32_t wi = src >> 2;
+                uint32_t w0 = far ? Ow[wi] : ringw[wi & (kRingMask >> 2)];
+                uint32_t w1 = far ? Ow[wi + 1u] : ringw[(wi + 1u) & (kRingMask >> 2)];
+                uint32_t x = __funnelshift_r(w0, w1, sh);  // source bytes 0..3
+                for (uint32_t k = 0; k < head; ++k) ring[(ms + k) & kRingMask] = (uint8_t)(x >> (8u * k));
+                // source bytes from `head` on, four at a time: they start (src + head) & 3 bytes into word (src + head) >> 2
+                const uint32_t a0 = src + head, sh2 = (a0 & 3u) * 8u;
+                if ((a0 >> 2) != wi) {
+                    wi = a0 >> 2;
+                    w0 = w1;
+                    w1 = far ? Ow[wi + 1u] : ringw[(wi + 1u) & (kRingMask >> 2)];
+                }
+                const uint32_t body = ml - head;
+                uint32_t dw = ((ms + head) & kRingMask) >> 2;
+                uint32_t k = 0;
+                for (; k + 4u <= body; k += 4u) {
+                    reinterpret_cast<uint32_t *>(ring)[dw] = __funnelshift_r(w0, w1, sh2);
+                    dw = (dw + 1u) & (kRingMask >> 2);
+                    ++wi;
+                    w0 = w1;
+                    w1 = far ? Ow[wi + 1u] : ringw[(wi + 1u) & (kRingMask >> 2)];
+                }
+                x = __funnelshift_r(w0, w1, sh2);
+                for (uint32_t t = 0; k + t < body; ++t) ring[(ms + head + k + t) & kRingMask] = (uint8_t)(x >> (8u * t));
             }
             __syncwarp();
+            // ---- long independent matches, the whole warp on one (rare; the source may lie behind the ring) ----
+            uint32_t lm = __ballot_sync(kFull, has && !indep && src + ml <= outq);
+#pragma unroll 1
+            while (lm) {
+                const int b = __ffs((int)lm) - 1;
+                lm &= lm - 1u;
+                const uint32_t tk = __shfl_sync(kFull, cur, b), m0 = __shfl_sync(kFull, ms, b);
+                const uint32_t len = (tk >> 8) & 511u, s0 = m0 - ((tk >> 17) + 1u);
+                for (uint32_t j = lane; j < len; j += 32u) ring[(m0 + j) & kRingMask] = s0 + j < ring_lo ? O[s0 + j] : ring[(s0 + j) & kRingMask];
+            }
+            __syncwarp();
+            // ---- the others in token order, the whole warp on one match: a chain of matches costs one short step per link.
+            // Their sources reach into the group itself, so they lie in the ring. ----
+            uint32_t dm = __ballot_sync(kFull, has && src + ml > outq);
+            const uint32_t pk = (ms & kRingMask) | (ml << 16);  // what the warp needs of a match, packed by its owner
+            const uint32_t sk = src & kRingMask;
+#pragma unroll 1
+            while (dm) {
+                const int b = __ffs((int)dm) - 1;
+                dm &= dm - 1u;
+                const uint32_t p = __shfl_sync(kFull, pk, b), s0 = __shfl_sync(kFull, sk, b);
+                const uint32_t len = p >> 16, m0 = p & 0xFFFFu, dd = (m0 - s0) & kRingMask;
+                if (len <= 32u && dd >= len) {  // the common case: one step, no overlap
+                    if ((uint32_t)lane < len) ring[(m0 + lane) & kRingMask] = ring[(s0 + lane) & kRingMask];
+                } else if (dd >= 32u) {  // every step's 32 source bytes lie below its 32 destination bytes
+                    for (uint32_t j0 = 0; j0 < len; j0 += 32u) {
+                        const uint32_t j = j0 + lane;
+                        if (j < len) ring[(m0 + j) & kRingMask] = ring[(s0 + j) & kRingMask];
+                        __syncwarp();
+                    }
+                } else {  // the match overlaps itself: its first dd bytes repeat
+                    for (uint32_t j = lane; j < len; j += 32u) ring[(m0 + j) & kRingMask] = ring[(s0 + j % dd) & kRingMask];
+                }
+                __syncwarp();
+            }
+            outq += gs;
+            lit_off += gl;
+            ti += (uint32_t)n;
+            // ---- finished bytes leave the ring ----
+            const bool at_end = ti >= n_tok;
+            if (outq - flushed >= kFlush || at_end) {
+                const uint32_t lim = at_end ? outq : (outq & ~15u);
+                for (uint32_t u = flushed + 16u * (uint32_t)lane; u < lim; u += 512u) {
+                    if (u >= q0 && u + 16u <= lim) {
+                        *reinterpret_cast<uint4 *>(O + u) = *reinterpret_cast<const uint4 *>(&ring[u & kRingMask]);
+                    } else {  // the member's first and last unit are shared with its neighbours
+                        const uint32_t a = max(u, q0), b = min(u + 16u, lim);
+                        for (uint32_t x = a; x < b; ++x) O[x] = ring[x & kRingMask];
+                    }
+                }
+                flushed = lim & ~15u;
+                __syncwarp();
+            }
+            // ---- next tokens ----
+            if (n == 32) {
+                cur = nxt;
+                nxt = ti + 32u + lane < n_tok ? member_token(tokw, last_sector, ti + 32u + lane) : 0u;
+            } else {
+                const int from = lane + n;
+                const uint32_t a = __shfl_sync(kFull, cur, from & 31), b = __shfl_sync(kFull, nxt, from & 31);
+                const uint32_t b2 = ti + 32u + lane < n_tok ? member_token(tokw, last_sector, ti + 32u + lane) : 0u;
+                cur = from < 32 ? a : b;
+                nxt = from < 32 ? b : b2;
+            }
         }
     }
 }
 
 template <int LB, int DB>
-int launch_decode(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_bitmap, uint32_t *d_flags) {
+int launch_decode(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint4 *d_tokens, uint32_t *d_flags) {
     static int occ = 0;
-    constexpr size_t smem = sizeof(LaneTabs<LB, DB>) * kDecWarps * 32;
+    constexpr size_t smem = sizeof(WarpTabs<LB, DB>) * kDecWarps;
     if (!occ) {
         CUDA_TRY(cudaFuncSetAttribute(inflate_decode_kernel<LB, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inflate_decode_kernel<LB, DB>, kDecWarps * 32, smem));
         if (occ < 1) occ = 1;
     }
-    const int per_cta = kDecWarps * 32;
-    const int grid = std::min((n_members + per_cta - 1) / per_cta, occ * c->sm_count);
-    inflate_decode_kernel<LB, DB><<<grid, per_cta, smem, c->stream>>>(d_comp, d_table, n_members, d_bitmap, d_flags, (int *)(d_flags + 1));
+    // one wave when the members fit: spread them over every warp the machine holds (at least 8 lanes per warp)
+    const int max_ctas = occ * c->sm_count, max_warps = max_ctas * kDecWarps;
+    int lpw = std::min(32, std::max(8, (n_members + max_warps - 1) / max_warps));
+    static const int forced_lpw = [] {
+        const char *e = getenv("EXON_GPU_INFLATE_LANES");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced_lpw >= 1 && forced_lpw <= 32) lpw = forced_lpw;
+    const int per_cta = kDecWarps * lpw;
+    const int grid = std::min((n_members + per_cta - 1) / per_cta, max_ctas);
+    inflate_decode_kernel<LB, DB><<<grid, kDecWarps * 32, smem, c->stream>>>(d_comp, d_table, n_members, lpw, d_tokens, d_flags, (int *)(d_flags + 1));
     c->launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return EXON_GPU_OK;
@@ -598,56 +785,65 @@ int launch_decode(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int 
 
 }  // namespace
 
-// Gives every member its place in the match bitmap (1 bit per output byte, counted from the member's 16-byte aligned
-// origin, whole 32-bit words per member); returns the number of words.
-size_t bgzf_assign_bitmap(BgzfMember *m, size_t n) {
-    size_t words = 0;
+// Gives every member its place in the token scratch; returns the number of 16-byte units.
+size_t bgzf_assign_tokens(BgzfMember *m, size_t n) {
+    size_t units = 0;
     for (size_t i = 0; i < n; ++i) {
-        m[i].bm_off = (uint32_t)words;
+        m[i].tok_off = (uint32_t)units;
         m[i].pad_ = 0;
-        if (m[i].isize) words += ((size_t)(m[i].out_addr & 15u) + m[i].isize + 31) / 32;
+        if (m[i].isize) units += bgzf_token_units(m[i].isize);
     }
-    return words;
+    return units;
 }
 
 // Enqueues the inflate of `n_members` members (table in device memory; in_off relative to d_comp, out_addr absolute,
-// bm_off from bgzf_assign_bitmap) on the context's stream.  d_flags: two words of device scratch, {0, INT_MAX} before
-// the launch.
-int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words,
+// tok_off from bgzf_assign_tokens or its device-side equivalent) on the context's stream.  d_flags: two words of device
+// scratch, {0, INT_MAX} before the launch.  d_comp must be 16-byte aligned.
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t token_units,
                         size_t comp_bytes) {
     if (n_members <= 0) return EXON_GPU_OK;
-    const size_t bm_bytes = (bitmap_words + 64) * sizeof(uint32_t);
-    if (bm_bytes > c->inf_bitmap_cap) {
-        if (c->inf_bitmap) {
+    if (token_units > 0xFFFFFFFFull) return fail(EXON_GPU_ERR_UNSUPPORTED, "inflate: more than 48 GiB of output in one launch");
+    const size_t tok_bytes = (token_units + 4) * 16;
+    if (tok_bytes > c->inf_tokens_cap) {
+        if (c->inf_tokens) {
             CUDA_TRY(cudaStreamSynchronize(c->stream));
-            CUDA_TRY(cudaFree(c->inf_bitmap));
-            c->inf_bitmap = nullptr;
-            c->inf_bitmap_cap = 0;
+            CUDA_TRY(cudaFree(c->inf_tokens));
+            c->inf_tokens = nullptr;
+            c->inf_tokens_cap = 0;
         }
-        const size_t cap = bm_bytes + bm_bytes / 4;
-        CUDA_TRY(cudaMalloc(&c->inf_bitmap, cap));
-        c->inf_bitmap_cap = cap;
+        const size_t cap = tok_bytes + tok_bytes / 8;
+        CUDA_TRY(cudaMalloc(&c->inf_tokens, cap));
+        c->inf_tokens_cap = cap;
     }
-    uint32_t *bm = (uint32_t *)c->inf_bitmap;
-    CUDA_TRY(cudaMemsetAsync(bm, 0, bm_bytes, c->stream));
-    // Table size: 9-bit literal tables decode faster (fewer long-code fallbacks, and 2 CTAs per SM leave the L1 to the
-    // input streams) but hold only 128 lanes per SM; 8-bit tables put 320 lanes on an SM.  A launch that fits one wave of
-    // the 9-bit kernel, or that is literal-heavy (compressed > 40 % of the output: BAM), takes the 9-bit tables.
-    // EXON_GPU_INFLATE_TABLES = 87 | 97 forces one.
+    uint4 *tok = (uint4 *)c->inf_tokens;
+    // Table size.  The decoder is bound by the latency of each lane's serial chain, so what counts is warps per SM, and the
+    // tables are what limits them: 7-bit literal / 6-bit distance tables put 16 warps on an SM, 8 / 7 bits 8, 9 / 7 bits 4.
+    // Codes longer than the table take the slow canonical search -- 1.7 % of the symbols of VCF text at 7 bits, 4.4 % of
+    // BAM records (tools/deflate_stats.c).  EXON_GPU_INFLATE_TABLES = 76 | 87 | 97 forces one.
     static const int forced = [] {
         const char *e = getenv("EXON_GPU_INFLATE_TABLES");
         return e ? atoi(e) : 0;
     }();
-    const bool wide9 = forced ? forced == 97 : (n_members <= 2 * c->sm_count * kDecWarps * 32 || (double)comp_bytes > 0.4 * 32.0 * (double)bitmap_words);
-    const int rc = wide9 ? launch_decode<9, 7>(c, d_comp, d_table, n_members, bm, d_flags) : launch_decode<8, 7>(c, d_comp, d_table, n_members, bm, d_flags);
+    const int pick = forced ? forced : 76;
+    (void)comp_bytes;
+    const int rc = pick == 97   ? launch_decode<9, 7>(c, d_comp, d_table, n_members, tok, d_flags)
+                   : pick == 87 ? launch_decode<8, 7>(c, d_comp, d_table, n_members, tok, d_flags)
+                                : launch_decode<7, 6>(c, d_comp, d_table, n_members, tok, d_flags);
     if (rc) return rc;
     static int occ = 0;
+    constexpr size_t copy_smem = (size_t)kCopyWarps * kRing;
     if (!occ) {
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inflate_copy_kernel, kCopyWarps * 32, 0));
+        CUDA_TRY(cudaFuncSetAttribute(inflate_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)copy_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inflate_copy_kernel, kCopyWarps * 32, copy_smem));
         if (occ < 1) occ = 1;
     }
-    const int grid = std::min((n_members + kCopyWarps - 1) / kCopyWarps, occ * c->sm_count);
-    inflate_copy_kernel<<<grid, kCopyWarps * 32, 0, c->stream>>>(d_table, n_members, bm);
+    static const int copy_ctas = [] {  // experiment knob: CTAs per SM (fewer members in flight = more of their history still in the L2)
+        const char *e = getenv("EXON_GPU_INFLATE_COPY_CTAS");
+        return e ? atoi(e) : 0;
+    }();
+    const int ctas_per_sm = copy_ctas > 0 ? std::min(copy_ctas, occ) : occ;
+    const int grid = std::min((n_members + kCopyWarps - 1) / kCopyWarps, ctas_per_sm * c->sm_count);
+    inflate_copy_kernel<<<grid, kCopyWarps * 32, copy_smem, c->stream>>>(d_table, n_members, tok);
     c->launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return EXON_GPU_OK;

@@ -48,7 +48,7 @@ struct Ctx {
         return e;
     }
     std::mutex mu;
-    std::recursive_mutex work_mu;  // serialises users of the context-wide scratch areas (scratch, h_scratch, scratch_b, inf_bitmap); recursive: framing helpers that need it are reached both with and without it held
+    std::recursive_mutex work_mu;  // serialises users of the context-wide scratch areas (scratch, h_scratch, scratch_b, inf_tokens); recursive: framing helpers that need it are reached both with and without it held
     std::vector<DevBlock> free_blocks;
     // scratch for filter_agg / allreduce
     void *scratch = nullptr;
@@ -57,8 +57,8 @@ struct Ctx {
     size_t h_scratch_cap = 0;
     void *scratch_b = nullptr;  // second device scratch area (K2 keeps per-row temporaries here while `scratch` holds tile tables)
     size_t scratch_b_cap = 0;
-    void *inf_bitmap = nullptr;  // inflate.cu: one bit per output byte of the launch in flight (match starts)
-    size_t inf_bitmap_cap = 0;
+    void *inf_tokens = nullptr;  // inflate.cu: literal / token streams of the launch in flight (about 4/3 of its output)
+    size_t inf_tokens_cap = 0;
     // NCCL (dlopen'ed lazily; see nccl.cu)
     void *nccl_comm = nullptr;
     int nccl_ranks = 0;
@@ -98,9 +98,17 @@ struct BgzfMember {
     uint32_t in_len;   // payload bytes
     uint32_t isize;    // uncompressed bytes (gzip trailer)
     uint64_t out_addr; // bgzf_walk: byte offset in the uncompressed stream; at launch: absolute device address of the member's output
-    uint32_t bm_off;   // bgzf_assign_bitmap: first word of the member's match bitmap (inflate.cu)
+    uint32_t tok_off;  // bgzf_assign_tokens: first 16-byte unit of the member's token area (inflate.cu)
     uint32_t pad_;
 };
+
+// 16-byte units of token scratch a member of `isize` output bytes needs (inflate.cu), a whole number of 32-byte sectors: a
+// header sector, the literal bytes and four bytes per token -- a match is worth at least three output bytes, so 4/3 of ISIZE
+// bounds the two together -- plus the padding of the last literal sector and token group.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t bgzf_token_units(uint32_t isize) { return ((isize + isize / 3u + 160u) / 32u + 1u) * 2u; }
 
 // One piece of a run that belongs to a single file (runs are cut at the recorded file ends).
 struct Piece {
@@ -274,8 +282,8 @@ int filter_agg_multi_launch(Ctx *c, const FaBatchDesc *d_descs, int n_batches, i
                             unsigned long long *d_out, bool timed);
 
 int bgzf_walk(const uint8_t *data, size_t len, std::vector<BgzfMember> &out, uint64_t *total_out);
-size_t bgzf_assign_bitmap(BgzfMember *m, size_t n);
-int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t bitmap_words,
+size_t bgzf_assign_tokens(BgzfMember *m, size_t n);
+int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int n_members, uint32_t *d_flags, size_t token_units,
                         size_t comp_bytes);
 
 // defined in bam.cu

@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) mzml_sum_kernel(const SpecDesc *specs, un
 // ---- zlib detour ----------------------------------------------------------------------------------------------------
 // Inflated size of a zlib array: defaultArrayLength x value width, computed in 64 bits and clamped to what DEFLATE can
 // expand `comp` bytes to (at most 1032 : 1) and to 1 GiB.  defaultArrayLength is an untrusted XML attribute: an absurd
-// value must not wrap the int32 size scans (and with them the output and bitmap allocations); a clamped size differs
+// value must not wrap the int32 size scans (and with them the output and token scratch allocations); a clamped size differs
 // from what the stream inflates to, so the array fails the inflate kernels' size check and the query reports it.
 __device__ __forceinline__ uint32_t zarr_isize(uint32_t n_default, bool f32, uint32_t comp) {
     const unsigned long long want = (unsigned long long)n_default * (f32 ? 4ull : 8ull);
@@ -363,7 +363,7 @@ __device__ __forceinline__ uint32_t zarr_isize(uint32_t n_default, bool f32, uin
 struct ZArr {
     uint32_t spec, which;  // which: 0 = m/z, 1 = intensity, 2 = wavelength
 };
-// Z0: the list of zlib arrays + their sizes: [0] compressed bytes (padded), [1] inflated bytes (padded to 16), [2] bitmap words
+// Z0: the list of zlib arrays + their sizes: [0] compressed bytes (padded), [1] inflated bytes (padded to 16), [2] token scratch units
 __global__ void mzml_zlist_kernel(const SpecDesc *specs, unsigned long long n_spec, ZArr *list, unsigned long long *n_list, int32_t *sizes,
                                   unsigned long long cap) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -380,7 +380,7 @@ __global__ void mzml_zlist_kernel(const SpecDesc *specs, unsigned long long n_sp
         const uint32_t isize = zarr_isize(d.n_default, d.f32[which] != 0, comp);
         sizes[k] = (int32_t)((comp + 64u + 15u) & ~15u);
         sizes[cap + 1 + k] = (int32_t)((isize + 15u) & ~15u);
-        sizes[2 * (cap + 1) + k] = (int32_t)((isize + 31u) / 32u);
+        sizes[2 * (cap + 1) + k] = (int32_t)bgzf_token_units(isize);
     }
 }
 
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(256) mzml_b64_kernel(const SpecDesc *specs, co
 // Z3: member table of the inflate kernels + the descriptors' pointers to the inflated values.  RFC 1950: CMF (deflate, window
 // <= 32 KiB), FLG (check bits, no preset dictionary), DEFLATE data, Adler-32.
 __global__ void mzml_ztable_kernel(SpecDesc *specs, const ZArr *list, unsigned long long n_list, const long long *comp_off, const long long *out_off,
-                                   const long long *bm_off, const uint8_t *comp, uint8_t *out, BgzfMember *table, uint32_t *flags) {
+                                   const long long *tok_off, const uint8_t *comp, uint8_t *out, BgzfMember *table, uint32_t *flags) {
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_list) return;
     SpecDesc &d = specs[list[k].spec];
@@ -438,7 +438,7 @@ __global__ void mzml_ztable_kernel(SpecDesc *specs, const ZArr *list, unsigned l
     m.in_len = nbytes >= 6u ? nbytes - 6u : 0u;
     m.isize = isize;
     m.out_addr = (uint64_t)reinterpret_cast<uintptr_t>(out + out_off[k]);
-    m.bm_off = (uint32_t)bm_off[k];
+    m.tok_off = (uint32_t)tok_off[k];
     m.pad_ = 0;
     if (nbytes < 6u || (z[0] & 0x0Fu) != 8u || (z[0] >> 4) > 7u || (((uint32_t)z[0] << 8) | z[1]) % 31u != 0u || (z[1] & 0x20u)) {
         atomicOr(flags, kMzErrZlib);
