@@ -486,48 +486,34 @@ __global__ void __launch_bounds__(kDecWarps * 32, LB == 7 ? 4 : 2) inflate_decod
                 err = kInfErrData;
                 break;
             }
-            // ---- symbols: two per trip, the FIFO topped up once per trip, finished sectors stored every fourth trip ----
+            // ---- symbols: one per round; the FIFO is topped up every second round, finished sectors leave every eighth.
+            // One exit, at the bottom: the lanes of the warp meet again after the literal / match fork of every round. ----
             br.fill();
-            bool eob = false;
-            uint32_t trip = 0;
+            uint32_t round = 0;
 #pragma unroll 1
-            while (!eob && !br.spent) {
-                br.topup();
-                if ((++trip & 3u) == 0u) out.store_if_complete();
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    if (eob) break;
-                    br.refill();  // bp < 32: a literal/length code and its extra bits (<= 20) are there
-                    uint32_t w = br.peek();
-                    uint32_t e = lit[(w & ((1u << LB) - 1u)) * 32];
-                    if (!e) {
-                        const uint32_t r = canon_long<LB>(w, LM.llim, LM.loff, CL);
-                        if (r == 0xFFFFFFFFu) {
-                            err = kInfErrData;
-                            eob = true;
-                            break;
-                        }
-                        e = (litlen_payload(r & 0xFFFFu) << 4) | (r >> 16);
-                    }
-                    const int clen = (int)(e & 15u);
-                    const uint32_t pay = e >> 4;
-                    if (pay < 0x100u) {
-                        br.skip(clen);
-                        if (pos >= isize) {
-                            err = kInfErrData;
-                            eob = true;
-                            break;
-                        }
+            while (true) {
+                if ((round & 1u) == 0u) br.topup();
+                if ((round & 7u) == 7u) out.store_if_complete();
+                ++round;
+                br.refill();  // bp < 32: a literal/length code and its extra bits (<= 20) are there
+                uint32_t w = br.peek();
+                uint32_t e = lit[(w & ((1u << LB) - 1u)) * 32];
+                if (!e) {
+                    const uint32_t r = canon_long<LB>(w, LM.llim, LM.loff, CL);
+                    e = r == 0xFFFFFFFFu ? (0x200u << 4) : (litlen_payload(r & 0xFFFFu) << 4) | (r >> 16);
+                }
+                const int clen = (int)(e & 15u);
+                const uint32_t pay = e >> 4;
+                bool stop = br.spent;
+                if (pay < 0x100u) {
+                    br.skip(clen);
+                    if (pos < isize) {
                         ++pos;
                         out.literal(pay);
-                        continue;
+                    } else {
+                        err = kInfErrData;
                     }
-                    if (!(pay & 0x800u)) {  // end of block, or a symbol that does not exist
-                        br.skip(clen);
-                        if (pay != 0x100u) err = kInfErrData;
-                        eob = true;
-                        break;
-                    }
+                } else if (pay & 0x800u) {
                     // length = 3 + (m << lx) + extra (+ 255 for symbol 285), RFC 1951 3.2.5
                     const uint32_t lx = (pay >> 3) & 7u;
                     const uint32_t len = 3u + ((pay & 7u) << lx) + ((w >> clen) & ((1u << lx) - 1u)) + ((pay >> 6) & 1u) * 255u;
@@ -538,25 +524,24 @@ __global__ void __launch_bounds__(kDecWarps * 32, LB == 7 ? 4 : 2) inflate_decod
                     int dlen = (int)(e & 7u), ds = (int)(e >> 3);
                     if (!e) {
                         const uint32_t r = canon_long<DB>(w, LM.dlim, LM.doff, CD);
-                        if (r == 0xFFFFFFFFu) {
-                            err = kInfErrData;
-                            eob = true;
-                            break;
-                        }
-                        dlen = (int)(r >> 16);
-                        ds = (int)(r & 0xFFFFu);
+                        dlen = r == 0xFFFFFFFFu ? 0 : (int)(r >> 16);
+                        ds = r == 0xFFFFFFFFu ? 30 : (int)(r & 0xFFFFu);
                     }
                     const int dx = (max(ds, 2) - 2) >> 1;
                     const uint32_t dist = 1u + ((uint32_t)(ds < 2 ? ds : 2 + (ds & 1)) << dx) + ((w >> dlen) & ((1u << dx) - 1u));
                     br.skip(dlen + dx);  // <= 15 + 13
-                    if (ds >= 30 || dist > pos || pos + len > isize) {
+                    if (ds < 30 && dist <= pos && pos + len <= isize) {
+                        out.match(len, dist);
+                        pos += len;
+                    } else {
                         err = kInfErrData;
-                        eob = true;
-                        break;
                     }
-                    out.match(len, dist);
-                    pos += len;
+                } else {  // end of block, or a symbol that does not exist
+                    br.skip(clen);
+                    if (pay != 0x100u) err = kInfErrData;
+                    stop = true;
                 }
+                if (stop || err) break;
             }
             out.drain();
             br.land();
@@ -575,21 +560,20 @@ __global__ void __launch_bounds__(kDecWarps * 32, LB == 7 ? 4 : 2) inflate_decod
 // K_copy
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kCopyWarps = 4;
-#ifndef EXON_INF_RING
-#define EXON_INF_RING 8192
-#endif
-constexpr uint32_t kRing = EXON_INF_RING;   // bytes of output a warp keeps in shared memory
-constexpr uint32_t kRingMask = kRing - 1;
-constexpr uint32_t kSpan = kRing / 4;       // most output bytes one group of tokens may produce (one token: <= 513)
-constexpr uint32_t kNear = kRing - kSpan - 64;  // a source at most this far behind the group's first byte is read from the ring
+// kRing: bytes of output a warp keeps in shared memory (8 KiB: 24 warps per SM; 16 KiB: 12, but fewer sources behind the ring)
+// kSpan: most output bytes one group of tokens may produce (one token: <= 513)
+// kNear: a source at most this far behind the group's first byte is read from the ring
+constexpr uint32_t kLaneCopyMax = 32;       // an independent match up to this long is copied by its own lane
 constexpr uint32_t kFlush = 512;            // finished bytes leave the ring as soon as there are this many
-static_assert(kSpan >= 1024 && kNear >= kFlush + 16 + 128, "ring too small");
 
 __device__ __forceinline__ uint32_t member_token(const uint32_t *tokw, uint32_t last_sector, uint32_t i) {
     return __ldg(tokw + 8u * (last_sector - (i >> 3)) + (i & 7u));
 }
 
+template <uint32_t kRing>
 __global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const BgzfMember *members, int n_members, const uint4 *tokens) {
+    constexpr uint32_t kRingMask = kRing - 1, kSpan = kRing / 4, kNear = kRing - kSpan - 64;
+    static_assert(kSpan >= 1024 && kNear >= kFlush + 16 + 128, "ring too small");
     extern __shared__ __align__(16) uint8_t copy_smem_raw[];
     uint8_t *const ring = copy_smem_raw + (size_t)(threadIdx.x >> 5) * kRing;  // ring[q & kRingMask] = output byte q (q counted from the member's 16-byte aligned origin)
     const uint32_t *const ringw = reinterpret_cast<const uint32_t *>(ring);
@@ -637,7 +621,7 @@ __global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const Bgz
             const bool has = mine && ml != 0u;
             // a match whose source ends before the group's first byte depends on nothing the group produces; the long ones
             // go the cooperative way all the same (one lane would spend 64 steps on 258 bytes while 31 wait)
-            const bool indep = has && src + ml <= outq && ml <= 32u;
+            const bool indep = has && src + ml <= outq && ml <= kLaneCopyMax;
             if (has && src < ring_lo) {
                 prefetch_line(O + src);
                 prefetch_line(O + src + ml - 1u);
@@ -659,35 +643,58 @@ __global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const Bgz
             }
             // ---- independent matches, one lane each; a source behind the ring left for global memory long ago ----
             // head bytes up to the first aligned destination word, whole words (each one funnel shift of two source words),
-            // tail bytes: half the shared-memory stores of a bytewise copy
+            // tail bytes: half the shared-memory stores of a bytewise copy.  The first 16 body bytes without a loop.
             if (indep) {
-                const bool far = src < ring_lo;  // (then the whole source lies below flushed: ring_lo <= flushed - 128 and ml <= 32)
+                const bool far = src < ring_lo;  // (then the whole source lies below flushed: ring_lo <= flushed - 128)
                 const uint32_t head = min((0u - ms) & 3u, ml);
-                const uint32_t sh = (src & 3u) * 8u;
                 uint32_t wi = src >> 2;
-                uint32_t w0 = far ? Ow[wi] : ringw[wi & (kRingMask >> 2)];
-                uint32_t w1 = far ? Ow[wi + 1u] : ringw[(wi + 1u) & (kRingMask >> 2)];
-                uint32_t x = __funnelshift_r(w0, w1, sh);  // source bytes 0..3
-                for (uint32_t k = 0; k < head; ++k) ring[(ms + k) & kRingMask] = (uint8_t)(x >> (8u * k));
-                // source bytes from `head` on, four at a time: they start (src + head) & 3 bytes into word (src + head) >> 2
+                uint32_t sw[6];  // the source words the head and the first 16 body bytes can touch
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const bool live = (uint32_t)(4 * i) < (src & 3u) + ml;
+                    sw[i] = !live ? 0u : far ? Ow[wi + i] : ringw[(wi + i) & (kRingMask >> 2)];
+                }
+                const uint32_t sh = (src & 3u) * 8u;
+                const uint32_t x = __funnelshift_r(sw[0], sw[1], sh);  // source bytes 0..3
+                if (head > 0u) ring[ms & kRingMask] = (uint8_t)x;
+                if (head > 1u) ring[(ms + 1u) & kRingMask] = (uint8_t)(x >> 8);
+                if (head > 2u) ring[(ms + 2u) & kRingMask] = (uint8_t)(x >> 16);
+                // from `head` on the destination is word aligned; the source then starts (src + head) & 3 bytes into word
+                // (src + head) >> 2, which is sw[0] or sw[1]
                 const uint32_t a0 = src + head, sh2 = (a0 & 3u) * 8u;
-                if ((a0 >> 2) != wi) {
-                    wi = a0 >> 2;
-                    w0 = w1;
-                    w1 = far ? Ow[wi + 1u] : ringw[(wi + 1u) & (kRingMask >> 2)];
-                }
+                const bool up = (a0 >> 2) != wi;
                 const uint32_t body = ml - head;
-                uint32_t dw = ((ms + head) & kRingMask) >> 2;
-                uint32_t k = 0;
-                for (; k + 4u <= body; k += 4u) {
-                    reinterpret_cast<uint32_t *>(ring)[dw] = __funnelshift_r(w0, w1, sh2);
-                    dw = (dw + 1u) & (kRingMask >> 2);
-                    ++wi;
-                    w0 = w1;
-                    w1 = far ? Ow[wi + 1u] : ringw[(wi + 1u) & (kRingMask >> 2)];
+                uint32_t *dwp = reinterpret_cast<uint32_t *>(ring);
+                const uint32_t dw = (ms + head) >> 2;
+                uint32_t y[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) y[i] = __funnelshift_r(up ? sw[i + 1] : sw[i], up ? sw[i + 2] : sw[i + 1], sh2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t rem = body - min(body, (uint32_t)(4 * i));
+                    const uint32_t d = (ms + head + 4u * i);
+                    if (rem >= 4u) {
+                        dwp[(dw + i) & (kRingMask >> 2)] = y[i];
+                    } else {
+                        if (rem > 0u) ring[d & kRingMask] = (uint8_t)y[i];
+                        if (rem > 1u) ring[(d + 1u) & kRingMask] = (uint8_t)(y[i] >> 8);
+                        if (rem > 2u) ring[(d + 2u) & kRingMask] = (uint8_t)(y[i] >> 16);
+                    }
                 }
-                x = __funnelshift_r(w0, w1, sh2);
-                for (uint32_t t = 0; k + t < body; ++t) ring[(ms + head + k + t) & kRingMask] = (uint8_t)(x >> (8u * t));
+                for (uint32_t k = 16u; k < body; k += 4u) {  // the few matches of 17..32 bytes
+                    const uint32_t w_i = (a0 + k) >> 2;
+                    const uint32_t w0 = far ? Ow[w_i] : ringw[w_i & (kRingMask >> 2)];
+                    const uint32_t w1 = far ? Ow[w_i + 1u] : ringw[(w_i + 1u) & (kRingMask >> 2)];
+                    const uint32_t yy = __funnelshift_r(w0, w1, sh2);
+                    const uint32_t rem = body - k, d = ms + head + k;
+                    if (rem >= 4u) {
+                        dwp[(d >> 2) & (kRingMask >> 2)] = yy;
+                    } else {
+                        ring[d & kRingMask] = (uint8_t)yy;
+                        if (rem > 1u) ring[(d + 1u) & kRingMask] = (uint8_t)(yy >> 8);
+                        if (rem > 2u) ring[(d + 2u) & kRingMask] = (uint8_t)(yy >> 16);
+                    }
+                }
             }
             __syncwarp();
             // ---- long independent matches, the whole warp on one (rare; the source may lie behind the ring) ----
@@ -703,7 +710,8 @@ __global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const Bgz
             __syncwarp();
             // ---- the others in token order, the whole warp on one match: a chain of matches costs one short step per link.
             // Their sources reach into the group itself, so they lie in the ring. ----
-            uint32_t dm = __ballot_sync(kFull, has && src + ml > outq);
+            const bool dep = has && src + ml > outq;
+            uint32_t dm = __ballot_sync(kFull, dep);
             const uint32_t pk = (ms & kRingMask) | (ml << 16);  // what the warp needs of a match, packed by its owner
             const uint32_t sk = src & kRingMask;
 #pragma unroll 1
@@ -783,6 +791,27 @@ int launch_decode(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table, int 
     return EXON_GPU_OK;
 }
 
+template <uint32_t kRing>
+int launch_copy(Ctx *c, const BgzfMember *d_table, int n_members, const uint4 *tok) {
+    static int occ = 0;
+    constexpr size_t copy_smem = (size_t)kCopyWarps * kRing;
+    if (!occ) {
+        CUDA_TRY(cudaFuncSetAttribute(inflate_copy_kernel<kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)copy_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inflate_copy_kernel<kRing>, kCopyWarps * 32, copy_smem));
+        if (occ < 1) occ = 1;
+    }
+    static const int copy_ctas = [] {  // experiment knob: CTAs per SM (fewer members in flight = more of their history still in the L2)
+        const char *e = getenv("EXON_GPU_INFLATE_COPY_CTAS");
+        return e ? atoi(e) : 0;
+    }();
+    const int ctas_per_sm = copy_ctas > 0 ? std::min(copy_ctas, occ) : occ;
+    const int grid = std::min((n_members + kCopyWarps - 1) / kCopyWarps, ctas_per_sm * c->sm_count);
+    inflate_copy_kernel<kRing><<<grid, kCopyWarps * 32, copy_smem, c->stream>>>(d_table, n_members, tok);
+    c->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return EXON_GPU_OK;
+}
+
 }  // namespace
 
 // Gives every member its place in the token scratch; returns the number of 16-byte units.
@@ -830,23 +859,11 @@ int bgzf_inflate_launch(Ctx *c, const uint8_t *d_comp, const BgzfMember *d_table
                    : pick == 87 ? launch_decode<8, 7>(c, d_comp, d_table, n_members, tok, d_flags)
                                 : launch_decode<7, 6>(c, d_comp, d_table, n_members, tok, d_flags);
     if (rc) return rc;
-    static int occ = 0;
-    constexpr size_t copy_smem = (size_t)kCopyWarps * kRing;
-    if (!occ) {
-        CUDA_TRY(cudaFuncSetAttribute(inflate_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)copy_smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inflate_copy_kernel, kCopyWarps * 32, copy_smem));
-        if (occ < 1) occ = 1;
-    }
-    static const int copy_ctas = [] {  // experiment knob: CTAs per SM (fewer members in flight = more of their history still in the L2)
-        const char *e = getenv("EXON_GPU_INFLATE_COPY_CTAS");
-        return e ? atoi(e) : 0;
+    static const int ring_kib = [] {
+        const char *e = getenv("EXON_GPU_INFLATE_RING_KIB");
+        return e ? atoi(e) : 8;
     }();
-    const int ctas_per_sm = copy_ctas > 0 ? std::min(copy_ctas, occ) : occ;
-    const int grid = std::min((n_members + kCopyWarps - 1) / kCopyWarps, ctas_per_sm * c->sm_count);
-    inflate_copy_kernel<<<grid, kCopyWarps * 32, copy_smem, c->stream>>>(d_table, n_members, tok);
-    c->launches.fetch_add(1);
-    CUDA_TRY(cudaGetLastError());
-    return EXON_GPU_OK;
+    return ring_kib == 16 ? launch_copy<16384>(c, d_table, n_members, tok) : launch_copy<8192>(c, d_table, n_members, tok);
 }
 
 }  // namespace exon
