@@ -105,6 +105,9 @@ int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
     if (len)
         if (int rc = bgzf_walk(data, len, members, &total)) return rc;
     uint8_t *dst = nullptr;
+    // a group that would outgrow one wave of decoder lanes goes first: the members beyond the wave would cost a second pass
+    if (!gz_members.empty() && gz_members.size() + members.size() > gz_wave_members())
+        if (int rc = launch_gz()) return rc;
     if (total > 0) {
         const size_t need = ((len + 16 + 255) & ~(size_t)255);
         uint8_t *dz = nullptr;
@@ -131,7 +134,7 @@ int VcfStream::feed_gzip(const uint8_t *data, size_t len, bool is_last) {
     }
     gz_files.push_back(GzFile{dst, total, gz_members.size() - (total > 0 ? members.size() : 0), total > 0 ? members.size() : 0});
     file_open = false;
-    if (gz_members.size() >= 16384) return launch_gz();
+    if (gz_members.size() >= gz_wave_members()) return launch_gz();
     return EXON_GPU_OK;
 }
 
@@ -204,12 +207,17 @@ int VcfStream::feed_gzip_chunk(const uint8_t *data, size_t len, uint64_t file_of
     f.range_lo = (int64_t)u0;
     f.range_hi = (int64_t)end_pos;
     gz_files.push_back(f);
-    if (gz_members.size() >= 16384) return launch_gz();
+    if (gz_members.size() >= gz_wave_members()) return launch_gz();
     return EXON_GPU_OK;
 }
 
 // Staging space for `need` compressed bytes.  When the current buffer is full its group is launched and filling moves to
 // the other buffer -- after the copy stream has been told to wait for the inflate that last read that buffer.
+constexpr size_t kGzStageMax = (size_t)4 << 30;  // a staging buffer stops growing here (two of them exist)
+
+// members one launch of the decoder holds in flight at full occupancy: 12 warps of 32 lanes per SM (inflate.cu, 7/6-bit tables)
+size_t VcfStream::gz_wave_members() const { return (size_t)ctx->sm_count * 384; }
+
 int VcfStream::gz_stage(size_t need, uint8_t **out) {
     if (!gz_copy_stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&gz_copy_stream, cudaStreamNonBlocking));
@@ -217,7 +225,26 @@ int VcfStream::gz_stage(size_t need, uint8_t **out) {
         for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&gz_done_ev[i], cudaEventDisableTiming));
     }
     if (gz_staged + need > d_gz_buf_cap[gz_cur] && gz_staged > 0) {
-        if (int rc = launch_gz()) return rc;  // moves on to the other buffer
+        // The decoder runs one lane per member and every member is a serial chain of the same length, so a launch takes about
+        // as long for 10 000 members as for a full wave of them (inflate.cu): a group is worth launching only when it is a
+        // wave, and until then a full staging buffer grows instead (the staged bytes move with a device copy on the copy
+        // stream; this happens a few times in a stream's life, the buffers are kept).
+        if (gz_members.size() < gz_wave_members() && d_gz_buf_cap[gz_cur] < kGzStageMax) {
+            const size_t cap = std::min(std::max(d_gz_buf_cap[gz_cur] * 2, gz_staged + need), std::max(kGzStageMax, gz_staged + need));
+            void *nb = nullptr;
+            CUDA_TRY(cudaMalloc(&nb, cap));
+            cudaError_t e = cudaMemcpyAsync(nb, d_gz_buf[gz_cur], gz_staged, cudaMemcpyDeviceToDevice, gz_copy_stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(gz_copy_stream);
+            if (e != cudaSuccess) {
+                cudaFree(nb);
+                return fail(EXON_GPU_ERR_CUDA, "feed_gzip: growing the staging buffer: %s", cudaGetErrorString(e));
+            }
+            CUDA_TRY(cudaFree(d_gz_buf[gz_cur]));
+            d_gz_buf[gz_cur] = nb;
+            d_gz_buf_cap[gz_cur] = cap;
+        } else {
+            if (int rc = launch_gz()) return rc;  // moves on to the other buffer
+        }
     }
     if (need > d_gz_buf_cap[gz_cur]) {
         // grow: nothing is staged in this buffer now; an earlier inflate may still be reading it

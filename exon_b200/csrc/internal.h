@@ -209,6 +209,7 @@ struct VcfStream {
         size_t tab_bytes = 0;
     };
     std::vector<GzGroup> gz_inflight;
+    size_t gz_wave_members() const;
     int gz_stage(size_t need, uint8_t **out);  // `need` bytes of staging (launches the pending group / grows the buffer as needed)
     int launch_gz();                           // enqueue the inflate of the pending files; no host synchronisation
     int harvest_gz();                          // wait for every launched group, check it, frame its files in feed order
