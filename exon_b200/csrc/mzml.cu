@@ -515,7 +515,7 @@ int mzml_scan_spectra(VcfStream *s, MzScan *out) {
         CUDA_TRY(exclusive_sum_i32_i64(nullptr, scan_bytes, (const int32_t *)nullptr, (long long *)nullptr, (int)(cap + 1), st));
         const size_t o_segs = 0, o_ev = o_segs + al256(h_segs.size() * sizeof(ScanSeg)), o_ev2 = o_ev + al256(cap * 8), o_sort = o_ev2 + al256(cap * 8),
                      o_flag = o_sort + al256(std::max(sort_bytes, scan_bytes)), o_rank = o_flag + al256((cap + 1) * 4), o_files = o_rank + al256((cap + 1) * 8),
-                     o_out = o_files + al256(file_seg0.size() * 12 + 16);
+                     o_out = o_files + al256(file_seg0.size() * 4) + al256(file_seg0.size() * 8 + 16);  // d_seg0 (u32 per file) | d_f0 (i64 per file), each on its own 256-byte boundary
         if (int rc = ctx->ensure_scratch(o_out + 256, 256 + file_seg0.size() * 8)) return rc;
         uint8_t *scr = (uint8_t *)ctx->scratch;
         unsigned long long *d_out = (unsigned long long *)(scr + o_out);

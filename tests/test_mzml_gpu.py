@@ -79,6 +79,21 @@ def test_synthetic(gpu_ctx, peaks):
         assert n == sh.truth_count and close(s, sh.truth_sum)
 
 
+@pytest.mark.parametrize("n_files", [1, 2, 4, 5, 8, 16, 22, 33])
+def test_file_counts(gpu_ctx, n_files):
+    """Any number of files per stream (a rank's share of a sharded set): 4..21 files used to put the per-file spectrum table on
+    top of the query's result slots."""
+    from synth import mzml
+
+    sh = mzml.shards(40 * n_files, n_files, peaks=31)
+    with gpu_ctx.open_mzml() as st:
+        for f in sh.files:
+            st.feed(f)
+        for _ in range(2):
+            s, n, sp = st.filter_sum(sh.lo, sh.hi)
+            assert sp == sh.n and n == sh.truth_count and close(s, sh.truth_sum), (n_files, n, sh.truth_count)
+
+
 def test_feeds_and_f32(gpu_ctx):
     import base64
     import struct
