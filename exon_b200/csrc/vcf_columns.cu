@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include "vcf_tile.cuh"
+#include "vcf_wide.cuh"
 
 namespace exon {
 
@@ -41,12 +42,14 @@ namespace exon {
 
 namespace {
 
+// What a tile contributes: rows that start in it, CHROM bytes of those rows and, for the wide columns, list entries / bytes of
+// id and filter and the bytes of ref.
 struct TileSum {
-    unsigned long long rows, bytes;
+    unsigned long long rows, bytes, idE, idB, refB, fiE, fiB, pad_;
 };
 struct TileSumAdd {
     __host__ __device__ __forceinline__ TileSum operator()(const TileSum &x, const TileSum &y) const {
-        return TileSum{x.rows + y.rows, x.bytes + y.bytes};
+        return TileSum{x.rows + y.rows, x.bytes + y.bytes, x.idE + y.idE, x.idB + y.idB, x.refB + y.refB, x.fiE + y.fiE, x.fiB + y.fiB, 0ull};
     }
 };
 
@@ -62,6 +65,17 @@ struct ColArgs {
     uint8_t *values;             // pass B out
     uint32_t *flags;
     unsigned long long *first_bad_row;
+    // ---- columns 2..6 inside the same two passes (WIDE instantiations) ----
+    int32_t want_id, want_ref, want_alt, want_qual, want_filter;
+    // pass B out, ABSOLUTE numbering (low 32 bits; pass C turns them into per-batch offsets): first list entry of a row, byte
+    // offset of an entry / of a row's REF
+    uint32_t *id_eabs, *id_vabs, *ref_vabs, *fi_eabs, *fi_vabs;
+    uint8_t *id_val, *ref_val, *fi_val;
+    float *qual;                                              // [row]
+    uint32_t *id_valid_abs, *alt_valid_abs, *qual_valid_abs;  // one bit per absolute row (zeroed before the launch)
+    QualSlow *qual_list;                                      // rows whose QUAL needs the exact parser
+    unsigned long long *qual_list_n;                          // pass A counts them, pass B appends (zeroed in between)
+    unsigned long long qual_list_cap;
 };
 
 // Byte-exact field reader: CHROM = bytes up to the first '\t', non-empty; POS = Rust `usize::from_str` (optional
@@ -144,8 +158,197 @@ __device__ __forceinline__ void line_fields_swar(uint32_t sa, int ls, int want_p
     pos = (long long)((unsigned long long)(q0 * 10000u + q1) * 10000ull + q2);
 }
 
-template <bool EMIT, int U, int S, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_cols_kernel(const __grid_constant__ ColArgs a) {
+// ---- columns 2..6 of one line (LazyVCFArrayBuilder::append, lazy_array_builder.rs:169-216; vcf_wide.cu has the row-parallel
+// twin of this walk).  Readers: RdFast takes bytes straight from the staged tile and gives up at the window's end (the line is
+// then walked again through RdView, which falls back to global memory and knows where the segment ends).
+struct RdFast {
+    uint32_t sa;
+    int lim;
+    bool over;
+    __device__ __forceinline__ uint32_t operator()(int i) {
+        if (i >= lim) {
+            over = true;
+            return '\n';
+        }
+        return lds8(sa + (uint32_t)i);
+    }
+};
+struct RdView {
+    TileView t;
+    __device__ __forceinline__ uint32_t operator()(int i) { return ld_byte(t, i); }
+};
+struct WideRow {
+    int t1, t2, t3, t4, t5, t6;  // tile-relative indices of the tabs that end POS, ID, REF, ALT, QUAL, FILTER
+    int32_t idE, idB, fiE, fiB;  // list entries / bytes (a missing field: 0 / 0)
+    uint32_t rf;                 // 1 id valid | 2 alt valid | 4 qual valid (q holds it) | 8 qual left to the exact parser
+    float q;
+    uint32_t err;
+};
+template <class Rd>
+__device__ __forceinline__ void wide_fields(Rd &rd, int t0, WideRow &R) {
+    R.idE = R.idB = R.fiE = R.fiB = 0;
+    R.rf = 0;
+    R.q = 0.0f;
+    R.err = 0;
+    R.t1 = R.t2 = R.t3 = R.t4 = R.t5 = R.t6 = t0;
+    int i = t0 + 1;
+    uint32_t c;
+    auto field_end = [&](int &semi) -> bool {  // i -> the tab that ends the field; false when the line ends first
+        semi = 0;
+        while ((c = rd(i)) != '\t') {
+            if (c == '\n') return false;
+            semi += c == ';';
+            ++i;
+        }
+        return true;
+    };
+    int semi;
+    if (!field_end(semi)) goto bad;  // POS
+    R.t1 = i;
+    {
+        const int f0 = ++i;
+        if (!field_end(semi)) goto bad;  // ID
+        R.t2 = i;
+        const int n = i - f0;
+        if (!(n == 0 || (n == 1 && rd(f0) == '.'))) {
+            R.rf |= 1u;
+            R.idE = semi + 1;
+            R.idB = n - semi;
+        }
+    }
+    ++i;
+    if (!field_end(semi)) goto bad;  // REF
+    R.t3 = i;
+    {
+        const int f0 = ++i;
+        if (!field_end(semi)) goto bad;  // ALT
+        R.t4 = i;
+        const int n = i - f0;
+        if (!(n == 0 || (n == 1 && rd(f0) == '.'))) R.rf |= 2u;
+    }
+    {
+        const int f0 = ++i;
+        uint32_t v = 0;
+        bool plain = true;
+        while ((c = rd(i)) != '\t') {  // QUAL: the usual one is a short unsigned integer, exact in f32 below 2^24
+            if (c == '\n') goto bad;
+            const uint32_t d = c - '0';
+            plain = plain && d <= 9u;
+            v = v * 10u + d;
+            ++i;
+        }
+        R.t5 = i;
+        const int n = i - f0;
+        if (!(n == 1 && rd(f0) == '.')) {
+            if (plain && n >= 1 && n <= 7) {
+                R.q = (float)v;
+                R.rf |= 4u;
+            } else {
+                R.rf |= 8u;
+            }
+        }
+    }
+    {
+        const int f0 = ++i;
+        if (!field_end(semi)) goto bad;  // FILTER (an 8th field must follow: the tab is required)
+        R.t6 = i;
+        const int n = i - f0;
+        if (!(n == 0 || (n == 1 && rd(f0) == '.'))) {
+            R.fiE = semi + 1;
+            R.fiB = n - semi;
+        }
+    }
+    return;
+bad:
+    R.err = kWErrFields;
+}
+// The same walk for a line whose first 64 bytes are staged (interior tiles, all but the lines that start in the tile's last
+// bytes): separator-class flags ({BS, TAB, LF, VT}, the K1 test) of sixteen unaligned words -> one 64-bit mask -> the first
+// seven separators, each verified to be a tab; the few bytes that need looking at (ID, QUAL digits, FILTER) are read singly.
+// false: anything else (a separator that is not a tab, fewer than seven in reach) -- the caller walks the line byte by byte.
+__device__ __forceinline__ bool wide_fields_swar(uint32_t sa, int ls, int sm_hi, WideRow &R) {
+    const uint32_t la = sa + (uint32_t)ls, a0 = la & ~3u, sh = (la & 3u) << 3;
+    unsigned long long m = 0;
+    uint32_t prev = lds32(a0);
+    // sixteen bytes at a time, and no further than the seventh separator (two rounds for the usual 30-byte record head)
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        if (ls + 16 * (q + 1) + 4 > sm_hi) return false;  // the window would leave the staged bytes
+        uint32_t f[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t next = lds32(a0 + 4u * (uint32_t)(4 * q + k + 1));
+            const uint32_t v = __funnelshift_r(prev, next, sh);
+            f[k] = zero_bytes_exact((v & 0xFCFCFCFCu) ^ 0x08080808u);
+            prev = next;
+        }
+        m |= (unsigned long long)pack16(f[0], f[1], f[2], f[3]) << (16 * q);
+        if (__popcll(m) >= 7) break;
+    }
+    int t[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        if (m == 0ull) return false;
+        t[k] = __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+    }
+    uint32_t all_tabs = 1u;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) all_tabs &= (uint32_t)(lds8(la + (uint32_t)t[k]) == '\t');
+    if (!all_tabs) return false;
+    R.t1 = ls + t[1], R.t2 = ls + t[2], R.t3 = ls + t[3], R.t4 = ls + t[4], R.t5 = ls + t[5], R.t6 = ls + t[6];
+    R.idE = R.idB = R.fiE = R.fiB = 0;
+    R.rf = 0;
+    R.q = 0.0f;
+    R.err = 0;
+    auto list_field = [&](int f0, int f1, int32_t &ne, int32_t &nb) -> bool {  // false: missing
+        const int n = f1 - f0;
+        if (n == 0 || (n == 1 && lds8(la + (uint32_t)f0) == '.')) return false;
+        int semi = 0;
+        for (int i = f0; i < f1; ++i) semi += lds8(la + (uint32_t)i) == ';';
+        ne = semi + 1;
+        nb = n - semi;
+        return true;
+    };
+    if (list_field(t[1] + 1, t[2], R.idE, R.idB)) R.rf |= 1u;
+    {
+        const int n = t[4] - t[3] - 1;
+        if (!(n == 0 || (n == 1 && lds8(la + (uint32_t)(t[3] + 1)) == '.'))) R.rf |= 2u;
+    }
+    {
+        const int f0 = t[4] + 1, n = t[5] - f0;
+        if (!(n == 1 && lds8(la + (uint32_t)f0) == '.')) {
+            uint32_t v = 0;
+            bool plain = n >= 1 && n <= 7;
+            for (int i = 0; plain && i < n; ++i) {
+                const uint32_t d = lds8(la + (uint32_t)(f0 + i)) - '0';
+                plain = d <= 9u;
+                v = v * 10u + d;
+            }
+            if (plain) {
+                R.q = (float)v;
+                R.rf |= 4u;
+            } else {
+                R.rf |= 8u;
+            }
+        }
+    }
+    list_field(t[5] + 1, t[6], R.fiE, R.fiB);
+    return true;
+}
+// items of a list cell [f0, f1): byte offsets of the items (absolute) and the bytes without the ';'
+template <class Rd>
+__device__ __forceinline__ void wide_items(Rd &rd, int f0, int f1, uint32_t *vabs, uint8_t *val, unsigned long long e, unsigned long long v) {
+    vabs[e] = (uint32_t)v;
+    for (int i = f0; i < f1; ++i) {
+        const uint32_t c = rd(i);
+        if (c == ';') vabs[++e] = (uint32_t)v;
+        else val[v++] = (uint8_t)c;
+    }
+}
+
+template <bool EMIT, bool WIDE, int U, int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WIDE ? 2 : ctas_per_sm<U, S, WARPS>()) vcf_cols_kernel(const __grid_constant__ ColArgs a) {
     using L = SmemLayout<U, S, WARPS>;
     constexpr int TILE = L::TILE, STAGE = L::STAGE;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -202,7 +405,7 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_co
     }
     __syncwarp();
 
-    const bool need_fields = EMIT || a.want_chrom;  // pass A of a pos-only projection just counts lines
+    const bool need_fields = EMIT || WIDE || a.want_chrom;  // pass A of a pos-only projection just counts lines
     uint32_t err = 0;
     unsigned long long bad_row = ~0ull;
     uint32_t parity = 0;
@@ -229,6 +432,10 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_co
         unsigned long long t_bytes = 0;  // EMIT: CHROM bytes already placed (warp-uniform); pass A: this lane's partial sum
         uint32_t lane_rows = 0;        // pass A without CHROM: this lane's line count
         int qn = 0;
+        // columns 2..6: EMIT: entries / bytes already placed in this tile (warp-uniform); pass A: this lane's partial sums
+        uint32_t w_idE = 0, w_idB = 0, w_refB = 0, w_fiE = 0, w_fiB = 0;
+        TileSum pre = TileSum{0, 0, 0, 0, 0, 0, 0, 0};
+        if (EMIT && WIDE) pre = a.tile_prefix[T];
 
         auto drain = [&]() {
             __syncwarp();
@@ -248,6 +455,40 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_co
                         clen = (uint32_t)r;
                         e = (uint32_t)(r >> 32);
                     }
+                }
+                WideRow R;
+                uint32_t refB = 0;
+                if (WIDE) {
+                    R.idE = R.idB = R.fiE = R.fiB = 0;
+                    R.rf = 0;
+                    R.q = 0.0f;
+                    R.err = 0;
+                    R.t1 = R.t2 = R.t3 = R.t4 = R.t5 = R.t6 = 0;
+                    if (act && !e) {
+                        const int t0 = ls + (int)clen;
+                        bool done = false;
+                        if (interior) done = wide_fields_swar(sa, ls, sm_hi, R) && R.t1 > t0;
+                        if (!done && interior) {
+                            RdFast rd{sa, sm_hi, false};
+                            wide_fields(rd, t0, R);
+                            done = !rd.over;
+                        }
+                        if (!done) {
+                            RdView rd{TileView{sm, g, seg_lo, hi, sm_lo, sm_hi}};
+                            wide_fields(rd, t0, R);
+                        }
+                        if (R.err) {
+                            R.idE = R.idB = R.fiE = R.fiB = 0;
+                            R.rf = 0;
+                        } else {
+                            refB = (uint32_t)(R.t3 - R.t2 - 1);
+                        }
+                    }
+                    const uint32_t slow_q = __ballot_sync(0xFFFFFFFFu, (R.rf & 8u) != 0u);
+                    if (!EMIT) {
+                        w_idE += (uint32_t)R.idE, w_idB += (uint32_t)R.idB, w_refB += refB, w_fiE += (uint32_t)R.fiE, w_fiB += (uint32_t)R.fiB;
+                        if (slow_q && lane == 0 && a.want_qual) atomicAdd(a.qual_list_n, (unsigned long long)__popc(slow_q));
+                    }  // (a malformed line contributes nothing here and is reported, with its row number, by pass B)
                 }
                 if (EMIT) {
                     uint32_t incl = clen;
@@ -272,6 +513,70 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_co
                         }
                     }
                     t_bytes += total;
+                    if (WIDE) {
+                        uint32_t s_idE = (uint32_t)R.idE, s_idB = (uint32_t)R.idB, s_refB = refB, s_fiE = (uint32_t)R.fiE, s_fiB = (uint32_t)R.fiB;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t v0 = __shfl_up_sync(0xFFFFFFFFu, s_idE, d), v1 = __shfl_up_sync(0xFFFFFFFFu, s_idB, d),
+                                           v2 = __shfl_up_sync(0xFFFFFFFFu, s_refB, d), v3 = __shfl_up_sync(0xFFFFFFFFu, s_fiE, d),
+                                           v4 = __shfl_up_sync(0xFFFFFFFFu, s_fiB, d);
+                            if (lane >= d) s_idE += v0, s_idB += v1, s_refB += v2, s_fiE += v3, s_fiB += v4;
+                        }
+                        const unsigned long long row = row0 + t_rows + (uint32_t)i;
+                        if (act) {
+                            auto emit_cells = [&](auto &rd) {
+                                if (a.want_id) {
+                                    const unsigned long long ea = pre.idE + w_idE + (s_idE - (uint32_t)R.idE), va = pre.idB + w_idB + (s_idB - (uint32_t)R.idB);
+                                    a.id_eabs[row] = (uint32_t)ea;
+                                    if (R.rf & 1u) wide_items(rd, R.t1 + 1, R.t2, a.id_vabs, a.id_val, ea, va);
+                                }
+                                if (a.want_ref) {
+                                    const unsigned long long va = pre.refB + w_refB + (s_refB - refB);
+                                    a.ref_vabs[row] = (uint32_t)va;
+                                    for (uint32_t j = 0; j < refB; ++j) a.ref_val[va + j] = (uint8_t)rd(R.t2 + 1 + (int)j);
+                                }
+                                if (a.want_filter) {
+                                    const unsigned long long ea = pre.fiE + w_fiE + (s_fiE - (uint32_t)R.fiE), va = pre.fiB + w_fiB + (s_fiB - (uint32_t)R.fiB);
+                                    a.fi_eabs[row] = (uint32_t)ea;
+                                    if (R.fiE) wide_items(rd, R.t5 + 1, R.t6, a.fi_vabs, a.fi_val, ea, va);
+                                }
+                            };
+                            if (interior && R.t6 < sm_hi) {  // every byte the cells hold is staged: no range checks
+                                RdFast rd{sa, sm_hi, false};
+                                emit_cells(rd);
+                            } else {
+                                RdView rd{TileView{sm, g, seg_lo, hi, sm_lo, sm_hi}};
+                                emit_cells(rd);
+                            }
+                            if (a.want_qual) {
+                                a.qual[row] = R.q;
+                                if (R.rf & 8u) {
+                                    const unsigned long long k = atomicAdd(a.qual_list_n, 1ull);
+                                    if (k < a.qual_list_cap) a.qual_list[k] = QualSlow{g + R.t4 + 1, (uint32_t)(R.t5 - R.t4 - 1), 0u, row};
+                                }
+                            }
+                            if (R.err) {
+                                atomicOr(a.flags + 1, R.err);
+                                atomicMin(a.first_bad_row, row);
+                            }
+                        }
+                        // validity: the 32 rows of this step are consecutive, so their bits fall into two bitmap words
+                        const unsigned long long rfirst = row0 + t_rows + (uint32_t)i0;
+                        const uint32_t sh = (uint32_t)(rfirst & 31ull);
+                        const unsigned long long wd = rfirst >> 5;
+                        auto put_valid = [&](uint32_t *bm, uint32_t bit) {
+                            const uint32_t m = __ballot_sync(0xFFFFFFFFu, (R.rf & bit) != 0u);
+                            if (lane == 0) {
+                                if (m << sh) atomicOr(bm + wd, m << sh);
+                                if (sh && (m >> (32u - sh))) atomicOr(bm + wd + 1, m >> (32u - sh));
+                            }
+                        };
+                        if (a.want_id) put_valid(a.id_valid_abs, 1u);
+                        if (a.want_alt) put_valid(a.alt_valid_abs, 2u);
+                        if (a.want_qual) put_valid(a.qual_valid_abs, 4u);
+                        w_idE += __shfl_sync(0xFFFFFFFFu, s_idE, 31), w_idB += __shfl_sync(0xFFFFFFFFu, s_idB, 31), w_refB += __shfl_sync(0xFFFFFFFFu, s_refB, 31);
+                        w_fiE += __shfl_sync(0xFFFFFFFFu, s_fiE, 31), w_fiB += __shfl_sync(0xFFFFFFFFu, s_fiB, 31);
+                    }
                 } else {
                     t_bytes += clen;
                 }
@@ -348,7 +653,15 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_co
             unsigned long long bytes = t_bytes;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(0xFFFFFFFFu, bytes, d);
-            if (lane == 0) a.tile_stats[T] = TileSum{rows, bytes};
+            unsigned long long s0 = w_idE, s1 = w_idB, s2 = w_refB, s3 = w_fiE, s4 = w_fiB;
+            if (WIDE) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, d), s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, d), s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, d);
+                    s3 += __shfl_xor_sync(0xFFFFFFFFu, s3, d), s4 += __shfl_xor_sync(0xFFFFFFFFu, s4, d);
+                }
+            }
+            if (lane == 0) a.tile_stats[T] = TileSum{rows, bytes, s0, s1, s2, s3, s4, 0ull};
         }
         __syncwarp();
         if (lane == 0) {
@@ -368,10 +681,10 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_co
 
 constexpr int kColU = 8, kColS = 2, kColW = 8;  // 4 KiB tiles, the geometry K1 settled on
 
-template <bool EMIT>
+template <bool EMIT, bool WIDE>
 cudaError_t launch_cols(const ColArgs &args, int sm_count, cudaStream_t stream) {
     constexpr size_t smem = SmemLayout<kColU, kColS, kColW>::total;
-    auto kern = vcf_cols_kernel<EMIT, kColU, kColS, kColW>;
+    auto kern = vcf_cols_kernel<EMIT, WIDE, kColU, kColS, kColW>;
     static int occ = 0;
     if (!occ) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -429,6 +742,81 @@ __global__ void __launch_bounds__(256) batch_offsets(const long long *batch_row0
         const uint32_t v = r >= n_rows ? (uint32_t)total : off32[r];
         o[i] = (int32_t)(v - base);
     }
+}
+
+// ---- pass C of the wide columns: absolute numbering -> the per-batch layout arrow-rs' builders emit ----
+struct WideAbs {
+    const uint32_t *id_eabs, *id_vabs, *ref_vabs, *fi_eabs, *fi_vabs;
+    unsigned long long tot[5];  // kIdE, kIdB, kRefB, kFiE, kFiB
+    int32_t want_id, want_ref, want_filter;
+};
+// 64-bit entry / byte number of the first row of every batch (and the totals at index n_batches): the tile that holds the
+// row comes from a binary search over the tile prefix, the low 32 bits from the row's absolute offsets
+__global__ void wide_batch_bases(const TileSum *prefix, int64_t n_tiles, const long long *brow, int64_t n_batches, int64_t n_rows, WideAbs w,
+                                 long long *base /* [5][n_batches + 1] */) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_batches) return;
+    const int64_t nb1 = n_batches + 1;
+    const unsigned long long row = (unsigned long long)brow[b];
+    if ((int64_t)row >= n_rows) {
+        for (int k = 0; k < 5; ++k) base[k * nb1 + b] = (long long)w.tot[k];
+        return;
+    }
+    int64_t lo = 0, hi = n_tiles;  // last tile t with prefix[t].rows <= row
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (prefix[mid].rows <= row) lo = mid;
+        else hi = mid;
+    }
+    const TileSum p = prefix[lo];
+    auto widen = [](unsigned long long tile_base, uint32_t low) { return tile_base + (uint32_t)(low - (uint32_t)tile_base); };
+    unsigned long long idE = 0, idB = 0, refB = 0, fiE = 0, fiB = 0;
+    if (w.want_id) {
+        idE = widen(p.idE, w.id_eabs[row]);
+        idB = widen(p.idB, w.id_vabs[idE]);
+    }
+    if (w.want_ref) refB = widen(p.refB, w.ref_vabs[row]);
+    if (w.want_filter) {
+        fiE = widen(p.fiE, w.fi_eabs[row]);
+        fiB = widen(p.fiB, w.fi_vabs[fiE]);
+    }
+    base[0 * nb1 + b] = (long long)idE, base[1 * nb1 + b] = (long long)idB, base[2 * nb1 + b] = (long long)refB, base[3 * nb1 + b] = (long long)fiE,
+                   base[4 * nb1 + b] = (long long)fiB;
+}
+// offsets[b * (batch_rows + 1) + i] = abs[row0(b) + i] - abs[row0(b)], i = 0 .. rows of the batch (abs has n_rows + 1 entries)
+__global__ void __launch_bounds__(256) wide_rebase_rows(const long long *brow, int batch_rows, const uint32_t *abs, int32_t *out) {
+    const int64_t b = blockIdx.x;
+    const long long r0 = brow[b];
+    const int n = (int)(brow[b + 1] - r0);
+    const uint32_t base = abs[r0];
+    int32_t *o = out + b * (int64_t)(batch_rows + 1);
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) o[i] = (int32_t)(abs[r0 + i] - base);
+}
+// child offsets of a batch: entries e0(b) .. e0(b + 1) (inclusive: the closing offset) at out[e0(b) + b ..]
+__global__ void __launch_bounds__(256) wide_rebase_children(const long long *ebase, const uint32_t *vabs, int32_t *out) {
+    const int64_t b = blockIdx.x;
+    const long long e0 = ebase[b], n = ebase[b + 1] - e0;
+    const uint32_t base = vabs[e0];
+    int32_t *o = out + e0 + b;
+    for (long long j = threadIdx.x; j <= n; j += blockDim.x) o[j] = (int32_t)(vabs[e0 + j] - base);
+}
+// validity words of a batch from the one-bit-per-absolute-row bitmap (which has a spare word at its end)
+__global__ void __launch_bounds__(256) wide_repack_valid(const long long *brow, int wpb, const uint32_t *abs_bits, uint32_t *out) {
+    const int64_t b = blockIdx.x;
+    const unsigned long long r0 = (unsigned long long)brow[b];
+    const int n = (int)(brow[b + 1] - (long long)r0);
+    for (int w = threadIdx.x; w < (n + 31) / 32; w += blockDim.x) {
+        const unsigned long long r = r0 + 32ull * (unsigned)w;
+        uint32_t v = __funnelshift_r(abs_bits[r >> 5], abs_bits[(r >> 5) + 1], (uint32_t)(r & 31ull));
+        const int left = n - 32 * w;
+        if (left < 32) v &= (1u << left) - 1u;
+        out[b * (int64_t)wpb + w] = v;
+    }
+}
+__global__ void wide_set_terminals(uint32_t *id_eabs, uint32_t *id_vabs, uint32_t *ref_vabs, uint32_t *fi_eabs, uint32_t *fi_vabs, int64_t n_rows, WideAbs w) {
+    if (w.want_id) id_eabs[n_rows] = (uint32_t)w.tot[0], id_vabs[w.tot[0]] = (uint32_t)w.tot[1];
+    if (w.want_ref) ref_vabs[n_rows] = (uint32_t)w.tot[2];
+    if (w.want_filter) fi_eabs[n_rows] = (uint32_t)w.tot[3], fi_vabs[w.tot[3]] = (uint32_t)w.tot[4];
 }
 
 }  // namespace
@@ -580,8 +968,13 @@ int build_columns(VcfStream *s) {
     std::vector<Piece> pieces;
     s->cut_pieces(pieces);
     if (pieces.empty()) return EXON_GPU_OK;  // zero rows
-    if (!c->want_chrom && !c->want_pos && wide_wanted(c->projection)) {
-        // only columns 2..6: the line index of the wide build also yields the batch table
+    // Columns 2..6 ride in K2's two passes (WIDE instantiations of the tile kernel).  INFO / FORMAT (7, 8) are built row-parallel on
+    // the line index (vcf_wide.cu); when one of them is projected that build takes columns 2..6 along.
+    bool text78 = false;
+    for (int p : s->projection) text78 = text78 || p >= 7;
+    const bool tile_wide = wide_wanted(c->projection) && !text78;
+    if (!c->want_chrom && !c->want_pos && wide_wanted(c->projection) && !tile_wide) {
+        // only columns 2..8: the line index of the wide build also yields the batch table
         int64_t n = -1;
         if (int rc = wide_build(s, &c->batch_row0, &n, &c->wide)) return rc;
         c->n_rows = n;
@@ -615,7 +1008,7 @@ int build_columns(VcfStream *s) {
 
     // ---- scratch A (persists in the context): segs | tile stats | tile prefix | cub temp | gather in/out | misc ----
     size_t cub_bytes = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveScan(nullptr, cub_bytes, (TileSum *)nullptr, (TileSum *)nullptr, TileSumAdd(), TileSum{0, 0},
+    CUDA_TRY(cub::DeviceScan::ExclusiveScan(nullptr, cub_bytes, (TileSum *)nullptr, (TileSum *)nullptr, TileSumAdd(), TileSum{0, 0, 0, 0, 0, 0, 0, 0},
                                             (int)(n_tiles + 1), st));
     const size_t o_segs = 0;
     const size_t o_stats = o_segs + align256(h_segs.size() * sizeof(ScanSeg));
@@ -648,13 +1041,17 @@ int build_columns(VcfStream *s) {
     a.want_pos = c->want_pos;
     a.tile_stats = d_stats;
     a.tile_prefix = d_prefix;
-    a.flags = reinterpret_cast<uint32_t *>(d_misc);
+    a.flags = reinterpret_cast<uint32_t *>(d_misc);  // low word: chrom / pos errors, high word: columns 2..6 (kWErr*)
     a.first_bad_row = d_misc + 1;
+    a.qual_list_n = d_misc + 3;
+    bool want_col[9] = {false, false, false, false, false, false, false, false, false};
+    for (int p : s->projection) want_col[p] = true;
+    if (tile_wide) a.want_id = want_col[2], a.want_ref = want_col[3], a.want_alt = want_col[4], a.want_qual = want_col[5], a.want_filter = want_col[6];
 
     // ---- pass A + scan ----
-    CUDA_TRY(launch_cols<false>(a, ctx->sm_count, st));
+    CUDA_TRY((tile_wide ? launch_cols<false, true>(a, ctx->sm_count, st) : launch_cols<false, false>(a, ctx->sm_count, st)));
     ctx->launches.fetch_add(1);
-    CUDA_TRY(cub::DeviceScan::ExclusiveScan(scr + o_cub, cub_bytes, d_stats, d_prefix, TileSumAdd(), TileSum{0, 0}, (int)(n_tiles + 1), st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveScan(scr + o_cub, cub_bytes, d_stats, d_prefix, TileSumAdd(), TileSum{0, 0, 0, 0, 0, 0, 0, 0}, (int)(n_tiles + 1), st));
     ctx->launches.fetch_add(1);
     gather_prefix<<<(unsigned)((file_tiles.size() + 127) / 128), 128, 0, st>>>(d_prefix, d_gidx, (int)file_tiles.size(), d_gout);
     ctx->launches.fetch_add(1);
@@ -681,14 +1078,33 @@ int build_columns(VcfStream *s) {
         for (long long r = file_row0[f]; r < file_row0[f + 1]; r += c->batch_rows) c->batch_row0.push_back(r);
     c->n_batches = (int64_t)c->batch_row0.size();
     c->batch_row0.push_back(n_rows);
-    if (!c->want_chrom && !c->want_pos) return EXON_GPU_OK;  // empty projection: row counts only
+    if (!c->want_chrom && !c->want_pos && !tile_wide) return EXON_GPU_OK;  // empty projection: row counts only
 
     // ---- outputs + scratch B: absolute u32 offsets | batch_row0 | batch_v0 ----
     const size_t nb1 = (size_t)c->n_batches + 1;
     const size_t ob_off32 = 0;
     const size_t ob_brow = ob_off32 + align256(c->want_chrom ? sizeof(uint32_t) * (size_t)(n_rows + 1) : 0);
     const size_t ob_bv0 = ob_brow + align256(nb1 * sizeof(long long));
-    if (int rc = ctx->ensure_scratch_b(ob_bv0 + align256(nb1 * sizeof(long long)))) return rc;
+    // columns 2..6: absolute offsets per row / per entry (+ 1 closing element each), three one-bit-per-row bitmaps, batch bases, QUAL list
+    const TileSum tot = h_g[n_files_max];
+    unsigned long long h_misc_a[4] = {0, 0, 0, 0};
+    if (tile_wide) {
+        CUDA_TRY(cudaMemcpyAsync(h_misc_a, d_misc, sizeof(h_misc_a), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemsetAsync(d_misc + 3, 0, 8, st));
+    }
+    const unsigned long long n_qslow = h_misc_a[3];
+    const size_t rows1 = (size_t)n_rows + 1, bm_words = ((size_t)n_rows + 31) / 32 + 2;
+    const size_t ow_ide = ob_bv0 + align256(nb1 * sizeof(long long));
+    const size_t ow_idv = ow_ide + align256(tile_wide && want_col[2] ? rows1 * 4 : 0);
+    const size_t ow_ref = ow_idv + align256(tile_wide && want_col[2] ? ((size_t)tot.idE + 1) * 4 : 0);
+    const size_t ow_fie = ow_ref + align256(tile_wide && want_col[3] ? rows1 * 4 : 0);
+    const size_t ow_fiv = ow_fie + align256(tile_wide && want_col[6] ? rows1 * 4 : 0);
+    const size_t ow_bm = ow_fiv + align256(tile_wide && want_col[6] ? ((size_t)tot.fiE + 1) * 4 : 0);
+    const size_t ow_base = ow_bm + align256(tile_wide ? 3 * bm_words * 4 : 0);
+    const size_t ow_ql = ow_base + align256(tile_wide ? 5 * nb1 * 8 : 0);
+    const size_t ow_end = ow_ql + align256((size_t)n_qslow * sizeof(QualSlow));
+    if (int rc = ctx->ensure_scratch_b(ow_end)) return rc;
     uint8_t *scb = (uint8_t *)ctx->scratch_b;
     uint32_t *d_off32 = (uint32_t *)(scb + ob_off32);
     long long *d_brow = (long long *)(scb + ob_brow), *d_bv0 = (long long *)(scb + ob_bv0);
@@ -703,10 +1119,109 @@ int build_columns(VcfStream *s) {
     a.pos = c->d_pos;
     a.off32 = d_off32;
     a.values = c->d_values;
+    if (!c->want_chrom && !c->want_pos) CUDA_TRY(cudaMemcpyAsync(d_brow, c->batch_row0.data(), nb1 * sizeof(long long), cudaMemcpyHostToDevice, st));
+    else if (tile_wide && !c->want_chrom) CUDA_TRY(cudaMemcpyAsync(d_brow, c->batch_row0.data(), nb1 * sizeof(long long), cudaMemcpyHostToDevice, st));
+    WideStore *w = nullptr;
+    uint32_t *bm_abs = reinterpret_cast<uint32_t *>(scb + ow_bm);
+    long long *d_wbase = reinterpret_cast<long long *>(scb + ow_base);
+    auto wide_alloc = [&](WideBuf &b, size_t bytes, bool zero) -> int {
+        b.bytes = std::max<size_t>(bytes, 8);
+        CUDA_TRY(cudaMallocAsync(&b.d, b.bytes, st));
+        if (zero) CUDA_TRY(cudaMemsetAsync(b.d, 0, b.bytes, st));
+        return EXON_GPU_OK;
+    };
+    if (tile_wide) {
+        w = new (std::nothrow) WideStore();
+        if (!w) return fail(EXON_GPU_ERR_OOM, "next_batch: out of host memory");
+        c->wide = w;
+        w->device = ctx->device;
+        w->on_device = s->columns_on_device;
+        w->batch_rows = s->batch_rows;
+        w->wpb = ((s->batch_rows + 63) / 64) * 2;
+        for (int p : s->projection) w->want[p] = true;
+        w->n_rows = n_rows;
+        w->n_batches = c->n_batches;
+        w->batch_row0 = c->batch_row0;
+        const size_t valid_bytes = (size_t)w->n_batches * (size_t)w->wpb * 4, loff_bytes = (size_t)w->n_batches * (size_t)(w->batch_rows + 1) * 4;
+        if (want_col[2]) {
+            if (int rc = wide_alloc(w->id_loff, loff_bytes, false)) return rc;
+            if (int rc = wide_alloc(w->id_coff, ((size_t)tot.idE + nb1) * 4, false)) return rc;
+            if (int rc = wide_alloc(w->id_val, (size_t)tot.idB, false)) return rc;
+            if (int rc = wide_alloc(w->id_valid, valid_bytes, true)) return rc;
+            a.id_eabs = reinterpret_cast<uint32_t *>(scb + ow_ide), a.id_vabs = reinterpret_cast<uint32_t *>(scb + ow_idv);
+            a.id_val = (uint8_t *)w->id_val.d, a.id_valid_abs = bm_abs;
+        }
+        if (want_col[3]) {
+            if (int rc = wide_alloc(w->ref_off, loff_bytes, false)) return rc;
+            if (int rc = wide_alloc(w->ref_val, (size_t)tot.refB, false)) return rc;
+            a.ref_vabs = reinterpret_cast<uint32_t *>(scb + ow_ref), a.ref_val = (uint8_t *)w->ref_val.d;
+        }
+        if (want_col[4]) {
+            if (int rc = wide_alloc(w->alt_valid, valid_bytes, true)) return rc;
+            if (int rc = wide_alloc(w->zeros, (size_t)(w->batch_rows + 1) * 4, true)) return rc;
+            a.alt_valid_abs = bm_abs + bm_words;
+        }
+        if (want_col[5]) {
+            if (int rc = wide_alloc(w->qual, (size_t)n_rows * 4, false)) return rc;
+            if (int rc = wide_alloc(w->qual_valid, valid_bytes, true)) return rc;
+            a.qual = (float *)w->qual.d, a.qual_valid_abs = bm_abs + 2 * bm_words;
+            a.qual_list = reinterpret_cast<QualSlow *>(scb + ow_ql);
+            a.qual_list_cap = n_qslow;
+        }
+        if (want_col[6]) {
+            if (int rc = wide_alloc(w->fi_loff, loff_bytes, false)) return rc;
+            if (int rc = wide_alloc(w->fi_coff, ((size_t)tot.fiE + nb1) * 4, false)) return rc;
+            if (int rc = wide_alloc(w->fi_val, (size_t)tot.fiB, false)) return rc;
+            a.fi_eabs = reinterpret_cast<uint32_t *>(scb + ow_fie), a.fi_vabs = reinterpret_cast<uint32_t *>(scb + ow_fiv);
+            a.fi_val = (uint8_t *)w->fi_val.d;
+        }
+        CUDA_TRY(cudaMemsetAsync(bm_abs, 0, 3 * bm_words * 4, st));
+    }
 
     // ---- pass B (+ C) ----
-    CUDA_TRY(launch_cols<true>(a, ctx->sm_count, st));
+    CUDA_TRY((tile_wide ? launch_cols<true, true>(a, ctx->sm_count, st) : launch_cols<true, false>(a, ctx->sm_count, st)));
     ctx->launches.fetch_add(1);
+    if (tile_wide) {
+        WideAbs wa;
+        wa.id_eabs = a.id_eabs, wa.id_vabs = a.id_vabs, wa.ref_vabs = a.ref_vabs, wa.fi_eabs = a.fi_eabs, wa.fi_vabs = a.fi_vabs;
+        wa.tot[0] = tot.idE, wa.tot[1] = tot.idB, wa.tot[2] = tot.refB, wa.tot[3] = tot.fiE, wa.tot[4] = tot.fiB;
+        wa.want_id = want_col[2], wa.want_ref = want_col[3], wa.want_filter = want_col[6];
+        wide_set_terminals<<<1, 1, 0, st>>>(a.id_eabs, a.id_vabs, a.ref_vabs, a.fi_eabs, a.fi_vabs, n_rows, wa);
+        if (want_col[5] && n_qslow)
+            if (int rc = wide_qual_list(ctx, a.qual_list, n_qslow, a.qual, a.qual_valid_abs, a.flags + 1, a.first_bad_row)) return rc;
+        wide_batch_bases<<<(unsigned)((nb1 + 127) / 128), 128, 0, st>>>(d_prefix, n_tiles, d_brow, c->n_batches, n_rows, wa, d_wbase);
+        const unsigned nbat = (unsigned)c->n_batches;
+        if (want_col[2]) {
+            wide_rebase_rows<<<nbat, 256, 0, st>>>(d_brow, c->batch_rows, a.id_eabs, (int32_t *)w->id_loff.d);
+            wide_rebase_children<<<nbat, 256, 0, st>>>(d_wbase + 0 * nb1, a.id_vabs, (int32_t *)w->id_coff.d);
+            wide_repack_valid<<<nbat, 256, 0, st>>>(d_brow, w->wpb, a.id_valid_abs, (uint32_t *)w->id_valid.d);
+            ctx->launches.fetch_add(3);
+        }
+        if (want_col[3]) {
+            wide_rebase_rows<<<nbat, 256, 0, st>>>(d_brow, c->batch_rows, a.ref_vabs, (int32_t *)w->ref_off.d);
+            ctx->launches.fetch_add(1);
+        }
+        if (want_col[4]) {
+            wide_repack_valid<<<nbat, 256, 0, st>>>(d_brow, w->wpb, a.alt_valid_abs, (uint32_t *)w->alt_valid.d);
+            ctx->launches.fetch_add(1);
+        }
+        if (want_col[5]) {
+            wide_repack_valid<<<nbat, 256, 0, st>>>(d_brow, w->wpb, a.qual_valid_abs, (uint32_t *)w->qual_valid.d);
+            ctx->launches.fetch_add(1);
+        }
+        if (want_col[6]) {
+            wide_rebase_rows<<<nbat, 256, 0, st>>>(d_brow, c->batch_rows, a.fi_eabs, (int32_t *)w->fi_loff.d);
+            wide_rebase_children<<<nbat, 256, 0, st>>>(d_wbase + 3 * nb1, a.fi_vabs, (int32_t *)w->fi_coff.d);
+            ctx->launches.fetch_add(2);
+        }
+        ctx->launches.fetch_add(2);
+        CUDA_TRY(cudaGetLastError());
+        static const int kOf[5] = {kIdE, kIdB, kRefB, kFiE, kFiB};
+        for (int k = 0; k < 5; ++k) {
+            w->base[kOf[k]].resize(nb1);
+            CUDA_TRY(cudaMemcpyAsync(w->base[kOf[k]].data(), d_wbase + (size_t)k * nb1, nb1 * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
     if (c->want_chrom) {
         batch_value_offsets<<<(unsigned)((nb1 + 127) / 128), 128, 0, st>>>(d_prefix, n_tiles, d_brow, c->n_batches, n_rows, total_values,
                                                                           d_off32, d_bv0);
@@ -719,6 +1234,8 @@ int build_columns(VcfStream *s) {
     unsigned long long h_misc[4];
     CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (const uint32_t we = (uint32_t)(h_misc[0] >> 32)) return wide_fail(we, h_misc[1]);
+    if (tile_wide && h_misc[3] != n_qslow) return fail(EXON_GPU_ERR_STATE, "vcf_next_batch: the two passes disagree on the rows with a non-trivial QUAL");
     if ((uint32_t)h_misc[0])
         return fail(EXON_GPU_ERR_PARSE, "malformed VCF record at row %llu:%s%s", h_misc[1],
                     ((uint32_t)h_misc[0] & kErrBadPos) ? " POS is not a positive decimal integer;" : "",
@@ -741,6 +1258,24 @@ int build_columns(VcfStream *s) {
             CUDA_TRY(cudaMemcpyAsync(c->h_values, c->d_values, (size_t)total_values, cudaMemcpyDeviceToHost, st));
         }
         CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    if (tile_wide) {
+        static const int kOf[5] = {kIdE, kIdB, kRefB, kFiE, kFiB};
+        for (int k = 0; k < 5; ++k)
+            for (int64_t b = 0; b < w->n_batches; ++b)
+                if (w->base[kOf[k]][(size_t)b + 1] - w->base[kOf[k]][(size_t)b] > 0x7FFFFFFFll)
+                    return fail(EXON_GPU_ERR_UNSUPPORTED, "vcf_next_batch: batch %lld overflows int32 offsets", (long long)b);
+        if (!w->on_device) {
+            WideBuf *b[WideStore::kBufs];
+            w->all(b);
+            for (int i = 0; i < WideStore::kBufs; ++i) {
+                if (!b[i]->d) continue;
+                CUDA_TRY(cudaHostAlloc(&b[i]->h, b[i]->bytes, cudaHostAllocDefault));
+                CUDA_TRY(cudaMemcpyAsync(b[i]->h, b[i]->d, b[i]->bytes, cudaMemcpyDeviceToHost, st));
+            }
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        return EXON_GPU_OK;
     }
     if (wide_wanted(c->projection)) {
         int64_t n = n_rows;

@@ -29,6 +29,7 @@
 #include "f32_parse.cuh"
 #include "internal.h"
 #include "scan_i64.cuh"
+#include "vcf_wide.cuh"
 
 namespace exon {
 
@@ -41,18 +42,6 @@ namespace exon {
     } while (0)
 
 namespace {
-
-constexpr uint32_t kWErrFields = 1u;       // fewer than 8 tab-separated fields
-constexpr uint32_t kWErrQual = 2u;         // QUAL is not a float literal
-constexpr uint32_t kWErrQualDigits = 4u;   // QUAL has more than 36 significant digits
-constexpr uint32_t kWErrFieldLen = 8u;     // a line of 2 GiB or more
-constexpr uint32_t kWErrInfoValue = 16u;   // INFO: a non-flag key without a value (the reference unwraps a None there)
-constexpr uint32_t kWErrInfoKey = 32u;     // INFO: a key the header does not define
-constexpr uint32_t kWErrInfoForm = 64u;    // INFO: a value noodles cannot parse as its declared type, or a flag with a value
-constexpr uint32_t kWErrFmtValue = 128u;   // FORMAT: a missing sample value ('.'): the reference unwraps a None there
-constexpr uint32_t kWErrFmtForm = 256u;    // FORMAT: a sample value noodles cannot parse as its declared type
-
-enum { kIdE = 0, kIdB = 1, kRefB = 2, kFiE = 3, kFiB = 4, kInfoB = 5, kFmtB = 6, kNScan = 7 };
 
 struct KeyDefs;  // defined with the INFO / FORMAT walks below
 struct KeyDefsPod {  // KeyDefs by value inside the kernel argument
@@ -575,6 +564,23 @@ __global__ void __launch_bounds__(256) vw_qual_kernel(const __grid_constant__ Wi
     }
 }
 
+// The same for the rows the tile-pipeline build (vcf_columns.cu) could not settle: it hands over (row, field) pairs.
+__global__ void __launch_bounds__(256) vw_qual_list_kernel(const QualSlow *list, unsigned long long n_list, float *qual, uint32_t *valid_abs,
+                                                          uint32_t *flags, unsigned long long *first_bad_row) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_list) return;
+    const QualSlow e = list[i];
+    float q = 0.0f;
+    const int rc = e.n > 4096u ? kF32Malformed : parse_f32_rust(e.p, (int)e.n, &q);
+    if (rc == kF32Ok) {
+        qual[e.row] = q;
+        atomicOr(valid_abs + (e.row >> 5), 1u << (e.row & 31ull));
+    } else {
+        atomicOr(flags, rc == kF32Unsupported ? kWErrQualDigits : kWErrQual);
+        atomicMin(first_bad_row, e.row);
+    }
+}
+
 // writes the items of one list cell: child offsets (relative to the batch's first byte) and bytes
 __device__ __forceinline__ void emit_items(const uint8_t *f, int32_t n, int32_t *coff, uint8_t *val, long long v_abs, long long v_rel) {
     int32_t k = 0;
@@ -739,29 +745,24 @@ size_t al256w(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
-struct WideBuf {
-    void *d = nullptr, *h = nullptr;
-    size_t bytes = 0;
-};
+int wide_qual_list(Ctx *ctx, const QualSlow *list, unsigned long long n, float *qual, uint32_t *valid_abs, uint32_t *flags,
+                   unsigned long long *first_bad_row) {
+    if (n == 0) return EXON_GPU_OK;
+    vw_qual_list_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(list, n, qual, valid_abs, flags, first_bad_row);
+    ctx->launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return EXON_GPU_OK;
+}
 
-struct WideStore {
-    int device = 0;
-    bool on_device = false;
-    int batch_rows = 8192, wpb = 256;
-    int64_t n_batches = 0, n_rows = 0;
-    bool want[9] = {false, false, false, false, false, false, false, false, false};
-    WideBuf id_loff, id_coff, id_val, id_valid, ref_off, ref_val, alt_valid, zeros, qual, qual_valid, fi_loff, fi_coff, fi_val, info_off, info_val, info_tab,
-        fmt_off, fmt_val, fmt_tab;
-    std::vector<long long> batch_row0, base[kNScan];  // per batch (+ total): global item / byte offset of the batch's first row
-    static constexpr int kBufs = 19;
-    void all(WideBuf *out[kBufs]) {
-        WideBuf *v[kBufs] = {&id_loff, &id_coff, &id_val, &id_valid, &ref_off, &ref_val, &alt_valid, &zeros, &qual, &qual_valid, &fi_loff, &fi_coff, &fi_val, &info_off, &info_val, &info_tab,
-                             &fmt_off, &fmt_val, &fmt_tab};
-        for (int i = 0; i < kBufs; ++i) out[i] = v[i];
-    }
-    template <class T>
-    const T *p(const WideBuf &b) const { return static_cast<const T *>(on_device ? b.d : b.h); }
-};
+int wide_fail(uint32_t e, unsigned long long row) {
+    return fail((e & ~kWErrQualDigits) ? EXON_GPU_ERR_PARSE : EXON_GPU_ERR_UNSUPPORTED, "VCF record at row %llu:%s%s%s%s%s%s%s%s", row,
+                (e & kWErrFields) ? " fewer than 8 tab-separated fields;" : "", (e & kWErrQual) ? " QUAL is not a float literal;" : "",
+                (e & kWErrQualDigits) ? " QUAL has more than 36 significant digits;" : "", (e & kWErrFieldLen) ? " a line of 2 GiB or more;" : "",
+                (e & kWErrInfoValue) ? " an INFO key that is not a flag has no value (or '.'): the reference's builder unwraps a None there;" : "",
+                (e & kWErrInfoForm) ? " an INFO value that does not parse as its declared type (or a flag with a value);" : "",
+                (e & kWErrFmtValue) ? " a sample value is missing ('.'): the reference's builder unwraps a None there;" : "",
+                (e & kWErrFmtForm) ? " a sample value that does not parse as its declared type;" : "");
+}
 
 void wide_free(WideStore *w) {
     if (!w) return;
@@ -959,14 +960,7 @@ int wide_build(VcfStream *s, std::vector<long long> *batch_row0, int64_t *n_rows
         CUDA_TRY(cudaMemcpyAsync(h_misc, d_misc, sizeof(h_misc), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
-    if (const uint32_t e = (uint32_t)h_misc[0])
-        return fail((e & ~kWErrQualDigits) ? EXON_GPU_ERR_PARSE : EXON_GPU_ERR_UNSUPPORTED, "VCF record at row %llu:%s%s%s%s%s%s%s%s", h_misc[1],
-                    (e & kWErrFields) ? " fewer than 8 tab-separated fields;" : "", (e & kWErrQual) ? " QUAL is not a float literal;" : "",
-                    (e & kWErrQualDigits) ? " QUAL has more than 36 significant digits;" : "", (e & kWErrFieldLen) ? " a line of 2 GiB or more;" : "",
-                    (e & kWErrInfoValue) ? " an INFO key that is not a flag has no value (or '.'): the reference's builder unwraps a None there;" : "",
-                    (e & kWErrInfoForm) ? " an INFO value that does not parse as its declared type (or a flag with a value);" : "",
-                    (e & kWErrFmtValue) ? " a sample value is missing ('.'): the reference's builder unwraps a None there;" : "",
-                    (e & kWErrFmtForm) ? " a sample value that does not parse as its declared type;" : "");
+    if (const uint32_t e = (uint32_t)h_misc[0]) return wide_fail(e, h_misc[1]);
     for (int k = 0; k < kNScan; ++k) {
         if (!need[k]) continue;
         for (int64_t b = 0; b < w->n_batches; ++b)
