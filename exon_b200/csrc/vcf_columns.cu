@@ -262,40 +262,43 @@ __device__ __forceinline__ void wide_fields(Rd &rd, int t0, WideRow &R) {
 bad:
     R.err = kWErrFields;
 }
-// The same walk for a line whose first 64 bytes are staged (interior tiles, all but the lines that start in the tile's last
-// bytes): separator-class flags ({BS, TAB, LF, VT}, the K1 test) of sixteen unaligned words -> one 64-bit mask -> the first
-// seven separators, each verified to be a tab; the few bytes that need looking at (ID, QUAL digits, FILTER) are read singly.
-// false: anything else (a separator that is not a tab, fewer than seven in reach) -- the caller walks the line byte by byte.
-__device__ __forceinline__ bool wide_fields_swar(uint32_t sa, int ls, int sm_hi, WideRow &R) {
-    const uint32_t la = sa + (uint32_t)ls, a0 = la & ~3u, sh = (la & 3u) << 3;
-    unsigned long long m = 0;
-    uint32_t prev = lds32(a0);
-    // sixteen bytes at a time, and no further than the seventh separator (two rounds for the usual 30-byte record head)
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-        if (ls + 16 * (q + 1) + 4 > sm_hi) return false;  // the window would leave the staged bytes
-        uint32_t f[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t next = lds32(a0 + 4u * (uint32_t)(4 * q + k + 1));
-            const uint32_t v = __funnelshift_r(prev, next, sh);
-            f[k] = zero_bytes_exact((v & 0xFCFCFCFCu) ^ 0x08080808u);
-            prev = next;
-        }
-        m |= (unsigned long long)pack16(f[0], f[1], f[2], f[3]) << (16 * q);
-        if (__popcll(m) >= 7) break;
-    }
+// The same walk for the lines of an interior tile, from three BITMAPS of the staged bytes (tab, newline, semicolon: one bit per
+// byte, built once per tile by all lanes, 16 bytes each -- a per-line SWAR window looked at every byte 2.4 times and paid
+// the unaligned fetch per line): 64 bits of each from the line's first byte on, the first seven tabs by find-first-set, the
+// list entries by population counts; single bytes are read only to tell "." from a one-character value and for QUAL.
+// false: the line ends before its eighth field or the seven tabs are not within 64 staged bytes -- the caller walks the line
+// byte by byte (and reports what is wrong with it).
+constexpr int kBmU = 8;                                        // == kColU (asserted at the launch)
+constexpr int kBmChunks = (512 * kBmU + kHalo) / 16;           // 16-byte chunks of the staged tile (kBmU = the kernel's U)
+constexpr int kBmWords = ((kBmChunks + 1) / 2 + 2 + 3) & ~3;   // + two zero words behind the last one (64-bit reads), 16-byte multiple
+constexpr int kBmBytes = 3 * kBmWords * 4;                     // per warp
+__device__ __forceinline__ unsigned long long bits64(uint32_t bm_sa, int bit) {
+    const uint32_t wa = bm_sa + 4u * (uint32_t)(bit >> 5), sh = (uint32_t)bit & 31u;
+    const uint32_t w0 = lds32(wa), w1 = lds32(wa + 4), w2 = lds32(wa + 8);
+    return (unsigned long long)__funnelshift_r(w0, w1, sh) | ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+}
+__device__ __forceinline__ unsigned long long bit_range(int a, int b) {  // bits [a, b), 0 <= a <= b <= 64, b - a < 64
+    return b <= a ? 0ull : ((~0ull >> (64 - (b - a))) << a);
+}
+__device__ __forceinline__ bool wide_fields_bitmap(uint32_t bm_sa, uint32_t sa, int ls, WideRow &R) {
+    const unsigned long long T = bits64(bm_sa, ls), N = bits64(bm_sa + kBmWords * 4, ls), S = bits64(bm_sa + 2 * kBmWords * 4, ls);
+    const int nl = N ? __ffsll((long long)N) - 1 : 64;
+    uint32_t lo = (uint32_t)T, hi = (uint32_t)(T >> 32);
     int t[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-        if (m == 0ull) return false;
-        t[k] = __ffsll((long long)m) - 1;
-        m &= m - 1ull;
+        if (lo) {
+            t[k] = __ffs((int)lo) - 1;
+            lo &= lo - 1u;
+        } else if (hi) {
+            t[k] = 31 + __ffs((int)hi);
+            hi &= hi - 1u;
+        } else {
+            return false;
+        }
     }
-    uint32_t all_tabs = 1u;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) all_tabs &= (uint32_t)(lds8(la + (uint32_t)t[k]) == '\t');
-    if (!all_tabs) return false;
+    if (t[6] >= nl) return false;
+    const uint32_t la = sa + (uint32_t)ls;
     R.t1 = ls + t[1], R.t2 = ls + t[2], R.t3 = ls + t[3], R.t4 = ls + t[4], R.t5 = ls + t[5], R.t6 = ls + t[6];
     R.idE = R.idB = R.fiE = R.fiB = 0;
     R.rf = 0;
@@ -304,8 +307,7 @@ __device__ __forceinline__ bool wide_fields_swar(uint32_t sa, int ls, int sm_hi,
     auto list_field = [&](int f0, int f1, int32_t &ne, int32_t &nb) -> bool {  // false: missing
         const int n = f1 - f0;
         if (n == 0 || (n == 1 && lds8(la + (uint32_t)f0) == '.')) return false;
-        int semi = 0;
-        for (int i = f0; i < f1; ++i) semi += lds8(la + (uint32_t)i) == ';';
+        const int semi = __popcll(S & bit_range(f0, f1));
         ne = semi + 1;
         nb = n - semi;
         return true;
@@ -359,6 +361,7 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE ? 2 : ctas_per_sm<U, S, WARPS
     StageMeta *meta = reinterpret_cast<StageMeta *>(smem_raw + L::meta) + warp * S;
     const uint32_t ring_sa = smem_u32(ring);
     const uint32_t queue_sa = smem_u32(smem_raw + L::queue) + (uint32_t)(warp * kQueue * sizeof(uint16_t));
+    const uint32_t bm_sa = smem_u32(smem_raw + ((L::total + 15) & ~(size_t)15)) + (uint32_t)(warp * kBmBytes);  // WIDE: the warp's three bitmaps
 
     if (lane == 0) {
 #pragma unroll
@@ -422,6 +425,30 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE ? 2 : ctas_per_sm<U, S, WARPS
         const int sm_hi = hi < TILE + kHalo ? ((hi + 15) & ~15) : TILE + kHalo;
         const bool interior = hi >= TILE + kHalo && (lo <= 0);
         const uint32_t sa = ring_sa + (uint32_t)(s * STAGE + kPre);
+        if (WIDE && interior) {
+            // the tile's tab / newline / semicolon bitmaps (halo included): every staged byte is looked at once, by one lane
+            static_assert(U == kBmU, "bitmap sizes are fixed for this U");
+#pragma unroll 1
+            for (int u = 0; u <= U; ++u) {
+                const int ch = u * 32 + lane;
+                if (ch < kBmChunks) {
+                    const uint4 w = lds128(sa + (uint32_t)ch * 16u);
+                    const uint32_t bt = pack16(zero_bytes_exact(w.x ^ 0x09090909u), zero_bytes_exact(w.y ^ 0x09090909u), zero_bytes_exact(w.z ^ 0x09090909u),
+                                               zero_bytes_exact(w.w ^ 0x09090909u));
+                    const uint32_t bn = pack16(zero_bytes_exact(w.x ^ kNL4), zero_bytes_exact(w.y ^ kNL4), zero_bytes_exact(w.z ^ kNL4), zero_bytes_exact(w.w ^ kNL4));
+                    const uint32_t bs = pack16(zero_bytes_exact(w.x ^ 0x3B3B3B3Bu), zero_bytes_exact(w.y ^ 0x3B3B3B3Bu), zero_bytes_exact(w.z ^ 0x3B3B3B3Bu),
+                                               zero_bytes_exact(w.w ^ 0x3B3B3B3Bu));
+                    sts16(bm_sa + 2u * (uint32_t)ch, bt);
+                    sts16(bm_sa + kBmWords * 4 + 2u * (uint32_t)ch, bn);
+                    sts16(bm_sa + 2 * kBmWords * 4 + 2u * (uint32_t)ch, bs);
+                } else if (ch < kBmWords * 2) {
+                    sts16(bm_sa + 2u * (uint32_t)ch, 0u);
+                    sts16(bm_sa + kBmWords * 4 + 2u * (uint32_t)ch, 0u);
+                    sts16(bm_sa + 2 * kBmWords * 4 + 2u * (uint32_t)ch, 0u);
+                }
+            }
+            __syncwarp();
+        }
 
         unsigned long long row0 = 0, vb = 0;
         if (EMIT) {
@@ -467,7 +494,7 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE ? 2 : ctas_per_sm<U, S, WARPS
                     if (act && !e) {
                         const int t0 = ls + (int)clen;
                         bool done = false;
-                        if (interior) done = wide_fields_swar(sa, ls, sm_hi, R) && R.t1 > t0;
+                        if (interior) done = wide_fields_bitmap(bm_sa, sa, ls, R) && R.t1 > t0;
                         if (!done && interior) {
                             RdFast rd{sa, sm_hi, false};
                             wide_fields(rd, t0, R);
@@ -683,7 +710,7 @@ constexpr int kColU = 8, kColS = 2, kColW = 8;  // 4 KiB tiles, the geometry K1 
 
 template <bool EMIT, bool WIDE>
 cudaError_t launch_cols(const ColArgs &args, int sm_count, cudaStream_t stream) {
-    constexpr size_t smem = SmemLayout<kColU, kColS, kColW>::total;
+    constexpr size_t smem = ((SmemLayout<kColU, kColS, kColW>::total + 15) & ~(size_t)15) + (WIDE ? (size_t)kColW * kBmBytes : 0);
     auto kern = vcf_cols_kernel<EMIT, WIDE, kColU, kColS, kColW>;
     static int occ = 0;
     if (!occ) {
