@@ -113,6 +113,36 @@ def test_random_rows(gpu_ctx, seed):
     check(gpu_ctx, files, tuple(rng.sample(range(2, 7), 3)), 8192)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_long_fields_across_tiles(gpu_ctx, seed):
+    """Records whose first seven fields do not fit the 64-byte bitmap window, the 48-byte halo or a 4 KiB tile: long CHROM names, ID
+    lists of hundreds of bytes, REF alleles of several KiB, tabs right at tile edges -- the byte-exact walker and its global-memory
+    fallback, mixed with ordinary short records so that both paths meet in one warp."""
+    rng = random.Random(7000 + seed)
+    rows = []
+    pos = 0
+    for i in range(rng.choice([300, 1500])):
+        pos += rng.randrange(1, 9)
+        kind = rng.random()
+        chrom = rng.choice(["1", "chr1", "scaffold_" + "x" * rng.randrange(1, 80)])
+        if kind < 0.6:
+            ids, ref = rng.choice([".", "rs1", "a;b"]), rng.choice("ACGT")
+        elif kind < 0.8:
+            ids = ";".join("rs%d" % rng.randrange(10 ** 8) for _ in range(rng.randrange(5, 60)))
+            ref = "".join(rng.choice("ACGT") for _ in range(rng.randrange(30, 200)))
+        else:
+            ids = rng.choice([".", ";".join("x%d" % k for k in range(rng.randrange(1, 400)))])
+            ref = "".join(rng.choice("ACGTN") for _ in range(rng.choice([63, 64, 65, 4000, 4096, 4097, 9000])))
+        alt = rng.choice([".", "A", "A,C", "<DEL>"]) * rng.choice([1, 1, 30])
+        qual = rng.choice([".", "7", "1234567", "12345678", "3.25", "1e-3"])
+        flt = rng.choice([".", "PASS", ";".join("f%d" % k for k in range(rng.randrange(1, 50)))])
+        rows.append(f"{chrom}\t{pos}\t{ids}\t{ref}\t{alt}\t{qual}\t{flt}\tDP={i}")
+    text = (HEADER + "\n".join(rows) + "\n").encode()
+    check(gpu_ctx, [text, text], (0, 1, 2, 3, 4, 5, 6), rng.choice([8192, 97]))
+    check(gpu_ctx, [text], (6, 3, 2), 8192)
+    check(gpu_ctx, [text], (5, 4), 8192, gz=True)
+
+
 def test_device_resident_batches(gpu_ctx, index_vcf):
     _, sizes = gpu_rows(gpu_ctx, [index_vcf], (2, 3, 4, 5, 6), 100, on_device=True)
     assert sum(sizes) == 621 and sizes[:-1] == [100] * 6
