@@ -54,6 +54,16 @@ def test_binary_and_degenerate_inputs(gpu_ctx):
         assert gpu_ctx.gzip_inflate(bgzf_compress(c, 6, block=1000)).tobytes() == c  # many tiny members
 
 
+def test_more_members_than_decoder_lanes(gpu_ctx):
+    """One launch holds at most 148 x 12 x 32 = 56 832 members in flight: with more, lanes (and the copy kernel's warps) take
+    several members each; with a handful, the members are spread over warps with few working lanes."""
+    rng = np.random.default_rng(5)
+    text = bytes(rng.integers(0, 6, 6_000_000, dtype=np.uint8) + 97)
+    for block, n in ((80, 6_000_000), (80, 4000), (3000, 200_000)):
+        comp = bgzf_compress(text[:n], 1, block=block)
+        assert gpu_ctx.gzip_inflate(comp).tobytes() == text[:n], (block, n)
+
+
 def test_corrupt_members_fail(gpu_ctx):
     text = make_vcf([("1", str(i + 1)) for i in range(5000)])
     comp = bytearray(bgzf_compress(text))
