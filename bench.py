@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time COUNT(*), interval-only and the column builds")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the FASTQ / BAM / mzML sub-lines (tools/bench_formats.py in subprocesses, N = 1 only, about a minute)")
     return ap.parse_args()
 
 
@@ -406,12 +408,39 @@ def run_b200(args):
     for p in pins:
         p.free()
     ctx.close()
+    if rank == 0 and world == 1 and not args.no_extra_configs and args.rows == 100_000_000:
+        line["extra_configs"] = extra_configs()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def extra_configs():
+    """The other BASELINE configs (FASTQ mean-quality filter, BAM flag / MAPQ per-reference count, mzML m/z filter + SUM), each
+    measured by tools/bench_formats.py in its own process after this one has released the GPU: the compact form of the lines
+    profiles/r2_{fastq_config2,bam_config4,mzml_config5}.json hold in full.  A failure is recorded, never raised."""
+    import subprocess
+
+    out = {}
+    for fmt in ("fastq", "bam", "mzml"):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_formats.py"), fmt, "--steps", "10"], capture_output=True, text=True,
+                               timeout=240, cwd=ROOT)
+            rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode != 0 or not rows:
+                out[fmt] = {"error": (r.stderr or r.stdout)[-300:]}
+                continue
+            d = json.loads(rows[-1])
+            out[fmt] = {"metric": d["metric"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                        "workload": d["config"]["workload"], "e2e": d.get("e2e"), "roofline": d.get("roofline"),
+                        "cpu_baseline": d.get("cpu_baseline"),
+                        "matches_truth": bool(d.get("count_matches_truth", d.get("sum_matches_truth_1e-6", False)))}
+        except Exception as e:  # noqa: BLE001
+            out[fmt] = {"error": repr(e)[:300]}
+    return out
 
 
 def extra_measurements(args, ctx, tstream, timed, dbufs, files, region, n_rows, truth, peak):

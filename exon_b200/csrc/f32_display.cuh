@@ -15,9 +15,9 @@
 #include <string.h>
 
 #ifdef __CUDACC__
-#define EXON_HD __host__ __device__ __forceinline__
+#define EXON_FD_HD __host__ __device__ __forceinline__
 #else
-#define EXON_HD inline
+#define EXON_FD_HD inline
 #endif
 
 namespace exon {
@@ -54,10 +54,10 @@ EXON_F32D_TABLE uint64_t kPow5[47] = {
     0x1d6329f1c35ca4bfull, 0x125dfa371a19e6f7ull, 0x16f578c4e0a060b5ull, 0x1cb2d6f618c878e3ull,
     0x11efc659cf7d4b8dull, 0x166bb7f0435c9e71ull, 0x1c06a5ec5433c60dull};
 
-EXON_HD uint32_t pow5bits(int32_t e) { return (uint32_t)(((uint32_t)e * 1217359u) >> 19) + 1u; }
-EXON_HD uint32_t log10pow2(int32_t e) { return ((uint32_t)e * 78913u) >> 18; }
-EXON_HD uint32_t log10pow5(int32_t e) { return ((uint32_t)e * 732923u) >> 20; }
-EXON_HD uint32_t pow5factor(uint32_t v) {
+EXON_FD_HD uint32_t pow5bits(int32_t e) { return (uint32_t)(((uint32_t)e * 1217359u) >> 19) + 1u; }
+EXON_FD_HD uint32_t log10pow2(int32_t e) { return ((uint32_t)e * 78913u) >> 18; }
+EXON_FD_HD uint32_t log10pow5(int32_t e) { return ((uint32_t)e * 732923u) >> 20; }
+EXON_FD_HD uint32_t pow5factor(uint32_t v) {
     uint32_t c = 0;
     while (v && v % 5u == 0u) {
         v /= 5u;
@@ -65,14 +65,14 @@ EXON_HD uint32_t pow5factor(uint32_t v) {
     }
     return c;
 }
-EXON_HD uint32_t mulshift(uint32_t m, uint64_t factor, int32_t shift) {  // (m * factor) >> shift, shift > 32
+EXON_FD_HD uint32_t mulshift(uint32_t m, uint64_t factor, int32_t shift) {  // (m * factor) >> shift, shift > 32
     const uint64_t b0 = (uint64_t)m * (uint32_t)factor, b1 = (uint64_t)m * (uint32_t)(factor >> 32);
     return (uint32_t)(((b0 >> 32) + b1) >> (shift - 32));
 }
 }  // namespace f32d
 
 // shortest decimal (digits, exponent) with value = digits * 10^exponent for a finite non-zero f32 given as mantissa / exponent fields
-EXON_HD void f32_shortest(uint32_t ieee_m, uint32_t ieee_e, uint32_t *digits, int32_t *exp10) {
+EXON_FD_HD void f32_shortest(uint32_t ieee_m, uint32_t ieee_e, uint32_t *digits, int32_t *exp10) {
     using namespace f32d;
     int32_t e2;
     uint32_t m2;
@@ -163,7 +163,7 @@ EXON_HD void f32_shortest(uint32_t ieee_m, uint32_t ieee_e, uint32_t *digits, in
 }
 
 // `f32::to_string()`: writes at most kF32DisplayMax bytes to out (NULL: only measures), returns the length
-EXON_HD int f32_display(float v, uint8_t *out) {
+EXON_FD_HD int f32_display(float v, uint8_t *out) {
     uint32_t bits;
     memcpy(&bits, &v, 4);
     const bool neg = (bits >> 31) != 0u;
@@ -214,7 +214,7 @@ EXON_HD int f32_display(float v, uint8_t *out) {
 }
 
 // `i32::to_string()`: at most 11 bytes
-EXON_HD int i32_display(int32_t v, uint8_t *out) {
+EXON_FD_HD int i32_display(int32_t v, uint8_t *out) {
     uint8_t d[10];
     int nd = 0, n = 0;
     uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;

@@ -606,7 +606,6 @@ static int mz_build_columns(VcfStream *s) {
         return EXON_GPU_OK;
     }
     const size_t nb1 = (size_t)c->n_batches + 1, nr1 = (size_t)n_rows + 1;
-    const bool need[kSlots] = {want[0], want[4], want[4], want[4], want[4], want[1], want[2], want[3]};
     // temporaries from the stream-ordered pool: counts, prefixes, flags, precursor values, batch tables
     size_t cub_bytes = 0;
     CUDA_TRY(exclusive_sum_i32_i64(nullptr, cub_bytes, (const int32_t *)nullptr, (long long *)nullptr, (int)nr1, st));

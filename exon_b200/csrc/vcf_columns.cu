@@ -1,4 +1,4 @@
-// vcf_columns.cu -- K2: VCF text -> Arrow columns {chrom: utf8, pos: int64} in reference-sized batches.
+// vcf_columns.cu -- K2: VCF text -> Arrow columns {chrom: utf8, pos: int64} (+ columns 2..6) in reference-sized batches.
 //
 // Replaces AsyncBatchStream::read_batch (exon/exon-vcf/src/async_batch_stream.rs:80-109),
 // LazyVCFArrayBuilder::{append, finish} for the projected columns 0 and 1
@@ -15,6 +15,10 @@
 //                bytes at their final place in the values buffer, and the absolute value offset of the row (u32)
 //   C. offsets   per batch: absolute offsets -> int32 offsets that restart at 0 in every batch (the layout
 //                arrow-rs' StringBuilder emits), batch_rows + 1 entries per batch
+// Columns 2..6 (id, ref, alt, qual, filter; lazy_array_builder.rs:169-216) ride in the same two passes (WIDE instantiations of the
+// kernel): per-tile sums of their list entries / bytes in pass A, ranks inside a tile from warp scans in pass B, values at
+// their final place plus absolute 32-bit offsets, and an element-wise pass C per batch for the layout arrow-rs emits; the
+// per-line field positions come from tab / newline / semicolon bitmaps built once per tile (wide_fields_bitmap below).
 // A row belongs to the tile that holds the '\n' before it (the first row of a segment to the segment's first
 // tile), exactly as in K1.  Segments are cut at file ends, so no batch spans two files (the reference opens one
 // AsyncBatchStream per file).  Batches own nothing: they are views into the stream's column store, kept alive by

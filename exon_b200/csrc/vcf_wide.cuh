@@ -14,7 +14,7 @@ constexpr uint32_t kWErrQual = 2u;         // QUAL is not a float literal
 constexpr uint32_t kWErrQualDigits = 4u;   // QUAL has more than 36 significant digits
 constexpr uint32_t kWErrFieldLen = 8u;     // a line of 2 GiB or more
 constexpr uint32_t kWErrInfoValue = 16u;   // INFO: a non-flag key without a value (the reference unwraps a None there)
-constexpr uint32_t kWErrInfoKey = 32u;     // INFO: a key the header does not define
+constexpr uint32_t kWErrInfoKey = 32u;     // INFO: a key the header does not define (reserved: such keys fall back to noodles' tables)
 constexpr uint32_t kWErrInfoForm = 64u;    // INFO: a value noodles cannot parse as its declared type, or a flag with a value
 constexpr uint32_t kWErrFmtValue = 128u;   // FORMAT: a missing sample value ('.'): the reference unwraps a None there
 constexpr uint32_t kWErrFmtForm = 256u;    // FORMAT: a sample value noodles cannot parse as its declared type
