@@ -567,7 +567,8 @@ constexpr uint32_t kLaneCopyMax = 32;       // an independent match up to this l
 constexpr uint32_t kFlush = 512;            // finished bytes leave the ring as soon as there are this many
 
 __device__ __forceinline__ uint32_t member_token(const uint32_t *tokw, uint32_t last_sector, uint32_t i) {
-    return __ldg(tokw + 8u * (last_sector - (i >> 3)) + (i & 7u));
+    // read once, 128 bytes per warp instruction: evict-first, so that the L2 is left to the output the far sources come from
+    return __ldcs(tokw + 8u * (last_sector - (i >> 3)) + (i & 7u));
 }
 
 template <uint32_t kRing>
