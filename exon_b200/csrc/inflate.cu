@@ -599,6 +599,7 @@ __global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const Bgz
         uint32_t lit_off = 0, ti = 0;
         uint32_t cur = lane < (int)n_tok ? member_token(tokw, last_sector, (uint32_t)lane) : 0u;
         uint32_t nxt = 32u + lane < n_tok ? member_token(tokw, last_sector, 32u + lane) : 0u;
+        uint32_t nx2 = 64u + lane < n_tok ? member_token(tokw, last_sector, 64u + lane) : 0u;  // two groups ahead: a loaded DRAM round trip outlasts one group
         __syncwarp();
 #pragma unroll 1
         while (ti < n_tok) {
@@ -753,15 +754,19 @@ __global__ void __launch_bounds__(kCopyWarps * 32) inflate_copy_kernel(const Bgz
                 __syncwarp();
             }
             // ---- next tokens ----
-            if (n == 32) {
-                cur = nxt;
-                nxt = ti + 32u + lane < n_tok ? member_token(tokw, last_sector, ti + 32u + lane) : 0u;
-            } else {
-                const int from = lane + n;
-                const uint32_t a = __shfl_sync(kFull, cur, from & 31), b = __shfl_sync(kFull, nxt, from & 31);
-                const uint32_t b2 = ti + 32u + lane < n_tok ? member_token(tokw, last_sector, ti + 32u + lane) : 0u;
-                cur = from < 32 ? a : b;
-                nxt = from < 32 ? b : b2;
+            {
+                const uint32_t fresh = ti + 64u + lane < n_tok ? member_token(tokw, last_sector, ti + 64u + lane) : 0u;
+                if (n == 32) {
+                    cur = nxt;
+                    nxt = nx2;
+                    nx2 = fresh;
+                } else {
+                    const int from = lane + n;
+                    const uint32_t x = __shfl_sync(kFull, cur, from & 31), y = __shfl_sync(kFull, nxt, from & 31), z = __shfl_sync(kFull, nx2, from & 31);
+                    cur = from < 32 ? x : y;
+                    nxt = from < 32 ? y : z;
+                    nx2 = from < 32 ? z : fresh;
+                }
             }
         }
     }
