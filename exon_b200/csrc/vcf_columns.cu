@@ -27,6 +27,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <type_traits>
 #include <new>
 
 #include "common.cuh"
@@ -56,14 +57,21 @@ struct TileSumAdd {
         return TileSum{x.rows + y.rows, x.bytes + y.bytes, x.idE + y.idE, x.idB + y.idB, x.refB + y.refB, x.fiE + y.fiE, x.fiB + y.fiB, 0ull};
     }
 };
+// the two fields a projection of chrom / pos alone needs (a quarter of the scan's traffic)
+struct TileSum2 {
+    unsigned long long rows, bytes;
+};
+struct TileSum2Add {
+    __host__ __device__ __forceinline__ TileSum2 operator()(const TileSum2 &x, const TileSum2 &y) const { return TileSum2{x.rows + y.rows, x.bytes + y.bytes}; }
+};
 
 struct ColArgs {
     const ScanSeg *segs;  // n_segs + 1 entries (sentinel carries tile0 = n_tiles)
     int32_t n_segs;
     int64_t n_tiles;
     int32_t want_chrom, want_pos;
-    TileSum *tile_stats;         // pass A out, one per tile
-    const TileSum *tile_prefix;  // pass B in: exclusive prefix of tile_stats
+    void *tile_stats;         // pass A out, one per tile: TileSum (WIDE) or TileSum2
+    const void *tile_prefix;  // pass B in: exclusive prefix of tile_stats
     int64_t *pos;                // pass B out
     uint32_t *off32;             // pass B out: low 32 bits of the row's absolute offset into `values`
     uint8_t *values;             // pass B out
@@ -456,8 +464,9 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE ? 2 : ctas_per_sm<U, S, WARPS
 
         unsigned long long row0 = 0, vb = 0;
         if (EMIT) {
-            row0 = __ldg(&a.tile_prefix[T].rows);
-            vb = __ldg(&a.tile_prefix[T].bytes);
+            using TS = typename std::conditional<WIDE, TileSum, TileSum2>::type;
+            row0 = __ldg(&static_cast<const TS *>(a.tile_prefix)[T].rows);
+            vb = __ldg(&static_cast<const TS *>(a.tile_prefix)[T].bytes);
         }
         uint32_t t_rows = 0;           // rows of this tile already drained (warp-uniform)
         unsigned long long t_bytes = 0;  // EMIT: CHROM bytes already placed (warp-uniform); pass A: this lane's partial sum
@@ -466,7 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE ? 2 : ctas_per_sm<U, S, WARPS
         // columns 2..6: EMIT: entries / bytes already placed in this tile (warp-uniform); pass A: this lane's partial sums
         uint32_t w_idE = 0, w_idB = 0, w_refB = 0, w_fiE = 0, w_fiB = 0;
         TileSum pre = TileSum{0, 0, 0, 0, 0, 0, 0, 0};
-        if (EMIT && WIDE) pre = a.tile_prefix[T];
+        if (EMIT && WIDE) pre = static_cast<const TileSum *>(a.tile_prefix)[T];
 
         auto drain = [&]() {
             __syncwarp();
@@ -692,7 +701,10 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE ? 2 : ctas_per_sm<U, S, WARPS
                     s3 += __shfl_xor_sync(0xFFFFFFFFu, s3, d), s4 += __shfl_xor_sync(0xFFFFFFFFu, s4, d);
                 }
             }
-            if (lane == 0) a.tile_stats[T] = TileSum{rows, bytes, s0, s1, s2, s3, s4, 0ull};
+            if (lane == 0) {
+                if (WIDE) static_cast<TileSum *>(a.tile_stats)[T] = TileSum{rows, bytes, s0, s1, s2, s3, s4, 0ull};
+                else static_cast<TileSum2 *>(a.tile_stats)[T] = TileSum2{rows, bytes};
+            }
         }
         __syncwarp();
         if (lane == 0) {
@@ -733,14 +745,16 @@ cudaError_t launch_cols(const ColArgs &args, int sm_count, cudaStream_t stream) 
 }
 
 // out[i] = prefix[idx[i]]
-__global__ void gather_prefix(const TileSum *prefix, const long long *idx, int n, TileSum *out) {
+template <class TS>
+__global__ void gather_prefix(const TS *prefix, const long long *idx, int n, TS *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = prefix[idx[i]];
 }
 
 // Full 64-bit value offset of the first row of every batch (and the grand total at index n_batches): the tile
 // that holds the row is found by binary search over the tile prefix; the row's u32 offset supplies the low bits.
-__global__ void batch_value_offsets(const TileSum *prefix, int64_t n_tiles, const long long *batch_row0, int64_t n_batches,
+template <class TS>
+__global__ void batch_value_offsets(const TS *prefix, int64_t n_tiles, const long long *batch_row0, int64_t n_batches,
                                     int64_t n_rows, unsigned long long total, const uint32_t *off32, long long *batch_v0) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b > n_batches) return;
@@ -1038,9 +1052,11 @@ int build_columns(VcfStream *s) {
     const int n_files_max = (int)file_tiles.size() - 1;
 
     // ---- scratch A (persists in the context): segs | tile stats | tile prefix | cub temp | gather in/out | misc ----
-    size_t cub_bytes = 0;
+    size_t cub_bytes = 0, cub_bytes2 = 0;
     CUDA_TRY(cub::DeviceScan::ExclusiveScan(nullptr, cub_bytes, (TileSum *)nullptr, (TileSum *)nullptr, TileSumAdd(), TileSum{0, 0, 0, 0, 0, 0, 0, 0},
                                             (int)(n_tiles + 1), st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveScan(nullptr, cub_bytes2, (TileSum2 *)nullptr, (TileSum2 *)nullptr, TileSum2Add(), TileSum2{0, 0}, (int)(n_tiles + 1), st));
+    cub_bytes = std::max(cub_bytes, cub_bytes2);
     const size_t o_segs = 0;
     const size_t o_stats = o_segs + align256(h_segs.size() * sizeof(ScanSeg));
     const size_t o_prefix = o_stats + align256((size_t)(n_tiles + 1) * sizeof(TileSum));
@@ -1059,7 +1075,8 @@ int build_columns(VcfStream *s) {
 
     CUDA_TRY(cudaMemcpyAsync(d_segs, h_segs.data(), h_segs.size() * sizeof(ScanSeg), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_gidx, file_tiles.data(), file_tiles.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(d_stats + n_tiles, 0, sizeof(TileSum), st));
+    const size_t ts_bytes = tile_wide ? sizeof(TileSum) : sizeof(TileSum2);  // element of the stats / prefix / gather arrays
+    CUDA_TRY(cudaMemsetAsync(reinterpret_cast<uint8_t *>(d_stats) + (size_t)n_tiles * ts_bytes, 0, ts_bytes, st));
     const unsigned long long init_misc[4] = {0ull, ~0ull, 0ull, 0ull};
     CUDA_TRY(cudaMemcpyAsync(d_misc, init_misc, sizeof(init_misc), cudaMemcpyHostToDevice, st));
 
@@ -1082,14 +1099,29 @@ int build_columns(VcfStream *s) {
     // ---- pass A + scan ----
     CUDA_TRY((tile_wide ? launch_cols<false, true>(a, ctx->sm_count, st) : launch_cols<false, false>(a, ctx->sm_count, st)));
     ctx->launches.fetch_add(1);
-    CUDA_TRY(cub::DeviceScan::ExclusiveScan(scr + o_cub, cub_bytes, d_stats, d_prefix, TileSumAdd(), TileSum{0, 0, 0, 0, 0, 0, 0, 0}, (int)(n_tiles + 1), st));
-    ctx->launches.fetch_add(1);
-    gather_prefix<<<(unsigned)((file_tiles.size() + 127) / 128), 128, 0, st>>>(d_prefix, d_gidx, (int)file_tiles.size(), d_gout);
-    ctx->launches.fetch_add(1);
+    if (tile_wide) {
+        CUDA_TRY(cub::DeviceScan::ExclusiveScan(scr + o_cub, cub_bytes, d_stats, d_prefix, TileSumAdd(), TileSum{0, 0, 0, 0, 0, 0, 0, 0}, (int)(n_tiles + 1), st));
+        gather_prefix<TileSum><<<(unsigned)((file_tiles.size() + 127) / 128), 128, 0, st>>>(d_prefix, d_gidx, (int)file_tiles.size(), d_gout);
+    } else {
+        CUDA_TRY(cub::DeviceScan::ExclusiveScan(scr + o_cub, cub_bytes, reinterpret_cast<TileSum2 *>(d_stats), reinterpret_cast<TileSum2 *>(d_prefix), TileSum2Add(),
+                                                TileSum2{0, 0}, (int)(n_tiles + 1), st));
+        gather_prefix<TileSum2><<<(unsigned)((file_tiles.size() + 127) / 128), 128, 0, st>>>(reinterpret_cast<const TileSum2 *>(d_prefix), d_gidx, (int)file_tiles.size(),
+                                                                                           reinterpret_cast<TileSum2 *>(d_gout));
+    }
+    ctx->launches.fetch_add(2);
     CUDA_TRY(cudaGetLastError());
-    TileSum *h_g = (TileSum *)ctx->h_scratch;
-    CUDA_TRY(cudaMemcpyAsync(h_g, d_gout, file_tiles.size() * sizeof(TileSum), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_scratch, d_gout, file_tiles.size() * ts_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<TileSum> h_gv(file_tiles.size());
+    for (size_t f = 0; f < file_tiles.size(); ++f) {
+        if (tile_wide) {
+            h_gv[f] = static_cast<const TileSum *>(ctx->h_scratch)[f];
+        } else {
+            const TileSum2 t2 = static_cast<const TileSum2 *>(ctx->h_scratch)[f];
+            h_gv[f] = TileSum{t2.rows, t2.bytes, 0, 0, 0, 0, 0, 0};
+        }
+    }
+    const TileSum *h_g = h_gv.data();
     const int64_t n_rows = (int64_t)h_g[n_files_max].rows;
     const unsigned long long total_values = h_g[n_files_max].bytes;
     c->n_rows = n_rows;
@@ -1254,8 +1286,11 @@ int build_columns(VcfStream *s) {
         }
     }
     if (c->want_chrom) {
-        batch_value_offsets<<<(unsigned)((nb1 + 127) / 128), 128, 0, st>>>(d_prefix, n_tiles, d_brow, c->n_batches, n_rows, total_values,
-                                                                          d_off32, d_bv0);
+        if (tile_wide)
+            batch_value_offsets<TileSum><<<(unsigned)((nb1 + 127) / 128), 128, 0, st>>>(d_prefix, n_tiles, d_brow, c->n_batches, n_rows, total_values, d_off32, d_bv0);
+        else
+            batch_value_offsets<TileSum2><<<(unsigned)((nb1 + 127) / 128), 128, 0, st>>>(reinterpret_cast<const TileSum2 *>(d_prefix), n_tiles, d_brow, c->n_batches,
+                                                                                        n_rows, total_values, d_off32, d_bv0);
         batch_offsets<<<(unsigned)c->n_batches, 256, 0, st>>>(d_brow, d_bv0, n_rows, total_values, c->batch_rows, d_off32, c->d_offsets);
         ctx->launches.fetch_add(2);
         CUDA_TRY(cudaGetLastError());
