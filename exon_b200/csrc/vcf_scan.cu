@@ -213,15 +213,20 @@ struct LineConsts {
 // than 12 digits, anything malformed.  Not LAZY (strict streams, or no chrom literal): CHROM must be non-empty and POS a
 // positive decimal on EVERY line (what the reference's builder checks while it fills the columns,
 // lazy_array_builder.rs:157-168); LAZY: only a line whose CHROM matches is looked at.
-template <bool LAZY>
+// NW = 6: the 24-byte window; NW = 4: the first 16 bytes only (CHROM, POS and both tabs of an ordinary record fit: "chr10",
+// nine digits) -- two loads, two shifts and a third of the digit flags less; a line it cannot settle is given to NW = 6.
+template <bool LAZY, int NW>
 __device__ __forceinline__ uint32_t line_swar(uint32_t sa, int ls, const LineConsts &K, const Konst &C, bool &slow) {
     const uint32_t la = sa + (uint32_t)ls;  // address of the line's first byte
     const uint32_t a0 = la & ~3u;
     const uint32_t sh = (la & 3u) << 3;     // tile byte 0 is 16-byte aligned
-    const uint32_t w0 = lds32(a0), w1 = lds32(a0 + 4), w2 = lds32(a0 + 8), w3 = lds32(a0 + 12), w4 = lds32(a0 + 16),
-                   w5 = lds32(a0 + 20), w6 = lds32(a0 + 24);
+    const uint32_t w0 = lds32(a0), w1 = lds32(a0 + 4), w2 = lds32(a0 + 8), w3 = lds32(a0 + 12), w4 = lds32(a0 + 16);
+    uint32_t w5 = 0, w6 = 0;
+    if (NW == 6) w5 = lds32(a0 + 20), w6 = lds32(a0 + 24);
     const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh),
-                   v3 = __funnelshift_r(w3, w4, sh), v4 = __funnelshift_r(w4, w5, sh), v5 = __funnelshift_r(w5, w6, sh);
+                   v3 = __funnelshift_r(w3, w4, sh);
+    uint32_t v4 = 0, v5 = 0;
+    if (NW == 6) v4 = __funnelshift_r(w4, w5, sh), v5 = __funnelshift_r(w5, w6, sh);
     const bool chrom_ok = lop3<0xFE>(lop3<0x28>(v0, K.P[0], K.M[0]), lop3<0x28>(v1, K.P[1], K.M[1]), lop3<0x28>(v2, K.P[2], K.M[2])) == 0;
     if (LAZY && !chrom_ok) return 0;
     if (LAZY && !K.has_interval) return 1;
@@ -240,13 +245,17 @@ __device__ __forceinline__ uint32_t line_swar(uint32_t sa, int ls, const LineCon
         p0 = s1 + 1;
     }
     // non-digit flags of the whole window; the first one at or after p0 ends POS
-    const uint32_t d0 = v0 ^ C.c30, d1 = v1 ^ C.c30, d2 = v2 ^ C.c30, d3 = v3 ^ C.c30, d4 = v4 ^ C.c30, d5 = v5 ^ C.c30;
+    const uint32_t d0 = v0 ^ C.c30, d1 = v1 ^ C.c30, d2 = v2 ^ C.c30, d3 = v3 ^ C.c30;
     const uint32_t n0 = lop3<0xA8>(fma_add(d0, C.c76, C.one), d0, C.c80), n1 = lop3<0xA8>(fma_add(d1, C.c76, C.one), d1, C.c80),
-                   n2 = lop3<0xA8>(fma_add(d2, C.c76, C.one), d2, C.c80), n3 = lop3<0xA8>(fma_add(d3, C.c76, C.one), d3, C.c80),
-                   n4 = lop3<0xA8>(fma_add(d4, C.c76, C.one), d4, C.c80), n5 = lop3<0xA8>(fma_add(d5, C.c76, C.one), d5, C.c80);
-    uint32_t nh = __dp4a(n4, 0x08040201u, 0u);
-    nh = __dp4a(n5, 0x80402010u, nh);                             // bits 7..14 for bytes 16..23
-    const uint32_t nm = nh * 65536u + pack16_7(n0, n1, n2, n3);   // bit 7 + i: byte i is not a digit
+                   n2 = lop3<0xA8>(fma_add(d2, C.c76, C.one), d2, C.c80), n3 = lop3<0xA8>(fma_add(d3, C.c76, C.one), d3, C.c80);
+    uint32_t nm = pack16_7(n0, n1, n2, n3);                       // bit 7 + i: byte i is not a digit
+    if (NW == 6) {
+        const uint32_t d4 = v4 ^ C.c30, d5 = v5 ^ C.c30;
+        const uint32_t n4 = lop3<0xA8>(fma_add(d4, C.c76, C.one), d4, C.c80), n5 = lop3<0xA8>(fma_add(d5, C.c76, C.one), d5, C.c80);
+        uint32_t nh = __dp4a(n4, 0x08040201u, 0u);
+        nh = __dp4a(n5, 0x80402010u, nh);                         // bits 7..14 for bytes 16..23
+        nm = nh * 65536u + nm;
+    }
     const uint32_t nd = nm >> (7 + p0);
     const int n = __ffs(nd) - 1;                                  // digits of POS (-1: none in reach)
     const uint32_t c_end = lds8(la + (uint32_t)(p0 + n)), c_first = lds8(la + (uint32_t)p0);
@@ -566,7 +575,15 @@ __global__ void __launch_bounds__(WARPS * 32, ctas_per_sm<U, S, WARPS>()) vcf_sc
             for (int i = lane; i < qn; i += 32) {
                 const int ls = (int)lds16(queue_sa + 2u * (uint32_t)i);
                 bool slow = EDGE && ls + kWindow > hi;  // the window would leave the segment
-                if (!slow) cnt += line_swar<LAZY>(sa, ls, K, C, slow);
+                if (!slow) {
+                    if (LAZY) {
+                        cnt += line_swar<LAZY, 6>(sa, ls, K, C, slow);
+                    } else {
+                        bool wider = false;
+                        cnt += line_swar<LAZY, 4>(sa, ls, K, C, wider);
+                        if (wider) cnt += line_swar<LAZY, 6>(sa, ls, K, C, slow);
+                    }
+                }
                 if (slow) {
                     const unsigned long long r = line_exact<LAZY>(sm, g, seg_lo, hi, sm_lo, sm_hi, ls, &a);
                     cnt += (uint32_t)r;
